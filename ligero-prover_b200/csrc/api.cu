@@ -1,0 +1,602 @@
+// C ABI (include/lgr.h) over the sm_100a kernels: context, twiddle tables, NTT plans, pipelines.
+// Host-side counterpart of src/webgpu/engine.cpp + src/webgpu/device_context.cpp of the reference
+// (pipeline / bind-group creation and per-op command submission) re-done for one CUDA stream.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lgr.h"
+#include "host_fr.h"
+#include "kernels.h"
+
+using namespace lgr;
+using host::Fr;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(e__ == cudaErrorMemoryAllocation ? LGR_ERR_NOMEM : LGR_ERR_CUDA,                 \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                            \
+    } while (0)
+#define REQUIRE(cond, msg) do { if (!(cond)) return fail(LGR_ERR_INVALID, msg); } while (0)
+
+namespace {
+
+struct DevTable {
+    fr_mem *d = nullptr;
+    size_t count = 0;
+};
+
+struct NttPlan {
+    int logn = 0;
+    bool inverse = false;
+    int l1 = 0, l2 = 0;          // four-step split (l1 + l2 = logn) or l1 = logn, l2 = 0
+    DevTable tw1, tw2;           // sub-transform twiddles
+    DevTable twist_lo, twist_hi;
+    int twist_shift = 0;
+    DevTable scale;              // N^-1 * R for inverse transforms
+};
+
+struct PlanKey {
+    int logn; bool inverse; uint64_t w[4];
+    bool operator<(const PlanKey &o) const {
+        if (logn != o.logn) return logn < o.logn;
+        if (inverse != o.inverse) return inverse < o.inverse;
+        return memcmp(w, o.w, 32) < 0;
+    }
+};
+
+}  // namespace
+
+struct lgr_ctx {
+    int device = 0;
+    uint32_t l = 0, k = 0, n = 0;
+    int logk = 0;
+    Fr root_k, root_2k, root_n;
+    cudaStream_t own_stream = nullptr, stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_enc[2] = {nullptr, nullptr}, ev_hash[2] = {nullptr, nullptr}, ev_join = nullptr, ev_fork = nullptr;
+    uint64_t launches = 0;
+    std::map<PlanKey, NttPlan> plans;
+    std::vector<void *> owned;              // tables etc.
+    EncodeTables enc{};                      // fused encoder tables (k <= 2048)
+    bool enc_ready = false;
+    fr_mem *scratch = nullptr; size_t scratch_elems = 0;
+    fr_mem *tile[2] = {nullptr, nullptr}; size_t tile_elems = 0;
+    uint32_t *commit_sha = nullptr;
+    void *staging = nullptr; size_t staging_bytes = 0;      // pinned host staging for lgr_write
+    cudaEvent_t ev_staging = nullptr;
+    uint32_t *sample_idx = nullptr; uint32_t sample_count = 0;
+};
+
+static int upload(lgr_ctx *c, const std::vector<Fr> &v, DevTable &t) {
+    t.count = v.size();
+    if (v.empty()) { t.d = nullptr; return LGR_OK; }
+    CU(cudaMalloc((void **)&t.d, v.size() * 32));
+    c->owned.push_back(t.d);
+    CU(cudaMemcpy(t.d, v.data(), v.size() * 32, cudaMemcpyHostToDevice));
+    return LGR_OK;
+}
+
+static int ensure_scratch(lgr_ctx *c, size_t elems) {
+    if (c->scratch_elems >= elems) return LGR_OK;
+    if (c->scratch) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->scratch)); c->scratch = nullptr; c->scratch_elems = 0; }
+    CU(cudaMalloc((void **)&c->scratch, elems * 32));
+    c->scratch_elems = elems;
+    return LGR_OK;
+}
+
+// ---- NTT plans ---------------------------------------------------------------------------------
+static int get_plan(lgr_ctx *c, int logn, const Fr &omega, bool inverse, NttPlan **out) {
+    PlanKey key{logn, inverse, {omega.v[0], omega.v[1], omega.v[2], omega.v[3]}};
+    auto it = c->plans.find(key);
+    if (it != c->plans.end()) { *out = &it->second; return LGR_OK; }
+    REQUIRE(logn >= 1 && logn <= 2 * ntt_tile_max_logm(), "transform size out of range (2 .. 2^22 points)");
+    // omega must have order exactly 2^logn
+    {
+        Fr t = omega;
+        for (int i = 0; i < logn - 1; i++) t = host::mul(t, t);
+        Fr minus1; const uint64_t one[4] = {1, 0, 0, 0}; host::sub4(minus1.v, host::kP, one);
+        REQUIRE(host::is_canonical(omega) && t == minus1, "omega is not a primitive 2^logn-th root of unity");
+    }
+    NttPlan p;
+    p.logn = logn; p.inverse = inverse;
+    const Fr w = inverse ? host::inv(omega) : omega;
+    const size_t N = (size_t)1 << logn;
+    int rc;
+    if (logn <= ntt_tile_max_logm()) {
+        p.l1 = logn; p.l2 = 0;
+        if ((rc = upload(c, host::power_table_mont(w, N / 2), p.tw1))) return rc;
+    } else {
+        p.l2 = logn / 2; p.l1 = logn - p.l2;
+        const size_t N1 = (size_t)1 << p.l1, N2 = (size_t)1 << p.l2;
+        if ((rc = upload(c, host::power_table_mont(host::pow(w, N2), N1 / 2), p.tw1))) return rc;   // w_N1 = w^N2
+        if ((rc = upload(c, host::power_table_mont(host::pow(w, N1), N2 / 2), p.tw2))) return rc;   // w_N2 = w^N1
+        p.twist_shift = (logn + 1) / 2;
+        const size_t lo = (size_t)1 << p.twist_shift, hi = N >> p.twist_shift;
+        if ((rc = upload(c, host::power_table_mont(w, lo), p.twist_lo))) return rc;
+        if ((rc = upload(c, host::power_table_mont(host::pow(w, lo), hi), p.twist_hi))) return rc;
+    }
+    if (inverse) {
+        std::vector<Fr> s(1, host::to_mont(host::inv(host::from_u64(N))));
+        if ((rc = upload(c, s, p.scale))) return rc;
+    }
+    auto ins = c->plans.emplace(key, p);
+    *out = &ins.first->second;
+    return LGR_OK;
+}
+
+// a CTA owns up to 2048 elements (64 KiB of shared memory) and 256 threads
+static int lanes_per_cta(int logm) {
+    const int M = 1 << logm;
+    int C = std::max(1, 2048 / M);
+    const int TL = M >= 8 ? M / 8 : 1;
+    if (C * TL > 256) C = 256 / TL;
+    return std::max(C, 1);
+}
+
+// batch transforms of 2^logn points; transform b starts at buf + b*batch_stride (elements)
+static int run_ntt(lgr_ctx *c, fr_mem *buf, NttPlan &p, uint32_t batch, size_t batch_stride) {
+    if (batch == 0) return LGR_OK;
+    const long long N = 1ll << p.logn;
+    NttTileParams q{};
+    q.in_natural = 1;
+    if (p.l2 == 0) {
+        q.in = buf; q.out = buf;
+        q.in_outer_stride = q.out_outer_stride = 0;
+        q.in_lane_stride = q.out_lane_stride = (long long)batch_stride;
+        q.in_point_stride = q.out_point_stride = 1;
+        q.lanes_inner = (int)batch; q.total_lanes = (int)batch;
+        q.logm = p.l1; q.lanes_per_cta = lanes_per_cta(p.l1);
+        q.tw = p.tw1.d; q.tws = 1;
+        q.scale = p.inverse ? p.scale.d : nullptr;
+        q.canon = 1;
+        CU(launch_ntt_tile(q, c->stream)); c->launches++;
+        return LGR_OK;
+    }
+    const long long N1 = 1ll << p.l1, N2 = 1ll << p.l2;
+    REQUIRE((unsigned long long)batch * (unsigned long long)N2 < (1ull << 31) && (unsigned long long)batch * (unsigned long long)N1 < (1ull << 31), "batch too large");
+    int rc = ensure_scratch(c, (size_t)batch * (size_t)N);
+    if (rc) return rc;
+    // pass 1: for every column i2, N1-point transform over i1 (stride N2), twist by w^(i2*k1); user -> scratch
+    q.in = buf; q.out = c->scratch;
+    q.in_outer_stride = (long long)batch_stride; q.out_outer_stride = N;
+    q.in_lane_stride = q.out_lane_stride = 1;
+    q.in_point_stride = q.out_point_stride = N2;
+    q.lanes_inner = (int)N2; q.total_lanes = (int)(batch * N2);
+    q.logm = p.l1; q.lanes_per_cta = lanes_per_cta(p.l1);
+    q.tw = p.tw1.d; q.tws = 1;
+    q.twist_lo = p.twist_lo.d; q.twist_hi = p.twist_hi.d; q.twist_shift = p.twist_shift;
+    q.scale = nullptr; q.canon = 0;
+    CU(launch_ntt_tile(q, c->stream)); c->launches++;
+    // pass 2: for every k1, N2-point transform over i2 (contiguous); output index k1 + N1*k2; scratch -> user
+    NttTileParams r{};
+    r.in_natural = 1;
+    r.in = c->scratch; r.out = buf;
+    r.in_outer_stride = N; r.out_outer_stride = (long long)batch_stride;
+    r.in_lane_stride = N2; r.in_point_stride = 1;
+    r.out_lane_stride = 1; r.out_point_stride = N1;
+    r.lanes_inner = (int)N1; r.total_lanes = (int)(batch * N1);
+    r.logm = p.l2; r.lanes_per_cta = lanes_per_cta(p.l2);
+    r.tw = p.tw2.d; r.tws = 1;
+    r.scale = p.inverse ? p.scale.d : nullptr;
+    r.canon = 1;
+    CU(launch_ntt_tile(r, c->stream)); c->launches++;
+    return LGR_OK;
+}
+
+static int ilog2u(uint64_t x) { int l = 0; while ((1ull << l) < x) l++; return l; }
+
+static int build_encode_tables(lgr_ctx *c) {
+    if (c->enc_ready) return LGR_OK;
+    const size_t k = c->k;
+    const int logk = c->logk;
+    DevTable a, b, t;
+    int rc;
+    if ((rc = upload(c, host::power_table_mont(host::inv(c->root_k), k / 2), a))) return rc;
+    const Fr wn4 = host::pow(c->root_n, 4);
+    if ((rc = upload(c, host::power_table_mont(wn4, k / 2), b))) return rc;
+    // twist[r][q] = w_n^(r * bitrev_k(q)) / k * R
+    std::vector<Fr> tw(4 * k);
+    const Fr kinv_m = host::to_mont(host::inv(host::from_u64(k)));
+    for (int r = 0; r < 4; r++) {
+        std::vector<Fr> pw = host::power_table_mont(host::pow(c->root_n, r), k);     // (w_n^r)^i * R
+        for (size_t q = 0; q < k; q++) {
+            size_t i = 0; for (int bit = 0; bit < logk; bit++) if (q >> bit & 1) i |= (size_t)1 << (logk - 1 - bit);
+            tw[r * k + q] = host::montmul(pw[i], kinv_m);                              // (x R)(k^-1 R)/R
+        }
+    }
+    if ((rc = upload(c, tw, t))) return rc;
+    c->enc.inv_k = a.d; c->enc.fwd_c = b.d; c->enc.twist = t.d;
+    c->enc_ready = true;
+    return LGR_OK;
+}
+
+static bool fused_encode_ok(const lgr_ctx *c) { return c->logk >= encode_rows_min_logk() && c->logk <= encode_rows_max_logk(); }
+
+// nrows encodes: rows -> codewords (may alias when in place)
+static int encode_rows_impl(lgr_ctx *c, const fr_mem *rows, size_t row_stride, uint32_t nrows, fr_mem *cw, cudaStream_t st) {
+    if (nrows == 0) return LGR_OK;
+    if (fused_encode_ok(c)) {
+        int rc = build_encode_tables(c);
+        if (rc) return rc;
+        CU(launch_encode_rows(rows, (long long)row_stride, cw, (long long)c->n, (int)nrows, c->logk, c->enc, st)); c->launches++;
+        return LGR_OK;
+    }
+    // large k: the reference's composition (engine.cpp:755-770) on the generic engine
+    REQUIRE(st == c->stream, "internal: generic encode runs on the main stream");
+    if ((const void *)rows != (const void *)cw || row_stride != c->n) {
+        CU(cudaMemsetAsync(cw, 0, (size_t)nrows * c->n * 32, st));
+        CU(cudaMemcpy2DAsync(cw, (size_t)c->n * 32, rows, row_stride * 32, (size_t)c->k * 32, nrows, cudaMemcpyDeviceToDevice, st));
+    }
+    NttPlan *pi, *pf; int rc;
+    if ((rc = get_plan(c, c->logk, c->root_k, true, &pi))) return rc;
+    if ((rc = get_plan(c, c->logk + 2, c->root_n, false, &pf))) return rc;
+    if ((rc = run_ntt(c, cw, *pi, nrows, c->n))) return rc;
+    return run_ntt(c, cw, *pf, nrows, c->n);
+}
+
+// ================================================================================================
+extern "C" {
+
+const char *lgr_last_error(void) { return g_err.c_str(); }
+int lgr_version(void) { return 100; }
+
+int lgr_create(lgr_ctx **out, int device, uint32_t l, uint32_t k, uint32_t n, const uint32_t p[8], const uint32_t root_k[8],
+               const uint32_t root_2k[8], const uint32_t root_n[8]) {
+    REQUIRE(out && p && root_k && root_2k && root_n, "null argument");
+    REQUIRE(k >= 2 && (k & (k - 1)) == 0, "k must be a power of two >= 2");
+    REQUIRE(n == 4 * k, "n must equal 4k (src/webgpu_prover.cpp:88-97)");
+    REQUIRE(l <= k, "l must not exceed k");
+    REQUIRE(memcmp(p, host::kP, 32) == 0, "modulus is not the BN254 scalar field (the kernels are specialised, as the reference's WGSL is)");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this library has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(LGR_ERR_UNSUPPORTED, std::string("liblgr is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor));
+    lgr_ctx *c = new lgr_ctx();
+    c->device = device; c->l = l; c->k = k; c->n = n; c->logk = ilog2u(k);
+    c->root_k = host::from_u32(root_k); c->root_2k = host::from_u32(root_2k); c->root_n = host::from_u32(root_n);
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CU(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, lo));
+    CU(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+    c->stream = c->own_stream;
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&c->ev_enc[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_hash[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_staging, cudaEventDisableTiming));
+    // validate the roots and build the six context plans eagerly (engine.cpp:196-211 does the same)
+    NttPlan *pl; int rc = LGR_OK;
+    for (int inv = 0; inv < 2 && !rc; inv++) {
+        rc = get_plan(c, c->logk, c->root_k, inv, &pl);
+        if (!rc) rc = get_plan(c, c->logk + 1, c->root_2k, inv, &pl);
+        if (!rc) rc = get_plan(c, c->logk + 2, c->root_n, inv, &pl);
+    }
+    if (!rc && fused_encode_ok(c)) rc = build_encode_tables(c);
+    if (rc) { std::string keep = g_err; lgr_destroy(c); g_err = keep; return rc; }
+    *out = c;
+    return LGR_OK;
+}
+
+int lgr_destroy(lgr_ctx *c) {
+    if (!c) return LGR_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void *p : c->owned) cudaFree(p);
+    if (c->scratch) cudaFree(c->scratch);
+    for (int i = 0; i < 2; i++) { if (c->tile[i]) cudaFree(c->tile[i]); if (c->ev_enc[i]) cudaEventDestroy(c->ev_enc[i]); if (c->ev_hash[i]) cudaEventDestroy(c->ev_hash[i]); }
+    if (c->commit_sha) cudaFree(c->commit_sha);
+    if (c->sample_idx) cudaFree(c->sample_idx);
+    if (c->staging) cudaFreeHost(c->staging);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_staging) cudaEventDestroy(c->ev_staging);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    delete c;
+    return LGR_OK;
+}
+
+int lgr_set_stream(lgr_ctx *c, void *s) { REQUIRE(c, "null context"); c->stream = s ? (cudaStream_t)s : c->own_stream; return LGR_OK; }
+int lgr_sync(lgr_ctx *c) { REQUIRE(c, "null context"); CU(cudaStreamSynchronize(c->stream)); return LGR_OK; }
+int lgr_geometry(const lgr_ctx *c, uint32_t *l, uint32_t *k, uint32_t *n) {
+    REQUIRE(c, "null context");
+    if (l) *l = c->l; if (k) *k = c->k; if (n) *n = c->n;
+    return LGR_OK;
+}
+int lgr_launch_count(const lgr_ctx *c, uint64_t *count) { REQUIRE(c && count, "null argument"); *count = c->launches; return LGR_OK; }
+
+// ---- buffers -----------------------------------------------------------------------------------
+int lgr_alloc(lgr_ctx *c, size_t bytes, void **dptr) {
+    REQUIRE(c && dptr, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(dptr, bytes ? bytes : 32));
+    CU(cudaMemsetAsync(*dptr, 0, bytes ? bytes : 32, c->stream));
+    return LGR_OK;
+}
+int lgr_free(lgr_ctx *c, void *dptr) {
+    REQUIRE(c, "null context");
+    if (dptr) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(dptr)); }
+    return LGR_OK;
+}
+int lgr_write(lgr_ctx *c, void *dst, size_t off, const void *src, size_t bytes) {
+    REQUIRE(c && dst && (src || !bytes), "null argument");
+    if (!bytes) return LGR_OK;
+    // the caller may reuse `src` immediately (nonbatch_context.hpp:455-468): stage through pinned memory
+    if (c->staging_bytes < bytes) {
+        if (c->staging) { CU(cudaEventSynchronize(c->ev_staging)); CU(cudaFreeHost(c->staging)); c->staging = nullptr; c->staging_bytes = 0; }
+        size_t cap = std::max(bytes, (size_t)1 << 20);
+        CU(cudaMallocHost(&c->staging, cap));
+        c->staging_bytes = cap;
+    } else {
+        CU(cudaEventSynchronize(c->ev_staging));       // previous upload must have left the staging buffer
+    }
+    memcpy(c->staging, src, bytes);
+    CU(cudaMemcpyAsync((char *)dst + off, c->staging, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev_staging, c->stream));
+    return LGR_OK;
+}
+int lgr_clear(lgr_ctx *c, void *dst, size_t off, size_t bytes) {
+    REQUIRE(c && dst, "null argument");
+    if (bytes) CU(cudaMemsetAsync((char *)dst + off, 0, bytes, c->stream));
+    return LGR_OK;
+}
+int lgr_write_clear(lgr_ctx *c, void *dst, size_t dst_bytes, const void *src, size_t bytes) {
+    REQUIRE(bytes <= dst_bytes, "write_buffer_clear: source larger than destination");
+    int rc = lgr_write(c, dst, 0, src, bytes);
+    if (rc) return rc;
+    return lgr_clear(c, dst, bytes, dst_bytes - bytes);
+}
+int lgr_copy(lgr_ctx *c, const void *src, void *dst, size_t bytes) {
+    REQUIRE(c && src && dst, "null argument");
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return LGR_OK;
+}
+int lgr_copy_clear(lgr_ctx *c, const void *src, size_t src_bytes, void *dst, size_t dst_bytes) {
+    REQUIRE(src_bytes <= dst_bytes, "copy_buffer_clear: source larger than destination");
+    int rc = lgr_copy(c, src, dst, src_bytes);
+    if (rc) return rc;
+    return lgr_clear(c, dst, src_bytes, dst_bytes - src_bytes);
+}
+int lgr_read(lgr_ctx *c, void *host_dst, const void *src, size_t off, size_t bytes) {
+    REQUIRE(c && host_dst && src, "null argument");
+    if (bytes) CU(cudaMemcpyAsync(host_dst, (const char *)src + off, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return LGR_OK;
+}
+
+// ---- transforms --------------------------------------------------------------------------------
+int lgr_ntt(lgr_ctx *c, void *buf, int sel, int dir) {
+    REQUIRE(c && buf, "null argument");
+    REQUIRE(sel >= LGR_SIZE_K && sel <= LGR_SIZE_N && (dir == LGR_FORWARD || dir == LGR_INVERSE), "bad size selector / direction");
+    const Fr &w = sel == LGR_SIZE_K ? c->root_k : (sel == LGR_SIZE_2K ? c->root_2k : c->root_n);
+    NttPlan *p; int rc = get_plan(c, c->logk + sel, w, dir == LGR_INVERSE, &p);
+    if (rc) return rc;
+    return run_ntt(c, (fr_mem *)buf, *p, 1, (size_t)1 << (c->logk + sel));
+}
+int lgr_ntt_pow2(lgr_ctx *c, void *buf, uint32_t logn, uint32_t batch, const uint32_t omega[8], int dir) {
+    REQUIRE(c && buf && omega, "null argument");
+    REQUIRE(dir == LGR_FORWARD || dir == LGR_INVERSE, "bad direction");
+    NttPlan *p; int rc = get_plan(c, (int)logn, host::from_u32(omega), dir == LGR_INVERSE, &p);
+    if (rc) return rc;
+    return run_ntt(c, (fr_mem *)buf, *p, batch, (size_t)1 << logn);
+}
+int lgr_encode(lgr_ctx *c, void *buf) {
+    REQUIRE(c && buf, "null argument");
+    return encode_rows_impl(c, (const fr_mem *)buf, c->n, 1, (fr_mem *)buf, c->stream);
+}
+int lgr_encode_rows(lgr_ctx *c, const void *rows, uint64_t row_stride, uint32_t nrows, void *cw) {
+    REQUIRE(c && rows && cw, "null argument");
+    REQUIRE(row_stride >= c->k, "row stride smaller than k");
+    REQUIRE(rows != cw || row_stride == c->n, "in-place encode needs a row stride of n elements");
+    return encode_rows_impl(c, (const fr_mem *)rows, row_stride, nrows, (fr_mem *)cw, c->stream);
+}
+int lgr_decode(lgr_ctx *c, void *buf) {
+    REQUIRE(c && buf, "null argument");
+    NttPlan *pi, *pf; int rc;
+    if ((rc = get_plan(c, c->logk + 2, c->root_n, true, &pi))) return rc;
+    if ((rc = get_plan(c, c->logk, c->root_k, false, &pf))) return rc;
+    if ((rc = run_ntt(c, (fr_mem *)buf, *pi, 1, c->n))) return rc;
+    EltParams e{};                                    // ntt_fold (kernels.wgsl.in:104-116): c[i] += c[i+k]
+    e.x = (fr_mem *)buf; e.y = (fr_mem *)buf + c->k; e.out = (fr_mem *)buf; e.n = c->k;
+    CU(launch_eltwise(ELT_ADD, e, c->stream)); c->launches++;
+    return run_ntt(c, (fr_mem *)buf, *pf, 1, c->k);
+}
+
+// ---- hashing -----------------------------------------------------------------------------------
+size_t lgr_sha_ctx_bytes(uint32_t ninst) { return sha_ctx_words(ninst) * 4; }
+int lgr_sha_init(lgr_ctx *c, void *s, uint32_t ninst) {
+    REQUIRE(c && s, "null argument");
+    CU(launch_sha_init((uint32_t *)s, (int)ninst, c->stream)); c->launches++;
+    return LGR_OK;
+}
+int lgr_sha_update_rows(lgr_ctx *c, void *s, uint32_t ninst, const void *tile, uint64_t row_stride, uint32_t nrows) {
+    REQUIRE(c && s && tile, "null argument");
+    CU(launch_sha_update((uint32_t *)s, (int)ninst, (const fr_mem *)tile, (long long)row_stride, (int)nrows, c->stream)); c->launches++;
+    return LGR_OK;
+}
+int lgr_sha_update(lgr_ctx *c, void *s, uint32_t ninst, const void *buf) { return lgr_sha_update_rows(c, s, ninst, buf, ninst, 1); }
+int lgr_sha_final(lgr_ctx *c, const void *s, uint32_t ninst, void *digests) {
+    REQUIRE(c && s && digests, "null argument");
+    CU(launch_sha_final((const uint32_t *)s, (int)ninst, (uint32_t *)digests, c->stream)); c->launches++;
+    return LGR_OK;
+}
+size_t lgr_merkle_node_count(uint32_t nleaves) { size_t p = 1; while (p < nleaves) p <<= 1; return 2 * p - 1; }
+int lgr_merkle_build(lgr_ctx *c, const void *leaf, uint32_t nleaves, void *nodes) {
+    REQUIRE(c && leaf && nodes && nleaves, "null argument");
+    CU(launch_merkle_build((const uint32_t *)leaf, (int)nleaves, (uint32_t *)nodes, c->stream));
+    int P2 = 1, lv = 1; while (P2 < (int)nleaves) P2 <<= 1;
+    for (int cnt = P2 >> 1; cnt > 256; cnt >>= 1) lv++;
+    c->launches += lv + 1;
+    return LGR_OK;
+}
+
+// ---- element-wise ------------------------------------------------------------------------------
+static int elt(lgr_ctx *c, EltOp op, const void *x, const void *y, const void *z, void *out, size_t n, const uint32_t *sc, bool to_mont,
+               const void *idx = nullptr, uint32_t bit = 0) {
+    REQUIRE(c && out, "null argument");
+    EltParams p{};
+    p.x = (const fr_mem *)x; p.y = (const fr_mem *)y; p.z = (const fr_mem *)z; p.out = (fr_mem *)out; p.n = n;
+    p.idx = (const uint32_t *)idx; p.bit = bit;
+    if (sc) {
+        Fr s = host::from_u32(sc);
+        REQUIRE(host::is_canonical(s), "scalar is not reduced modulo p");
+        if (to_mont) s = host::to_mont(s);
+        host::to_u32(p.scalar, s);
+    }
+    CU(launch_eltwise(op, p, c->stream)); c->launches++;
+    return LGR_OK;
+}
+int lgr_elt_add(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_ADD, x, y, 0, o, n, 0, false); }
+int lgr_elt_sub(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_SUB, x, y, 0, o, n, 0, false); }
+int lgr_elt_mul(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_MUL, x, y, 0, o, n, 0, false); }
+int lgr_elt_div(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_DIV, x, y, 0, o, n, 0, false); }
+int lgr_elt_fma(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_FMA, x, y, 0, o, n, 0, false); }
+int lgr_elt_fma_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_FMA_CONST, x, 0, 0, o, n, k, true); }
+int lgr_elt_add_assign(lgr_ctx *c, const void *x, void *o, size_t n) { REQUIRE(x, "null argument"); return elt(c, ELT_ADD_ASSIGN, x, 0, 0, o, n, 0, false); }
+int lgr_elt_add_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_ADD_CONST, x, 0, 0, o, n, k, false); }
+int lgr_elt_sub_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_SUB_CONST, x, 0, 0, o, n, k, false); }
+int lgr_elt_const_sub(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_CONST_SUB, x, 0, 0, o, n, k, false); }
+int lgr_elt_mul_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_MUL_CONST, x, 0, 0, o, n, k, true); }
+int lgr_elt_montmul_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_MONTMUL_CONST, x, 0, 0, o, n, k, false); }
+int lgr_elt_bit(lgr_ctx *c, const void *x, void *o, size_t n, uint32_t bit) { REQUIRE(x, "null argument"); REQUIRE(bit < 256, "bit index out of range"); return elt(c, ELT_BIT, x, 0, 0, o, n, 0, false, nullptr, bit); }
+int lgr_elt_powmod(lgr_ctx *c, const void *coeff, const void *exp, void *o, size_t n, const uint32_t base[8], int add) {
+    REQUIRE(coeff && exp && base, "null argument");
+    return elt(c, add ? ELT_POWADD : ELT_POWMOD, coeff, 0, 0, o, n, base, true, exp);
+}
+int lgr_elt_quad(lgr_ctx *c, const void *x, const void *y, const void *z, void *o, size_t n, const uint32_t r[8]) {
+    REQUIRE(x && y && z && r, "null argument");
+    return elt(c, ELT_QUAD_FUSED, x, y, z, o, n, r, true);
+}
+
+// ---- sampling ----------------------------------------------------------------------------------
+int lgr_sample_init(lgr_ctx *c, const uint64_t *idx, uint32_t count) {
+    REQUIRE(c && (idx || !count), "null argument");
+    if (c->sample_idx) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->sample_idx)); c->sample_idx = nullptr; }
+    c->sample_count = count;
+    if (!count) return LGR_OK;
+    std::vector<uint32_t> v(count);
+    for (uint32_t i = 0; i < count; i++) { REQUIRE(idx[i] < c->n, "sample index out of range"); v[i] = (uint32_t)idx[i]; }
+    CU(cudaMalloc((void **)&c->sample_idx, count * 4));
+    CU(cudaMemcpy(c->sample_idx, v.data(), count * 4, cudaMemcpyHostToDevice));
+    return LGR_OK;
+}
+int lgr_sample_gather(lgr_ctx *c, const void *x, void *out) {
+    REQUIRE(c && x && out, "null argument");
+    REQUIRE(c->sample_idx, "sampling_init has not been called");
+    return elt(c, ELT_GATHER, x, 0, 0, out, c->sample_count, 0, false, c->sample_idx);
+}
+
+// ---- stage-1 commit pipeline -------------------------------------------------------------------
+int lgr_encode_commit(lgr_ctx *c, const void *rows_v, uint64_t nrows, void *digests, void *nodes) {
+    REQUIRE(c && rows_v && digests, "null argument");
+    REQUIRE(nrows < (1ull << 40), "too many rows");
+    const fr_mem *rows = (const fr_mem *)rows_v;
+    const size_t n = c->n, k = c->k;
+    // tile: even number of rows, ~2^21 codeword elements (64 MiB) per buffer; both buffers L2-friendly for small n
+    size_t T = ((size_t)1 << 21) / n;
+    if (T < 2) T = 2;
+    T &= ~(size_t)1;
+    if (T > nrows) T = (size_t)nrows;
+    if (T == 0) T = 1;
+    const bool overlap = fused_encode_ok(c);            // generic-engine encodes use the main stream + shared scratch
+    if (c->tile_elems < T * n) {
+        CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(c->aux_stream));
+        for (int i = 0; i < 2; i++) { if (c->tile[i]) CU(cudaFree(c->tile[i])); c->tile[i] = nullptr; }
+        for (int i = 0; i < 2; i++) CU(cudaMalloc((void **)&c->tile[i], T * n * 32));
+        c->tile_elems = T * n;
+    }
+    if (!c->commit_sha) CU(cudaMalloc((void **)&c->commit_sha, lgr_sha_ctx_bytes((uint32_t)n)));
+    cudaStream_t es = c->stream, hs = overlap ? c->aux_stream : c->stream;
+    if (overlap) { CU(cudaEventRecord(c->ev_fork, es)); CU(cudaStreamWaitEvent(hs, c->ev_fork, 0)); }
+    CU(launch_sha_init(c->commit_sha, (int)n, hs)); c->launches++;
+    int rc;
+    size_t tile_idx = 0;
+    for (uint64_t r0 = 0; r0 < nrows; r0 += T, tile_idx++) {
+        const int b = (int)(tile_idx & 1);
+        const uint32_t t = (uint32_t)std::min<uint64_t>(T, nrows - r0);
+        if (overlap && tile_idx >= 2) CU(cudaStreamWaitEvent(es, c->ev_hash[b], 0));     // buffer free again
+        if ((rc = encode_rows_impl(c, rows + r0 * k, k, t, c->tile[b], es))) return rc;
+        if (overlap) { CU(cudaEventRecord(c->ev_enc[b], es)); CU(cudaStreamWaitEvent(hs, c->ev_enc[b], 0)); }
+        CU(launch_sha_update(c->commit_sha, (int)n, c->tile[b], (long long)n, (int)t, hs)); c->launches++;
+        if (overlap) CU(cudaEventRecord(c->ev_hash[b], hs));
+    }
+    CU(launch_sha_final(c->commit_sha, (int)n, (uint32_t *)digests, hs)); c->launches++;
+    if (nodes) {
+        CU(launch_merkle_build((const uint32_t *)digests, (int)n, (uint32_t *)nodes, hs));
+        int lv = 1; for (size_t cnt = n >> 1; cnt > 256; cnt >>= 1) lv++;
+        c->launches += lv + 1;
+    }
+    if (overlap) { CU(cudaEventRecord(c->ev_join, hs)); CU(cudaStreamWaitEvent(es, c->ev_join, 0)); }
+    return LGR_OK;
+}
+
+// ---- stage-2 tile combiners --------------------------------------------------------------------
+int lgr_combine_code(lgr_ctx *c, const void *tile, uint32_t nrows, const uint32_t *host_r, void *acc) {
+    REQUIRE(c && tile && host_r && acc, "null argument");
+    if (!nrows) return LGR_OK;
+    const size_t part = combine_scratch_elems((int)nrows, (int)c->n);
+    int rc = ensure_scratch(c, part + nrows);
+    if (rc) return rc;
+    std::vector<Fr> r(nrows);
+    for (uint32_t i = 0; i < nrows; i++) {
+        Fr s = host::from_u32(host_r + 8 * i);
+        REQUIRE(host::is_canonical(s), "scalar is not reduced modulo p");
+        r[i] = host::to_mont(s);
+    }
+    fr_mem *r_dev = c->scratch + part;
+    if ((rc = lgr_write(c, r_dev, 0, r.data(), (size_t)nrows * 32))) return rc;
+    CU(launch_combine_code((const fr_mem *)tile, (long long)c->n, (int)nrows, (int)c->n, r_dev, (fr_mem *)acc, c->scratch, part, c->stream));
+    c->launches += 2;
+    return LGR_OK;
+}
+int lgr_combine_linear(lgr_ctx *c, const void *a, const void *b, uint32_t nrows, void *acc) {
+    REQUIRE(c && a && b && acc, "null argument");
+    if (!nrows) return LGR_OK;
+    const size_t part = combine_scratch_elems((int)nrows, (int)c->n);
+    int rc = ensure_scratch(c, part);
+    if (rc) return rc;
+    CU(launch_combine_linear((const fr_mem *)a, (const fr_mem *)b, (long long)c->n, (int)nrows, (int)c->n, (fr_mem *)acc, c->scratch, part, c->stream));
+    c->launches += 2;
+    return LGR_OK;
+}
+
+// ---- synthetic data / micro-benchmarks ---------------------------------------------------------
+int lgr_synth(lgr_ctx *c, void *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols) {
+    REQUIRE(c && out, "null argument");
+    CU(launch_synth((fr_mem *)out, seed, row0, nrows, ncols, c->stream)); c->launches++;
+    return LGR_OK;
+}
+int lgr_ubench(lgr_ctx *c, int which, double *ops) {
+    REQUIRE(c && ops, "null argument");
+    REQUIRE(which >= 0 && which <= 2, "unknown micro-benchmark");
+    uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int blocks = 148 * 8, threads = 256;
+    const int iters = which == 0 ? 4096 : (which == 1 ? 512 : 256);
+    CU(launch_ubench(which, d, iters, blocks, threads, c->stream));           // warm-up
+    CU(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < 5; i++) CU(launch_ubench(which, d, iters, blocks, threads, c->stream));
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    c->launches += 6;
+    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double per_thread = which == 0 ? 8.0 * iters : (double)iters * (which == 1 ? 4.0 : 1.0);
+    *ops = 5.0 * per_thread * blocks * threads / (ms * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return LGR_OK;
+}
+
+}  // extern "C"

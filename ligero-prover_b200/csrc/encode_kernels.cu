@@ -1,0 +1,108 @@
+// Fused Reed-Solomon row encoder for k = 2^LOGK <= 2048.
+//
+// Reference semantics (src/webgpu/engine.cpp:755-770 encode_ntt_device): c = iNTT_k(row) on the
+// w_k domain, codeword e = NTT_n(c || 0...0) on the w_n domain, n = 4k: 15 dispatches, every stage
+// a pass over global memory, 3/4 of the forward input known-zero.
+//
+// Here one row never leaves the SM between input and codeword:
+//   1. DIF inverse transform (natural in -> bit-reversed coefficients; no permutation pass)
+//   2. the 4k-point forward transform is split into four k-point coset transforms:
+//        e[4m + r] = sum_i (c_i * w_n^(r*i)) * (w_n^4)^(i*m),   r = 0..3
+//      so the zero padding is never touched; the twist table also carries the 1/k of the inverse
+//   3. each coset runs as a DIT (bit-reversed in -> natural out) and is written interleaved.
+// Per witness element: (log2(k)-1)/2 + 4 + 4*(log2(k)-1)/2 Montgomery multiplications.
+#include "kernels.h"
+#include "ntt.cuh"
+
+#ifndef LGR_ENC_LOGK
+#error "compile with -DLGR_ENC_LOGK=<3..11> (see Makefile): one translation unit per row size keeps the build parallel"
+#endif
+
+namespace lgr {
+
+template <int TL> struct slot_sync {
+    int id;
+    __device__ __forceinline__ void operator()() const {
+        if constexpr (TL <= 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(TL) : "memory");
+    }
+};
+
+template <int LOGK> struct enc_cfg {
+    static constexpr int K = 1 << LOGK;
+    static constexpr int TL = K / 8;                                    // threads per row
+    static constexpr int THREADS = (TL >= 128) ? TL : 128;
+    static constexpr int SLOTS = THREADS / TL;                          // rows in flight per CTA
+    static constexpr size_t SMEM = (size_t)SLOTS * 2 * K * 32;          // coefficients + work array per slot
+};
+
+template <int LOGK>
+__global__ void __launch_bounds__(enc_cfg<LOGK>::THREADS) encode_rows_kernel(
+    const fr_mem *__restrict__ rows_in, long long in_row_stride, fr_mem *__restrict__ out, long long out_row_stride, int R,
+    const EncodeTables t) {
+    using cfg = enc_cfg<LOGK>;
+    constexpr int K = cfg::K, TL = cfg::TL;
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int slot = threadIdx.x / TL, tl = threadIdx.x % TL;
+    fr_mem *C = reinterpret_cast<fr_mem *>(smem_raw) + (size_t)slot * 2 * K;
+    fr_mem *W = C + K;
+    const long long row = (long long)blockIdx.x * cfg::SLOTS + slot;
+    const bool active = row < R;
+    slot_sync<TL> sync{slot + 1};
+
+    // 1. load the message row (coalesced, natural order)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int i = tl + j * TL;
+        fr_t x = active ? fr_ldg(rows_in + row * in_row_stride + i) : fr_zero();
+        fr_sts(C + i, x);
+    }
+    sync();
+    // 2. coefficients, bit-reversed order, [0,2p)  (w_k^-1 twiddles; 1/k folded into the twist)
+    ntt_dif<LOGK>(C, tl, t.inv_k, 1, sync);
+    // 3. four coset transforms
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int q = tl + j * TL;
+            fr_t c = fr_lds(C + q);
+            fr_sts(W + q, fr_mont_mul(c, fr_ldc(t.twist + r * K + q)));
+        }
+        sync();
+        ntt_dit<LOGK>(W, tl, t.fwd_c, 1, sync);
+        if (active) {
+            fr_mem *o = out + row * out_row_stride + r;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int m = tl + j * TL;
+                fr_stg(o + 4 * m, fr_canon4(fr_lds(W + m)));
+            }
+        }
+        sync();
+    }
+}
+
+template <int LOGK>
+static cudaError_t launch_enc(const fr_mem *rows_in, long long in_row_stride, fr_mem *out, long long out_row_stride, int R,
+                              const EncodeTables &t, cudaStream_t st) {
+    using cfg = enc_cfg<LOGK>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(encode_rows_kernel<LOGK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int grid = (R + cfg::SLOTS - 1) / cfg::SLOTS;
+    encode_rows_kernel<LOGK><<<grid, cfg::THREADS, cfg::SMEM, st>>>(rows_in, in_row_stride, out, out_row_stride, R, t);
+    return cudaGetLastError();
+}
+
+#define LGR_CAT2(a, b) a##b
+#define LGR_CAT(a, b) LGR_CAT2(a, b)
+cudaError_t LGR_CAT(launch_encode_rows_, LGR_ENC_LOGK)(const fr_mem *rows_in, long long in_row_stride, fr_mem *out, long long out_row_stride,
+                                                       int R, const EncodeTables &t, cudaStream_t st) {
+    return launch_enc<LGR_ENC_LOGK>(rows_in, in_row_stride, out, out_row_stride, R, t, st);
+}
+
+}  // namespace lgr

@@ -1,0 +1,232 @@
+// BN254 scalar field (Fr) arithmetic for sm_100a: 8 x u32 limbs held entirely in registers.
+//
+// Replaces shader/bigint.wgsl.in + shader/bn254fr.wgsl.in of the reference (256-bit integers as
+// 2 x vec4<u32>, products built from 16-bit halves because WGSL has no mulhi,
+// bigint.wgsl.in:69-88).  Here one 32x32->64 product is one IMAD.WIDE; a Montgomery
+// multiplication is an interleaved 8-row CIOS on two 64-bit-aligned accumulator sets ("even"
+// columns and "odd" columns) so that every partial product is a wide multiply-add on a carry
+// chain (mad.lo.cc / madc.hi.cc pairs).
+//
+// Value conventions
+//   * host-visible elements: canonical [0,p), NOT Montgomery form (bn254fr.wgsl.in)
+//   * twiddles / constants: value * 2^256 mod p ("Montgomery form"), canonical
+//   * fr_mont_mul(a, b): a in [0,4p), b in [0,p)  ->  a*b*2^-256 mod p in [0,2p)
+//     (same residue as montgomery_mul_2p, bn254fr.wgsl.in:106-109)
+//
+// The file also compiles for the host (LGR_FR_HOST_EMU) with the PTX carry primitives emulated,
+// so the algorithm can be checked against the oracle without a GPU (tests/test_fr_emulation.py).
+#pragma once
+#include <stdint.h>
+
+#ifdef LGR_FR_HOST_EMU
+#define LGR_DEV static inline
+namespace lgr_emu {
+static thread_local uint32_t cc;
+static inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+static inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + cc; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+static inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + cc; }
+// PTX semantics: after sub.cc / subc.cc the flag holds the BORROW; subc computes a - (b + CF)
+static inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b; cc = (uint32_t)((s >> 32) & 1); return (uint32_t)s; }
+static inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b - cc; cc = (uint32_t)((s >> 32) & 1); return (uint32_t)s; }
+static inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - cc; }
+static inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + c; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+static inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + c + cc; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+static inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (((uint64_t)a * b) >> 32) + c; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+static inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (((uint64_t)a * b) >> 32) + c + cc; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+static inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)((((uint64_t)a * b) >> 32) + c + cc); }
+static inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+static inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+}  // namespace lgr_emu
+using namespace lgr_emu;
+#else
+#define LGR_DEV __device__ __forceinline__
+// PTX carry-flag primitives.  The condition code is not a modelled register: the statements are
+// volatile so the compiler keeps them in program order, and nothing else we emit between them
+// writes CC (plain add/sub/mad do not).
+LGR_DEV uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+LGR_DEV uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+LGR_DEV uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+LGR_DEV uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+LGR_DEV uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+LGR_DEV uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+LGR_DEV uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+LGR_DEV uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+LGR_DEV uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+LGR_DEV uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+LGR_DEV uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+LGR_DEV uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+LGR_DEV uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#endif
+
+namespace lgr {
+
+struct fr_t { uint32_t v[8]; };
+
+// p  (src/bn254.cpp:21-22, shader/bn254fr.wgsl.in:19-22), little-endian u32 limbs
+#define LGR_P0 0xF0000001u
+#define LGR_P1 0x43E1F593u
+#define LGR_P2 0x79B97091u
+#define LGR_P3 0x2833E848u
+#define LGR_P4 0x8181585Du
+#define LGR_P5 0xB85045B6u
+#define LGR_P6 0xE131A029u
+#define LGR_P7 0x30644E72u
+// -p^-1 mod 2^32
+#define LGR_M0 0xEFFFFFFFu
+
+LGR_DEV uint32_t fr_p(int i) {
+    switch (i) { case 0: return LGR_P0; case 1: return LGR_P1; case 2: return LGR_P2; case 3: return LGR_P3;
+                 case 4: return LGR_P4; case 5: return LGR_P5; case 6: return LGR_P6; default: return LGR_P7; }
+}
+// 2p limbs (shader/bn254fr.wgsl.in:25-28)
+LGR_DEV uint32_t fr_2p(int i) {
+    switch (i) { case 0: return 0xE0000002u; case 1: return 0x87C3EB27u; case 2: return 0xF372E122u; case 3: return 0x5067D090u;
+                 case 4: return 0x0302B0BAu; case 5: return 0x70A08B6Du; case 6: return 0xC2634053u; default: return 0x60C89CE5u; }
+}
+
+LGR_DEV fr_t fr_zero() { fr_t r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+
+// r = a + b (no reduction; caller guarantees < 2^256)
+LGR_DEV fr_t fr_add_raw(const fr_t &a, const fr_t &b) {
+    fr_t r;
+    r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+    r.v[7] = addc(a.v[7], b.v[7]);
+    return r;
+}
+
+// if (a >= m) a -= m, with m = p (TWO=false) or 2p (TWO=true); bn254fr_reduce / bn254fr_reduce_2p
+// (shader/bn254fr.wgsl.in:50-68).  Branch-free select on the final borrow.
+template <bool TWO>
+LGR_DEV fr_t fr_csub(const fr_t &a) {
+    fr_t d;
+    d.v[0] = sub_cc(a.v[0], TWO ? fr_2p(0) : fr_p(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) d.v[i] = subc_cc(a.v[i], TWO ? fr_2p(i) : fr_p(i));
+    uint32_t borrow = subc(0, 0);        // all ones iff a < m
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = borrow ? a.v[i] : d.v[i];
+    return r;
+}
+LGR_DEV fr_t fr_reduce_p(const fr_t &a) { return fr_csub<false>(a); }
+LGR_DEV fr_t fr_reduce_2p(const fr_t &a) { return fr_csub<true>(a); }
+// [0,4p) -> [0,p)
+LGR_DEV fr_t fr_canon4(const fr_t &a) { return fr_reduce_p(fr_reduce_2p(a)); }
+
+// a + b mod p for canonical inputs (EltwiseAddMod, kernels.wgsl.in:325-336)
+LGR_DEV fr_t fr_add(const fr_t &a, const fr_t &b) { return fr_reduce_p(fr_add_raw(a, b)); }
+
+// a - b mod p for canonical inputs (EltwiseSubMod, kernels.wgsl.in:364-380): add p back on borrow
+LGR_DEV fr_t fr_sub(const fr_t &a, const fr_t &b) {
+    fr_t d;
+    d.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) d.v[i] = subc_cc(a.v[i], b.v[i]);
+    uint32_t mask = subc(0, 0);          // all ones iff a < b
+    fr_t r;
+    r.v[0] = add_cc(d.v[0], fr_p(0) & mask);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = addc_cc(d.v[i], fr_p(i) & mask);
+    r.v[7] = addc(d.v[7], fr_p(7) & mask);
+    return r;
+}
+
+// lazy butterfly helpers: inputs in [0,2p)
+//   sum  = a + b           reduced to [0,2p)
+//   diff = a - b + 2p      in (0,4p)   (fed straight into fr_mont_mul, which accepts [0,4p))
+LGR_DEV fr_t fr_add_lazy(const fr_t &a, const fr_t &b) { return fr_reduce_2p(fr_add_raw(a, b)); }
+LGR_DEV fr_t fr_sub_lazy4(const fr_t &a, const fr_t &b) {
+    fr_t t;
+    t.v[0] = add_cc(a.v[0], fr_2p(0));
+#pragma unroll
+    for (int i = 1; i < 7; i++) t.v[i] = addc_cc(a.v[i], fr_2p(i));
+    t.v[7] = addc(a.v[7], fr_2p(7));
+    fr_t r;
+    r.v[0] = sub_cc(t.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = subc_cc(t.v[i], b.v[i]);
+    r.v[7] = subc(t.v[7], b.v[7]);
+    return r;
+}
+// a - b in [0,2p) for a,b in [0,2p)
+LGR_DEV fr_t fr_sub_lazy(const fr_t &a, const fr_t &b) { return fr_reduce_2p(fr_sub_lazy4(a, b)); }
+
+// ---- Montgomery multiplication -------------------------------------------------------------
+// T = even + 2^32 * odd.  Row i adds a*b[i] (even-indexed limbs of a into `even`, odd-indexed
+// into `odd`), then m = T[0] * M0 and adds m*p the same way, which zeroes limb 0; the shift by one
+// limb is a swap of the roles of the two sets.
+namespace detail {
+LGR_DEV void mul_n(uint32_t *acc, const uint32_t *a, uint32_t bi) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) { acc[j] = mul_lo(a[j], bi); acc[j + 1] = mul_hi(a[j], bi); }
+}
+LGR_DEV void cmad_n(uint32_t *acc, const uint32_t *a, uint32_t bi) {
+    acc[0] = mad_lo_cc(a[0], bi, acc[0]);
+    acc[1] = madc_hi_cc(a[0], bi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) { acc[j] = madc_lo_cc(a[j], bi, acc[j]); acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 1]); }
+}
+LGR_DEV void cmad_p(uint32_t *acc, int first, uint32_t mi) {      // acc += p[first, first+2, ..] * mi
+    acc[0] = mad_lo_cc(fr_p(first), mi, acc[0]);
+    acc[1] = madc_hi_cc(fr_p(first), mi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) { acc[j] = madc_lo_cc(fr_p(first + j), mi, acc[j]); acc[j + 1] = madc_hi_cc(fr_p(first + j), mi, acc[j + 1]); }
+}
+LGR_DEV void madc_n_rshift(uint32_t *odd, const uint32_t *a, uint32_t bi) {
+#pragma unroll
+    for (int j = 0; j < 6; j += 2) { odd[j] = madc_lo_cc(a[j], bi, odd[j + 2]); odd[j + 1] = madc_hi_cc(a[j], bi, odd[j + 3]); }
+    odd[6] = madc_lo_cc(a[6], bi, 0);
+    odd[7] = madc_hi(a[6], bi, 0);
+}
+LGR_DEV void mad_row(uint32_t *even, uint32_t *odd, const uint32_t *a, uint32_t bi, bool first) {
+    if (first) {
+        mul_n(odd, a + 1, bi);
+        mul_n(even, a, bi);
+    } else {
+        even[0] = add_cc(even[0], odd[1]);
+        madc_n_rshift(odd, a + 1, bi);
+        cmad_n(even, a, bi);
+        odd[7] = addc(odd[7], 0);
+    }
+    uint32_t mi = mul_lo(even[0], LGR_M0);
+    cmad_p(odd, 1, mi);
+    cmad_p(even, 0, mi);
+    odd[7] = addc(odd[7], 0);
+}
+}  // namespace detail
+
+// a in [0,4p), b in [0,p)  ->  a*b*2^-256 mod p, in [0,2p)
+LGR_DEV fr_t fr_mont_mul(const fr_t &a, const fr_t &b) {
+    uint32_t even[8], odd[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        detail::mad_row(even, odd, a.v, b.v[i], i == 0);
+        detail::mad_row(odd, even, a.v, b.v[i + 1], false);
+    }
+    fr_t r;
+    r.v[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = addc_cc(even[i], odd[i + 1]);
+    r.v[7] = addc(even[7], 0);
+    return r;
+}
+
+// canonical result
+LGR_DEV fr_t fr_mont_mul_canon(const fr_t &a, const fr_t &b) { return fr_canon4(fr_mont_mul(a, b)); }
+
+LGR_DEV bool fr_eq(const fr_t &a, const fr_t &b) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= a.v[i] ^ b.v[i];
+    return d == 0;
+}
+LGR_DEV bool fr_is_zero(const fr_t &a) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= a.v[i];
+    return d == 0;
+}
+
+}  // namespace lgr

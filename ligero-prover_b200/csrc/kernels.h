@@ -1,0 +1,87 @@
+// Internal launch interface between the C-ABI layer (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lgr {
+
+struct __align__(32) fr_mem { uint4 lo, hi; };   // one 32-byte element in global or shared memory
+
+// ---- generic tile NTT (ntt_kernels.cu) -------------------------------------------------------
+// A "lane" is one M-point transform.  Lane L = outer * lanes_inner + inner lives at
+//   in  + outer*in_outer_stride  + inner*in_lane_stride  + m*in_point_stride
+// and is written to the same formula with the out_* strides (all in elements).
+struct NttTileParams {
+    const fr_mem *in;
+    fr_mem *out;
+    long long in_outer_stride, in_lane_stride, in_point_stride;
+    long long out_outer_stride, out_lane_stride, out_point_stride;
+    int lanes_inner;
+    int total_lanes;
+    int lanes_per_cta;
+    int logm;
+    const fr_mem *tw;        // tw[j*tws] = w_M^j * R, j < M/2 (inverse root for inverse transforms)
+    int tws;
+    // optional four-step twist: out(inner, m) *= w_N^(inner*m) = twist_hi[e >> shift] * twist_lo[e & mask]
+    const fr_mem *twist_lo, *twist_hi;
+    int twist_shift;
+    const fr_mem *scale;     // optional N^-1 * R (Montgomery form)
+    int canon;               // 1: outputs reduced to [0,p)
+    int in_natural;          // 1: input natural order (bit-reverse on load, DIT); 0 never used here
+};
+cudaError_t launch_ntt_tile(const NttTileParams &p, cudaStream_t st);
+int ntt_tile_max_logm();
+
+// ---- fused row encoder (encode_kernels.cu), k = 2^logk, 3 <= logk <= 11 ----------------------
+struct EncodeTables {
+    const fr_mem *inv_k;     // w_k^-j * R, j < k/2
+    const fr_mem *fwd_c;     // (w_n^4)^j * R, j < k/2
+    const fr_mem *twist;     // [4][k]: w_n^(r*bitrev_k(q)) / k * R
+};
+// rows_in: [R][in_row_stride] elements (first k of each row used); out: [R][n] codewords
+cudaError_t launch_encode_rows(const fr_mem *rows_in, long long in_row_stride, fr_mem *out, long long out_row_stride,
+                               int R, int logk, const EncodeTables &t, cudaStream_t st);
+int encode_rows_max_logk();
+int encode_rows_min_logk();
+
+// ---- element-wise (eltwise_kernels.cu) -------------------------------------------------------
+enum EltOp {
+    ELT_ADD = 0, ELT_SUB, ELT_MUL, ELT_DIV, ELT_FMA, ELT_FMA_CONST, ELT_ADD_ASSIGN, ELT_ADD_CONST, ELT_SUB_CONST,
+    ELT_CONST_SUB, ELT_MUL_CONST, ELT_MONTMUL_CONST, ELT_BIT, ELT_POWMOD, ELT_POWADD, ELT_GATHER, ELT_QUAD_FUSED
+};
+struct EltParams {
+    const fr_mem *x, *y, *z;
+    fr_mem *out;
+    size_t n;
+    uint32_t scalar[8];      // canonical constant (op-dependent pre-conversion done by the caller)
+    uint32_t scalar2[8];
+    const uint32_t *idx;     // gather indices / powmod exponents
+    uint32_t bit;
+};
+cudaError_t launch_eltwise(EltOp op, const EltParams &p, cudaStream_t st);
+
+// tile combiners: acc[j] (+)= sum_t r[t] * tile[t][j]   (check_code over a resident tile)
+cudaError_t launch_combine_code(const fr_mem *tile, long long row_stride, int T, int n, const fr_mem *r_mont /*[T], r*R*/,
+                                fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st);
+// acc[j] += sum_t a[t][j] * b[t][j]   (check_linear over two resident tiles)
+cudaError_t launch_combine_linear(const fr_mem *a, const fr_mem *b, long long row_stride, int T, int n,
+                                  fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st);
+size_t combine_scratch_elems(int T, int n);
+
+// ---- SHA-256 column hashing + Merkle (sha_kernels.cu) ----------------------------------------
+// ctx layout (u32 words): state[8][n] | pend[8][n] | rows_lo[n] | rows_hi[n]
+static inline size_t sha_ctx_words(size_t n) { return 18 * n; }
+cudaError_t launch_sha_init(uint32_t *ctx, int n, cudaStream_t st);
+// absorb T rows: element j of row t at tile + t*row_stride + j
+cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long long row_stride, int T, cudaStream_t st);
+cudaError_t launch_sha_final(const uint32_t *ctx, int n, uint32_t *digests, cudaStream_t st);
+// nodes: (2*P2-1)*8 u32, P2 = bit_ceil(nleaves)
+cudaError_t launch_merkle_build(const uint32_t *leaf_digests, int nleaves, uint32_t *nodes, cudaStream_t st);
+
+// ---- synthetic witness generator (sha_kernels.cu; bench / tests only) ------------------------
+cudaError_t launch_synth(fr_mem *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols, cudaStream_t st);
+
+// ---- micro-benchmarks (ubench.cu) ------------------------------------------------------------
+cudaError_t launch_ubench(int which, uint32_t *out, int iters, int blocks, int threads, cudaStream_t st);
+
+}  // namespace lgr

@@ -1,0 +1,250 @@
+// Column-wise SHA-256 leaf hashing and the Merkle tree, on the device.
+//
+// Replaces shader/sha256.wgsl (thread-per-instance contexts that keep every pending BYTE as a u32
+// in global memory and a 64-entry message array in private memory, sha256.wgsl:23-28,65-125) and
+// the host OpenSSL tree build of include/zkp/merkle_tree.hpp:343-375.
+//
+// Byte order facts this file relies on:
+//   * sha256_update appends limb i of an element most-significant byte first
+//     (sha256.wgsl:155-162)  =>  the little-endian u32 limb IS the big-endian message word.
+//     An even row supplies W[0..7], the next row W[8..15]: one compression per two rows, no swaps.
+//   * sha256_final stores the digest as the 8 state words in native u32 (sha256.wgsl:226-228).
+//   * tree nodes are byte strings: node = SHA-256(left.bytes || right.bytes) with the standard
+//     big-endian digest (OpenSSL, include/zkp/hash.hpp:181-187).  In terms of u32 loads:
+//     message word = bswap32(stored word), stored parent word = bswap32(state word), uniformly for
+//     every level (the leaf level's stored words are raw state words).
+#include "kernels.h"
+#include "ntt.cuh"
+
+namespace lgr {
+
+__constant__ uint32_t c_K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+// compile-time copy so the fully unrolled rounds carry K as immediates
+#define LGR_K256_LIST                                                                                  \
+    0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u, \
+    0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u, \
+    0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau, \
+    0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u, \
+    0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u, \
+    0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u, \
+    0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u, \
+    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u
+
+__device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+
+// FIPS 180-4 compression; w[16] is consumed (rolling schedule), all loops unrolled.
+__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+    constexpr uint32_t K[64] = {LGR_K256_LIST};
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        uint32_t wi;
+        if (i < 16) wi = w[i];
+        else {
+            const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+            const uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+            const uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+            wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+            w[i & 15] = wi;
+        }
+        const uint32_t t1 = h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + wi;
+        const uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+// ---- column contexts: state[8][n] | pend[8][n] | rows_lo[n] | rows_hi[n] ----------------------
+__global__ void sha_init_kernel(uint32_t *ctx, int n) {
+    const uint32_t iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { ctx[(size_t)i * n + j] = iv[i]; ctx[(size_t)(8 + i) * n + j] = 0; }
+        ctx[(size_t)16 * n + j] = 0; ctx[(size_t)17 * n + j] = 0;
+    }
+}
+
+__device__ __forceinline__ void load_words(uint32_t *dst, const fr_mem *p) {
+    fr_t x = fr_ldg(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[i] = x.v[i];
+}
+
+// one thread per column; absorbs T rows of a row-major tile (shader/sha256.wgsl:147-177 semantics)
+__global__ void __launch_bounds__(128) sha_update_kernel(uint32_t *ctx, int n, const fr_mem *__restrict__ tile, long long row_stride, int T) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t st[8], w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = ctx[(size_t)i * n + j];
+    const uint32_t rows_lo = ctx[(size_t)16 * n + j], rows_hi = ctx[(size_t)17 * n + j];
+    const fr_mem *col = tile + j;
+    int t = 0;
+    if ((rows_lo & 1u) && T > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = ctx[(size_t)(8 + i) * n + j];
+        load_words(w + 8, col);
+        sha256_compress(st, w);
+        t = 1;
+    }
+    uint32_t nx[16];
+    if (t + 1 < T) { load_words(nx, col + (long long)t * row_stride); load_words(nx + 8, col + (long long)(t + 1) * row_stride); }
+    for (; t + 1 < T; t += 2) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = nx[i];
+        if (t + 3 < T) { load_words(nx, col + (long long)(t + 2) * row_stride); load_words(nx + 8, col + (long long)(t + 3) * row_stride); }
+        sha256_compress(st, w);
+    }
+    if (t < T) {
+        load_words(w, col + (long long)t * row_stride);
+#pragma unroll
+        for (int i = 0; i < 8; i++) ctx[(size_t)(8 + i) * n + j] = w[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) ctx[(size_t)i * n + j] = st[i];
+    const uint32_t lo = rows_lo + (uint32_t)T;
+    ctx[(size_t)16 * n + j] = lo;
+    ctx[(size_t)17 * n + j] = rows_hi + (lo < rows_lo ? 1u : 0u);
+}
+
+// padding + length + digest as native state words (shader/sha256.wgsl:179-230); the context is
+// left untouched so that final is idempotent.
+__global__ void sha_final_kernel(const uint32_t *ctx, int n, uint32_t *digests) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t st[8], w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = ctx[(size_t)i * n + j];
+    const uint32_t rows_lo = ctx[(size_t)16 * n + j], rows_hi = ctx[(size_t)17 * n + j];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = 0;
+    if (rows_lo & 1u) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = ctx[(size_t)(8 + i) * n + j];
+        w[8] = 0x80000000u;
+    } else {
+        w[0] = 0x80000000u;
+    }
+    const unsigned long long rows = ((unsigned long long)rows_hi << 32) | rows_lo;
+    const unsigned long long bits = rows * 256ull;
+    w[14] = (uint32_t)(bits >> 32);
+    w[15] = (uint32_t)bits;
+    sha256_compress(st, w);
+    uint4 *o = reinterpret_cast<uint4 *>(digests + (size_t)8 * j);
+    o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+    o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+
+// ---- Merkle tree ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// parent = SHA-256(left.bytes || right.bytes): data block + constant padding block
+__device__ __forceinline__ void merkle_parent(const uint32_t *left_right /*16 words*/, uint32_t *parent /*8 words*/) {
+    uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    uint32_t w[16];
+    const uint4 *p = reinterpret_cast<const uint4 *>(left_right);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint4 v = p[i];
+        w[4 * i] = bswap32(v.x); w[4 * i + 1] = bswap32(v.y); w[4 * i + 2] = bswap32(v.z); w[4 * i + 3] = bswap32(v.w);
+    }
+    sha256_compress(st, w);
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = 0;
+    w[0] = 0x80000000u; w[15] = 512u;
+    sha256_compress(st, w);
+    uint4 *o = reinterpret_cast<uint4 *>(parent);
+    o[0] = make_uint4(bswap32(st[0]), bswap32(st[1]), bswap32(st[2]), bswap32(st[3]));
+    o[1] = make_uint4(bswap32(st[4]), bswap32(st[5]), bswap32(st[6]), bswap32(st[7]));
+}
+
+// heap layout: the level with `cnt` nodes occupies indices [cnt-1, 2cnt-1)
+__global__ void merkle_level_kernel(uint32_t *nodes, int cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const size_t parent = (size_t)(cnt - 1) + i, child = 2 * parent + 1;
+    merkle_parent(nodes + 8 * child, nodes + 8 * parent);
+}
+// all levels with <= blockDim.x nodes in one CTA
+__global__ void merkle_top_kernel(uint32_t *nodes, int cnt) {
+    for (; cnt >= 1; cnt >>= 1) {
+        if ((int)threadIdx.x < cnt) {
+            const size_t parent = (size_t)(cnt - 1) + threadIdx.x, child = 2 * parent + 1;
+            merkle_parent(nodes + 8 * child, nodes + 8 * parent);
+        }
+        __syncthreads();
+    }
+}
+__global__ void merkle_place_leaves(const uint32_t *leaf, int nleaves, uint32_t *nodes, int P2) {
+    const size_t total = (size_t)P2 * 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        nodes[(size_t)(P2 - 1) * 8 + i] = (i < (size_t)nleaves * 8) ? leaf[i] : 0u;
+}
+
+// ---- synthetic witness (same generator as the oracle's lgo_synth) -------
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long &s) {
+    unsigned long long z = (s += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31);
+}
+__global__ void synth_kernel(fr_mem *out, unsigned long long seed, unsigned long long row0, unsigned long long nrows, unsigned long long ncols) {
+    const unsigned long long total = nrows * ncols;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long r = row0 + i / ncols, c = i % ncols;
+        unsigned long long s = seed * 0xd1342543de82ef95ull + r * 0x2545f4914f6cdd1dull + c * 0x9e3779b97f4a7c15ull + 0x632be59bd9b4e019ull;
+        unsigned long long w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) w[q] = splitmix(s);
+        // finite_field_gmp.hpp:70-78 generate_random: 256 bits >> 2, one conditional subtract
+        w[0] = (w[0] >> 2) | (w[1] << 62); w[1] = (w[1] >> 2) | (w[2] << 62); w[2] = (w[2] >> 2) | (w[3] << 62); w[3] >>= 2;
+        fr_t x;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { x.v[2 * q] = (uint32_t)w[q]; x.v[2 * q + 1] = (uint32_t)(w[q] >> 32); }
+        fr_stg(out + i, fr_reduce_p(x));
+    }
+}
+
+// ---- launchers --------------------------------------------------------------------------------
+cudaError_t launch_sha_init(uint32_t *ctx, int n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    sha_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long long row_stride, int T, cudaStream_t st) {
+    if (n <= 0 || T <= 0) return cudaSuccess;
+    // few columns: one warp per CTA so that every chain gets its own scheduler slot
+    const int threads = (n <= 148 * 4 * 32) ? 32 : 128;
+    sha_update_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(ctx, n, tile, row_stride, T);
+    return cudaGetLastError();
+}
+cudaError_t launch_sha_final(const uint32_t *ctx, int n, uint32_t *digests, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    sha_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(ctx, n, digests);
+    return cudaGetLastError();
+}
+cudaError_t launch_merkle_build(const uint32_t *leaf, int nleaves, uint32_t *nodes, cudaStream_t st) {
+    if (nleaves <= 0) return cudaSuccess;
+    int P2 = 1; while (P2 < nleaves) P2 <<= 1;
+    merkle_place_leaves<<<min(1024, (P2 * 8 + 255) / 256), 256, 0, st>>>(leaf, nleaves, nodes, P2);
+    int cnt = P2 >> 1;
+    for (; cnt > 256; cnt >>= 1) merkle_level_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(nodes, cnt);
+    if (cnt >= 1) merkle_top_kernel<<<1, 256, 0, st>>>(nodes, cnt);
+    return cudaGetLastError();
+}
+cudaError_t launch_synth(fr_mem *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols, cudaStream_t st) {
+    if (nrows * ncols == 0) return cudaSuccess;
+    const unsigned long long total = nrows * ncols;
+    const int grid = (int)((total + 255) / 256 < 148ull * 16 ? (total + 255) / 256 : 148ull * 16);
+    synth_kernel<<<grid, 256, 0, st>>>(out, seed, row0, nrows, ncols);
+    return cudaGetLastError();
+}
+
+}  // namespace lgr

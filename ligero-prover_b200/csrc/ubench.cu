@@ -1,0 +1,85 @@
+// Micro-benchmarks of the two issue-bound primitives ("first deliverable is an
+// IMAD-throughput microbenchmark"): the path is integer-issue-bound, so the honest roofline
+// next to HBM bandwidth is the measured IMAD.WIDE / Montgomery / SHA-256 rate of this part.
+#include "kernels.h"
+#include "ntt.cuh"
+
+namespace lgr {
+
+// 8 independent 32x32+64 multiply-add chains per thread
+__global__ void __launch_bounds__(256) ubench_imad_kernel(uint32_t *out, int iters) {
+    unsigned long long a[8];
+    uint32_t x = threadIdx.x * 2654435761u + 12345u, y = blockIdx.x * 40503u + 977u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = (unsigned long long)(x + i) << 20;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(x), "r"(y));
+        x += 3;
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)s ^ (uint32_t)(s >> 32);
+}
+
+// 4 independent Montgomery multiplications per iteration
+__global__ void __launch_bounds__(256) ubench_mont_kernel(uint32_t *out, int iters) {
+    fr_t x[4], w;
+#pragma unroll
+    for (int i = 0; i < 8; i++) w.v[i] = (threadIdx.x + 1) * 0x9E3779B1u + i * 0x85EBCA77u;
+    w.v[7] &= 0x0FFFFFFFu;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { x[q] = w; x[q].v[0] += q + blockIdx.x; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) x[q] = fr_mont_mul(x[q], w);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) s ^= x[q].v[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__device__ __forceinline__ uint32_t ub_rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+// one dependent SHA-256 compression per iteration (same round structure as sha_kernels.cu)
+__global__ void __launch_bounds__(256) ubench_sha_kernel(uint32_t *out, int iters) {
+    uint32_t st[8], w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = threadIdx.x * 0x01000193u + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = st[i & 7] + i + it;
+        uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            uint32_t wi;
+            if (i < 16) wi = w[i];
+            else {
+                const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                wi = w[i & 15] + (ub_rotr(w15, 7) ^ ub_rotr(w15, 18) ^ (w15 >> 3)) + w[(i + 9) & 15] + (ub_rotr(w2, 17) ^ ub_rotr(w2, 19) ^ (w2 >> 10));
+                w[i & 15] = wi;
+            }
+            const uint32_t t1 = h + (ub_rotr(e, 6) ^ ub_rotr(e, 11) ^ ub_rotr(e, 25)) + ((e & f) ^ (~e & g)) + 0x428a2f98u * (i + 1) + wi;
+            const uint32_t t2 = (ub_rotr(a, 2) ^ ub_rotr(a, 13) ^ ub_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= st[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t launch_ubench(int which, uint32_t *out, int iters, int blocks, int threads, cudaStream_t st) {
+    if (which == 0) ubench_imad_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    else if (which == 1) ubench_mont_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    else ubench_sha_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace lgr

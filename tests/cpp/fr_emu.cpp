@@ -1,0 +1,32 @@
+// Host build of ligero-prover_b200/csrc/fr.cuh with the PTX carry primitives emulated
+// (LGR_FR_HOST_EMU): lets the CPU test-suite check the Montgomery/lazy-reduction algorithm that
+// the CUDA kernels run against the oracle, bit for bit, without a GPU.
+#define LGR_FR_HOST_EMU 1
+#include "../../ligero-prover_b200/csrc/fr.cuh"
+#include <cstddef>
+using namespace lgr;
+extern "C" {
+// out[i] = fr_mont_mul(a[i], b[i]) raw (in [0,2p))
+void emu_mont_mul(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t n, int canon) {
+    for (size_t i = 0; i < n; i++) {
+        fr_t x, y; for (int j = 0; j < 8; j++) { x.v[j] = a[8*i+j]; y.v[j] = b[8*i+j]; }
+        fr_t r = canon ? fr_mont_mul_canon(x, y) : fr_mont_mul(x, y);
+        for (int j = 0; j < 8; j++) out[8*i+j] = r.v[j];
+    }
+}
+void emu_binop(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t n, int op) {
+    for (size_t i = 0; i < n; i++) {
+        fr_t x, y, r; for (int j = 0; j < 8; j++) { x.v[j] = a[8*i+j]; y.v[j] = b[8*i+j]; }
+        switch (op) {
+            case 0: r = fr_add(x, y); break;
+            case 1: r = fr_sub(x, y); break;
+            case 2: r = fr_add_lazy(x, y); break;
+            case 3: r = fr_sub_lazy4(x, y); break;
+            case 4: r = fr_sub_lazy(x, y); break;
+            case 5: r = fr_canon4(x); break;
+            default: r = fr_add_raw(x, y); break;
+        }
+        for (int j = 0; j < 8; j++) out[8*i+j] = r.v[j];
+    }
+}
+}

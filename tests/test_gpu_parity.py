@@ -1,0 +1,446 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle, bit-exact.  Needs a B200."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+P = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_vectors.json")))
+
+
+def rand_elems(oracle, seed, n, ncols=1):
+    return oracle.synth(seed, 0, n, ncols).reshape(n * ncols, 8)
+
+
+def edge_elems(lgr):
+    vals = [0, 1, 2, P - 1, P - 2, (1 << 32) - 1, 1 << 32, (1 << 64) - 1, 1 << 128, (1 << 253) + 12345, P >> 1, 0x0123456789abcdef]
+    return lgr.ints_to_array(vals)
+
+
+# ---------------------------------------------------------------- transforms
+@pytest.mark.parametrize("logn", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16])
+def test_ntt_pow2_forward_inverse(lgr, oracle, executor_factory, logn):
+    ex = executor_factory(256)
+    N = 1 << logn
+    w = lgr.root_of_unity(logn)
+    batch = 3 if logn <= 12 else 1
+    x = rand_elems(oracle, 100 + logn, batch * N).reshape(batch, N, 8)
+    buf = ex.make_device_buffer(batch * N * 32)
+    ex.write_buffer(buf, x)
+    ex.ntt_pow2(buf, logn, batch, w, inverse=False)
+    got = ex.read_elements(buf).reshape(batch, N, 8)
+    want = oracle.ntt_batch(x, w, inverse=False)
+    assert np.array_equal(got, want)
+    ex.ntt_pow2(buf, logn, batch, w, inverse=True)
+    assert np.array_equal(ex.read_elements(buf).reshape(batch, N, 8), x)
+    # inverse alone against the oracle
+    ex.write_buffer(buf, x)
+    ex.ntt_pow2(buf, logn, batch, w, inverse=True)
+    assert np.array_equal(ex.read_elements(buf).reshape(batch, N, 8), oracle.ntt_batch(x, w, inverse=True))
+
+
+def test_config1_ntt_4096_three_way(lgr, oracle, executor_factory):
+    """BASELINE config 1: 2^12-point forward NTT, w = root1^(2^16), seed 1: GPU = oracle = naive DFT"""
+    ex = executor_factory(256)
+    N = 4096
+    w = lgr.root_of_unity(12)
+    assert w == pow(lgr.ROOT1, 1 << 16, P)
+    x = rand_elems(oracle, 1, N)
+    buf = ex.make_device_buffer(N * 32)
+    ex.write_buffer(buf, x)
+    ex.ntt_pow2(buf, 12, 1, w)
+    got = ex.read_elements(buf)
+    assert np.array_equal(got, oracle.ntt(x, w))
+    assert np.array_equal(got, oracle.dft_naive(x, w))
+
+
+def test_ntt_rejects_bad_root(lgr, executor_factory):
+    ex = executor_factory(256)
+    buf = ex.make_device_buffer(16 * 32)
+    with pytest.raises(lgr.LgrError):
+        ex.ntt_pow2(buf, 4, 1, 12345)
+
+
+@pytest.mark.parametrize("k", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_encode_decode_executor_api(lgr, oracle, executor_factory, k):
+    """encode_ntt_device / decode_ntt_device / ntt_*_{k,2k,n} exactly as nonbatch_context.hpp drives them"""
+    ex = executor_factory(k)
+    n = 4 * k
+    row = rand_elems(oracle, 7 + k, k)
+    dev = ex.make_codeword_buffer()
+    bind = ex.bind_ntt(dev)
+    limbs = np.zeros((2 * k, 8), np.uint32)     # nonbatch_context.hpp:415: scratch of 2k elements, upper half zero
+    limbs[:k] = row
+    ex.write_buffer_clear(dev, limbs)
+    ex.encode_ntt_device(bind)
+    cw = ex.read_elements(dev)
+    want = oracle.encode(row, k)
+    assert np.array_equal(cw, want)
+    # decode gives back the message on [0,k) and zero high coefficients (src/webgpu_prover.cpp:465-471)
+    ex.decode_ntt_device(bind)
+    dec = ex.read_elements(dev)
+    assert np.array_equal(dec, oracle.decode(want, k))
+    assert np.array_equal(dec[:k], row)
+    assert not dec[k:].any()
+    # mask-row path: ntt_inverse_2k + ntt_forward_n (nonbatch_context.hpp:482-494)
+    m2 = rand_elems(oracle, 9 + k, 2 * k)
+    ex.write_buffer_clear(dev, m2)
+    ex.ntt_inverse_2k(bind)
+    ex.ntt_forward_n(bind)
+    assert np.array_equal(ex.read_elements(dev), oracle.encode_2k(m2, k))
+    # remaining size selectors round-trip
+    for fwd, inv, size, wsel in ((ex.ntt_forward_k, ex.ntt_inverse_k, k, 0), (ex.ntt_forward_2k, ex.ntt_inverse_2k, 2 * k, 1), (ex.ntt_forward_n, ex.ntt_inverse_n, n, 2)):
+        x = rand_elems(oracle, 11 + size, n)
+        ex.write_buffer(dev, x)
+        fwd(bind)
+        y = ex.read_elements(dev)
+        w = lgr.generate_omegas(k, n)[wsel]
+        assert np.array_equal(y[:size], oracle.ntt(x[:size], w))
+        assert np.array_equal(y[size:], x[size:])
+        inv(bind)
+        assert np.array_equal(ex.read_elements(dev), x)
+
+
+def test_encode_golden_vectors_k8192(lgr, oracle, executor_factory):
+    """SURVEY 8c derived vectors at the reference's default geometry"""
+    k, n = 8192, 32768
+    ex = executor_factory(k)
+    dev = ex.make_codeword_buffer()
+    for name, pos in (("encode_delta0", 0), ("encode_delta1", 1)):
+        row = np.zeros((k, 8), np.uint32)
+        row[pos, 0] = 1
+        ex.write_buffer_clear(dev, row)
+        ex.encode_ntt_device(ex.bind_ntt(dev))
+        e = lgr.array_to_ints(ex.read_elements(dev))
+        g = GOLD[name]
+        assert e[0] == int(g["e0"], 16) and e[1] == int(g["e1"], 16)
+        if "e_last" in g:
+            assert e[-1] == int(g["e_last"], 16)
+
+
+@pytest.mark.parametrize("k,R", [(8, 5), (64, 33), (256, 64), (1024, 9), (4096, 3)])
+def test_encode_rows_batch(lgr, oracle, executor_factory, k, R):
+    ex = executor_factory(k)
+    n = 4 * k
+    rows = oracle.synth(21, 0, R, k)
+    src = ex.make_device_buffer(R * k * 32)
+    dst = ex.make_device_buffer(R * n * 32)
+    ex.write_buffer(src, rows)
+    ex.encode_rows(src, R, dst)
+    got = ex.read_elements(dst).reshape(R, n, 8)
+    for r in range(R):
+        assert np.array_equal(got[r], oracle.encode(rows[r], k)), r
+    # linearity (size-independent property): enc(a) + enc(b) = enc(a + b)
+    a, b = rows[0], rows[1]
+    s = oracle.elt_add(a, b)
+    assert np.array_equal(oracle.elt_add(got[0], got[1]), oracle.encode(s, k))
+
+
+# ---------------------------------------------------------------- hashing
+def test_sha_leaf_golden_and_streaming(lgr, oracle, executor_factory):
+    ex = executor_factory(256)
+    ninst = 1024
+    ex.sha256_init(ninst)
+    ctx = ex.make_device_buffer(ex.sha256_context_bytes(ninst))
+    assert ex.sha256_context_bytes(ninst) <= ninst * 75 * 4        # fits the reference's sha256_context (wgpu.hpp:63-68)
+    dig = ex.make_device_buffer(ninst * 32)
+    cb = ex.bind_sha256_context(ctx, dig)
+    dev = ex.make_codeword_buffer()
+    sb = ex.bind_sha256_buffer(dev)
+    # golden: one row holding the value 1; three rows (1, p-1, 0x0123456789abcdef)
+    ex.sha256_digest_init(cb)
+    ex.write_buffer(dev, lgr.ints_to_array([1] * ninst))
+    ex.sha256_digest_update(cb, sb)
+    ex.sha256_digest_final(cb)
+    d = ex.copy_to_host(dig, np.uint8).reshape(ninst, 32)
+    assert d[0].tobytes().hex() == GOLD["leaf_one_row_value_1"] and (d == d[0]).all()
+    ex.sha256_digest_init(cb)
+    for v in (1, P - 1, 0x0123456789abcdef):
+        ex.write_buffer(dev, lgr.ints_to_array([v] * ninst))
+        ex.sha256_digest_update(cb, sb)
+    ex.sha256_digest_final(cb)
+    d3 = ex.copy_to_host(dig, np.uint8).reshape(ninst, 32)
+    assert d3[5].tobytes().hex() == GOLD["leaf_three_rows"]["digest"]
+    # empty stream (0 rows) = SHA-256("") with swapped words
+    ex.sha256_digest_init(cb)
+    ex.sha256_digest_final(cb)
+    s = oracle.Sha(ninst)
+    assert np.array_equal(ex.copy_to_host(dig, np.uint8).reshape(ninst, 32), s.final())
+    # random rows, ragged update sizes (1 row, then tiles of odd/even length), final is idempotent
+    R = 23
+    rows = oracle.synth(5, 0, R, ninst)
+    tile = ex.make_device_buffer(R * ninst * 32)
+    ex.write_buffer(tile, rows)
+    ex.sha256_digest_init(cb)
+    s = oracle.Sha(ninst)
+    pos = 0
+    for chunk in (1, 2, 3, 1, 4, 5, 7):
+        ex.sha256_digest_update_rows(cb, tile.slice(pos * ninst * 32), chunk)
+        for r in range(pos, pos + chunk):
+            s.update(rows[r])
+        pos += chunk
+        ex.sha256_digest_final(cb)
+        assert np.array_equal(ex.copy_to_host(dig, np.uint8).reshape(ninst, 32), s.final()), pos
+    assert pos == R
+
+
+@pytest.mark.parametrize("nleaves", [1, 2, 3, 8, 192, 1024, 1025, 4096, 32768])
+def test_merkle_build(lgr, oracle, executor_factory, nleaves):
+    ex = executor_factory(256)
+    rng = np.random.default_rng(nleaves)
+    leaves = rng.integers(0, 256, size=(nleaves, 32), dtype=np.uint8)
+    d = ex.make_device_buffer(nleaves * 32)
+    ex.write_buffer(d, leaves)
+    nn = ex.merkle_node_count(nleaves)
+    nodes = ex.make_device_buffer(nn * 32)
+    ex.merkle_build(d, nleaves, nodes)
+    got = ex.copy_to_host(nodes, np.uint8).reshape(nn, 32)
+    assert np.array_equal(got, oracle.merkle_build(leaves))
+
+
+def test_merkle_golden_parent(lgr, executor_factory):
+    ex = executor_factory(256)
+    leaves = np.frombuffer(bytes.fromhex(GOLD["leaf_one_row_value_1"] + GOLD["leaf_three_rows"]["digest"]), np.uint8).reshape(2, 32)
+    d = ex.make_device_buffer(64)
+    ex.write_buffer(d, leaves)
+    nodes = ex.make_device_buffer(3 * 32)
+    ex.merkle_build(d, 2, nodes)
+    assert ex.copy_to_host(nodes, np.uint8)[:32].tobytes().hex() == GOLD["parent_of_the_two"]
+
+
+@pytest.mark.parametrize("k,R", [(8, 1), (8, 6), (64, 17), (256, 100), (256, 4100), (1024, 5), (4096, 4)])
+def test_encode_commit_pipeline(lgr, oracle, executor_factory, k, R):
+    """stage-1 commit (nonbatch_context.hpp:445-451,555-558 + merkle_tree.hpp:343-375)"""
+    ex = executor_factory(k)
+    n = 4 * k
+    rows = oracle.synth(3, 0, R, k)
+    src = ex.make_device_buffer(R * k * 32)
+    ex.write_buffer(src, rows)
+    dig = ex.make_device_buffer(n * 32)
+    nodes = ex.make_device_buffer((2 * n - 1) * 32)
+    ex.encode_commit(src, R, dig, nodes)
+    want_d, want_n, _ = oracle.encode_commit(rows, k)
+    assert np.array_equal(ex.copy_to_host(dig, np.uint8).reshape(n, 32), want_d)
+    assert np.array_equal(ex.copy_to_host(nodes, np.uint8).reshape(2 * n - 1, 32), want_n)
+    # run again on the same context: identical result (buffers / contexts are re-initialised)
+    ex.encode_commit(src, R, dig, nodes)
+    assert np.array_equal(ex.copy_to_host(nodes, np.uint8).reshape(2 * n - 1, 32), want_n)
+
+
+def test_synth_matches_oracle(lgr, oracle, executor_factory):
+    ex = executor_factory(256)
+    buf = ex.make_device_buffer(37 * 256 * 32)
+    ex.synth(buf, 3, 1000, 37, 256)
+    assert np.array_equal(ex.read_elements(buf).reshape(37, 256, 8), oracle.synth(3, 1000, 37, 256))
+
+
+# ---------------------------------------------------------------- element-wise / combiners
+def test_eltwise_all_ops(lgr, oracle, executor_factory):
+    ex = executor_factory(256)
+    n = 1024
+    edge = edge_elems(lgr)
+    x = rand_elems(oracle, 31, n); y = rand_elems(oracle, 32, n); z = rand_elems(oracle, 33, n)
+    ne = len(edge)
+    x[:ne] = edge; y[:ne] = edge[::-1]
+    x[ne:2 * ne] = edge; y[ne:2 * ne] = edge            # squares / x - x
+    bx, by, bz, bo = (ex.make_codeword_buffer() for _ in range(4))
+    ex.write_buffer(bx, x); ex.write_buffer(by, y); ex.write_buffer(bz, z)
+    b3 = ex.bind_eltwise3(bx, by, bo)
+    b2 = ex.bind_eltwise2(bx, bo)
+    c = 0x2f0b1c0ffee123456789abcdef0123456789abcdef0123456789abcdef012345 % P
+
+    def out():
+        return ex.read_elements(bo)
+
+    ex.EltwiseAddMod(b3); assert np.array_equal(out(), oracle.elt_add(x, y))
+    ex.EltwiseSubMod(b3); assert np.array_equal(out(), oracle.elt_sub(x, y))
+    ex.EltwiseMultMod(b3); assert np.array_equal(out(), oracle.elt_mul(x, y))
+    ex.write_buffer(bo, z); ex.EltwiseFMAMod(b3); assert np.array_equal(out(), oracle.elt_fma(z, x, y))
+    for cc in (c, 0, 1, P - 1):
+        ex.write_buffer(bo, z); ex.EltwiseFMAMod(b2, cc); assert np.array_equal(out(), oracle.elt_fma_const(z, x, cc))
+        ex.EltwiseAddMod(b2, cc); assert np.array_equal(out(), oracle.elt_add_const(x, cc))
+        ex.EltwiseSubConstMod(b2, cc); assert np.array_equal(out(), oracle.elt_sub_const(x, cc))
+        ex.EltwiseConstSubMod(b2, cc); assert np.array_equal(out(), oracle.elt_const_sub(x, cc))
+        ex.EltwiseMultMod(b2, cc); assert np.array_equal(out(), oracle.elt_mul_const(x, cc))
+        ex.EltwiseMontMultMod(b2, cc); assert np.array_equal(out(), oracle.elt_montmul_const(x, cc))
+    ex.write_buffer(bo, z); ex.EltwiseAddAssignMod(b2); assert np.array_equal(out(), oracle.elt_add_assign(z, x))
+    for bit in (0, 1, 31, 32, 63, 100, 253, 255):
+        ex.EltwiseBitDecompose(b2, bit); assert np.array_equal(out(), oracle.elt_bit(x, bit))
+    # in-place variants used by the reference (bind_eltwise3(tmp1, z, tmp2) etc. alias freely)
+    ex.write_buffer(bo, z)
+    ex.EltwiseAddMod(ex.bind_eltwise3(bo, bx, bo)); assert np.array_equal(out(), oracle.elt_add(z, x))
+    # scalar must be reduced
+    with pytest.raises(lgr.LgrError):
+        ex.EltwiseFMAMod(b2, P)
+    # fused check_quadratic = Mult, Sub, FMA-const of the reference (nonbatch_context.hpp:771-780)
+    ex.write_buffer(bo, z)
+    ex.quadratic_fused(bx, by, bz, bo, c)
+    want = oracle.elt_fma_const(z, oracle.elt_sub(oracle.elt_mul(x, y), z), c)
+    assert np.array_equal(out(), want)
+    # element offsets (vbn254fr arena addressing, vbn254fr.hpp:56-66)
+    ex.EltwiseAddMod(b3, element_offsets=(8, 16, 24), count=100)
+    assert np.array_equal(out()[24:124], oracle.elt_add(x[8:108], y[16:116]))
+
+
+def test_eltwise_div(lgr, oracle, executor_factory):
+    ex = executor_factory(256)
+    n = 1024
+    x = rand_elems(oracle, 41, n); y = rand_elems(oracle, 42, n)
+    y[:3] = lgr.ints_to_array([0, 1, P - 1])
+    bx, by, bo = (ex.make_codeword_buffer() for _ in range(3))
+    ex.write_buffer(bx, x); ex.write_buffer(by, y)
+    ex.EltwiseDivMod(ex.bind_eltwise3(bx, by, bo))
+    assert np.array_equal(ex.read_elements(bo), oracle.elt_div(x, y))
+
+
+@pytest.mark.parametrize("base", [1, 7, P - 1, 0x1234567890abcdef1234567890abcdef])
+def test_powmod_kat(lgr, oracle, executor_factory, base):
+    """the reference's only device KAT: tests/webgpu/test_powmod.cpp:50-197 -- coeff*base^exp vs
+    mpz_powm_ui for 8192 lanes, bases 1, 7, p-1 (here checked against Python's pow)"""
+    ex = executor_factory(256)
+    n = 8192
+    rng = random.Random(base & 0xffff)
+    exps = [0, 1, 2, 0xFFFFFFFF, 0x80000000] + [rng.getrandbits(32) for _ in range(n - 5)]
+    coeffs = [1, 0, P - 1] + [rng.randrange(P) for _ in range(n - 3)]
+    be = ex.make_device_buffer(n * 4); bc = ex.make_device_buffer(n * 32); bo = ex.make_device_buffer(n * 32)
+    ex.write_buffer(be, np.array(exps, np.uint32)); ex.write_buffer(bc, lgr.ints_to_array(coeffs))
+    ex.powmod_init(32); ex.powmod_set_base(base)
+    bind = ex.bind_powmod(be, bc, bo)
+    ex.EltwisePowMod(bind)
+    want = [c * pow(base, e, P) % P for c, e in zip(coeffs, exps)]
+    assert lgr.array_to_ints(ex.read_elements(bo)) == want
+    ex.EltwisePowAddMod(bind)
+    assert lgr.array_to_ints(ex.read_elements(bo)) == [2 * w % P for w in want]
+    assert np.array_equal(ex.read_elements(bo), oracle.elt_powmod(lgr.ints_to_array(coeffs), exps, base, out=lgr.ints_to_array(want)))
+
+
+def test_sample_gather(lgr, oracle, executor_factory):
+    ex = executor_factory(256)
+    n = 1024
+    rng = random.Random(9)
+    idx = sorted(rng.sample(range(n), 192))
+    ex.sampling_init(idx)
+    x = rand_elems(oracle, 51, n)
+    bx = ex.make_codeword_buffer(); ex.write_buffer(bx, x)
+    stage = ex.make_device_buffer(256 * 192 * 32)             # nonbatch_context.hpp:906-909
+    bind = ex.bind_sampling(bx, stage)
+    ex.sample_gather(bind, 0); ex.sample_gather(bind, 3)
+    got = ex.read_elements(stage).reshape(256, 192, 8)
+    want = oracle.gather(x, idx)
+    assert np.array_equal(got[0], want) and np.array_equal(got[3], want) and not got[1].any()
+
+
+@pytest.mark.parametrize("k,T", [(64, 1), (64, 31), (256, 32), (256, 77)])
+def test_tile_combiners(lgr, oracle, executor_factory, k, T):
+    """check_code / check_linear over a resident tile == the reference's per-row schedule"""
+    ex = executor_factory(k)
+    n = 4 * k
+    a = oracle.synth(61, 0, T, n); b = oracle.synth(62, 0, T, n)
+    acc0 = rand_elems(oracle, 63, n)
+    rng = random.Random(T)
+    rs = [0, 1, P - 1][: min(3, T)] + [rng.randrange(P) for _ in range(max(0, T - 3))]
+    ta = ex.make_device_buffer(T * n * 32); tb = ex.make_device_buffer(T * n * 32); acc = ex.make_codeword_buffer()
+    ex.write_buffer(ta, a); ex.write_buffer(tb, b)
+    ex.write_buffer(acc, acc0)
+    ex.combine_code(ta, T, rs, acc)
+    want = acc0.copy()
+    for t in range(T):
+        want = oracle.elt_fma_const(want, a[t], rs[t])
+    assert np.array_equal(ex.read_elements(acc), want)
+    ex.write_buffer(acc, acc0)
+    ex.combine_linear(ta, tb, T, acc)
+    want = acc0.copy()
+    for t in range(T):
+        want = oracle.elt_fma(want, a[t], b[t])
+    assert np.array_equal(ex.read_elements(acc), want)
+
+
+# ---------------------------------------------------------------- the reference's stage schedule
+def test_stage1_stage2_schedule_like_nonbatch_context(lgr, oracle, executor_factory):
+    """Drive the executor exactly as nonbatch_stage1_context / nonbatch_stage2_context do for one
+    linear row, one quadratic triple and the three mask rows (BASELINE config 4's row schedule:
+    7 encodes per stage), and compare root / code / linear / quad with the oracle."""
+    k = 512; n = 4 * k; l = k - 192
+    ex = executor_factory(k)
+    rng = random.Random(4)
+
+    def row(seed, size=k):
+        return rand_elems(oracle, seed, size)
+
+    lin, lin_r = row(70), row(71)
+    X, Y = row(72), row(73)
+    Z = oracle.elt_mul(X, Y)
+    xr, yr, zr = row(74), row(75), row(76)
+    mask_c = row(77); mask_l = row(78, 2 * k); mask_q = row(79, 2 * k)
+    r_code = [rng.randrange(P) for _ in range(4)]; r_quad = rng.randrange(P)
+
+    # ---- stage 1 (nonbatch_context.hpp:445-494,555-558)
+    ex.sha256_init(n)
+    dx, dy, dz = (ex.make_codeword_buffer() for _ in range(3))
+    sctx = ex.make_device_buffer(ex.sha256_context_bytes(n)); sdig = ex.make_device_buffer(n * 32)
+    cb = ex.bind_sha256_context(sctx, sdig)
+    ex.sha256_digest_init(cb)
+    limbs = np.zeros((2 * k, 8), np.uint32)
+
+    def upload(dev, vals):
+        limbs[:] = 0; limbs[: vals.shape[0]] = vals
+        ex.write_buffer_clear(dev, limbs)
+
+    for dev, vals in ((dx, lin), (dx, X), (dy, Y), (dz, Z)):
+        upload(dev, vals); ex.encode_ntt_device(ex.bind_ntt(dev)); ex.sha256_digest_update(cb, ex.bind_sha256_buffer(dev))
+    upload(dx, mask_c); ex.encode_ntt_device(ex.bind_ntt(dx)); ex.sha256_digest_update(cb, ex.bind_sha256_buffer(dx))
+    for dev, vals in ((dy, mask_l), (dz, mask_q)):
+        upload(dev, vals); ex.ntt_inverse_2k(ex.bind_ntt(dev)); ex.ntt_forward_n(ex.bind_ntt(dev)); ex.sha256_digest_update(cb, ex.bind_sha256_buffer(dev))
+    ex.sha256_digest_final(cb)
+    nodes = ex.make_device_buffer((2 * n - 1) * 32)
+    ex.merkle_build(sdig, n, nodes)
+    root = ex.copy_to_host(nodes, np.uint8)[:32]
+
+    enc = lambda v: oracle.encode(v, k)
+    enc2 = lambda v: oracle.encode_2k(v, k)
+    cws = [enc(lin), enc(X), enc(Y), enc(Z), enc(mask_c), enc2(mask_l), enc2(mask_q)]
+    s = oracle.Sha(n)
+    for cw in cws:
+        s.update(cw)
+    assert np.array_equal(root, oracle.merkle_build(s.final())[0])
+
+    # ---- stage 2 (nonbatch_context.hpp:654-780)
+    code, linear, quad, tmp1, tmp2 = (ex.make_codeword_buffer() for _ in range(5))
+    drx, dry, drz = (ex.make_codeword_buffer() for _ in range(3))
+    upload(dx, lin); upload(drx, lin_r)
+    ex.encode_ntt_device(ex.bind_ntt(dx)); ex.encode_ntt_device(ex.bind_ntt(drx))
+    ex.EltwiseFMAMod(ex.bind_eltwise2(dx, code), r_code[0])
+    ex.EltwiseFMAMod(ex.bind_eltwise3(dx, drx, linear))
+    for dev, vals in ((dx, X), (drx, xr), (dy, Y), (dry, yr), (dz, Z), (drz, zr)):
+        upload(dev, vals); ex.encode_ntt_device(ex.bind_ntt(dev))
+    for dev, r in ((dx, r_code[1]), (dy, r_code[2]), (dz, r_code[3])):
+        ex.EltwiseFMAMod(ex.bind_eltwise2(dev, code), r)
+    for dev, rnd in ((dx, drx), (dy, dry), (dz, drz)):
+        ex.EltwiseFMAMod(ex.bind_eltwise3(dev, rnd, linear))
+    ex.EltwiseMultMod(ex.bind_eltwise3(dx, dy, tmp1)); ex.EltwiseSubMod(ex.bind_eltwise3(tmp1, dz, tmp2)); ex.EltwiseFMAMod(ex.bind_eltwise2(tmp2, quad), r_quad)
+    upload(dx, mask_c); ex.encode_ntt_device(ex.bind_ntt(dx)); ex.EltwiseAddAssignMod(ex.bind_eltwise2(dx, code))
+    upload(dy, mask_l); ex.ntt_inverse_2k(ex.bind_ntt(dy)); ex.ntt_forward_n(ex.bind_ntt(dy)); ex.EltwiseAddAssignMod(ex.bind_eltwise2(dy, linear))
+    upload(dz, mask_q); ex.ntt_inverse_2k(ex.bind_ntt(dz)); ex.ntt_forward_n(ex.bind_ntt(dz)); ex.EltwiseAddAssignMod(ex.bind_eltwise2(dz, quad))
+
+    zero = np.zeros((n, 8), np.uint32)
+    w_code = zero
+    for cw, r in zip(cws[:4], r_code):
+        w_code = oracle.elt_fma_const(w_code, cw, r)
+    w_code = oracle.elt_add_assign(w_code, cws[4])
+    w_lin = zero
+    for cw, rnd in zip(cws[:4], (lin_r, xr, yr, zr)):
+        w_lin = oracle.elt_fma(w_lin, cw, enc(rnd))
+    w_lin = oracle.elt_add_assign(w_lin, cws[5])
+    w_quad = oracle.elt_fma_const(zero, oracle.elt_sub(oracle.elt_mul(cws[1], cws[2]), cws[3]), r_quad)
+    w_quad = oracle.elt_add_assign(w_quad, cws[6])
+    assert np.array_equal(ex.read_elements(code), w_code)
+    assert np.array_equal(ex.read_elements(linear), w_lin)
+    assert np.array_equal(ex.read_elements(quad), w_quad)
+    # prover self-checks (src/webgpu_prover.cpp:465-471): code decodes to degree < k; the quadratic
+    # test polynomial (degree < 2k) vanishes on the first k points before the mask is added
+    ex.decode_ntt_device(ex.bind_ntt(code))
+    assert not ex.read_elements(code)[k:].any()
