@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Ligero hot path.
+
+Metric (BASELINE.json): witness Fr-elements/sec (encode+commit).
+Workload at N=1: BASELINE config 3 -- Ligero encode + SHA-256 Merkle commit of a synthetic
+R = 2^22 rows x k = 256 message columns witness (n = 4k = 1024 codeword columns), BN254 Fr,
+32 GiB resident in HBM, seed 3 (uniform canonical elements, finite_field_gmp.hpp:70-78).
+One "step" = one full commit of the witness: every row Reed-Solomon encoded (iNTT_k -> NTT_4k),
+every codeword column SHA-256 hashed over all rows in order, Merkle tree over the n leaves.
+
+  value : elements/s with the witness already resident in HBM (device time, CUDA events)
+  e2e   : same metric through the C-ABI call lgr_encode_commit_host with HOST (pinned) rows:
+          H2D of every tile and D2H of the root inside the timed region
+  N > 1 : one process per GPU, each commits its own R-row shard (weak scaling); the n leaf digests
+          of every shard are all-gathered over NCCL and every rank builds the tree over the G*n
+          leaves (DESIGN.md "Multi-GPU").  value = G*R*k / max-over-ranks device time.
+
+`--impl reference` times the CPU oracle (the reference has no CPU implementation of this path and
+cannot be built here -- DESIGN.md "Oracle") on the host cores, on a bounded sample of the same
+workload.  Only that leg and the cpu_baseline leg touch oracle/.
+"""
+import argparse
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "witness Fr-elements/sec (encode+commit)"
+UNIT = "elements/s"
+K = 256
+LOG_ROWS = 22
+SEED = 3
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_package():
+    if "ligero_prover_b200" in sys.modules:
+        return sys.modules["ligero_prover_b200"]
+    path = os.path.join(ROOT, "ligero-prover_b200", "__init__.py")
+    spec = importlib.util.spec_from_file_location("ligero_prover_b200", path, submodule_search_locations=[os.path.dirname(path)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ligero_prover_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(target_seconds, k=K):
+    """CPU oracle (oracle/liblgo.so, OpenMP over all host cores) on a bounded sample of the workload"""
+    from oracle import lgo
+    lgo.build()
+    cores = lgo.num_threads()
+    t0 = time.perf_counter()
+    lgo.encode_commit_synth(SEED, 1 << 11, k)              # calibration: 2^11 rows
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rows = int((1 << 11) * target_seconds / dt)
+    rows = max(1 << 11, min(rows, 1 << LOG_ROWS))
+    rows = 1 << (rows.bit_length() - 1)
+    t0 = time.perf_counter()
+    lgo.encode_commit_synth(SEED, rows, k)
+    dt = time.perf_counter() - t0
+    return rows * k / dt, cores, rows, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    cores = rows = 0
+    for i in range(args.warmup + args.steps):
+        v, cores, rows, dt = cpu_reference_rate(per_step)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = statistics.mean(v for v, _ in vals)
+    ms = statistics.mean(dt for _, dt in vals) * 1e3
+    sample = "oracle encode+commit of 2^%d rows x k=%d (seed %d) per step, OpenMP" % (rows.bit_length() - 1, K, SEED)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "ligero encode+commit, R=2^%d rows x k=%d (n=%d), BN254 Fr" % (LOG_ROWS, K, 4 * K), "sample_rows_per_step": rows,
+                   "note": "reference has no CPU path for these kernels and cannot be built here; this is the CPU oracle port"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-rows", type=int, default=LOG_ROWS, help="rows per GPU = 2^log_rows (default: BASELINE config 3)")
+    ap.add_argument("--k", type=int, default=K)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--aux", action="store_true", help="also time the reference's default geometry k=8192 and the 2^20 NTT (extra keys)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; the hot path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lgr = load_package()
+    k, n = args.k, 4 * args.k
+    R = 1 << args.log_rows
+    dev = torch.device("cuda", local_rank)
+
+    ex = lgr.Executor(local_rank)
+    ex.ntt_init(max(k - 192, 1), k, n)
+    stream = torch.cuda.Stream(device=dev)
+    peaks, peak_src = measured_peaks()
+
+    with torch.cuda.stream(stream):
+        ex.use_torch_stream()
+        witness = torch.empty(R * k * 8, dtype=torch.int32, device=dev)          # [R][k][8] u32
+        wbuf = ex.wrap(witness)
+        ex.synth(wbuf, SEED, rank * R, R, k)                                     # shard `rank` of the global matrix
+        digests = ex.make_device_buffer(n * 32)
+        nleaves = world * n
+        nodes = ex.make_device_buffer(ex.merkle_node_count(nleaves) * 32)
+        gathered = torch.empty(world * n * 8, dtype=torch.int32, device=dev) if world > 1 else None
+
+        def step():
+            if world == 1:
+                ex.encode_commit(wbuf, R, digests, nodes)
+            else:
+                ex.encode_commit(wbuf, R, digests, None)
+                dist.all_gather_into_tensor(gathered, digests.storage[: n * 8])
+                ex.merkle_build(ex.wrap(gathered), nleaves, nodes)
+
+        def sync_all():
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        for _ in range(args.warmup):
+            step()
+        sync_all()
+        ex.profile(True)
+        l0 = ex.launch_count()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        sync_all()
+        clocks = sampler.stop() if rank == 0 else {}
+        ms_total = e0.elapsed_time(e1)
+        launches = ex.launch_count() - l0 + (args.steps if world > 1 else 0)
+        prof = ex.profile_read()
+        ex.profile(False)
+        root = ex.copy_to_host(nodes, np.uint8)[:32].tobytes().hex()
+
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        ms_step = ms_total / args.steps
+        value = world * R * k / (ms_step * 1e-3)
+
+        # ---- end to end: host-resident rows through lgr_encode_commit_host -------------------------
+        e2e = None
+        if not args.no_e2e:
+            need = R * k * 32
+            avail = mem_available_bytes()
+            e2e_rows = R
+            while e2e_rows * k * 32 > max(avail - (8 << 30), 0) * 0.8 // max(world, 1) and e2e_rows > (1 << 12):
+                e2e_rows >>= 1
+            host = torch.empty(e2e_rows * k * 8, dtype=torch.int32, pin_memory=True)
+            host.copy_(witness[: e2e_rows * k * 8])
+            stream.synchronize()
+            root_e2e = None
+            for _ in range(min(args.warmup, 1)):
+                _, root_e2e = ex.encode_commit_host(host, e2e_rows)
+            sync_all()
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(args.steps):
+                _, root_e2e = ex.encode_commit_host(host, e2e_rows)          # blocking: root is on the host on return
+            e1.record(stream)
+            sync_all()
+            wall = (time.perf_counter() - t0) * 1e3
+            te = torch.tensor([max(wall, e0.elapsed_time(e1))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e_ms = float(te.item()) / args.steps
+            e2e = {"value": world * e2e_rows * k / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_rows * k * 32,
+                   "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms, "rows_per_gpu": e2e_rows,
+                   "root_matches_device_path": (root_e2e.hex() == root) if (e2e_rows == R and world == 1) else None}
+            del host
+
+        # ---- roofline of the kernel on the critical path + the other kernel of the step ------------
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        kern = {}
+        if prof["encode_launches"]:
+            per = prof["encode_ms"] / prof["encode_launches"]
+            rows_per_launch = R * args.steps / prof["encode_launches"]
+            by = rows_per_launch * (k + n) * 32                                  # read k, write n elements per row
+            kern["encode_rows_kernel"] = {"ms_per_launch": per, "launches": prof["encode_launches"], "algorithmic_bytes_per_launch": by,
+                                          "achieved_gbs": by / (per * 1e-3) / 1e9, "frac_hbm": by / (per * 1e-3) / 1e9 / hbm,
+                                          "share_of_step": prof["encode_ms"] / (ms_step * args.steps)}
+        if prof["sha_launches"]:
+            per = prof["sha_ms"] / prof["sha_launches"]
+            rows_per_launch = R * args.steps / prof["sha_launches"]
+            by = rows_per_launch * n * 32                                        # every codeword element read once
+            kern["sha_update_kernel"] = {"ms_per_launch": per, "launches": prof["sha_launches"], "algorithmic_bytes_per_launch": by,
+                                         "achieved_gbs": by / (per * 1e-3) / 1e9, "frac_hbm": by / (per * 1e-3) / 1e9 / hbm,
+                                         "share_of_step": prof["sha_ms"] / (ms_step * args.steps)}
+        dominant = max(kern, key=lambda kk: kern[kk]["share_of_step"]) if kern else None
+        roofline = None
+        if dominant:
+            d = kern[dominant]
+            roofline = {"kernel": dominant, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": hbm, "unit": "GB/s", "frac": d["frac_hbm"],
+                        "traffic": None, "peak_source": peak_src,
+                        "path_bytes_per_element": 32, "path_achieved": value / world * 32 / 1e9, "path_frac": value / world * 32 / 1e9 / hbm,
+                        "note": "integer-issue bound path: see int_roofline and DESIGN.md"}
+        ub = {"imad_wide_per_s": ex.ubench(0), "montmul_per_s": ex.ubench(1), "sha256_compress_per_s": ex.ubench(2)}
+        import math
+        mm_per_elem = (math.log2(k) - 1) / 2 + 4 + 4 * (math.log2(k) - 1) / 2
+        int_roofline = {"measured": ub, "montmul_per_element": mm_per_elem, "sha_compress_per_element": 2,
+                        "throughput_bound_elements_per_s": 1.0 / (mm_per_elem / ub["montmul_per_s"] + 2.0 / ub["sha256_compress_per_s"]),
+                        "frac": (value / world) / (1.0 / (mm_per_elem / ub["montmul_per_s"] + 2.0 / ub["sha256_compress_per_s"]))}
+
+        aux = {}
+        if args.aux and world == 1:
+            aux = run_aux(lgr, torch, dev, stream, hbm)
+
+    # ---- CPU baseline: rank 0, N = 1 only ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, rows, dt = cpu_reference_rate(12.0, k)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "oracle encode+commit of 2^%d rows x k=%d, seed %d, %.1f s, OpenMP threads=%d" % (rows.bit_length() - 1, k, SEED, dt, cores)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "ligero encode+commit, R=2^%d rows x k=%d (n=%d) per GPU, BN254 Fr, seed %d" % (args.log_rows, k, n, SEED),
+                       "rows_per_gpu": R, "k": k, "n": n, "l2": "inputs (%.0f GiB per GPU) larger than L2 (126 MB); no flush needed" % (R * k * 32 / 2**30),
+                       "parallelism": "rows sharded over %d GPU(s); digests all-gathered (NCCL) for the tree" % world},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kern, "int_roofline": int_roofline,
+            "cpu_baseline": cpu, "root": root,
+        }
+        if aux:
+            line["aux"] = aux
+        print(json.dumps(line), flush=True)
+    ex.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_aux(lgr, torch, dev, stream, hbm):
+    """extra measurements (not the headline): reference default geometry and BASELINE config 2"""
+    out = {}
+    # reference default geometry k = 8192, n = 32768 (include/params.hpp:24-32), 2^14 rows = 4 GiB
+    k, R = 8192, 1 << 14
+    ex = lgr.Executor(dev.index)
+    ex.ntt_init(k - 192, k, 4 * k)
+    ex.use_torch_stream()
+    w = torch.empty(R * k * 8, dtype=torch.int32, device=dev)
+    wb = ex.wrap(w)
+    ex.synth(wb, 5, 0, R, k)
+    dig = ex.make_device_buffer(4 * k * 32); nodes = ex.make_device_buffer((8 * k - 1) * 32)
+    for _ in range(2):
+        ex.encode_commit(wb, R, dig, nodes)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream.synchronize(); e0.record(stream)
+    for _ in range(3):
+        ex.encode_commit(wb, R, dig, nodes)
+    e1.record(stream); stream.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out["encode_commit_k8192"] = {"rows": R, "k": k, "ms_per_step": ms, "elements_per_s": R * k / (ms * 1e-3)}
+    # BASELINE config 2: 2^20-point NTT then iNTT, 64 MiB algorithmic bytes per transform
+    logn = 20
+    buf = ex.make_device_buffer((1 << logn) * 32)
+    ex.synth(buf, 2, 0, 1, 1 << logn)
+    wroot = lgr.root_of_unity(logn)
+    for _ in range(3):
+        ex.ntt_pow2(buf, logn, 1, wroot, False); ex.ntt_pow2(buf, logn, 1, wroot, True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tf = ti = 0.0
+    for _ in range(5):
+        flush.fill_(1); e0.record(stream); ex.ntt_pow2(buf, logn, 1, wroot, False); e1.record(stream); stream.synchronize(); tf += e0.elapsed_time(e1)
+        flush.fill_(2); e0.record(stream); ex.ntt_pow2(buf, logn, 1, wroot, True); e1.record(stream); stream.synchronize(); ti += e0.elapsed_time(e1)
+    by = 2 * (1 << logn) * 32
+    for name, tms in (("ntt_2^20_forward", tf / 5), ("ntt_2^20_inverse", ti / 5)):
+        out[name] = {"ms": tms, "algorithmic_bytes": by, "achieved_gbs": by / (tms * 1e-3) / 1e9, "frac_hbm": by / (tms * 1e-3) / 1e9 / hbm, "l2": "flushed (256 MiB write) before each timed launch"}
+    ex.close()
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

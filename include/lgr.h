@@ -132,6 +132,15 @@ int lgr_encode_rows(lgr_ctx *ctx, const void *rows, uint64_t row_stride_elems, u
  * (nonbatch_context.hpp:555-558, merkle_tree.hpp:343-375).  digests: n*32 B; nodes: (2n-1)*32 B or NULL.
  * Encoding of tile t+1 overlaps hashing of tile t on a second stream. */
 int lgr_encode_commit(lgr_ctx *ctx, const void *rows, uint64_t nrows, void *digests, void *nodes);
+/* same pipeline for a HOST-resident witness (pinned memory recommended): rows are copied tile by
+ * tile on a third stream (H2D of tile t+2, encode of tile t+1 and hashing of tile t overlap), the
+ * n digests (may be NULL) and the 32-byte root come back to the host; blocking.  This is the call
+ * behind bench.py's "e2e" figure. */
+int lgr_encode_commit_host(lgr_ctx *ctx, const void *host_rows, uint64_t nrows, void *host_digests, void *host_root);
+/* per-kernel device timing of the commit pipeline: CUDA events on the launching streams around
+ * every encode / hash-update launch.  lgr_profile_read drains the totals (ms) and launch counts. */
+int lgr_profile(lgr_ctx *ctx, int enable);
+int lgr_profile_read(lgr_ctx *ctx, double *encode_ms, uint64_t *encode_launches, double *sha_ms, uint64_t *sha_launches);
 /* check_code over a resident tile of nrows codewords: acc[j] += sum_t r[t]*tile[t][j]
  * (nonbatch_context.hpp:756-763); host_r = nrows x 8 u32 canonical scalars */
 int lgr_combine_code(lgr_ctx *ctx, const void *tile, uint32_t nrows, const uint32_t *host_r, void *acc);

@@ -183,7 +183,9 @@ class Executor:
     def use_torch_stream(self):
         """enqueue on torch's current CUDA stream so tensors produced by torch are ordered correctly"""
         s = self._torch.cuda.current_stream(self._device).cuda_stream
-        _check(lib().lgr_set_stream(self._ctx, C.c_void_p(s)))
+        # handle 0 is the legacy default stream: pass cudaStreamLegacy (0x1) explicitly, NULL would
+        # select the context's own stream
+        _check(lib().lgr_set_stream(self._ctx, C.c_void_p(s if s else 1)))
 
     def close(self):
         if self._ctx is not None:
@@ -453,6 +455,24 @@ class Executor:
 
     def encode_commit(self, rows, nrows, digests, nodes=None):
         _check(lib().lgr_encode_commit(self._ctx, rows.ptr(), C.c_uint64(nrows), digests.ptr(), nodes.ptr() if nodes is not None else None))
+
+    def encode_commit_host(self, host_rows, nrows, want_digests=False):
+        """host-resident witness (numpy array or pinned torch tensor) -> (digests or None, root bytes)"""
+        ptr = host_rows.ctypes.data if isinstance(host_rows, np.ndarray) else host_rows.data_ptr()
+        root = np.zeros(32, np.uint8)
+        dig = np.zeros((self._n, 32), np.uint8) if want_digests else None
+        _check(lib().lgr_encode_commit_host(self._ctx, C.c_void_p(ptr), C.c_uint64(nrows),
+                                            dig.ctypes.data_as(C.c_void_p) if want_digests else None, root.ctypes.data_as(C.c_void_p)))
+        return dig, root.tobytes()
+
+    def profile(self, enable):
+        _check(lib().lgr_profile(self._ctx, C.c_int(int(enable))))
+
+    def profile_read(self):
+        em, sm = C.c_double(), C.c_double()
+        el, sl = C.c_uint64(), C.c_uint64()
+        _check(lib().lgr_profile_read(self._ctx, C.byref(em), C.byref(el), C.byref(sm), C.byref(sl)))
+        return {"encode_ms": em.value, "encode_launches": el.value, "sha_ms": sm.value, "sha_launches": sl.value}
 
     def combine_code(self, tile, nrows, scalars, acc):
         r = np.ascontiguousarray(ints_to_array(scalars))

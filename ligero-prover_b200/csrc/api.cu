@@ -73,7 +73,21 @@ struct lgr_ctx {
     void *staging = nullptr; size_t staging_bytes = 0;      // pinned host staging for lgr_write
     cudaEvent_t ev_staging = nullptr;
     uint32_t *sample_idx = nullptr; uint32_t sample_count = 0;
+    // per-kernel timing of the commit pipeline (lgr_profile): events on the launching streams
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_enc, prof_sha;
+    std::vector<cudaEvent_t> prof_pool;
+    fr_mem *h2d_buf[2] = {nullptr, nullptr}; size_t h2d_elems = 0;   // device landing buffers for host-resident rows
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_h2d_free[2] = {nullptr, nullptr};
 };
+
+static cudaEvent_t prof_event(lgr_ctx *c) {
+    cudaEvent_t e = nullptr;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
 
 static int upload(lgr_ctx *c, const std::vector<Fr> &v, DevTable &t) {
     t.count = v.size();
@@ -277,6 +291,11 @@ int lgr_create(lgr_ctx **out, int device, uint32_t l, uint32_t k, uint32_t n, co
     CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_staging, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_h2d_free[i], cudaEventDisableTiming));
+    }
     // validate the roots and build the six context plans eagerly (engine.cpp:196-211 does the same)
     NttPlan *pl; int rc = LGR_OK;
     for (int inv = 0; inv < 2 && !rc; inv++) {
@@ -303,6 +322,11 @@ int lgr_destroy(lgr_ctx *c) {
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_staging) cudaEventDestroy(c->ev_staging);
+    for (int i = 0; i < 2; i++) { if (c->h2d_buf[i]) cudaFree(c->h2d_buf[i]); if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if (c->ev_h2d_free[i]) cudaEventDestroy(c->ev_h2d_free[i]); }
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
+    for (auto &pr : c->prof_enc) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto &pr : c->prof_sha) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     delete c;
@@ -500,12 +524,11 @@ int lgr_sample_gather(lgr_ctx *c, const void *x, void *out) {
 }
 
 // ---- stage-1 commit pipeline -------------------------------------------------------------------
-int lgr_encode_commit(lgr_ctx *c, const void *rows_v, uint64_t nrows, void *digests, void *nodes) {
-    REQUIRE(c && rows_v && digests, "null argument");
+// rows: device-resident (host_rows == nullptr) or host-resident (pinned or pageable) row-major R x k.
+static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host_rows, uint64_t nrows, void *digests, void *nodes) {
     REQUIRE(nrows < (1ull << 40), "too many rows");
-    const fr_mem *rows = (const fr_mem *)rows_v;
     const size_t n = c->n, k = c->k;
-    // tile: even number of rows, ~2^21 codeword elements (64 MiB) per buffer; both buffers L2-friendly for small n
+    // tile: even number of rows, ~2^21 codeword elements (64 MiB) per buffer
     size_t T = ((size_t)1 << 21) / n;
     if (T < 2) T = 2;
     T &= ~(size_t)1;
@@ -518,19 +541,40 @@ int lgr_encode_commit(lgr_ctx *c, const void *rows_v, uint64_t nrows, void *dige
         for (int i = 0; i < 2; i++) CU(cudaMalloc((void **)&c->tile[i], T * n * 32));
         c->tile_elems = T * n;
     }
+    if (host_rows && c->h2d_elems < T * k) {
+        CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(c->copy_stream));
+        for (int i = 0; i < 2; i++) { if (c->h2d_buf[i]) CU(cudaFree(c->h2d_buf[i])); c->h2d_buf[i] = nullptr; }
+        for (int i = 0; i < 2; i++) CU(cudaMalloc((void **)&c->h2d_buf[i], T * k * 32));
+        c->h2d_elems = T * k;
+    }
     if (!c->commit_sha) CU(cudaMalloc((void **)&c->commit_sha, lgr_sha_ctx_bytes((uint32_t)n)));
-    cudaStream_t es = c->stream, hs = overlap ? c->aux_stream : c->stream;
-    if (overlap) { CU(cudaEventRecord(c->ev_fork, es)); CU(cudaStreamWaitEvent(hs, c->ev_fork, 0)); }
+    cudaStream_t es = c->stream, hs = overlap ? c->aux_stream : c->stream, cs = c->copy_stream;
+    CU(cudaEventRecord(c->ev_fork, es));
+    if (overlap) CU(cudaStreamWaitEvent(hs, c->ev_fork, 0));
+    if (host_rows) CU(cudaStreamWaitEvent(cs, c->ev_fork, 0));
     CU(launch_sha_init(c->commit_sha, (int)n, hs)); c->launches++;
     int rc;
     size_t tile_idx = 0;
     for (uint64_t r0 = 0; r0 < nrows; r0 += T, tile_idx++) {
         const int b = (int)(tile_idx & 1);
         const uint32_t t = (uint32_t)std::min<uint64_t>(T, nrows - r0);
-        if (overlap && tile_idx >= 2) CU(cudaStreamWaitEvent(es, c->ev_hash[b], 0));     // buffer free again
-        if ((rc = encode_rows_impl(c, rows + r0 * k, k, t, c->tile[b], es))) return rc;
+        const fr_mem *src = rows ? rows + r0 * k : c->h2d_buf[b];
+        if (host_rows) {                                 // H2D of tile i overlaps encode of tile i-1 and hash of tile i-2
+            if (tile_idx >= 2) CU(cudaStreamWaitEvent(cs, c->ev_h2d_free[b], 0));
+            CU(cudaMemcpyAsync(c->h2d_buf[b], host_rows + r0 * k, (size_t)t * k * 32, cudaMemcpyHostToDevice, cs));
+            CU(cudaEventRecord(c->ev_h2d[b], cs));
+            CU(cudaStreamWaitEvent(es, c->ev_h2d[b], 0));
+        }
+        if (overlap && tile_idx >= 2) CU(cudaStreamWaitEvent(es, c->ev_hash[b], 0));     // codeword buffer free again
+        cudaEvent_t p0 = nullptr, p1 = nullptr;
+        if (c->profiling) { p0 = prof_event(c); p1 = prof_event(c); CU(cudaEventRecord(p0, es)); }
+        if ((rc = encode_rows_impl(c, src, k, t, c->tile[b], es))) return rc;
+        if (c->profiling) { CU(cudaEventRecord(p1, es)); c->prof_enc.emplace_back(p0, p1); }
+        if (host_rows) CU(cudaEventRecord(c->ev_h2d_free[b], es));
         if (overlap) { CU(cudaEventRecord(c->ev_enc[b], es)); CU(cudaStreamWaitEvent(hs, c->ev_enc[b], 0)); }
+        if (c->profiling) { p0 = prof_event(c); p1 = prof_event(c); CU(cudaEventRecord(p0, hs)); }
         CU(launch_sha_update(c->commit_sha, (int)n, c->tile[b], (long long)n, (int)t, hs)); c->launches++;
+        if (c->profiling) { CU(cudaEventRecord(p1, hs)); c->prof_sha.emplace_back(p0, p1); }
         if (overlap) CU(cudaEventRecord(c->ev_hash[b], hs));
     }
     CU(launch_sha_final(c->commit_sha, (int)n, (uint32_t *)digests, hs)); c->launches++;
@@ -540,6 +584,44 @@ int lgr_encode_commit(lgr_ctx *c, const void *rows_v, uint64_t nrows, void *dige
         c->launches += lv + 1;
     }
     if (overlap) { CU(cudaEventRecord(c->ev_join, hs)); CU(cudaStreamWaitEvent(es, c->ev_join, 0)); }
+    return LGR_OK;
+}
+
+int lgr_encode_commit(lgr_ctx *c, const void *rows, uint64_t nrows, void *digests, void *nodes) {
+    REQUIRE(c && rows && digests, "null argument");
+    return encode_commit_impl(c, (const fr_mem *)rows, nullptr, nrows, digests, nodes);
+}
+
+int lgr_encode_commit_host(lgr_ctx *c, const void *host_rows, uint64_t nrows, void *host_digests, void *host_root) {
+    REQUIRE(c && host_rows && (host_digests || host_root), "null argument");
+    const size_t n = c->n;
+    const size_t need = n + (2 * n - 1);                // digests + nodes, in elements of 32 bytes
+    int rc = LGR_OK;
+    // results live at the tail of the scratch buffer (not used by the fused encoder)
+    if (!fused_encode_ok(c)) { if ((rc = ensure_scratch(c, (size_t)c->n * std::min<uint64_t>(nrows, ((size_t)1 << 21) / n + 2) + need))) return rc; }
+    else if ((rc = ensure_scratch(c, need))) return rc;
+    fr_mem *dig = c->scratch + (c->scratch_elems - need), *nodes = dig + n;
+    if ((rc = encode_commit_impl(c, nullptr, (const fr_mem *)host_rows, nrows, dig, nodes))) return rc;
+    if (host_digests) CU(cudaMemcpyAsync(host_digests, dig, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (host_root) CU(cudaMemcpyAsync(host_root, nodes, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return LGR_OK;
+}
+
+int lgr_profile(lgr_ctx *c, int enable) { REQUIRE(c, "null context"); c->profiling = enable != 0; return LGR_OK; }
+int lgr_profile_read(lgr_ctx *c, double *enc_ms, uint64_t *enc_launches, double *sha_ms, uint64_t *sha_launches) {
+    REQUIRE(c && enc_ms && enc_launches && sha_ms && sha_launches, "null argument");
+    CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(c->aux_stream));
+    double acc[2] = {0, 0};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *v[2] = {&c->prof_enc, &c->prof_sha};
+    for (int i = 0; i < 2; i++) {
+        for (auto &pr : *v[i]) {
+            float ms = 0; CU(cudaEventElapsedTime(&ms, pr.first, pr.second)); acc[i] += ms;
+            c->prof_pool.push_back(pr.first); c->prof_pool.push_back(pr.second);
+        }
+    }
+    *enc_ms = acc[0]; *enc_launches = c->prof_enc.size(); *sha_ms = acc[1]; *sha_launches = c->prof_sha.size();
+    c->prof_enc.clear(); c->prof_sha.clear();
     return LGR_OK;
 }
 
@@ -596,6 +678,22 @@ int lgr_ubench(lgr_ctx *c, int which, double *ops) {
     const double per_thread = which == 0 ? 8.0 * iters : (double)iters * (which == 1 ? 4.0 : 1.0);
     *ops = 5.0 * per_thread * blocks * threads / (ms * 1e-3);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return LGR_OK;
+}
+
+// cycles per SHA-256 compression of one warp owning a scheduler (variant 3/4/5, see ubench.cu)
+int lgr_ubench_chain(lgr_ctx *c, int variant, int warps_per_cta, int active_lanes, double *cycles) {
+    REQUIRE(c && cycles, "null argument");
+    REQUIRE(variant >= 3 && variant <= 5 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
+    uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
+    CU(launch_ubench_chain(variant, d, 64, warps_per_cta, active_lanes, c->stream));
+    CU(launch_ubench_chain(variant, d, 512, warps_per_cta, active_lanes, c->stream));
+    uint32_t cyc = 0;
+    CU(cudaMemcpyAsync(&cyc, d + 148 * 8 * 256 - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->launches += 2;
+    *cycles = cyc;
+    cudaFree(d);
     return LGR_OK;
 }
 

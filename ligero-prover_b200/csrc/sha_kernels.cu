@@ -18,16 +18,6 @@
 
 namespace lgr {
 
-__constant__ uint32_t c_K256[64] = {
-    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
-    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
-    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
-    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
-    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
-    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
-    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
-    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
-
 // compile-time copy so the fully unrolled rounds carry K as immediates
 #define LGR_K256_LIST                                                                                  \
     0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u, \
@@ -114,6 +104,135 @@ __global__ void __launch_bounds__(128) sha_update_kernel(uint32_t *ctx, int n, c
     const uint32_t lo = rows_lo + (uint32_t)T;
     ctx[(size_t)16 * n + j] = lo;
     ctx[(size_t)17 * n + j] = rows_hi + (lo < rows_lo ? 1u : 0u);
+}
+
+// ---- narrow matrices: one dependent chain per column, few columns ------------------------------
+// With n = 1024 columns there are only 32 warps of work and every column is a Merkle-Damgard chain
+// over all rows, so the commit is bound by how fast ONE warp gets through a compression
+// (measured on B200, ubench variants 3/4: 2660 cycles with the message schedule in line, 1938
+// when K+W comes from shared memory).  sha_chain_kernel therefore splits the work inside a CTA:
+//   warp 0      : the chain -- 64 rounds per block, reads K[t]+W[t] from a shared-memory ring
+//   warps 1..3  : the message schedule for blocks b = h, h+3, ... (state independent), each on its
+//                 own scheduler, filling the ring ahead of the chain
+// Ring slots are handed over with mbarriers (full: 32 producer lanes arrive; empty: the chain
+// warp's lane 0 arrives).  The CTA asks for enough shared memory that no other CTA shares the SM,
+// so the chain warp never competes for issue slots.
+constexpr int kChainSlots = 22;                               // 22 x 8 KiB = 176 KiB
+constexpr int kChainHelpers = 3;
+constexpr size_t kChainSmem = (size_t)kChainSlots * 64 * 32 * 4 + 2 * kChainSlots * 8;
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}"
+        :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// 64 rounds with pre-added K+W (kw[t*32 + lane])
+__device__ __forceinline__ void sha256_rounds_kw(uint32_t st[8], const uint32_t *kw, int lane) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        const uint32_t t1 = h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + kw[i * 32 + lane];
+        const uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+// virtual row v of the stream seen by this launch: the pending row (if the row count so far is
+// odd) followed by the T tile rows
+__device__ __forceinline__ void load_virtual_row(uint32_t *dst, int v, int p, const uint32_t *ctx, int n, int col, const fr_mem *tile, long long row_stride) {
+    if (p && v == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) dst[i] = ctx[(size_t)(8 + i) * n + col];
+    } else {
+        load_words(dst, tile + (long long)(v - p) * row_stride + col);
+    }
+}
+
+__global__ void __launch_bounds__(128, 1) sha_chain_kernel(uint32_t *ctx, int n, const fr_mem *__restrict__ tile, long long row_stride, int T) {
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    uint32_t *ring = reinterpret_cast<uint32_t *>(chain_smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(chain_smem + (size_t)kChainSlots * 64 * 32 * 4);
+    uint64_t *empty = full + kChainSlots;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 32 + lane;                   // n is a multiple of 32
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kChainSlots; s++) { mbar_init(full + s, 32); mbar_init(empty + s, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t rows_lo = ctx[(size_t)16 * n + col], rows_hi = ctx[(size_t)17 * n + col];
+    const int p = (int)(rows_lo & 1u);
+    const int nblk = (p + T) >> 1;
+    if (warp == 0) {
+        uint32_t st[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) st[i] = ctx[(size_t)i * n + col];
+        int slot = 0; uint32_t phase = 0;
+        for (int b = 0; b < nblk; b++) {
+            mbar_wait(full + slot, phase);
+            sha256_rounds_kw(st, ring + (size_t)slot * 64 * 32, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);
+            if (++slot == kChainSlots) { slot = 0; phase ^= 1u; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) ctx[(size_t)i * n + col] = st[i];
+        if ((p + T) & 1) {                                     // an unpaired last row stays pending
+            uint32_t w[8];
+            load_words(w, tile + (long long)(T - 1) * row_stride + col);
+#pragma unroll
+            for (int i = 0; i < 8; i++) ctx[(size_t)(8 + i) * n + col] = w[i];
+        }
+        const uint32_t lo = rows_lo + (uint32_t)T;
+        ctx[(size_t)16 * n + col] = lo;
+        ctx[(size_t)17 * n + col] = rows_hi + (lo < rows_lo ? 1u : 0u);
+    } else {
+        constexpr uint32_t K[64] = {LGR_K256_LIST};
+        const int hsel = warp - 1;
+        uint32_t w[16], nx[16];
+        if (hsel < nblk) {
+            load_virtual_row(nx, 2 * hsel, p, ctx, n, col, tile, row_stride);
+            load_virtual_row(nx + 8, 2 * hsel + 1, p, ctx, n, col, tile, row_stride);
+        }
+        for (int b = hsel; b < nblk; b += kChainHelpers) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = nx[i];
+            const int bn = b + kChainHelpers;
+            if (bn < nblk) {
+                load_virtual_row(nx, 2 * bn, p, ctx, n, col, tile, row_stride);
+                load_virtual_row(nx + 8, 2 * bn + 1, p, ctx, n, col, tile, row_stride);
+            }
+            const int slot = b % kChainSlots;
+            const uint32_t phase = (uint32_t)(b / kChainSlots) & 1u;
+            mbar_wait(empty + slot, phase ^ 1u);               // passes immediately the first time round
+            uint32_t *dst = ring + (size_t)slot * 64 * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 64; i++) {
+                uint32_t wi;
+                if (i < 16) wi = w[i];
+                else {
+                    const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                    wi = w[i & 15] + (rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3)) + w[(i + 9) & 15] + (rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10));
+                    w[i & 15] = wi;
+                }
+                dst[i * 32] = wi + K[i];
+            }
+            mbar_arrive(full + slot);                          // every lane: releases its own stores
+        }
+    }
 }
 
 // padding + length + digest as native state words (shader/sha256.wgsl:179-230); the context is
@@ -220,6 +339,13 @@ cudaError_t launch_sha_init(uint32_t *ctx, int n, cudaStream_t st) {
 }
 cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long long row_stride, int T, cudaStream_t st) {
     if (n <= 0 || T <= 0) return cudaSuccess;
+    if (n % 32 == 0 && n / 32 <= 148 && T >= 4) {
+        // narrow matrix: producer/consumer CTAs, one chain warp per SM
+        cudaError_t e = cudaFuncSetAttribute(sha_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem);
+        if (e != cudaSuccess) return e;
+        sha_chain_kernel<<<n / 32, 128, kChainSmem, st>>>(ctx, n, tile, row_stride, T);
+        return cudaGetLastError();
+    }
     // few columns: one warp per CTA so that every chain gets its own scheduler slot
     const int threads = (n <= 148 * 4 * 32) ? 32 : 128;
     sha_update_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(ctx, n, tile, row_stride, T);

@@ -75,6 +75,100 @@ __global__ void __launch_bounds__(256) ubench_sha_kernel(uint32_t *out, int iter
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- single-warp SHA-256 chain experiments (one warp per SM sub-partition) ---------------------
+// The column hash of a narrow matrix (n = 1024 -> 32 warps) is a dependent chain: what matters is
+// the cycles one warp needs per compression when it owns a scheduler.  Variants:
+//   3: plain rounds + in-line message schedule (what sha_update_kernel does)
+//   4: rounds only, K+W pre-computed in shared memory (message schedule done by helper warps)
+//   5: as 4, with part of the rotations / additions moved to the FMA pipe through opaque
+//      multipliers (kernel parameters), so ALU and FMA pipes share the 2-cycle/instruction load
+struct ChainConsts { uint32_t one, m6, m11, m25, m2, m13, m22; };
+
+__device__ __forceinline__ uint32_t rot_fma(uint32_t x, uint32_t mult) {      // rotr(x, s), mult = 2^(32-s): 2 FMA-pipe ops
+    uint32_t hi = __umulhi(x, mult);
+    return x * mult + hi;
+}
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one) { return a * one + b; }
+
+template <int VARIANT>
+__device__ __forceinline__ void chain_rounds(uint32_t st[8], const uint32_t *kw /* [64][32] in smem */, int lane, const ChainConsts cc) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        const uint32_t kwi = kw[i * 32 + lane];
+        if (VARIANT == 4) {
+            const uint32_t t1 = h + (ub_rotr(e, 6) ^ ub_rotr(e, 11) ^ ub_rotr(e, 25)) + ((e & f) ^ (~e & g)) + kwi;
+            const uint32_t t2 = (ub_rotr(a, 2) ^ ub_rotr(a, 13) ^ ub_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        } else {
+            // early terms on the FMA pipe
+            const uint32_t x = add_fma(h, kwi, cc.one);                  // h + KW
+            const uint32_t ch = (e & f) ^ (~e & g);
+            const uint32_t xch = add_fma(x, ch, cc.one);                 // h + KW + Ch
+            const uint32_t ych = add_fma(xch, d, cc.one);                // d + h + KW + Ch
+            const uint32_t s1 = ub_rotr(e, 6) ^ rot_fma(e, cc.m11) ^ ub_rotr(e, 25);
+            const uint32_t s0 = ub_rotr(a, 2) ^ rot_fma(a, cc.m13) ^ rot_fma(a, cc.m22);
+            const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            const uint32_t ne = ych + s1;
+            const uint32_t na = xch + s1 + (s0 + mj);
+            h = g; g = f; f = e; e = ne; d = c; c = b; b = a; a = na;
+        }
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(128) ubench_chain_kernel(uint32_t *out, int iters, const ChainConsts cc, int active_lanes) {
+    __shared__ uint32_t kw[4][64 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = lane; i < 64 * 32; i += 32) kw[warp][i] = i * 2654435761u + warp;
+    __syncwarp();
+    if (lane >= active_lanes) return;
+    uint32_t st[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = threadIdx.x * 0x01000193u + i;
+    long long t0 = clock64();
+    if (VARIANT == 3) {
+        uint32_t w[16];
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = kw[warp][i * 32 + lane] + it;
+            uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+            for (int i = 0; i < 64; i++) {
+                uint32_t wi;
+                if (i < 16) wi = w[i];
+                else {
+                    const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                    wi = w[i & 15] + (ub_rotr(w15, 7) ^ ub_rotr(w15, 18) ^ (w15 >> 3)) + w[(i + 9) & 15] + (ub_rotr(w2, 17) ^ ub_rotr(w2, 19) ^ (w2 >> 10));
+                    w[i & 15] = wi;
+                }
+                const uint32_t t1 = h + (ub_rotr(e, 6) ^ ub_rotr(e, 11) ^ ub_rotr(e, 25)) + ((e & f) ^ (~e & g)) + 0x428a2f98u * (i + 1) + wi;
+                const uint32_t t2 = (ub_rotr(a, 2) ^ ub_rotr(a, 13) ^ ub_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+                h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+            }
+            st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+        }
+    } else {
+        for (int it = 0; it < iters; it++) chain_rounds<VARIANT>(st, kw[warp], lane, cc);
+    }
+    long long t1 = clock64();
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= st[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[148 * 8 * 256 - 1] = (uint32_t)((t1 - t0) / iters); }
+}
+
+cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps_per_cta, int active_lanes, cudaStream_t st) {
+    ChainConsts cc{1u, 1u << 26, 1u << 21, 1u << 7, 1u << 30, 1u << 19, 1u << 10};
+    const int threads = warps_per_cta * 32;
+    if (variant == 3) ubench_chain_kernel<3><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 4) ubench_chain_kernel<4><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else ubench_chain_kernel<5><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ubench(int which, uint32_t *out, int iters, int blocks, int threads, cudaStream_t st) {
     if (which == 0) ubench_imad_kernel<<<blocks, threads, 0, st>>>(out, iters);
     else if (which == 1) ubench_mont_kernel<<<blocks, threads, 0, st>>>(out, iters);
