@@ -14,7 +14,7 @@
 //     (same residue as montgomery_mul_2p, bn254fr.wgsl.in:106-109)
 //
 // The file also compiles for the host (LGR_FR_HOST_EMU) with the PTX carry primitives emulated,
-// so the algorithm can be checked against the oracle without a GPU (tests/test_fr_emulation.py).
+// so the algorithm can be checked against the oracle without a GPU (tests/cpp/fr_emu.cpp, tests/test_host_cpu.py).
 #pragma once
 #include <stdint.h>
 

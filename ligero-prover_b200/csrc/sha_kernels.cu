@@ -309,7 +309,7 @@ __global__ void merkle_place_leaves(const uint32_t *leaf, int nleaves, uint32_t 
         nodes[(size_t)(P2 - 1) * 8 + i] = (i < (size_t)nleaves * 8) ? leaf[i] : 0u;
 }
 
-// ---- synthetic witness (same generator as the oracle's lgo_synth) -------
+// ---- synthetic witness (the counter-based generator of BASELINE.md section 3) -------
 __device__ __forceinline__ unsigned long long splitmix(unsigned long long &s) {
     unsigned long long z = (s += 0x9e3779b97f4a7c15ull);
     z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31);

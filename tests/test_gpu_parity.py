@@ -444,3 +444,39 @@ def test_stage1_stage2_schedule_like_nonbatch_context(lgr, oracle, executor_fact
     # test polynomial (degree < 2k) vanishes on the first k points before the mask is added
     ex.decode_ntt_device(ex.bind_ntt(code))
     assert not ex.read_elements(code)[k:].any()
+
+
+def test_cpp_cuda_executor_drop_in(lgr, oracle, tmp_path):
+    """the C++ adapter (host/cuda_executor.hpp) driven like nonbatch_stage1/2_context, vs the oracle"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_executor")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "tests", "cpp"), "-s"])
+    k, nrows = 512, 7
+    n = 4 * k
+    rows = oracle.synth(13, 0, nrows, k)
+    rng = random.Random(13)
+    scal = [rng.randrange(P) for _ in range(nrows)]
+    wk, w2k, wn = lgr.generate_omegas(k, n)
+    hdr = lgr.ints_to_array([P, wk, w2k, wn])
+    cnt = np.zeros((1, 8), np.uint32); cnt[0, 0] = nrows
+    blob = np.concatenate([hdr, cnt, lgr.ints_to_array(scal), rows.reshape(-1, 8)])
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    blob.tofile(fin)
+    out = subprocess.check_output([exe, str(k), str(fin), str(fout)], stderr=subprocess.STDOUT, timeout=300)
+    assert b"ok" in out
+    data = np.fromfile(fout, np.uint8)
+    dig = data[: n * 32].reshape(n, 32)
+    code = data[n * 32: 2 * n * 32].view(np.uint32).reshape(n, 8)
+    quad = data[2 * n * 32:].view(np.uint32).reshape(n, 8)
+    want_d, _, _ = oracle.encode_commit(rows, k)
+    assert np.array_equal(dig, want_d)
+    cws = [oracle.encode(rows[r], k) for r in range(nrows)]
+    wc = np.zeros((n, 8), np.uint32)
+    for r in range(nrows):
+        wc = oracle.elt_fma_const(wc, cws[r], scal[r])
+    wq = np.zeros((n, 8), np.uint32)
+    for r in range(0, nrows - 2, 3):
+        wq = oracle.elt_fma_const(wq, oracle.elt_sub(oracle.elt_mul(cws[r], cws[r + 1]), cws[r + 2]), scal[r])
+    assert np.array_equal(code, wc) and np.array_equal(quad, wq)
