@@ -524,16 +524,22 @@ int lgr_sample_gather(lgr_ctx *c, const void *x, void *out) {
 }
 
 // ---- stage-1 commit pipeline -------------------------------------------------------------------
-// rows: device-resident (host_rows == nullptr) or host-resident (pinned or pageable) row-major R x k.
-static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host_rows, uint64_t nrows, void *digests, void *nodes) {
-    REQUIRE(nrows < (1ull << 40), "too many rows");
-    const size_t n = c->n, k = c->k;
-    // tile: even number of rows, ~2^21 codeword elements (64 MiB) per buffer
-    size_t T = ((size_t)1 << 21) / n;
+// tile: even number of rows, 2^23 codeword elements (256 MiB) per buffer: at k = 256 that is 8192 rows
+// = 2048 encoder CTAs (4.6 waves of 444 resident CTAs; a 2^21 tile was 1.15 waves and lost 40% to the tail)
+static size_t commit_tile_rows(const lgr_ctx *c, uint64_t nrows) {
+    size_t T = ((size_t)1 << 23) / c->n;
     if (T < 2) T = 2;
     T &= ~(size_t)1;
     if (T > nrows) T = (size_t)nrows;
     if (T == 0) T = 1;
+    return T;
+}
+
+// rows: device-resident (host_rows == nullptr) or host-resident (pinned or pageable) row-major R x k.
+static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host_rows, uint64_t nrows, void *digests, void *nodes) {
+    REQUIRE(nrows < (1ull << 40), "too many rows");
+    const size_t n = c->n, k = c->k;
+    const size_t T = commit_tile_rows(c, nrows);
     const bool overlap = fused_encode_ok(c);            // generic-engine encodes use the main stream + shared scratch
     if (c->tile_elems < T * n) {
         CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(c->aux_stream));
@@ -598,7 +604,7 @@ int lgr_encode_commit_host(lgr_ctx *c, const void *host_rows, uint64_t nrows, vo
     const size_t need = n + (2 * n - 1);                // digests + nodes, in elements of 32 bytes
     int rc = LGR_OK;
     // results live at the tail of the scratch buffer (not used by the fused encoder)
-    if (!fused_encode_ok(c)) { if ((rc = ensure_scratch(c, (size_t)c->n * std::min<uint64_t>(nrows, ((size_t)1 << 21) / n + 2) + need))) return rc; }
+    if (!fused_encode_ok(c)) { if ((rc = ensure_scratch(c, (size_t)c->n * commit_tile_rows(c, nrows) + need))) return rc; }
     else if ((rc = ensure_scratch(c, need))) return rc;
     fr_mem *dig = c->scratch + (c->scratch_elems - need), *nodes = dig + n;
     if ((rc = encode_commit_impl(c, nullptr, (const fr_mem *)host_rows, nrows, dig, nodes))) return rc;
@@ -684,7 +690,7 @@ int lgr_ubench(lgr_ctx *c, int which, double *ops) {
 // cycles per SHA-256 compression of one warp owning a scheduler (variant 3/4/5, see ubench.cu)
 int lgr_ubench_chain(lgr_ctx *c, int variant, int warps_per_cta, int active_lanes, double *cycles) {
     REQUIRE(c && cycles, "null argument");
-    REQUIRE(variant >= 3 && variant <= 5 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
+    REQUIRE(variant >= 3 && variant <= 8 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
     uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
     CU(launch_ubench_chain(variant, d, 64, warps_per_cta, active_lanes, c->stream));
     CU(launch_ubench_chain(variant, d, 512, warps_per_cta, active_lanes, c->stream));

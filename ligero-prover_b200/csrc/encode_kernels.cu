@@ -50,35 +50,22 @@ __global__ void __launch_bounds__(enc_cfg<LOGK>::THREADS) encode_rows_kernel(
     const bool active = row < R;
     slot_sync<TL> sync{slot + 1};
 
-    // 1. load the message row (coalesced, natural order)
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int i = tl + j * TL;
-        fr_t x = active ? fr_ldg(rows_in + row * in_row_stride + i) : fr_zero();
-        fr_sts(C + i, x);
-    }
+    // 1. inverse transform: the top pass reads the message row straight from global memory
+    //    (coalesced: consecutive threads, consecutive elements); result = coefficients in
+    //    bit-reversed order in C, values in [0,2p).  w_k^-1 twiddles; 1/k is folded into the twist.
+    const fr_mem *src = rows_in + (active ? row : 0) * in_row_stride;
+    ntt_passes_io<LOGK, 0, true>(C, tl, t.inv_k, 1, sync,
+                                 [&](int i) { return active ? fr_ldg(src + i) : fr_zero(); }, smem_io{C});
     sync();
-    // 2. coefficients, bit-reversed order, [0,2p)  (w_k^-1 twiddles; 1/k folded into the twist)
-    ntt_dif<LOGK>(C, tl, t.inv_k, 1, sync);
-    // 3. four coset transforms
+    // 2. four coset transforms: the first pass applies the twist while loading the coefficients,
+    //    the last pass canonicalises and writes e[4m + r] straight to global memory
+    fr_mem *dst = out + (active ? row : 0) * out_row_stride;
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int q = tl + j * TL;
-            fr_t c = fr_lds(C + q);
-            fr_sts(W + q, fr_mont_mul(c, fr_ldc(t.twist + r * K + q)));
-        }
-        sync();
-        ntt_dit<LOGK>(W, tl, t.fwd_c, 1, sync);
-        if (active) {
-            fr_mem *o = out + row * out_row_stride + r;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int m = tl + j * TL;
-                fr_stg(o + 4 * m, fr_canon4(fr_lds(W + m)));
-            }
-        }
+        const fr_mem *tw_r = t.twist + r * K;
+        ntt_passes_io<LOGK, 0, false>(W, tl, t.fwd_c, 1, sync,
+                                      [&](int q) { return fr_mont_mul(fr_lds(C + q), fr_ldc(tw_r + q)); },
+                                      [&](int m, const fr_t &x) { if (active) fr_stg(dst + 4 * m + r, fr_canon4(x)); });
         sync();
     }
 }

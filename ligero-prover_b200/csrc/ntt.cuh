@@ -42,10 +42,12 @@ LGR_DEV fr_t fr_ldc(const fr_mem *p) {
 
 LGR_DEV uint32_t bitrev(uint32_t x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
 
-// One shared-memory pass over index bits [LO, LO+T) of an M-point transform held at `sm`.
+// One pass over index bits [LO, LO+T) of an M-point transform.  `load(idx)` / `store(idx, x)` move the
+// elements (shared memory by default; the first / last pass of a fused kernel reads or writes global
+// memory directly, applying a twist or a canonicalisation on the way).
 // `tl` = thread index within the lane (0 .. max(M/8,1)-1); tw[j*tws] = w^j * R for the M-point root.
-template <int LOGM, int LO, int T, bool DIF>
-LGR_DEV void ntt_pass(fr_mem *sm, int tl, const fr_mem *__restrict__ tw, int tws) {
+template <int LOGM, int LO, int T, bool DIF, typename Load, typename Store>
+LGR_DEV void ntt_pass_io(int tl, const fr_mem *__restrict__ tw, int tws, Load load, Store store) {
     constexpr int M = 1 << LOGM;
     constexpr int TL = (M >= 8) ? (M / 8) : 1;
     constexpr int E = M / TL;
@@ -60,7 +62,7 @@ LGR_DEV void ntt_pass(fr_mem *sm, int tl, const fr_mem *__restrict__ tw, int tws
         const int base = low | ((q >> LO) << (LO + T));
         fr_t x[R];
 #pragma unroll
-        for (int j = 0; j < R; j++) x[j] = fr_lds(sm + base + j * S);
+        for (int j = 0; j < R; j++) x[j] = load(base + j * S);
 #pragma unroll
         for (int ss = 0; ss < T; ss++) {
             const int s = DIF ? (T - 1 - ss) : ss;
@@ -91,35 +93,59 @@ LGR_DEV void ntt_pass(fr_mem *sm, int tl, const fr_mem *__restrict__ tw, int tws
             }
         }
 #pragma unroll
-        for (int j = 0; j < R; j++) fr_sts(sm + base + j * S, x[j]);
+        for (int j = 0; j < R; j++) store(base + j * S, x[j]);
     }
 }
 
+struct smem_io {
+    fr_mem *sm;
+    LGR_DEV fr_t operator()(int i) const { return fr_lds(sm + i); }
+    LGR_DEV void operator()(int i, const fr_t &x) const { fr_sts(sm + i, x); }
+};
+
 // Pass schedule: index bits are consumed three at a time; a tail of four bits is split 2+2 so
-// that no pass is a single stage (except the 2-point transform).
-template <int LOGM, int LO, bool DIF, typename Sync>
-LGR_DEV void ntt_passes_from(fr_mem *sm, int tl, const fr_mem *tw, int tws, Sync sync) {
-    // DIT walks LO upward, DIF walks the same partition downward
+// that no pass is a single stage (except the 2-point transform).  DIT walks the partition upward
+// (bit-reversed in -> natural out, values rest in [0,4p)), DIF walks it downward (natural in ->
+// bit-reversed out, values in [0,2p)).  The first pass executed takes its input from `first`, the
+// last pass executed hands its output to `last`; passes in between work in place on `sm`.
+// sync() is called between passes (not after the last one).
+template <int LOGM, int LO, bool DIF, typename Sync, typename First, typename Last>
+LGR_DEV void ntt_passes_io(fr_mem *sm, int tl, const fr_mem *tw, int tws, Sync sync, First first, Last last) {
     if constexpr (LO < LOGM) {
         constexpr int left = LOGM - LO;
         constexpr int T = (left == 4) ? 2 : (left >= 3 ? 3 : left);
+        constexpr bool low = (LO == 0), top = (LO + T == LOGM);
+        smem_io io{sm};
         if constexpr (DIF) {
-            ntt_passes_from<LOGM, LO + T, DIF>(sm, tl, tw, tws, sync);
-            ntt_pass<LOGM, LO, T, true>(sm, tl, tw, tws);
-            sync();
+            ntt_passes_io<LOGM, LO + T, DIF>(sm, tl, tw, tws, sync, first, last);
+            if constexpr (!top) sync();
+            if constexpr (top && low) ntt_pass_io<LOGM, LO, T, true>(tl, tw, tws, first, last);
+            else if constexpr (top) ntt_pass_io<LOGM, LO, T, true>(tl, tw, tws, first, io);
+            else if constexpr (low) ntt_pass_io<LOGM, LO, T, true>(tl, tw, tws, io, last);
+            else ntt_pass_io<LOGM, LO, T, true>(tl, tw, tws, io, io);
         } else {
-            ntt_pass<LOGM, LO, T, false>(sm, tl, tw, tws);
-            sync();
-            ntt_passes_from<LOGM, LO + T, DIF>(sm, tl, tw, tws, sync);
+            if constexpr (top && low) ntt_pass_io<LOGM, LO, T, false>(tl, tw, tws, first, last);
+            else if constexpr (low) ntt_pass_io<LOGM, LO, T, false>(tl, tw, tws, first, io);
+            else if constexpr (top) ntt_pass_io<LOGM, LO, T, false>(tl, tw, tws, io, last);
+            else ntt_pass_io<LOGM, LO, T, false>(tl, tw, tws, io, io);
+            if constexpr (!top) sync();
+            ntt_passes_io<LOGM, LO + T, DIF>(sm, tl, tw, tws, sync, first, last);
         }
     }
 }
 
-// M-point DIT: sm holds the input in bit-reversed order, result in natural order, values in [0,4p)
+// M-point DIT entirely in shared memory: sm holds the input in bit-reversed order, result in
+// natural order, values in [0,4p); a sync() follows the last pass
 template <int LOGM, typename Sync>
-LGR_DEV void ntt_dit(fr_mem *sm, int tl, const fr_mem *tw, int tws, Sync sync) { ntt_passes_from<LOGM, 0, false>(sm, tl, tw, tws, sync); }
-// M-point DIF: natural order in (values in [0,2p)), bit-reversed order out, values in [0,2p)
+LGR_DEV void ntt_dit(fr_mem *sm, int tl, const fr_mem *tw, int tws, Sync sync) {
+    ntt_passes_io<LOGM, 0, false>(sm, tl, tw, tws, sync, smem_io{sm}, smem_io{sm});
+    sync();
+}
+// M-point DIF entirely in shared memory: natural order in (values in [0,2p)), bit-reversed out
 template <int LOGM, typename Sync>
-LGR_DEV void ntt_dif(fr_mem *sm, int tl, const fr_mem *tw, int tws, Sync sync) { ntt_passes_from<LOGM, 0, true>(sm, tl, tw, tws, sync); }
+LGR_DEV void ntt_dif(fr_mem *sm, int tl, const fr_mem *tw, int tws, Sync sync) {
+    ntt_passes_io<LOGM, 0, true>(sm, tl, tw, tws, sync, smem_io{sm}, smem_io{sm});
+    sync();
+}
 
 }  // namespace lgr

@@ -100,6 +100,17 @@ __device__ __forceinline__ void chain_rounds(uint32_t st[8], const uint32_t *kw 
             const uint32_t t1 = h + (ub_rotr(e, 6) ^ ub_rotr(e, 11) ^ ub_rotr(e, 25)) + ((e & f) ^ (~e & g)) + kwi;
             const uint32_t t2 = (ub_rotr(a, 2) ^ ub_rotr(a, 13) ^ ub_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
             h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        } else if (VARIANT >= 6) {
+            // 6: one FMA-pipe rotation in each Sigma; 7: Sigma1 one, Sigma0 two; 8: Sigma1 two, Sigma0 one
+            const uint32_t r25 = rot_fma(e, cc.m25);
+            const uint32_t r11 = (VARIANT == 8) ? rot_fma(e, cc.m11) : ub_rotr(e, 11);
+            const uint32_t s1 = ub_rotr(e, 6) ^ r11 ^ r25;
+            const uint32_t r22 = rot_fma(a, cc.m22);
+            const uint32_t r13 = (VARIANT == 7) ? rot_fma(a, cc.m13) : ub_rotr(a, 13);
+            const uint32_t s0 = ub_rotr(a, 2) ^ r13 ^ r22;
+            const uint32_t t1 = h + s1 + ((e & f) ^ (~e & g)) + kwi;
+            const uint32_t t2 = s0 + ((a & b) ^ (a & c) ^ (b & c));
+            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
         } else {
             // early terms on the FMA pipe
             const uint32_t x = add_fma(h, kwi, cc.one);                  // h + KW
@@ -165,7 +176,10 @@ cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps
     const int threads = warps_per_cta * 32;
     if (variant == 3) ubench_chain_kernel<3><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 4) ubench_chain_kernel<4><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
-    else ubench_chain_kernel<5><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 5) ubench_chain_kernel<5><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 6) ubench_chain_kernel<6><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 7) ubench_chain_kernel<7><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else ubench_chain_kernel<8><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     return cudaGetLastError();
 }
 

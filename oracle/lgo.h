@@ -112,6 +112,7 @@ int lgo_encode_commit_synth(uint64_t seed, size_t R, size_t k, uint8_t *digests,
 /* batch of independent NTTs (CPU baseline for config 2): x[batch][N] */
 int lgo_ntt_batch(lgo_fr *x, size_t N, size_t batch, const lgo_fr *omega, int inverse);
 int lgo_num_threads(void);
+void lgo_set_threads(int n);   /* torchrun exports OMP_NUM_THREADS=1: the baseline legs set all cores explicitly */
 
 #ifdef __cplusplus
 }

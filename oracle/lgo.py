@@ -211,3 +211,7 @@ def encode_commit_synth(seed, R, k):
 
 def num_threads():
     return lib().lgo_num_threads()
+
+
+def set_threads(n):
+    lib().lgo_set_threads(C.c_int(n))

@@ -454,6 +454,13 @@ void lgo_synth(lgo_fr *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64
         for (uint64_t c = 0; c < ncols; c++) synth_one(&out[r * ncols + c], seed, row0 + r, c);
 }
 
+void lgo_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int lgo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

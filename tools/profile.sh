@@ -1,0 +1,18 @@
+#!/bin/bash
+# ncu evidence for profiles/ (run under gpurun on one B200; outputs land in gpurun_out/).
+#   1. launch list (device time per launch, cold-cache + serialised: compare SHARES) of the bench command
+#   2. one --set full capture each of the encoder, the hash chain and the tile NTT
+set -x
+mkdir -p gpurun_out
+NCU="ncu --clock-control none"
+$NCU --metrics gpu__time_duration.sum -s 40 -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+$NCU --set full --import-source on -k regex:encode_rows_kernel -s 6 -c 2 -f -o gpurun_out/prof_encode \
+    python bench.py --steps 1 --warmup 3 --log-rows 15 --no-e2e --no-cpu-baseline > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:sha_chain_kernel -s 6 -c 2 -f -o gpurun_out/prof_sha_chain \
+    python bench.py --steps 1 --warmup 3 --log-rows 15 --no-e2e --no-cpu-baseline > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:ntt_tile_kernel -s 8 -c 2 -f -o gpurun_out/prof_ntt \
+    python tools/ntt_bench.py > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:combine_partial -s 2 -c 1 -f -o gpurun_out/prof_combine \
+    python tools/combine_bench.py > /dev/null 2>&1
+ls -la gpurun_out
