@@ -687,6 +687,26 @@ int lgr_ubench(lgr_ctx *c, int which, double *ops) {
     return LGR_OK;
 }
 
+// Montgomery multiplications per second with `warps_per_sm` resident warps and `nchain` independent
+// multiplications per thread (occupancy / ILP sweep)
+int lgr_ubench_mont_occ(lgr_ctx *c, int nchain, int warps_per_sm, double *ops) {
+    REQUIRE(c && ops, "null argument");
+    REQUIRE((nchain == 1 || nchain == 2 || nchain == 4) && warps_per_sm >= 1 && warps_per_sm <= 32, "bad arguments");
+    uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 1024 * 4));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int iters = 2048 / nchain;
+    CU(launch_ubench_mont_occ(nchain, warps_per_sm, d, iters, c->stream));
+    CU(cudaEventRecord(e0, c->stream));
+    CU(launch_ubench_mont_occ(nchain, warps_per_sm, d, iters, c->stream));
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+    *ops = (double)iters * nchain * 148.0 * warps_per_sm * 32 / (ms * 1e-3);
+    c->launches += 2;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return LGR_OK;
+}
+
 // cycles per SHA-256 compression of one warp owning a scheduler (variant 3/4/5, see ubench.cu)
 int lgr_ubench_chain(lgr_ctx *c, int variant, int warps_per_cta, int active_lanes, double *cycles) {
     REQUIRE(c && cycles, "null argument");

@@ -83,6 +83,7 @@ cudaError_t launch_synth(fr_mem *out, uint64_t seed, uint64_t row0, uint64_t nro
 
 // ---- micro-benchmarks (ubench.cu) ------------------------------------------------------------
 cudaError_t launch_ubench(int which, uint32_t *out, int iters, int blocks, int threads, cudaStream_t st);
+cudaError_t launch_ubench_mont_occ(int nchain, int warps_per_sm, uint32_t *out, int iters, cudaStream_t st);
 cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps_per_cta, int active_lanes, cudaStream_t st);
 
 }  // namespace lgr

@@ -183,6 +183,41 @@ cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps
     return cudaGetLastError();
 }
 
+// Montgomery-multiply throughput as a function of resident warps per SM and independent chains per
+// thread: tells how much TLP / ILP the butterfly kernels need to keep the FMA pipe busy.
+template <int NCHAIN>
+__global__ void ubench_mont_occ_kernel(uint32_t *out, int iters) {
+    extern __shared__ unsigned char occ_pad[];
+    fr_t x[NCHAIN], w;
+#pragma unroll
+    for (int i = 0; i < 8; i++) w.v[i] = (threadIdx.x + 1) * 0x9E3779B1u + i * 0x85EBCA77u;
+    w.v[7] &= 0x0FFFFFFFu;
+#pragma unroll
+    for (int q = 0; q < NCHAIN; q++) { x[q] = w; x[q].v[0] += q + blockIdx.x; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int q = 0; q < NCHAIN; q++) x[q] = fr_mont_mul(x[q], w);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int q = 0; q < NCHAIN; q++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) s ^= x[q].v[i];
+    if (s == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = s + occ_pad[0];
+}
+cudaError_t launch_ubench_mont_occ(int nchain, int warps_per_sm, uint32_t *out, int iters, cudaStream_t st) {
+    // one CTA per SM with warps_per_sm warps; 120 KiB of dynamic shared memory keeps it alone on the SM
+    const size_t smem = 120 * 1024;
+    const int threads = warps_per_sm * 32;
+    cudaError_t e;
+#define LGR_OCC(N)                                                                                                        \
+    e = cudaFuncSetAttribute(ubench_mont_occ_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e != cudaSuccess) return e;                                                                                       \
+    ubench_mont_occ_kernel<N><<<148, threads, smem, st>>>(out, iters);
+    if (nchain == 1) { LGR_OCC(1) } else if (nchain == 2) { LGR_OCC(2) } else { LGR_OCC(4) }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ubench(int which, uint32_t *out, int iters, int blocks, int threads, cudaStream_t st) {
     if (which == 0) ubench_imad_kernel<<<blocks, threads, 0, st>>>(out, iters);
     else if (which == 1) ubench_mont_kernel<<<blocks, threads, 0, st>>>(out, iters);
