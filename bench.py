@@ -278,6 +278,7 @@ def main():
             for _ in range(min(args.warmup, 1)):
                 _, root_e2e = ex.encode_commit_host(host, e2e_rows)
             sync_all()
+            ex.profile(True)
             t0 = time.perf_counter()
             e0.record(stream)
             for _ in range(args.steps):
@@ -289,7 +290,9 @@ def main():
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e2e_ms = float(te.item()) / args.steps
-            e2e = {"value": world * e2e_rows * k / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_rows * k * 32,
+            pe = ex.profile_read()
+            ex.profile(False)
+            e2e = {"kernel_ms_per_launch": {"encode": pe["encode_ms"] / max(pe["encode_launches"], 1), "sha": pe["sha_ms"] / max(pe["sha_launches"], 1)},"value": world * e2e_rows * k / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_rows * k * 32,
                    "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms, "rows_per_gpu": e2e_rows,
                    "root_matches_device_path": (root_e2e.hex() == root) if (e2e_rows == R and world == 1) else None}
             del host

@@ -144,6 +144,9 @@ int lgr_profile_read(lgr_ctx *ctx, double *encode_ms, uint64_t *encode_launches,
 /* check_code over a resident tile of nrows codewords: acc[j] += sum_t r[t]*tile[t][j]
  * (nonbatch_context.hpp:756-763); host_r = nrows x 8 u32 canonical scalars */
 int lgr_combine_code(lgr_ctx *ctx, const void *tile, uint32_t nrows, const uint32_t *host_r, void *acc);
+/* check_quadratic over three resident tiles: acc[j] += sum_t r[t]*(x[t][j]*y[t][j] - z[t][j])
+ * (nonbatch_context.hpp:771-780: EltwiseMultMod, EltwiseSubMod, EltwiseFMAMod(r) per triple) */
+int lgr_combine_quad(lgr_ctx *ctx, const void *tile_x, const void *tile_y, const void *tile_z, uint32_t nrows, const uint32_t *host_r, void *acc);
 /* check_linear over two resident tiles: acc[j] += sum_t a[t][j]*b[t][j] (nonbatch_context.hpp:765-769) */
 int lgr_combine_linear(lgr_ctx *ctx, const void *tile_a, const void *tile_b, uint32_t nrows, void *acc);
 
@@ -151,8 +154,12 @@ int lgr_combine_linear(lgr_ctx *ctx, const void *tile_a, const void *tile_b, uin
 /* uniform canonical elements keyed by (seed,row,col): 256 bits >> 2, one conditional subtract
  * (include/zkp/finite_field_gmp.hpp:70-78); identical to the oracle's generator */
 int lgr_synth(lgr_ctx *ctx, void *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols);
-/* which: 0 = IMAD.WIDE chain, 1 = Montgomery multiply, 2 = SHA-256 compression; returns ops/s */
+/* which: 0 = IMAD.WIDE chains, 1 = Montgomery multiply, 2 = SHA-256 compression, 3 = IMAD (low word)
+ * chains, 4 = double-precision FMA chains; returns ops/s chip-wide */
 int lgr_ubench(lgr_ctx *ctx, int which, double *ops_per_sec);
+/* occupancy / ILP sweep of the Montgomery multiply; cycles per SHA-256 compression of a lone warp (ubench.cu) */
+int lgr_ubench_mont_occ(lgr_ctx *ctx, int nchain, int warps_per_sm, double *ops_per_sec);
+int lgr_ubench_chain(lgr_ctx *ctx, int variant, int warps_per_cta, int active_lanes, double *cycles);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblgr.so")
+LIB_PATH = os.environ.get("LGR_LIB") or os.path.join(_HERE, "liblgr.so")   # LGR_LIB: A/B builds during tuning
 
 # BN254 scalar field constants (src/bn254.cpp:21-43)
 P = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
@@ -475,8 +475,13 @@ class Executor:
         return {"encode_ms": em.value, "encode_launches": el.value, "sha_ms": sm.value, "sha_launches": sl.value}
 
     def combine_code(self, tile, nrows, scalars, acc):
-        r = np.ascontiguousarray(ints_to_array(scalars))
+        """scalars: python ints or a [nrows, 8] uint32 array of canonical limbs"""
+        r = np.ascontiguousarray(scalars if isinstance(scalars, np.ndarray) else ints_to_array(scalars), dtype=np.uint32)
         _check(lib().lgr_combine_code(self._ctx, tile.ptr(), C.c_uint32(nrows), r.ctypes.data_as(C.c_void_p), acc.ptr()))
+
+    def combine_quad(self, tile_x, tile_y, tile_z, nrows, scalars, acc):
+        r = np.ascontiguousarray(scalars if isinstance(scalars, np.ndarray) else ints_to_array(scalars), dtype=np.uint32)
+        _check(lib().lgr_combine_quad(self._ctx, tile_x.ptr(), tile_y.ptr(), tile_z.ptr(), C.c_uint32(nrows), r.ctypes.data_as(C.c_void_p), acc.ptr()))
 
     def combine_linear(self, tile_a, tile_b, nrows, acc):
         _check(lib().lgr_combine_linear(self._ctx, tile_a.ptr(), tile_b.ptr(), C.c_uint32(nrows), acc.ptr()))

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -39,7 +40,7 @@ struct NttPlan {
     bool inverse = false;
     int l1 = 0, l2 = 0;          // four-step split (l1 + l2 = logn) or l1 = logn, l2 = 0
     DevTable tw1, tw2;           // sub-transform twiddles
-    DevTable twist_lo, twist_hi;
+    DevTable twist_lo, twist_hi, twist_full;   // four-step twist: full table (N <= 2^20) or lo/hi factors
     int twist_shift = 0;
     DevTable scale;              // N^-1 * R for inverse transforms
 };
@@ -66,6 +67,7 @@ struct lgr_ctx {
     std::map<PlanKey, NttPlan> plans;
     std::vector<void *> owned;              // tables etc.
     EncodeTables enc{};                      // fused encoder tables (k <= 2048)
+    fr_mem *enc_large_twist = nullptr;       // tile-engine encoder (k > 2048): [4][k] coset twists
     bool enc_ready = false;
     fr_mem *scratch = nullptr; size_t scratch_elems = 0;
     fr_mem *tile[2] = {nullptr, nullptr}; size_t tile_elems = 0;
@@ -132,10 +134,14 @@ static int get_plan(lgr_ctx *c, int logn, const Fr &omega, bool inverse, NttPlan
         const size_t N1 = (size_t)1 << p.l1, N2 = (size_t)1 << p.l2;
         if ((rc = upload(c, host::power_table_mont(host::pow(w, N2), N1 / 2), p.tw1))) return rc;   // w_N1 = w^N2
         if ((rc = upload(c, host::power_table_mont(host::pow(w, N1), N2 / 2), p.tw2))) return rc;   // w_N2 = w^N1
-        p.twist_shift = (logn + 1) / 2;
-        const size_t lo = (size_t)1 << p.twist_shift, hi = N >> p.twist_shift;
-        if ((rc = upload(c, host::power_table_mont(w, lo), p.twist_lo))) return rc;
-        if ((rc = upload(c, host::power_table_mont(host::pow(w, lo), hi), p.twist_hi))) return rc;
+        if (logn <= 20) {                                       // full table (<= 32 MiB): one multiplication per element
+            if ((rc = upload(c, host::power_table_mont(w, N), p.twist_full))) return rc;                // w^e, e = i2*k1 < N
+        } else {
+            p.twist_shift = (logn + 1) / 2;
+            const size_t lo = (size_t)1 << p.twist_shift, hi = N >> p.twist_shift;
+            if ((rc = upload(c, host::power_table_mont(w, lo), p.twist_lo))) return rc;
+            if ((rc = upload(c, host::power_table_mont(host::pow(w, lo), hi), p.twist_hi))) return rc;
+        }
     }
     if (inverse) {
         std::vector<Fr> s(1, host::to_mont(host::inv(host::from_u64(N))));
@@ -146,63 +152,95 @@ static int get_plan(lgr_ctx *c, int logn, const Fr &omega, bool inverse, NttPlan
     return LGR_OK;
 }
 
-// a CTA owns up to 2048 elements (64 KiB of shared memory) and 256 threads
+// a CTA owns up to 1024 elements (32 KiB of shared memory, 128 threads; four CTAs per SM) -- measured
+// 12% faster on the 2^20 transform than 2048-element / 256-thread tiles; 2048-point sub-transforms
+// take one lane of 256 threads
 static int lanes_per_cta(int logm) {
     const int M = 1 << logm;
-    int C = std::max(1, 2048 / M);
+    static const int tile = getenv("LGR_NTT_TILE") ? atoi(getenv("LGR_NTT_TILE")) : 1024;   // tuning knob
+    int C = std::max(1, tile / M);
     const int TL = M >= 8 ? M / 8 : 1;
     if (C * TL > 256) C = 256 / TL;
     return std::max(C, 1);
 }
 
-// batch transforms of 2^logn points; transform b starts at buf + b*batch_stride (elements)
-static int run_ntt(lgr_ctx *c, fr_mem *buf, NttPlan &p, uint32_t batch, size_t batch_stride) {
-    if (batch == 0) return LGR_OK;
+// One batched transform job.  Plain mode: `batch` transforms, transform b read at in + b*in_stride and
+// written to out + b*out_stride (in place allowed for single-pass plans; four-step plans go through
+// `tmp`, batch*N elements).  Coset mode (coset_in_twist != nullptr, large-k encoder): the batch index
+// packs (row, r) = (b >> 2, b & 3); input row `row` is read from in + row*in_stride and multiplied by
+// coset_in_twist[r*N + i]; output element m of coset r goes to out + row*out_stride + 4*m + r.
+struct NttJob {
+    const fr_mem *in; long long in_stride;
+    fr_mem *out; long long out_stride;
+    fr_mem *tmp;
+    uint32_t batch;
+    const fr_mem *coset_in_twist;
+    bool no_scale;
+};
+
+static int run_ntt_job(lgr_ctx *c, NttPlan &p, const NttJob &j) {
+    if (j.batch == 0) return LGR_OK;
     const long long N = 1ll << p.logn;
+    const bool coset = j.coset_in_twist != nullptr;
+    const fr_mem *scale = (p.inverse && !j.no_scale) ? p.scale.d : nullptr;
     NttTileParams q{};
     q.in_natural = 1;
     if (p.l2 == 0) {
-        q.in = buf; q.out = buf;
-        q.in_outer_stride = q.out_outer_stride = 0;
-        q.in_lane_stride = q.out_lane_stride = (long long)batch_stride;
+        REQUIRE(!coset, "internal: coset mode needs a four-step plan");
+        q.in = j.in; q.out = j.out;
+        q.in_lane_stride = j.in_stride; q.out_lane_stride = j.out_stride;
         q.in_point_stride = q.out_point_stride = 1;
-        q.lanes_inner = (int)batch; q.total_lanes = (int)batch;
+        q.lanes_inner = (int)j.batch; q.total_lanes = (int)j.batch;
         q.logm = p.l1; q.lanes_per_cta = lanes_per_cta(p.l1);
         q.tw = p.tw1.d; q.tws = 1;
-        q.scale = p.inverse ? p.scale.d : nullptr;
+        q.scale = scale;
         q.canon = 1;
         CU(launch_ntt_tile(q, c->stream)); c->launches++;
         return LGR_OK;
     }
     const long long N1 = 1ll << p.l1, N2 = 1ll << p.l2;
-    REQUIRE((unsigned long long)batch * (unsigned long long)N2 < (1ull << 31) && (unsigned long long)batch * (unsigned long long)N1 < (1ull << 31), "batch too large");
-    int rc = ensure_scratch(c, (size_t)batch * (size_t)N);
-    if (rc) return rc;
-    // pass 1: for every column i2, N1-point transform over i1 (stride N2), twist by w^(i2*k1); user -> scratch
-    q.in = buf; q.out = c->scratch;
-    q.in_outer_stride = (long long)batch_stride; q.out_outer_stride = N;
+    REQUIRE((unsigned long long)j.batch * (unsigned long long)N2 < (1ull << 31) && (unsigned long long)j.batch * (unsigned long long)N1 < (1ull << 31), "batch too large");
+    REQUIRE(j.tmp, "internal: four-step plan without scratch");
+    // pass 1: for every column i2, N1-point transform over i1 (stride N2), twist by w^(i2*k1); in -> tmp
+    q.in = j.in; q.out = j.tmp;
+    q.in_outer_stride = j.in_stride; q.out_outer_stride = N;
     q.in_lane_stride = q.out_lane_stride = 1;
     q.in_point_stride = q.out_point_stride = N2;
-    q.lanes_inner = (int)N2; q.total_lanes = (int)(batch * N2);
+    q.lanes_inner = (int)N2; q.total_lanes = (int)(j.batch * N2);
     q.logm = p.l1; q.lanes_per_cta = lanes_per_cta(p.l1);
     q.tw = p.tw1.d; q.tws = 1;
-    q.twist_lo = p.twist_lo.d; q.twist_hi = p.twist_hi.d; q.twist_shift = p.twist_shift;
+    q.twist_full = p.twist_full.d; q.twist_lo = p.twist_lo.d; q.twist_hi = p.twist_hi.d; q.twist_shift = p.twist_shift;
+    if (coset) { q.in_outer_shift = 2; q.in_twist = j.coset_in_twist; q.in_twist_sub_stride = N; }
     q.scale = nullptr; q.canon = 0;
     CU(launch_ntt_tile(q, c->stream)); c->launches++;
-    // pass 2: for every k1, N2-point transform over i2 (contiguous); output index k1 + N1*k2; scratch -> user
+    // pass 2: for every k1, N2-point transform over i2 (contiguous); output index k1 + N1*k2; tmp -> out
     NttTileParams r{};
     r.in_natural = 1;
-    r.in = c->scratch; r.out = buf;
-    r.in_outer_stride = N; r.out_outer_stride = (long long)batch_stride;
+    r.in = j.tmp; r.out = j.out;
+    r.in_outer_stride = N;
     r.in_lane_stride = N2; r.in_point_stride = 1;
-    r.out_lane_stride = 1; r.out_point_stride = N1;
-    r.lanes_inner = (int)N1; r.total_lanes = (int)(batch * N1);
+    if (coset) {
+        r.out_outer_shift = 2; r.out_outer_stride = j.out_stride; r.out_sub_stride = 1;
+        r.out_lane_stride = 4; r.out_point_stride = 4 * N1;
+    } else {
+        r.out_outer_stride = j.out_stride;
+        r.out_lane_stride = 1; r.out_point_stride = N1;
+    }
+    r.lanes_inner = (int)N1; r.total_lanes = (int)(j.batch * N1);
     r.logm = p.l2; r.lanes_per_cta = lanes_per_cta(p.l2);
     r.tw = p.tw2.d; r.tws = 1;
-    r.scale = p.inverse ? p.scale.d : nullptr;
+    r.scale = scale;
     r.canon = 1;
     CU(launch_ntt_tile(r, c->stream)); c->launches++;
     return LGR_OK;
+}
+
+// batch transforms of 2^logn points in place; transform b starts at buf + b*batch_stride (elements)
+static int run_ntt(lgr_ctx *c, fr_mem *buf, NttPlan &p, uint32_t batch, size_t batch_stride) {
+    if (batch == 0) return LGR_OK;
+    if (p.l2 != 0) { int rc = ensure_scratch(c, (size_t)batch << p.logn); if (rc) return rc; }
+    NttJob j{buf, (long long)batch_stride, buf, (long long)batch_stride, c->scratch, batch, nullptr, false};
+    return run_ntt_job(c, p, j);
 }
 
 static int ilog2u(uint64_t x) { int l = 0; while ((1ull << l) < x) l++; return l; }
@@ -232,6 +270,23 @@ static int build_encode_tables(lgr_ctx *c) {
     return LGR_OK;
 }
 
+// coset twist for the tile-engine encoder: [4][k], natural index: w_n^(r*i) / k * R
+static int build_large_encode_tables(lgr_ctx *c) {
+    if (c->enc_large_twist) return LGR_OK;
+    const size_t k = c->k;
+    std::vector<Fr> tw(4 * k);
+    const Fr kinv_m = host::to_mont(host::inv(host::from_u64(k)));
+    for (int r = 0; r < 4; r++) {
+        std::vector<Fr> pw = host::power_table_mont(host::pow(c->root_n, r), k);
+        for (size_t i = 0; i < k; i++) tw[r * k + i] = host::montmul(pw[i], kinv_m);
+    }
+    DevTable t;
+    int rc = upload(c, tw, t);
+    if (rc) return rc;
+    c->enc_large_twist = t.d;
+    return LGR_OK;
+}
+
 static bool fused_encode_ok(const lgr_ctx *c) { return c->logk >= encode_rows_min_logk() && c->logk <= encode_rows_max_logk(); }
 
 // nrows encodes: rows -> codewords (may alias when in place)
@@ -243,17 +298,25 @@ static int encode_rows_impl(lgr_ctx *c, const fr_mem *rows, size_t row_stride, u
         CU(launch_encode_rows(rows, (long long)row_stride, cw, (long long)c->n, (int)nrows, c->logk, c->enc, st)); c->launches++;
         return LGR_OK;
     }
-    // large k: the reference's composition (engine.cpp:755-770) on the generic engine
-    REQUIRE(st == c->stream, "internal: generic encode runs on the main stream");
-    if ((const void *)rows != (const void *)cw || row_stride != c->n) {
-        CU(cudaMemsetAsync(cw, 0, (size_t)nrows * c->n * 32, st));
-        CU(cudaMemcpy2DAsync(cw, (size_t)c->n * 32, rows, row_stride * 32, (size_t)c->k * 32, nrows, cudaMemcpyDeviceToDevice, st));
-    }
-    NttPlan *pi, *pf; int rc;
+    // large k (> 2048): same decomposition as the fused kernel, on the tile engine.  Coefficients
+    // c = iNTT_k(row) (four-step, unscaled) go to scratch; the four coset transforms
+    // e[4m+r] = NTT_k(c_i * w_n^(r i) / k) with root w_n^4 run as one batched four-step job whose first
+    // pass applies the coset twist on load and whose second pass writes the interleaved codeword.
+    // The zero padding of engine.cpp:755-770's NTT_n is never touched.
+    REQUIRE(st == c->stream, "internal: the tile engine runs on the main stream");
+    REQUIRE(c->logk > ntt_tile_max_logm(), "internal: small k takes the fused encoder");
+    const size_t k = c->k;
+    int rc;
+    if ((rc = build_large_encode_tables(c))) return rc;
+    NttPlan *pi, *pf;
     if ((rc = get_plan(c, c->logk, c->root_k, true, &pi))) return rc;
-    if ((rc = get_plan(c, c->logk + 2, c->root_n, false, &pf))) return rc;
-    if ((rc = run_ntt(c, cw, *pi, nrows, c->n))) return rc;
-    return run_ntt(c, cw, *pf, nrows, c->n);
+    if ((rc = get_plan(c, c->logk, host::pow(c->root_n, 4), false, &pf))) return rc;
+    if ((rc = ensure_scratch(c, (size_t)nrows * k * 5))) return rc;
+    fr_mem *coef = c->scratch, *tmp = c->scratch + (size_t)nrows * k;
+    NttJob inv{rows, (long long)row_stride, coef, (long long)k, tmp, nrows, nullptr, true};
+    if ((rc = run_ntt_job(c, *pi, inv))) return rc;
+    NttJob fwd{coef, (long long)k, cw, (long long)c->n, tmp, nrows * 4, c->enc_large_twist, false};
+    return run_ntt_job(c, *pf, fwd);
 }
 
 // ================================================================================================
@@ -540,7 +603,7 @@ static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host
     REQUIRE(nrows < (1ull << 40), "too many rows");
     const size_t n = c->n, k = c->k;
     const size_t T = commit_tile_rows(c, nrows);
-    const bool overlap = fused_encode_ok(c);            // generic-engine encodes use the main stream + shared scratch
+    const bool overlap = true;                          // encodes on the main stream, hashing on the aux stream
     if (c->tile_elems < T * n) {
         CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(c->aux_stream));
         for (int i = 0; i < 2; i++) { if (c->tile[i]) CU(cudaFree(c->tile[i])); c->tile[i] = nullptr; }
@@ -604,7 +667,7 @@ int lgr_encode_commit_host(lgr_ctx *c, const void *host_rows, uint64_t nrows, vo
     const size_t need = n + (2 * n - 1);                // digests + nodes, in elements of 32 bytes
     int rc = LGR_OK;
     // results live at the tail of the scratch buffer (not used by the fused encoder)
-    if (!fused_encode_ok(c)) { if ((rc = ensure_scratch(c, (size_t)c->n * commit_tile_rows(c, nrows) + need))) return rc; }
+    if (!fused_encode_ok(c)) { if ((rc = ensure_scratch(c, (size_t)c->k * 5 * commit_tile_rows(c, nrows) + need))) return rc; }
     else if ((rc = ensure_scratch(c, need))) return rc;
     fr_mem *dig = c->scratch + (c->scratch_elems - need), *nodes = dig + n;
     if ((rc = encode_commit_impl(c, nullptr, (const fr_mem *)host_rows, nrows, dig, nodes))) return rc;
@@ -632,22 +695,32 @@ int lgr_profile_read(lgr_ctx *c, double *enc_ms, uint64_t *enc_launches, double 
 }
 
 // ---- stage-2 tile combiners --------------------------------------------------------------------
+// upload nrows canonical scalars to scratch + at (raw; the kernels rescale them on the device)
+static int upload_scalars(lgr_ctx *c, const uint32_t *host_r, uint32_t nrows, size_t at) {
+    for (uint32_t i = 0; i < nrows; i++) REQUIRE(host::is_canonical(host::from_u32(host_r + 8 * i)), "scalar is not reduced modulo p");
+    return lgr_write(c, c->scratch + at, 0, host_r, (size_t)nrows * 32);
+}
 int lgr_combine_code(lgr_ctx *c, const void *tile, uint32_t nrows, const uint32_t *host_r, void *acc) {
     REQUIRE(c && tile && host_r && acc, "null argument");
     if (!nrows) return LGR_OK;
     const size_t part = combine_scratch_elems((int)nrows, (int)c->n);
-    int rc = ensure_scratch(c, part + nrows);
+    int rc = ensure_scratch(c, part + 2 * (size_t)nrows);
     if (rc) return rc;
-    std::vector<Fr> r(nrows);
-    for (uint32_t i = 0; i < nrows; i++) {
-        Fr s = host::from_u32(host_r + 8 * i);
-        REQUIRE(host::is_canonical(s), "scalar is not reduced modulo p");
-        r[i] = host::to_mont(s);
-    }
-    fr_mem *r_dev = c->scratch + part;
-    if ((rc = lgr_write(c, r_dev, 0, r.data(), (size_t)nrows * 32))) return rc;
-    CU(launch_combine_code((const fr_mem *)tile, (long long)c->n, (int)nrows, (int)c->n, r_dev, (fr_mem *)acc, c->scratch, part, c->stream));
-    c->launches += 2;
+    if ((rc = upload_scalars(c, host_r, nrows, part + nrows))) return rc;
+    CU(launch_combine_code((const fr_mem *)tile, (long long)c->n, (int)nrows, (int)c->n, c->scratch + part + nrows, (fr_mem *)acc, c->scratch, part + nrows, c->stream));
+    c->launches += 3;
+    return LGR_OK;
+}
+int lgr_combine_quad(lgr_ctx *c, const void *x, const void *y, const void *z, uint32_t nrows, const uint32_t *host_r, void *acc) {
+    REQUIRE(c && x && y && z && host_r && acc, "null argument");
+    if (!nrows) return LGR_OK;
+    const size_t part = combine_scratch_elems((int)nrows, (int)c->n);
+    int rc = ensure_scratch(c, part + 3 * (size_t)nrows);
+    if (rc) return rc;
+    if ((rc = upload_scalars(c, host_r, nrows, part + 2 * (size_t)nrows))) return rc;
+    CU(launch_combine_quad((const fr_mem *)x, (const fr_mem *)y, (const fr_mem *)z, (long long)c->n, (int)nrows, (int)c->n, c->scratch + part + 2 * (size_t)nrows,
+                           (fr_mem *)acc, c->scratch, part + 2 * (size_t)nrows, c->stream));
+    c->launches += 4;
     return LGR_OK;
 }
 int lgr_combine_linear(lgr_ctx *c, const void *a, const void *b, uint32_t nrows, void *acc) {
@@ -669,11 +742,11 @@ int lgr_synth(lgr_ctx *c, void *out, uint64_t seed, uint64_t row0, uint64_t nrow
 }
 int lgr_ubench(lgr_ctx *c, int which, double *ops) {
     REQUIRE(c && ops, "null argument");
-    REQUIRE(which >= 0 && which <= 2, "unknown micro-benchmark");
+    REQUIRE(which >= 0 && which <= 4, "unknown micro-benchmark");
     uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
     cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     const int blocks = 148 * 8, threads = 256;
-    const int iters = which == 0 ? 4096 : (which == 1 ? 512 : 256);
+    const int iters = (which == 0 || which >= 3) ? 4096 : (which == 1 ? 512 : 256);
     CU(launch_ubench(which, d, iters, blocks, threads, c->stream));           // warm-up
     CU(cudaEventRecord(e0, c->stream));
     for (int i = 0; i < 5; i++) CU(launch_ubench(which, d, iters, blocks, threads, c->stream));
@@ -681,7 +754,7 @@ int lgr_ubench(lgr_ctx *c, int which, double *ops) {
     CU(cudaEventSynchronize(e1));
     c->launches += 6;
     float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
-    const double per_thread = which == 0 ? 8.0 * iters : (double)iters * (which == 1 ? 4.0 : 1.0);
+    const double per_thread = (which == 0 || which >= 3) ? 8.0 * iters : (double)iters * (which == 1 ? 4.0 : 1.0);
     *ops = 5.0 * per_thread * blocks * threads / (ms * 1e-3);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return LGR_OK;

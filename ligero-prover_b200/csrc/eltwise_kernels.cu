@@ -129,28 +129,98 @@ cudaError_t launch_eltwise(EltOp op, const EltParams &p, cudaStream_t st) {
 }
 
 // ---- tile combiners ----------------------------------------------------------------------------
-// One sweep over a resident tile of T codeword rows: every thread owns one column of one row
-// chunk, accumulates lazily in [0,2p), and the per-chunk partial sums are folded into acc by a
-// second small kernel.  32 bytes read per codeword element (SURVEY 8d iii).
-constexpr int kCombineChunk = 32;
+// One sweep over a resident tile of T codeword rows: every thread owns one column of one 64-row
+// chunk and accumulates the plain 512-bit products in a 576-bit accumulator (fr.cuh: wide_mad, 64
+// wide multiply-adds per element instead of the 136 of a Montgomery multiplication, no reduction per
+// element); one 9-round Montgomery reduction per chunk.  The per-chunk partial sums are folded into
+// acc by a second small kernel.  32 bytes (code) / 64 bytes (linear) read per codeword element
+// (SURVEY 8d iii): with the multiplier work halved the sweep is bound by HBM.
+//   code  : scalars arrive pre-multiplied by 2^288, so the reduction returns sum r_t*e_t directly
+//   linear: the reduction returns S*2^-288; one Montgomery multiplication by 2^544 undoes it
+constexpr int kCombineChunk = 64;
 size_t combine_scratch_elems(int T, int n) { return (size_t)((T + kCombineChunk - 1) / kCombineChunk) * n; }
+
+__device__ __forceinline__ fr_t fr_2p544() {       // 2^544 mod p
+    fr_t r;
+    r.v[0] = 0x04f2bf4fu; r.v[1] = 0x6dae765eu; r.v[2] = 0xa11298d6u; r.v[3] = 0x347d7b17u;
+    r.v[4] = 0xf603929eu; r.v[5] = 0x70f88a97u; r.v[6] = 0x83e5893eu; r.v[7] = 0x0ad4bd84u;
+    return r;
+}
+
+// r_scaled[t] = r[t] * 2^288 mod p (canonical): montmul by 2^544
+__global__ void combine_scale_kernel(const fr_mem *__restrict__ r, int T, fr_mem *__restrict__ r_scaled) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) fr_stg(r_scaled + t, fr_reduce_p(fr_mont_mul(fr_ldg(r + t), fr_2p544())));
+}
 
 template <bool LINEAR>
 __global__ void __launch_bounds__(128) combine_partial_kernel(const fr_mem *__restrict__ a, const fr_mem *__restrict__ b, long long row_stride,
-                                                              int T, int n, const fr_mem *__restrict__ r_mont, fr_mem *__restrict__ partial) {
+                                                              int T, int n, const fr_mem *__restrict__ r_scaled, fr_mem *__restrict__ partial) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = blockIdx.y;
     if (j >= n) return;
     const int t0 = chunk * kCombineChunk, t1 = min(T, t0 + kCombineChunk);
-    fr_t s = fr_zero();
-    for (int t = t0; t < t1; t++) {
-        fr_t e = fr_ldg(a + (long long)t * row_stride + j);
-        fr_t m;
-        if (LINEAR) m = fr_mul_canon(e, fr_ldg(b + (long long)t * row_stride + j));
-        else m = fr_mont_mul(e, fr_ldc(r_mont + t));           // e * r, [0,2p)
-        s = fr_add_lazy(s, m);
+    fr_wide w;
+    wide_zero(w);
+    const fr_mem *pa = a + (long long)t0 * row_stride + j;
+    const fr_mem *pb = LINEAR ? b + (long long)t0 * row_stride + j : r_scaled + t0;
+    int t = t0;
+    for (; t + 1 < t1; t += 2) {                               // two rows in flight per thread
+        fr_t e0 = fr_ldg(pa), e1 = fr_ldg(pa + row_stride);
+        fr_t m0 = LINEAR ? fr_ldg(pb) : fr_ldc(pb);
+        fr_t m1 = LINEAR ? fr_ldg(pb + row_stride) : fr_ldc(pb + 1);
+        wide_mad(w, e0, m0);
+        wide_mad(w, e1, m1);
+        pa += 2 * row_stride;
+        pb += LINEAR ? 2 * row_stride : 2;
     }
+    if (t < t1) {
+        fr_t e0 = fr_ldg(pa);
+        fr_t m0 = LINEAR ? fr_ldg(pb) : fr_ldc(pb);
+        wide_mad(w, e0, m0);
+    }
+    fr_t s = wide_reduce9(w);                                  // [0,2p)
+    if (LINEAR) s = fr_mont_mul(s, fr_2p544());
     fr_stg(partial + (size_t)chunk * n + j, fr_reduce_p(s));
+}
+// check_quadratic over resident tiles (nonbatch_context.hpp:771-780): partial = sum_t r_t*(X_t*Y_t - Z_t)
+//   = REDC9( sum_t (r_t X_t mod p) * Y_t ) * 2^288  -  REDC9( sum_t (r_t 2^288) * Z_t )
+// one Montgomery multiplication + two wide products per triple element, 96 bytes read
+__global__ void __launch_bounds__(128) combine_quad_kernel(const fr_mem *__restrict__ x, const fr_mem *__restrict__ y, const fr_mem *__restrict__ z,
+                                                           long long row_stride, int T, int n, const fr_mem *__restrict__ r_mont,
+                                                           const fr_mem *__restrict__ r_scaled, fr_mem *__restrict__ partial) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.y;
+    if (j >= n) return;
+    const int t0 = chunk * kCombineChunk, t1 = min(T, t0 + kCombineChunk);
+    fr_wide wp, wz;
+    wide_zero(wp); wide_zero(wz);
+    for (int t = t0; t < t1; t++) {
+        const long long off = (long long)t * row_stride + j;
+        fr_t rx = fr_reduce_p(fr_mont_mul(fr_ldg(x + off), fr_ldc(r_mont + t)));     // r_t * X, canonical
+        wide_mad(wp, rx, fr_ldg(y + off));
+        wide_mad(wz, fr_ldg(z + off), fr_ldc(r_scaled + t));
+    }
+    fr_t a = fr_reduce_p(fr_mont_mul(wide_reduce9(wp), fr_2p544()));
+    fr_t b = fr_reduce_p(wide_reduce9(wz));
+    fr_stg(partial + (size_t)chunk * n + j, fr_sub(a, b));
+}
+// r_mont[t] = r[t] * 2^256 mod p
+__global__ void combine_mont_kernel(const fr_mem *__restrict__ r, int T, fr_mem *__restrict__ r_mont) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) fr_stg(r_mont + t, fr_reduce_p(fr_mont_mul(fr_ldg(r + t), fr_R2())));
+}
+// partial sums -> acc, two levels so that narrow matrices (n = 1024, thousands of chunks) do not
+// serialise thousands of dependent loads per thread: level 1 folds chunk c into group c % G (in place
+// on the first G rows of `partial`), level 2 adds the G group sums to acc
+constexpr int kFoldGroups = 32;
+__global__ void combine_fold1_kernel(fr_mem *__restrict__ partial, int chunks, int n, int G) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (j >= n) return;
+    fr_t s = fr_ldg(partial + (size_t)g * n + j);
+    for (int c = g + G; c < chunks; c += G) s = fr_add(s, fr_ldg(partial + (size_t)c * n + j));
+    fr_stg(partial + (size_t)g * n + j, s);
 }
 __global__ void combine_fold_kernel(const fr_mem *__restrict__ partial, int chunks, int n, fr_mem *acc) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,15 +229,24 @@ __global__ void combine_fold_kernel(const fr_mem *__restrict__ partial, int chun
     for (int c = 0; c < chunks; c++) s = fr_add(s, fr_ldg(partial + (size_t)c * n + j));
     fr_stg(acc + j, s);
 }
+static void launch_fold(fr_mem *partial, int chunks, int n, fr_mem *acc, cudaStream_t st) {
+    if (chunks > 2 * kFoldGroups) {
+        combine_fold1_kernel<<<dim3((n + 127) / 128, kFoldGroups), 128, 0, st>>>(partial, chunks, n, kFoldGroups);
+        chunks = kFoldGroups;
+    }
+    combine_fold_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, chunks, n, acc);
+}
 
-cudaError_t launch_combine_code(const fr_mem *tile, long long row_stride, int T, int n, const fr_mem *r_mont, fr_mem *acc,
+cudaError_t launch_combine_code(const fr_mem *tile, long long row_stride, int T, int n, const fr_mem *r_raw, fr_mem *acc,
                                 fr_mem *scratch, size_t scratch_elems, cudaStream_t st) {
     if (T <= 0 || n <= 0) return cudaSuccess;
     const int chunks = (T + kCombineChunk - 1) / kCombineChunk;
-    if (scratch_elems < (size_t)chunks * n) return cudaErrorInvalidValue;
+    if (scratch_elems < (size_t)chunks * n + T) return cudaErrorInvalidValue;
     dim3 grid((n + 127) / 128, chunks);
-    combine_partial_kernel<false><<<grid, 128, 0, st>>>(tile, nullptr, row_stride, T, n, r_mont, scratch);
-    combine_fold_kernel<<<(n + 127) / 128, 128, 0, st>>>(scratch, chunks, n, acc);
+    fr_mem *r_scaled = scratch + (size_t)chunks * n;
+    combine_scale_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_raw, T, r_scaled);
+    combine_partial_kernel<false><<<grid, 128, 0, st>>>(tile, nullptr, row_stride, T, n, r_scaled, scratch);
+    launch_fold(scratch, chunks, n, acc, st);
     return cudaGetLastError();
 }
 cudaError_t launch_combine_linear(const fr_mem *a, const fr_mem *b, long long row_stride, int T, int n, fr_mem *acc,
@@ -177,7 +256,21 @@ cudaError_t launch_combine_linear(const fr_mem *a, const fr_mem *b, long long ro
     if (scratch_elems < (size_t)chunks * n) return cudaErrorInvalidValue;
     dim3 grid((n + 127) / 128, chunks);
     combine_partial_kernel<true><<<grid, 128, 0, st>>>(a, b, row_stride, T, n, nullptr, scratch);
-    combine_fold_kernel<<<(n + 127) / 128, 128, 0, st>>>(scratch, chunks, n, acc);
+    launch_fold(scratch, chunks, n, acc, st);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_combine_quad(const fr_mem *x, const fr_mem *y, const fr_mem *z, long long row_stride, int T, int n, const fr_mem *r_raw,
+                                fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st) {
+    if (T <= 0 || n <= 0) return cudaSuccess;
+    const int chunks = (T + kCombineChunk - 1) / kCombineChunk;
+    if (scratch_elems < (size_t)chunks * n + 2 * (size_t)T) return cudaErrorInvalidValue;
+    dim3 grid((n + 127) / 128, chunks);
+    fr_mem *r_scaled = scratch + (size_t)chunks * n, *r_mont = r_scaled + T;
+    combine_scale_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_raw, T, r_scaled);
+    combine_mont_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_raw, T, r_mont);
+    combine_quad_kernel<<<grid, 128, 0, st>>>(x, y, z, row_stride, T, n, r_mont, r_scaled, scratch);
+    launch_fold(scratch, chunks, n, acc, st);
     return cudaGetLastError();
 }
 

@@ -198,6 +198,7 @@ LGR_DEV void mad_row(uint32_t *even, uint32_t *odd, const uint32_t *a, uint32_t 
 }  // namespace detail
 
 // a in [0,4p), b in [0,p)  ->  a*b*2^-256 mod p, in [0,2p)
+// (kept inline: a real call passes the operands through a 352-byte local stack frame -- measured, slower)
 LGR_DEV fr_t fr_mont_mul(const fr_t &a, const fr_t &b) {
     uint32_t even[8], odd[8];
 #pragma unroll
@@ -215,6 +216,68 @@ LGR_DEV fr_t fr_mont_mul(const fr_t &a, const fr_t &b) {
 
 // canonical result
 LGR_DEV fr_t fr_mont_mul_canon(const fr_t &a, const fr_t &b) { return fr_canon4(fr_mont_mul(a, b)); }
+
+// ---- wide (unreduced) accumulation of products ----------------------------------------------
+// S += a*b as a plain 512-bit product added into a 576-bit accumulator: 64 wide multiply-adds and no
+// reduction per product (a Montgomery multiplication costs 136).  The accumulator is kept as an
+// even-aligned limb array E (limbs 0..15), an odd-aligned one O (O[x] = limb x+1, limbs 1..15) and
+// per-limb carry counters C (limbs 8..16), so every partial-product row is one 8-limb carry chain
+// plus one addc.  wide_reduce9 merges them and runs 9 Montgomery rounds:
+//   result = S * 2^-288 mod p, in [0,2p), valid for S < 2^540 (e.g. 2^32 products of canonical values)
+struct fr_wide { uint32_t e[16], o[15], c[17]; };
+
+LGR_DEV void wide_zero(fr_wide &w) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) w.e[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 15; i++) w.o[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 17; i++) w.c[i] = 0;
+}
+LGR_DEV void wide_mad(fr_wide &w, const fr_t &a, const fr_t &b) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        detail::cmad_n(w.e + i, a.v, b.v[i]);          w.c[i + 8] = addc(w.c[i + 8], 0);    // even j: limbs i..i+7
+        detail::cmad_n(w.o + i, a.v + 1, b.v[i]);      w.c[i + 9] = addc(w.c[i + 9], 0);    // odd j:  limbs i+1..i+8
+        detail::cmad_n(w.o + i, a.v, b.v[i + 1]);      w.c[i + 9] = addc(w.c[i + 9], 0);    // even j: limbs i+1..i+8
+        detail::cmad_n(w.e + i + 2, a.v + 1, b.v[i + 1]); w.c[i + 10] = addc(w.c[i + 10], 0); // odd j: limbs i+2..i+9
+    }
+}
+LGR_DEV fr_t wide_reduce9(const fr_wide &w) {
+    uint32_t v[18];
+    // v = E + (O << 32) + (C << 32*limb)
+    v[0] = w.e[0];
+    v[1] = add_cc(w.e[1], w.o[0]);
+#pragma unroll
+    for (int i = 2; i < 16; i++) v[i] = addc_cc(w.e[i], w.o[i - 1]);
+    v[16] = addc_cc(0, 0);
+    v[17] = 0;
+    v[8] = add_cc(v[8], w.c[8]);
+#pragma unroll
+    for (int i = 9; i < 17; i++) v[i] = addc_cc(v[i], w.c[i]);
+    v[17] = addc(v[17], 0);
+    // 9 Montgomery rounds: v[r] becomes 0, the value shifts down by 288 bits in total
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        const uint32_t m = mul_lo(v[r], LGR_M0);
+        v[r] = mad_lo_cc(m, fr_p(0), v[r]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) v[r + j] = madc_lo_cc(m, fr_p(j), v[r + j]);
+#pragma unroll
+        for (int j = r + 8; j < 17; j++) v[j] = addc_cc(v[j], 0);
+        v[17] = addc(v[17], 0);
+        v[r + 1] = mad_hi_cc(m, fr_p(0), v[r + 1]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) v[r + 1 + j] = madc_hi_cc(m, fr_p(j), v[r + 1 + j]);
+#pragma unroll
+        for (int j = r + 9; j < 17; j++) v[j] = addc_cc(v[j], 0);
+        v[17] = addc(v[17], 0);
+    }
+    fr_t res;
+#pragma unroll
+    for (int i = 0; i < 8; i++) res.v[i] = v[9 + i];
+    return res;
+}
 
 LGR_DEV bool fr_eq(const fr_t &a, const fr_t &b) {
     uint32_t d = 0;

@@ -22,9 +22,17 @@ struct NttTileParams {
     int logm;
     const fr_mem *tw;        // tw[j*tws] = w_M^j * R, j < M/2 (inverse root for inverse transforms)
     int tws;
-    // optional four-step twist: out(inner, m) *= w_N^(inner*m) = twist_hi[e >> shift] * twist_lo[e & mask]
-    const fr_mem *twist_lo, *twist_hi;
+    // optional four-step twist: out(inner, m) *= w_N^(inner*m): one lookup in twist_full (small N) or
+    // twist_hi[e >> shift] * twist_lo[e & mask] composed on the fly
+    const fr_mem *twist_lo, *twist_hi, *twist_full;
     int twist_shift;
+    // coset mode (large-k encoder): the outer index packs (row, r) as outer = row << shift | r.
+    //   input : row = outer >> in_outer_shift is used for addressing; every loaded element is multiplied
+    //           by in_twist[(outer & mask) * in_twist_sub_stride + element offset within the row]
+    //   output: base = (outer >> out_outer_shift) * out_outer_stride + (outer & mask) * out_sub_stride
+    int in_outer_shift, out_outer_shift;
+    const fr_mem *in_twist;
+    long long in_twist_sub_stride, out_sub_stride;
     const fr_mem *scale;     // optional N^-1 * R (Montgomery form)
     int canon;               // 1: outputs reduced to [0,p)
     int in_natural;          // 1: input natural order (bit-reverse on load, DIT); 0 never used here
@@ -61,12 +69,15 @@ struct EltParams {
 cudaError_t launch_eltwise(EltOp op, const EltParams &p, cudaStream_t st);
 
 // tile combiners: acc[j] (+)= sum_t r[t] * tile[t][j]   (check_code over a resident tile)
-cudaError_t launch_combine_code(const fr_mem *tile, long long row_stride, int T, int n, const fr_mem *r_mont /*[T], r*R*/,
+cudaError_t launch_combine_code(const fr_mem *tile, long long row_stride, int T, int n, const fr_mem *r_raw /*[T] canonical scalars (device)*/,
                                 fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st);
 // acc[j] += sum_t a[t][j] * b[t][j]   (check_linear over two resident tiles)
 cudaError_t launch_combine_linear(const fr_mem *a, const fr_mem *b, long long row_stride, int T, int n,
                                   fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st);
-size_t combine_scratch_elems(int T, int n);
+// acc[j] += sum_t r[t] * (x[t][j]*y[t][j] - z[t][j])   (check_quadratic over resident tiles)
+cudaError_t launch_combine_quad(const fr_mem *x, const fr_mem *y, const fr_mem *z, long long row_stride, int T, int n, const fr_mem *r_raw,
+                                fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st);
+size_t combine_scratch_elems(int T, int n);   // partial sums only; callers add T (code) or 2T (quad) for scalars
 
 // ---- SHA-256 column hashing + Merkle (sha_kernels.cu) ----------------------------------------
 // ctx layout (u32 words): state[8][n] | pend[8][n] | rows_lo[n] | rows_hi[n]

@@ -70,8 +70,12 @@ LGR_DEV void ntt_pass_io(int tl, const fr_mem *__restrict__ tw, int tws, Load lo
             const int h = 1 << s;
 #pragma unroll
             for (int jl = 0; jl < h; jl++) {
+                // twiddle exponent e = low*(M>>(b+1)) + jl*(M>>(s+1)); it is 0 (w = 1, no multiplication)
+                // for the whole of stage b = 0 and, in the pass that owns bit 0 (low == 0), whenever
+                // jl == 0 -- both known at compile time: 3 of the 8 multiplications of that pass
+                const bool mul = (b > 0) && !(LO == 0 && jl == 0);
                 fr_t w;
-                if (b > 0) {
+                if (mul) {
                     const int e = low * (M >> (b + 1)) + jl * (M >> (s + 1));
                     w = fr_ldc(tw + (size_t)e * tws);
                 }
@@ -82,10 +86,10 @@ LGR_DEV void ntt_pass_io(int tl, const fr_mem *__restrict__ tw, int tws, Load lo
                     if (DIF) {
                         fr_t u = x[j0], v = x[j1];
                         x[j0] = fr_add_lazy(u, v);
-                        x[j1] = (b > 0) ? fr_mont_mul(fr_sub_lazy4(u, v), w) : fr_sub_lazy(u, v);
+                        x[j1] = mul ? fr_mont_mul(fr_sub_lazy4(u, v), w) : fr_sub_lazy(u, v);
                     } else {
                         fr_t u = fr_reduce_2p(x[j0]);
-                        fr_t t = (b > 0) ? fr_mont_mul(x[j1], w) : fr_reduce_2p(x[j1]);
+                        fr_t t = mul ? fr_mont_mul(x[j1], w) : fr_reduce_2p(x[j1]);
                         x[j0] = fr_add_raw(u, t);
                         x[j1] = fr_sub_lazy4(u, t);
                     }

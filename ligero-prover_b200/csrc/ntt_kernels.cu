@@ -32,7 +32,10 @@ __global__ void __launch_bounds__(256, 2) ntt_tile_kernel(const NttTileParams p)
         if (c < nl) {
             const int L = lane0 + c;
             const long long outer = L / p.lanes_inner, inner = L % p.lanes_inner;
-            fr_t x = fr_ldg(p.in + outer * p.in_outer_stride + inner * p.in_lane_stride + (long long)m * p.in_point_stride);
+            const long long off = inner * p.in_lane_stride + (long long)m * p.in_point_stride;
+            fr_t x = fr_ldg(p.in + (outer >> p.in_outer_shift) * p.in_outer_stride + off);
+            if (p.in_twist)                                             // coset twist (and 1/k) on the way in
+                x = fr_mont_mul(x, fr_ldc(p.in_twist + (outer & ((1ll << p.in_outer_shift) - 1)) * p.in_twist_sub_stride + off));
             fr_sts(sm + (c << LOGM) + bitrev(m, LOGM), x);
         }
     }
@@ -53,14 +56,17 @@ __global__ void __launch_bounds__(256, 2) ntt_tile_kernel(const NttTileParams p)
             const int L = lane0 + c;
             const long long outer = L / p.lanes_inner, inner = L % p.lanes_inner;
             fr_t x = fr_lds(sm + (c << LOGM) + m);                      // [0,4p)
-            if (p.twist_lo) {
+            if (p.twist_full) {
+                x = fr_mont_mul(x, fr_ldc(p.twist_full + (unsigned long long)inner * (unsigned)m));   // [0,2p)
+            } else if (p.twist_lo) {
                 const unsigned long long e = (unsigned long long)inner * (unsigned)m;
                 fr_t w = fr_mont_mul(fr_ldc(p.twist_hi + (e >> p.twist_shift)), fr_ldc(p.twist_lo + (e & ((1ull << p.twist_shift) - 1))));
                 x = fr_mont_mul(x, fr_reduce_p(w));                     // [0,2p)
             }
             if (p.scale) x = fr_mont_mul(x, fr_ldc(p.scale));           // [0,2p)
             if (p.canon) x = fr_canon4(x);
-            fr_stg(p.out + outer * p.out_outer_stride + inner * p.out_lane_stride + (long long)m * p.out_point_stride, x);
+            fr_stg(p.out + (outer >> p.out_outer_shift) * p.out_outer_stride + (outer & ((1ll << p.out_outer_shift) - 1)) * p.out_sub_stride +
+                       inner * p.out_lane_stride + (long long)m * p.out_point_stride, x);
         }
     }
 }

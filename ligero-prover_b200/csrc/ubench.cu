@@ -6,22 +6,41 @@
 
 namespace lgr {
 
-// 8 independent 32x32+64 multiply-add chains per thread
+// 8 independent 32x32+64 multiply-add chains per thread; every chain multiplies its own running low
+// word so that nothing can be hoisted or strength-reduced (WIDE = IMAD.WIDE.U32, otherwise IMAD lo)
+template <bool WIDE>
 __global__ void __launch_bounds__(256) ubench_imad_kernel(uint32_t *out, int iters) {
     unsigned long long a[8];
-    uint32_t x = threadIdx.x * 2654435761u + 12345u, y = blockIdx.x * 40503u + 977u;
+    uint32_t lo[8];
+    const uint32_t y = blockIdx.x * 40503u + 977u + threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < 8; i++) a[i] = (unsigned long long)(x + i) << 20;
+    for (int i = 0; i < 8; i++) { a[i] = ((unsigned long long)(threadIdx.x + i) << 20) | 0x9E3779B1u; lo[i] = threadIdx.x * 2654435761u + i; }
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(x), "r"(y));
-        x += 3;
+        for (int i = 0; i < 8; i++) {
+            if (WIDE) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"((uint32_t)a[i]), "r"(y));
+            else asm volatile("mad.lo.u32 %0, %0, %1, %0;" : "+r"(lo[i]) : "r"(y));
+        }
     }
     unsigned long long s = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) s ^= a[i];
+    for (int i = 0; i < 8; i++) s ^= a[i] ^ lo[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)s ^ (uint32_t)(s >> 32);
+}
+// 8 independent double-precision FMA chains per thread (is the FP64 pipe a second multiplier?)
+__global__ void __launch_bounds__(256) ubench_dfma_kernel(uint32_t *out, int iters) {
+    double a[8];
+    const double y = 1.0 + 1e-9 * threadIdx.x, z = 1e-3 * blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = 1.0 + i + threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = fma(a[i], y, z);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)__double2ll_rn(s);
 }
 
 // 4 independent Montgomery multiplications per iteration
@@ -219,7 +238,9 @@ cudaError_t launch_ubench_mont_occ(int nchain, int warps_per_sm, uint32_t *out, 
 }
 
 cudaError_t launch_ubench(int which, uint32_t *out, int iters, int blocks, int threads, cudaStream_t st) {
-    if (which == 0) ubench_imad_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    if (which == 0) ubench_imad_kernel<true><<<blocks, threads, 0, st>>>(out, iters);
+    else if (which == 3) ubench_imad_kernel<false><<<blocks, threads, 0, st>>>(out, iters);
+    else if (which == 4) ubench_dfma_kernel<<<blocks, threads, 0, st>>>(out, iters);
     else if (which == 1) ubench_mont_kernel<<<blocks, threads, 0, st>>>(out, iters);
     else ubench_sha_kernel<<<blocks, threads, 0, st>>>(out, iters);
     return cudaGetLastError();

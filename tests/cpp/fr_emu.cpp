@@ -6,6 +6,18 @@
 #include <cstddef>
 using namespace lgr;
 extern "C" {
+// out[c] = (sum_t a[t][c] * b[t][c]) * 2^-288 mod p, in [0,2p): wide accumulation + 9-round reduction
+void emu_wide_dot(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, size_t ncols) {
+    for (size_t c = 0; c < ncols; c++) {
+        fr_wide w; wide_zero(w);
+        for (size_t t = 0; t < T; t++) {
+            fr_t x, y; for (int j = 0; j < 8; j++) { x.v[j] = a[8*(t*ncols+c)+j]; y.v[j] = b[8*(t*ncols+c)+j]; }
+            wide_mad(w, x, y);
+        }
+        fr_t r = wide_reduce9(w);
+        for (int j = 0; j < 8; j++) out[8*c+j] = r.v[j];
+    }
+}
 // out[i] = fr_mont_mul(a[i], b[i]) raw (in [0,2p))
 void emu_mont_mul(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t n, int canon) {
     for (size_t i = 0; i < n; i++) {

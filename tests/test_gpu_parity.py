@@ -334,9 +334,9 @@ def test_sample_gather(lgr, oracle, executor_factory):
     assert np.array_equal(got[0], want) and np.array_equal(got[3], want) and not got[1].any()
 
 
-@pytest.mark.parametrize("k,T", [(64, 1), (64, 31), (256, 32), (256, 77)])
+@pytest.mark.parametrize("k,T", [(64, 1), (64, 31), (256, 64), (256, 65), (256, 200), (1024, 130), (8, 64 * 70 + 3)])
 def test_tile_combiners(lgr, oracle, executor_factory, k, T):
-    """check_code / check_linear over a resident tile == the reference's per-row schedule"""
+    """check_code / check_linear / check_quadratic over a resident tile == the reference's per-row schedule"""
     ex = executor_factory(k)
     n = 4 * k
     a = oracle.synth(61, 0, T, n); b = oracle.synth(62, 0, T, n)
@@ -357,14 +357,28 @@ def test_tile_combiners(lgr, oracle, executor_factory, k, T):
     for t in range(T):
         want = oracle.elt_fma(want, a[t], b[t])
     assert np.array_equal(ex.read_elements(acc), want)
+    # quadratic: worst-case operands in the first rows (p-1 everywhere) exercise the wide accumulator bound
+    z = oracle.synth(64, 0, T, n)
+    a2, b2 = a.copy(), b.copy()
+    a2[0] = lgr.ints_to_array([P - 1] * n); b2[0] = a2[0]; z[0] = 0
+    tz = ex.make_device_buffer(T * n * 32)
+    ex.write_buffer(ta, a2); ex.write_buffer(tb, b2); ex.write_buffer(tz, z)
+    ex.write_buffer(acc, acc0)
+    ex.combine_quad(ta, tb, tz, T, rs, acc)
+    want = acc0.copy()
+    for t in range(T):
+        want = oracle.elt_fma_const(want, oracle.elt_sub(oracle.elt_mul(a2[t], b2[t]), z[t]), rs[t])
+    assert np.array_equal(ex.read_elements(acc), want)
 
 
 # ---------------------------------------------------------------- the reference's stage schedule
-def test_stage1_stage2_schedule_like_nonbatch_context(lgr, oracle, executor_factory):
+@pytest.mark.parametrize("k", [512, 8192])
+def test_stage1_stage2_schedule_like_nonbatch_context(lgr, oracle, executor_factory, k):
     """Drive the executor exactly as nonbatch_stage1_context / nonbatch_stage2_context do for one
-    linear row, one quadratic triple and the three mask rows (BASELINE config 4's row schedule:
-    7 encodes per stage), and compare root / code / linear / quad with the oracle."""
-    k = 512; n = 4 * k; l = k - 192
+    linear row, one quadratic triple and the three mask rows (BASELINE config 4's row schedule at the
+    reference's default k = 8192: 7 encodes per stage), and compare root / code / linear / quad with
+    the oracle."""
+    n = 4 * k; l = k - 192
     ex = executor_factory(k)
     rng = random.Random(4)
 

@@ -15,9 +15,11 @@ for k, T in ((256, 1 << 16), (8192, 1 << 11)):
     a = ex.make_device_buffer(T * n * 32); b = ex.make_device_buffer(T * n * 32)
     ex.synth(a, 7, 0, T, n); ex.synth(b, 8, 0, T, n)
     acc = ex.make_codeword_buffer()
-    rs = [(i * 0x9E3779B97F4A7C15 + 12345) % lgr.P for i in range(T)]
+    rs = lgr.ints_to_array([(i * 0x9E3779B97F4A7C15 + 12345) % lgr.P for i in range(T)])   # converted once, outside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for name, fn, by in (("combine_code", lambda: ex.combine_code(a, T, rs, acc), T * n * 32), ("combine_linear", lambda: ex.combine_linear(a, b, T, acc), 2 * T * n * 32)):
+    z = ex.make_device_buffer(T * n * 32); ex.synth(z, 9, 0, T, n)
+    for name, fn, by in (("combine_code", lambda: ex.combine_code(a, T, rs, acc), T * n * 32), ("combine_linear", lambda: ex.combine_linear(a, b, T, acc), 2 * T * n * 32),
+                         ("combine_quad", lambda: ex.combine_quad(a, b, z, T, rs, acc), 3 * T * n * 32)):
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
