@@ -178,6 +178,9 @@ def main():
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layout", default="sharded", choices=["sharded", "exact"],
+                    help="N>1: 'sharded' = per-rank commitments + one digest all-gather (north_star); 'exact' = bit-exact single root "
+                         "via all-to-all of codeword column slabs (ligero-prover_b200/sharding.py)")
     ap.add_argument("--aux", action="store_true", help="also time the reference's default geometry k=8192 and the 2^20 NTT (extra keys)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -221,9 +224,22 @@ def main():
         nodes = ex.make_device_buffer(ex.merkle_node_count(nleaves) * 32)
         gathered = torch.empty(world * n * 8, dtype=torch.int32, device=dev) if world > 1 else None
 
+        exact_engine = None
+        if args.layout == "exact" and world > 1:
+            spec = importlib.util.spec_from_file_location("lgr_sharding", os.path.join(ROOT, "ligero-prover_b200", "sharding.py"))
+            sh = importlib.util.module_from_spec(spec); spec.loader.exec_module(sh)
+            T_ex = max(2, (1 << 23) // n)
+            exact_engine = sh.GpuEngine(ex, T_ex, world)
+            nodes = ex.make_device_buffer(ex.merkle_node_count(n) * 32)
+
         def step():
             if world == 1:
                 ex.encode_commit(wbuf, R, digests, nodes)
+            elif exact_engine is not None:
+                # global tile i*world + rank = local rows [i*T, (i+1)*T)
+                leaves = sh.commit_exact(exact_engine, lambda i: (wbuf.slice(i * T_ex * k * 32, (i + 1) * T_ex * k * 32), T_ex), world * R, T_ex, world, rank, dist)
+                ex.use_torch_stream()
+                ex.merkle_build(ex.wrap(leaves.contiguous()), n, nodes)
             else:
                 ex.encode_commit(wbuf, R, digests, None)
                 dist.all_gather_into_tensor(gathered, digests.storage[: n * 8])
@@ -346,7 +362,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "ligero encode+commit, R=2^%d rows x k=%d (n=%d) per GPU, BN254 Fr, seed %d" % (args.log_rows, k, n, SEED),
                        "rows_per_gpu": R, "k": k, "n": n, "l2": "inputs (%.0f GiB per GPU) larger than L2 (126 MB); no flush needed" % (R * k * 32 / 2**30),
-                       "parallelism": "rows sharded over %d GPU(s); digests all-gathered (NCCL) for the tree" % world},
+                       "parallelism": ("rows sharded over %d GPU(s); digests all-gathered (NCCL) for the tree" % world) if exact_engine is None else
+                                      ("exact layout over %d GPUs: tiles round-robin, all-to-all of column slabs, one root" % world)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kern, "int_roofline": int_roofline,
             "cpu_baseline": cpu, "root": root,
         }

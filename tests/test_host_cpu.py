@@ -238,6 +238,62 @@ def test_world_size_2_gloo_sharded_commitment(tmp_path):
     assert "ROOT" in out, out
 
 
+_WORKER_EXACT = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import importlib.util
+spec = importlib.util.spec_from_file_location("lgr_sharding", os.path.join(%(root)r, "ligero-prover_b200", "sharding.py"))
+sh = importlib.util.module_from_spec(spec); spec.loader.exec_module(sh)
+from oracle import lgo
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+k, T, total = 16, 4, 4 * 5 + 3            # 6 tiles: rounds with a missing tile and a short last tile
+n = 4 * k; slab = n // world
+
+class OracleEngine:                        # the oracle stands in for the GPU in this CPU test
+    def begin(self):
+        self.sha = lgo.Sha(slab)
+    def encode_round(self, rnd, rows, nrows):
+        self.send = np.zeros((world, T, slab, 8), np.uint32)
+        for r in range(nrows):
+            cw = lgo.encode(rows[r], k)
+            for h in range(world):
+                self.send[h, r] = cw[h * slab:(h + 1) * slab]
+    def exchange_and_hash(self, rnd, rows_per_rank, dist_):
+        s = torch.from_numpy(self.send.view(np.int32).reshape(-1).copy()); r = torch.empty_like(s)
+        dist_.all_to_all_single(r, s)
+        recv = r.numpy().view(np.uint32).reshape(world, T, slab, 8)
+        for h in range(world):
+            for row in range(rows_per_rank[h]):
+                self.sha.update(recv[h, row])
+    def finish(self, dist_):
+        local = torch.from_numpy(self.sha.final().view(np.int32).reshape(slab, 8).copy())
+        return sh.gather_leaf_digests(local, world, dist_)
+
+num_tiles = (total + T - 1) // T
+mine = sh.tiles_of_rank(num_tiles, world, rank)
+tiles = [(lgo.synth(3, t * T, min(T, total - t * T), k), min(T, total - t * T)) for t in mine]
+leaves = sh.commit_exact(OracleEngine(), lambda i: tiles[i], total, T, world, rank, dist)
+got = leaves.numpy().view(np.uint8).reshape(n, 32)
+want, nodes, _ = lgo.encode_commit(lgo.synth(3, 0, total, k), k)
+assert np.array_equal(got, want), "exact multi-rank layout differs from the single-device commitment"
+if rank == 0:
+    print("EXACT-ROOT", lgo.merkle_build(got)[0].tobytes().hex() == nodes[0].tobytes().hex())
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_2_gloo_exact_layout(tmp_path):
+    """the bit-exact layout (round-robin tiles, all-to-all of column slabs, ordered absorption) on gloo"""
+    script = tmp_path / "worker_exact.py"
+    script.write_text(_WORKER_EXACT % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    out = subprocess.check_output([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                                   "--master-port", "29534", str(script)], env=env, stderr=subprocess.STDOUT, timeout=300).decode()
+    assert "EXACT-ROOT True" in out, out
+
+
 def test_shard_rows_partition():
     import importlib.util
     spec = importlib.util.spec_from_file_location("lgr_sharding", os.path.join(ROOT, "ligero-prover_b200", "sharding.py"))
