@@ -287,7 +287,14 @@ def main():
             e2e_rows = R
             while e2e_rows * k * 32 > max(avail - (8 << 30), 0) * 0.8 // max(world, 1) and e2e_rows > (1 << 12):
                 e2e_rows >>= 1
-            host = torch.empty(e2e_rows * k * 8, dtype=torch.int32, pin_memory=True)
+            host = None
+            while host is None:
+                try:
+                    host = torch.empty(e2e_rows * k * 8, dtype=torch.int32, pin_memory=True)
+                except RuntimeError:                     # cannot pin that much on this box: halve the e2e witness
+                    if e2e_rows <= (1 << 12):
+                        raise
+                    e2e_rows >>= 1
             host.copy_(witness[: e2e_rows * k * 8])
             stream.synchronize()
             root_e2e = None
