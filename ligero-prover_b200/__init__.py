@@ -494,6 +494,12 @@ class Executor:
         _check(lib().lgr_ubench(self._ctx, C.c_int(which), C.byref(v)))
         return v.value
 
+    def ubench_chain(self, variant, warps_per_cta=1, active_lanes=32):
+        """cycles per SHA-256 compression of a lone warp (csrc/ubench.cu variants)"""
+        v = C.c_double()
+        _check(lib().lgr_ubench_chain(self._ctx, C.c_int(variant), C.c_int(warps_per_cta), C.c_int(active_lanes), C.byref(v)))
+        return v.value
+
 
 def make_executor(l, k, n=None, device=0):
     """webgpu_init + ntt_init with the reference's default roots (src/webgpu_prover.cpp:226-237)"""

@@ -69,6 +69,7 @@ struct lgr_ctx {
     EncodeTables enc{};                      // fused encoder tables (k <= 2048)
     fr_mem *enc_large_twist = nullptr;       // tile-engine encoder (k > 2048): [4][k] coset twists
     bool enc_ready = false;
+    uint32_t sys_mul = 0;                    // w_n^4 = w_k^sys_mul (find_sys_mul); 0 = not usable
     fr_mem *scratch = nullptr; size_t scratch_elems = 0;
     fr_mem *tile[2] = {nullptr, nullptr}; size_t tile_elems = 0;
     uint32_t *commit_sha = nullptr;
@@ -167,8 +168,8 @@ static int lanes_per_cta(int logm) {
 // One batched transform job.  Plain mode: `batch` transforms, transform b read at in + b*in_stride and
 // written to out + b*out_stride (in place allowed for single-pass plans; four-step plans go through
 // `tmp`, batch*N elements).  Coset mode (coset_in_twist != nullptr, large-k encoder): the batch index
-// packs (row, r) = (b >> 2, b & 3); input row `row` is read from in + row*in_stride and multiplied by
-// coset_in_twist[r*N + i]; output element m of coset r goes to out + row*out_stride + 4*m + r.
+// packs (row, r) = (b / cosets, b % cosets + coset_base); input row `row` is read from in + row*in_stride and multiplied by
+// coset_in_twist[(r - coset_base)*N + i]; output element m of coset r goes to out + row*out_stride + 4*m + r.
 struct NttJob {
     const fr_mem *in; long long in_stride;
     fr_mem *out; long long out_stride;
@@ -176,6 +177,8 @@ struct NttJob {
     uint32_t batch;
     const fr_mem *coset_in_twist;
     bool no_scale;
+    int cosets = 4;              // coset mode: transforms per row; batch index b = row*cosets + s, r = s + coset_base
+    int coset_base = 0;          // coset_in_twist points at the table of coset `coset_base`
 };
 
 static int run_ntt_job(lgr_ctx *c, NttPlan &p, const NttJob &j) {
@@ -210,7 +213,7 @@ static int run_ntt_job(lgr_ctx *c, NttPlan &p, const NttJob &j) {
     q.logm = p.l1; q.lanes_per_cta = lanes_per_cta(p.l1);
     q.tw = p.tw1.d; q.tws = 1;
     q.twist_full = p.twist_full.d; q.twist_lo = p.twist_lo.d; q.twist_hi = p.twist_hi.d; q.twist_shift = p.twist_shift;
-    if (coset) { q.in_outer_shift = 2; q.in_twist = j.coset_in_twist; q.in_twist_sub_stride = N; }
+    if (coset) { q.in_outer_div = j.cosets; q.in_twist = j.coset_in_twist; q.in_twist_sub_stride = N; }
     q.scale = nullptr; q.canon = 0;
     CU(launch_ntt_tile(q, c->stream)); c->launches++;
     // pass 2: for every k1, N2-point transform over i2 (contiguous); output index k1 + N1*k2; tmp -> out
@@ -220,7 +223,7 @@ static int run_ntt_job(lgr_ctx *c, NttPlan &p, const NttJob &j) {
     r.in_outer_stride = N;
     r.in_lane_stride = N2; r.in_point_stride = 1;
     if (coset) {
-        r.out_outer_shift = 2; r.out_outer_stride = j.out_stride; r.out_sub_stride = 1;
+        r.out_outer_div = j.cosets; r.out_outer_stride = j.out_stride; r.out_sub_stride = 1; r.out_sub_base = j.coset_base;
         r.out_lane_stride = 4; r.out_point_stride = 4 * N1;
     } else {
         r.out_outer_stride = j.out_stride;
@@ -245,6 +248,19 @@ static int run_ntt(lgr_ctx *c, fr_mem *buf, NttPlan &p, uint32_t batch, size_t b
 
 static int ilog2u(uint64_t x) { int l = 0; while ((1ull << l) < x) l++; return l; }
 
+// c with w_n^4 = w_k^c: both generate the k-th roots of unity, so c exists and is odd.  For the reference's
+// roots (w_n from root2 = root1^(2^61-1), src/bn254.cpp:36-43,59-61) c = 2^61-1 mod k = k-1.  Then
+// e[4m] = U(w_k^(c m)) = row[c m mod k]: one of the four cosets of the codeword is a permuted copy.
+static uint32_t find_sys_mul(const lgr_ctx *c) {
+    const Fr wn4 = host::pow(c->root_n, 4);
+    if (host::pow(c->root_k, c->k - 1) == wn4) return c->k - 1;
+    if (c->k == 2) return 1;
+    const Fr wm = host::to_mont(c->root_k);
+    Fr x = host::consts().R, target = host::to_mont(wn4);
+    for (uint32_t e = 0; e < c->k; e++) { if (x == target) return e; x = host::montmul(x, wm); }
+    return 0;                                                   // unreachable for valid roots: compute all four cosets
+}
+
 static int build_encode_tables(lgr_ctx *c) {
     if (c->enc_ready) return LGR_OK;
     const size_t k = c->k;
@@ -265,7 +281,7 @@ static int build_encode_tables(lgr_ctx *c) {
         }
     }
     if ((rc = upload(c, tw, t))) return rc;
-    c->enc.inv_k = a.d; c->enc.fwd_c = b.d; c->enc.twist = t.d;
+    c->enc.inv_k = a.d; c->enc.fwd_c = b.d; c->enc.twist = t.d; c->enc.sys_mul = (int)c->sys_mul;
     c->enc_ready = true;
     return LGR_OK;
 }
@@ -299,10 +315,11 @@ static int encode_rows_impl(lgr_ctx *c, const fr_mem *rows, size_t row_stride, u
         return LGR_OK;
     }
     // large k (> 2048): same decomposition as the fused kernel, on the tile engine.  Coefficients
-    // c = iNTT_k(row) (four-step, unscaled) go to scratch; the four coset transforms
+    // c = iNTT_k(row) (four-step, unscaled) go to scratch; the coset transforms
     // e[4m+r] = NTT_k(c_i * w_n^(r i) / k) with root w_n^4 run as one batched four-step job whose first
     // pass applies the coset twist on load and whose second pass writes the interleaved codeword.
-    // The zero padding of engine.cpp:755-770's NTT_n is never touched.
+    // Coset 0 is a permuted copy of the row (find_sys_mul).  The zero padding of engine.cpp:755-770's
+    // NTT_n is never touched.
     REQUIRE(st == c->stream, "internal: the tile engine runs on the main stream");
     REQUIRE(c->logk > ntt_tile_max_logm(), "internal: small k takes the fused encoder");
     const size_t k = c->k;
@@ -311,11 +328,22 @@ static int encode_rows_impl(lgr_ctx *c, const fr_mem *rows, size_t row_stride, u
     NttPlan *pi, *pf;
     if ((rc = get_plan(c, c->logk, c->root_k, true, &pi))) return rc;
     if ((rc = get_plan(c, c->logk, host::pow(c->root_n, 4), false, &pf))) return rc;
-    if ((rc = ensure_scratch(c, (size_t)nrows * k * 5))) return rc;
+    const bool sys = c->sys_mul != 0, inplace = (rows == cw);
+    const uint32_t ncos = sys ? 3 : 4;
+    if ((rc = ensure_scratch(c, (size_t)nrows * k * (1 + ncos + ((sys && inplace) ? 1 : 0))))) return rc;
     fr_mem *coef = c->scratch, *tmp = c->scratch + (size_t)nrows * k;
     NttJob inv{rows, (long long)row_stride, coef, (long long)k, tmp, nrows, nullptr, true};
     if ((rc = run_ntt_job(c, *pi, inv))) return rc;
-    NttJob fwd{coef, (long long)k, cw, (long long)c->n, tmp, nrows * 4, c->enc_large_twist, false};
+    if (sys) {
+        const fr_mem *src = rows; long long src_stride = (long long)row_stride;
+        if (inplace) {                                          // the permuted copy would overwrite rows it still has to read
+            fr_mem *keep = c->scratch + (size_t)nrows * k * (1 + ncos);
+            CU(cudaMemcpy2DAsync(keep, k * 32, rows, row_stride * 32, k * 32, nrows, cudaMemcpyDeviceToDevice, st));
+            src = keep; src_stride = (long long)k;
+        }
+        CU(launch_sys_copy(src, src_stride, cw, (long long)c->n, (int)nrows, c->logk, c->sys_mul, st)); c->launches++;
+    }
+    NttJob fwd{coef, (long long)k, cw, (long long)c->n, tmp, nrows * ncos, c->enc_large_twist + (sys ? k : 0), false, (int)ncos, sys ? 1 : 0};
     return run_ntt_job(c, *pf, fwd);
 }
 
@@ -359,6 +387,7 @@ int lgr_create(lgr_ctx **out, int device, uint32_t l, uint32_t k, uint32_t n, co
         CU(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_h2d_free[i], cudaEventDisableTiming));
     }
+    if (!getenv("LGR_NO_SYSTEMATIC")) c->sys_mul = find_sys_mul(c);    // debugging knob: compute all four cosets
     // validate the roots and build the six context plans eagerly (engine.cpp:196-211 does the same)
     NttPlan *pl; int rc = LGR_OK;
     for (int inv = 0; inv < 2 && !rc; inv++) {
@@ -783,7 +812,7 @@ int lgr_ubench_mont_occ(lgr_ctx *c, int nchain, int warps_per_sm, double *ops) {
 // cycles per SHA-256 compression of one warp owning a scheduler (variant 3/4/5, see ubench.cu)
 int lgr_ubench_chain(lgr_ctx *c, int variant, int warps_per_cta, int active_lanes, double *cycles) {
     REQUIRE(c && cycles, "null argument");
-    REQUIRE(variant >= 3 && variant <= 8 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
+    REQUIRE(variant >= 3 && variant <= 16 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
     uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
     CU(launch_ubench_chain(variant, d, 64, warps_per_cta, active_lanes, c->stream));
     CU(launch_ubench_chain(variant, d, 512, warps_per_cta, active_lanes, c->stream));

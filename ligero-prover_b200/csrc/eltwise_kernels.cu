@@ -6,6 +6,7 @@
 // include/zkp/nonbatch_context.hpp:756-780.  Canonical in, canonical out, bit-exact with the WGSL
 // for canonical inputs.  A canonical product x*y is two Montgomery multiplications
 // (x*y/R, then *R^2/R); a product with a host constant c is one (c is pre-multiplied by R).
+#include <algorithm>
 #include "kernels.h"
 #include "ntt.cuh"
 
@@ -271,6 +272,28 @@ cudaError_t launch_combine_quad(const fr_mem *x, const fr_mem *y, const fr_mem *
     combine_mont_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_raw, T, r_mont);
     combine_quad_kernel<<<grid, 128, 0, st>>>(x, y, z, row_stride, T, n, r_mont, r_scaled, scratch);
     launch_fold(scratch, chunks, n, acc, st);
+    return cudaGetLastError();
+}
+
+// ---- coset 0 of the large-k encoder --------------------------------------------------------------
+// out[row][4m] = rows[row][c*m mod k] reduced to [0,p): w_n^4 = w_k^c, so the codeword positions 4m are
+// the message evaluations themselves (api.cu: find_sys_mul).  Writes are 32-byte sectors 128 bytes apart;
+// the other three cosets fill the gaps right after, while the lines are still in L2.
+__global__ void __launch_bounds__(256) sys_copy_kernel(const fr_mem *__restrict__ rows, long long row_stride, fr_mem *__restrict__ out,
+                                                       long long out_row_stride, long long total, int logk, uint32_t c) {
+    const uint32_t mask = (1u << logk) - 1u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i >> logk;
+        const uint32_t m = (uint32_t)i & mask;
+        const fr_t x = fr_ldg(rows + row * row_stride + ((m * c) & mask));
+        fr_stg(out + row * out_row_stride + 4ll * m, fr_reduce_p(fr_reduce_2p(fr_reduce_2p(x))));
+    }
+}
+cudaError_t launch_sys_copy(const fr_mem *rows, long long row_stride, fr_mem *out, long long out_row_stride, int R, int logk, uint32_t c, cudaStream_t st) {
+    if (R <= 0) return cudaSuccess;
+    const long long total = (long long)R << logk;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    sys_copy_kernel<<<grid, 256, 0, st>>>(rows, row_stride, out, out_row_stride, total, logk, c);
     return cudaGetLastError();
 }
 

@@ -26,11 +26,11 @@ struct NttTileParams {
     // twist_hi[e >> shift] * twist_lo[e & mask] composed on the fly
     const fr_mem *twist_lo, *twist_hi, *twist_full;
     int twist_shift;
-    // coset mode (large-k encoder): the outer index packs (row, r) as outer = row << shift | r.
-    //   input : row = outer >> in_outer_shift is used for addressing; every loaded element is multiplied
-    //           by in_twist[(outer & mask) * in_twist_sub_stride + element offset within the row]
-    //   output: base = (outer >> out_outer_shift) * out_outer_stride + (outer & mask) * out_sub_stride
-    int in_outer_shift, out_outer_shift;
+    // coset mode (large-k encoder): the outer index packs (row, s) as outer = row * div + s  (div = 0: plain mode).
+    //   input : row = outer / in_outer_div is used for addressing; every loaded element is multiplied
+    //           by in_twist[s * in_twist_sub_stride + element offset within the row]
+    //   output: base = (outer / out_outer_div) * out_outer_stride + (s + out_sub_base) * out_sub_stride
+    int in_outer_div, out_outer_div, out_sub_base;
     const fr_mem *in_twist;
     long long in_twist_sub_stride, out_sub_stride;
     const fr_mem *scale;     // optional N^-1 * R (Montgomery form)
@@ -45,10 +45,13 @@ struct EncodeTables {
     const fr_mem *inv_k;     // w_k^-j * R, j < k/2
     const fr_mem *fwd_c;     // (w_n^4)^j * R, j < k/2
     const fr_mem *twist;     // [4][k]: w_n^(r*bitrev_k(q)) / k * R
+    int sys_mul;             // c with w_n^4 = w_k^c (odd, < k): e[4m] = row[c*m mod k]; 0 = unknown, compute coset 0 too
 };
 // rows_in: [R][in_row_stride] elements (first k of each row used); out: [R][n] codewords
 cudaError_t launch_encode_rows(const fr_mem *rows_in, long long in_row_stride, fr_mem *out, long long out_row_stride,
                                int R, int logk, const EncodeTables &t, cudaStream_t st);
+// coset 0 of the large-k encoder: out[row][4m] = canonical(rows[row][c*m mod k])
+cudaError_t launch_sys_copy(const fr_mem *rows, long long row_stride, fr_mem *out, long long out_row_stride, int R, int logk, uint32_t c, cudaStream_t st);
 int encode_rows_max_logk();
 int encode_rows_min_logk();
 

@@ -31,11 +31,12 @@ __global__ void __launch_bounds__(256, 2) ntt_tile_kernel(const NttTileParams p)
         if (lane_fast_in) { c = idx % C; m = idx / C; } else { c = idx >> LOGM; m = idx & (M - 1); }
         if (c < nl) {
             const int L = lane0 + c;
-            const long long outer = L / p.lanes_inner, inner = L % p.lanes_inner;
-            const long long off = inner * p.in_lane_stride + (long long)m * p.in_point_stride;
-            fr_t x = fr_ldg(p.in + (outer >> p.in_outer_shift) * p.in_outer_stride + off);
+            const int outer = L / p.lanes_inner, inner = L % p.lanes_inner;
+            const long long off = (long long)inner * p.in_lane_stride + (long long)m * p.in_point_stride;
+            const int orow = p.in_outer_div ? outer / p.in_outer_div : outer;
+            fr_t x = fr_ldg(p.in + (long long)orow * p.in_outer_stride + off);
             if (p.in_twist)                                             // coset twist (and 1/k) on the way in
-                x = fr_mont_mul(x, fr_ldc(p.in_twist + (outer & ((1ll << p.in_outer_shift) - 1)) * p.in_twist_sub_stride + off));
+                x = fr_mont_mul(x, fr_ldc(p.in_twist + (long long)(outer - orow * p.in_outer_div) * p.in_twist_sub_stride + off));
             fr_sts(sm + (c << LOGM) + bitrev(m, LOGM), x);
         }
     }
@@ -54,7 +55,9 @@ __global__ void __launch_bounds__(256, 2) ntt_tile_kernel(const NttTileParams p)
         if (lane_fast_out) { c = idx % C; m = idx / C; } else { c = idx >> LOGM; m = idx & (M - 1); }
         if (c < nl) {
             const int L = lane0 + c;
-            const long long outer = L / p.lanes_inner, inner = L % p.lanes_inner;
+            const int outer = L / p.lanes_inner, inner = L % p.lanes_inner;
+            const int orow = p.out_outer_div ? outer / p.out_outer_div : outer;
+            const int osub = p.out_outer_div ? outer - orow * p.out_outer_div + p.out_sub_base : 0;
             fr_t x = fr_lds(sm + (c << LOGM) + m);                      // [0,4p)
             if (p.twist_full) {
                 x = fr_mont_mul(x, fr_ldc(p.twist_full + (unsigned long long)inner * (unsigned)m));   // [0,2p)
@@ -65,8 +68,8 @@ __global__ void __launch_bounds__(256, 2) ntt_tile_kernel(const NttTileParams p)
             }
             if (p.scale) x = fr_mont_mul(x, fr_ldc(p.scale));           // [0,2p)
             if (p.canon) x = fr_canon4(x);
-            fr_stg(p.out + (outer >> p.out_outer_shift) * p.out_outer_stride + (outer & ((1ll << p.out_outer_shift) - 1)) * p.out_sub_stride +
-                       inner * p.out_lane_stride + (long long)m * p.out_point_stride, x);
+            fr_stg(p.out + (long long)orow * p.out_outer_stride + (long long)osub * p.out_sub_stride +
+                       (long long)inner * p.out_lane_stride + (long long)m * p.out_point_stride, x);
         }
     }
 }

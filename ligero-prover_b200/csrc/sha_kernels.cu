@@ -13,6 +13,7 @@
 //     big-endian digest (OpenSSL, include/zkp/hash.hpp:181-187).  In terms of u32 loads:
 //     message word = bswap32(stored word), stored parent word = bswap32(state word), uniformly for
 //     every level (the leaf level's stored words are raw state words).
+#include <cstdlib>
 #include "kernels.h"
 #include "ntt.cuh"
 
@@ -138,14 +139,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-// 64 rounds with pre-added K+W (kw[t*32 + lane])
-__device__ __forceinline__ void sha256_rounds_kw(uint32_t st[8], const uint32_t *kw, int lane) {
+// 64 rounds with pre-added K+W (kw[t*32 + lane]).
+// One warp per scheduler: the ALU pipe (SHF/LOP3/IADD3) issues one warp instruction every 2 cycles and so
+// does the FMA pipe (IMAD), so a round costs max(2*ALU ops, 2*FMA ops, dependent chain).  The textbook
+// association  e' = d + (h + S1 + Ch + KW)  (REASSOC = false) puts SHF -> LOP3 -> IADD3 -> IADD -> IADD on
+// the chain: 1938 cycles per block for a lone warp.  REASSOC sums everything that is known early
+// (h + KW + d, Maj - d) ahead of time on the FMA pipe -- multiplications by an opaque 1 / -1 (`one`,
+// `mone` are kernel parameters so that ptxas keeps them as IMAD) -- which leaves SHF -> LOP3 -> IADD3 on
+// the chain and 12 ALU instructions per round: 1641 cycles per block (24 cycles per round is the ALU-issue
+// floor).  Other splits measured with lgr_ubench_chain (tools/chain_ubench.py): every addition on the FMA
+// pipe 1717 (cross-pipe hops lengthen the chain), a' through FMA adds 1677, plain C re-association 1827.
+template <bool REASSOC>
+__device__ __forceinline__ void sha256_rounds_kw(uint32_t st[8], const uint32_t *kw, int lane, const uint32_t one, const uint32_t mone) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
-        const uint32_t t1 = h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + kw[i * 32 + lane];
-        const uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        const uint32_t kwi = kw[i * 32 + lane];
+        const uint32_t s1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+        const uint32_t ch = (e & f) ^ (~e & g);
+        const uint32_t s0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+        const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t ne, na;
+        if (REASSOC) {
+            const uint32_t hkd = (h * one + kwi) * one + d;            // FMA pipe, three rounds ahead of its use
+            const uint32_t pd = d * mone + mj;                         // Maj - d
+            ne = hkd + s1 + ch;                                        // IADD3
+            na = ne + s0 + pd;                                         // IADD3
+        } else {
+            const uint32_t t1 = h + s1 + ch + kwi;
+            ne = d + t1;
+            na = t1 + (s0 + mj);
+        }
+        h = g; g = f; f = e; e = ne; d = c; c = b; b = a; a = na;
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
@@ -161,7 +186,8 @@ __device__ __forceinline__ void load_virtual_row(uint32_t *dst, int v, int p, co
     }
 }
 
-__global__ void __launch_bounds__(128, 1) sha_chain_kernel(uint32_t *ctx, int n, const fr_mem *__restrict__ tile, long long row_stride, int T) {
+template <bool REASSOC>
+__global__ void __launch_bounds__(128, 1) sha_chain_kernel(uint32_t *ctx, int n, const fr_mem *__restrict__ tile, long long row_stride, int T, const uint32_t one, const uint32_t mone) {
     extern __shared__ __align__(16) unsigned char chain_smem[];
     uint32_t *ring = reinterpret_cast<uint32_t *>(chain_smem);
     uint64_t *full = reinterpret_cast<uint64_t *>(chain_smem + (size_t)kChainSlots * 64 * 32 * 4);
@@ -183,7 +209,7 @@ __global__ void __launch_bounds__(128, 1) sha_chain_kernel(uint32_t *ctx, int n,
         int slot = 0; uint32_t phase = 0;
         for (int b = 0; b < nblk; b++) {
             mbar_wait(full + slot, phase);
-            sha256_rounds_kw(st, ring + (size_t)slot * 64 * 32, lane);
+            sha256_rounds_kw<REASSOC>(st, ring + (size_t)slot * 64 * 32, lane, one, mone);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + slot);
             if (++slot == kChainSlots) { slot = 0; phase ^= 1u; }
@@ -341,9 +367,11 @@ cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long lon
     if (n <= 0 || T <= 0) return cudaSuccess;
     if (n % 32 == 0 && n / 32 <= 148 && T >= 4) {
         // narrow matrix: producer/consumer CTAs, one chain warp per SM
-        cudaError_t e = cudaFuncSetAttribute(sha_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem);
+        static const bool textbook = getenv("LGR_CHAIN_TEXTBOOK") != nullptr;   // A/B knob: the textbook round association
+        cudaError_t e = cudaFuncSetAttribute(textbook ? sha_chain_kernel<false> : sha_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem);
         if (e != cudaSuccess) return e;
-        sha_chain_kernel<<<n / 32, 128, kChainSmem, st>>>(ctx, n, tile, row_stride, T);
+        if (textbook) sha_chain_kernel<false><<<n / 32, 128, kChainSmem, st>>>(ctx, n, tile, row_stride, T, 1u, 0xFFFFFFFFu);
+        else sha_chain_kernel<true><<<n / 32, 128, kChainSmem, st>>>(ctx, n, tile, row_stride, T, 1u, 0xFFFFFFFFu);
         return cudaGetLastError();
     }
     // few columns: one warp per CTA so that every chain gets its own scheduler slot

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) ubench_sha_kernel(uint32_t *out, int iter
 //   4: rounds only, K+W pre-computed in shared memory (message schedule done by helper warps)
 //   5: as 4, with part of the rotations / additions moved to the FMA pipe through opaque
 //      multipliers (kernel parameters), so ALU and FMA pipes share the 2-cycle/instruction load
-struct ChainConsts { uint32_t one, m6, m11, m25, m2, m13, m22; };
+struct ChainConsts { uint32_t one, m6, m11, m25, m2, m13, m22, mone; };
 
 __device__ __forceinline__ uint32_t rot_fma(uint32_t x, uint32_t mult) {      // rotr(x, s), mult = 2^(32-s): 2 FMA-pipe ops
     uint32_t hi = __umulhi(x, mult);
@@ -119,6 +119,41 @@ __device__ __forceinline__ void chain_rounds(uint32_t st[8], const uint32_t *kw 
             const uint32_t t1 = h + (ub_rotr(e, 6) ^ ub_rotr(e, 11) ^ ub_rotr(e, 25)) + ((e & f) ^ (~e & g)) + kwi;
             const uint32_t t2 = (ub_rotr(a, 2) ^ ub_rotr(a, 13) ^ ub_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
             h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        } else if (VARIANT >= 9) {
+            // 9..12: all rotations on the ALU pipe; the additions are re-associated so that only
+            // Sigma -> sum sits on the dependent chain, and the early sums run on the FMA pipe
+            //   9: ne = IADD3 (ALU), na through FMA-pipe adds        (11 ALU ops / round)
+            //  10: every addition on the FMA pipe                    (10 ALU ops / round)
+            //  11: ne and na both IADD3, early sums on the FMA pipe  (12 ALU ops / round, shortest chain)
+            //  12: as 11 but plain C (ptxas picks the pipes)
+            const uint32_t s1 = ub_rotr(e, 6) ^ ub_rotr(e, 11) ^ ub_rotr(e, 25);
+            const uint32_t ch = (e & f) ^ (~e & g);
+            const uint32_t s0 = ub_rotr(a, 2) ^ ub_rotr(a, 13) ^ ub_rotr(a, 22);
+            const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            uint32_t ne, na;
+            if (VARIANT == 12) {
+                const uint32_t hkd = (h + kwi) + d;
+                const uint32_t pd = mj - d;
+                ne = hkd + s1 + ch;
+                na = ne + s0 + pd;
+            } else {
+                const uint32_t hk = add_fma(h, kwi, cc.one);
+                const uint32_t hkd = add_fma(hk, d, cc.one);
+                const uint32_t pd = add_fma(d, mj, cc.mone);              // Maj - d
+                if (VARIANT == 9) {
+                    ne = hkd + s1 + ch;
+                    const uint32_t q = add_fma(s0, pd, cc.one);
+                    na = add_fma(ne, q, cc.one);
+                } else if (VARIANT == 10) {
+                    ne = add_fma(add_fma(ch, hkd, cc.one), s1, cc.one);
+                    const uint32_t q = add_fma(s0, pd, cc.one);
+                    na = add_fma(ne, q, cc.one);
+                } else {
+                    ne = hkd + s1 + ch;
+                    na = ne + s0 + pd;
+                }
+            }
+            h = g; g = f; f = e; e = ne; d = c; c = b; b = a; a = na;
         } else if (VARIANT >= 6) {
             // 6: one FMA-pipe rotation in each Sigma; 7: Sigma1 one, Sigma0 two; 8: Sigma1 two, Sigma0 one
             const uint32_t r25 = rot_fma(e, cc.m25);
@@ -191,14 +226,18 @@ __global__ void __launch_bounds__(128) ubench_chain_kernel(uint32_t *out, int it
 }
 
 cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps_per_cta, int active_lanes, cudaStream_t st) {
-    ChainConsts cc{1u, 1u << 26, 1u << 21, 1u << 7, 1u << 30, 1u << 19, 1u << 10};
+    ChainConsts cc{1u, 1u << 26, 1u << 21, 1u << 7, 1u << 30, 1u << 19, 1u << 10, 0xFFFFFFFFu};
     const int threads = warps_per_cta * 32;
     if (variant == 3) ubench_chain_kernel<3><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 4) ubench_chain_kernel<4><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 5) ubench_chain_kernel<5><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 6) ubench_chain_kernel<6><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 7) ubench_chain_kernel<7><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
-    else ubench_chain_kernel<8><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 8) ubench_chain_kernel<8><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 9) ubench_chain_kernel<9><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 10) ubench_chain_kernel<10><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 11) ubench_chain_kernel<11><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else ubench_chain_kernel<12><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     return cudaGetLastError();
 }
 

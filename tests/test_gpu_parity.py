@@ -140,6 +140,58 @@ def test_encode_rows_batch(lgr, oracle, executor_factory, k, R):
     assert np.array_equal(oracle.elt_add(got[0], got[1]), oracle.encode(s, k))
 
 
+@pytest.mark.parametrize("k,R", [(256, 4096), (2048, 64), (8192, 16)])
+def test_codeword_contains_the_message(lgr, oracle, executor_factory, k, R):
+    """size-independent property: w_n^4 = w_k^(k-1) for the reference's roots (src/bn254.cpp:36-43,51-64), so
+    codeword position 4m holds message position (k-m) mod k; the encoder copies that coset instead of
+    computing it, the remaining positions are checked against the oracle on a few rows"""
+    ex = executor_factory(k)
+    n = 4 * k
+    src = ex.make_device_buffer(R * k * 32)
+    dst = ex.make_device_buffer(R * n * 32)
+    ex.synth(src, 11, 0, R, k)
+    ex.encode_rows(src, R, dst)
+    rows = ex.read_elements(src).reshape(R, k, 8)
+    got = ex.read_elements(dst).reshape(R, n, 8)
+    perm = (k - np.arange(k)) % k
+    assert np.array_equal(got[:, 0::4], rows[:, perm])
+    for r in (0, R // 2, R - 1):
+        assert np.array_equal(got[r], oracle.encode(rows[r], k)), r
+
+
+@pytest.mark.parametrize("k,c", [(64, 1), (64, 3), (256, 77), (4096, 5)])
+def test_encode_with_other_roots(lgr, oracle, k, c):
+    """lgr_create takes the roots as arguments (include/wgpu.hpp:75-82): for any w_n the shortcut exponent is
+    found by search (w_n^4 = w_k^c); results must still equal iNTT_k -> zero pad -> NTT_n"""
+    n = 4 * k
+    w_k, w_2k, _ = lgr.generate_omegas(k, n)
+    w_4k = lgr.root_of_unity(n.bit_length() - 1)
+    w_n = pow(w_4k, c, lgr.P)                                       # w_n^4 = w_k^c
+    assert pow(w_n, 4, lgr.P) == pow(w_k, c, lgr.P)
+    ex = lgr.Executor(0)
+    ex.webgpu_init(0, "")
+    ex.ntt_init(max(k - 192, 1), k, n, root_k=w_k, root_2k=w_2k, root_n=w_n)
+    try:
+        R = 5
+        rows = oracle.synth(13, 0, R, k)
+        src = ex.make_device_buffer(R * k * 32)
+        dst = ex.make_device_buffer(R * n * 32)
+        ex.write_buffer(src, rows)
+        ex.encode_rows(src, R, dst)
+        got = ex.read_elements(dst).reshape(R, n, 8)
+        for r in range(R):
+            coef = np.zeros((n, 8), np.uint32)
+            coef[:k] = oracle.ntt(rows[r], w_k, inverse=True)
+            assert np.array_equal(got[r], oracle.ntt(coef, w_n)), r
+        # in place, one row (encode_ntt_device)
+        buf = ex.make_codeword_buffer()
+        ex.write_buffer_clear(buf, rows[0])
+        ex.encode_ntt_device(ex.bind_ntt(buf))
+        assert np.array_equal(ex.read_elements(buf), got[0])
+    finally:
+        ex.close()
+
+
 # ---------------------------------------------------------------- hashing
 def test_sha_leaf_golden_and_streaming(lgr, oracle, executor_factory):
     ex = executor_factory(256)

@@ -178,3 +178,14 @@ def test_synth_distribution_and_determinism(oracle):
     assert np.array_equal(a, b)                      # keyed by (seed,row,col), independent of batching
     vals = oracle.from_limbs(oracle.synth(9, 0, 64, 64).reshape(-1, 8))
     assert all(v < P for v in vals) and len(set(vals)) == len(vals)
+
+
+@pytest.mark.parametrize("k", [8, 64, 1024])
+def test_codeword_contains_the_message(oracle, k):
+    """w_n^4 = w_k^(2^61-1) (src/bn254.cpp:36-43,51-64: root2 = root1^(2^61-1)) = w_k^(k-1): codeword position
+    4m is message position (k-m) mod k.  The CUDA encoder relies on it (csrc/encode_kernels.cu)."""
+    w_k, _, w_n = oracle.omegas(k)
+    assert pow(w_n, 4, P) == pow(w_k, k - 1, P)
+    row = oracle.synth(5, 3, 1, k)[0]
+    e = oracle.encode(row, k)
+    assert np.array_equal(e[0::4], row[(k - np.arange(k)) % k])
