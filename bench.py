@@ -168,6 +168,23 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/*_ncu_full_summary.csv, written by tools/summarize_profiles.py; the capture profiles a launch of the same
+    tile size as the bench's).  Returns (bytes or None, source)."""
+    import csv, glob
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_ncu_full_summary.csv")), reverse=True):
+        tot, seen = 0.0, 0
+        for row in csv.reader(open(path)):
+            if len(row) >= 5 and kernel in row[1] and row[2] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(row[3]) * unit.get(row[4], 1.0)
+                seen += 1
+        if seen == 2:
+            return tot, os.path.relpath(path, os.path.dirname(os.path.abspath(__file__)))
+    return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -341,13 +358,15 @@ def main():
         roofline = None
         if dominant:
             d = kern[dominant]
+            traffic, traffic_src = ncu_traffic(dominant)
             roofline = {"kernel": dominant, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": hbm, "unit": "GB/s", "frac": d["frac_hbm"],
-                        "traffic": None, "peak_source": peak_src,
+                        "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
+                        "peak_source": peak_src,
                         "path_bytes_per_element": 32, "path_achieved": value / world * 32 / 1e9, "path_frac": value / world * 32 / 1e9 / hbm,
                         "note": "integer-issue bound path: see int_roofline and DESIGN.md"}
         ub = {"imad_wide_per_s": ex.ubench(0), "montmul_per_s": ex.ubench(1), "sha256_compress_per_s": ex.ubench(2)}
         import math
-        mm_per_elem = (math.log2(k) - 1) / 2 + 4 + 4 * (math.log2(k) - 1) / 2
+        mm_per_elem = (math.log2(k) - 1) / 2 + 3 + 3 * (math.log2(k) - 1) / 2      # iNTT_k + 3 computed cosets (the 4th is a copy)
         int_roofline = {"measured": ub, "montmul_per_element": mm_per_elem, "sha_compress_per_element": 2,
                         "throughput_bound_elements_per_s": 1.0 / (mm_per_elem / ub["montmul_per_s"] + 2.0 / ub["sha256_compress_per_s"]),
                         "frac": (value / world) / (1.0 / (mm_per_elem / ub["montmul_per_s"] + 2.0 / ub["sha256_compress_per_s"]))}

@@ -123,6 +123,10 @@ int lgr_elt_quad(lgr_ctx *ctx, const void *x, const void *y, const void *z, void
 int lgr_sample_init(lgr_ctx *ctx, const uint64_t *host_indices, uint32_t count);          /* sampling_init */
 int lgr_sample_gather(lgr_ctx *ctx, const void *x, void *out);                            /* sample_gather: out[i] = x[idx[i]] */
 
+/* sample_gather for nrows resident codewords: out[t][s] = tile[t*row_stride_elems + idx[s]], i.e. the proof's
+ * host_samplings layout [row][sample][8 x u32] (nonbatch_context.hpp:906-950) */
+int lgr_sample_gather_rows(lgr_ctx *ctx, const void *tile, uint64_t row_stride_elems, uint32_t nrows, void *out);
+
 /* ---- batched fast paths (B200-native additions; same results as the per-row calls) ------------ */
 /* nrows encodes in one launch: rows[r] = k elements at rows + r*row_stride_elems, codewords[r] = n
  * elements at codewords + r*n.  rows may alias codewords when row_stride_elems == n (in place). */
@@ -147,6 +151,9 @@ int lgr_combine_code(lgr_ctx *ctx, const void *tile, uint32_t nrows, const uint3
 /* check_quadratic over three resident tiles: acc[j] += sum_t r[t]*(x[t][j]*y[t][j] - z[t][j])
  * (nonbatch_context.hpp:771-780: EltwiseMultMod, EltwiseSubMod, EltwiseFMAMod(r) per triple) */
 int lgr_combine_quad(lgr_ctx *ctx, const void *tile_x, const void *tile_y, const void *tile_z, uint32_t nrows, const uint32_t *host_r, void *acc);
+/* same with the three operand rows of triple t at x/y/z + t*row_stride_elems: the layout of a tile encoded in
+ * emission order (x_0, y_0, z_0, x_1, ...: x = tile, y = tile + n, z = tile + 2n, stride 3n) */
+int lgr_combine_quad_rows(lgr_ctx *ctx, const void *x, const void *y, const void *z, uint64_t row_stride_elems, uint32_t nrows, const uint32_t *host_r, void *acc);
 /* check_linear over two resident tiles: acc[j] += sum_t a[t][j]*b[t][j] (nonbatch_context.hpp:765-769) */
 int lgr_combine_linear(lgr_ctx *ctx, const void *tile_a, const void *tile_b, uint32_t nrows, void *acc);
 

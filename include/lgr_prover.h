@@ -1,0 +1,82 @@
+/*
+ * lgr_prover.h -- C ABI of the host-side prover driver (liblgr_prover.so), the layer ABOVE include/lgr.h.
+ *
+ * The reference's prover entry point is `main` of src/webgpu_prover.cpp:59-495: interpreter -> rows -> three
+ * stages -> proof_data.gz.  The interpreter / witness manager are out of scope; this library
+ * is the rest of that function for a caller that already has the rows: stage 1/2/3 over the device hot path
+ * (nonbatch_context.hpp:445-993), the Fiat-Shamir transcript and sampler (src/webgpu_prover.cpp:281-353,
+ * include/zkp/random.hpp:87-146, include/util/portable_sample.hpp), Merkle openings
+ * (include/zkp/merkle_tree.hpp:155-318) and the proof container (include/zkp/proof_serializer.hpp:60-224,
+ * proto/ligero_proof.proto).  Host pieces are callable on their own (no GPU needed) so that they can be
+ * checked against an independent restatement.
+ *
+ * All functions return 0 on success; lgrp_last_error() gives the text otherwise.
+ */
+#ifndef LGR_PROVER_H
+#define LGR_PROVER_H
+#include <stddef.h>
+#include <stdint.h>
+
+#include "lgr.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *lgrp_last_error(void);
+
+/* ---- transcript / randomness (host only) ------------------------------------------------------- */
+/* zkp::hash<sha256>("LigetronStage1", root, instance_hash)  (src/webgpu_prover.cpp:281-282) */
+int lgrp_stage1_seed(const uint8_t root[32], const uint8_t instance_hash[32], uint8_t out[32]);
+/* zkp::hash<sha256>("LigetronStage2", root, code, linear, quad), each vector = nwords u32 (src/webgpu_prover.cpp:337-341) */
+int lgrp_stage2_seed(const uint8_t root[32], const uint32_t *code, const uint32_t *linear, const uint32_t *quad, size_t nwords, uint8_t out[32]);
+/* the first `count` bytes of zkp::hash_random_engine<sha256>(seed)  (include/zkp/random.hpp:87-146) */
+int lgrp_hash_random_bytes(const uint8_t seed[32], uint8_t *out, size_t count);
+/* portable_sample(iota(n), sample_size, hash_random_engine(seed)) + sort (src/webgpu_prover.cpp:343-351);
+ * out holds min(n, sample_size) indices */
+int lgrp_sample_indices(const uint8_t seed[32], uint64_t n, uint64_t sample_size, uint64_t *out, uint64_t *out_count);
+/* `count` draws of bn254_gmp::generate_random over mpz_random_engine(key, iv): 8 x u32 limbs each
+ * (include/util/csprng.hpp:28-110, include/zkp/finite_field_gmp.hpp:70-78) */
+int lgrp_fr_random(const uint8_t key[32], const uint8_t iv[16], size_t count, uint32_t *out_limbs);
+
+/* ---- Merkle openings (host only; nodes = the array lgr_merkle_build produced) ------------------ */
+/* merkle_tree::decommit + canonical sibling order (merkle_tree.hpp:155-215, proof_serializer.hpp:82-117).
+ * positions_out / siblings_out need room for at most total_count entries; *count_out = number written */
+int lgrp_decommit(const uint8_t *nodes, uint64_t total_count, const uint64_t *leaf_idx, uint64_t nidx, uint64_t *positions_out,
+                  uint8_t *siblings_out, uint64_t *count_out);
+/* merkle_tree::recommit (merkle_tree.hpp:232-318): leaves = nidx digests of the opened leaves */
+int lgrp_recommit(const uint8_t *leaves, const uint64_t *leaf_idx, uint64_t nidx, uint64_t total_count, const uint8_t *siblings, uint64_t nsib,
+                  uint8_t root_out[32]);
+
+/* ---- proof container (host only) ---------------------------------------------------------------- */
+typedef struct lgrp_proof lgrp_proof;
+/* which: 0 = serialized LigeroProofEnvelope, 1 = gzip of it (what the reference writes to proof_data.gz) */
+int lgrp_proof_bytes(const lgrp_proof *p, int which, const uint8_t **data, size_t *len);
+/* parse an envelope (gzip or plain) back into a proof object (deserialize_proof, proof_serializer.hpp:193-224);
+ * lgrp_proof_bytes(.., 0, ..) then returns the re-serialized envelope */
+int lgrp_proof_parse(const uint8_t *data, size_t len, lgrp_proof **out);
+void lgrp_proof_free(lgrp_proof *p);
+/* prover self-check flags (src/webgpu_prover.cpp:465-471): bit 0 code, bit 1 linear, bit 2 quadratic; the two stage seeds */
+int lgrp_proof_info(const lgrp_proof *p, uint32_t *valid_bits, uint8_t stage1_seed[32], uint8_t stage2_seed[32], uint64_t *encoded_rows);
+
+/* ---- the three-stage prover over a witness matrix (needs a B200: runs the hot path through lgr.h) -- */
+typedef struct {
+    uint32_t l, k;                 /* must match the context (n = 4k) */
+    uint64_t n_events;             /* row events in emission order */
+    const uint8_t *kinds;          /* n_events bytes: 0 = linear row (1 encoded row), 1 = quadratic triple (rows x, y, z) */
+    const uint32_t *values;        /* encoded rows in emission order: [rows][l][8 x u32], canonical */
+    const uint32_t *coefs;         /* linear-test coefficient rows, same shape; NULL = all zero */
+    uint32_t const_sum[8];         /* linear test constant (zkp/common.hpp:68-79) */
+    uint8_t encoding_seed[32];     /* AES-CTR key of the padding / mask stream (src/webgpu_prover.cpp:239-263) */
+    uint8_t instance_hash[32];     /* src/webgpu_prover.cpp:161-168 */
+    uint8_t program_hash[32];      /* metadata only */
+    int64_t generated_at_seconds;  /* metadata; < 0 = wall clock */
+    uint32_t sample_size;          /* params::sample_size = 192 */
+} lgrp_statement;
+
+int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

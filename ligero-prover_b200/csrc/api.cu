@@ -614,6 +614,12 @@ int lgr_sample_gather(lgr_ctx *c, const void *x, void *out) {
     REQUIRE(c->sample_idx, "sampling_init has not been called");
     return elt(c, ELT_GATHER, x, 0, 0, out, c->sample_count, 0, false, c->sample_idx);
 }
+int lgr_sample_gather_rows(lgr_ctx *c, const void *tile, uint64_t row_stride, uint32_t nrows, void *out) {
+    REQUIRE(c && tile && out, "null argument");
+    REQUIRE(c->sample_idx, "sampling_init has not been called");
+    CU(launch_gather_rows((const fr_mem *)tile, (long long)row_stride, (int)nrows, c->sample_idx, (int)c->sample_count, (fr_mem *)out, c->stream)); c->launches++;
+    return LGR_OK;
+}
 
 // ---- stage-1 commit pipeline -------------------------------------------------------------------
 // tile: even number of rows, 2^23 codeword elements (256 MiB) per buffer: at k = 256 that is 8192 rows
@@ -741,13 +747,17 @@ int lgr_combine_code(lgr_ctx *c, const void *tile, uint32_t nrows, const uint32_
     return LGR_OK;
 }
 int lgr_combine_quad(lgr_ctx *c, const void *x, const void *y, const void *z, uint32_t nrows, const uint32_t *host_r, void *acc) {
+    return lgr_combine_quad_rows(c, x, y, z, c ? c->n : 0, nrows, host_r, acc);
+}
+int lgr_combine_quad_rows(lgr_ctx *c, const void *x, const void *y, const void *z, uint64_t row_stride, uint32_t nrows, const uint32_t *host_r, void *acc) {
     REQUIRE(c && x && y && z && host_r && acc, "null argument");
+    REQUIRE(row_stride >= c->n, "row stride smaller than n");
     if (!nrows) return LGR_OK;
     const size_t part = combine_scratch_elems((int)nrows, (int)c->n);
     int rc = ensure_scratch(c, part + 3 * (size_t)nrows);
     if (rc) return rc;
     if ((rc = upload_scalars(c, host_r, nrows, part + 2 * (size_t)nrows))) return rc;
-    CU(launch_combine_quad((const fr_mem *)x, (const fr_mem *)y, (const fr_mem *)z, (long long)c->n, (int)nrows, (int)c->n, c->scratch + part + 2 * (size_t)nrows,
+    CU(launch_combine_quad((const fr_mem *)x, (const fr_mem *)y, (const fr_mem *)z, (long long)row_stride, (int)nrows, (int)c->n, c->scratch + part + 2 * (size_t)nrows,
                            (fr_mem *)acc, c->scratch, part + 2 * (size_t)nrows, c->stream));
     c->launches += 4;
     return LGR_OK;
@@ -812,7 +822,7 @@ int lgr_ubench_mont_occ(lgr_ctx *c, int nchain, int warps_per_sm, double *ops) {
 // cycles per SHA-256 compression of one warp owning a scheduler (variant 3/4/5, see ubench.cu)
 int lgr_ubench_chain(lgr_ctx *c, int variant, int warps_per_cta, int active_lanes, double *cycles) {
     REQUIRE(c && cycles, "null argument");
-    REQUIRE(variant >= 3 && variant <= 16 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
+    REQUIRE(variant >= 3 && variant <= 17 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
     uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
     CU(launch_ubench_chain(variant, d, 64, warps_per_cta, active_lanes, c->stream));
     CU(launch_ubench_chain(variant, d, 512, warps_per_cta, active_lanes, c->stream));

@@ -297,4 +297,24 @@ cudaError_t launch_sys_copy(const fr_mem *rows, long long row_stride, fr_mem *ou
     return cudaGetLastError();
 }
 
+// ---- stage-3 openings over a resident codeword tile ------------------------------------------------
+// out[t][s] = tile[t][idx[s]] (sample_gather, kernels.wgsl.in:541-549, for T rows at once; the staging
+// layout [row][sample][8 x u32] is the proof's host_samplings, nonbatch_context.hpp:906-933)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const fr_mem *__restrict__ tile, long long row_stride, int T, const uint32_t *__restrict__ idx,
+                                                          int count, fr_mem *__restrict__ out) {
+    const long long total = (long long)T * count;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / count;
+        const int s = (int)(i - t * count);
+        fr_stg(out + i, fr_ldg(tile + t * row_stride + idx[s]));
+    }
+}
+cudaError_t launch_gather_rows(const fr_mem *tile, long long row_stride, int T, const uint32_t *idx, int count, fr_mem *out, cudaStream_t st) {
+    if (T <= 0 || count <= 0) return cudaSuccess;
+    const long long total = (long long)T * count;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(tile, row_stride, T, idx, count, out);
+    return cudaGetLastError();
+}
+
 }  // namespace lgr

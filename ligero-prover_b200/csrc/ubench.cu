@@ -119,6 +119,39 @@ __device__ __forceinline__ void chain_rounds(uint32_t st[8], const uint32_t *kw 
             const uint32_t t1 = h + (ub_rotr(e, 6) ^ ub_rotr(e, 11) ^ ub_rotr(e, 25)) + ((e & f) ^ (~e & g)) + kwi;
             const uint32_t t2 = (ub_rotr(a, 2) ^ ub_rotr(a, 13) ^ ub_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
             h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        } else if (VARIANT == 17) {
+            // e' through two FMA-pipe adds (h+KW+d+Ch early, + Sigma1 late), a' as IADD3: 11 ALU ops per round
+            const uint32_t s1 = ub_rotr(e, 6) ^ ub_rotr(e, 11) ^ ub_rotr(e, 25);
+            const uint32_t ch = (e & f) ^ (~e & g);
+            const uint32_t s0 = ub_rotr(a, 2) ^ ub_rotr(a, 13) ^ ub_rotr(a, 22);
+            const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            const uint32_t hkd = add_fma(add_fma(h, kwi, cc.one), d, cc.one);
+            const uint32_t pd = add_fma(d, mj, cc.mone);
+            const uint32_t ne = add_fma(add_fma(ch, hkd, cc.one), s1, cc.one);
+            const uint32_t na = ne + s0 + pd;
+            h = g; g = f; f = e; e = ne; d = c; c = b; b = a; a = na;
+        } else if (VARIANT >= 13) {
+            // 13..16: variant 11's association with rotations moved to the FMA pipe where the chain has slack
+            //  13: rotr(a,22) as IMAD.HI + IMAD       14: rotr(a,22) and rotr(e,25)
+            //  15: rotr(a,22) and rotr(a,13)          16: rotr(a,22) as IMAD.WIDE halves xor-ed by a wider LOP3 tree
+            const uint32_t r25 = (VARIANT == 14) ? rot_fma(e, cc.m25) : ub_rotr(e, 25);
+            const uint32_t s1 = ub_rotr(e, 6) ^ ub_rotr(e, 11) ^ r25;
+            const uint32_t ch = (e & f) ^ (~e & g);
+            uint32_t s0;
+            if (VARIANT == 16) {
+                const unsigned long long w = (unsigned long long)a * cc.m22;
+                s0 = (ub_rotr(a, 2) ^ ub_rotr(a, 13) ^ (uint32_t)w) ^ (uint32_t)(w >> 32);
+            } else {
+                const uint32_t r13 = (VARIANT == 15) ? rot_fma(a, cc.m13) : ub_rotr(a, 13);
+                s0 = ub_rotr(a, 2) ^ r13 ^ rot_fma(a, cc.m22);
+            }
+            const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            const uint32_t hk = add_fma(h, kwi, cc.one);
+            const uint32_t hkd = add_fma(hk, d, cc.one);
+            const uint32_t pd = add_fma(d, mj, cc.mone);
+            const uint32_t ne = hkd + s1 + ch;
+            const uint32_t na = ne + s0 + pd;
+            h = g; g = f; f = e; e = ne; d = c; c = b; b = a; a = na;
         } else if (VARIANT >= 9) {
             // 9..12: all rotations on the ALU pipe; the additions are re-associated so that only
             // Sigma -> sum sits on the dependent chain, and the early sums run on the FMA pipe
@@ -237,7 +270,12 @@ cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps
     else if (variant == 9) ubench_chain_kernel<9><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 10) ubench_chain_kernel<10><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 11) ubench_chain_kernel<11><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
-    else ubench_chain_kernel<12><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 12) ubench_chain_kernel<12><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 13) ubench_chain_kernel<13><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 14) ubench_chain_kernel<14><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 15) ubench_chain_kernel<15><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 16) ubench_chain_kernel<16><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else ubench_chain_kernel<17><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     return cudaGetLastError();
 }
 

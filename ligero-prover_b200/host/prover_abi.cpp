@@ -1,0 +1,165 @@
+// C ABI (include/lgr_prover.h) over the header-only host layer: fiat_shamir.hpp, merkle_host.hpp,
+// proof_wire.hpp, matrix_prover.hpp.  Built as liblgr_prover.so, linked against liblgr.so, libcrypto, libz.
+#include <exception>
+#include <string>
+
+#include "../../include/lgr_prover.h"
+#include "matrix_prover.hpp"
+
+using namespace ligero::cuda::host;
+
+static thread_local std::string g_perr;
+
+struct lgrp_proof {
+    prove_result r;
+};
+
+#define LGRP_TRY try {
+#define LGRP_END                                                        \
+    }                                                                   \
+    catch (const std::exception &e) { g_perr = e.what(); return 1; }    \
+    catch (...) { g_perr = "unknown error"; return 1; }                 \
+    return 0;
+
+static digest dg(const uint8_t *p) { digest d; memcpy(d.data, p, 32); return d; }
+
+extern "C" {
+
+const char *lgrp_last_error(void) { return g_perr.c_str(); }
+
+int lgrp_stage1_seed(const uint8_t root[32], const uint8_t instance_hash[32], uint8_t out[32]) {
+    LGRP_TRY
+    const digest d = stage1_seed(dg(root), dg(instance_hash));
+    memcpy(out, d.data, 32);
+    LGRP_END
+}
+
+int lgrp_stage2_seed(const uint8_t root[32], const uint32_t *code, const uint32_t *linear, const uint32_t *quad, size_t nwords, uint8_t out[32]) {
+    LGRP_TRY
+    const std::vector<uint32_t> c(code, code + nwords), l(linear, linear + nwords), q(quad, quad + nwords);
+    const digest d = stage2_seed(dg(root), c, l, q);
+    memcpy(out, d.data, 32);
+    LGRP_END
+}
+
+int lgrp_hash_random_bytes(const uint8_t seed[32], uint8_t *out, size_t count) {
+    LGRP_TRY
+    hash_random_engine eng(dg(seed));
+    for (size_t i = 0; i < count; i++) out[i] = eng();
+    LGRP_END
+}
+
+int lgrp_sample_indices(const uint8_t seed[32], uint64_t n, uint64_t sample_size, uint64_t *out, uint64_t *out_count) {
+    LGRP_TRY
+    const std::vector<uint64_t> s = sample_indices(dg(seed), n, sample_size);
+    for (size_t i = 0; i < s.size(); i++) out[i] = s[i];
+    if (out_count) *out_count = s.size();
+    LGRP_END
+}
+
+int lgrp_fr_random(const uint8_t key[32], const uint8_t iv[16], size_t count, uint32_t *out_limbs) {
+    LGRP_TRY
+    fr_random_stream s(key, iv);
+    for (size_t i = 0; i < count; i++) s.next(out_limbs + 8 * i);
+    LGRP_END
+}
+
+int lgrp_decommit(const uint8_t *nodes, uint64_t total_count, const uint64_t *leaf_idx, uint64_t nidx, uint64_t *positions_out,
+                  uint8_t *siblings_out, uint64_t *count_out) {
+    LGRP_TRY
+    const std::vector<uint64_t> idx(leaf_idx, leaf_idx + nidx);
+    const decommitment d = decommit(nodes, total_count, idx);
+    for (size_t i = 0; i < d.positions.size(); i++) {
+        if (positions_out) positions_out[i] = d.positions[i];
+        if (siblings_out) memcpy(siblings_out + 32 * i, d.siblings[i].data, 32);
+    }
+    if (count_out) *count_out = d.positions.size();
+    LGRP_END
+}
+
+int lgrp_recommit(const uint8_t *leaves, const uint64_t *leaf_idx, uint64_t nidx, uint64_t total_count, const uint8_t *siblings, uint64_t nsib,
+                  uint8_t root_out[32]) {
+    LGRP_TRY
+    decommitment d;
+    d.total_count = total_count;
+    d.known_index.assign(leaf_idx, leaf_idx + nidx);
+    d.positions = sibling_positions(d.known_index, total_count);
+    if (d.positions.size() != nsib) throw std::runtime_error("Sibling hash count mismatch: expected " + std::to_string(d.positions.size()) + ", got " + std::to_string(nsib));
+    d.siblings.resize(nsib);
+    for (uint64_t i = 0; i < nsib; i++) memcpy(d.siblings[i].data, siblings + 32 * i, 32);
+    std::vector<digest> lv(nidx);
+    for (uint64_t i = 0; i < nidx; i++) memcpy(lv[i].data, leaves + 32 * i, 32);
+    const digest r = recommit(lv, d);
+    memcpy(root_out, r.data, 32);
+    LGRP_END
+}
+
+int lgrp_proof_bytes(const lgrp_proof *p, int which, const uint8_t **data, size_t *len) {
+    LGRP_TRY
+    if (!p || !data || !len) throw std::invalid_argument("null argument");
+    const std::string &s = which == 0 ? p->r.envelope : p->r.gzip;
+    *data = reinterpret_cast<const uint8_t *>(s.data());
+    *len = s.size();
+    LGRP_END
+}
+
+int lgrp_proof_parse(const uint8_t *data, size_t len, lgrp_proof **out) {
+    LGRP_TRY
+    if (!data || !out) throw std::invalid_argument("null argument");
+    std::string in(reinterpret_cast<const char *>(data), len);
+    if (len >= 2 && data[0] == 0x1f && data[1] == 0x8b) in = gzip_decompress(in);
+    lgrp_proof *p = new lgrp_proof();
+    try {
+        p->r.proof = deserialize_proof(in);
+        p->r.envelope = serialize_proof(p->r.proof);
+        p->r.gzip = gzip_compress(p->r.envelope, 6);
+    } catch (...) { delete p; throw; }
+    *out = p;
+    LGRP_END
+}
+
+void lgrp_proof_free(lgrp_proof *p) { delete p; }
+
+int lgrp_proof_info(const lgrp_proof *p, uint32_t *valid_bits, uint8_t s1[32], uint8_t s2[32], uint64_t *encoded_rows) {
+    LGRP_TRY
+    if (!p) throw std::invalid_argument("null argument");
+    if (valid_bits) *valid_bits = (p->r.valid_code ? 1u : 0u) | (p->r.valid_linear ? 2u : 0u) | (p->r.valid_quad ? 4u : 0u);
+    if (s1) memcpy(s1, p->r.stage1_seed.data, 32);
+    if (s2) memcpy(s2, p->r.stage2_seed.data, 32);
+    if (encoded_rows) *encoded_rows = p->r.encoded_rows;
+    LGRP_END
+}
+
+int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *s, lgrp_proof **out) {
+    LGRP_TRY
+    if (!ctx || !s || !out) throw std::invalid_argument("null argument");
+    if (s->n_events && (!s->kinds || !s->values)) throw std::invalid_argument("statement without rows");
+    statement st;
+    st.l = s->l; st.k = s->k;
+    memcpy(st.const_sum, s->const_sum, 32);
+    memcpy(st.encoding_seed, s->encoding_seed, 32);
+    st.instance_hash = dg(s->instance_hash);
+    st.program_hash = dg(s->program_hash);
+    st.generated_at_seconds = s->generated_at_seconds;
+    st.sample_size = s->sample_size ? s->sample_size : 192;
+    size_t row = 0;
+    const size_t stride = (size_t)s->l * 8;
+    st.events.resize(s->n_events);
+    for (uint64_t e = 0; e < s->n_events; e++) {
+        row_event &ev = st.events[e];
+        ev.quadratic = s->kinds[e] != 0;
+        for (int j = 0; j < (ev.quadratic ? 3 : 1); j++, row++) {
+            ev.val[j] = s->values + row * stride;
+            ev.coef[j] = s->coefs ? s->coefs + row * stride : nullptr;
+        }
+    }
+    lgrp_proof *p = new lgrp_proof();
+    try {
+        matrix_prover mp(ctx);
+        p->r = mp.prove(st);
+    } catch (...) { delete p; throw; }
+    *out = p;
+    LGRP_END
+}
+
+}  // extern "C"

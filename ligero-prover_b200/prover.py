@@ -1,0 +1,166 @@
+"""ctypes mirror of include/lgr_prover.h (liblgr_prover.so): the host-side prover driver above the hot path --
+transcript, sampler, Merkle openings, proof container, and the three-stage prover over a witness matrix
+(what src/webgpu_prover.cpp:249-471 does once the rows exist).  Same names as the C ABI, numpy in / out."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class ProverError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "liblgr_prover.so")
+        if not os.path.exists(path):
+            raise ProverError("liblgr_prover.so is not built (make -C ligero-prover_b200); there is no fallback")
+        C.CDLL(os.path.join(_HERE, "liblgr.so"), mode=C.RTLD_GLOBAL)
+        _lib = C.CDLL(path)
+        _lib.lgrp_last_error.restype = C.c_char_p
+        _lib.lgrp_proof_free.restype = None
+    return _lib
+
+
+def _check(rc):
+    if rc:
+        raise ProverError(lib().lgrp_last_error().decode())
+
+
+def _u8(b, n=None):
+    a = np.frombuffer(bytes(b), np.uint8).copy()
+    assert n is None or a.size == n
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def stage1_seed(root, instance_hash):
+    out = np.zeros(32, np.uint8)
+    _check(lib().lgrp_stage1_seed(_p(_u8(root, 32)), _p(_u8(instance_hash, 32)), _p(out)))
+    return out.tobytes()
+
+
+def stage2_seed(root, code, linear, quad):
+    c, l, q = (np.ascontiguousarray(v, np.uint32).reshape(-1) for v in (code, linear, quad))
+    assert c.size == l.size == q.size
+    out = np.zeros(32, np.uint8)
+    _check(lib().lgrp_stage2_seed(_p(_u8(root, 32)), _p(c), _p(l), _p(q), C.c_size_t(c.size), _p(out)))
+    return out.tobytes()
+
+
+def hash_random_bytes(seed, count):
+    out = np.zeros(count, np.uint8)
+    _check(lib().lgrp_hash_random_bytes(_p(_u8(seed, 32)), _p(out), C.c_size_t(count)))
+    return out.tobytes()
+
+
+def sample_indices(seed, n, sample_size=192):
+    out = np.zeros(min(n, sample_size), np.uint64)
+    cnt = C.c_uint64()
+    _check(lib().lgrp_sample_indices(_p(_u8(seed, 32)), C.c_uint64(n), C.c_uint64(sample_size), _p(out), C.byref(cnt)))
+    return [int(x) for x in out[: cnt.value]]
+
+
+def fr_random(key, count, iv=bytes(16)):
+    out = np.zeros((count, 8), np.uint32)
+    _check(lib().lgrp_fr_random(_p(_u8(key, 32)), _p(_u8(iv, 16)), C.c_size_t(count), _p(out)))
+    return out
+
+
+def decommit(nodes, leaf_idx):
+    nodes = np.ascontiguousarray(nodes, np.uint8).reshape(-1, 32)
+    idx = np.ascontiguousarray(leaf_idx, np.uint64)
+    pos = np.zeros(nodes.shape[0], np.uint64); sib = np.zeros((nodes.shape[0], 32), np.uint8)
+    cnt = C.c_uint64()
+    _check(lib().lgrp_decommit(_p(nodes), C.c_uint64(nodes.shape[0]), _p(idx), C.c_uint64(idx.size), _p(pos), _p(sib), C.byref(cnt)))
+    return [int(x) for x in pos[: cnt.value]], [sib[i].tobytes() for i in range(cnt.value)]
+
+
+def recommit(leaves, leaf_idx, total_count, siblings):
+    lv = np.frombuffer(b"".join(leaves), np.uint8).copy() if leaves else np.zeros(1, np.uint8)
+    sb = np.frombuffer(b"".join(siblings), np.uint8).copy() if siblings else np.zeros(1, np.uint8)
+    idx = np.ascontiguousarray(leaf_idx, np.uint64)
+    out = np.zeros(32, np.uint8)
+    _check(lib().lgrp_recommit(_p(lv), _p(idx), C.c_uint64(idx.size), C.c_uint64(total_count), _p(sb), C.c_uint64(len(siblings)), _p(out)))
+    return out.tobytes()
+
+
+class Statement(C.Structure):
+    _fields_ = [("l", C.c_uint32), ("k", C.c_uint32), ("n_events", C.c_uint64), ("kinds", C.c_void_p), ("values", C.c_void_p),
+                ("coefs", C.c_void_p), ("const_sum", C.c_uint32 * 8), ("encoding_seed", C.c_uint8 * 32), ("instance_hash", C.c_uint8 * 32),
+                ("program_hash", C.c_uint8 * 32), ("generated_at_seconds", C.c_int64), ("sample_size", C.c_uint32)]
+
+
+class Proof:
+    def __init__(self, handle):
+        self._h = handle
+
+    def _bytes(self, which):
+        data, ln = C.POINTER(C.c_uint8)(), C.c_size_t()
+        _check(lib().lgrp_proof_bytes(self._h, C.c_int(which), C.byref(data), C.byref(ln)))
+        return C.string_at(data, ln.value)
+
+    @property
+    def envelope(self):
+        return self._bytes(0)
+
+    @property
+    def gzip(self):
+        return self._bytes(1)
+
+    def info(self):
+        bits, rows = C.c_uint32(), C.c_uint64()
+        s1, s2 = np.zeros(32, np.uint8), np.zeros(32, np.uint8)
+        _check(lib().lgrp_proof_info(self._h, C.byref(bits), _p(s1), _p(s2), C.byref(rows)))
+        return {"valid": (bool(bits.value & 1), bool(bits.value & 2), bool(bits.value & 4)), "stage1_seed": s1.tobytes(),
+                "stage2_seed": s2.tobytes(), "encoded_rows": rows.value}
+
+    def close(self):
+        if self._h:
+            lib().lgrp_proof_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def parse_proof(data):
+    buf = _u8(data)
+    h = C.c_void_p()
+    _check(lib().lgrp_proof_parse(_p(buf), C.c_size_t(buf.size), C.byref(h)))
+    return Proof(h)
+
+
+def prove(executor, kinds, values, coefs=None, const_sum=0, encoding_seed=bytes(32), instance_hash=bytes(32), program_hash=bytes(32),
+          generated_at=0, sample_size=192):
+    """executor: ligero_prover_b200.Executor (its lgr_ctx runs the hot path); kinds: per event 0 = linear row, 1 = quadratic
+    triple; values / coefs: [encoded rows, l, 8] uint32 in emission order"""
+    l, k = executor.message_size(), executor.padding_size()
+    kinds = np.ascontiguousarray(kinds, np.uint8)
+    values = np.ascontiguousarray(values, np.uint32).reshape(-1, l, 8)
+    assert values.shape[0] == int(kinds.size + 2 * kinds.astype(bool).sum()), "one row per linear event, three per triple"
+    st = Statement()
+    st.l, st.k, st.n_events = l, k, kinds.size
+    st.kinds, st.values = kinds.ctypes.data, values.ctypes.data
+    if coefs is not None:
+        coefs = np.ascontiguousarray(coefs, np.uint32).reshape(values.shape)
+        st.coefs = coefs.ctypes.data
+    for i in range(8):
+        st.const_sum[i] = (const_sum >> (32 * i)) & 0xFFFFFFFF
+    for name, v in (("encoding_seed", encoding_seed), ("instance_hash", instance_hash), ("program_hash", program_hash)):
+        getattr(st, name)[:] = list(bytes(v))
+    st.generated_at_seconds, st.sample_size = generated_at, sample_size
+    h = C.c_void_p()
+    _check(lib().lgrp_prove(executor._ctx, C.byref(st), C.byref(h)))
+    return Proof(h)

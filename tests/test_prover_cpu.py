@@ -1,0 +1,180 @@
+"""Host-side prover layer (include/lgr_prover.h, liblgr_prover.so) against the independent Python restatement
+(oracle/prover_ref.py: hashlib, `cryptography` AES, google.protobuf).  No GPU needed: SURVEY 8f rows N1 / N2."""
+import ctypes as C
+import gzip
+import hashlib
+import importlib
+import os
+import random
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import prover_ref as ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pr(lgr):
+    return importlib.import_module("ligero_prover_b200.prover")
+
+
+def test_prover_abi_exports_every_declared_symbol(pr):
+    hdr = open(os.path.join(ROOT, "include", "lgr_prover.h")).read()
+    declared = set(re.findall(r"\b(lgrp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 13
+    missing = [s for s in sorted(declared) if not hasattr(pr.lib(), s)]
+    assert not missing, missing
+
+
+def test_stage_seeds_hash_the_literal_with_its_nul(pr):
+    """hash("LigetronStage1", root, instance) binds the literal to the array overload (hash.hpp:61-65): 15 bytes"""
+    rng = random.Random(1)
+    root, inst = rng.randbytes(32), rng.randbytes(32)
+    want = hashlib.sha256(b"LigetronStage1\x00" + root + inst).digest()
+    assert pr.stage1_seed(root, inst) == want == ref.stage1_seed(root, inst)
+    assert want != hashlib.sha256(b"LigetronStage1" + root + inst).digest()
+    v = [np.frombuffer(rng.randbytes(4 * 8 * 16), np.uint32) for _ in range(3)]
+    want2 = hashlib.sha256(b"LigetronStage2\x00" + root + b"".join(x.tobytes() for x in v)).digest()
+    assert pr.stage2_seed(root, *v) == want2 == ref.stage2_seed(root, *v)
+
+
+def test_hash_random_engine_block_structure(pr):
+    """random.hpp:129-138: block 0 = SHA-256(LE64(0)) (no seed), block i = SHA-256(seed || LE64(i)); bytes from index 31 down"""
+    seed = bytes(range(32))
+    got = pr.hash_random_bytes(seed, 96)
+    b0 = hashlib.sha256(struct.pack("<Q", 0)).digest()
+    b1 = hashlib.sha256(seed + struct.pack("<Q", 1)).digest()
+    b2 = hashlib.sha256(seed + struct.pack("<Q", 2)).digest()
+    assert got == b0[::-1] + b1[::-1] + b2[::-1]
+    e = ref.HashRandomEngine(seed)
+    assert got == bytes(e() for _ in range(96))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 100, 192, 193, 255, 256, 257, 300, 448, 1024, 4096, 32768, 65536, 1 << 17])
+def test_sampler_matches_restatement(pr, n):
+    """every branch of Boost's generate_uniform_int is reached: range 0, == 255, < 255 (small n), > 255"""
+    for s in range(3):
+        seed = hashlib.sha256(b"sampler%d/%d" % (n, s)).digest()
+        got = pr.sample_indices(seed, n)
+        assert got == ref.sample_indices(seed, n)
+        assert len(got) == min(n, 192) == len(set(got)) and got == sorted(got) and all(0 <= i < n for i in got)
+
+
+def test_sampler_statistics_and_the_seedless_first_block(pr):
+    """sanity of the restated Boost algorithm: every index of a small population gets drawn.  The reference's PRG
+    quirk shows too: its first 32 bytes do not depend on the seed (random.hpp:129-138), so the first ~16 draws of
+    the partial shuffle -- and with them a handful of sampled columns -- are the same for EVERY proof."""
+    n, seeds, cnt = 1000, 200, np.zeros(1000)
+    for s in range(seeds):
+        for i in pr.sample_indices(hashlib.sha256(b"u%d" % s).digest(), n, 100):
+            cnt[i] += 1
+    always = int((cnt == seeds).sum())
+    assert 10 <= always <= 16                                   # 32 bytes / 2 bytes per draw (range > 255 takes two)
+    rest = cnt[cnt < seeds]
+    assert rest.min() > 0 and rest.max() < 45 and abs(rest.mean() - seeds * (100 - always) / (n - always)) < 1e-9
+
+
+def test_fr_random_stream(pr, oracle):
+    key = hashlib.sha256(b"key").digest()
+    got = pr.fr_random(key, 1300)                     # crosses two 16 KiB refills (512 draws each)
+    want = ref.FrRandomStream(key).take(1300)
+    assert np.array_equal(got, oracle.to_limbs(want))
+    assert all(0 <= v < ref.P for v in want)
+    # definition: AES-256-CTR keystream of zeros, 32 bytes little-endian, >> 2, one conditional subtract
+    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+    ks = Cipher(algorithms.AES(key), modes.CTR(bytes(16))).encryptor().update(bytes(64))
+    v1 = int.from_bytes(ks[32:64], "little") >> 2
+    assert oracle.from_limbs(got[1])[0] == (v1 - ref.P if v1 >= ref.P else v1)
+
+
+@pytest.mark.parametrize("nleaves,opened", [(8, [3]), (8, [0, 1, 6]), (256, None), (1024, None), (1000, None)])
+def test_decommit_recommit(pr, oracle, nleaves, opened):
+    rng = random.Random(nleaves)
+    leaves = np.frombuffer(rng.randbytes(32 * nleaves), np.uint8).reshape(nleaves, 32)
+    nodes = oracle.merkle_build(leaves)
+    total = nodes.shape[0]
+    if opened is None:
+        opened = sorted(rng.sample(range(nleaves), min(192, nleaves // 2)))
+    pos, sib = pr.decommit(nodes, opened)
+    assert pos == ref.sibling_positions(opened, total)
+    assert sib == [nodes[p].tobytes() for p in pos]
+    half = total // 2
+    lv = [nodes[half + i].tobytes() for i in opened]
+    root = nodes[0].tobytes()
+    assert pr.recommit(lv, opened, total, sib) == root
+    assert ref.recommit(dict(zip(opened, lv)), opened, total, sib) == root          # plain recursive recomputation
+    bad = list(sib); bad[0] = bytes(32)
+    assert pr.recommit(lv, opened, total, bad) != root
+    with pytest.raises(pr.ProverError):
+        pr.recommit(lv, opened, total, sib[:-1])                                     # "Sibling hash count mismatch"
+
+
+def _random_proof_fields(rng, k, rows, nsib, S):
+    n = 4 * k
+    u = lambda cnt: np.frombuffer(rng.randbytes(4 * cnt), np.uint32)
+    return dict(code=u(n * 8), linear=u(n * 8), quad=u(n * 8), samplings=u(rows * S * 8))
+
+
+def test_envelope_bytes_equal_google_protobuf(pr):
+    """the hand-written proto3 writer emits exactly what libprotobuf would for the same field values, and the reader
+    round-trips it (proof_serializer.hpp:166-224)"""
+    rng = random.Random(7)
+    k, S = 64, 192
+    n = 4 * k
+    opened = sorted(rng.sample(range(n), S))
+    total = 2 * n - 1
+    pos = ref.sibling_positions(opened, total)
+    sib = [rng.randbytes(32) for _ in pos]
+    f = _random_proof_fields(rng, k, 9, len(pos), S)
+    meta = {"prover_version": "1.5.0", "program_hash": rng.randbytes(32), "generated_at": 1792214281, "k": k, "n": n, "sample_size": S}
+    want = ref.build_envelope(meta, rng.randbytes(32), sib, opened, f["code"], f["linear"], f["quad"], f["samplings"])
+    for blob in (want, gzip.compress(want)):
+        p = pr.parse_proof(blob)
+        assert p.envelope == want
+        assert gzip.decompress(p.gzip) == want
+        p.close()
+    # a zero index, a zero timestamp and empty vectors exercise proto3's "default values are not written" rule
+    meta0 = dict(meta, generated_at=0)
+    want0 = ref.build_envelope(meta0, bytes(32), [], list(range(n)), [], [], [], [])
+    p = pr.parse_proof(want0)
+    assert p.envelope == want0
+    p.close()
+    with pytest.raises(pr.ProverError):
+        pr.parse_proof(want[: len(want) // 2])
+    with pytest.raises(pr.ProverError):
+        pr.parse_proof(ref.build_envelope(meta, bytes(32), sib[:-1], opened, [], [], [], []))   # sibling count mismatch
+
+
+def test_oracle_prover_is_self_consistent(oracle):
+    """the CPU restatement proves a small true statement, its container parses back, and the verifier-side checks
+    (openings recommit, test vectors match the openings) pass -- and fail on a tampered proof"""
+    rng = random.Random(11)
+    k, l, kinds = 64, 40, [0, 1, 1, 0]
+    n = 4 * k
+    vals, coefs, acc = [], [], 0
+    for kind in kinds:
+        if kind:
+            x = [rng.randrange(ref.P) for _ in range(l)]; y = [rng.randrange(ref.P) for _ in range(l)]
+            rows = [x, y, [a * b % ref.P for a, b in zip(x, y)]]
+        else:
+            rows = [[rng.randrange(ref.P) for _ in range(l)]]
+        for r in rows:
+            c = [rng.randrange(ref.P) for _ in range(l)]
+            acc += sum(a * b for a, b in zip(r, c)); vals.append(oracle.to_limbs(r)); coefs.append(oracle.to_limbs(c))
+    values, coef = np.stack(vals), np.stack(coefs)
+    inst = bytes(range(32))
+    w = ref.prove(l, k, kinds, values, coef, (-acc) % ref.P, hashlib.sha256(b"s").digest(), inst)
+    assert w["valid"] == (True, True, True)
+    meta = {"prover_version": "1.5.0", "program_hash": bytes(32), "generated_at": 5, "k": k, "n": n, "sample_size": 192}
+    blob = ref.build_envelope(meta, w["root"], w["siblings"], w["sample"], w["code"], w["linear"], w["quad"], w["samplings"])
+    env = ref.parse_envelope(gzip.compress(blob))
+    assert ref.verify_openings(env, l, k, kinds, coef, inst)
+    bad = w["samplings"].copy(); bad[1, 5, 0] ^= 1
+    env2 = ref.parse_envelope(ref.build_envelope(meta, w["root"], w["siblings"], w["sample"], w["code"], w["linear"], w["quad"], bad))
+    with pytest.raises(AssertionError):
+        ref.verify_openings(env2, l, k, kinds, coef, inst)
+    assert not ref.prove(l, k, kinds, values, coef, (1 - acc) % ref.P, bytes(32), inst)["valid"][1]

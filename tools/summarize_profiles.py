@@ -26,7 +26,7 @@ out = ["# %s: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-e2e 
        "# per-launch times are cold-cache and serialised: compare SHARES with bench.py's `kernels.*.share_of_step`",
        "kernel,launches,total_us,avg_us,share"]
 for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
-    out.append("%s,%d,%.1f,%.1f,%.3f" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
+    out.append("\"%s\",%d,%.1f,%.1f,%.3f" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
 open("profiles/%s_launches_summary.csv" % tag, "w").write("\n".join(out) + "\n")
 shutil.copy("gpurun_out/launches.csv", "profiles/%s_launches_raw.csv" % tag)
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -48,7 +48,7 @@ for f in sorted(os.listdir("gpurun_out")):
     kn = r[h.index("Kernel Name")].split("(")[0]
     for w in want:
         if w in h:
-            lines.append("%s,%s,%s,%s,%s" % (f, kn, w, r[h.index(w)], rr[1][h.index(w)]))
+            lines.append("%s,\"%s\",%s,%s,%s" % (f, kn, w, r[h.index(w)].replace(",", ""), rr[1][h.index(w)]))
 open("profiles/%s_ncu_full_summary.csv" % tag, "w").write("\n".join(lines) + "\n")
 for j in ("ntt_bench.json", "combine_bench.json"):
     if os.path.exists(os.path.join("gpurun_out", j)):
