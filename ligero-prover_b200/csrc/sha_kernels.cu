@@ -13,6 +13,7 @@
 //     big-endian digest (OpenSSL, include/zkp/hash.hpp:181-187).  In terms of u32 loads:
 //     message word = bswap32(stored word), stored parent word = bswap32(state word), uniformly for
 //     every level (the leaf level's stored words are raw state words).
+#include <cstdio>
 #include <cstdlib>
 #include "kernels.h"
 #include "ntt.cuh"
@@ -269,6 +270,192 @@ __global__ void __launch_bounds__(128, 1) sha_chain_kernel(uint32_t *ctx, int n,
     }
 }
 
+// ---- lane-split chain: 16 columns per warp, the two halves of a round on the two half-warps --------
+// The compression round has two halves of identical SHAPE -- three rotations xor-ed, one bitwise
+// choice, one sum:
+//     e' = d + h + KW + Sigma1(e) + Ch(e,f,g)            a' = (e' - d) + Sigma0(a) + Maj(a,b,c)
+// (a' = T1 + T2 with T1 = e' - d), and Maj(a,b,c) = Ch(a, b|c, b&c).  Lane L < 16 of the chain warp
+// keeps (e,f,g,h) of column L and lane L+16 keeps (a,b,c,d); both run ONE instruction stream whose
+// per-lane constants (rotation amounts, a mask, a sign) select the half:
+//     u = q | (r & M)    v = r & (~M | q)                 (from the previous round's values: off the chain)
+//     p' = [rot(p,s1) ^ rot(p,s2) ^ rot(p,s3)]  +  [(p & u) | (~p & v)]  +  [sgn*s + KW + R]
+// where R is the partner lane's p' of two iterations ago, exchanged with one SHFL.BFLY per round: the
+// E lanes need a_{i-3} (as d), the A lanes need e_{i+1}; running the A lanes two rounds behind the E
+// lanes gives both a slack of two iterations, so the shuffle latency never shows.  8 ALU-pipe instructions
+// per round (3 SHF, 4 LOP3, 1 IADD3) instead of 12, the sums known early on the FMA pipe as before.
+// The feed-forward at block boundaries (st += working variables) is folded into the same stream:
+// every lane keeps its chaining words CV and adds them at its own boundary (E lanes at iteration 0, A
+// lanes at iteration 2 of a block; multipliers mE / mA make the other half's instruction a no-op), and
+// the E lanes keep a copy CA of the A-side chaining words so that d = a + CA in the first four rounds
+// of a block -- which is also the new CA.  One CTA = one chain warp (16 columns) + 3 schedule warps
+// (6 half-warps, each preparing every 6th block); ring slots are 4 KiB.
+constexpr int kC16Slots = 48;                                 // 48 x 4 KiB = 192 KiB: the CTA has its SM to itself
+constexpr int kC16Stride = 64 * 16 + 16;                       // words per ring slot: the 16-word skew puts consecutive slots on opposite
+                                                              // halves of the 32 banks (two half-warps store to consecutive slots; the A lanes'
+                                                              // zero words sit on the half the E lanes do not read)
+constexpr size_t kC16Smem = (size_t)(kC16Slots + 1) * kC16Stride * 4 + 2 * kC16Slots * 8;
+
+// forced instruction shapes for the lane-split rounds: left to itself nvcc re-fuses the boolean algebra into a form
+// whose three LOP3 all wait for the new p, and re-associates the sums onto the dependent chain
+template <int LUT> __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d; asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT)); return d;
+}
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
+template <int G>
+__global__ void __launch_bounds__(128, 1) sha_chain16_kernel(uint32_t *ctx, int n, const fr_mem *__restrict__ tile, long long row_stride, int T, const uint32_t one) {
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    constexpr int NG = kC16Slots / G;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(chain_smem);
+    uint32_t *zeros = ring + (size_t)kC16Slots * kC16Stride;  // what the A lanes read in place of K+W
+    uint64_t *full = reinterpret_cast<uint64_t *>(zeros + kC16Stride);
+    uint64_t *empty = full + kC16Slots;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4;
+    const int col = blockIdx.x * 16 + (lane & 15);            // n is a multiple of 16
+    for (int i = threadIdx.x; i < kC16Stride; i += blockDim.x) zeros[i] = 0;
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < NG; g++) { mbar_init(full + g, 16 * G); mbar_init(empty + g, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t rows_lo = ctx[(size_t)16 * n + col], rows_hi = ctx[(size_t)17 * n + col];
+    // control flow follows the first column of the group (a uniform load: every column of a context has absorbed
+    // the same number of rows, the API updates them together), so the compiler sees convergent loops
+    const int pend = (int)(ctx[(size_t)16 * n + blockIdx.x * 16] & 1u);
+    const int nblk = (pend + T) >> 1;
+    if (warp == 0) {
+        const bool isE = half == 0;
+        const uint32_t s1 = isE ? 6 : 2, s2 = isE ? 11 : 13, s3 = isE ? 25 : 22;
+        const uint32_t sgn = isE ? one : 0u - one, mE = isE ? one : 0u, mA = isE ? 0u : one;
+        const uint32_t M = 0u - mA;                           // all-ones on the A lanes; opaque (one is a kernel parameter)
+        const int base = isE ? 4 : 0;
+        uint32_t p = ctx[(size_t)(base + 0) * n + col], q = ctx[(size_t)(base + 1) * n + col];
+        uint32_t r = ctx[(size_t)(base + 2) * n + col], s = ctx[(size_t)(base + 3) * n + col];
+        uint32_t u = 0, v = 0;                                // choice operands of the coming round: Ch(p,u,v)
+        uint32_t cv0 = 0, cv1 = 0, cv2 = 0, cv3 = 0;          // own chaining words (0 until the first boundary step)
+        uint32_t ca[4] = {0, 0, 0, 0};                        // E lanes: the A side's chaining words
+        // delay line of received words: the E lanes start with d, c (then b, a arrive from the idle A lanes)
+        uint32_t rm2 = __shfl_xor_sync(0xffffffffu, s, 16), rm1 = __shfl_xor_sync(0xffffffffu, r, 16);
+        u = lop3<0xF8>(q, r, M); v = lop3<0xC4>(q, r, M);
+#define LGR_C16_BOUNDARY(MX)                                                                   \
+    { uint32_t t_;                                                                             \
+      t_ = p; p = cv0 * (MX) + p; cv0 = t_ * (MX) + cv0;  t_ = q; q = cv1 * (MX) + q; cv1 = t_ * (MX) + cv1; \
+      t_ = r; r = cv2 * (MX) + r; cv2 = t_ * (MX) + cv2;  t_ = s; s = cv3 * (MX) + s; cv3 = t_ * (MX) + cv3; \
+      u = lop3<0xF8>(q, r, M); v = lop3<0xC4>(q, r, M); }
+        // one iteration: E lanes round J of the current block, A lanes two rounds behind
+#define LGR_C16_SHIFT(NP) { s = r; r = q; q = p; p = (NP); u = lop3<0xF8>(q, r, M); v = lop3<0xC4>(q, r, M); }
+#define LGR_C16_ROUND(J, KWX, ACT_A, IDLE_SEND)                                                \
+    { uint32_t d_ = rm2;                                                                       \
+      if ((J) < 4) { d_ = mad_lo(ca[3 - (J)], one, rm2); ca[3 - (J)] = mad_lo(d_, mE, 0u); }   \
+      const uint32_t wr_ = mad_lo(mad_lo(s, sgn, (KWX)), one, d_);                             \
+      const uint32_t sg_ = lop3<0x96>(__funnelshift_r(p, p, s1), __funnelshift_r(p, p, s2), __funnelshift_r(p, p, s3)); \
+      const uint32_t np_ = sg_ + lop3<0xCA>(p, u, v) + wr_;                                    \
+      if (ACT_A) { const uint32_t r0_ = __shfl_xor_sync(0xffffffffu, np_, 16); LGR_C16_SHIFT(np_) rm2 = rm1; rm1 = r0_; } \
+      else { const uint32_t r0_ = __shfl_xor_sync(0xffffffffu, isE ? np_ : (IDLE_SEND), 16);   \
+             if (isE) LGR_C16_SHIFT(np_) rm2 = rm1; rm1 = r0_; } }
+        int grp = 0; uint32_t phase = 0;
+        uint32_t kq[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // K+W of the next eight rounds, loaded ahead of their use
+        for (int b0 = 0; b0 < nblk; b0 += G) {
+            mbar_wait(full + grp, phase);
+            const int cnt = min(G, nblk - b0);
+#pragma unroll 1
+            for (int qb = 0; qb < cnt; qb++) {
+                const int slot = grp * G + qb;
+                const uint32_t *kwp = isE ? ring + (size_t)slot * kC16Stride + lane : zeros + ((slot + 1) & 1) * 16 + (lane & 15);
+                // the next block of the same group is already in the ring: its first eight K+W words are fetched during
+                // the last eight rounds of this block (the A lanes keep reading zeros)
+                const bool chained = qb + 1 < cnt;
+                const uint32_t *kwn = (isE && chained) ? kwp + kC16Stride : zeros + (slot & 1) * 16 + (lane & 15);
+                const bool a_on = (b0 + qb) > 0;              // the A lanes idle through the first two iterations of the launch
+                if (qb == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) kq[j] = kwp[j * 16];
+                }
+                LGR_C16_BOUNDARY(mE)
+                if (a_on) { LGR_C16_ROUND(0, kq[0], true, 0u) LGR_C16_ROUND(1, kq[1], true, 0u) }
+                else { LGR_C16_ROUND(0, kq[0], false, q) LGR_C16_ROUND(1, kq[1], false, p) }
+                kq[0] = kwp[8 * 16]; kq[1] = kwp[9 * 16];
+                LGR_C16_BOUNDARY(mA)
+#pragma unroll
+                for (int j = 2; j < 64; j++) {
+                    const uint32_t kw_ = kq[j & 7];
+                    kq[j & 7] = (j + 8 < 64) ? kwp[(j + 8) * 16] : kwn[(j + 8 - 64) * 16];
+                    LGR_C16_ROUND(j, kw_, true, 0u)
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + grp);
+            if (++grp == NG) { grp = 0; phase ^= 1u; }
+        }
+        if (nblk > 0) {                                        // the A lanes' last two rounds; the E lanes only forward
+            const uint32_t *kwp = zeros + (lane & 15);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const uint32_t wr_ = mad_lo(mad_lo(s, sgn, kwp[j * 16]), one, rm2);
+                const uint32_t sg_ = lop3<0x96>(__funnelshift_r(p, p, s1), __funnelshift_r(p, p, s2), __funnelshift_r(p, p, s3));
+                const uint32_t np_ = sg_ + lop3<0xCA>(p, u, v) + wr_;
+                if (!isE) LGR_C16_SHIFT(np_)
+                rm2 = rm1; rm1 = 0;
+            }
+            p += cv0; q += cv1; r += cv2; s += cv3;            // the last feed-forward
+        }
+#undef LGR_C16_ROUND
+#undef LGR_C16_SHIFT
+#undef LGR_C16_BOUNDARY
+        ctx[(size_t)(base + 0) * n + col] = p; ctx[(size_t)(base + 1) * n + col] = q;
+        ctx[(size_t)(base + 2) * n + col] = r; ctx[(size_t)(base + 3) * n + col] = s;
+        if (isE) {
+            if ((pend + T) & 1) {                              // an unpaired last row stays pending
+                uint32_t w[8];
+                load_words(w, tile + (long long)(T - 1) * row_stride + col);
+#pragma unroll
+                for (int i = 0; i < 8; i++) ctx[(size_t)(8 + i) * n + col] = w[i];
+            }
+            const uint32_t lo = rows_lo + (uint32_t)T;
+            ctx[(size_t)16 * n + col] = lo;
+            ctx[(size_t)17 * n + col] = rows_hi + (lo < rows_lo ? 1u : 0u);
+        }
+    } else {
+        constexpr uint32_t K[64] = {LGR_K256_LIST};
+        const int hv = (warp - 1) * 2 + half;                 // half-warp index
+        const int kC16Helpers = (int)(blockDim.x >> 5) * 2 - 2;
+        uint32_t w[16], nx[16];
+        if (hv < nblk) {
+            load_virtual_row(nx, 2 * hv, pend, ctx, n, col, tile, row_stride);
+            load_virtual_row(nx + 8, 2 * hv + 1, pend, ctx, n, col, tile, row_stride);
+        }
+        for (int b = hv; b < nblk; b += kC16Helpers) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = nx[i];
+            const int bn = b + kC16Helpers;
+            if (bn < nblk) {
+                load_virtual_row(nx, 2 * bn, pend, ctx, n, col, tile, row_stride);
+                load_virtual_row(nx + 8, 2 * bn + 1, pend, ctx, n, col, tile, row_stride);
+            }
+            const int gi = b / G, grp = gi % NG;
+            const uint32_t phase = (uint32_t)(gi / NG) & 1u;
+            mbar_wait(empty + grp, phase ^ 1u);                // passes immediately the first time round
+            uint32_t *dst = ring + (size_t)(grp * G + b % G) * kC16Stride + (lane & 15);
+#pragma unroll
+            for (int i = 0; i < 64; i++) {
+                uint32_t wi;
+                if (i < 16) wi = w[i];
+                else {
+                    const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                    wi = w[i & 15] + (rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3)) + w[(i + 9) & 15] + (rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10));
+                    w[i & 15] = wi;
+                }
+                dst[i * 16] = wi + K[i];
+            }
+            mbar_arrive(full + grp);                           // every lane: releases its own stores
+            if (G > 1 && b == nblk - 1)                        // a ragged last group: stand in for the missing blocks
+                for (int qq = nblk % G; qq != 0 && qq < G; qq++) mbar_arrive(full + grp);
+        }
+    }
+}
+
 // padding + length + digest as native state words (shader/sha256.wgsl:179-230); the context is
 // left untouched so that final is idempotent.
 __global__ void sha_final_kernel(const uint32_t *ctx, int n, uint32_t *digests) {
@@ -373,6 +560,24 @@ cudaError_t launch_sha_init(uint32_t *ctx, int n, cudaStream_t st) {
 }
 cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long long row_stride, int T, cudaStream_t st) {
     if (n <= 0 || T <= 0) return cudaSuccess;
+    // experimental, opt-in: the lane-split chain (16 columns per warp).  In isolation its rounds run in 1277 cycles per
+    // block against 1641 for the 32-column rounds (lgr_ubench_chain 19 vs 11); inside the kernel it measured 1518-1575
+    // against 1573, for twice the SMs, so the 32-column kernel below stays the default.
+    static const bool lane_split = getenv("LGR_CHAIN_SPLIT") != nullptr;
+    if (lane_split && n % 16 == 0 && n / 16 <= 148 && T >= 4) {
+        static const int group16 = getenv("LGR_CHAIN_GROUP") ? atoi(getenv("LGR_CHAIN_GROUP")) : 8;
+        static const int helper_warps = getenv("LGR_CHAIN_HELPERS") ? atoi(getenv("LGR_CHAIN_HELPERS")) : 3;
+#define LGR_C16_LAUNCH(G)                                                                                                               \
+    {                                                                                                                                   \
+        cudaError_t e = cudaFuncSetAttribute(sha_chain16_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC16Smem);        \
+        if (e != cudaSuccess) return e;                                                                                                 \
+        sha_chain16_kernel<G><<<n / 16, 32 * (1 + helper_warps), kC16Smem, st>>>(ctx, n, tile, row_stride, T, 1u);                        \
+        return cudaGetLastError();                                                                                                      \
+    }
+        if (group16 == 1) LGR_C16_LAUNCH(1)
+        if (group16 == 4) LGR_C16_LAUNCH(4)
+        LGR_C16_LAUNCH(8)
+    }
     if (n % 32 == 0 && n / 32 <= 148 && T >= 4) {
         // narrow matrix: producer/consumer CTAs, one chain warp per SM
         static const bool textbook = getenv("LGR_CHAIN_TEXTBOOK") != nullptr;   // A/B knobs: textbook round association, blocks per hand-over

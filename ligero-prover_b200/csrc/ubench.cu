@@ -215,6 +215,13 @@ __device__ __forceinline__ void chain_rounds(uint32_t st[8], const uint32_t *kw 
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
+template <int LUT> __device__ __forceinline__ uint32_t ub_lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d; asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT)); return d;
+}
+__device__ __forceinline__ uint32_t ub_mad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
 template <int VARIANT>
 __global__ void __launch_bounds__(128) ubench_chain_kernel(uint32_t *out, int iters, const ChainConsts cc, int active_lanes) {
     __shared__ uint32_t kw[4][64 * 32];
@@ -247,6 +254,36 @@ __global__ void __launch_bounds__(128) ubench_chain_kernel(uint32_t *out, int it
             }
             st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
         }
+    } else if (VARIANT == 18) {
+        // latency of one SHFL.BFLY hop: 64 dependent shuffles (+ one dependent add each) per iteration
+        uint32_t x = st[0];
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 64; i++) x = __shfl_xor_sync(0xffffffffu, x, 16) + cc.one;
+        }
+        st[0] = x;
+    } else if (VARIANT == 19 || VARIANT == 20) {
+        // lane-split rounds (sha_kernels.cu: sha_chain16_kernel): E half on lanes 0-15, A half on lanes 16-31, one
+        // shuffle per round; 19: partner word used two iterations later (as in the kernel), 20: three iterations later
+        // (not a valid SHA schedule -- it only shows what the exchange latency costs)
+        const bool isE = lane < 16;
+        const uint32_t s1 = isE ? 6 : 2, s2 = isE ? 11 : 13, s3 = isE ? 25 : 22;
+        const uint32_t sgn = isE ? cc.one : 0u - cc.one, M = isE ? 0u : 0u - cc.one;
+        uint32_t p = st[0], q = st[1], r = st[2], s = st[3], rm3 = st[4], rm2 = st[5], rm1 = st[6];
+        uint32_t u = ub_lop3<0xF8>(q, r, M), v = ub_lop3<0xC4>(q, r, M);
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 64; i++) {
+                const uint32_t d = (VARIANT == 20) ? rm3 : rm2;
+                const uint32_t wr = ub_mad(ub_mad(s, sgn, kw[warp][i * 32 + lane]), cc.one, d);
+                const uint32_t sg = ub_lop3<0x96>(__funnelshift_r(p, p, s1), __funnelshift_r(p, p, s2), __funnelshift_r(p, p, s3));
+                const uint32_t np = sg + ub_lop3<0xCA>(p, u, v) + wr;
+                const uint32_t r0 = __shfl_xor_sync(0xffffffffu, np, 16);
+                s = r; r = q; q = p; p = np; u = ub_lop3<0xF8>(q, r, M); v = ub_lop3<0xC4>(q, r, M);
+                rm3 = rm2; rm2 = rm1; rm1 = r0;
+            }
+        }
+        st[0] = p; st[1] = q; st[2] = r; st[3] = s; st[4] = rm2 ^ rm3;
     } else {
         for (int it = 0; it < iters; it++) chain_rounds<VARIANT>(st, kw[warp], lane, cc);
     }
@@ -275,7 +312,10 @@ cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps
     else if (variant == 14) ubench_chain_kernel<14><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 15) ubench_chain_kernel<15><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 16) ubench_chain_kernel<16><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
-    else ubench_chain_kernel<17><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 17) ubench_chain_kernel<17><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 18) ubench_chain_kernel<18><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 19) ubench_chain_kernel<19><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else ubench_chain_kernel<20><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     return cudaGetLastError();
 }
 

@@ -546,3 +546,32 @@ def test_cpp_cuda_executor_drop_in(lgr, oracle, tmp_path):
     for r in range(0, nrows - 2, 3):
         wq = oracle.elt_fma_const(wq, oracle.elt_sub(oracle.elt_mul(cws[r], cws[r + 1]), cws[r + 2]), scal[r])
     assert np.array_equal(code, wc) and np.array_equal(quad, wq)
+
+
+def test_lane_split_chain_kernel_opt_in(tmp_path):
+    """LGR_CHAIN_SPLIT=1 selects sha_chain16_kernel (round split over the two half-warps, csrc/sha_kernels.cu); it is
+    not the default (no faster in the kernel, see the comment at its launch site) but must stay bit-exact"""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, %r)
+        import numpy as np
+        import __graft_entry__ as ge
+        from oracle import lgo
+        lgr = ge._load_package()
+        for k, R in ((256, 4100), (64, 17), (256, 7)):
+            n = 4 * k
+            ex = lgr.make_executor(max(k - 192, 1), k)
+            rows = lgo.synth(3, 0, R, k)
+            src = ex.make_device_buffer(R * k * 32); ex.write_buffer(src, rows)
+            dig = ex.make_device_buffer(n * 32); nodes = ex.make_device_buffer((2 * n - 1) * 32)
+            ex.encode_commit(src, R, dig, nodes)
+            want_d, want_n, _ = lgo.encode_commit(rows, k)
+            assert np.array_equal(ex.copy_to_host(dig, np.uint8).reshape(n, 32), want_d), (k, R)
+            assert np.array_equal(ex.copy_to_host(nodes, np.uint8).reshape(2 * n - 1, 32), want_n), (k, R)
+            ex.close()
+        print("ok")
+    """) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LGR_CHAIN_SPLIT="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

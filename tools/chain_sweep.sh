@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 : > gpurun_out/sweep.log
 run() {  # name, env...
   local name=$1; shift
-  env "$@" python -m pytest tests -m gpu -x -q -k "encode_commit_pipeline or sha_leaf or stage1_stage2" > gpurun_out/pytest_$name.log 2>&1
-  echo "pytest $name: $?" | tee -a gpurun_out/sweep.log
+  env "$@" python -m pytest tests -m gpu -x -q -k "encode_commit_pipeline or sha_leaf or stage1_stage2 or prove" > gpurun_out/pytest_$name.log 2>&1
+  echo "pytest $name: $? $(tail -1 gpurun_out/pytest_$name.log)" | tee -a gpurun_out/sweep.log
   env "$@" python bench.py --log-rows 19 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
   python - <<PY | tee -a gpurun_out/sweep.log
 import json
@@ -17,9 +17,7 @@ except Exception as e:
     print("$name failed", e)
 PY
 }
-run group4 LGR_CHAIN_GROUP=4
-run group8 LGR_CHAIN_GROUP=8
-run group2 LGR_CHAIN_GROUP=2
-run textbook LGR_CHAIN_TEXTBOOK=1
-python tools/chain_ubench.py > gpurun_out/chain_ubench.log 2>&1
-tail -40 gpurun_out/chain_ubench.log
+run split8 LGR_CHAIN_GROUP=8
+run split4 LGR_CHAIN_GROUP=4
+run split1 LGR_CHAIN_GROUP=1
+run nosplit LGR_CHAIN_NO_SPLIT=1
