@@ -178,3 +178,27 @@ def test_oracle_prover_is_self_consistent(oracle):
     with pytest.raises(AssertionError):
         ref.verify_openings(env2, l, k, kinds, coef, inst)
     assert not ref.prove(l, k, kinds, values, coef, (1 - acc) % ref.P, bytes(32), inst)["valid"][1]
+
+
+def _load_fixture():
+    import json
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "prover_k64.json")))
+    l = fx["l"]
+    values = np.frombuffer(bytes.fromhex(fx["values_hex"]), np.uint32).reshape(-1, l, 8)
+    coefs = np.frombuffer(bytes.fromhex(fx["coefs_hex"]), np.uint32).reshape(-1, l, 8)
+    return fx, values, coefs
+
+
+def test_oracle_prover_matches_committed_fixture(oracle):
+    """tests/golden/prover_k64.json (made by tests/golden/make_prover_fixture.py) pins the restatement"""
+    fx, values, coefs = _load_fixture()
+    w = ref.prove(fx["l"], fx["k"], fx["kinds"], values, coefs, int(fx["const_sum"], 16), bytes.fromhex(fx["encoding_seed"]),
+                  bytes.fromhex(fx["instance_hash"]))
+    assert w["root"].hex() == fx["root"] and w["stage1_seed"].hex() == fx["stage1_seed"] and w["stage2_seed"].hex() == fx["stage2_seed"]
+    assert w["sample"] == fx["sample"] and list(w["valid"]) == fx["valid"]
+    assert hashlib.sha256(w["code"].tobytes()).hexdigest() == fx["code_sha256"]
+    assert hashlib.sha256(w["samplings"].tobytes()).hexdigest() == fx["samplings_sha256"]
+    meta = {"prover_version": "1.5.0", "program_hash": bytes.fromhex(fx["program_hash"]), "generated_at": fx["generated_at"], "k": fx["k"],
+            "n": 4 * fx["k"], "sample_size": 192}
+    env = ref.build_envelope(meta, w["root"], w["siblings"], w["sample"], w["code"], w["linear"], w["quad"], w["samplings"])
+    assert len(env) == fx["envelope_len"] and hashlib.sha256(env).hexdigest() == fx["envelope_sha256"]

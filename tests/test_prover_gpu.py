@@ -130,3 +130,20 @@ def test_prove_large_matrix_properties(lgr, oracle, pr, executor_factory):
         row = np.zeros((k, 8), np.uint32); row[:l] = values[t]; row[l:] = oracle.to_limbs(enc.take(k - l))
         assert np.array_equal(samp[t], oracle.encode(row, k)[sample])
     proof.close()
+
+
+def test_prove_matches_committed_fixture(lgr, pr, executor_factory):
+    """the GPU prover reproduces the committed golden proof (tests/golden/prover_k64.json) byte for byte"""
+    import json, os
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prover_k64.json")))
+    l, k = fx["l"], fx["k"]
+    values = np.frombuffer(bytes.fromhex(fx["values_hex"]), np.uint32).reshape(-1, l, 8)
+    coefs = np.frombuffer(bytes.fromhex(fx["coefs_hex"]), np.uint32).reshape(-1, l, 8)
+    ex = executor_factory(k, l)
+    proof = pr.prove(ex, fx["kinds"], values, coefs, int(fx["const_sum"], 16), bytes.fromhex(fx["encoding_seed"]), bytes.fromhex(fx["instance_hash"]),
+                     bytes.fromhex(fx["program_hash"]), generated_at=fx["generated_at"])
+    info = proof.info()
+    assert list(info["valid"]) == fx["valid"] and info["stage1_seed"].hex() == fx["stage1_seed"] and info["stage2_seed"].hex() == fx["stage2_seed"]
+    env = proof.envelope
+    assert len(env) == fx["envelope_len"] and hashlib.sha256(env).hexdigest() == fx["envelope_sha256"]
+    proof.close()
