@@ -364,6 +364,16 @@ def main():
                         "peak_source": peak_src,
                         "path_bytes_per_element": 32, "path_achieved": value / world * 32 / 1e9, "path_frac": value / world * 32 / 1e9 / hbm,
                         "note": "integer-issue bound path: see int_roofline and DESIGN.md"}
+        # the dominant kernel against the bound that actually holds for it: one warp per 32 columns, ALU-issue-bound
+        # (12 SHF/LOP3/IADD3 per round at one warp instruction per 2 cycles, 64 rounds: DESIGN.md section 4)
+        chain_roofline = None
+        if "sha_chain_kernel" in kern and clocks.get("sm_mhz"):
+            d = kern["sha_chain_kernel"]
+            blocks_per_launch = (R * args.steps / d["launches"]) / 2.0
+            cyc = d["ms_per_launch"] * 1e-3 * clocks["sm_mhz"] * 1e6 / blocks_per_launch
+            chain_roofline = {"kernel": "sha_chain_kernel", "bound": "alu_issue_of_one_warp", "unit": "cycles per 64-byte block per column",
+                              "floor": 1536.0, "achieved": cyc, "frac": 1536.0 / cyc,
+                              "note": "a column is one SHA-256 chain: n/32 warps of work whatever the GPU; floor = 64 rounds x 12 ALU instructions x 2 cycles"}
         ub = {"imad_wide_per_s": ex.ubench(0), "montmul_per_s": ex.ubench(1), "sha256_compress_per_s": ex.ubench(2)}
         import math
         mm_per_elem = (math.log2(k) - 1) / 2 + 3 + 3 * (math.log2(k) - 1) / 2      # iNTT_k + 3 computed cosets (the 4th is a copy)
@@ -390,7 +400,7 @@ def main():
                        "rows_per_gpu": R, "k": k, "n": n, "l2": "inputs (%.0f GiB per GPU) larger than L2 (126 MB); no flush needed" % (R * k * 32 / 2**30),
                        "parallelism": ("rows sharded over %d GPU(s); digests all-gathered (NCCL) for the tree" % world) if exact_engine is None else
                                       ("exact layout over %d GPUs: tiles round-robin, all-to-all of column slabs, one root" % world)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kern, "int_roofline": int_roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "chain_roofline": chain_roofline, "kernels": kern, "int_roofline": int_roofline,
             "cpu_baseline": cpu, "root": root,
         }
         if aux:

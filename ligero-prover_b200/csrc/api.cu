@@ -781,11 +781,12 @@ int lgr_synth(lgr_ctx *c, void *out, uint64_t seed, uint64_t row0, uint64_t nrow
 }
 int lgr_ubench(lgr_ctx *c, int which, double *ops) {
     REQUIRE(c && ops, "null argument");
-    REQUIRE(which >= 0 && which <= 4, "unknown micro-benchmark");
+    REQUIRE(which >= 0 && which <= 5, "unknown micro-benchmark");
     uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
     cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     const int blocks = 148 * 8, threads = 256;
-    const int iters = (which == 0 || which >= 3) ? 4096 : (which == 1 ? 512 : 256);
+    const bool mulbench = (which == 1 || which == 5);           // Montgomery / Shoup multiplications, 4 per iteration
+    const int iters = mulbench ? 512 : ((which == 0 || which >= 3) ? 4096 : 256);
     CU(launch_ubench(which, d, iters, blocks, threads, c->stream));           // warm-up
     CU(cudaEventRecord(e0, c->stream));
     for (int i = 0; i < 5; i++) CU(launch_ubench(which, d, iters, blocks, threads, c->stream));
@@ -793,7 +794,7 @@ int lgr_ubench(lgr_ctx *c, int which, double *ops) {
     CU(cudaEventSynchronize(e1));
     c->launches += 6;
     float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
-    const double per_thread = (which == 0 || which >= 3) ? 8.0 * iters : (double)iters * (which == 1 ? 4.0 : 1.0);
+    const double per_thread = mulbench ? 4.0 * iters : ((which == 0 || which >= 3) ? 8.0 * iters : (double)iters);
     *ops = 5.0 * per_thread * blocks * threads / (ms * 1e-3);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return LGR_OK;

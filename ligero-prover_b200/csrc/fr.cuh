@@ -217,6 +217,64 @@ LGR_DEV fr_t fr_mont_mul(const fr_t &a, const fr_t &b) {
 // canonical result
 LGR_DEV fr_t fr_mont_mul_canon(const fr_t &a, const fr_t &b) { return fr_canon4(fr_mont_mul(a, b)); }
 
+// ---- multiplication by a table constant (Shoup) --------------------------------------------------
+// For a fixed w < p with the precomputed quotient wq = floor(w * 2^256 / p):
+//     q = floor(x * wq / 2^256),   r = x*w - q*p  in [0, 2p)      for ANY x < 2^256
+// so only the HIGH half of x*wq and the LOW halves of x*w and q*p are needed: 99 wide multiply-adds and
+// 16 low-word ones instead of the 136 + 8 of a Montgomery multiplication, operands and result in the plain
+// (non-Montgomery) domain.  The high half is computed from the partial products of columns >= 7 plus the
+// high words of column 6; what is dropped is < 2^229, so the quotient is at most one short and
+// r < 3p < 2^256; one conditional subtraction of 2p brings it back to [0,2p).
+// Column-wise (Comba) accumulation: (c0,c1,c2) hold limbs k, k+1, k+2 while column k is summed; each
+// product is one IMAD.WIDE with carry-out plus one IADD3.X (the ALU pipe idles in these kernels).
+namespace detail {
+#define LGR_COMBA_FULL(A, B) { c0 = mad_lo_cc((A), (B), c0); c1 = madc_hi_cc((A), (B), c1); c2 = addc(c2, 0); }
+// approximate high half of x*y: q[0..7] = limbs 8..15 (at most one unit in q too small)
+LGR_DEV void mul_hi_approx(uint32_t *q, const uint32_t *x, const uint32_t *y) {
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) { c0 = mad_hi_cc(x[6 - i], y[i], c0); c1 = addc(c1, 0); }     // limb 7: high words of column 6
+#pragma unroll
+    for (int k = 7; k < 15; k++) {
+#pragma unroll
+        for (int i = k - 7; i < 8; i++) LGR_COMBA_FULL(x[k - i], y[i])
+        if (k >= 8) q[k - 8] = c0;
+        c0 = c1; c1 = c2; c2 = 0;
+    }
+    q[7] = c0;
+}
+// low half of x*y (mod 2^256); YCONST: y = p
+template <bool YCONST>
+LGR_DEV void mul_lo_256(uint32_t *r, const uint32_t *x, const uint32_t *y) {
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+#pragma unroll
+        for (int i = 0; i <= k; i++) LGR_COMBA_FULL(x[k - i], YCONST ? fr_p(i) : y[i])
+        r[k] = c0;
+        c0 = c1; c1 = c2; c2 = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) c0 += mul_lo(x[7 - i], YCONST ? fr_p(i) : y[i]);
+    r[7] = c0;
+}
+#undef LGR_COMBA_FULL
+}  // namespace detail
+
+// x < 2^256 (any lazy range), w in [0,p), wq = floor(w*2^256/p)  ->  x*w mod p in [0,2p)
+LGR_DEV fr_t fr_shoup_mul(const fr_t &x, const fr_t &w, const fr_t &wq) {
+    uint32_t q[8], lo[8], qp[8];
+    detail::mul_hi_approx(q, x.v, wq.v);
+    detail::mul_lo_256<false>(lo, x.v, w.v);
+    detail::mul_lo_256<true>(qp, q, nullptr);
+    fr_t r;
+    r.v[0] = sub_cc(lo[0], qp[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = subc_cc(lo[i], qp[i]);
+    r.v[7] = subc(lo[7], qp[7]);
+    return fr_reduce_2p(r);
+}
+
 // ---- wide (unreduced) accumulation of products ----------------------------------------------
 // S += a*b as a plain 512-bit product added into a 576-bit accumulator: 64 wide multiply-adds and no
 // reduction per product (a Montgomery multiplication costs 136).  The accumulator is kept as an

@@ -63,6 +63,26 @@ __global__ void __launch_bounds__(256) ubench_mont_kernel(uint32_t *out, int ite
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// 4 independent Shoup multiplications per iteration (fr_shoup_mul: the twiddle multiplication of the butterflies)
+__global__ void __launch_bounds__(256) ubench_shoup_kernel(uint32_t *out, int iters) {
+    fr_t x[4], w, wq;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { w.v[i] = (threadIdx.x + 1) * 0x9E3779B1u + i * 0x85EBCA77u; wq.v[i] = w.v[i] * 0x2545F491u + 77u; }
+    w.v[7] &= 0x0FFFFFFFu;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { x[q] = w; x[q].v[0] += q + blockIdx.x; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) x[q] = fr_shoup_mul(x[q], w, wq);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) s ^= x[q].v[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __device__ __forceinline__ uint32_t ub_rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 // one dependent SHA-256 compression per iteration (same round structure as sha_kernels.cu)
 __global__ void __launch_bounds__(256) ubench_sha_kernel(uint32_t *out, int iters) {
@@ -359,6 +379,7 @@ cudaError_t launch_ubench(int which, uint32_t *out, int iters, int blocks, int t
     else if (which == 3) ubench_imad_kernel<false><<<blocks, threads, 0, st>>>(out, iters);
     else if (which == 4) ubench_dfma_kernel<<<blocks, threads, 0, st>>>(out, iters);
     else if (which == 1) ubench_mont_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    else if (which == 5) ubench_shoup_kernel<<<blocks, threads, 0, st>>>(out, iters);
     else ubench_sha_kernel<<<blocks, threads, 0, st>>>(out, iters);
     return cudaGetLastError();
 }

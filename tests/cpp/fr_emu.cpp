@@ -26,6 +26,14 @@ void emu_mont_mul(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t n,
         for (int j = 0; j < 8; j++) out[8*i+j] = r.v[j];
     }
 }
+// out[i] = fr_shoup_mul(a[i], w[i], wq[i]) (in [0,2p)); wq = floor(w * 2^256 / p) supplied by the caller
+void emu_shoup_mul(uint32_t *out, const uint32_t *a, const uint32_t *w, const uint32_t *wq, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fr_t x, y, z; for (int j = 0; j < 8; j++) { x.v[j] = a[8*i+j]; y.v[j] = w[8*i+j]; z.v[j] = wq[8*i+j]; }
+        fr_t r = fr_shoup_mul(x, y, z);
+        for (int j = 0; j < 8; j++) out[8*i+j] = r.v[j];
+    }
+}
 void emu_binop(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t n, int op) {
     for (size_t i = 0; i < n; i++) {
         fr_t x, y, r; for (int j = 0; j < 8; j++) { x.v[j] = a[8*i+j]; y.v[j] = b[8*i+j]; }

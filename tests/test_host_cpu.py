@@ -44,6 +44,22 @@ def test_device_montgomery_algorithm_under_emulation(emu, oracle):
     assert got == [x * b[0] * rinv % P for x in ac[:50]]
 
 
+def test_device_shoup_multiplication_under_emulation(emu, oracle):
+    """fr_shoup_mul (twiddle multiplications: truncated high product + two low products): any x < 2^256, w < p ->
+    x*w mod p in [0,2p)"""
+    rng = random.Random(8)
+    edge = [0, 1, 2, P - 1, P, 2 * P, 4 * P - 1, (1 << 256) - 1, (1 << 255), (1 << 224) - 1, (1 << 32) - 1]
+    wedge = [0, 1, 2, P - 1, P - 2, P >> 1, (1 << 32) - 1, (1 << 224), 7]
+    a = [rng.randrange(1 << 256) for _ in range(6000)] + [x for x in edge for _ in wedge]
+    w = [rng.randrange(P) for _ in range(6000)] + [y for _ in edge for y in wedge]
+    wq = [(y << 256) // P for y in w]
+    A, W, WQ = oracle.to_limbs(a), oracle.to_limbs(w), oracle.to_limbs(wq)
+    O = np.zeros_like(A)
+    emu.emu_shoup_mul(O.ctypes.data_as(C.c_void_p), A.ctypes.data_as(C.c_void_p), W.ctypes.data_as(C.c_void_p), WQ.ctypes.data_as(C.c_void_p), C.c_size_t(len(a)))
+    out = oracle.from_limbs(O)
+    assert all(z % P == x * y % P and z < 2 * P for x, y, z in zip(a, w, out))
+
+
 def test_device_lazy_reductions_under_emulation(emu, oracle):
     rng = random.Random(6)
     a = [rng.randrange(P) for _ in range(2000)] + [0, P - 1, 0, P - 1]
