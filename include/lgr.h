@@ -136,6 +136,10 @@ int lgr_encode_rows(lgr_ctx *ctx, const void *rows, uint64_t row_stride_elems, u
  * (nonbatch_context.hpp:555-558, merkle_tree.hpp:343-375).  digests: n*32 B; nodes: (2n-1)*32 B or NULL.
  * Encoding of tile t+1 overlaps hashing of tile t on a second stream. */
 int lgr_encode_commit(lgr_ctx *ctx, const void *rows, uint64_t nrows, void *digests, void *nodes);
+/* the same tile pipeline without init / final / tree: every row is encoded and absorbed, in order, into the caller's
+ * column-hash context (n instances, lgr_sha_init): what a stage-1 context does between its first row and
+ * flush_digests when other rows (the 2k-domain mask rows, nonbatch_context.hpp:482-494) have to follow */
+int lgr_encode_absorb(lgr_ctx *ctx, void *sha_ctx, const void *rows, uint64_t nrows);
 /* same pipeline for a HOST-resident witness (pinned memory recommended): rows are copied tile by
  * tile on a third stream (H2D of tile t+2, encode of tile t+1 and hashing of tile t overlap), the
  * n digests (may be NULL) and the 32-byte root come back to the host; blocking.  This is the call

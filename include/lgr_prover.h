@@ -59,6 +59,10 @@ void lgrp_proof_free(lgrp_proof *p);
 /* prover self-check flags (src/webgpu_prover.cpp:465-471): bit 0 code, bit 1 linear, bit 2 quadratic; the two stage seeds */
 int lgrp_proof_info(const lgrp_proof *p, uint32_t *valid_bits, uint8_t stage1_seed[32], uint8_t stage2_seed[32], uint64_t *encoded_rows);
 
+/* host wall-clock milliseconds of stage 1 (commit), stage 2 (test vectors, sampling, self-check), stage 3 (openings) and
+ * the container (serialise + gzip); every stage ends with a blocking read, so device time is included */
+int lgrp_proof_timing(const lgrp_proof *p, double ms[4]);
+
 /* ---- the three-stage prover over a witness matrix (needs a B200: runs the hot path through lgr.h) -- */
 typedef struct {
     uint32_t l, k;                 /* must match the context (n = 4k) */

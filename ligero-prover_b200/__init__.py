@@ -465,6 +465,10 @@ class Executor:
                                             dig.ctypes.data_as(C.c_void_p) if want_digests else None, root.ctypes.data_as(C.c_void_p)))
         return dig, root.tobytes()
 
+    def encode_absorb(self, sha_ctx, rows, nrows):
+        """lgr_encode_absorb: encode nrows device-resident rows and absorb them, in order, into a caller-owned column-hash context"""
+        _check(lib().lgr_encode_absorb(self._ctx, sha_ctx.ptr(), rows.ptr(), C.c_uint64(nrows)))
+
     def profile(self, enable):
         _check(lib().lgr_profile(self._ctx, C.c_int(int(enable))))
 

@@ -634,7 +634,8 @@ static size_t commit_tile_rows(const lgr_ctx *c, uint64_t nrows) {
 }
 
 // rows: device-resident (host_rows == nullptr) or host-resident (pinned or pageable) row-major R x k.
-static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host_rows, uint64_t nrows, void *digests, void *nodes) {
+// ext_sha != nullptr: absorb into the caller's column-hash context and stop there (no init, no final, no tree)
+static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host_rows, uint64_t nrows, void *digests, void *nodes, uint32_t *ext_sha = nullptr) {
     REQUIRE(nrows < (1ull << 40), "too many rows");
     const size_t n = c->n, k = c->k;
     const size_t T = commit_tile_rows(c, nrows);
@@ -651,12 +652,13 @@ static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host
         for (int i = 0; i < 2; i++) CU(cudaMalloc((void **)&c->h2d_buf[i], T * k * 32));
         c->h2d_elems = T * k;
     }
-    if (!c->commit_sha) CU(cudaMalloc((void **)&c->commit_sha, lgr_sha_ctx_bytes((uint32_t)n)));
+    if (!ext_sha && !c->commit_sha) CU(cudaMalloc((void **)&c->commit_sha, lgr_sha_ctx_bytes((uint32_t)n)));
+    uint32_t *sha = ext_sha ? ext_sha : c->commit_sha;
     cudaStream_t es = c->stream, hs = overlap ? c->aux_stream : c->stream, cs = c->copy_stream;
     CU(cudaEventRecord(c->ev_fork, es));
     if (overlap) CU(cudaStreamWaitEvent(hs, c->ev_fork, 0));
     if (host_rows) CU(cudaStreamWaitEvent(cs, c->ev_fork, 0));
-    CU(launch_sha_init(c->commit_sha, (int)n, hs)); c->launches++;
+    if (!ext_sha) { CU(launch_sha_init(sha, (int)n, hs)); c->launches++; }
     int rc;
     size_t tile_idx = 0;
     for (uint64_t r0 = 0; r0 < nrows; r0 += T, tile_idx++) {
@@ -677,12 +679,12 @@ static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host
         if (host_rows) CU(cudaEventRecord(c->ev_h2d_free[b], es));
         if (overlap) { CU(cudaEventRecord(c->ev_enc[b], es)); CU(cudaStreamWaitEvent(hs, c->ev_enc[b], 0)); }
         if (c->profiling) { p0 = prof_event(c); p1 = prof_event(c); CU(cudaEventRecord(p0, hs)); }
-        CU(launch_sha_update(c->commit_sha, (int)n, c->tile[b], (long long)n, (int)t, hs)); c->launches++;
+        CU(launch_sha_update(sha, (int)n, c->tile[b], (long long)n, (int)t, hs)); c->launches++;
         if (c->profiling) { CU(cudaEventRecord(p1, hs)); c->prof_sha.emplace_back(p0, p1); }
         if (overlap) CU(cudaEventRecord(c->ev_hash[b], hs));
     }
-    CU(launch_sha_final(c->commit_sha, (int)n, (uint32_t *)digests, hs)); c->launches++;
-    if (nodes) {
+    if (!ext_sha) { CU(launch_sha_final(sha, (int)n, (uint32_t *)digests, hs)); c->launches++; }
+    if (!ext_sha && nodes) {
         CU(launch_merkle_build((const uint32_t *)digests, (int)n, (uint32_t *)nodes, hs));
         int lv = 1; for (size_t cnt = n >> 1; cnt > 256; cnt >>= 1) lv++;
         c->launches += lv + 1;
@@ -694,6 +696,12 @@ static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host
 int lgr_encode_commit(lgr_ctx *c, const void *rows, uint64_t nrows, void *digests, void *nodes) {
     REQUIRE(c && rows && digests, "null argument");
     return encode_commit_impl(c, (const fr_mem *)rows, nullptr, nrows, digests, nodes);
+}
+
+int lgr_encode_absorb(lgr_ctx *c, void *sha_ctx, const void *rows, uint64_t nrows) {
+    REQUIRE(c && sha_ctx && rows, "null argument");
+    if (!nrows) return LGR_OK;
+    return encode_commit_impl(c, (const fr_mem *)rows, nullptr, nrows, nullptr, nullptr, (uint32_t *)sha_ctx);
 }
 
 int lgr_encode_commit_host(lgr_ctx *c, const void *host_rows, uint64_t nrows, void *host_digests, void *host_root) {

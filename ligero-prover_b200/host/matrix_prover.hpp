@@ -58,6 +58,7 @@ struct prove_result {
     bool valid_code = false, valid_linear = false, valid_quad = false;   // the prover's self-check (src/webgpu_prover.cpp:465-471)
     bool ok() const { return valid_code && valid_linear && valid_quad; }
     uint64_t encoded_rows = 0;                   // incl. the three mask rows
+    double ms[4] = {0, 0, 0, 0};                 // wall time of stage 1, stage 2 (+ sampling, self-check), stage 3, container
 };
 
 class matrix_prover {
@@ -81,11 +82,9 @@ public:
         void *sha = dalloc(sha_bytes), *digests = dalloc((size_t)n_ * 32);
         const size_t node_count = lgr_merkle_node_count(n_);
         void *nodes = dalloc(node_count * 32);
+        const auto t0 = clock_now();
         chk(lgr_sha_init(ctx_, sha, n_));
-        for_each_tile([&](size_t r0, uint32_t T) {
-            chk(lgr_encode_rows(ctx_, at(d_val_, r0 * k_), k_, T, tile_));
-            chk(lgr_sha_update_rows(ctx_, sha, n_, tile_, n_, T));
-        });
+        chk(lgr_encode_absorb(ctx_, sha, d_val_, rows_));      // tile pipeline: encode of tile t+1 overlaps hashing of tile t
         for (int m = 0; m < 3; m++) { encode_mask(m); chk(lgr_sha_update(ctx_, sha, n_, mask_cw_)); }
         chk(lgr_sha_final(ctx_, sha, n_, digests));
         chk(lgr_merkle_build(ctx_, digests, n_, nodes));
@@ -94,13 +93,13 @@ public:
         digest root;
         memcpy(root.data, host_nodes.data(), 32);
         out.stage1_seed = stage1_seed(root, st.instance_hash);
+        const auto t1 = clock_now();
 
         // ---- stage 2: test vectors -----------------------------------------------------------------
         static const uint8_t any_iv[16] = {0};                                 // params::any_iv
         fr_random_stream code_rng(out.stage1_seed.data, any_iv), quad_rng(out.stage1_seed.data, any_iv);   // nonbatch_context.hpp:105-112
         std::vector<uint32_t> r_code(rows_ * 8), r_quad;
         // draw order = callback order: linear row -> 1 code draw; triple -> 3 code draws then 1 quadratic draw
-        for (const row_event &e : st.events) { (void)e; }
         {
             size_t r = 0;
             for (const row_event &e : st.events) {
@@ -153,6 +152,7 @@ public:
             for (size_t i = 0; i < (size_t)l_ * 8; i++) if (h[i]) { out.valid_quad = false; break; }
         }
 
+        const auto t2 = clock_now();
         // ---- stage 3: open the sampled columns -----------------------------------------------------
         const uint32_t S = (uint32_t)sample.size();
         chk(lgr_sample_init(ctx_, sample.data(), S));
@@ -169,6 +169,7 @@ public:
             chk(lgr_read(ctx_, &pd.samplings[(rows_ + m) * S * 8], d_samp, 0, (size_t)S * 32));
         }
 
+        const auto t3 = clock_now();
         // ---- container (src/webgpu_prover.cpp:410-458) ---------------------------------------------
         pd.meta.program_hash = st.program_hash;
         pd.meta.packing_size = k_;
@@ -179,11 +180,16 @@ public:
             : (int64_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::system_clock::now().time_since_epoch()).count();
         out.envelope = serialize_proof(pd);
         out.gzip = gzip_compress(out.envelope, 6);
+        const auto t4 = clock_now();
+        out.ms[0] = ms_between(t0, t1); out.ms[1] = ms_between(t1, t2); out.ms[2] = ms_between(t2, t3); out.ms[3] = ms_between(t3, t4);
         release();
         return out;
     }
 
 private:
+    using clock_point = std::chrono::steady_clock::time_point;
+    static clock_point clock_now() { return std::chrono::steady_clock::now(); }
+    static double ms_between(clock_point a, clock_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); }
     [[noreturn]] void fail(const char *what) { throw std::runtime_error(std::string(what) + ": " + lgr_last_error()); }
     void chk(int rc) { if (rc) fail("liblgr"); }
     static void *at(void *base, size_t elems) { return static_cast<uint8_t *>(base) + elems * 32; }

@@ -10,10 +10,15 @@
 #pragma once
 #include <zlib.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <exception>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "merkle_host.hpp"
@@ -214,31 +219,82 @@ inline proof_data deserialize_proof(const std::string &bytes) {
 }
 
 // ---- gzip (src/webgpu_prover.cpp:437-446: level 6) ---------------------------------------------
-inline std::string gzip_compress(const std::string &in, int level = 6) {
+// One gzip member, deflate level 6 as the reference asks.  Proofs are mostly sampled field elements
+// (incompressible), so zlib runs at ~45 MB/s on one core; inputs above 8 MiB are therefore cut into chunks that
+// are deflated in parallel as raw streams, each ended with a sync flush (byte-aligned empty stored block), and
+// stitched into a single member with the CRCs combined -- the construction pigz uses; any inflater reads it.
+namespace detail {
+inline std::string deflate_raw_chunk(const char *data, size_t len, int level, bool last) {
     z_stream zs{};
-    if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("deflateInit2 failed");
-    std::string out(deflateBound(&zs, in.size()) + 32, '\0');
-    zs.next_in = reinterpret_cast<Bytef *>(const_cast<char *>(in.data())); zs.avail_in = (uInt)in.size();
+    if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("deflateInit2 failed");
+    std::string out(deflateBound(&zs, len) + 64, '\0');
+    zs.next_in = reinterpret_cast<Bytef *>(const_cast<char *>(data)); zs.avail_in = (uInt)len;
     zs.next_out = reinterpret_cast<Bytef *>(&out[0]); zs.avail_out = (uInt)out.size();
-    if (in.size() > 0xFFFFFFF0u || out.size() > 0xFFFFFFF0u) { deflateEnd(&zs); throw std::runtime_error("proof larger than 4 GiB"); }
-    const int rc = deflate(&zs, Z_FINISH);
-    deflateEnd(&zs);
-    if (rc != Z_STREAM_END) throw std::runtime_error("deflate failed");
+    const int rc = deflate(&zs, last ? Z_FINISH : Z_SYNC_FLUSH);
+    const bool ok = last ? rc == Z_STREAM_END : (rc == Z_OK && zs.avail_in == 0);
     out.resize(zs.total_out);
+    deflateEnd(&zs);
+    if (!ok) throw std::runtime_error("deflate failed");
+    return out;
+}
+}  // namespace detail
+
+inline std::string gzip_compress(const std::string &in, int level = 6, unsigned threads = 0) {
+    const size_t chunk = (size_t)8 << 20;
+    const size_t nchunks = in.empty() ? 1 : (in.size() + chunk - 1) / chunk;
+    std::vector<std::string> parts(nchunks);
+    std::vector<uLong> crcs(nchunks);
+    auto work = [&](size_t c) {
+        const size_t off = c * chunk, len = std::min(chunk, in.size() - off);
+        parts[c] = detail::deflate_raw_chunk(in.data() + off, len, level, c + 1 == nchunks);
+        crcs[c] = crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const Bytef *>(in.data() + off), (uInt)len);
+    };
+    if (threads == 0) threads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (nchunks == 1 || threads == 1) {
+        for (size_t c = 0; c < nchunks; c++) work(c);
+    } else {
+        std::atomic<size_t> next{0};
+        std::exception_ptr err;
+        std::mutex mu;
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < std::min<size_t>(threads, nchunks); t++)
+            pool.emplace_back([&] {
+                try { for (size_t c; (c = next.fetch_add(1)) < nchunks;) work(c); }
+                catch (...) { std::lock_guard<std::mutex> g(mu); err = std::current_exception(); }
+            });
+        for (auto &th : pool) th.join();
+        if (err) std::rethrow_exception(err);
+    }
+    std::string out;
+    static const unsigned char hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3};      // no name, mtime 0, OS = Unix (what zlib writes)
+    out.append(reinterpret_cast<const char *>(hdr), 10);
+    uLong crc = crc32(0L, Z_NULL, 0);
+    for (size_t c = 0; c < nchunks; c++) {
+        out += parts[c];
+        crc = crc32_combine(crc, crcs[c], (z_off_t)std::min(chunk, in.size() - c * chunk));
+    }
+    const uint32_t trailer[2] = {(uint32_t)crc, (uint32_t)(in.size() & 0xFFFFFFFFu)};
+    out.append(reinterpret_cast<const char *>(trailer), 8);
     return out;
 }
 inline std::string gzip_decompress(const std::string &in) {
     z_stream zs{};
     if (inflateInit2(&zs, 15 + 32) != Z_OK) throw std::runtime_error("inflateInit2 failed");
     std::string out;
-    std::vector<char> buf(1 << 20);
-    zs.next_in = reinterpret_cast<Bytef *>(const_cast<char *>(in.data())); zs.avail_in = (uInt)in.size();
-    int rc;
+    std::vector<char> buf(1 << 22);
+    size_t fed = 0;
+    int rc = Z_OK;
     do {
+        if (zs.avail_in == 0 && fed < in.size()) {
+            const size_t take = std::min<size_t>(in.size() - fed, (size_t)1 << 30);
+            zs.next_in = reinterpret_cast<Bytef *>(const_cast<char *>(in.data() + fed)); zs.avail_in = (uInt)take;
+            fed += take;
+        }
         zs.next_out = reinterpret_cast<Bytef *>(buf.data()); zs.avail_out = (uInt)buf.size();
         rc = inflate(&zs, Z_NO_FLUSH);
         if (rc != Z_OK && rc != Z_STREAM_END) { inflateEnd(&zs); throw std::runtime_error("inflate failed"); }
         out.append(buf.data(), buf.size() - zs.avail_out);
+        if (rc == Z_OK && zs.avail_in == 0 && fed >= in.size() && zs.avail_out != 0) { inflateEnd(&zs); throw std::runtime_error("truncated gzip stream"); }
     } while (rc != Z_STREAM_END);
     inflateEnd(&zs);
     return out;

@@ -130,6 +130,13 @@ int lgrp_proof_info(const lgrp_proof *p, uint32_t *valid_bits, uint8_t s1[32], u
     LGRP_END
 }
 
+int lgrp_proof_timing(const lgrp_proof *p, double ms[4]) {
+    LGRP_TRY
+    if (!p || !ms) throw std::invalid_argument("null argument");
+    for (int i = 0; i < 4; i++) ms[i] = p->r.ms[i];
+    LGRP_END
+}
+
 int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *s, lgrp_proof **out) {
     LGRP_TRY
     if (!ctx || !s || !out) throw std::invalid_argument("null argument");

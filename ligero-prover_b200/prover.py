@@ -123,6 +123,11 @@ class Proof:
         return {"valid": (bool(bits.value & 1), bool(bits.value & 2), bool(bits.value & 4)), "stage1_seed": s1.tobytes(),
                 "stage2_seed": s2.tobytes(), "encoded_rows": rows.value}
 
+    def timing(self):
+        ms = (C.c_double * 4)()
+        _check(lib().lgrp_proof_timing(self._h, ms))
+        return {"stage1_ms": ms[0], "stage2_ms": ms[1], "stage3_ms": ms[2], "container_ms": ms[3]}
+
     def close(self):
         if self._h:
             lib().lgrp_proof_free(self._h)

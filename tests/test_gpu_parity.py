@@ -1,4 +1,5 @@
 """GPU parity: CUDA path (through the C ABI) vs the CPU oracle, bit-exact.  Needs a B200."""
+import ctypes as C
 import json
 import os
 import random
@@ -575,3 +576,27 @@ def test_lane_split_chain_kernel_opt_in(tmp_path):
     env = dict(os.environ, LGR_CHAIN_SPLIT="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("k,R1,R2", [(256, 4100, 37), (64, 5, 6), (4096, 3, 4)])
+def test_encode_absorb_equals_row_by_row_updates(lgr, oracle, executor_factory, k, R1, R2):
+    """lgr_encode_absorb (the commit pipeline without init / final) interleaves with plain updates: two absorbs and a
+    single-row update in between give the leaf digests of the whole row sequence"""
+    ex = executor_factory(k)
+    n = 4 * k
+    rows = oracle.synth(17, 0, R1 + 1 + R2, k)
+    src = ex.make_device_buffer(rows.shape[0] * k * 32)
+    ex.write_buffer(src, rows)
+    sha = ex.make_device_buffer(lgr.lib().lgr_sha_ctx_bytes(C.c_uint32(n)))
+    lib = lgr.lib()
+    assert lib.lgr_sha_init(ex._ctx, sha.ptr(), C.c_uint32(n)) == 0
+    ex.encode_absorb(sha, src, R1)
+    one = ex.make_codeword_buffer()
+    ex.write_buffer_clear(one, rows[R1])
+    ex.encode_ntt_device(ex.bind_ntt(one))
+    assert lib.lgr_sha_update(ex._ctx, sha.ptr(), C.c_uint32(n), one.ptr()) == 0
+    ex.encode_absorb(sha, src.slice((R1 + 1) * k * 32), R2)
+    dig = ex.make_device_buffer(n * 32)
+    assert lib.lgr_sha_final(ex._ctx, sha.ptr(), C.c_uint32(n), dig.ptr()) == 0
+    want_d, _, _ = oracle.encode_commit(rows, k)
+    assert np.array_equal(ex.copy_to_host(dig, np.uint8).reshape(n, 32), want_d)

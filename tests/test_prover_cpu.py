@@ -202,3 +202,27 @@ def test_oracle_prover_matches_committed_fixture(oracle):
             "n": 4 * fx["k"], "sample_size": 192}
     env = ref.build_envelope(meta, w["root"], w["siblings"], w["sample"], w["code"], w["linear"], w["quad"], w["samplings"])
     assert len(env) == fx["envelope_len"] and hashlib.sha256(env).hexdigest() == fx["envelope_sha256"]
+
+
+def test_gzip_of_a_large_proof_is_one_valid_member(pr):
+    """proofs above 8 MiB are deflated in parallel chunks stitched into ONE gzip member (proof_wire.hpp); Python's gzip
+    (single-member reader path included) must give back the envelope, and the parser must accept it"""
+    import zlib
+    rng = random.Random(9)
+    k, S = 256, 192
+    n = 4 * k
+    opened = sorted(rng.sample(range(n), S))
+    pos = ref.sibling_positions(opened, 2 * n - 1)
+    sib = [rng.randbytes(32) for _ in pos]
+    u = lambda cnt: np.frombuffer(rng.randbytes(4 * cnt), np.uint32)
+    meta = {"prover_version": "1.5.0", "program_hash": bytes(32), "generated_at": 7, "k": k, "n": n, "sample_size": S}
+    want = ref.build_envelope(meta, bytes(32), sib, opened, u(n * 8), u(n * 8), u(n * 8), u(3000 * S * 8))
+    assert len(want) > (16 << 20)
+    p = pr.parse_proof(want)
+    gz = p.gzip
+    d = zlib.decompressobj(31)                                # gzip wrapper, one member
+    assert d.decompress(gz) == want and d.eof and d.unused_data == b""
+    assert gzip.decompress(gz) == want
+    p2 = pr.parse_proof(gz)
+    assert p2.envelope == want
+    p.close(); p2.close()
