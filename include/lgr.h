@@ -158,6 +158,9 @@ int lgr_combine_quad(lgr_ctx *ctx, const void *tile_x, const void *tile_y, const
 /* same with the three operand rows of triple t at x/y/z + t*row_stride_elems: the layout of a tile encoded in
  * emission order (x_0, y_0, z_0, x_1, ...: x = tile, y = tile + n, z = tile + 2n, stride 3n) */
 int lgr_combine_quad_rows(lgr_ctx *ctx, const void *x, const void *y, const void *z, uint64_t row_stride_elems, uint32_t nrows, const uint32_t *host_r, void *acc);
+/* same for triples scattered over a tile encoded in emission order: triple t occupies codeword rows host_x_rows[t],
+ * +1 and +2 of `tile` (row stride n); one launch for any interleaving of linear rows and triples */
+int lgr_combine_quad_indexed(lgr_ctx *ctx, const void *tile, const uint32_t *host_x_rows, uint32_t ntriples, const uint32_t *host_r, void *acc);
 /* check_linear over two resident tiles: acc[j] += sum_t a[t][j]*b[t][j] (nonbatch_context.hpp:765-769) */
 int lgr_combine_linear(lgr_ctx *ctx, const void *tile_a, const void *tile_b, uint32_t nrows, void *acc);
 

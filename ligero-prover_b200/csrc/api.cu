@@ -770,6 +770,22 @@ int lgr_combine_quad_rows(lgr_ctx *c, const void *x, const void *y, const void *
     c->launches += 4;
     return LGR_OK;
 }
+int lgr_combine_quad_indexed(lgr_ctx *c, const void *tile, const uint32_t *host_x_rows, uint32_t ntriples, const uint32_t *host_r, void *acc) {
+    REQUIRE(c && tile && host_x_rows && host_r && acc, "null argument");
+    if (!ntriples) return LGR_OK;
+    const size_t part = combine_scratch_elems((int)ntriples, (int)c->n);
+    const size_t idx_elems = ((size_t)ntriples * 4 + 31) / 32;                  // u32 indices, in 32-byte elements
+    int rc = ensure_scratch(c, part + 3 * (size_t)ntriples + idx_elems);
+    if (rc) return rc;
+    if ((rc = upload_scalars(c, host_r, ntriples, part + 2 * (size_t)ntriples))) return rc;
+    fr_mem *idx = c->scratch + part + 3 * (size_t)ntriples;
+    if ((rc = lgr_write(c, idx, 0, host_x_rows, (size_t)ntriples * 4))) return rc;
+    const fr_mem *x = (const fr_mem *)tile;
+    CU(launch_combine_quad(x, x + c->n, x + 2 * (size_t)c->n, (long long)c->n, (int)ntriples, (int)c->n, c->scratch + part + 2 * (size_t)ntriples,
+                           (fr_mem *)acc, c->scratch, part + 2 * (size_t)ntriples, c->stream, (const uint32_t *)idx));
+    c->launches += 4;
+    return LGR_OK;
+}
 int lgr_combine_linear(lgr_ctx *c, const void *a, const void *b, uint32_t nrows, void *acc) {
     REQUIRE(c && a && b && acc, "null argument");
     if (!nrows) return LGR_OK;

@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(128) combine_partial_kernel(const fr_mem *__re
 // one Montgomery multiplication + two wide products per triple element, 96 bytes read
 __global__ void __launch_bounds__(128) combine_quad_kernel(const fr_mem *__restrict__ x, const fr_mem *__restrict__ y, const fr_mem *__restrict__ z,
                                                            long long row_stride, int T, int n, const fr_mem *__restrict__ r_mont,
-                                                           const fr_mem *__restrict__ r_scaled, fr_mem *__restrict__ partial) {
+                                                           const fr_mem *__restrict__ r_scaled, fr_mem *__restrict__ partial,
+                                                           const uint32_t *__restrict__ row_idx) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = blockIdx.y;
     if (j >= n) return;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(128) combine_quad_kernel(const fr_mem *__restr
     fr_wide wp, wz;
     wide_zero(wp); wide_zero(wz);
     for (int t = t0; t < t1; t++) {
-        const long long off = (long long)t * row_stride + j;
+        const long long off = (long long)(row_idx ? row_idx[t] : (uint32_t)t) * row_stride + j;     // row_idx: triples scattered over a tile
         fr_t rx = fr_reduce_p(fr_mont_mul(fr_ldg(x + off), fr_ldc(r_mont + t)));     // r_t * X, canonical
         wide_mad(wp, rx, fr_ldg(y + off));
         wide_mad(wz, fr_ldg(z + off), fr_ldc(r_scaled + t));
@@ -262,7 +263,7 @@ cudaError_t launch_combine_linear(const fr_mem *a, const fr_mem *b, long long ro
 }
 
 cudaError_t launch_combine_quad(const fr_mem *x, const fr_mem *y, const fr_mem *z, long long row_stride, int T, int n, const fr_mem *r_raw,
-                                fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st) {
+                                fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st, const uint32_t *row_idx) {
     if (T <= 0 || n <= 0) return cudaSuccess;
     const int chunks = (T + kCombineChunk - 1) / kCombineChunk;
     if (scratch_elems < (size_t)chunks * n + 2 * (size_t)T) return cudaErrorInvalidValue;
@@ -270,7 +271,7 @@ cudaError_t launch_combine_quad(const fr_mem *x, const fr_mem *y, const fr_mem *
     fr_mem *r_scaled = scratch + (size_t)chunks * n, *r_mont = r_scaled + T;
     combine_scale_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_raw, T, r_scaled);
     combine_mont_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_raw, T, r_mont);
-    combine_quad_kernel<<<grid, 128, 0, st>>>(x, y, z, row_stride, T, n, r_mont, r_scaled, scratch);
+    combine_quad_kernel<<<grid, 128, 0, st>>>(x, y, z, row_stride, T, n, r_mont, r_scaled, scratch, row_idx);
     launch_fold(scratch, chunks, n, acc, st);
     return cudaGetLastError();
 }

@@ -77,9 +77,10 @@ cudaError_t launch_combine_code(const fr_mem *tile, long long row_stride, int T,
 // acc[j] += sum_t a[t][j] * b[t][j]   (check_linear over two resident tiles)
 cudaError_t launch_combine_linear(const fr_mem *a, const fr_mem *b, long long row_stride, int T, int n,
                                   fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st);
-// acc[j] += sum_t r[t] * (x[t][j]*y[t][j] - z[t][j])   (check_quadratic over resident tiles)
+// acc[j] += sum_t r[t] * (x[t][j]*y[t][j] - z[t][j])   (check_quadratic over resident tiles); row_idx (device, optional):
+// triple t sits at row row_idx[t] of x / y / z instead of row t
 cudaError_t launch_combine_quad(const fr_mem *x, const fr_mem *y, const fr_mem *z, long long row_stride, int T, int n, const fr_mem *r_raw,
-                                fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st);
+                                fr_mem *acc, fr_mem *scratch, size_t scratch_elems, cudaStream_t st, const uint32_t *row_idx = nullptr);
 size_t combine_scratch_elems(int T, int n);
 // out[t][s] = tile[t][idx[s]]: the sampled columns of T resident codewords (stage 3)
 cudaError_t launch_gather_rows(const fr_mem *tile, long long row_stride, int T, const uint32_t *idx, int count, fr_mem *out, cudaStream_t st);   // partial sums only; callers add T (code) or 2T (quad) for scalars

@@ -114,16 +114,12 @@ public:
             chk(lgr_encode_rows(ctx_, at(d_coef_, r0 * k_), k_, T, tile2_));
             chk(lgr_combine_code(ctx_, tile_, T, &r_code[r0 * 8], code));
             chk(lgr_combine_linear(ctx_, tile_, tile2_, T, linear));
-            // runs of consecutive triples inside the tile: rows x, y, z are 3 consecutive codewords
-            size_t r = r0;
-            while (r < r0 + T) {
-                if (!row_is_quad_x_[r]) { r++; continue; }
-                size_t q = 0, rr = r;
-                while (rr < r0 + T && row_is_quad_x_[rr]) { q++; rr += 3; }
-                chk(lgr_combine_quad_rows(ctx_, at(tile_, (r - r0) * n_), at(tile_, (r - r0 + 1) * n_), at(tile_, (r - r0 + 2) * n_), 3ull * n_, (uint32_t)q,
-                                          &r_quad[quad_seen * 8], quad));
-                quad_seen += q;
-                r = rr;
+            // the triples of the tile, wherever they sit between linear rows: x, y, z are 3 consecutive codewords
+            std::vector<uint32_t> xrows;
+            for (size_t r = r0; r < r0 + T; r++) if (row_is_quad_x_[r]) xrows.push_back((uint32_t)(r - r0));
+            if (!xrows.empty()) {
+                chk(lgr_combine_quad_indexed(ctx_, tile_, xrows.data(), (uint32_t)xrows.size(), &r_quad[quad_seen * 8], quad));
+                quad_seen += xrows.size();
             }
         });
         encode_mask(0); chk(lgr_elt_add_assign(ctx_, mask_cw_, code, n_));     // nonbatch_context.hpp:732-754

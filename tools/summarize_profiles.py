@@ -50,7 +50,7 @@ for f in sorted(os.listdir("gpurun_out")):
         if w in h:
             lines.append("%s,\"%s\",%s,%s,%s" % (f, kn, w, r[h.index(w)].replace(",", ""), rr[1][h.index(w)]))
 open("profiles/%s_ncu_full_summary.csv" % tag, "w").write("\n".join(lines) + "\n")
-for j in ("ntt_bench.json", "combine_bench.json"):
+for j in ("ntt_bench.json", "combine_bench.json", "chain_ubench.json", "sha_bench.json", "encode_bench.json"):
     if os.path.exists(os.path.join("gpurun_out", j)):
         shutil.copy(os.path.join("gpurun_out", j), "profiles/%s_%s" % (tag, j))
 print("profiles/ updated for", tag)
