@@ -12,7 +12,7 @@ $NCU --set full --import-source on -k regex:encode_rows_kernel -s 6 -c 2 -f -o g
     python bench.py --steps 1 --warmup 3 --log-rows 15 --no-e2e --no-cpu-baseline > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:sha_chain_kernel -s 6 -c 2 -f -o gpurun_out/prof_sha_chain \
     python bench.py --steps 1 --warmup 3 --log-rows 15 --no-e2e --no-cpu-baseline > /dev/null 2>&1
-$NCU --set full --import-source on --kernel-name-base demangled -k "regex:ntt_tile_kernel<10>" -s 12 -c 2 -f -o gpurun_out/prof_ntt \
+$NCU --set full --import-source on --kernel-name-base demangled -k "regex:ntt_tile_kernel<.int.10>" -s 12 -c 2 -f -o gpurun_out/prof_ntt \
     python tools/ntt_bench.py > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:combine_partial -s 2 -c 1 -f -o gpurun_out/prof_combine \
     python tools/combine_bench.py > /dev/null 2>&1
