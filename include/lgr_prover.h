@@ -63,6 +63,20 @@ int lgrp_proof_info(const lgrp_proof *p, uint32_t *valid_bits, uint8_t stage1_se
  * the container (serialise + gzip); every stage ends with a blocking read, so device time is included */
 int lgrp_proof_timing(const lgrp_proof *p, double ms[4]);
 
+/* ---- packing committed witnesses into rows (host only) --------------------------------------------
+ * witness_manager::commit_release_witness / process_reset_*_row / finalize
+ * (include/zkp/backend/witness_manager.hpp:117-186,188-269,497-503): rows are emitted lazily, when a witness arrives
+ * and the open row already holds l of them; finalize emits the partial linear row, then the partial triple.  The
+ * result is exactly the (kinds, values, coefs) triple of lgrp_statement. */
+typedef struct lgrp_packer lgrp_packer;
+int lgrp_packer_create(uint32_t l, lgrp_packer **out);
+void lgrp_packer_free(lgrp_packer *p);
+int lgrp_packer_push_linear(lgrp_packer *p, const uint32_t value[8], const uint32_t coef[8]);          /* commit_status::linear_ready */
+int lgrp_packer_push_quadratic(lgrp_packer *p, const uint32_t xyz[24], const uint32_t coef_xyz[24]);   /* commit_status::quadratic_ready */
+int lgrp_packer_finalize(lgrp_packer *p);
+/* views into the packer (valid until the next push / free): n_rows encoded rows of l elements each */
+int lgrp_packer_rows(const lgrp_packer *p, uint64_t *n_events, const uint8_t **kinds, uint64_t *n_rows, const uint32_t **values, const uint32_t **coefs);
+
 /* ---- the three-stage prover over a witness matrix (needs a B200: runs the hot path through lgr.h) -- */
 typedef struct {
     uint32_t l, k;                 /* must match the context (n = 4k) */

@@ -5,6 +5,7 @@
 
 #include "../../include/lgr_prover.h"
 #include "matrix_prover.hpp"
+#include "row_packer.hpp"
 
 using namespace ligero::cuda::host;
 
@@ -134,6 +135,47 @@ int lgrp_proof_timing(const lgrp_proof *p, double ms[4]) {
     LGRP_TRY
     if (!p || !ms) throw std::invalid_argument("null argument");
     for (int i = 0; i < 4; i++) ms[i] = p->r.ms[i];
+    LGRP_END
+}
+
+struct lgrp_packer {
+    row_packer p;
+    explicit lgrp_packer(uint32_t l) : p(l) {}
+};
+
+int lgrp_packer_create(uint32_t l, lgrp_packer **out) {
+    LGRP_TRY
+    if (!out || !l) throw std::invalid_argument("row size must be positive");
+    *out = new lgrp_packer(l);
+    LGRP_END
+}
+void lgrp_packer_free(lgrp_packer *p) { delete p; }
+int lgrp_packer_push_linear(lgrp_packer *p, const uint32_t value[8], const uint32_t coef[8]) {
+    LGRP_TRY
+    if (!p || !value || !coef) throw std::invalid_argument("null argument");
+    p->p.push_linear(value, coef);
+    LGRP_END
+}
+int lgrp_packer_push_quadratic(lgrp_packer *p, const uint32_t xyz[24], const uint32_t coef_xyz[24]) {
+    LGRP_TRY
+    if (!p || !xyz || !coef_xyz) throw std::invalid_argument("null argument");
+    p->p.push_quadratic(xyz, xyz + 8, xyz + 16, coef_xyz, coef_xyz + 8, coef_xyz + 16);
+    LGRP_END
+}
+int lgrp_packer_finalize(lgrp_packer *p) {
+    LGRP_TRY
+    if (!p) throw std::invalid_argument("null argument");
+    p->p.finalize();
+    LGRP_END
+}
+int lgrp_packer_rows(const lgrp_packer *p, uint64_t *n_events, const uint8_t **kinds, uint64_t *n_rows, const uint32_t **values, const uint32_t **coefs) {
+    LGRP_TRY
+    if (!p) throw std::invalid_argument("null argument");
+    if (n_events) *n_events = p->p.kinds().size();
+    if (kinds) *kinds = p->p.kinds().data();
+    if (n_rows) *n_rows = p->p.rows();
+    if (values) *values = p->p.values().data();
+    if (coefs) *coefs = p->p.coefs().data();
     LGRP_END
 }
 

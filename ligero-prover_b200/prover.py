@@ -24,6 +24,7 @@ def lib():
         _lib = C.CDLL(path)
         _lib.lgrp_last_error.restype = C.c_char_p
         _lib.lgrp_proof_free.restype = None
+        _lib.lgrp_packer_free.restype = None
     return _lib
 
 
@@ -91,6 +92,48 @@ def recommit(leaves, leaf_idx, total_count, siblings):
     out = np.zeros(32, np.uint8)
     _check(lib().lgrp_recommit(_p(lv), _p(idx), C.c_uint64(idx.size), C.c_uint64(total_count), _p(sb), C.c_uint64(len(siblings)), _p(out)))
     return out.tobytes()
+
+
+class RowPacker:
+    """lgrp_packer_*: witness_manager's row packing (witness_manager.hpp:117-269,497-503)"""
+
+    def __init__(self, l):
+        self._h = C.c_void_p()
+        self.l = l
+        _check(lib().lgrp_packer_create(C.c_uint32(l), C.byref(self._h)))
+
+    def push_linear(self, value, coef):
+        v = np.ascontiguousarray(value, np.uint32).reshape(8); c = np.ascontiguousarray(coef, np.uint32).reshape(8)
+        _check(lib().lgrp_packer_push_linear(self._h, _p(v), _p(c)))
+
+    def push_quadratic(self, xyz, coef_xyz):
+        v = np.ascontiguousarray(xyz, np.uint32).reshape(24); c = np.ascontiguousarray(coef_xyz, np.uint32).reshape(24)
+        _check(lib().lgrp_packer_push_quadratic(self._h, _p(v), _p(c)))
+
+    def finalize(self):
+        _check(lib().lgrp_packer_finalize(self._h))
+
+    def rows(self):
+        """(kinds, values[rows, l, 8], coefs[rows, l, 8]) as numpy copies"""
+        ne, nr = C.c_uint64(), C.c_uint64()
+        kp, vp, cp = C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+        _check(lib().lgrp_packer_rows(self._h, C.byref(ne), C.byref(kp), C.byref(nr), C.byref(vp), C.byref(cp)))
+        cnt = nr.value * self.l * 8
+        kinds = np.ctypeslib.as_array(kp, (ne.value,)).copy() if ne.value else np.zeros(0, np.uint8)
+        vals = np.ctypeslib.as_array(vp, (cnt,)).copy().reshape(-1, self.l, 8) if cnt else np.zeros((0, self.l, 8), np.uint32)
+        coefs = np.ctypeslib.as_array(cp, (cnt,)).copy().reshape(-1, self.l, 8) if cnt else np.zeros((0, self.l, 8), np.uint32)
+        return kinds, vals, coefs
+
+    def close(self):
+        if self._h:
+            lib().lgrp_packer_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Statement(C.Structure):

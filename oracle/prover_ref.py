@@ -361,3 +361,41 @@ def verify_openings(proof_env, l, k, kinds, coefs, instance_hash):
     acc_c = lgo.elt_add_assign(acc_c, samp[rows]); acc_l = lgo.elt_add_assign(acc_l, samp[rows + 1]); acc_q = lgo.elt_add_assign(acc_q, samp[rows + 2])
     assert np.array_equal(acc_c, code[sample]) and np.array_equal(acc_l, linear[sample]) and np.array_equal(acc_q, quad[sample]), "test vectors disagree with the openings"
     return True
+
+
+# ---------------------------------------------------------------- row packing (witness_manager.hpp:117-269,497-503)
+def pack_rows(l, witnesses):
+    """witnesses: sequence of ("L", value, coef) / ("Q", (x, y, z), (cx, cy, cz)) in release order (python ints).
+    Returns (kinds, values, coefs) with rows as lists of l ints -- lazy emission: a row leaves when a witness arrives
+    and the open row is full; finalize emits the partial linear row, then the partial triple."""
+    kinds, values, coefs = [], [], []
+    lin_v, lin_c = [], []
+    qv, qc = ([], [], []), ([], [], [])
+
+    def pad(r):
+        return r + [0] * (l - len(r))
+
+    def flush_lin():
+        if lin_v:
+            kinds.append(0); values.append(pad(list(lin_v))); coefs.append(pad(list(lin_c)))
+            lin_v.clear(); lin_c.clear()
+
+    def flush_quad():
+        if qv[0]:
+            kinds.append(1)
+            for i in range(3):
+                values.append(pad(list(qv[i]))); coefs.append(pad(list(qc[i])))
+                qv[i].clear(); qc[i].clear()
+
+    for w in witnesses:
+        if w[0] == "L":
+            if len(lin_v) >= l:
+                flush_lin()
+            lin_v.append(w[1]); lin_c.append(w[2])
+        else:
+            if len(qv[0]) >= l:
+                flush_quad()
+            for i in range(3):
+                qv[i].append(w[1][i]); qc[i].append(w[2][i])
+    flush_lin(); flush_quad()
+    return kinds, values, coefs

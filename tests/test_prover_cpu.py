@@ -226,3 +226,39 @@ def test_gzip_of_a_large_proof_is_one_valid_member(pr):
     p2 = pr.parse_proof(gz)
     assert p2.envelope == want
     p.close(); p2.close()
+
+
+@pytest.mark.parametrize("l,nw,seed", [(4, 0, 1), (4, 3, 2), (4, 50, 3), (7, 200, 4), (40, 500, 5)])
+def test_row_packer_matches_restatement(pr, oracle, l, nw, seed):
+    """lazy row emission of witness_manager (rows leave when the (l+1)-th witness arrives; finalize: linear then triple)"""
+    rng = random.Random(seed)
+    ws = []
+    for _ in range(nw):
+        if rng.random() < 0.6:
+            ws.append(("L", rng.randrange(ref.P), rng.randrange(ref.P)))
+        else:
+            x, y = rng.randrange(ref.P), rng.randrange(ref.P)
+            ws.append(("Q", (x, y, x * y % ref.P), tuple(rng.randrange(ref.P) for _ in range(3))))
+    want_k, want_v, want_c = ref.pack_rows(l, ws)
+    pk = pr.RowPacker(l)
+    for w in ws:
+        if w[0] == "L":
+            pk.push_linear(oracle.to_limbs([w[1]])[0], oracle.to_limbs([w[2]])[0])
+        else:
+            pk.push_quadratic(oracle.to_limbs(w[1]), oracle.to_limbs(w[2]))
+    pk.finalize()
+    kinds, vals, coefs = pk.rows()
+    assert list(kinds) == want_k
+    assert vals.shape[0] == len(want_v) == len(want_k) + 2 * sum(want_k)
+    for r in range(len(want_v)):
+        assert oracle.from_limbs(vals[r]) == want_v[r] and oracle.from_limbs(coefs[r]) == want_c[r]
+    # exactly-full rows are NOT emitted before finalize (lazy flush): l linear witnesses -> one row, at finalize
+    pk2 = pr.RowPacker(l)
+    for i in range(l):
+        pk2.push_linear(oracle.to_limbs([i + 1])[0], oracle.to_limbs([0])[0])
+    assert pk2.rows()[0].size == 0
+    pk2.push_linear(oracle.to_limbs([99])[0], oracle.to_limbs([0])[0])
+    assert list(pk2.rows()[0]) == [0]
+    pk2.finalize()
+    assert list(pk2.rows()[0]) == [0, 0]
+    pk.close(); pk2.close()

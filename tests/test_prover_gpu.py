@@ -147,3 +147,41 @@ def test_prove_matches_committed_fixture(lgr, pr, executor_factory):
     env = proof.envelope
     assert len(env) == fx["envelope_len"] and hashlib.sha256(env).hexdigest() == fx["envelope_sha256"]
     proof.close()
+
+
+def test_witnesses_to_proof_through_the_packer(lgr, oracle, pr, executor_factory):
+    """released witnesses -> row_packer (witness_manager's packing) -> three-stage prover, against the CPU restatement of
+    both steps: the seam where the interpreter's backend would plug in"""
+    k, l = 64, 40
+    rng = random.Random(77)
+    ws, acc = [], 0
+    for _ in range(230):
+        if rng.random() < 0.55:
+            v, c = rng.randrange(1 << 64), rng.randrange(P)
+            ws.append(("L", v, c)); acc += v * c
+        else:
+            x, y = rng.randrange(1 << 64), rng.randrange(1 << 64)
+            cs = tuple(rng.randrange(P) for _ in range(3))
+            ws.append(("Q", (x, y, x * y % P), cs)); acc += x * cs[0] + y * cs[1] + (x * y % P) * cs[2]
+    const_sum = (-acc) % P
+    pk = pr.RowPacker(l)
+    for w in ws:
+        if w[0] == "L":
+            pk.push_linear(oracle.to_limbs([w[1]])[0], oracle.to_limbs([w[2]])[0])
+        else:
+            pk.push_quadratic(oracle.to_limbs(w[1]), oracle.to_limbs(w[2]))
+    pk.finalize()
+    kinds, vals, coefs = pk.rows()
+    wk, wv, wc = ref.pack_rows(l, ws)
+    assert list(kinds) == wk and len(set(wk)) == 2
+    ref_vals = np.stack([oracle.to_limbs(r) for r in wv]); ref_coefs = np.stack([oracle.to_limbs(r) for r in wc])
+    assert np.array_equal(vals, ref_vals) and np.array_equal(coefs, ref_coefs)
+    ex = executor_factory(k, l)
+    seed = hashlib.sha256(b"packer").digest()
+    proof = pr.prove(ex, kinds, vals, coefs, const_sum, seed, bytes(32), bytes(32), generated_at=1)
+    want = ref.prove(l, k, wk, ref_vals, ref_coefs, const_sum, seed, bytes(32))
+    assert proof.info()["valid"] == (True, True, True) == want["valid"]
+    env = ref.parse_envelope(proof.envelope)
+    assert env.ligero_proof.merkle_tree.root.value == want["root"]
+    assert np.array_equal(np.array(env.ligero_proof.sampled_data.values, np.uint32).reshape(want["samplings"].shape), want["samplings"])
+    proof.close(); pk.close()
