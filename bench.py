@@ -351,7 +351,10 @@ def main():
             per = prof["sha_ms"] / prof["sha_launches"]
             rows_per_launch = R * args.steps / prof["sha_launches"]
             by = rows_per_launch * n * 32                                        # every codeword element read once
-            kern["sha_chain_kernel" if n <= 4736 else "sha_update_kernel"] = {"ms_per_launch": per, "launches": prof["sha_launches"], "algorithmic_bytes_per_launch": by,
+            split = os.environ.get("LGR_CHAIN_SPLIT")
+            lane_split = (n // 16 <= 64) if split is None else (split != "0")       # launch_sha_update's choice (csrc/sha_kernels.cu)
+            sha_name = "sha_update_kernel" if n > 4736 else ("sha_chain16_kernel" if (lane_split and n % 16 == 0 and n // 16 <= 148) else "sha_chain_kernel")
+            kern[sha_name] = {"ms_per_launch": per, "launches": prof["sha_launches"], "algorithmic_bytes_per_launch": by,
                                          "achieved_gbs": by / (per * 1e-3) / 1e9, "frac_hbm": by / (per * 1e-3) / 1e9 / hbm,
                                          "share_of_step": prof["sha_ms"] / (ms_step * args.steps)}
         dominant = max(kern, key=lambda kk: kern[kk]["share_of_step"]) if kern else None
@@ -367,13 +370,19 @@ def main():
         # the dominant kernel against the bound that actually holds for it: one warp per 32 columns, ALU-issue-bound
         # (12 SHF/LOP3/IADD3 per round at one warp instruction per 2 cycles, 64 rounds: DESIGN.md section 4)
         chain_roofline = None
-        if "sha_chain_kernel" in kern and clocks.get("sm_mhz"):
-            d = kern["sha_chain_kernel"]
+        chain_name = next((kk for kk in kern if kk.startswith("sha_chain")), None)
+        if chain_name and clocks.get("sm_mhz"):
+            d = kern[chain_name]
             blocks_per_launch = (R * args.steps / d["launches"]) / 2.0
             cyc = d["ms_per_launch"] * 1e-3 * clocks["sm_mhz"] * 1e6 / blocks_per_launch
-            chain_roofline = {"kernel": "sha_chain_kernel", "bound": "alu_issue_of_one_warp", "unit": "cycles per 64-byte block per column",
-                              "floor": 1536.0, "achieved": cyc, "frac": 1536.0 / cyc,
-                              "note": "a column is one SHA-256 chain: n/32 warps of work whatever the GPU; floor = 64 rounds x 12 ALU instructions x 2 cycles"}
+            if chain_name == "sha_chain16_kernel":
+                floor, why = 1216.0, ("lane-split rounds: the e -> shuffle -> a -> shuffle -> e loop spans 4 rounds and holds two 26-cycle SHFL hops "
+                                      "plus two IMAD+IADD3 steps: 19 cycles per round (ALU issue alone would allow 16)")
+            else:
+                floor, why = 1536.0, "64 rounds x 12 ALU instructions x 2 cycles per warp instruction"
+            chain_roofline = {"kernel": chain_name, "bound": "single-warp latency / ALU issue", "unit": "cycles per 64-byte block per column",
+                              "floor": floor, "achieved": cyc, "frac": floor / cyc,
+                              "note": "a column is one SHA-256 chain: n/32 (n/16) warps of work whatever the GPU; floor = " + why}
         ub = {"imad_wide_per_s": ex.ubench(0), "montmul_per_s": ex.ubench(1), "sha256_compress_per_s": ex.ubench(2)}
         import math
         mm_per_elem = (math.log2(k) - 1) / 2 + 3 + 3 * (math.log2(k) - 1) / 2      # iNTT_k + 3 computed cosets (the 4th is a copy)

@@ -560,10 +560,12 @@ cudaError_t launch_sha_init(uint32_t *ctx, int n, cudaStream_t st) {
 }
 cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long long row_stride, int T, cudaStream_t st) {
     if (n <= 0 || T <= 0) return cudaSuccess;
-    // experimental, opt-in: the lane-split chain (16 columns per warp).  In isolation its rounds run in 1277 cycles per
-    // block against 1641 for the 32-column rounds (lgr_ubench_chain 19 vs 11); inside the kernel it measured 1518-1575
-    // against 1573, for twice the SMs, so the 32-column kernel below stays the default.
-    static const bool lane_split = getenv("LGR_CHAIN_SPLIT") != nullptr;
+    // Lane-split chain (16 columns per warp, twice the SMs of the 32-column kernel below).  In isolation its rounds run
+    // in 1277 cycles per block against 1641 (lgr_ubench_chain 19 vs 11); inside the kernel it measures 1470-1575 against
+    // 1573-1586 depending on how ptxas lays the loop out, so it is used only where the extra SMs are free anyway: up to 64
+    // CTAs (n <= 1024), where the encoder of the next tile still hides under the hash.  LGR_CHAIN_SPLIT=0/1 forces it.
+    static const int split_env = getenv("LGR_CHAIN_SPLIT") ? atoi(getenv("LGR_CHAIN_SPLIT")) : -1;
+    const bool lane_split = split_env >= 0 ? split_env != 0 : (n / 16 <= 64);
     if (lane_split && n % 16 == 0 && n / 16 <= 148 && T >= 4) {
         static const int group16 = getenv("LGR_CHAIN_GROUP") ? atoi(getenv("LGR_CHAIN_GROUP")) : 8;
         static const int helper_warps = getenv("LGR_CHAIN_HELPERS") ? atoi(getenv("LGR_CHAIN_HELPERS")) : 3;

@@ -549,9 +549,10 @@ def test_cpp_cuda_executor_drop_in(lgr, oracle, tmp_path):
     assert np.array_equal(code, wc) and np.array_equal(quad, wq)
 
 
-def test_lane_split_chain_kernel_opt_in(tmp_path):
-    """LGR_CHAIN_SPLIT=1 selects sha_chain16_kernel (round split over the two half-warps, csrc/sha_kernels.cu); it is
-    not the default (no faster in the kernel, see the comment at its launch site) but must stay bit-exact"""
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_both_chain_kernels_forced(tmp_path, split):
+    """LGR_CHAIN_SPLIT=1 forces sha_chain16_kernel (round split over the two half-warps, csrc/sha_kernels.cu; the default
+    for n <= 1024), =0 forces the 32-column sha_chain_kernel: both must be bit-exact at every narrow size"""
     import subprocess, sys, textwrap
     code = textwrap.dedent("""
         import os, sys
@@ -560,7 +561,7 @@ def test_lane_split_chain_kernel_opt_in(tmp_path):
         import __graft_entry__ as ge
         from oracle import lgo
         lgr = ge._load_package()
-        for k, R in ((256, 4100), (64, 17), (256, 7)):
+        for k, R in ((256, 4100), (64, 17), (256, 7), (512, 33)):
             n = 4 * k
             ex = lgr.make_executor(max(k - 192, 1), k)
             rows = lgo.synth(3, 0, R, k)
@@ -573,7 +574,7 @@ def test_lane_split_chain_kernel_opt_in(tmp_path):
             ex.close()
         print("ok")
     """) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, LGR_CHAIN_SPLIT="1")
+    env = dict(os.environ, LGR_CHAIN_SPLIT=split)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 

@@ -10,7 +10,7 @@ $NCU --metrics gpu__time_duration.sum -s 40 -c 400 --csv --log-file gpurun_out/l
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 $NCU --set full --import-source on -k regex:encode_rows_kernel -s 6 -c 2 -f -o gpurun_out/prof_encode \
     python bench.py --steps 1 --warmup 3 --log-rows 15 --no-e2e --no-cpu-baseline > /dev/null 2>&1
-$NCU --set full --import-source on -k regex:sha_chain_kernel -s 6 -c 2 -f -o gpurun_out/prof_sha_chain \
+$NCU --set full --import-source on -k regex:sha_chain -s 6 -c 2 -f -o gpurun_out/prof_sha_chain \
     python bench.py --steps 1 --warmup 3 --log-rows 15 --no-e2e --no-cpu-baseline > /dev/null 2>&1
 $NCU --set full --import-source on --kernel-name-base demangled -k "regex:ntt_tile_kernel<.int.10>" -s 12 -c 2 -f -o gpurun_out/prof_ntt \
     python tools/ntt_bench.py > /dev/null 2>&1
