@@ -304,6 +304,47 @@ __global__ void __launch_bounds__(128) ubench_chain_kernel(uint32_t *out, int it
             }
         }
         st[0] = p; st[1] = q; st[2] = r; st[3] = s; st[4] = rm2 ^ rm3;
+    } else if (VARIANT == 21 || VARIANT == 22 || VARIANT == 23) {
+        // the block loop of sha_chain16_kernel verbatim (boundary steps, K+W ring of eight registers, A lanes reading
+        // zeros); 22: without the boundary steps and the first-four-rounds special case; 23: as 22 with 32-word rows (the A
+        // lanes read the upper half of the row the E lanes read: one 128-byte row per LDS)
+        const bool isE = lane < 16;
+        const uint32_t s1 = isE ? 6 : 2, s2 = isE ? 11 : 13, s3 = isE ? 25 : 22;
+        const uint32_t one = cc.one, sgn = isE ? one : 0u - one, mE = isE ? one : 0u, mA = isE ? 0u : one, M = 0u - mA;
+        uint32_t p = st[0], q = st[1], r = st[2], s = st[3], rm2 = st[5], rm1 = st[6];
+        uint32_t cv0 = 0, cv1 = 0, cv2 = 0, cv3 = 0, ca[4] = {0, 0, 0, 0};
+        uint32_t u = ub_lop3<0xF8>(q, r, M), v = ub_lop3<0xC4>(q, r, M);
+        uint32_t kq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        constexpr int RS = (VARIANT == 23) ? 32 : 16;            // row stride in words
+        const uint32_t *kwp = (VARIANT == 23) ? &kw[warp][lane] : (isE ? &kw[warp][lane] : &kw[warp][16 + (lane & 15)]);
+        const uint32_t *kwn = kwp;
+#define UB_BOUNDARY(MX) { uint32_t t_; t_ = p; p = cv0 * (MX) + p; cv0 = t_ * (MX) + cv0; t_ = q; q = cv1 * (MX) + q; cv1 = t_ * (MX) + cv1; \
+      t_ = r; r = cv2 * (MX) + r; cv2 = t_ * (MX) + cv2; t_ = s; s = cv3 * (MX) + s; cv3 = t_ * (MX) + cv3; u = ub_lop3<0xF8>(q, r, M); v = ub_lop3<0xC4>(q, r, M); }
+#define UB_ROUND(J, KWX) { uint32_t d_ = rm2; \
+      if (VARIANT == 21 && (J) < 4) { d_ = ub_mad(ca[3 - (J)], one, rm2); ca[3 - (J)] = ub_mad(d_, mE, 0u); } \
+      const uint32_t wr_ = ub_mad(ub_mad(s, sgn, (KWX)), one, d_); \
+      const uint32_t sg_ = ub_lop3<0x96>(__funnelshift_r(p, p, s1), __funnelshift_r(p, p, s2), __funnelshift_r(p, p, s3)); \
+      const uint32_t np_ = sg_ + ub_lop3<0xCA>(p, u, v) + wr_; \
+      const uint32_t r0_ = __shfl_xor_sync(0xffffffffu, np_, 16); \
+      s = r; r = q; q = p; p = np_; u = ub_lop3<0xF8>(q, r, M); v = ub_lop3<0xC4>(q, r, M); rm2 = rm1; rm1 = r0_; }
+#pragma unroll
+        for (int j = 0; j < 8; j++) kq[j] = kwp[j * RS];
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+            if (VARIANT == 21) UB_BOUNDARY(mE)
+            UB_ROUND(0, kq[0]) UB_ROUND(1, kq[1])
+            kq[0] = kwp[8 * RS]; kq[1] = kwp[9 * RS];
+            if (VARIANT == 21) UB_BOUNDARY(mA)
+#pragma unroll
+            for (int j = 2; j < 64; j++) {
+                const uint32_t kw_ = kq[j & 7];
+                kq[j & 7] = (j + 8 < 64) ? kwp[(j + 8) * RS] : kwn[(j + 8 - 64) * RS];
+                UB_ROUND(j, kw_)
+            }
+        }
+#undef UB_ROUND
+#undef UB_BOUNDARY
+        st[0] = p + cv0; st[1] = q + cv1; st[2] = r + cv2; st[3] = s + cv3; st[4] = rm2 ^ ca[0] ^ ca[1] ^ ca[2] ^ ca[3];
     } else {
         for (int it = 0; it < iters; it++) chain_rounds<VARIANT>(st, kw[warp], lane, cc);
     }
@@ -335,7 +376,10 @@ cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps
     else if (variant == 17) ubench_chain_kernel<17><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 18) ubench_chain_kernel<18><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 19) ubench_chain_kernel<19><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
-    else ubench_chain_kernel<20><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 20) ubench_chain_kernel<20><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 21) ubench_chain_kernel<21><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 22) ubench_chain_kernel<22><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else ubench_chain_kernel<23><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     return cudaGetLastError();
 }
 
