@@ -158,7 +158,8 @@ def run_reference(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "ligero encode+commit, R=2^%d rows x k=%d (n=%d), BN254 Fr" % (LOG_ROWS, K, 4 * K), "sample_rows_per_step": rows,
+        "config": {"workload": "ligero encode+commit, R=2^%d rows x k=%d (n=%d) per GPU, BN254 Fr, seed %d" % (LOG_ROWS, K, 4 * K, SEED),
+                   "rows_per_gpu": 1 << LOG_ROWS, "k": K, "n": 4 * K, "sample_rows_per_step": rows,
                    "note": "reference has no CPU path for these kernels and cannot be built here; this is the CPU oracle port"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
