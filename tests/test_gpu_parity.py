@@ -601,3 +601,23 @@ def test_encode_absorb_equals_row_by_row_updates(lgr, oracle, executor_factory, 
     assert lib.lgr_sha_final(ex._ctx, sha.ptr(), C.c_uint32(n), dig.ptr()) == 0
     want_d, _, _ = oracle.encode_commit(rows, k)
     assert np.array_equal(ex.copy_to_host(dig, np.uint8).reshape(n, 32), want_d)
+
+
+@pytest.mark.parametrize("k,R", [(256, 20001), (64, 70000), (2048, 2100), (8192, 700)])
+def test_encode_commit_across_tiles(lgr, oracle, executor_factory, k, R):
+    """several tiles of the commit pipeline (tile = 2^23 codeword elements, double-buffered, encode of tile t+1 overlapping
+    the hash of tile t) with a ragged last tile, device-resident and host-resident rows, against the oracle"""
+    ex = executor_factory(k)
+    n = 4 * k
+    assert R * n > 2 * (1 << 23)
+    rows = oracle.synth(29, 0, R, k)
+    want_d, want_n, _ = oracle.encode_commit(rows, k)
+    src = ex.make_device_buffer(R * k * 32)
+    ex.write_buffer(src, rows)
+    dig = ex.make_device_buffer(n * 32)
+    nodes = ex.make_device_buffer((2 * n - 1) * 32)
+    ex.encode_commit(src, R, dig, nodes)
+    assert np.array_equal(ex.copy_to_host(dig, np.uint8).reshape(n, 32), want_d)
+    assert np.array_equal(ex.copy_to_host(nodes, np.uint8).reshape(2 * n - 1, 32), want_n)
+    _, root = ex.encode_commit_host(np.ascontiguousarray(rows), R)          # pageable host rows, H2D tile by tile
+    assert root == want_n[0].tobytes()
