@@ -185,3 +185,28 @@ def test_witnesses_to_proof_through_the_packer(lgr, oracle, pr, executor_factory
     assert env.ligero_proof.merkle_tree.root.value == want["root"]
     assert np.array_equal(np.array(env.ligero_proof.sampled_data.values, np.uint32).reshape(want["samplings"].shape), want["samplings"])
     proof.close(); pk.close()
+
+
+@pytest.mark.parametrize("k,l,kinds", [(64, 40, []), (8, 4, [0, 1, 0]), (16, 16, [1])])
+def test_prove_edge_geometries(lgr, oracle, pr, executor_factory, k, l, kinds):
+    """an empty statement (the three mask rows only), n smaller than the sample size (every column opened, no sibling
+    hashes), and l = k (no padding columns)"""
+    n = 4 * k
+    ex = executor_factory(k, l)
+    values, coefs, const_sum = make_statement(oracle, l, kinds, seed=3) if kinds else (np.zeros((0, l, 8), np.uint32), np.zeros((0, l, 8), np.uint32), 0)
+    seed = hashlib.sha256(b"edge%d" % k).digest()
+    proof = pr.prove(ex, kinds, values, coefs, const_sum, seed, bytes(32), bytes(32), generated_at=1)
+    want = ref.prove(l, k, kinds, values, coefs, const_sum, seed, bytes(32))
+    assert proof.info()["valid"] == (True, True, True) == want["valid"]
+    assert proof.info()["encoded_rows"] == values.shape[0] + 3
+    env = ref.parse_envelope(proof.envelope)
+    pf = env.ligero_proof
+    assert pf.merkle_tree.root.value == want["root"]
+    assert list(pf.merkle_tree.leaf_indices) == want["sample"] and len(want["sample"]) == min(192, n)
+    assert [s.value for s in pf.merkle_tree.sibling_hashes] == want["siblings"]
+    if n <= 192:
+        assert want["siblings"] == []
+    assert np.array_equal(np.array(pf.sampled_data.values, np.uint32).reshape(want["samplings"].shape), want["samplings"])
+    meta = {"prover_version": "1.5.0", "program_hash": bytes(32), "generated_at": 1, "k": k, "n": n, "sample_size": 192}
+    assert proof.envelope == ref.build_envelope(meta, want["root"], want["siblings"], want["sample"], want["code"], want["linear"], want["quad"], want["samplings"])
+    proof.close()
