@@ -17,7 +17,8 @@ except Exception as e:
     print("$name failed", e)
 PY
 }
-run split8 LGR_CHAIN_GROUP=8
-run split4 LGR_CHAIN_GROUP=4
-run split1 LGR_CHAIN_GROUP=1
-run nosplit LGR_CHAIN_NO_SPLIT=1
+run split8 LGR_CHAIN_SPLIT=1 LGR_CHAIN_GROUP=8
+run split4 LGR_CHAIN_SPLIT=1 LGR_CHAIN_GROUP=4
+run split1 LGR_CHAIN_SPLIT=1 LGR_CHAIN_GROUP=1
+run cols32 LGR_CHAIN_SPLIT=0
+run cols32_textbook LGR_CHAIN_SPLIT=0 LGR_CHAIN_TEXTBOOK=1
