@@ -50,7 +50,7 @@ int lgr_version(void);
 
 /* ---- lifecycle -------------------------------------------------------------------------------
  * lgr_create = webgpu_init + ntt_init (include/wgpu.hpp:73-82, src/webgpu/engine.cpp:176-211):
- * l = message size, k = padded size (power of two >= 2), n = 4k, p must equal the BN254 scalar
+ * l = message size, k = padded size (power of two >= 8), n = 4k, p must equal the BN254 scalar
  * modulus, root_k / root_2k / root_n as returned by bn254_gmp::generate_omegas
  * (src/bn254.cpp:51-64).  Builds the twiddle tables (engine.cpp:1382-1503) on `device`. */
 int lgr_create(lgr_ctx **out, int device, uint32_t l, uint32_t k, uint32_t n, const uint32_t p[8],

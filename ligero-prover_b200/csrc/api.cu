@@ -356,7 +356,7 @@ int lgr_version(void) { return 100; }
 int lgr_create(lgr_ctx **out, int device, uint32_t l, uint32_t k, uint32_t n, const uint32_t p[8], const uint32_t root_k[8],
                const uint32_t root_2k[8], const uint32_t root_n[8]) {
     REQUIRE(out && p && root_k && root_2k && root_n, "null argument");
-    REQUIRE(k >= 2 && (k & (k - 1)) == 0, "k must be a power of two >= 2");
+    REQUIRE(k >= 8 && (k & (k - 1)) == 0, "k must be a power of two >= 8 (the reference needs k >= 512, engine.cpp:850)");
     REQUIRE(n == 4 * k, "n must equal 4k (src/webgpu_prover.cpp:88-97)");
     REQUIRE(l <= k, "l must not exceed k");
     REQUIRE(memcmp(p, host::kP, 32) == 0, "modulus is not the BN254 scalar field (the kernels are specialised, as the reference's WGSL is)");
