@@ -5,11 +5,11 @@
 // a pass over global memory, 3/4 of the forward input known-zero.
 //
 // Here one row never leaves the SM between input and codeword:
-//   1. DIF inverse transform (natural in -> bit-reversed coefficients; no permutation pass)
+//   1. inverse transform (unscaled), coefficients in shared memory
 //   2. the 4k-point forward transform is split into four k-point coset transforms:
 //        e[4m + r] = sum_i (c_i * w_n^(r*i)) * (w_n^4)^(i*m),   r = 0..3
 //      so the zero padding is never touched; the twist table also carries the 1/k of the inverse
-//   3. each coset runs as a DIT (bit-reversed in -> natural out) and is written interleaved;
+//   3. every transform runs as a DIT (bit-reversed in -> natural out), the cosets are written interleaved;
 //      coset r = 0 is a permutation of the message (w_n^4 is a power of w_k) and is copied, not computed.
 // Per witness element: (log2(k)-1)/2 + 3 + 3*(log2(k)-1)/2 Montgomery multiplications.
 #include "kernels.h"
@@ -52,39 +52,54 @@ __global__ void __launch_bounds__(enc_cfg<LOGK>::THREADS, (enc_cfg<LOGK>::SMEM <
     const bool active = row < R;
     auto sync = [] { __syncthreads(); };
 
-    // 1. inverse transform: the top pass reads the message row straight from global memory
-    //    (coalesced: consecutive threads, consecutive elements); result = coefficients in
-    //    bit-reversed order in C, values in [0,2p).  w_k^-1 twiddles; 1/k is folded into the twist.
-    //    The raw row is also parked in W (unused until the coset transforms) for step 2.
+    // All transforms of a row -- the inverse one and the cosets -- run through ONE decimation-in-time body (bit-reversed
+    // in, natural out), selected by run-time flags: a second, decimation-in-frequency body for the inverse transform
+    // doubled the straight-line code to 220 KB, more than the instruction cache holds (ncu: 20 % of the stall samples
+    // were `no_inst`).
+    //   pass t = 0      : c = k * iNTT_k(row): the first pass gathers row[bitrev(q)] from global memory (32-byte sectors,
+    //                     so the gather costs no extra traffic), twiddles w_k^-1, result to C in natural order, values
+    //                     in [0,4p); the raw row is parked in W for the copied coset; 1/k is folded into the twists
+    //   pass t = 1..    : coset r: the first pass reads C[bitrev(q)] and applies the twist w_n^(r*bitrev(q))/k, the last
+    //                     pass canonicalises and writes e[4m + r] straight to global memory
     const fr_mem *src = rows_in + (active ? row : 0) * in_row_stride;
-    const bool sys = t.sys_mul != 0;
-    ntt_passes_io<LOGK, 0, true>(C, tl, t.inv_k, 1, sync,
-                                 [&](int i) { fr_t x = active ? fr_ldg(src + i) : fr_zero(); if (sys) fr_sts(W + i, x); return x; }, smem_io{C});
-    sync();
     fr_mem *dst = out + (active ? row : 0) * out_row_stride;
-    // 2. coset r = 0 is the message itself: w_n^4 and w_k generate the same group of k-th roots of unity,
-    //    w_n^4 = w_k^c (c = 2^61-1 mod k = k-1 for the reference's roots, src/bn254.cpp:36-43,51-64), so
-    //    e[4m] = U((w_n^4)^m) = U(w_k^(c m)) = row[c m mod k]: a permuted copy, no arithmetic.
-    if (sys) {
-        if (active) {
-#pragma unroll
-            for (int g = 0; g < 8; g++) {
-                const int m = tl + g * TL;
-                const fr_t x = fr_lds(W + (int)(((unsigned)m * (unsigned)t.sys_mul) & (unsigned)(K - 1)));
-                fr_stg(dst + 4 * m, fr_reduce_p(fr_reduce_2p(fr_reduce_2p(x))));   // any 256-bit input -> [0,p), as the transforms would
-            }
-        }
-        sync();
-    }
-    // 3. the other cosets: the first pass applies the twist while loading the coefficients,
-    //    the last pass canonicalises and writes e[4m + r] straight to global memory
+    const bool sys = t.sys_mul != 0;
+    const int ntrans = sys ? 4 : 5;
 #pragma unroll 1
-    for (int r = sys ? 1 : 0; r < 4; r++) {
-        const fr_mem *tw_r = t.twist + r * K;
-        ntt_passes_io<LOGK, 0, false>(W, tl, t.fwd_c, 1, sync,
-                                      [&](int q) { return fr_mont_mul(fr_lds(C + q), fr_ldc(tw_r + q)); },
-                                      [&](int m, const fr_t &x) { if (active) fr_stg(dst + 4 * m + r, fr_canon4(x)); });
+    for (int tr = 0; tr < ntrans; tr++) {
+        const bool inv = tr == 0;
+        const int r = sys ? tr : tr - 1;                                       // coset index of passes tr >= 1
+        const fr_mem *tw = inv ? t.inv_k : t.fwd_c;
+        const fr_mem *tw_r = t.twist + (inv ? 0 : r) * K;
+        ntt_passes_io<LOGK, 0, false>(inv ? C : W, tl, tw, 1, sync,
+            [&](int q) -> fr_t {
+                const int i = (int)bitrev((uint32_t)q, LOGK);
+                if (inv) {
+                    const fr_t x = active ? fr_ldg(src + i) : fr_zero();
+                    if (sys) fr_sts(W + i, x);
+                    return x;
+                }
+                return fr_mont_mul(fr_lds(C + i), fr_ldc(tw_r + q));
+            },
+            [&](int m, const fr_t &x) {
+                if (inv) fr_sts(C + m, x);
+                else if (active) fr_stg(dst + 4 * m + r, fr_canon4(x));
+            });
         sync();
+        // coset r = 0 is the message itself: w_n^4 and w_k generate the same group of k-th roots of unity,
+        // w_n^4 = w_k^c (c = 2^61-1 mod k = k-1 for the reference's roots, src/bn254.cpp:36-43,51-64), so
+        // e[4m] = U((w_n^4)^m) = U(w_k^(c m)) = row[c m mod k]: a permuted copy, no arithmetic.
+        if (inv && sys) {
+            if (active) {
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    const int m = tl + g * TL;
+                    const fr_t x = fr_lds(W + (int)(((unsigned)m * (unsigned)t.sys_mul) & (unsigned)(K - 1)));
+                    fr_stg(dst + 4 * m, fr_reduce_p(fr_reduce_2p(fr_reduce_2p(x))));   // any 256-bit input -> [0,p), as the transforms would
+                }
+            }
+            sync();
+        }
     }
 }
 
