@@ -487,6 +487,16 @@ class Executor:
         r = np.ascontiguousarray(scalars if isinstance(scalars, np.ndarray) else ints_to_array(scalars), dtype=np.uint32)
         _check(lib().lgr_combine_quad(self._ctx, tile_x.ptr(), tile_y.ptr(), tile_z.ptr(), C.c_uint32(nrows), r.ctypes.data_as(C.c_void_p), acc.ptr()))
 
+    def combine_quad_indexed(self, tile, x_rows, scalars, acc):
+        """triples scattered over a tile encoded in emission order: triple t = codeword rows x_rows[t], +1, +2"""
+        r = np.ascontiguousarray(scalars if isinstance(scalars, np.ndarray) else ints_to_array(scalars), dtype=np.uint32)
+        xr = np.ascontiguousarray(x_rows, dtype=np.uint32)
+        _check(lib().lgr_combine_quad_indexed(self._ctx, tile.ptr(), xr.ctypes.data_as(C.c_void_p), C.c_uint32(xr.size), r.ctypes.data_as(C.c_void_p), acc.ptr()))
+
+    def sample_gather_rows(self, tile, nrows, out, row_stride=None):
+        """out[t][s] = tile[t][idx[s]] for nrows resident codewords (sampling_init first)"""
+        _check(lib().lgr_sample_gather_rows(self._ctx, tile.ptr(), C.c_uint64(self._n if row_stride is None else row_stride), C.c_uint32(nrows), out.ptr()))
+
     def combine_linear(self, tile_a, tile_b, nrows, acc):
         _check(lib().lgr_combine_linear(self._ctx, tile_a.ptr(), tile_b.ptr(), C.c_uint32(nrows), acc.ptr()))
 

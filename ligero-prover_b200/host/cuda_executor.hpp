@@ -226,6 +226,14 @@ struct cuda_context {
     void encode_rows(buffer_type rows, size_t row_stride_elems, uint32_t nrows, buffer_type codewords) {
         cuda::check(lgr_encode_rows(ctx_, rows.get(), row_stride_elems, nrows, codewords.get()), "encode_rows");
     }
+    // stage-1 pipeline into a caller-owned column-hash context (no init / final): lgr_encode_absorb
+    void encode_absorb(buffer_type sha_ctx, buffer_type rows, uint64_t nrows) {
+        cuda::check(lgr_encode_absorb(ctx_, sha_ctx.get(), rows.get(), nrows), "encode_absorb");
+    }
+    // stage-3 openings of nrows resident codewords: out[t][s] = tile[t][idx[s]] (sampling_init first)
+    void sample_gather_rows(buffer_type tile, uint32_t nrows, buffer_type out) {
+        cuda::check(lgr_sample_gather_rows(ctx_, tile.get(), size_n_, nrows, out.get()), "sample_gather_rows");
+    }
     void encode_commit(buffer_type rows, uint64_t nrows, buffer_type digests, buffer_type nodes) {
         cuda::check(lgr_encode_commit(ctx_, rows.get(), nrows, digests.get(), nodes.size() ? nodes.get() : nullptr), "encode_commit");
     }

@@ -621,3 +621,32 @@ def test_encode_commit_across_tiles(lgr, oracle, executor_factory, k, R):
     assert np.array_equal(ex.copy_to_host(nodes, np.uint8).reshape(2 * n - 1, 32), want_n)
     _, root = ex.encode_commit_host(np.ascontiguousarray(rows), R)          # pageable host rows, H2D tile by tile
     assert root == want_n[0].tobytes()
+
+
+def test_indexed_quad_combiner_and_row_gather(lgr, oracle, executor_factory):
+    """lgr_combine_quad_indexed (triples scattered between linear rows of a tile) and lgr_sample_gather_rows against the
+    per-row Eltwise sequence of check_quadratic (nonbatch_context.hpp:771-780) and sample_gather"""
+    k, T = 64, 37
+    n = 4 * k
+    ex = executor_factory(k)
+    rng = random.Random(12)
+    rows = oracle.synth(41, 0, T, k)
+    src = ex.make_device_buffer(T * k * 32); ex.write_buffer(src, rows)
+    tile = ex.make_device_buffer(T * n * 32)
+    ex.encode_rows(src, T, tile)
+    cw = ex.read_elements(tile).reshape(T, n, 8)
+    x_rows = [0, 5, 8, 20, 34]                                   # x at these rows, y and z right behind
+    scal = [rng.randrange(P) for _ in x_rows]
+    acc = ex.make_codeword_buffer()
+    start = oracle.synth(42, 0, 1, n)[0]
+    ex.write_buffer(acc, start)
+    ex.combine_quad_indexed(tile, x_rows, scal, acc)
+    want = start
+    for xr, r in zip(x_rows, scal):
+        want = oracle.elt_fma_const(want, oracle.elt_sub(oracle.elt_mul(cw[xr], cw[xr + 1]), cw[xr + 2]), r)
+    assert np.array_equal(ex.read_elements(acc), want)
+    idx = sorted(rng.sample(range(n), 192))
+    ex.sampling_init(idx)
+    out = ex.make_device_buffer(T * 192 * 32)
+    ex.sample_gather_rows(tile, T, out)
+    assert np.array_equal(ex.read_elements(out).reshape(T, 192, 8), cw[:, idx])
