@@ -210,3 +210,47 @@ def test_prove_edge_geometries(lgr, oracle, pr, executor_factory, k, l, kinds):
     meta = {"prover_version": "1.5.0", "program_hash": bytes(32), "generated_at": 1, "k": k, "n": n, "sample_size": 192}
     assert proof.envelope == ref.build_envelope(meta, want["root"], want["siblings"], want["sample"], want["code"], want["linear"], want["quad"], want["samplings"])
     proof.close()
+
+
+def test_cpp_prover_program(lgr, oracle, tmp_path):
+    """tests/cpp/test_prover.cpp: witnesses -> row_packer -> matrix_prover in plain C++ (header-only host layer over the C
+    ABI), compared with the CPU restatement of the packing and of the three stages"""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_prover")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "tests", "cpp"), "-s"])
+    k, l = 256, 100
+    rng = random.Random(2026)
+    ws, acc = [], 0
+    for _ in range(470):
+        if rng.random() < 0.5:
+            v, c = rng.randrange(P), rng.randrange(P)
+            ws.append(("L", v, c)); acc += v * c
+        else:
+            x, y = rng.randrange(P), rng.randrange(P)
+            cs = tuple(rng.randrange(P) for _ in range(3))
+            ws.append(("Q", (x, y, x * y % P), cs)); acc += x * cs[0] + y * cs[1] + (x * y % P) * cs[2]
+    ws.append(("L", 1, (-acc) % P))                                   # closes the linear relation: const_sum = 0
+    rec = np.zeros((len(ws), 49), np.uint32)
+    for i, w in enumerate(ws):
+        if w[0] == "L":
+            rec[i, 1:9] = oracle.to_limbs([w[1]])[0]; rec[i, 25:33] = oracle.to_limbs([w[2]])[0]
+        else:
+            rec[i, 0] = 1
+            rec[i, 1:25] = oracle.to_limbs(w[1]).reshape(-1); rec[i, 25:49] = oracle.to_limbs(w[2]).reshape(-1)
+    fw, fr_, fp = tmp_path / "w.bin", tmp_path / "roots.bin", tmp_path / "proof.gz"
+    rec.tofile(fw)
+    lgr.ints_to_array(list(lgr.generate_omegas(k, 4 * k))).tofile(fr_)
+    out = subprocess.check_output([exe, str(k), str(l), str(fr_), str(fw), str(fp)], stderr=subprocess.STDOUT, timeout=300).decode()
+    assert "ok" in out and "valid 1 1 1" in out, out
+    wk, wv, wc = ref.pack_rows(l, ws)
+    vals = np.stack([oracle.to_limbs(r) for r in wv]); coefs = np.stack([oracle.to_limbs(r) for r in wc])
+    want = ref.prove(l, k, wk, vals, coefs, 0, bytes((i * 7 + 1) & 0xFF for i in range(32)), bytes(32))
+    assert want["valid"] == (True, True, True)
+    lines = dict(line.split(" ", 1) for line in out.strip().splitlines())
+    assert lines["root"] == want["root"].hex() and lines["stage1"] == want["stage1_seed"].hex() and lines["stage2"] == want["stage2_seed"].hex()
+    env = ref.parse_envelope(fp.read_bytes())
+    meta = {"prover_version": "1.5.0", "program_hash": bytes(32), "generated_at": 1, "k": k, "n": 4 * k, "sample_size": 192}
+    assert env.SerializeToString(deterministic=True) == ref.build_envelope(meta, want["root"], want["siblings"], want["sample"], want["code"],
+                                                                           want["linear"], want["quad"], want["samplings"])
