@@ -56,29 +56,51 @@ __global__ void __launch_bounds__(enc_cfg<LOGK>::THREADS, (enc_cfg<LOGK>::SMEM <
     // in, natural out), selected by run-time flags: a second, decimation-in-frequency body for the inverse transform
     // doubled the straight-line code to 220 KB, more than the instruction cache holds (ncu: 20 % of the stall samples
     // were `no_inst`).
-    //   pass t = 0      : c = k * iNTT_k(row): the first pass gathers row[bitrev(q)] from global memory (32-byte sectors,
-    //                     so the gather costs no extra traffic), twiddles w_k^-1, result to C in natural order, values
-    //                     in [0,4p); the raw row is parked in W for the copied coset; 1/k is folded into the twists
+    //   pass t = 0      : c = k * iNTT_k(row): the first pass gathers row[bitrev(q)] from the bulk-loaded row in W, twiddles
+    //                     w_k^-1, result to C in natural order, values in [0,4p); 1/k is folded into the twists
     //   pass t = 1..    : coset r: the first pass reads C[bitrev(q)] and applies the twist w_n^(r*bitrev(q))/k, the last
     //                     pass canonicalises and writes e[4m + r] straight to global memory
     const fr_mem *src = rows_in + (active ? row : 0) * in_row_stride;
     fr_mem *dst = out + (active ? row : 0) * out_row_stride;
     const bool sys = t.sys_mul != 0;
     const int ntrans = sys ? 4 : 5;
+    // The message row comes in as ONE bulk copy (TMA, cp.async.bulk global -> shared, k*32 contiguous bytes) issued by the
+    // first thread of the row's slot and signalled on an mbarrier; the row then sits in W, where the inverse transform
+    // gathers it in bit-reversed order and the copied coset reads it back.  In-place encodes (rows aliasing codewords) are
+    // safe: the whole row is in shared memory before the first codeword element is written.
+    __shared__ __align__(8) unsigned long long row_bar[cfg::SLOTS];
+    if (tl == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&row_bar[slot]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (active) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)(K * 32)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(W)), "l"(src), "r"((uint32_t)(K * 32)), "r"(bar) : "memory");
+        }
+    }
+    __syncthreads();                                                   // barrier initialised before anybody polls it
+    if (active) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&row_bar[slot]);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "ROW_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+            "@p bra ROW_DONE;\n\t"
+            "bra ROW_WAIT;\n\t"
+            "ROW_DONE:\n\t}" :: "r"(bar) : "memory");
+    }
 #pragma unroll 1
     for (int tr = 0; tr < ntrans; tr++) {
         const bool inv = tr == 0;
         const int r = sys ? tr : tr - 1;                                       // coset index of passes tr >= 1
         const fr_mem *tw = inv ? t.inv_k : t.fwd_c;
         const fr_mem *tw_r = t.twist + (inv ? 0 : r) * K;
+        // the inverse transform works in C (its first pass reads the raw row from W and leaves it there); the cosets work in W
         ntt_passes_io<LOGK, 0, false>(inv ? C : W, tl, tw, 1, sync,
             [&](int q) -> fr_t {
                 const int i = (int)bitrev((uint32_t)q, LOGK);
-                if (inv) {
-                    const fr_t x = active ? fr_ldg(src + i) : fr_zero();
-                    if (sys) fr_sts(W + i, x);
-                    return x;
-                }
+                if (inv) return active ? fr_lds(W + i) : fr_zero();
                 return fr_mont_mul(fr_lds(C + i), fr_ldc(tw_r + q));
             },
             [&](int m, const fr_t &x) {
