@@ -847,7 +847,7 @@ int lgr_ubench_mont_occ(lgr_ctx *c, int nchain, int warps_per_sm, double *ops) {
 // cycles per SHA-256 compression of one warp owning a scheduler (variant 3/4/5, see ubench.cu)
 int lgr_ubench_chain(lgr_ctx *c, int variant, int warps_per_cta, int active_lanes, double *cycles) {
     REQUIRE(c && cycles, "null argument");
-    REQUIRE(variant >= 3 && variant <= 23 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
+    REQUIRE(variant >= 3 && variant <= 25 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
     uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
     CU(launch_ubench_chain(variant, d, 64, warps_per_cta, active_lanes, c->stream));
     CU(launch_ubench_chain(variant, d, 512, warps_per_cta, active_lanes, c->stream));

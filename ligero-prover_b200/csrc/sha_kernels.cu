@@ -304,7 +304,7 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
 }
 
-template <int G>
+template <int G, int D>
 __global__ void __launch_bounds__(128, 1) sha_chain16_kernel(uint32_t *ctx, int n, const fr_mem *__restrict__ tile, long long row_stride, int T, const uint32_t one) {
     extern __shared__ __align__(16) unsigned char chain_smem[];
     constexpr int NG = kC16Slots / G;
@@ -356,7 +356,9 @@ __global__ void __launch_bounds__(128, 1) sha_chain16_kernel(uint32_t *ctx, int 
       else { const uint32_t r0_ = __shfl_xor_sync(0xffffffffu, isE ? np_ : (IDLE_SEND), 16);   \
              if (isE) LGR_C16_SHIFT(np_) rm2 = rm1; rm1 = r0_; } }
         int grp = 0; uint32_t phase = 0;
-        uint32_t kq[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // K+W of the next eight rounds, loaded ahead of their use
+        uint32_t kq[D];                                      // K+W of the next D rounds, loaded ahead of their use
+#pragma unroll
+        for (int j = 0; j < D; j++) kq[j] = 0;
         for (int b0 = 0; b0 < nblk; b0 += G) {
             mbar_wait(full + grp, phase);
             const int cnt = min(G, nblk - b0);
@@ -371,17 +373,17 @@ __global__ void __launch_bounds__(128, 1) sha_chain16_kernel(uint32_t *ctx, int 
                 const bool a_on = (b0 + qb) > 0;              // the A lanes idle through the first two iterations of the launch
                 if (qb == 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) kq[j] = kwp[j * 16];
+                    for (int j = 0; j < D; j++) kq[j] = kwp[j * 16];
                 }
                 LGR_C16_BOUNDARY(mE)
-                if (a_on) { LGR_C16_ROUND(0, kq[0], true, 0u) LGR_C16_ROUND(1, kq[1], true, 0u) }
-                else { LGR_C16_ROUND(0, kq[0], false, q) LGR_C16_ROUND(1, kq[1], false, p) }
-                kq[0] = kwp[8 * 16]; kq[1] = kwp[9 * 16];
+                if (a_on) { LGR_C16_ROUND(0, kq[0], true, 0u) kq[0] = kwp[D * 16]; LGR_C16_ROUND(1, kq[1 % D], true, 0u) }
+                else { LGR_C16_ROUND(0, kq[0], false, q) kq[0] = kwp[D * 16]; LGR_C16_ROUND(1, kq[1 % D], false, p) }
+                kq[1 % D] = kwp[(1 + D) * 16];
                 LGR_C16_BOUNDARY(mA)
 #pragma unroll
                 for (int j = 2; j < 64; j++) {
-                    const uint32_t kw_ = kq[j & 7];
-                    kq[j & 7] = (j + 8 < 64) ? kwp[(j + 8) * 16] : kwn[(j + 8 - 64) * 16];
+                    const uint32_t kw_ = kq[j % D];
+                    kq[j % D] = (j + D < 64) ? kwp[(j + D) * 16] : kwn[(j + D - 64) * 16];
                     LGR_C16_ROUND(j, kw_, true, 0u)
                 }
             }
@@ -569,16 +571,18 @@ cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long lon
     if (lane_split && n % 16 == 0 && n / 16 <= 148 && T >= 4) {
         static const int group16 = getenv("LGR_CHAIN_GROUP") ? atoi(getenv("LGR_CHAIN_GROUP")) : 8;
         static const int helper_warps = getenv("LGR_CHAIN_HELPERS") ? atoi(getenv("LGR_CHAIN_HELPERS")) : 3;
-#define LGR_C16_LAUNCH(G)                                                                                                               \
+#define LGR_C16_LAUNCH(G, D)                                                                                                            \
     {                                                                                                                                   \
-        cudaError_t e = cudaFuncSetAttribute(sha_chain16_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC16Smem);        \
+        cudaError_t e = cudaFuncSetAttribute(sha_chain16_kernel<G, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC16Smem);     \
         if (e != cudaSuccess) return e;                                                                                                 \
-        sha_chain16_kernel<G><<<n / 16, 32 * (1 + helper_warps), kC16Smem, st>>>(ctx, n, tile, row_stride, T, 1u);                        \
+        sha_chain16_kernel<G, D><<<n / 16, 32 * (1 + helper_warps), kC16Smem, st>>>(ctx, n, tile, row_stride, T, 1u);                     \
         return cudaGetLastError();                                                                                                      \
     }
-        if (group16 == 1) LGR_C16_LAUNCH(1)
-        if (group16 == 4) LGR_C16_LAUNCH(4)
-        LGR_C16_LAUNCH(8)
+        // D = K+W words in flight: measured 1534 / 1511 / 1490 / 1495 / 1448 / 1448 / 1481 / 1525 / 1517 / 1578 cycles per block
+        // for D = 1 / 2 / 4 / 6 / 7 / 8 / 10 / 12 / 16 / 24 (in isolation the trend is the opposite: lgr_ubench_chain 22, 24, 25)
+        if (group16 == 1) LGR_C16_LAUNCH(1, 8)
+        if (group16 == 4) LGR_C16_LAUNCH(4, 8)
+        LGR_C16_LAUNCH(8, 8)
     }
     if (n % 32 == 0 && n / 32 <= 148 && T >= 4) {
         // narrow matrix: producer/consumer CTAs, one chain warp per SM

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128) ubench_chain_kernel(uint32_t *out, int it
             }
         }
         st[0] = p; st[1] = q; st[2] = r; st[3] = s; st[4] = rm2 ^ rm3;
-    } else if (VARIANT == 21 || VARIANT == 22 || VARIANT == 23) {
+    } else if (VARIANT >= 21 && VARIANT <= 25) {
         // the block loop of sha_chain16_kernel verbatim (boundary steps, K+W ring of eight registers, A lanes reading
         // zeros); 22: without the boundary steps and the first-four-rounds special case; 23: as 22 with 32-word rows (the A
         // lanes read the upper half of the row the E lanes read: one 128-byte row per LDS)
@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(128) ubench_chain_kernel(uint32_t *out, int it
         uint32_t u = ub_lop3<0xF8>(q, r, M), v = ub_lop3<0xC4>(q, r, M);
         uint32_t kq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         constexpr int RS = (VARIANT == 23) ? 32 : 16;            // row stride in words
+        constexpr int D = (VARIANT == 24) ? 4 : ((VARIANT == 25) ? 2 : 8);   // 24 / 25: K+W fetched 4 / 2 rounds ahead instead of 8
         const uint32_t *kwp = (VARIANT == 23) ? &kw[warp][lane] : (isE ? &kw[warp][lane] : &kw[warp][16 + (lane & 15)]);
         const uint32_t *kwn = kwp;
 #define UB_BOUNDARY(MX) { uint32_t t_; t_ = p; p = cv0 * (MX) + p; cv0 = t_ * (MX) + cv0; t_ = q; q = cv1 * (MX) + q; cv1 = t_ * (MX) + cv1; \
@@ -328,17 +329,17 @@ __global__ void __launch_bounds__(128) ubench_chain_kernel(uint32_t *out, int it
       const uint32_t r0_ = __shfl_xor_sync(0xffffffffu, np_, 16); \
       s = r; r = q; q = p; p = np_; u = ub_lop3<0xF8>(q, r, M); v = ub_lop3<0xC4>(q, r, M); rm2 = rm1; rm1 = r0_; }
 #pragma unroll
-        for (int j = 0; j < 8; j++) kq[j] = kwp[j * RS];
+        for (int j = 0; j < D; j++) kq[j] = kwp[j * RS];
 #pragma unroll 1
         for (int it = 0; it < iters; it++) {
             if (VARIANT == 21) UB_BOUNDARY(mE)
-            UB_ROUND(0, kq[0]) UB_ROUND(1, kq[1])
-            kq[0] = kwp[8 * RS]; kq[1] = kwp[9 * RS];
+            UB_ROUND(0, kq[0]) kq[0] = (D > 0) ? kwp[D * RS] : 0u;
+            UB_ROUND(1, kq[1 % D]) kq[1 % D] = kwp[(1 + D) * RS];
             if (VARIANT == 21) UB_BOUNDARY(mA)
 #pragma unroll
             for (int j = 2; j < 64; j++) {
-                const uint32_t kw_ = kq[j & 7];
-                kq[j & 7] = (j + 8 < 64) ? kwp[(j + 8) * RS] : kwn[(j + 8 - 64) * RS];
+                const uint32_t kw_ = kq[j % D];
+                kq[j % D] = (j + D < 64) ? kwp[(j + D) * RS] : kwn[(j + D - 64) * RS];
                 UB_ROUND(j, kw_)
             }
         }
@@ -379,7 +380,9 @@ cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps
     else if (variant == 20) ubench_chain_kernel<20><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 21) ubench_chain_kernel<21><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     else if (variant == 22) ubench_chain_kernel<22><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
-    else ubench_chain_kernel<23><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 23) ubench_chain_kernel<23><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else if (variant == 24) ubench_chain_kernel<24><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
+    else ubench_chain_kernel<25><<<148, threads, 0, st>>>(out, iters, cc, active_lanes);
     return cudaGetLastError();
 }
 

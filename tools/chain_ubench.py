@@ -5,7 +5,7 @@ import __graft_entry__ as ge
 lgr = ge._load_package()
 ex = lgr.make_executor(64, 256)
 res = {}
-for v in range(3, 24):
+for v in range(3, 26):
     for wpc in (1, 4):
         res["variant%d_warps%d" % (v, wpc)] = ex.ubench_chain(v, wpc, 32)
 print(json.dumps(res, indent=1))
