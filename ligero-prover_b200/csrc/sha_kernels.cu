@@ -569,7 +569,7 @@ cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long lon
     static const int split_env = getenv("LGR_CHAIN_SPLIT") ? atoi(getenv("LGR_CHAIN_SPLIT")) : -1;
     const bool lane_split = split_env >= 0 ? split_env != 0 : (n / 16 <= 64);
     if (lane_split && n % 16 == 0 && n / 16 <= 148 && T >= 4) {
-        static const int group16 = getenv("LGR_CHAIN_GROUP") ? atoi(getenv("LGR_CHAIN_GROUP")) : 8;
+        static const int group16 = getenv("LGR_CHAIN_GROUP") ? atoi(getenv("LGR_CHAIN_GROUP")) : 16;
         static const int helper_warps = getenv("LGR_CHAIN_HELPERS") ? atoi(getenv("LGR_CHAIN_HELPERS")) : 3;
 #define LGR_C16_LAUNCH(G, D)                                                                                                            \
     {                                                                                                                                   \
@@ -582,7 +582,8 @@ cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long lon
         // for D = 1 / 2 / 4 / 6 / 7 / 8 / 10 / 12 / 16 / 24 (in isolation the trend is the opposite: lgr_ubench_chain 22, 24, 25)
         if (group16 == 1) LGR_C16_LAUNCH(1, 8)
         if (group16 == 4) LGR_C16_LAUNCH(4, 8)
-        LGR_C16_LAUNCH(8, 8)
+        if (group16 == 8) LGR_C16_LAUNCH(8, 8)
+        LGR_C16_LAUNCH(16, 8)                                  // hand-over group: 1 / 4 / 8 / 12 / 16 / 24 blocks -> 1511 / 1482 / 1450 / 1441 / 1431 / 1440 cycles
     }
     if (n % 32 == 0 && n / 32 <= 148 && T >= 4) {
         // narrow matrix: producer/consumer CTAs, one chain warp per SM
