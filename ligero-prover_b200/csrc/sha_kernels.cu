@@ -281,8 +281,9 @@ __global__ void __launch_bounds__(128, 1) sha_chain_kernel(uint32_t *ctx, int n,
 //     p' = [rot(p,s1) ^ rot(p,s2) ^ rot(p,s3)]  +  [(p & u) | (~p & v)]  +  [sgn*s + KW + R]
 // where R is the partner lane's p' of two iterations ago, exchanged with one SHFL.BFLY per round: the
 // E lanes need a_{i-3} (as d), the A lanes need e_{i+1}; running the A lanes two rounds behind the E
-// lanes gives both a slack of two iterations, so the shuffle latency never shows.  8 ALU-pipe instructions
-// per round (3 SHF, 4 LOP3, 1 IADD3) instead of 12, the sums known early on the FMA pipe as before.
+// lanes gives both a slack of two iterations.  8 ALU-pipe instructions per round (3 SHF, 4 LOP3, 1 IADD3) instead of
+// 12, the sums known early on the FMA pipe as before; what bounds the kernel is the loop e -> shuffle -> a -> shuffle -> e,
+// four rounds long with two 26-cycle hops in it (about 19 cycles per round; measured 22).
 // The feed-forward at block boundaries (st += working variables) is folded into the same stream:
 // every lane keeps its chaining words CV and adds them at its own boundary (E lanes at iteration 0, A
 // lanes at iteration 2 of a block; multipliers mE / mA make the other half's instruction a no-op), and
