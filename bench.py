@@ -137,8 +137,9 @@ def cpu_reference_rate(target_seconds, k=K):
     rows = max(1 << 11, min(rows, 1 << LOG_ROWS))
     rows = 1 << (rows.bit_length() - 1)
     t0 = time.perf_counter()
-    lgo.encode_commit_synth(SEED, rows, k)
+    _, nodes, _ = lgo.encode_commit_synth(SEED, rows, k)
     dt = time.perf_counter() - t0
+    cpu_reference_rate.last_root = nodes[0].tobytes().hex()   # root of the first `rows` rows of the seed-3 matrix
     return rows * k / dt, cores, rows, dt
 
 
@@ -199,6 +200,8 @@ def main():
     ap.add_argument("--layout", default="sharded", choices=["sharded", "exact"],
                     help="N>1: 'sharded' = per-rank commitments + one digest all-gather (north_star); 'exact' = bit-exact single root "
                          "via all-to-all of codeword column slabs (ligero-prover_b200/sharding.py)")
+    ap.add_argument("--no-exact", action="store_true", help="skip the exact-layout / k=8192 legs (N>1: exact, exact_k8192; N=1: encode_commit_k8192)")
+    ap.add_argument("--no-config5", action="store_true", help="N=8: skip the 2^26-row leg (BASELINE config 5)")
     ap.add_argument("--aux", action="store_true", help="also time the reference's default geometry k=8192 and the 2^20 NTT (extra keys)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -395,12 +398,40 @@ def main():
         if args.aux and world == 1:
             aux = run_aux(lgr, torch, dev, stream, hbm)
 
-    # ---- CPU baseline: rank 0, N = 1 only ---------------------------------------------------------
+    # ---- CPU baseline: rank 0, N = 1 only; its root pins the GPU path on the same rows ------------
     cpu = None
+    parity_check = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, rows, dt = cpu_reference_rate(12.0, k)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle encode+commit of 2^%d rows x k=%d, seed %d, %.1f s, OpenMP threads=%d" % (rows.bit_length() - 1, k, SEED, dt, cores)}
+        # the oracle (pinned to the reference's shaders, tests/test_wgslref_cpu.py) committed the first `rows` rows of the
+        # bench matrix: commit the same rows on the GPU, device-resident and through the host-buffer entry point
+        with torch.cuda.stream(stream):
+            ex.use_torch_stream()
+            ex.encode_commit(wbuf, rows, digests, nodes)
+            gpu_root = ex.copy_to_host(nodes, np.uint8)[:32].tobytes().hex()
+            hrows = torch.empty(rows * k * 8, dtype=torch.int32, pin_memory=True)
+            hrows.copy_(witness[: rows * k * 8])
+            stream.synchronize()
+            _, host_root = ex.encode_commit_host(hrows, rows)
+        parity_check = {"rows": rows, "k": k, "root_equal": gpu_root == cpu_reference_rate.last_root,
+                        "root_equal_host_path": host_root.hex() == cpu_reference_rate.last_root, "oracle_root": cpu_reference_rate.last_root}
+
+    # ---- the bit-exact single-root layout over N GPUs, and the reference's default geometry --------
+    exact = exact_k8192 = config5 = k8192 = None
+    if not args.no_exact:
+        with torch.cuda.stream(stream):
+            ex.use_torch_stream()
+            if world == 8 and args.log_rows == LOG_ROWS and k == K and not args.no_config5:
+                config5 = run_config5(ex, torch, dist, stream, dev, witness, wbuf, rank, world, k, n)
+            del wbuf, witness
+            torch.cuda.empty_cache()
+            if world > 1:
+                exact = run_exact(lgr, torch, dist, dev, stream, rank, world, 256, 1 << 20, hbm)
+                exact_k8192 = run_exact(lgr, torch, dist, dev, stream, rank, world, 8192, 1 << 15, hbm)
+            else:
+                k8192 = run_k8192_single(lgr, torch, dev, stream, 1 << 15)
 
     if rank == 0:
         line = {
@@ -411,8 +442,11 @@ def main():
                        "parallelism": ("rows sharded over %d GPU(s); digests all-gathered (NCCL) for the tree" % world) if exact_engine is None else
                                       ("exact layout over %d GPUs: tiles round-robin, all-to-all of column slabs, one root" % world)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "chain_roofline": chain_roofline, "kernels": kern, "int_roofline": int_roofline,
-            "cpu_baseline": cpu, "root": root,
+            "cpu_baseline": cpu, "root": root, "parity_check": parity_check,
         }
+        for key, val in (("exact", exact), ("exact_k8192", exact_k8192), ("config5", config5), ("encode_commit_k8192", k8192)):
+            if val is not None:
+                line[key] = val
         if aux:
             line["aux"] = aux
         print(json.dumps(line), flush=True)
@@ -421,6 +455,172 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def load_sharding():
+    spec = importlib.util.spec_from_file_location("lgr_sharding", os.path.join(ROOT, "ligero-prover_b200", "sharding.py"))
+    sh = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sh)
+    return sh
+
+
+def run_exact(lgr, torch, dist, dev, stream, rank, world, k, total_rows, hbm, steps=3):
+    """STRONG scaling of the reference's own commitment: ONE root over a fixed total_rows x k matrix (seed 3), rows dealt
+    tile-round-robin over the ranks, column slabs handed to their hashing rank (sharding.commit_exact).  Checked against
+    a single-GPU commitment of the same matrix computed on every rank."""
+    import numpy as np
+    sh = load_sharding()
+    n = 4 * k
+    ex = lgr.Executor(dev.index)
+    ex.ntt_init(max(k - 192, 1), k, n)
+    ex.use_torch_stream()
+    T = max(2, (1 << 23) // n)
+    while T * world > total_rows and T > 2:
+        T >>= 1
+    num_tiles = (total_rows + T - 1) // T
+    mine = sh.tiles_of_rank(num_tiles, world, rank)
+    bufs = []
+    for t in mine:
+        rows = min(T, total_rows - t * T)
+        b = ex.make_device_buffer(T * k * 32)
+        ex.synth(b, SEED, t * T, rows, k)
+        bufs.append((b, rows))
+    eng = sh.make_gpu_engine(ex, T, world, rank, dist)
+    nodes = ex.make_device_buffer(ex.merkle_node_count(n) * 32)
+
+    def step():
+        leaves = sh.commit_exact(eng, lambda i: bufs[i], total_rows, T, world, rank, dist)
+        ex.use_torch_stream()
+        ex.merkle_build(ex.wrap(leaves.contiguous()), n, nodes)
+
+    def sync_all():
+        stream.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(2):
+        step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    root = ex.copy_to_host(nodes, np.uint8)[:32].tobytes().hex()
+    # the same matrix on ONE GPU (every rank does it: no extra collective, and it gives the single-GPU time)
+    for b, _ in bufs:
+        del b
+    bufs.clear()
+    whole = ex.make_device_buffer(total_rows * k * 32)
+    ex.synth(whole, SEED, 0, total_rows, k)
+    d1 = ex.make_device_buffer(n * 32)
+    ex.encode_commit(whole, total_rows, d1, nodes)
+    stream.synchronize()
+    e0.record(stream)
+    ex.encode_commit(whole, total_rows, d1, nodes)
+    e1.record(stream)
+    stream.synchronize()
+    single_ms = e0.elapsed_time(e1)
+    want = ex.copy_to_host(nodes, np.uint8)[:32].tobytes().hex()
+    same = torch.tensor([1 if root == want else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    elems = total_rows * k
+    out = {"k": k, "n": n, "rows_total": total_rows, "tile_rows": T, "scaling": "strong", "transport": eng.transport,
+           "value": elems / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+           "single_gpu_value": elems / (single_ms * 1e-3), "speedup_vs_single_gpu": single_ms / ms,
+           "root_equals_single_gpu": bool(int(same.item())), "root": root,
+           "peer_bytes_per_step": int(elems * 4 * 32 * (world - 1) / world),
+           "peer_gbs_per_gpu": elems * 4 * 32 * (world - 1) / world / world / (ms * 1e-3) / 1e9,
+           "path_frac_hbm": elems / (ms * 1e-3) / world * 32 / 1e9 / hbm}
+    eng.close()
+    ex.close()
+    return out
+
+
+def run_k8192_single(lgr, torch, dev, stream, total_rows):
+    """the reference's default geometry (k = 8192, n = 32768, include/params.hpp:24-32) on one GPU: same fixed matrix as
+    exact_k8192 at N > 1 (2^15 rows, seed 3), device-resident and from pinned host rows"""
+    import numpy as np
+    k, n = 8192, 32768
+    ex = lgr.Executor(dev.index)
+    ex.ntt_init(k - 192, k, n)
+    ex.use_torch_stream()
+    w = torch.empty(total_rows * k * 8, dtype=torch.int32, device=dev)
+    wb = ex.wrap(w)
+    ex.synth(wb, SEED, 0, total_rows, k)
+    dig = ex.make_device_buffer(n * 32)
+    nodes = ex.make_device_buffer((2 * n - 1) * 32)
+    for _ in range(2):
+        ex.encode_commit(wb, total_rows, dig, nodes)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream.synchronize()
+    e0.record(stream)
+    for _ in range(3):
+        ex.encode_commit(wb, total_rows, dig, nodes)
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    root = ex.copy_to_host(nodes, np.uint8)[:32].tobytes().hex()
+    host = torch.empty(total_rows * k * 8, dtype=torch.int32, pin_memory=True)
+    host.copy_(w)
+    stream.synchronize()
+    _, r2 = ex.encode_commit_host(host, total_rows)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        _, r2 = ex.encode_commit_host(host, total_rows)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
+    elems = total_rows * k
+    out = {"k": k, "n": n, "rows_total": total_rows, "value": elems / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "root": root,
+           "e2e": {"value": elems / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": elems * 32, "d2h_bytes_per_step": 32,
+                   "root_matches_device_path": r2.hex() == root}}
+    del host
+    ex.close()
+    return out
+
+
+def run_config5(ex, torch, dist, stream, dev, witness, wbuf, rank, world, k, n):
+    """BASELINE config 5 at its stated size: 2^26 rows x k = 256 over 8 GPUs = 2^23 rows (64 GiB) per GPU, sharded layout
+    (per-rank commitments, one digest all-gather, tree over the 8n leaves).  The first 2^22 rows of the shard are the
+    resident bench witness; the second half is generated next to it."""
+    import numpy as np
+    R = 1 << 22
+    second = torch.empty(R * k * 8, dtype=torch.int32, device=dev)
+    sbuf = ex.wrap(second)
+    ex.synth(sbuf, SEED, (world + rank) * R, R, k)           # rows [(8+rank)*2^22, ...): disjoint from every first half
+    ctx = ex.make_device_buffer(ex.sha256_context_bytes(n))
+    dig = ex.make_device_buffer(n * 32)
+    bind = ex.bind_sha256_context(ctx, dig)
+    gathered = torch.empty(world * n * 8, dtype=torch.int32, device=dev)
+    nodes = ex.make_device_buffer(ex.merkle_node_count(world * n) * 32)
+    ex.sha256_init(n)
+
+    def step():
+        ex.sha256_digest_init(bind)
+        ex.encode_absorb(ctx, wbuf, R)
+        ex.encode_absorb(ctx, sbuf, R)
+        ex.sha256_digest_final(bind)
+        dist.all_gather_into_tensor(gathered, dig.storage[: n * 8])
+        ex.merkle_build(ex.wrap(gathered), world * n, nodes)
+
+    step()
+    stream.synchronize(); dist.barrier(); torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(2):
+        step()
+    e1.record(stream)
+    stream.synchronize(); dist.barrier(); torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / 2
+    root = ex.copy_to_host(nodes, np.uint8)[:32].tobytes().hex()
+    del second
+    return {"rows_total": world * 2 * R, "rows_per_gpu": 2 * R, "k": k, "layout": "sharded (one digest all-gather)", "value": world * 2 * R * k / (ms * 1e-3),
+            "unit": UNIT, "ms_per_step": ms, "steps": 2, "root": root}
 
 
 def run_aux(lgr, torch, dev, stream, hbm):

@@ -131,6 +131,25 @@ int lgr_sample_gather_rows(lgr_ctx *ctx, const void *tile, uint64_t row_stride_e
 /* nrows encodes in one launch: rows[r] = k elements at rows + r*row_stride_elems, codewords[r] = n
  * elements at codewords + r*n.  rows may alias codewords when row_stride_elems == n (in place). */
 int lgr_encode_rows(lgr_ctx *ctx, const void *rows, uint64_t row_stride_elems, uint32_t nrows, void *codewords);
+/* ---- exact multi-GPU commitment (B200-native; no reference counterpart: the reference is single-device) ----
+ * A column's leaf is ONE SHA-256 stream over all rows (nonbatch_context.hpp:445-451 -> sha256.wgsl:147-177), so rows
+ * shard across GPUs for the ENCODE only; the codeword columns are then cut into `nslabs` slabs of n/nslabs columns and
+ * slab h of every row is hashed by GPU h.  lgr_encode_rows_slabs writes column j of row r to
+ * slab_base[j / (n/nslabs)] + r*(n/nslabs) + j % (n/nslabs): row-major [nrows][n/nslabs] per slab.  slab_base[h] may
+ * be PEER memory (lgr_ipc_open): the encoder's stores then cross NVLink directly into the hasher's buffer. */
+int lgr_encode_rows_slabs(lgr_ctx *ctx, const void *rows, uint64_t row_stride_elems, uint32_t nrows, void *const *slab_base, uint32_t nslabs);
+/* peer-visible device memory through CUDA IPC (one process per GPU): alloc + export on the owner, open on the peers */
+int lgr_ipc_alloc(lgr_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64]);
+int lgr_ipc_open(lgr_ctx *ctx, const unsigned char handle[64], void **dptr);
+int lgr_ipc_close(lgr_ctx *ctx, void *dptr);
+int lgr_ipc_free(lgr_ctx *ctx, void *dptr);
+/* hand-over flags (u64 monotone counters in peer-visible memory), enqueued on the context's stream:
+ * signal: *slots[i] = value for every i, after everything enqueued before it (system-scope release);
+ * wait  : until flags[i] >= value for all i < nflags (system-scope acquire); gives up after timeout_ms and writes
+ *         a non-zero code to *err_flag (u32, device memory) instead of hanging the GPU. */
+int lgr_peer_signal(lgr_ctx *ctx, void *const *slots, uint32_t nslots, uint64_t value);
+int lgr_peer_wait(lgr_ctx *ctx, const void *flags, uint32_t nflags, uint64_t value, uint32_t timeout_ms, void *err_flag);
+
 /* stage-1 commit of an R x k device-resident row-major witness: for every row, encode and absorb
  * into the n column hashes in row order (nonbatch_context.hpp:445-451), then final + tree
  * (nonbatch_context.hpp:555-558, merkle_tree.hpp:343-375).  digests: n*32 B; nodes: (2n-1)*32 B or NULL.

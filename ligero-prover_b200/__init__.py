@@ -268,6 +268,10 @@ class Executor:
         _check(lib().lgr_read(self._ctx, out.ctypes.data_as(C.c_void_p), buf.ptr(), C.c_size_t(0), C.c_size_t(buf.size())))
         return out
 
+    def read_into(self, host_tensor, dev_addr, nbytes):
+        """blocking device -> host copy from a raw device address (peer-visible IPC memory) into a pinned torch tensor"""
+        _check(lib().lgr_read(self._ctx, C.c_void_p(host_tensor.data_ptr()), C.c_void_p(int(dev_addr)), C.c_size_t(0), C.c_size_t(nbytes)))
+
     def read_elements(self, buf):
         return self.copy_to_host(buf).reshape(-1, 8)
 
@@ -452,6 +456,38 @@ class Executor:
     def encode_rows(self, rows, nrows, codewords, row_stride_elems=None):
         rs = self._k if row_stride_elems is None else row_stride_elems
         _check(lib().lgr_encode_rows(self._ctx, rows.ptr(), C.c_uint64(rs), C.c_uint32(nrows), codewords.ptr()))
+
+    # ---- exact multi-GPU layout (include/lgr.h: slab-major codewords, peer memory, hand-over flags) ----
+    def encode_rows_slabs(self, rows, nrows, slab_ptrs, row_stride_elems=None):
+        """column slab h of every codeword -> row-major [nrows][n/G] at slab_ptrs[h] (raw device addresses, local or peer)"""
+        rs = self._k if row_stride_elems is None else row_stride_elems
+        arr = (C.c_void_p * len(slab_ptrs))(*[C.c_void_p(int(a)) for a in slab_ptrs])
+        _check(lib().lgr_encode_rows_slabs(self._ctx, rows.ptr(), C.c_uint64(rs), C.c_uint32(nrows), arr, C.c_uint32(len(slab_ptrs))))
+
+    def ipc_alloc(self, nbytes):
+        """peer-visible device memory: (device address, 64-byte CUDA IPC handle)"""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _check(lib().lgr_ipc_alloc(self._ctx, C.c_size_t(nbytes), C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def ipc_open(self, handle):
+        ptr = C.c_void_p()
+        _check(lib().lgr_ipc_open(self._ctx, (C.c_ubyte * 64)(*handle), C.byref(ptr)))
+        return ptr.value
+
+    def ipc_close(self, ptr):
+        _check(lib().lgr_ipc_close(self._ctx, C.c_void_p(ptr)))
+
+    def ipc_free(self, ptr):
+        _check(lib().lgr_ipc_free(self._ctx, C.c_void_p(ptr)))
+
+    def peer_signal(self, slot_ptrs, value):
+        arr = (C.c_void_p * len(slot_ptrs))(*[C.c_void_p(int(a)) for a in slot_ptrs])
+        _check(lib().lgr_peer_signal(self._ctx, arr, C.c_uint32(len(slot_ptrs)), C.c_uint64(value)))
+
+    def peer_wait(self, flags_ptr, nflags, value, err_ptr, timeout_ms=20000):
+        _check(lib().lgr_peer_wait(self._ctx, C.c_void_p(int(flags_ptr)), C.c_uint32(nflags), C.c_uint64(value), C.c_uint32(timeout_ms), C.c_void_p(int(err_ptr))))
 
     def encode_commit(self, rows, nrows, digests, nodes=None):
         _check(lib().lgr_encode_commit(self._ctx, rows.ptr(), C.c_uint64(nrows), digests.ptr(), nodes.ptr() if nodes is not None else None))

@@ -27,6 +27,8 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
                         std::string(#expr) + ": " + cudaGetErrorString(e__));                            \
     } while (0)
 #define REQUIRE(cond, msg) do { if (!(cond)) return fail(LGR_ERR_INVALID, msg); } while (0)
+// every ABI entry point runs with its context's device current, whatever the caller's current device is
+#define ENTER(c) do { REQUIRE((c) != nullptr, "null context"); CU(cudaSetDevice((c)->device)); } while (0)
 
 namespace {
 
@@ -179,6 +181,7 @@ struct NttJob {
     bool no_scale;
     int cosets = 4;              // coset mode: transforms per row; batch index b = row*cosets + s, r = s + coset_base
     int coset_base = 0;          // coset_in_twist points at the table of coset `coset_base`
+    CodewordSink sink{};         // coset mode: nslabs > 0 = slab-major codewords (out / out_stride ignored)
 };
 
 static int run_ntt_job(lgr_ctx *c, NttPlan &p, const NttJob &j) {
@@ -225,6 +228,7 @@ static int run_ntt_job(lgr_ctx *c, NttPlan &p, const NttJob &j) {
     if (coset) {
         r.out_outer_div = j.cosets; r.out_outer_stride = j.out_stride; r.out_sub_stride = 1; r.out_sub_base = j.coset_base;
         r.out_lane_stride = 4; r.out_point_stride = 4 * N1;
+        r.sink = j.sink;
     } else {
         r.out_outer_stride = j.out_stride;
         r.out_lane_stride = 1; r.out_point_stride = N1;
@@ -305,13 +309,14 @@ static int build_large_encode_tables(lgr_ctx *c) {
 
 static bool fused_encode_ok(const lgr_ctx *c) { return c->logk >= encode_rows_min_logk() && c->logk <= encode_rows_max_logk(); }
 
-// nrows encodes: rows -> codewords (may alias when in place)
-static int encode_rows_impl(lgr_ctx *c, const fr_mem *rows, size_t row_stride, uint32_t nrows, fr_mem *cw, cudaStream_t st) {
+// nrows encodes: rows -> codewords at `sink` (plain sinks may alias the rows: in-place encode)
+static int encode_rows_impl(lgr_ctx *c, const fr_mem *rows, size_t row_stride, uint32_t nrows, const CodewordSink &sink, cudaStream_t st) {
     if (nrows == 0) return LGR_OK;
+    fr_mem *cw = sink.nslabs ? nullptr : sink.base[0];
     if (fused_encode_ok(c)) {
         int rc = build_encode_tables(c);
         if (rc) return rc;
-        CU(launch_encode_rows(rows, (long long)row_stride, cw, (long long)c->n, (int)nrows, c->logk, c->enc, st)); c->launches++;
+        CU(launch_encode_rows(rows, (long long)row_stride, sink, (int)nrows, c->logk, c->enc, st)); c->launches++;
         return LGR_OK;
     }
     // large k (> 2048): same decomposition as the fused kernel, on the tile engine.  Coefficients
@@ -341,33 +346,14 @@ static int encode_rows_impl(lgr_ctx *c, const fr_mem *rows, size_t row_stride, u
             CU(cudaMemcpy2DAsync(keep, k * 32, rows, row_stride * 32, k * 32, nrows, cudaMemcpyDeviceToDevice, st));
             src = keep; src_stride = (long long)k;
         }
-        CU(launch_sys_copy(src, src_stride, cw, (long long)c->n, (int)nrows, c->logk, c->sys_mul, st)); c->launches++;
+        CU(launch_sys_copy(src, src_stride, sink, (int)nrows, c->logk, c->sys_mul, st)); c->launches++;
     }
-    NttJob fwd{coef, (long long)k, cw, (long long)c->n, tmp, nrows * ncos, c->enc_large_twist + (sys ? k : 0), false, (int)ncos, sys ? 1 : 0};
+    NttJob fwd{coef, (long long)k, cw, sink.row_stride, tmp, nrows * ncos, c->enc_large_twist + (sys ? k : 0), false, (int)ncos, sys ? 1 : 0, sink};
     return run_ntt_job(c, *pf, fwd);
 }
 
-// ================================================================================================
-extern "C" {
-
-const char *lgr_last_error(void) { return g_err.c_str(); }
-int lgr_version(void) { return 100; }
-
-int lgr_create(lgr_ctx **out, int device, uint32_t l, uint32_t k, uint32_t n, const uint32_t p[8], const uint32_t root_k[8],
-               const uint32_t root_2k[8], const uint32_t root_n[8]) {
-    REQUIRE(out && p && root_k && root_2k && root_n, "null argument");
-    REQUIRE(k >= 8 && (k & (k - 1)) == 0, "k must be a power of two >= 8 (the reference needs k >= 512, engine.cpp:850)");
-    REQUIRE(n == 4 * k, "n must equal 4k (src/webgpu_prover.cpp:88-97)");
-    REQUIRE(l <= k, "l must not exceed k");
-    REQUIRE(memcmp(p, host::kP, 32) == 0, "modulus is not the BN254 scalar field (the kernels are specialised, as the reference's WGSL is)");
-    int ndev = 0;
-    CU(cudaGetDeviceCount(&ndev));
-    REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this library has no CPU fallback)");
-    CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return fail(LGR_ERR_UNSUPPORTED, std::string("liblgr is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor));
-    lgr_ctx *c = new lgr_ctx();
+// everything lgr_create does after allocating the context: any early return leaves a context lgr_destroy can take
+static int create_body(lgr_ctx *c, int device, uint32_t l, uint32_t k, uint32_t n, const uint32_t root_k[8], const uint32_t root_2k[8], const uint32_t root_n[8]) {
     c->device = device; c->l = l; c->k = k; c->n = n; c->logk = ilog2u(k);
     c->root_k = host::from_u32(root_k); c->root_2k = host::from_u32(root_2k); c->root_n = host::from_u32(root_n);
     int lo = 0, hi = 0;
@@ -396,6 +382,31 @@ int lgr_create(lgr_ctx **out, int device, uint32_t l, uint32_t k, uint32_t n, co
         if (!rc) rc = get_plan(c, c->logk + 2, c->root_n, inv, &pl);
     }
     if (!rc && fused_encode_ok(c)) rc = build_encode_tables(c);
+    return rc;
+}
+
+// ================================================================================================
+extern "C" {
+
+const char *lgr_last_error(void) { return g_err.c_str(); }
+int lgr_version(void) { return 100; }
+
+int lgr_create(lgr_ctx **out, int device, uint32_t l, uint32_t k, uint32_t n, const uint32_t p[8], const uint32_t root_k[8],
+               const uint32_t root_2k[8], const uint32_t root_n[8]) {
+    REQUIRE(out && p && root_k && root_2k && root_n, "null argument");
+    REQUIRE(k >= 8 && (k & (k - 1)) == 0, "k must be a power of two >= 8 (the reference needs k >= 512, engine.cpp:850)");
+    REQUIRE(n == 4 * k, "n must equal 4k (src/webgpu_prover.cpp:88-97)");
+    REQUIRE(l <= k, "l must not exceed k");
+    REQUIRE(memcmp(p, host::kP, 32) == 0, "modulus is not the BN254 scalar field (the kernels are specialised, as the reference's WGSL is)");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this library has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(LGR_ERR_UNSUPPORTED, std::string("liblgr is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor));
+    lgr_ctx *c = new lgr_ctx();
+    int rc = create_body(c, device, l, k, n, root_k, root_2k, root_n);
     if (rc) { std::string keep = g_err; lgr_destroy(c); g_err = keep; return rc; }
     *out = c;
     return LGR_OK;
@@ -425,8 +436,8 @@ int lgr_destroy(lgr_ctx *c) {
     return LGR_OK;
 }
 
-int lgr_set_stream(lgr_ctx *c, void *s) { REQUIRE(c, "null context"); c->stream = s ? (cudaStream_t)s : c->own_stream; return LGR_OK; }
-int lgr_sync(lgr_ctx *c) { REQUIRE(c, "null context"); CU(cudaStreamSynchronize(c->stream)); return LGR_OK; }
+int lgr_set_stream(lgr_ctx *c, void *s) { ENTER(c); REQUIRE(c, "null context"); c->stream = s ? (cudaStream_t)s : c->own_stream; return LGR_OK; }
+int lgr_sync(lgr_ctx *c) { ENTER(c); REQUIRE(c, "null context"); CU(cudaStreamSynchronize(c->stream)); return LGR_OK; }
 int lgr_geometry(const lgr_ctx *c, uint32_t *l, uint32_t *k, uint32_t *n) {
     REQUIRE(c, "null context");
     if (l) *l = c->l; if (k) *k = c->k; if (n) *n = c->n;
@@ -435,19 +446,20 @@ int lgr_geometry(const lgr_ctx *c, uint32_t *l, uint32_t *k, uint32_t *n) {
 int lgr_launch_count(const lgr_ctx *c, uint64_t *count) { REQUIRE(c && count, "null argument"); *count = c->launches; return LGR_OK; }
 
 // ---- buffers -----------------------------------------------------------------------------------
-int lgr_alloc(lgr_ctx *c, size_t bytes, void **dptr) {
+int lgr_alloc(lgr_ctx *c, size_t bytes, void **dptr) { ENTER(c);
     REQUIRE(c && dptr, "null argument");
     CU(cudaSetDevice(c->device));
-    CU(cudaMalloc(dptr, bytes ? bytes : 32));
+    CU(cudaMallocAsync(dptr, bytes ? bytes : 32, c->stream));            // stream-ordered: no device-wide synchronisation
     CU(cudaMemsetAsync(*dptr, 0, bytes ? bytes : 32, c->stream));
     return LGR_OK;
 }
-int lgr_free(lgr_ctx *c, void *dptr) {
+int lgr_free(lgr_ctx *c, void *dptr) { ENTER(c);
     REQUIRE(c, "null context");
-    if (dptr) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(dptr)); }
+    // stream-ordered release: every op that used the buffer was enqueued on (or joined back into) c->stream before this call
+    if (dptr) CU(cudaFreeAsync(dptr, c->stream));
     return LGR_OK;
 }
-int lgr_write(lgr_ctx *c, void *dst, size_t off, const void *src, size_t bytes) {
+int lgr_write(lgr_ctx *c, void *dst, size_t off, const void *src, size_t bytes) { ENTER(c);
     REQUIRE(c && dst && (src || !bytes), "null argument");
     if (!bytes) return LGR_OK;
     // the caller may reuse `src` immediately (nonbatch_context.hpp:455-468): stage through pinned memory
@@ -464,29 +476,29 @@ int lgr_write(lgr_ctx *c, void *dst, size_t off, const void *src, size_t bytes) 
     CU(cudaEventRecord(c->ev_staging, c->stream));
     return LGR_OK;
 }
-int lgr_clear(lgr_ctx *c, void *dst, size_t off, size_t bytes) {
+int lgr_clear(lgr_ctx *c, void *dst, size_t off, size_t bytes) { ENTER(c);
     REQUIRE(c && dst, "null argument");
     if (bytes) CU(cudaMemsetAsync((char *)dst + off, 0, bytes, c->stream));
     return LGR_OK;
 }
-int lgr_write_clear(lgr_ctx *c, void *dst, size_t dst_bytes, const void *src, size_t bytes) {
+int lgr_write_clear(lgr_ctx *c, void *dst, size_t dst_bytes, const void *src, size_t bytes) { ENTER(c);
     REQUIRE(bytes <= dst_bytes, "write_buffer_clear: source larger than destination");
     int rc = lgr_write(c, dst, 0, src, bytes);
     if (rc) return rc;
     return lgr_clear(c, dst, bytes, dst_bytes - bytes);
 }
-int lgr_copy(lgr_ctx *c, const void *src, void *dst, size_t bytes) {
+int lgr_copy(lgr_ctx *c, const void *src, void *dst, size_t bytes) { ENTER(c);
     REQUIRE(c && src && dst, "null argument");
     if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
     return LGR_OK;
 }
-int lgr_copy_clear(lgr_ctx *c, const void *src, size_t src_bytes, void *dst, size_t dst_bytes) {
+int lgr_copy_clear(lgr_ctx *c, const void *src, size_t src_bytes, void *dst, size_t dst_bytes) { ENTER(c);
     REQUIRE(src_bytes <= dst_bytes, "copy_buffer_clear: source larger than destination");
     int rc = lgr_copy(c, src, dst, src_bytes);
     if (rc) return rc;
     return lgr_clear(c, dst, src_bytes, dst_bytes - src_bytes);
 }
-int lgr_read(lgr_ctx *c, void *host_dst, const void *src, size_t off, size_t bytes) {
+int lgr_read(lgr_ctx *c, void *host_dst, const void *src, size_t off, size_t bytes) { ENTER(c);
     REQUIRE(c && host_dst && src, "null argument");
     if (bytes) CU(cudaMemcpyAsync(host_dst, (const char *)src + off, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -494,7 +506,7 @@ int lgr_read(lgr_ctx *c, void *host_dst, const void *src, size_t off, size_t byt
 }
 
 // ---- transforms --------------------------------------------------------------------------------
-int lgr_ntt(lgr_ctx *c, void *buf, int sel, int dir) {
+int lgr_ntt(lgr_ctx *c, void *buf, int sel, int dir) { ENTER(c);
     REQUIRE(c && buf, "null argument");
     REQUIRE(sel >= LGR_SIZE_K && sel <= LGR_SIZE_N && (dir == LGR_FORWARD || dir == LGR_INVERSE), "bad size selector / direction");
     const Fr &w = sel == LGR_SIZE_K ? c->root_k : (sel == LGR_SIZE_2K ? c->root_2k : c->root_n);
@@ -502,24 +514,24 @@ int lgr_ntt(lgr_ctx *c, void *buf, int sel, int dir) {
     if (rc) return rc;
     return run_ntt(c, (fr_mem *)buf, *p, 1, (size_t)1 << (c->logk + sel));
 }
-int lgr_ntt_pow2(lgr_ctx *c, void *buf, uint32_t logn, uint32_t batch, const uint32_t omega[8], int dir) {
+int lgr_ntt_pow2(lgr_ctx *c, void *buf, uint32_t logn, uint32_t batch, const uint32_t omega[8], int dir) { ENTER(c);
     REQUIRE(c && buf && omega, "null argument");
     REQUIRE(dir == LGR_FORWARD || dir == LGR_INVERSE, "bad direction");
     NttPlan *p; int rc = get_plan(c, (int)logn, host::from_u32(omega), dir == LGR_INVERSE, &p);
     if (rc) return rc;
     return run_ntt(c, (fr_mem *)buf, *p, batch, (size_t)1 << logn);
 }
-int lgr_encode(lgr_ctx *c, void *buf) {
+int lgr_encode(lgr_ctx *c, void *buf) { ENTER(c);
     REQUIRE(c && buf, "null argument");
-    return encode_rows_impl(c, (const fr_mem *)buf, c->n, 1, (fr_mem *)buf, c->stream);
+    return encode_rows_impl(c, (const fr_mem *)buf, c->n, 1, plain_sink((fr_mem *)buf, c->n), c->stream);
 }
-int lgr_encode_rows(lgr_ctx *c, const void *rows, uint64_t row_stride, uint32_t nrows, void *cw) {
+int lgr_encode_rows(lgr_ctx *c, const void *rows, uint64_t row_stride, uint32_t nrows, void *cw) { ENTER(c);
     REQUIRE(c && rows && cw, "null argument");
     REQUIRE(row_stride >= c->k, "row stride smaller than k");
     REQUIRE(rows != cw || row_stride == c->n, "in-place encode needs a row stride of n elements");
-    return encode_rows_impl(c, (const fr_mem *)rows, row_stride, nrows, (fr_mem *)cw, c->stream);
+    return encode_rows_impl(c, (const fr_mem *)rows, row_stride, nrows, plain_sink((fr_mem *)cw, c->n), c->stream);
 }
-int lgr_decode(lgr_ctx *c, void *buf) {
+int lgr_decode(lgr_ctx *c, void *buf) { ENTER(c);
     REQUIRE(c && buf, "null argument");
     NttPlan *pi, *pf; int rc;
     if ((rc = get_plan(c, c->logk + 2, c->root_n, true, &pi))) return rc;
@@ -533,24 +545,30 @@ int lgr_decode(lgr_ctx *c, void *buf) {
 
 // ---- hashing -----------------------------------------------------------------------------------
 size_t lgr_sha_ctx_bytes(uint32_t ninst) { return sha_ctx_words(ninst) * 4; }
-int lgr_sha_init(lgr_ctx *c, void *s, uint32_t ninst) {
+int lgr_sha_init(lgr_ctx *c, void *s, uint32_t ninst) { ENTER(c);
     REQUIRE(c && s, "null argument");
+    REQUIRE(ninst > 0 && ninst < (1u << 30), "sha256: instance count out of range");
     CU(launch_sha_init((uint32_t *)s, (int)ninst, c->stream)); c->launches++;
     return LGR_OK;
 }
-int lgr_sha_update_rows(lgr_ctx *c, void *s, uint32_t ninst, const void *tile, uint64_t row_stride, uint32_t nrows) {
+int lgr_sha_update_rows(lgr_ctx *c, void *s, uint32_t ninst, const void *tile, uint64_t row_stride, uint32_t nrows) { ENTER(c);
     REQUIRE(c && s && tile, "null argument");
+    REQUIRE(ninst > 0 && ninst < (1u << 30), "sha256: instance count out of range");
+    REQUIRE(row_stride >= ninst, "sha256: row stride smaller than the instance count");
+    REQUIRE(nrows < (1u << 31), "sha256: too many rows in one call");
+    if (!nrows) return LGR_OK;
     CU(launch_sha_update((uint32_t *)s, (int)ninst, (const fr_mem *)tile, (long long)row_stride, (int)nrows, c->stream)); c->launches++;
     return LGR_OK;
 }
-int lgr_sha_update(lgr_ctx *c, void *s, uint32_t ninst, const void *buf) { return lgr_sha_update_rows(c, s, ninst, buf, ninst, 1); }
-int lgr_sha_final(lgr_ctx *c, const void *s, uint32_t ninst, void *digests) {
+int lgr_sha_update(lgr_ctx *c, void *s, uint32_t ninst, const void *buf) { ENTER(c); return lgr_sha_update_rows(c, s, ninst, buf, ninst, 1); }
+int lgr_sha_final(lgr_ctx *c, const void *s, uint32_t ninst, void *digests) { ENTER(c);
     REQUIRE(c && s && digests, "null argument");
+    REQUIRE(ninst > 0 && ninst < (1u << 30), "sha256: instance count out of range");
     CU(launch_sha_final((const uint32_t *)s, (int)ninst, (uint32_t *)digests, c->stream)); c->launches++;
     return LGR_OK;
 }
 size_t lgr_merkle_node_count(uint32_t nleaves) { size_t p = 1; while (p < nleaves) p <<= 1; return 2 * p - 1; }
-int lgr_merkle_build(lgr_ctx *c, const void *leaf, uint32_t nleaves, void *nodes) {
+int lgr_merkle_build(lgr_ctx *c, const void *leaf, uint32_t nleaves, void *nodes) { ENTER(c);
     REQUIRE(c && leaf && nodes && nleaves, "null argument");
     CU(launch_merkle_build((const uint32_t *)leaf, (int)nleaves, (uint32_t *)nodes, c->stream));
     int P2 = 1, lv = 1; while (P2 < (int)nleaves) P2 <<= 1;
@@ -575,30 +593,30 @@ static int elt(lgr_ctx *c, EltOp op, const void *x, const void *y, const void *z
     CU(launch_eltwise(op, p, c->stream)); c->launches++;
     return LGR_OK;
 }
-int lgr_elt_add(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_ADD, x, y, 0, o, n, 0, false); }
-int lgr_elt_sub(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_SUB, x, y, 0, o, n, 0, false); }
-int lgr_elt_mul(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_MUL, x, y, 0, o, n, 0, false); }
-int lgr_elt_div(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_DIV, x, y, 0, o, n, 0, false); }
-int lgr_elt_fma(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { REQUIRE(x && y, "null argument"); return elt(c, ELT_FMA, x, y, 0, o, n, 0, false); }
-int lgr_elt_fma_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_FMA_CONST, x, 0, 0, o, n, k, true); }
-int lgr_elt_add_assign(lgr_ctx *c, const void *x, void *o, size_t n) { REQUIRE(x, "null argument"); return elt(c, ELT_ADD_ASSIGN, x, 0, 0, o, n, 0, false); }
-int lgr_elt_add_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_ADD_CONST, x, 0, 0, o, n, k, false); }
-int lgr_elt_sub_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_SUB_CONST, x, 0, 0, o, n, k, false); }
-int lgr_elt_const_sub(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_CONST_SUB, x, 0, 0, o, n, k, false); }
-int lgr_elt_mul_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_MUL_CONST, x, 0, 0, o, n, k, true); }
-int lgr_elt_montmul_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { REQUIRE(x && k, "null argument"); return elt(c, ELT_MONTMUL_CONST, x, 0, 0, o, n, k, false); }
-int lgr_elt_bit(lgr_ctx *c, const void *x, void *o, size_t n, uint32_t bit) { REQUIRE(x, "null argument"); REQUIRE(bit < 256, "bit index out of range"); return elt(c, ELT_BIT, x, 0, 0, o, n, 0, false, nullptr, bit); }
-int lgr_elt_powmod(lgr_ctx *c, const void *coeff, const void *exp, void *o, size_t n, const uint32_t base[8], int add) {
+int lgr_elt_add(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { ENTER(c); REQUIRE(x && y, "null argument"); return elt(c, ELT_ADD, x, y, 0, o, n, 0, false); }
+int lgr_elt_sub(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { ENTER(c); REQUIRE(x && y, "null argument"); return elt(c, ELT_SUB, x, y, 0, o, n, 0, false); }
+int lgr_elt_mul(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { ENTER(c); REQUIRE(x && y, "null argument"); return elt(c, ELT_MUL, x, y, 0, o, n, 0, false); }
+int lgr_elt_div(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { ENTER(c); REQUIRE(x && y, "null argument"); return elt(c, ELT_DIV, x, y, 0, o, n, 0, false); }
+int lgr_elt_fma(lgr_ctx *c, const void *x, const void *y, void *o, size_t n) { ENTER(c); REQUIRE(x && y, "null argument"); return elt(c, ELT_FMA, x, y, 0, o, n, 0, false); }
+int lgr_elt_fma_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { ENTER(c); REQUIRE(x && k, "null argument"); return elt(c, ELT_FMA_CONST, x, 0, 0, o, n, k, true); }
+int lgr_elt_add_assign(lgr_ctx *c, const void *x, void *o, size_t n) { ENTER(c); REQUIRE(x, "null argument"); return elt(c, ELT_ADD_ASSIGN, x, 0, 0, o, n, 0, false); }
+int lgr_elt_add_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { ENTER(c); REQUIRE(x && k, "null argument"); return elt(c, ELT_ADD_CONST, x, 0, 0, o, n, k, false); }
+int lgr_elt_sub_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { ENTER(c); REQUIRE(x && k, "null argument"); return elt(c, ELT_SUB_CONST, x, 0, 0, o, n, k, false); }
+int lgr_elt_const_sub(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { ENTER(c); REQUIRE(x && k, "null argument"); return elt(c, ELT_CONST_SUB, x, 0, 0, o, n, k, false); }
+int lgr_elt_mul_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { ENTER(c); REQUIRE(x && k, "null argument"); return elt(c, ELT_MUL_CONST, x, 0, 0, o, n, k, true); }
+int lgr_elt_montmul_const(lgr_ctx *c, const void *x, void *o, size_t n, const uint32_t k[8]) { ENTER(c); REQUIRE(x && k, "null argument"); return elt(c, ELT_MONTMUL_CONST, x, 0, 0, o, n, k, false); }
+int lgr_elt_bit(lgr_ctx *c, const void *x, void *o, size_t n, uint32_t bit) { ENTER(c); REQUIRE(x, "null argument"); REQUIRE(bit < 256, "bit index out of range"); return elt(c, ELT_BIT, x, 0, 0, o, n, 0, false, nullptr, bit); }
+int lgr_elt_powmod(lgr_ctx *c, const void *coeff, const void *exp, void *o, size_t n, const uint32_t base[8], int add) { ENTER(c);
     REQUIRE(coeff && exp && base, "null argument");
     return elt(c, add ? ELT_POWADD : ELT_POWMOD, coeff, 0, 0, o, n, base, true, exp);
 }
-int lgr_elt_quad(lgr_ctx *c, const void *x, const void *y, const void *z, void *o, size_t n, const uint32_t r[8]) {
+int lgr_elt_quad(lgr_ctx *c, const void *x, const void *y, const void *z, void *o, size_t n, const uint32_t r[8]) { ENTER(c);
     REQUIRE(x && y && z && r, "null argument");
     return elt(c, ELT_QUAD_FUSED, x, y, z, o, n, r, true);
 }
 
 // ---- sampling ----------------------------------------------------------------------------------
-int lgr_sample_init(lgr_ctx *c, const uint64_t *idx, uint32_t count) {
+int lgr_sample_init(lgr_ctx *c, const uint64_t *idx, uint32_t count) { ENTER(c);
     REQUIRE(c && (idx || !count), "null argument");
     if (c->sample_idx) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->sample_idx)); c->sample_idx = nullptr; }
     c->sample_count = count;
@@ -609,12 +627,12 @@ int lgr_sample_init(lgr_ctx *c, const uint64_t *idx, uint32_t count) {
     CU(cudaMemcpy(c->sample_idx, v.data(), count * 4, cudaMemcpyHostToDevice));
     return LGR_OK;
 }
-int lgr_sample_gather(lgr_ctx *c, const void *x, void *out) {
+int lgr_sample_gather(lgr_ctx *c, const void *x, void *out) { ENTER(c);
     REQUIRE(c && x && out, "null argument");
     REQUIRE(c->sample_idx, "sampling_init has not been called");
     return elt(c, ELT_GATHER, x, 0, 0, out, c->sample_count, 0, false, c->sample_idx);
 }
-int lgr_sample_gather_rows(lgr_ctx *c, const void *tile, uint64_t row_stride, uint32_t nrows, void *out) {
+int lgr_sample_gather_rows(lgr_ctx *c, const void *tile, uint64_t row_stride, uint32_t nrows, void *out) { ENTER(c);
     REQUIRE(c && tile && out, "null argument");
     REQUIRE(c->sample_idx, "sampling_init has not been called");
     CU(launch_gather_rows((const fr_mem *)tile, (long long)row_stride, (int)nrows, c->sample_idx, (int)c->sample_count, (fr_mem *)out, c->stream)); c->launches++;
@@ -674,7 +692,7 @@ static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host
         if (overlap && tile_idx >= 2) CU(cudaStreamWaitEvent(es, c->ev_hash[b], 0));     // codeword buffer free again
         cudaEvent_t p0 = nullptr, p1 = nullptr;
         if (c->profiling) { p0 = prof_event(c); p1 = prof_event(c); CU(cudaEventRecord(p0, es)); }
-        if ((rc = encode_rows_impl(c, src, k, t, c->tile[b], es))) return rc;
+        if ((rc = encode_rows_impl(c, src, k, t, plain_sink(c->tile[b], (long long)n), es))) return rc;
         if (c->profiling) { CU(cudaEventRecord(p1, es)); c->prof_enc.emplace_back(p0, p1); }
         if (host_rows) CU(cudaEventRecord(c->ev_h2d_free[b], es));
         if (overlap) { CU(cudaEventRecord(c->ev_enc[b], es)); CU(cudaStreamWaitEvent(hs, c->ev_enc[b], 0)); }
@@ -693,18 +711,18 @@ static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host
     return LGR_OK;
 }
 
-int lgr_encode_commit(lgr_ctx *c, const void *rows, uint64_t nrows, void *digests, void *nodes) {
+int lgr_encode_commit(lgr_ctx *c, const void *rows, uint64_t nrows, void *digests, void *nodes) { ENTER(c);
     REQUIRE(c && rows && digests, "null argument");
     return encode_commit_impl(c, (const fr_mem *)rows, nullptr, nrows, digests, nodes);
 }
 
-int lgr_encode_absorb(lgr_ctx *c, void *sha_ctx, const void *rows, uint64_t nrows) {
+int lgr_encode_absorb(lgr_ctx *c, void *sha_ctx, const void *rows, uint64_t nrows) { ENTER(c);
     REQUIRE(c && sha_ctx && rows, "null argument");
     if (!nrows) return LGR_OK;
     return encode_commit_impl(c, (const fr_mem *)rows, nullptr, nrows, nullptr, nullptr, (uint32_t *)sha_ctx);
 }
 
-int lgr_encode_commit_host(lgr_ctx *c, const void *host_rows, uint64_t nrows, void *host_digests, void *host_root) {
+int lgr_encode_commit_host(lgr_ctx *c, const void *host_rows, uint64_t nrows, void *host_digests, void *host_root) { ENTER(c);
     REQUIRE(c && host_rows && (host_digests || host_root), "null argument");
     const size_t n = c->n;
     const size_t need = n + (2 * n - 1);                // digests + nodes, in elements of 32 bytes
@@ -720,8 +738,8 @@ int lgr_encode_commit_host(lgr_ctx *c, const void *host_rows, uint64_t nrows, vo
     return LGR_OK;
 }
 
-int lgr_profile(lgr_ctx *c, int enable) { REQUIRE(c, "null context"); c->profiling = enable != 0; return LGR_OK; }
-int lgr_profile_read(lgr_ctx *c, double *enc_ms, uint64_t *enc_launches, double *sha_ms, uint64_t *sha_launches) {
+int lgr_profile(lgr_ctx *c, int enable) { ENTER(c); REQUIRE(c, "null context"); c->profiling = enable != 0; return LGR_OK; }
+int lgr_profile_read(lgr_ctx *c, double *enc_ms, uint64_t *enc_launches, double *sha_ms, uint64_t *sha_launches) { ENTER(c);
     REQUIRE(c && enc_ms && enc_launches && sha_ms && sha_launches, "null argument");
     CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(c->aux_stream));
     double acc[2] = {0, 0};
@@ -743,7 +761,7 @@ static int upload_scalars(lgr_ctx *c, const uint32_t *host_r, uint32_t nrows, si
     for (uint32_t i = 0; i < nrows; i++) REQUIRE(host::is_canonical(host::from_u32(host_r + 8 * i)), "scalar is not reduced modulo p");
     return lgr_write(c, c->scratch + at, 0, host_r, (size_t)nrows * 32);
 }
-int lgr_combine_code(lgr_ctx *c, const void *tile, uint32_t nrows, const uint32_t *host_r, void *acc) {
+int lgr_combine_code(lgr_ctx *c, const void *tile, uint32_t nrows, const uint32_t *host_r, void *acc) { ENTER(c);
     REQUIRE(c && tile && host_r && acc, "null argument");
     if (!nrows) return LGR_OK;
     const size_t part = combine_scratch_elems((int)nrows, (int)c->n);
@@ -754,10 +772,10 @@ int lgr_combine_code(lgr_ctx *c, const void *tile, uint32_t nrows, const uint32_
     c->launches += 3;
     return LGR_OK;
 }
-int lgr_combine_quad(lgr_ctx *c, const void *x, const void *y, const void *z, uint32_t nrows, const uint32_t *host_r, void *acc) {
+int lgr_combine_quad(lgr_ctx *c, const void *x, const void *y, const void *z, uint32_t nrows, const uint32_t *host_r, void *acc) { ENTER(c);
     return lgr_combine_quad_rows(c, x, y, z, c ? c->n : 0, nrows, host_r, acc);
 }
-int lgr_combine_quad_rows(lgr_ctx *c, const void *x, const void *y, const void *z, uint64_t row_stride, uint32_t nrows, const uint32_t *host_r, void *acc) {
+int lgr_combine_quad_rows(lgr_ctx *c, const void *x, const void *y, const void *z, uint64_t row_stride, uint32_t nrows, const uint32_t *host_r, void *acc) { ENTER(c);
     REQUIRE(c && x && y && z && host_r && acc, "null argument");
     REQUIRE(row_stride >= c->n, "row stride smaller than n");
     if (!nrows) return LGR_OK;
@@ -770,7 +788,7 @@ int lgr_combine_quad_rows(lgr_ctx *c, const void *x, const void *y, const void *
     c->launches += 4;
     return LGR_OK;
 }
-int lgr_combine_quad_indexed(lgr_ctx *c, const void *tile, const uint32_t *host_x_rows, uint32_t ntriples, const uint32_t *host_r, void *acc) {
+int lgr_combine_quad_indexed(lgr_ctx *c, const void *tile, const uint32_t *host_x_rows, uint32_t ntriples, const uint32_t *host_r, void *acc) { ENTER(c);
     REQUIRE(c && tile && host_x_rows && host_r && acc, "null argument");
     if (!ntriples) return LGR_OK;
     const size_t part = combine_scratch_elems((int)ntriples, (int)c->n);
@@ -786,7 +804,7 @@ int lgr_combine_quad_indexed(lgr_ctx *c, const void *tile, const uint32_t *host_
     c->launches += 4;
     return LGR_OK;
 }
-int lgr_combine_linear(lgr_ctx *c, const void *a, const void *b, uint32_t nrows, void *acc) {
+int lgr_combine_linear(lgr_ctx *c, const void *a, const void *b, uint32_t nrows, void *acc) { ENTER(c);
     REQUIRE(c && a && b && acc, "null argument");
     if (!nrows) return LGR_OK;
     const size_t part = combine_scratch_elems((int)nrows, (int)c->n);
@@ -797,13 +815,73 @@ int lgr_combine_linear(lgr_ctx *c, const void *a, const void *b, uint32_t nrows,
     return LGR_OK;
 }
 
+// ---- exact multi-GPU layout: slab-major codewords, peer memory, hand-over flags -------------------
+int lgr_encode_rows_slabs(lgr_ctx *c, const void *rows, uint64_t row_stride, uint32_t nrows, void *const *slab_base, uint32_t nslabs) {
+    ENTER(c);
+    REQUIRE(rows && slab_base, "null argument");
+    REQUIRE(row_stride >= c->k, "row stride smaller than k");
+    REQUIRE(nslabs >= 1 && nslabs <= 8 && (nslabs & (nslabs - 1)) == 0 && c->n % nslabs == 0, "slab count must be 1, 2, 4 or 8");
+    CodewordSink s{};
+    s.nslabs = (int)nslabs;
+    s.slab_shift = ilog2u(c->n / nslabs);
+    s.row_stride = (long long)(c->n / nslabs);
+    for (uint32_t h = 0; h < nslabs; h++) { REQUIRE(slab_base[h], "null slab base"); s.base[h] = (fr_mem *)slab_base[h]; }
+    return encode_rows_impl(c, (const fr_mem *)rows, row_stride, nrows, s, c->stream);
+}
+int lgr_ipc_alloc(lgr_ctx *c, size_t bytes, void **dptr, unsigned char handle[64]) {
+    ENTER(c);
+    REQUIRE(dptr && handle && bytes, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    CU(cudaMalloc(dptr, bytes));                               // IPC needs a cudaMalloc allocation (not the stream-ordered pool)
+    CU(cudaMemset(*dptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dptr);
+    if (e != cudaSuccess) { cudaFree(*dptr); *dptr = nullptr; return fail(LGR_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(handle, &h, 64);
+    return LGR_OK;
+}
+int lgr_ipc_open(lgr_ctx *c, const unsigned char handle[64], void **dptr) {
+    ENTER(c);
+    REQUIRE(dptr && handle, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return LGR_OK;
+}
+int lgr_ipc_close(lgr_ctx *c, void *dptr) {
+    ENTER(c);
+    if (dptr) { CU(cudaDeviceSynchronize()); CU(cudaIpcCloseMemHandle(dptr)); }
+    return LGR_OK;
+}
+int lgr_ipc_free(lgr_ctx *c, void *dptr) {
+    ENTER(c);
+    if (dptr) { CU(cudaDeviceSynchronize()); CU(cudaFree(dptr)); }
+    return LGR_OK;
+}
+int lgr_peer_signal(lgr_ctx *c, void *const *slots, uint32_t nslots, uint64_t value) {
+    ENTER(c);
+    REQUIRE(slots && nslots <= 8, "at most 8 peers");
+    PeerSlots s{};
+    s.n = (int)nslots;
+    for (uint32_t i = 0; i < nslots; i++) { REQUIRE(slots[i], "null flag slot"); s.p[i] = (unsigned long long *)slots[i]; }
+    CU(launch_peer_signal(s, value, c->stream)); c->launches++;
+    return LGR_OK;
+}
+int lgr_peer_wait(lgr_ctx *c, const void *flags, uint32_t nflags, uint64_t value, uint32_t timeout_ms, void *err_flag) {
+    ENTER(c);
+    REQUIRE(flags && err_flag && nflags <= 32, "bad arguments");
+    CU(launch_peer_wait((const unsigned long long *)flags, (int)nflags, value, (unsigned long long)timeout_ms * 1000000ull, (unsigned int *)err_flag, c->stream));
+    c->launches++;
+    return LGR_OK;
+}
+
 // ---- synthetic data / micro-benchmarks ---------------------------------------------------------
-int lgr_synth(lgr_ctx *c, void *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols) {
+int lgr_synth(lgr_ctx *c, void *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols) { ENTER(c);
     REQUIRE(c && out, "null argument");
     CU(launch_synth((fr_mem *)out, seed, row0, nrows, ncols, c->stream)); c->launches++;
     return LGR_OK;
 }
-int lgr_ubench(lgr_ctx *c, int which, double *ops) {
+int lgr_ubench(lgr_ctx *c, int which, double *ops) { ENTER(c);
     REQUIRE(c && ops, "null argument");
     REQUIRE(which >= 0 && which <= 5, "unknown micro-benchmark");
     uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
@@ -826,7 +904,7 @@ int lgr_ubench(lgr_ctx *c, int which, double *ops) {
 
 // Montgomery multiplications per second with `warps_per_sm` resident warps and `nchain` independent
 // multiplications per thread (occupancy / ILP sweep)
-int lgr_ubench_mont_occ(lgr_ctx *c, int nchain, int warps_per_sm, double *ops) {
+int lgr_ubench_mont_occ(lgr_ctx *c, int nchain, int warps_per_sm, double *ops) { ENTER(c);
     REQUIRE(c && ops, "null argument");
     REQUIRE((nchain == 1 || nchain == 2 || nchain == 4) && warps_per_sm >= 1 && warps_per_sm <= 32, "bad arguments");
     uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 1024 * 4));
@@ -845,7 +923,7 @@ int lgr_ubench_mont_occ(lgr_ctx *c, int nchain, int warps_per_sm, double *ops) {
 }
 
 // cycles per SHA-256 compression of one warp owning a scheduler (variant 3/4/5, see ubench.cu)
-int lgr_ubench_chain(lgr_ctx *c, int variant, int warps_per_cta, int active_lanes, double *cycles) {
+int lgr_ubench_chain(lgr_ctx *c, int variant, int warps_per_cta, int active_lanes, double *cycles) { ENTER(c);
     REQUIRE(c && cycles, "null argument");
     REQUIRE(variant >= 3 && variant <= 25 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
     uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));

@@ -4,7 +4,7 @@
 
 namespace lgr {
 
-#define LGR_DECL_ENC(L) cudaError_t launch_encode_rows_##L(const fr_mem *, long long, fr_mem *, long long, int, const EncodeTables &, cudaStream_t);
+#define LGR_DECL_ENC(L) cudaError_t launch_encode_rows_##L(const fr_mem *, long long, const CodewordSink &, int, const EncodeTables &, cudaStream_t);
 LGR_DECL_ENC(3) LGR_DECL_ENC(4) LGR_DECL_ENC(5) LGR_DECL_ENC(6) LGR_DECL_ENC(7) LGR_DECL_ENC(8) LGR_DECL_ENC(9) LGR_DECL_ENC(10) LGR_DECL_ENC(11)
 #define LGR_DECL_NTT(L) cudaError_t launch_ntt_tile_##L(const NttTileParams &, cudaStream_t);
 LGR_DECL_NTT(1) LGR_DECL_NTT(2) LGR_DECL_NTT(3) LGR_DECL_NTT(4) LGR_DECL_NTT(5) LGR_DECL_NTT(6) LGR_DECL_NTT(7) LGR_DECL_NTT(8) LGR_DECL_NTT(9) LGR_DECL_NTT(10) LGR_DECL_NTT(11)
@@ -13,11 +13,11 @@ int encode_rows_max_logk() { return 11; }
 int encode_rows_min_logk() { return 3; }
 int ntt_tile_max_logm() { return 11; }
 
-cudaError_t launch_encode_rows(const fr_mem *rows_in, long long in_row_stride, fr_mem *out, long long out_row_stride, int R,
+cudaError_t launch_encode_rows(const fr_mem *rows_in, long long in_row_stride, const CodewordSink &sink, int R,
                                int logk, const EncodeTables &t, cudaStream_t st) {
     if (R <= 0) return cudaSuccess;
     switch (logk) {
-#define LGR_CASE_ENC(L) case L: return launch_encode_rows_##L(rows_in, in_row_stride, out, out_row_stride, R, t, st);
+#define LGR_CASE_ENC(L) case L: return launch_encode_rows_##L(rows_in, in_row_stride, sink, R, t, st);
         LGR_CASE_ENC(3) LGR_CASE_ENC(4) LGR_CASE_ENC(5) LGR_CASE_ENC(6) LGR_CASE_ENC(7) LGR_CASE_ENC(8) LGR_CASE_ENC(9) LGR_CASE_ENC(10) LGR_CASE_ENC(11)
         default: return cudaErrorInvalidValue;
     }

@@ -280,21 +280,21 @@ cudaError_t launch_combine_quad(const fr_mem *x, const fr_mem *y, const fr_mem *
 // out[row][4m] = rows[row][c*m mod k] reduced to [0,p): w_n^4 = w_k^c, so the codeword positions 4m are
 // the message evaluations themselves (api.cu: find_sys_mul).  Writes are 32-byte sectors 128 bytes apart;
 // the other three cosets fill the gaps right after, while the lines are still in L2.
-__global__ void __launch_bounds__(256) sys_copy_kernel(const fr_mem *__restrict__ rows, long long row_stride, fr_mem *__restrict__ out,
-                                                       long long out_row_stride, long long total, int logk, uint32_t c) {
+__global__ void __launch_bounds__(256) sys_copy_kernel(const fr_mem *__restrict__ rows, long long row_stride, const __grid_constant__ CodewordSink sink,
+                                                       long long total, int logk, uint32_t c) {
     const uint32_t mask = (1u << logk) - 1u;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long row = i >> logk;
         const uint32_t m = (uint32_t)i & mask;
         const fr_t x = fr_ldg(rows + row * row_stride + ((m * c) & mask));
-        fr_stg(out + row * out_row_stride + 4ll * m, fr_reduce_p(fr_reduce_2p(fr_reduce_2p(x))));
+        fr_stg(sink_at(sink, row, (int)(4u * m)), fr_reduce_p(fr_reduce_2p(fr_reduce_2p(x))));
     }
 }
-cudaError_t launch_sys_copy(const fr_mem *rows, long long row_stride, fr_mem *out, long long out_row_stride, int R, int logk, uint32_t c, cudaStream_t st) {
+cudaError_t launch_sys_copy(const fr_mem *rows, long long row_stride, const CodewordSink &sink, int R, int logk, uint32_t c, cudaStream_t st) {
     if (R <= 0) return cudaSuccess;
     const long long total = (long long)R << logk;
     const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-    sys_copy_kernel<<<grid, 256, 0, st>>>(rows, row_stride, out, out_row_stride, total, logk, c);
+    sys_copy_kernel<<<grid, 256, 0, st>>>(rows, row_stride, sink, total, logk, c);
     return cudaGetLastError();
 }
 

@@ -40,8 +40,7 @@ template <int LOGK> struct enc_cfg {
 
 template <int LOGK>
 __global__ void __launch_bounds__(enc_cfg<LOGK>::THREADS, (enc_cfg<LOGK>::SMEM <= 72 * 1024) ? 3 : ((enc_cfg<LOGK>::SMEM <= 110 * 1024) ? 2 : 1)) encode_rows_kernel(
-    const fr_mem *__restrict__ rows_in, long long in_row_stride, fr_mem *__restrict__ out, long long out_row_stride, int R,
-    const EncodeTables t) {
+    const fr_mem *__restrict__ rows_in, long long in_row_stride, const __grid_constant__ CodewordSink sink, int R, const EncodeTables t) {
     using cfg = enc_cfg<LOGK>;
     constexpr int K = cfg::K, TL = cfg::TL;
     extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -61,7 +60,7 @@ __global__ void __launch_bounds__(enc_cfg<LOGK>::THREADS, (enc_cfg<LOGK>::SMEM <
     //   pass t = 1..    : coset r: the first pass reads C[bitrev(q)] and applies the twist w_n^(r*bitrev(q))/k, the last
     //                     pass canonicalises and writes e[4m + r] straight to global memory
     const fr_mem *src = rows_in + (active ? row : 0) * in_row_stride;
-    fr_mem *dst = out + (active ? row : 0) * out_row_stride;
+    const long long drow = active ? row : 0;
     const bool sys = t.sys_mul != 0;
     const int ntrans = sys ? 4 : 5;
     // The message row comes in as ONE bulk copy (TMA, cp.async.bulk global -> shared, k*32 contiguous bytes) issued by the
@@ -105,7 +104,7 @@ __global__ void __launch_bounds__(enc_cfg<LOGK>::THREADS, (enc_cfg<LOGK>::SMEM <
             },
             [&](int m, const fr_t &x) {
                 if (inv) fr_sts(C + m, x);
-                else if (active) fr_stg(dst + 4 * m + r, fr_canon4(x));
+                else if (active) fr_stg(sink_at(sink, drow, 4 * m + r), fr_canon4(x));
             });
         sync();
         // coset r = 0 is the message itself: w_n^4 and w_k generate the same group of k-th roots of unity,
@@ -117,7 +116,7 @@ __global__ void __launch_bounds__(enc_cfg<LOGK>::THREADS, (enc_cfg<LOGK>::SMEM <
                 for (int g = 0; g < 8; g++) {
                     const int m = tl + g * TL;
                     const fr_t x = fr_lds(W + (int)(((unsigned)m * (unsigned)t.sys_mul) & (unsigned)(K - 1)));
-                    fr_stg(dst + 4 * m, fr_reduce_p(fr_reduce_2p(fr_reduce_2p(x))));   // any 256-bit input -> [0,p), as the transforms would
+                    fr_stg(sink_at(sink, drow, 4 * m), fr_reduce_p(fr_reduce_2p(fr_reduce_2p(x))));   // any 256-bit input -> [0,p), as the transforms would
                 }
             }
             sync();
@@ -126,25 +125,28 @@ __global__ void __launch_bounds__(enc_cfg<LOGK>::THREADS, (enc_cfg<LOGK>::SMEM <
 }
 
 template <int LOGK>
-static cudaError_t launch_enc(const fr_mem *rows_in, long long in_row_stride, fr_mem *out, long long out_row_stride, int R,
+static cudaError_t launch_enc(const fr_mem *rows_in, long long in_row_stride, const CodewordSink &sink, int R,
                               const EncodeTables &t, cudaStream_t st) {
     using cfg = enc_cfg<LOGK>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the opt-in above 48 KiB of dynamic shared memory is stored per device: cache it per device id
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(encode_rows_kernel<LOGK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const int grid = (R + cfg::SLOTS - 1) / cfg::SLOTS;
-    encode_rows_kernel<LOGK><<<grid, cfg::THREADS, cfg::SMEM, st>>>(rows_in, in_row_stride, out, out_row_stride, R, t);
+    encode_rows_kernel<LOGK><<<grid, cfg::THREADS, cfg::SMEM, st>>>(rows_in, in_row_stride, sink, R, t);
     return cudaGetLastError();
 }
 
 #define LGR_CAT2(a, b) a##b
 #define LGR_CAT(a, b) LGR_CAT2(a, b)
-cudaError_t LGR_CAT(launch_encode_rows_, LGR_ENC_LOGK)(const fr_mem *rows_in, long long in_row_stride, fr_mem *out, long long out_row_stride,
+cudaError_t LGR_CAT(launch_encode_rows_, LGR_ENC_LOGK)(const fr_mem *rows_in, long long in_row_stride, const CodewordSink &sink,
                                                        int R, const EncodeTables &t, cudaStream_t st) {
-    return launch_enc<LGR_ENC_LOGK>(rows_in, in_row_stride, out, out_row_stride, R, t, st);
+    return launch_enc<LGR_ENC_LOGK>(rows_in, in_row_stride, sink, R, t, st);
 }
 
 }  // namespace lgr

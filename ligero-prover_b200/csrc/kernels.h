@@ -7,6 +7,22 @@ namespace lgr {
 
 struct __align__(32) fr_mem { uint4 lo, hi; };   // one 32-byte element in global or shared memory
 
+// ---- where codewords go ----------------------------------------------------------------------------
+// nslabs == 0: plain row-major [row][n] at base[0], `row_stride` elements between rows.
+// nslabs == G (exact multi-GPU layout, sharding.py): the n columns are cut into G slabs of 2^slab_shift columns;
+// column j of row r goes to base[j >> slab_shift] + r * 2^slab_shift + (j & (2^slab_shift - 1)), i.e. slab h of every
+// row lands row-major [rows][n/G] at base[h] -- which may be PEER memory: the encoder's 256-bit stores then travel
+// over NVLink straight into the buffer the owner of slab h hashes from (no pack pass, no all-to-all kernel).
+struct CodewordSink {
+    fr_mem *base[8];
+    int nslabs;
+    int slab_shift;
+    long long row_stride;
+};
+static inline CodewordSink plain_sink(fr_mem *out, long long row_stride) {
+    CodewordSink s{}; s.base[0] = out; s.nslabs = 0; s.slab_shift = 0; s.row_stride = row_stride; return s;
+}
+
 // ---- generic tile NTT (ntt_kernels.cu) -------------------------------------------------------
 // A "lane" is one M-point transform.  Lane L = outer * lanes_inner + inner lives at
 //   in  + outer*in_outer_stride  + inner*in_lane_stride  + m*in_point_stride
@@ -33,6 +49,7 @@ struct NttTileParams {
     int in_outer_div, out_outer_div, out_sub_base;
     const fr_mem *in_twist;
     long long in_twist_sub_stride, out_sub_stride;
+    CodewordSink sink;       // coset mode only: nslabs > 0 scatters the codeword columns into slabs (out is ignored)
     const fr_mem *scale;     // optional N^-1 * R (Montgomery form)
     int canon;               // 1: outputs reduced to [0,p)
     int in_natural;          // 1: input natural order (bit-reverse on load, DIT); 0 never used here
@@ -47,11 +64,11 @@ struct EncodeTables {
     const fr_mem *twist;     // [4][k]: w_n^(r*bitrev_k(q)) / k * R
     int sys_mul;             // c with w_n^4 = w_k^c (odd, < k): e[4m] = row[c*m mod k]; 0 = unknown, compute coset 0 too
 };
-// rows_in: [R][in_row_stride] elements (first k of each row used); out: [R][n] codewords
-cudaError_t launch_encode_rows(const fr_mem *rows_in, long long in_row_stride, fr_mem *out, long long out_row_stride,
+// rows_in: [R][in_row_stride] elements (first k of each row used); codewords go to `sink`
+cudaError_t launch_encode_rows(const fr_mem *rows_in, long long in_row_stride, const CodewordSink &sink,
                                int R, int logk, const EncodeTables &t, cudaStream_t st);
-// coset 0 of the large-k encoder: out[row][4m] = canonical(rows[row][c*m mod k])
-cudaError_t launch_sys_copy(const fr_mem *rows, long long row_stride, fr_mem *out, long long out_row_stride, int R, int logk, uint32_t c, cudaStream_t st);
+// coset 0 of the large-k encoder: codeword[row][4m] = canonical(rows[row][c*m mod k])
+cudaError_t launch_sys_copy(const fr_mem *rows, long long row_stride, const CodewordSink &sink, int R, int logk, uint32_t c, cudaStream_t st);
 int encode_rows_max_logk();
 int encode_rows_min_logk();
 
@@ -94,6 +111,12 @@ cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long lon
 cudaError_t launch_sha_final(const uint32_t *ctx, int n, uint32_t *digests, cudaStream_t st);
 // nodes: (2*P2-1)*8 u32, P2 = bit_ceil(nleaves)
 cudaError_t launch_merkle_build(const uint32_t *leaf_digests, int nleaves, uint32_t *nodes, cudaStream_t st);
+
+// ---- cross-GPU hand-over flags (peer_kernels.cu) ------------------------------------------------
+struct PeerSlots { unsigned long long *p[8]; int n; };      // one u64 slot per peer (peer memory, CUDA IPC)
+cudaError_t launch_peer_signal(const PeerSlots &slots, unsigned long long value, cudaStream_t st);
+cudaError_t launch_peer_wait(const unsigned long long *flags, int n, unsigned long long value, unsigned long long timeout_ns,
+                             unsigned int *err, cudaStream_t st);
 
 // ---- synthetic witness generator (sha_kernels.cu; bench / tests only) ------------------------
 cudaError_t launch_synth(fr_mem *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols, cudaStream_t st);

@@ -40,6 +40,12 @@ LGR_DEV fr_t fr_ldc(const fr_mem *p) {
     uint4 a = __ldg(&p->lo), b = __ldg(&p->hi); return fr_unpack(a, b);
 }
 
+// address of codeword element (row, column j) in a CodewordSink (kernels.h)
+LGR_DEV fr_mem *sink_at(const CodewordSink &s, long long row, int j) {
+    if (s.nslabs == 0) return s.base[0] + row * s.row_stride + j;
+    return s.base[j >> s.slab_shift] + ((row << s.slab_shift) + (j & ((1 << s.slab_shift) - 1)));
+}
+
 LGR_DEV uint32_t bitrev(uint32_t x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
 
 // One pass over index bits [LO, LO+T) of an M-point transform.  `load(idx)` / `store(idx, x)` move the

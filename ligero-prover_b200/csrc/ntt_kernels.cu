@@ -14,7 +14,7 @@
 namespace lgr {
 
 template <int LOGM>
-__global__ void __launch_bounds__(256, 2) ntt_tile_kernel(const NttTileParams p) {
+__global__ void __launch_bounds__(256, 2) ntt_tile_kernel(const __grid_constant__ NttTileParams p) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     fr_mem *sm = reinterpret_cast<fr_mem *>(smem_raw);
     constexpr int M = 1 << LOGM;
@@ -68,8 +68,11 @@ __global__ void __launch_bounds__(256, 2) ntt_tile_kernel(const NttTileParams p)
             }
             if (p.scale) x = fr_mont_mul(x, fr_ldc(p.scale));           // [0,2p)
             if (p.canon) x = fr_canon4(x);
-            fr_stg(p.out + (long long)orow * p.out_outer_stride + (long long)osub * p.out_sub_stride +
-                       (long long)inner * p.out_lane_stride + (long long)m * p.out_point_stride, x);
+            if (p.sink.nslabs)                                          // coset mode, slab-major codewords (possibly peer memory)
+                fr_stg(sink_at(p.sink, orow, (int)((long long)osub * p.out_sub_stride + (long long)inner * p.out_lane_stride + (long long)m * p.out_point_stride)), x);
+            else
+                fr_stg(p.out + (long long)orow * p.out_outer_stride + (long long)osub * p.out_sub_stride +
+                           (long long)inner * p.out_lane_stride + (long long)m * p.out_point_stride, x);
         }
     }
 }
@@ -81,11 +84,14 @@ static cudaError_t launch_one(const NttTileParams &p, cudaStream_t st) {
     const int threads = p.lanes_per_cta * TL;
     const size_t smem = (size_t)p.lanes_per_cta * M * 32;
     if (threads > 256 || smem > 64 * 1024) return cudaErrorInvalidValue;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the opt-in above 48 KiB of dynamic shared memory is stored per device: cache it per device id
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(ntt_tile_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const int grid = (p.total_lanes + p.lanes_per_cta - 1) / p.lanes_per_cta;
     ntt_tile_kernel<LOGM><<<grid, threads, smem, st>>>(p);

@@ -650,3 +650,155 @@ def test_indexed_quad_combiner_and_row_gather(lgr, oracle, executor_factory):
     out = ex.make_device_buffer(T * 192 * 32)
     ex.sample_gather_rows(tile, T, out)
     assert np.array_equal(ex.read_elements(out).reshape(T, 192, 8), cw[:, idx])
+
+
+# ---------------------------------------------------------------- BASELINE config 2 and the large four-step plans
+def test_config2_ntt_2pow20(lgr, oracle, executor_factory):
+    """BASELINE config 2: 2^20-point NTT then iNTT, w = root1^(2^8), seed 2, 32 MiB in place: NTT = oracle,
+    iNTT = oracle, iNTT(NTT(x)) = x"""
+    ex = executor_factory(256)
+    N = 1 << 20
+    w = lgr.root_of_unity(20)
+    assert w == pow(lgr.ROOT1, 1 << 8, P)
+    x = rand_elems(oracle, 2, N)
+    buf = ex.make_device_buffer(N * 32)
+    ex.write_buffer(buf, x)
+    ex.ntt_pow2(buf, 20, 1, w)
+    f = ex.read_elements(buf)
+    assert np.array_equal(f, oracle.ntt(x, w))
+    ex.ntt_pow2(buf, 20, 1, w, inverse=True)
+    assert np.array_equal(ex.read_elements(buf), x)
+    ex.ntt_pow2(buf, 20, 1, w, inverse=True)
+    assert np.array_equal(ex.read_elements(buf), oracle.ntt(x, w, inverse=True))
+
+
+@pytest.mark.parametrize("logn", [17, 18, 19, 21, 22])
+def test_ntt_pow2_large(lgr, oracle, executor_factory, logn):
+    """four-step plans above 2^16, including the composed twist tables (twist_lo/twist_hi) of 2^21 and 2^22"""
+    ex = executor_factory(256)
+    N = 1 << logn
+    w = lgr.root_of_unity(logn)
+    x = rand_elems(oracle, 300 + logn, N)
+    buf = ex.make_device_buffer(N * 32)
+    ex.write_buffer(buf, x)
+    ex.ntt_pow2(buf, logn, 1, w)
+    f = ex.read_elements(buf)
+    assert np.array_equal(f, oracle.ntt(x, w))
+    ex.ntt_pow2(buf, logn, 1, w, inverse=True)
+    assert np.array_equal(ex.read_elements(buf), x)
+    # linearity spot check that does not go through the oracle: NTT(delta_j)[i] = w^(i*j)
+    d = np.zeros((N, 8), np.uint32)
+    j = 12345 % N
+    d[j, 0] = 1
+    ex.write_buffer(buf, d)
+    ex.ntt_pow2(buf, logn, 1, w)
+    got = lgr.array_to_ints(ex.read_elements(buf)[[0, 1, 2, N // 2 + 1, N - 1]])
+    assert got == [pow(w, i * j, P) for i in (0, 1, 2, N // 2 + 1, N - 1)]
+
+
+@pytest.mark.parametrize("ninst", [192, 5, 48, 1000])
+def test_sha_instance_counts_off_the_fast_path(lgr, oracle, executor_factory, ninst):
+    """192 = the verifier's instance count (sampled columns, src/webgpu_verifier.cpp); others: not a multiple of 16/32"""
+    ex = executor_factory(256)
+    ex.sha256_init(ninst)
+    ctx = ex.make_device_buffer(ex.sha256_context_bytes(ninst))
+    dig = ex.make_device_buffer(ninst * 32)
+    cb = ex.bind_sha256_context(ctx, dig)
+    R = 37
+    rows = oracle.synth(60 + ninst, 0, R, ninst)
+    tile = ex.make_device_buffer(R * ninst * 32)
+    ex.write_buffer(tile, rows)
+    # row by row through the reference's per-row call, then as ragged tiles
+    for chunks in ([1] * R, [5, 2, 30], [36, 1], [R]):
+        ex.sha256_digest_init(cb)
+        s = oracle.Sha(ninst)
+        pos = 0
+        for c in chunks:
+            if c == 1:
+                ex.sha256_digest_update(cb, ex.bind_sha256_buffer(tile.slice(pos * ninst * 32)))
+            else:
+                ex.sha256_digest_update_rows(cb, tile.slice(pos * ninst * 32), c)
+            for r in range(pos, pos + c):
+                s.update(rows[r])
+            pos += c
+        ex.sha256_digest_final(cb)
+        assert np.array_equal(ex.copy_to_host(dig, np.uint8).reshape(ninst, 32), s.final()), chunks
+    ex.sha256_init(1024)
+
+
+# ---------------------------------------------------------------- exact multi-GPU layout, the parts one GPU can check
+@pytest.mark.parametrize("k,R,G", [(256, 70, 2), (256, 33, 8), (64, 9, 4), (2048, 5, 8), (4096, 6, 4), (8192, 3, 8), (8192, 4, 1)])
+def test_encode_rows_slabs_is_the_codeword_cut_into_column_slabs(lgr, oracle, executor_factory, k, R, G):
+    """lgr_encode_rows_slabs: slab h of every row, row-major [R][n/G] at its own base (fused encoder and tile engine)"""
+    ex = executor_factory(k)
+    n = 4 * k
+    slab = n // G
+    rows = oracle.synth(70 + k, 0, R, k)
+    rb = ex.make_device_buffer(R * k * 32)
+    ex.write_buffer(rb, rows)
+    cw = ex.make_device_buffer(R * n * 32)
+    ex.encode_rows(rb, R, cw)
+    plain = ex.read_elements(cw).reshape(R, n, 8)
+    assert np.array_equal(plain[0], oracle.encode(rows[0], k))
+    T = R + 3                                                     # slab chunks are spaced for a larger tile, as in sharding.py
+    out = ex.make_device_buffer(G * T * slab * 32)
+    base = out.ptr().value
+    ex.encode_rows_slabs(rb, R, [base + h * T * slab * 32 for h in range(G)])
+    got = ex.read_elements(out).reshape(G, T, slab, 8)
+    for h in range(G):
+        assert np.array_equal(got[h, :R], plain[:, h * slab:(h + 1) * slab]), h
+        assert not got[h, R:].any()
+
+
+class _OneRankDist:
+    """world-size-1 stand-in for torch.distributed (the hand-over flags and the IPC allocation still run on the device)"""
+    @staticmethod
+    def all_gather_object(out, obj):
+        out[0] = obj
+
+    @staticmethod
+    def all_gather_into_tensor(out, t):
+        out.copy_(t)
+
+
+@pytest.mark.parametrize("k,T,total", [(256, 64, 64 * 5 + 17), (8192, 4, 11)])
+def test_peer_store_engine_single_rank(lgr, oracle, executor_factory, k, T, total):
+    """PeerStoreEngine at G = 1: IPC allocation, slab stores, ready / consumed flags, two commitments back to back"""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("lgr_sharding", os.path.join(os.path.dirname(__file__), "..", "ligero-prover_b200", "sharding.py"))
+    sh = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sh)
+    ex = executor_factory(k)
+    n = 4 * k
+    eng = sh.PeerStoreEngine(ex, T, 1, 0, _OneRankDist)
+    rows = oracle.synth(80 + k, 0, total, k)
+    bufs = []
+    for t0 in range(0, total, T):
+        r = min(T, total - t0)
+        b = ex.make_device_buffer(T * k * 32)
+        ex.write_buffer(b, rows[t0:t0 + r])
+        bufs.append((b, r))
+    want, _, _ = oracle.encode_commit(rows, k)
+    for _ in range(2):
+        leaves = sh.commit_exact(eng, lambda i: bufs[i], total, T, 1, 0, _OneRankDist)
+        torch.cuda.synchronize()
+        assert np.array_equal(leaves.cpu().numpy().view(np.uint8).reshape(n, 32), want)
+    eng.close()
+    ex.sha256_init(1024)
+
+
+def test_peer_wait_times_out_instead_of_hanging(lgr, executor_factory):
+    ex = executor_factory(256)
+    ptr, _ = ex.ipc_alloc(256)
+    ex.peer_wait(ptr, 2, 5, ptr + 128, timeout_ms=50)             # nobody will ever signal: must give up
+    ex.device_synchronize()
+    import torch
+    host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    ex.read_into(host, ptr + 128, 4)
+    assert int(host[0]) != 0
+    ex.peer_signal([ptr, ptr + 8], 5)
+    ex.peer_wait(ptr, 2, 5, ptr + 192, timeout_ms=50)
+    ex.read_into(host, ptr + 192, 4)
+    assert int(host[0]) == 0
+    ex.ipc_free(ptr)

@@ -29,7 +29,7 @@ for t in mine:
     b = ex.make_device_buffer(T * k * 32)
     ex.synth(b, 3, t * T, rows, k)                       # global rows [t*T, t*T+rows)
     bufs.append((b, rows))
-eng = sh.GpuEngine(ex, T, world)
+eng = sh.make_gpu_engine(ex, T, world, rank, dist if world > 1 else None) if world > 1 else sh.GpuEngine(ex, T, world)
 leaves = sh.commit_exact(eng, lambda i: bufs[i], total, T, world, rank, dist if world > 1 else None)
 nodes = ex.make_device_buffer((2 * n - 1) * 32)
 ex.merkle_build(ex.wrap(leaves.contiguous()), n, nodes)
@@ -41,7 +41,7 @@ d1 = ex.make_device_buffer(n * 32); n1 = ex.make_device_buffer((2 * n - 1) * 32)
 ex.encode_commit(whole, total, d1, n1)
 want = ex.copy_to_host(n1, np.uint8)[:32].tobytes().hex()
 ok = root == want and np.array_equal(ex.copy_to_host(d1, np.uint8), leaves.cpu().numpy().view(np.uint8).reshape(-1))
-print("rank", rank, "exact layout root", root[:16], "single-GPU root", want[:16], "MATCH" if ok else "MISMATCH", flush=True)
+print("rank", rank, eng.transport, "exact layout root", root[:16], "single-GPU root", want[:16], "MATCH" if ok else "MISMATCH", flush=True)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
