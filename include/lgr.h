@@ -180,6 +180,9 @@ int lgr_combine_quad_rows(lgr_ctx *ctx, const void *x, const void *y, const void
 /* same for triples scattered over a tile encoded in emission order: triple t occupies codeword rows host_x_rows[t],
  * +1 and +2 of `tile` (row stride n); one launch for any interleaving of linear rows and triples */
 int lgr_combine_quad_indexed(lgr_ctx *ctx, const void *tile, const uint32_t *host_x_rows, uint32_t ntriples, const uint32_t *host_r, void *acc);
+/* on_batch_bit rows (nonbatch_context.hpp:798-808 copies x into y and z before check_quadratic): acc += sum_t r_t *
+ * (x_t*x_t - x_t) for the codeword rows host_rows[t] of `tile` */
+int lgr_combine_bit_indexed(lgr_ctx *ctx, const void *tile, const uint32_t *host_rows, uint32_t count, const uint32_t *host_r, void *acc);
 /* check_linear over two resident tiles: acc[j] += sum_t a[t][j]*b[t][j] (nonbatch_context.hpp:765-769) */
 int lgr_combine_linear(lgr_ctx *ctx, const void *tile_a, const void *tile_b, uint32_t nrows, void *acc);
 

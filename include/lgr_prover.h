@@ -78,18 +78,40 @@ int lgrp_packer_finalize(lgrp_packer *p);
 int lgrp_packer_rows(const lgrp_packer *p, uint64_t *n_events, const uint8_t **kinds, uint64_t *n_rows, const uint32_t **values, const uint32_t **coefs);
 
 /* ---- the three-stage prover over a witness matrix (needs a B200: runs the hot path through lgr.h) -- */
+/* Event kinds.  0 / 1 come from the scalar backend (nonbatch_context.hpp:445-468); 2.. are vbn254fr host calls on
+ * device-resident variables of k elements (include/host_modules/vbn254fr.hpp:139-566) together with the on_batch_*
+ * callback each one triggers (nonbatch_context.hpp:497-553,782-847,996-1047).  Every vbn254fr event reads three u32
+ * from batch_args (variable indices out, x, y -- or the bit index in the third place), constant-taking ones also 8 u32
+ * from batch_consts; LGRP_EV_VSET consumes one row of `values` like a linear event. */
+enum {
+    LGRP_EV_LINEAR = 0,      /* 1 committed row */
+    LGRP_EV_QUAD = 1,        /* 3 committed rows x, y, z */
+    LGRP_EV_VSET = 2,        /* vbn254fr_set_*: out := values row, zero fill; on_batch_init: pads drawn into out[l..k), 1 row */
+    LGRP_EV_VCOPY = 3,       /* vbn254fr_copy: out := in; on_batch_equal(out, in): 2 rows */
+    LGRP_EV_VADD = 4,        /* out := x + y */
+    LGRP_EV_VSUB = 5,        /* out := x - y */
+    LGRP_EV_VMUL = 6,        /* tmp := x*y; on_batch_quadratic(x, y, tmp): 3 rows; out := tmp */
+    LGRP_EV_VDIV = 7,        /* tmp := x/y; on_batch_quadratic(tmp, y, x): 3 rows; out := tmp */
+    LGRP_EV_VASSERT_EQ = 8,  /* on_batch_equal(x = arg0, y = arg1): 2 rows */
+    LGRP_EV_VBIT = 9,        /* tmp := bit arg2 of x; out := tmp; on_batch_bit(out): 1 row */
+    LGRP_EV_VADDC = 10, LGRP_EV_VSUBC = 11, LGRP_EV_VCSUB = 12, LGRP_EV_VMULC = 13, LGRP_EV_VMONTMULC = 14   /* out := x (op) constant */
+};
+
 typedef struct {
     uint32_t l, k;                 /* must match the context (n = 4k) */
-    uint64_t n_events;             /* row events in emission order */
-    const uint8_t *kinds;          /* n_events bytes: 0 = linear row (1 encoded row), 1 = quadratic triple (rows x, y, z) */
-    const uint32_t *values;        /* encoded rows in emission order: [rows][l][8 x u32], canonical */
-    const uint32_t *coefs;         /* linear-test coefficient rows, same shape; NULL = all zero */
+    uint64_t n_events;             /* events in emission order */
+    const uint8_t *kinds;          /* n_events bytes, LGRP_EV_* */
+    const uint32_t *values;        /* host rows in event order (1 per linear / VSET event, 3 per triple): [rows][l][8 x u32], canonical */
+    const uint32_t *coefs;         /* linear-test coefficient rows, same shape (ignored for VSET rows); NULL = all zero */
     uint32_t const_sum[8];         /* linear test constant (zkp/common.hpp:68-79) */
     uint8_t encoding_seed[32];     /* AES-CTR key of the padding / mask stream (src/webgpu_prover.cpp:239-263) */
     uint8_t instance_hash[32];     /* src/webgpu_prover.cpp:161-168 */
     uint8_t program_hash[32];      /* metadata only */
     int64_t generated_at_seconds;  /* metadata; < 0 = wall clock */
     uint32_t sample_size;          /* params::sample_size = 192 */
+    uint32_t arena_slots;          /* vbn254fr variables (0 when there are no LGRP_EV_V* events) */
+    const uint32_t *batch_args;    /* 3 u32 per vbn254fr event, in event order */
+    const uint32_t *batch_consts;  /* 8 u32 per constant-taking vbn254fr event, in event order */
 } lgrp_statement;
 
 int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);

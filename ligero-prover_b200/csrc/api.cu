@@ -804,6 +804,23 @@ int lgr_combine_quad_indexed(lgr_ctx *c, const void *tile, const uint32_t *host_
     c->launches += 4;
     return LGR_OK;
 }
+int lgr_combine_bit_indexed(lgr_ctx *c, const void *tile, const uint32_t *host_rows, uint32_t count, const uint32_t *host_r, void *acc) {
+    ENTER(c);
+    REQUIRE(tile && host_rows && host_r && acc, "null argument");
+    if (!count) return LGR_OK;
+    const size_t part = combine_scratch_elems((int)count, (int)c->n);
+    const size_t idx_elems = ((size_t)count * 4 + 31) / 32;
+    int rc = ensure_scratch(c, part + 3 * (size_t)count + idx_elems);
+    if (rc) return rc;
+    if ((rc = upload_scalars(c, host_r, count, part + 2 * (size_t)count))) return rc;
+    fr_mem *idx = c->scratch + part + 3 * (size_t)count;
+    if ((rc = lgr_write(c, idx, 0, host_rows, (size_t)count * 4))) return rc;
+    const fr_mem *x = (const fr_mem *)tile;                                 // x = y = z: r (x*x - x), what on_batch_bit's copies give check_quadratic
+    CU(launch_combine_quad(x, x, x, (long long)c->n, (int)count, (int)c->n, c->scratch + part + 2 * (size_t)count,
+                           (fr_mem *)acc, c->scratch, part + 2 * (size_t)count, c->stream, (const uint32_t *)idx));
+    c->launches += 4;
+    return LGR_OK;
+}
 int lgr_combine_linear(lgr_ctx *c, const void *a, const void *b, uint32_t nrows, void *acc) { ENTER(c);
     REQUIRE(c && a && b && acc, "null argument");
     if (!nrows) return LGR_OK;

@@ -31,13 +31,44 @@ namespace ligero::cuda::host {
 
 using limbs = uint32_t[8];
 
-// One row event, in emission order: a linear row (1 encoded row) or a quadratic triple
-// (3 encoded rows x, y, z).  Pointers are to l canonical elements (8 x u32 each); coef = the row of
-// linear-test coefficients the backend accumulated for these witnesses (witness_manager.hpp:141-171).
+// One event, in emission order.
+//   EV_LINEAR / EV_QUAD: a linear row (1 encoded row) or a quadratic triple (3 encoded rows x, y, z) from the scalar
+//     backend.  Pointers are to l canonical elements (8 x u32 each); coef = the row of linear-test coefficients the
+//     backend accumulated for these witnesses (witness_manager.hpp:141-171).
+//   EV_V*: a vbn254fr host call (include/host_modules/vbn254fr.hpp:139-566) on DEVICE-RESIDENT variables of k elements
+//     each (`arg` = arena slot indices), with the on_batch_* callback it triggers
+//     (nonbatch_context.hpp:497-553 stage 1, :782-847 stage 2, :996-1047 stage 3):
+//       VSET   out            write_buffer_clear(out, val[0]); on_batch_init(out): 192 pads from the encoding stream are
+//                             written INTO the variable at [l, k), then 1 row is committed       [code: 1 draw]
+//       VCOPY  out, in        out = in; on_batch_equal(out, in): 2 rows                          [quad += r (x - y)]
+//       VASSERT_EQ x, y       on_batch_equal(x, y): 2 rows                                       [quad += r (x - y)]
+//       VMUL   out, x, y      tmp = x*y; on_batch_quadratic(x, y, tmp): 3 rows; out = tmp        [code: 3 draws, quad += r (xy - z)]
+//       VDIV   out, x, y      tmp = x/y; on_batch_quadratic(tmp, y, x): 3 rows; out = tmp
+//       VBIT   out, x, bit    tmp = bit `bit` of x; out = tmp; on_batch_bit(out): 1 row          [code: 1 draw, quad += r (x*x - x)]
+//       VADD / VSUB out, x, y and VADDC / VSUBC / VCSUB / VMULC / VMONTMULC out, x, konst: arithmetic only, no row
+//     All arithmetic runs over the whole k elements, pads included, exactly as the reference's arena kernels do.
+enum event_kind : uint8_t {
+    EV_LINEAR = 0, EV_QUAD = 1, EV_VSET = 2, EV_VCOPY = 3, EV_VADD = 4, EV_VSUB = 5, EV_VMUL = 6, EV_VDIV = 7, EV_VASSERT_EQ = 8,
+    EV_VBIT = 9, EV_VADDC = 10, EV_VSUBC = 11, EV_VCSUB = 12, EV_VMULC = 13, EV_VMONTMULC = 14, EV_KIND_COUNT = 15
+};
+inline int event_rows(uint8_t kind) {            // encoded (committed) rows of an event
+    switch (kind) {
+        case EV_LINEAR: case EV_VSET: case EV_VBIT: return 1;
+        case EV_VCOPY: case EV_VASSERT_EQ: return 2;
+        case EV_QUAD: case EV_VMUL: case EV_VDIV: return 3;
+        default: return 0;
+    }
+}
+inline int event_host_rows(uint8_t kind) {       // rows of `values` / `coefs` the event consumes
+    return kind == EV_LINEAR || kind == EV_VSET ? 1 : (kind == EV_QUAD ? 3 : 0);
+}
+inline bool event_takes_constant(uint8_t kind) { return kind >= EV_VADDC && kind <= EV_VMONTMULC; }
 struct row_event {
-    bool quadratic = false;
+    uint8_t kind = EV_LINEAR;
     const uint32_t *val[3] = {nullptr, nullptr, nullptr};
     const uint32_t *coef[3] = {nullptr, nullptr, nullptr};
+    uint32_t arg[3] = {0, 0, 0};                 // EV_V*: arena slots (out, x, y) / bit index
+    const uint32_t *konst = nullptr;             // EV_V*C: canonical constant
 };
 
 struct statement {
@@ -48,6 +79,7 @@ struct statement {
     digest instance_hash, program_hash;
     int64_t generated_at_seconds = -1;           // < 0: wall clock
     uint32_t sample_size = 192;                  // params::sample_size
+    uint32_t arena_slots = 0;                    // vbn254fr variables (k elements each, zero on allocation)
 };
 
 struct prove_result {
@@ -98,13 +130,25 @@ public:
         // ---- stage 2: test vectors -----------------------------------------------------------------
         static const uint8_t any_iv[16] = {0};                                 // params::any_iv
         fr_random_stream code_rng(out.stage1_seed.data, any_iv), quad_rng(out.stage1_seed.data, any_iv);   // nonbatch_context.hpp:105-112
-        std::vector<uint32_t> r_code(rows_ * 8), r_quad;
-        // draw order = callback order: linear row -> 1 code draw; triple -> 3 code draws then 1 quadratic draw
+        // draw order = callback order (nonbatch_context.hpp:756-780,782-847): per event, first the code draws (one per
+        // row that goes through check_code; on_batch_equal rows take none), then one quadratic draw for events that feed
+        // the quadratic test.  Rows without a code draw combine with r = 0.
+        std::vector<uint32_t> r_code(std::max<size_t>(rows_, 1) * 8, 0);
+        std::vector<quad_item> quads;
         {
             size_t r = 0;
             for (const row_event &e : st.events) {
-                for (int j = 0; j < (e.quadratic ? 3 : 1); j++, r++) code_rng.next(&r_code[r * 8]);
-                if (e.quadratic) { r_quad.resize(r_quad.size() + 8); quad_rng.next(&r_quad[r_quad.size() - 8]); }
+                const int nr = event_rows(e.kind);
+                const bool code_draw = e.kind != EV_VCOPY && e.kind != EV_VASSERT_EQ;
+                if (code_draw) for (int j = 0; j < nr; j++) code_rng.next(&r_code[(r + j) * 8]);
+                if (e.kind == EV_QUAD || e.kind == EV_VMUL || e.kind == EV_VDIV || e.kind == EV_VBIT || e.kind == EV_VCOPY || e.kind == EV_VASSERT_EQ) {
+                    quad_item q;
+                    q.row = r;
+                    q.shape = (e.kind == EV_VBIT) ? 1 : ((e.kind == EV_VCOPY || e.kind == EV_VASSERT_EQ) ? 2 : 0);
+                    quad_rng.next(q.r);
+                    quads.push_back(q);
+                }
+                r += nr;
             }
         }
         void *code = dalloc((size_t)n_ * 32), *linear = dalloc((size_t)n_ * 32), *quad = dalloc((size_t)n_ * 32);
@@ -114,13 +158,26 @@ public:
             chk(lgr_encode_rows(ctx_, at(d_coef_, r0 * k_), k_, T, tile2_));
             chk(lgr_combine_code(ctx_, tile_, T, &r_code[r0 * 8], code));
             chk(lgr_combine_linear(ctx_, tile_, tile2_, T, linear));
-            // the triples of the tile, wherever they sit between linear rows: x, y, z are 3 consecutive codewords
-            std::vector<uint32_t> xrows;
-            for (size_t r = r0; r < r0 + T; r++) if (row_is_quad_x_[r]) xrows.push_back((uint32_t)(r - r0));
-            if (!xrows.empty()) {
-                chk(lgr_combine_quad_indexed(ctx_, tile_, xrows.data(), (uint32_t)xrows.size(), &r_quad[quad_seen * 8], quad));
-                quad_seen += xrows.size();
+            // the quadratic-test items of the tile, wherever they sit between other rows:
+            //   triples: x, y, z are 3 consecutive codewords        quad += r (x*y - z)
+            //   bits   : one codeword                               quad += r (x*x - x)      (on_batch_bit copies x into y and z)
+            //   equals : two consecutive codewords                  quad += r x + (p - r) y  (EltwiseSubMod + EltwiseFMAMod)
+            std::vector<uint32_t> trip_rows, trip_r, bit_rows, bit_r, eq_scal;
+            for (; quad_seen < quads.size() && quads[quad_seen].row < r0 + T; quad_seen++) {
+                const quad_item &q = quads[quad_seen];
+                const uint32_t rel = (uint32_t)(q.row - r0);
+                if (q.shape == 0) { trip_rows.push_back(rel); trip_r.insert(trip_r.end(), q.r, q.r + 8); }
+                else if (q.shape == 1) { bit_rows.push_back(rel); bit_r.insert(bit_r.end(), q.r, q.r + 8); }
+                else {
+                    if (eq_scal.empty()) eq_scal.assign((size_t)T * 8, 0);
+                    memcpy(&eq_scal[(size_t)rel * 8], q.r, 32);
+                    uint64_t rr[4]; memcpy(rr, q.r, 32);
+                    negate(&eq_scal[(size_t)(rel + 1) * 8], rr);
+                }
             }
+            if (!trip_rows.empty()) chk(lgr_combine_quad_indexed(ctx_, tile_, trip_rows.data(), (uint32_t)trip_rows.size(), trip_r.data(), quad));
+            if (!bit_rows.empty()) chk(lgr_combine_bit_indexed(ctx_, tile_, bit_rows.data(), (uint32_t)bit_rows.size(), bit_r.data(), quad));
+            if (!eq_scal.empty()) chk(lgr_combine_code(ctx_, tile_, T, eq_scal.data(), quad));
         });
         encode_mask(0); chk(lgr_elt_add_assign(ctx_, mask_cw_, code, n_));     // nonbatch_context.hpp:732-754
         encode_mask(1); chk(lgr_elt_add_assign(ctx_, mask_cw_, linear, n_));
@@ -203,26 +260,49 @@ private:
         }
     }
 
+    struct quad_item { size_t row; int shape; uint32_t r[8]; };       // shape 0 = triple, 1 = bit, 2 = equal pair
+
     // rows in emission order -> device, pads from the encoding stream; the three masks
     void build_rows(const statement &st) {
         rows_ = 0;
-        for (const row_event &e : st.events) rows_ += e.quadratic ? 3 : 1;
+        bool any_batch = false;
+        for (const row_event &e : st.events) {
+            if (e.kind >= EV_KIND_COUNT) throw std::invalid_argument("unknown event kind");
+            rows_ += event_rows(e.kind);
+            any_batch |= e.kind >= EV_VSET;
+        }
         static const uint8_t any_iv[16] = {0};
         fr_random_stream enc(st.encoding_seed, any_iv);                       // init_encoding_random(seed, params::any_iv)
         const size_t pad = k_ - l_;
         std::vector<uint32_t> val(std::max<size_t>(rows_, 1) * k_ * 8, 0), coef(std::max<size_t>(rows_, 1) * k_ * 8, 0);
+        std::vector<std::vector<uint32_t>> vset_rows;                         // l values + pads of every VSET, in order
         row_is_quad_x_.assign(rows_ + 1, 0);
         row_starts_event_.assign(rows_ + 1, 0);
         size_t r = 0;
         for (const row_event &e : st.events) {
-            row_starts_event_[r] = 1;
-            if (e.quadratic) row_is_quad_x_[r] = 1;
-            for (int j = 0; j < (e.quadratic ? 3 : 1); j++, r++) {
-                if (!e.val[j]) throw std::invalid_argument("row event without values");
-                memcpy(&val[r * k_ * 8], e.val[j], (size_t)l_ * 32);
-                for (size_t i = 0; i < pad; i++) enc.next(&val[(r * k_ + l_ + i) * 8]);
-                if (e.coef[j]) memcpy(&coef[r * k_ * 8], e.coef[j], (size_t)l_ * 32);
+            const int nr = event_rows(e.kind);
+            if (nr) row_starts_event_[r] = 1;
+            if (e.kind == EV_QUAD) row_is_quad_x_[r] = 1;
+            if (e.kind == EV_LINEAR || e.kind == EV_QUAD) {
+                for (int j = 0; j < nr; j++, r++) {
+                    if (!e.val[j]) throw std::invalid_argument("row event without values");
+                    memcpy(&val[r * k_ * 8], e.val[j], (size_t)l_ * 32);
+                    for (size_t i = 0; i < pad; i++) enc.next(&val[(r * k_ + l_ + i) * 8]);
+                    if (e.coef[j]) memcpy(&coef[r * k_ * 8], e.coef[j], (size_t)l_ * 32);
+                }
+                continue;
             }
+            if (e.kind == EV_VSET) {                                          // pads are drawn when the event happens
+                if (!e.val[0]) throw std::invalid_argument("vbn254fr set without values");
+                std::vector<uint32_t> row((size_t)k_ * 8, 0);
+                memcpy(row.data(), e.val[0], (size_t)l_ * 32);
+                for (size_t i = 0; i < pad; i++) enc.next(&row[(l_ + i) * 8]);
+                vset_rows.push_back(std::move(row));
+            }
+            const int nslots = e.kind == EV_VSET ? 1 : ((e.kind == EV_VADD || e.kind == EV_VSUB || e.kind == EV_VMUL || e.kind == EV_VDIV) ? 3 : 2);
+            for (int j = 0; j < nslots; j++)
+                if (e.arg[j] >= st.arena_slots) throw std::invalid_argument("vbn254fr variable index out of range");
+            r += nr;
         }
         row_starts_event_[rows_] = 1;
         // masks (witness_manager.hpp:271-321)
@@ -243,12 +323,70 @@ private:
         d_coef_ = dalloc(coef.size() * 4);
         chk(lgr_write(ctx_, d_val_, 0, val.data(), val.size() * 4));
         chk(lgr_write(ctx_, d_coef_, 0, coef.data(), coef.size() * 4));
+        if (any_batch) run_arena_program(st, vset_rows);
         // codeword tiles: 2^22 elements (128 MiB) each, at least one triple
         tile_rows_ = std::max<size_t>(3, ((size_t)1 << 22) / n_);
         tile_rows_ = std::min<size_t>(tile_rows_, std::max<size_t>(rows_, 3));
         tile_ = dalloc(tile_rows_ * n_ * 32);
         tile2_ = dalloc(tile_rows_ * n_ * 32);
         mask_cw_ = dalloc((size_t)n_ * 32);
+    }
+
+    // The vbn254fr calls of the statement, executed on the device in event order; every on_batch_* row is snapshotted
+    // (device-to-device) into its slot of the row matrix, so that the three stages see it like any other row.
+    void run_arena_program(const statement &st, const std::vector<std::vector<uint32_t>> &vset_rows) {
+        const size_t vb = (size_t)k_ * 32;
+        void *arena = dalloc(std::max<size_t>(st.arena_slots, 1) * vb), *tmp = dalloc(vb);
+        auto var = [&](uint32_t slot) { return at(arena, (size_t)slot * k_); };
+        auto snap = [&](const void *src, size_t row) { chk(lgr_copy(ctx_, src, at(d_val_, row * k_), vb)); };
+        size_t r = 0, vs = 0;
+        for (const row_event &e : st.events) {
+            void *out = var(e.arg[0]);
+            switch (e.kind) {
+                case EV_VSET:
+                    chk(lgr_write(ctx_, out, 0, vset_rows[vs].data(), vb)); vs++;      // values, zero fill, then the pads at [l, k)
+                    snap(out, r);
+                    break;
+                case EV_VCOPY:
+                    if (e.arg[0] != e.arg[1]) chk(lgr_copy(ctx_, var(e.arg[1]), out, vb));
+                    snap(out, r); snap(var(e.arg[1]), r + 1);
+                    break;
+                case EV_VASSERT_EQ:
+                    snap(var(e.arg[0]), r); snap(var(e.arg[1]), r + 1);
+                    break;
+                case EV_VADD: chk(lgr_elt_add(ctx_, var(e.arg[1]), var(e.arg[2]), tmp, k_)); chk(lgr_copy(ctx_, tmp, out, vb)); break;
+                case EV_VSUB: chk(lgr_elt_sub(ctx_, var(e.arg[1]), var(e.arg[2]), tmp, k_)); chk(lgr_copy(ctx_, tmp, out, vb)); break;
+                case EV_VMUL:
+                    chk(lgr_elt_mul(ctx_, var(e.arg[1]), var(e.arg[2]), tmp, k_));
+                    snap(var(e.arg[1]), r); snap(var(e.arg[2]), r + 1); snap(tmp, r + 2);
+                    chk(lgr_copy(ctx_, tmp, out, vb));
+                    break;
+                case EV_VDIV:
+                    chk(lgr_elt_div(ctx_, var(e.arg[1]), var(e.arg[2]), tmp, k_));
+                    snap(tmp, r); snap(var(e.arg[2]), r + 1); snap(var(e.arg[1]), r + 2);
+                    chk(lgr_copy(ctx_, tmp, out, vb));
+                    break;
+                case EV_VBIT:
+                    if (e.arg[2] >= 256) throw std::invalid_argument("bit index out of range");
+                    chk(lgr_elt_bit(ctx_, var(e.arg[1]), tmp, k_, e.arg[2]));
+                    chk(lgr_copy(ctx_, tmp, out, vb));
+                    snap(out, r);
+                    break;
+                case EV_VADDC: case EV_VSUBC: case EV_VCSUB: case EV_VMULC: case EV_VMONTMULC: {
+                    if (!e.konst) throw std::invalid_argument("constant operation without a constant");
+                    const void *x = var(e.arg[1]);
+                    if (e.kind == EV_VADDC) chk(lgr_elt_add_const(ctx_, x, tmp, k_, e.konst));
+                    else if (e.kind == EV_VSUBC) chk(lgr_elt_sub_const(ctx_, x, tmp, k_, e.konst));
+                    else if (e.kind == EV_VCSUB) chk(lgr_elt_const_sub(ctx_, x, tmp, k_, e.konst));
+                    else if (e.kind == EV_VMULC) chk(lgr_elt_mul_const(ctx_, x, tmp, k_, e.konst));
+                    else chk(lgr_elt_montmul_const(ctx_, x, tmp, k_, e.konst));
+                    chk(lgr_copy(ctx_, tmp, out, vb));
+                    break;
+                }
+                default: break;
+            }
+            r += event_rows(e.kind);
+        }
     }
 
     // mask m as a codeword in mask_cw_: m = 0 a normal row; m = 1, 2 given on the w_2k domain:

@@ -191,15 +191,26 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *s, lgrp_proof **out) {
     st.program_hash = dg(s->program_hash);
     st.generated_at_seconds = s->generated_at_seconds;
     st.sample_size = s->sample_size ? s->sample_size : 192;
-    size_t row = 0;
+    size_t row = 0, nb = 0, nc = 0;
     const size_t stride = (size_t)s->l * 8;
+    st.arena_slots = s->arena_slots;
     st.events.resize(s->n_events);
     for (uint64_t e = 0; e < s->n_events; e++) {
         row_event &ev = st.events[e];
-        ev.quadratic = s->kinds[e] != 0;
-        for (int j = 0; j < (ev.quadratic ? 3 : 1); j++, row++) {
+        ev.kind = s->kinds[e];
+        if (ev.kind >= EV_KIND_COUNT) throw std::invalid_argument("unknown event kind");
+        for (int j = 0; j < event_host_rows(ev.kind); j++, row++) {
             ev.val[j] = s->values + row * stride;
-            ev.coef[j] = s->coefs ? s->coefs + row * stride : nullptr;
+            ev.coef[j] = (s->coefs && ev.kind != EV_VSET) ? s->coefs + row * stride : nullptr;
+        }
+        if (ev.kind >= EV_VSET) {
+            if (!s->batch_args) throw std::invalid_argument("vbn254fr events without batch_args");
+            for (int j = 0; j < 3; j++) ev.arg[j] = s->batch_args[3 * nb + j];
+            nb++;
+            if (event_takes_constant(ev.kind)) {
+                if (!s->batch_consts) throw std::invalid_argument("constant-taking vbn254fr event without batch_consts");
+                ev.konst = s->batch_consts + 8 * nc++;
+            }
         }
     }
     lgrp_proof *p = new lgrp_proof();

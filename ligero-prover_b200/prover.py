@@ -139,7 +139,15 @@ class RowPacker:
 class Statement(C.Structure):
     _fields_ = [("l", C.c_uint32), ("k", C.c_uint32), ("n_events", C.c_uint64), ("kinds", C.c_void_p), ("values", C.c_void_p),
                 ("coefs", C.c_void_p), ("const_sum", C.c_uint32 * 8), ("encoding_seed", C.c_uint8 * 32), ("instance_hash", C.c_uint8 * 32),
-                ("program_hash", C.c_uint8 * 32), ("generated_at_seconds", C.c_int64), ("sample_size", C.c_uint32)]
+                ("program_hash", C.c_uint8 * 32), ("generated_at_seconds", C.c_int64), ("sample_size", C.c_uint32),
+                ("arena_slots", C.c_uint32), ("batch_args", C.c_void_p), ("batch_consts", C.c_void_p)]
+
+
+# event kinds (include/lgr_prover.h LGRP_EV_*)
+EV_LINEAR, EV_QUAD, EV_VSET, EV_VCOPY, EV_VADD, EV_VSUB, EV_VMUL, EV_VDIV, EV_VASSERT_EQ, EV_VBIT = range(10)
+EV_VADDC, EV_VSUBC, EV_VCSUB, EV_VMULC, EV_VMONTMULC = range(10, 15)
+HOST_ROWS = {EV_LINEAR: 1, EV_QUAD: 3, EV_VSET: 1}
+COMMITTED_ROWS = {EV_LINEAR: 1, EV_QUAD: 3, EV_VSET: 1, EV_VBIT: 1, EV_VCOPY: 2, EV_VASSERT_EQ: 2, EV_VMUL: 3, EV_VDIV: 3}
 
 
 class Proof:
@@ -191,14 +199,23 @@ def parse_proof(data):
 
 
 def prove(executor, kinds, values, coefs=None, const_sum=0, encoding_seed=bytes(32), instance_hash=bytes(32), program_hash=bytes(32),
-          generated_at=0, sample_size=192):
-    """executor: ligero_prover_b200.Executor (its lgr_ctx runs the hot path); kinds: per event 0 = linear row, 1 = quadratic
-    triple; values / coefs: [encoded rows, l, 8] uint32 in emission order"""
+          generated_at=0, sample_size=192, arena_slots=0, batch_args=None, batch_consts=None):
+    """executor: ligero_prover_b200.Executor (its lgr_ctx runs the hot path); kinds: per event EV_* (0 = linear row,
+    1 = quadratic triple, 2.. = vbn254fr calls on `arena_slots` device variables, operands in batch_args [events, 3],
+    constants in batch_consts [*, 8]); values / coefs: [host rows, l, 8] uint32 in event order"""
     l, k = executor.message_size(), executor.padding_size()
     kinds = np.ascontiguousarray(kinds, np.uint8)
     values = np.ascontiguousarray(values, np.uint32).reshape(-1, l, 8)
-    assert values.shape[0] == int(kinds.size + 2 * kinds.astype(bool).sum()), "one row per linear event, three per triple"
+    assert values.shape[0] == sum(HOST_ROWS.get(int(kd), 0) for kd in kinds), "one host row per linear / VSET event, three per triple"
     st = Statement()
+    st.arena_slots = arena_slots
+    if batch_args is not None:
+        batch_args = np.ascontiguousarray(batch_args, np.uint32).reshape(-1, 3)
+        assert batch_args.shape[0] == int((kinds >= EV_VSET).sum())
+        st.batch_args = batch_args.ctypes.data
+    if batch_consts is not None:
+        batch_consts = np.ascontiguousarray(batch_consts, np.uint32).reshape(-1, 8)
+        st.batch_consts = batch_consts.ctypes.data
     st.l, st.k, st.n_events = l, k, kinds.size
     st.kinds, st.values = kinds.ctypes.data, values.ctypes.data
     if coefs is not None:

@@ -268,15 +268,104 @@ def masks(l, k, enc: FrRandomStream):
     return mc, lgo.to_limbs(ml), lgo.to_limbs(mq)
 
 
-def prove(l, k, kinds, values, coefs, const_sum, encoding_seed, instance_hash, sample_size=192):
+# event kinds (include/lgr_prover.h LGRP_EV_*): 0 / 1 from the scalar backend, 2.. vbn254fr host calls
+# (include/host_modules/vbn254fr.hpp:139-566) with their on_batch_* callbacks (nonbatch_context.hpp:497-553,782-847,996-1047)
+EV_LINEAR, EV_QUAD, EV_VSET, EV_VCOPY, EV_VADD, EV_VSUB, EV_VMUL, EV_VDIV, EV_VASSERT_EQ, EV_VBIT = range(10)
+EV_VADDC, EV_VSUBC, EV_VCSUB, EV_VMULC, EV_VMONTMULC = range(10, 15)
+
+
+def run_events(l, k, kinds, values, coefs, enc, arena_slots=0, batch_args=None, batch_consts=None):
+    """Replays the event list the way the interpreter would drive a stage context: returns the committed rows
+    (k elements each, pads included), their coefficient rows, and per event the list of committed-row indices.
+    vbn254fr variables are k-element device buffers; every arena operation acts on all k elements."""
+    values = np.ascontiguousarray(values, np.uint32).reshape(-1, l, 8)
+    coefs = np.zeros_like(values) if coefs is None else np.ascontiguousarray(coefs, np.uint32).reshape(-1, l, 8)
+    arena = np.zeros((max(arena_slots, 1), k, 8), np.uint32)
+    args = None if batch_args is None else np.ascontiguousarray(batch_args, np.uint32).reshape(-1, 3)
+    consts = None if batch_consts is None else np.ascontiguousarray(batch_consts, np.uint32).reshape(-1, 8)
+    M, C, ev_rows = [], [], []
+    hr = nb = nc = 0
+
+    def commit(row, coef=None):
+        M.append(np.array(row, np.uint32)); C.append(np.zeros((k, 8), np.uint32) if coef is None else coef)
+        return len(M) - 1
+
+    for kind in kinds:
+        kind = int(kind)
+        if kind in (EV_LINEAR, EV_QUAD):
+            idx = []
+            for _ in range(3 if kind == EV_QUAD else 1):
+                row = np.zeros((k, 8), np.uint32); row[:l] = values[hr]
+                row[l:] = lgo.to_limbs(enc.take(k - l))                       # witness_manager.hpp:200-214
+                cf = np.zeros((k, 8), np.uint32); cf[:l] = coefs[hr]
+                idx.append(commit(row, cf)); hr += 1
+            ev_rows.append(idx)
+            continue
+        out, x, y = (int(v) for v in args[nb]); nb += 1
+        if kind == EV_VSET:                                                   # write_buffer_clear + on_batch_init
+            arena[out] = 0; arena[out, :l] = values[hr]; hr += 1
+            arena[out, l:] = lgo.to_limbs(enc.take(k - l))
+            ev_rows.append([commit(arena[out])])
+        elif kind == EV_VCOPY:                                                # on_batch_equal(out, in)
+            arena[out] = arena[x]
+            ev_rows.append([commit(arena[out]), commit(arena[x])])
+        elif kind == EV_VASSERT_EQ:                                           # on_batch_equal(x, y): operands are args 0, 1
+            ev_rows.append([commit(arena[out]), commit(arena[x])])
+        elif kind == EV_VADD:
+            arena[out] = lgo.elt_add(arena[x], arena[y]); ev_rows.append([])
+        elif kind == EV_VSUB:
+            arena[out] = lgo.elt_sub(arena[x], arena[y]); ev_rows.append([])
+        elif kind == EV_VMUL:                                                 # on_batch_quadratic(x, y, tmp)
+            tmp = lgo.elt_mul(arena[x], arena[y])
+            ev_rows.append([commit(arena[x]), commit(arena[y]), commit(tmp)])
+            arena[out] = tmp
+        elif kind == EV_VDIV:                                                 # on_batch_quadratic(tmp, y, x)
+            tmp = lgo.elt_div(arena[x], arena[y])
+            ev_rows.append([commit(tmp), commit(arena[y]), commit(arena[x])])
+            arena[out] = tmp
+        elif kind == EV_VBIT:                                                 # on_batch_bit(out)
+            arena[out] = lgo.elt_bit(arena[x], y)
+            ev_rows.append([commit(arena[out])])
+        else:
+            c = lgo.from_limbs(consts[nc])[0]; nc += 1
+            fn = {EV_VADDC: lgo.elt_add_const, EV_VSUBC: lgo.elt_sub_const, EV_VCSUB: lgo.elt_const_sub, EV_VMULC: lgo.elt_mul_const,
+                  EV_VMONTMULC: lgo.elt_montmul_const}[kind]
+            arena[out] = fn(arena[x], c); ev_rows.append([])
+    return M, C, ev_rows
+
+
+def stage2_combine(kinds, ev_rows, rowvec, coefvec, s1, shape):
+    """code / linear / quad accumulators over `rowvec[r]` (encoded rows, or their sampled columns) in callback order"""
+    code_rng, quad_rng = FrRandomStream(s1), FrRandomStream(s1)
+    code = np.zeros(shape, np.uint32); linear = np.zeros(shape, np.uint32); quad = np.zeros(shape, np.uint32)
+    for kind, idx in zip(kinds, ev_rows):
+        kind = int(kind)
+        if kind in (EV_LINEAR, EV_QUAD):
+            for r in idx:
+                code = lgo.elt_fma_const(code, rowvec[r], code_rng.next())
+            for r in idx:
+                linear = lgo.elt_fma(linear, rowvec[r], coefvec(r))
+        elif kind in (EV_VSET, EV_VBIT, EV_VMUL, EV_VDIV):                    # check_code on every committed row of the event
+            for r in idx:
+                code = lgo.elt_fma_const(code, rowvec[r], code_rng.next())
+        if kind in (EV_QUAD, EV_VMUL, EV_VDIV):
+            t = lgo.elt_sub(lgo.elt_mul(rowvec[idx[0]], rowvec[idx[1]]), rowvec[idx[2]])
+            quad = lgo.elt_fma_const(quad, t, quad_rng.next())
+        elif kind == EV_VBIT:                                                 # y := x, z := x, then check_quadratic
+            x = rowvec[idx[0]]
+            quad = lgo.elt_fma_const(quad, lgo.elt_sub(lgo.elt_mul(x, x), x), quad_rng.next())
+        elif kind in (EV_VCOPY, EV_VASSERT_EQ):                               # EltwiseSubMod then EltwiseFMAMod(r)
+            quad = lgo.elt_fma_const(quad, lgo.elt_sub(rowvec[idx[0]], rowvec[idx[1]]), quad_rng.next())
+    return code, linear, quad
+
+
+def prove(l, k, kinds, values, coefs, const_sum, encoding_seed, instance_hash, sample_size=192, arena_slots=0, batch_args=None,
+          batch_consts=None):
     """Returns a dict with every value that goes into the proof plus the self-check flags."""
     n = 4 * k
-    values = np.ascontiguousarray(values, np.uint32).reshape(-1, l, 8)
-    rows = values.shape[0]
-    coefs = np.zeros_like(values) if coefs is None else np.ascontiguousarray(coefs, np.uint32).reshape(-1, l, 8)
     enc = FrRandomStream(encoding_seed)
-    M = pad_rows(kinds, values, l, k, enc)
-    C = np.zeros((rows, k, 8), np.uint32); C[:, :l] = coefs
+    M, C, ev_rows = run_events(l, k, kinds, values, coefs, enc, arena_slots, batch_args, batch_consts)
+    rows = len(M)
     mc, ml, mq = masks(l, k, enc)
     cw = [lgo.encode(M[r], k) for r in range(rows)]
     cw_masks = [lgo.encode(mc, k), lgo.encode_2k(ml, k), lgo.encode_2k(mq, k)]
@@ -289,19 +378,7 @@ def prove(l, k, kinds, values, coefs, const_sum, encoding_seed, instance_hash, s
     root = nodes[0].tobytes()
     s1 = stage1_seed(root, instance_hash)
     # stage 2
-    code_rng, quad_rng = FrRandomStream(s1), FrRandomStream(s1)
-    code = np.zeros((n, 8), np.uint32); linear = np.zeros((n, 8), np.uint32); quad = np.zeros((n, 8), np.uint32)
-    r = 0
-    for kind in kinds:
-        cnt = 3 if kind else 1
-        for j in range(cnt):
-            code = lgo.elt_fma_const(code, cw[r + j], code_rng.next())
-        for j in range(cnt):
-            linear = lgo.elt_fma(linear, cw[r + j], lgo.encode(C[r + j], k))
-        if kind:
-            t = lgo.elt_sub(lgo.elt_mul(cw[r], cw[r + 1]), cw[r + 2])
-            quad = lgo.elt_fma_const(quad, t, quad_rng.next())
-        r += cnt
+    code, linear, quad = stage2_combine(kinds, ev_rows, cw, lambda r: lgo.encode(C[r], k), s1, (n, 8))
     code = lgo.elt_add_assign(code, cw_masks[0]); linear = lgo.elt_add_assign(linear, cw_masks[1]); quad = lgo.elt_add_assign(quad, cw_masks[2])
     s2 = stage2_seed(root, code, linear, quad)
     sample = sample_indices(s2, n, sample_size)
@@ -317,11 +394,12 @@ def prove(l, k, kinds, values, coefs, const_sum, encoding_seed, instance_hash, s
     samplings = np.stack([e[sample] for e in cw + cw_masks])
     return {"root": root, "stage1_seed": s1, "stage2_seed": s2, "code": code, "linear": linear, "quad": quad, "sample": sample,
             "positions": pos, "siblings": siblings, "samplings": samplings, "digests": digests, "total_count": total,
-            "valid": (valid_code, valid_linear, valid_quad)}
+            "valid": (valid_code, valid_linear, valid_quad), "encoded_rows": rows + 3}
 
 
 def verify_openings(proof_env, l, k, kinds, coefs, instance_hash):
-    """The checks of src/webgpu_verifier.cpp:314-315,412-442 that need no re-execution: the sampled columns
+    """(vbn254fr events need no operands here: the verifier sees only committed rows, in event order.)
+    The checks of src/webgpu_verifier.cpp:314-315,412-442 that need no re-execution: the sampled columns
     re-hash to leaves that recommit to the root, and the three test vectors at the sampled positions equal
     the combinations recomputed from the opened columns (with r re-derived from the transcript)."""
     n = 4 * k
@@ -344,20 +422,26 @@ def verify_openings(proof_env, l, k, kinds, coefs, instance_hash):
     total = 2 * (1 << (n - 1).bit_length()) - 1
     assert recommit(leaves, sample, total, [s.value for s in pr.merkle_tree.sibling_hashes]) == root, "openings do not recommit to the root"
     s1 = stage1_seed(root, instance_hash)
-    code_rng, quad_rng = FrRandomStream(s1), FrRandomStream(s1)
-    acc_c = np.zeros((S, 8), np.uint32); acc_l = np.zeros((S, 8), np.uint32); acc_q = np.zeros((S, 8), np.uint32)
+    # which committed rows belong to which event, and the coefficient rows of the scalar events
+    committed = {EV_LINEAR: 1, EV_QUAD: 3, EV_VSET: 1, EV_VBIT: 1, EV_VCOPY: 2, EV_VASSERT_EQ: 2, EV_VMUL: 3, EV_VDIV: 3}
     coefs = np.ascontiguousarray(coefs, np.uint32).reshape(-1, l, 8)
-    r = 0
+    ev_rows, coef_of, r, hr = [], {}, 0, 0
     for kind in kinds:
-        cnt = 3 if kind else 1
-        for j in range(cnt):
-            acc_c = lgo.elt_fma_const(acc_c, samp[r + j], code_rng.next())
-        for j in range(cnt):
-            crow = np.zeros((k, 8), np.uint32); crow[:l] = coefs[r + j]
-            acc_l = lgo.elt_fma(acc_l, samp[r + j], lgo.encode(crow, k)[sample])
-        if kind:
-            acc_q = lgo.elt_fma_const(acc_q, lgo.elt_sub(lgo.elt_mul(samp[r], samp[r + 1]), samp[r + 2]), quad_rng.next())
+        kind = int(kind)
+        cnt = committed.get(kind, 0)
+        ev_rows.append(list(range(r, r + cnt)))
+        if kind in (EV_LINEAR, EV_QUAD):
+            for j in range(cnt):
+                coef_of[r + j] = hr; hr += 1
+        elif kind == EV_VSET:
+            hr += 1
         r += cnt
+    assert r == rows, "the proof holds %d rows, the statement commits %d" % (rows, r)
+
+    def coefvec(row):
+        crow = np.zeros((k, 8), np.uint32); crow[:l] = coefs[coef_of[row]]
+        return lgo.encode(crow, k)[sample]
+    acc_c, acc_l, acc_q = stage2_combine(kinds, ev_rows, samp, coefvec, s1, (S, 8))
     acc_c = lgo.elt_add_assign(acc_c, samp[rows]); acc_l = lgo.elt_add_assign(acc_l, samp[rows + 1]); acc_q = lgo.elt_add_assign(acc_q, samp[rows + 2])
     assert np.array_equal(acc_c, code[sample]) and np.array_equal(acc_l, linear[sample]) and np.array_equal(acc_q, quad[sample]), "test vectors disagree with the openings"
     return True

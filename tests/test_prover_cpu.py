@@ -262,3 +262,29 @@ def test_row_packer_matches_restatement(pr, oracle, l, nw, seed):
     pk2.finalize()
     assert list(pk2.rows()[0]) == [0, 0]
     pk.close(); pk2.close()
+
+
+def test_oracle_prover_vbn254fr_events_are_self_consistent(oracle):
+    """CPU restatement of the on_batch_* flow (vbn254fr calls on k-element variables): a satisfiable batch program
+    passes all three tests, a violated assertion fails the quadratic test only, and the committed-row count follows
+    nonbatch_context.hpp:497-553 (init 1, bit 1, equal 2, quadratic 3)"""
+    import random
+    R = ref
+    P = ref.P
+    l, k = 24, 64
+    rng = random.Random(9)
+    v0 = [rng.randrange(P) for _ in range(l)]
+    v1 = [rng.randrange(1, P) for _ in range(l)]
+    lin = [rng.randrange(P) for _ in range(l)]
+    cf = [rng.randrange(P) for _ in range(l)]
+    kinds = [R.EV_VSET, R.EV_VSET, R.EV_VMUL, R.EV_LINEAR, R.EV_VDIV, R.EV_VASSERT_EQ, R.EV_VBIT, R.EV_VCOPY]
+    args = [[0, 0, 0], [1, 0, 0], [2, 0, 1], [3, 2, 1], [3, 0, 0], [4, 2, 5], [5, 4, 0]]
+    values = np.stack([oracle.to_limbs(r) for r in (v0, v1, lin)])
+    coefs = np.stack([oracle.to_limbs(r) for r in ([0] * l, [0] * l, cf)])
+    const_sum = (-sum(a * b for a, b in zip(lin, cf))) % P
+    out = R.prove(l, k, kinds, values, coefs, const_sum, bytes(range(32)), bytes(32), arena_slots=6, batch_args=args)
+    assert out["valid"] == (True, True, True)
+    assert out["encoded_rows"] == 1 + 1 + 3 + 1 + 3 + 2 + 1 + 2 + 3
+    bad = [a[:] for a in args]
+    bad[4] = [3, 1, 0]                                   # v3 (= v0) asserted equal to v1
+    assert R.prove(l, k, kinds, values, coefs, const_sum, bytes(range(32)), bytes(32), arena_slots=6, batch_args=bad)["valid"] == (True, True, False)

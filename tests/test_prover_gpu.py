@@ -254,3 +254,87 @@ def test_cpp_prover_program(lgr, oracle, tmp_path):
     meta = {"prover_version": "1.5.0", "program_hash": bytes(32), "generated_at": 1, "k": k, "n": 4 * k, "sample_size": 192}
     assert env.SerializeToString(deterministic=True) == ref.build_envelope(meta, want["root"], want["siblings"], want["sample"], want["code"],
                                                                            want["linear"], want["quad"], want["samplings"])
+
+
+# ---------------------------------------------------------------- vbn254fr batch events
+def batch_statement(oracle, l, seed):
+    """a small vbn254fr program between scalar rows: sets, a product, its copy, an assertion that holds, a quotient,
+    bit decompositions of a 0/1 vector, constant arithmetic.  Returns everything lgrp_prove / prover_ref.prove take."""
+    from oracle import prover_ref as R
+    rng = random.Random(seed)
+    kinds, args, consts, vals, coefs = [], [], [], [], []
+    acc = 0
+
+    def host_row(row, with_coef=True):
+        nonlocal acc
+        c = [rng.randrange(P) if with_coef else 0 for _ in range(l)]
+        if with_coef:
+            acc += sum(a * b for a, b in zip(row, c))
+        vals.append(row); coefs.append(c)
+
+    def ev(kind, a=0, b=0, c=0, konst=None):
+        kinds.append(kind)
+        if kind >= R.EV_VSET:
+            args.append([a, b, c])
+        if konst is not None:
+            consts.append(konst)
+
+    ev(R.EV_LINEAR); host_row([rng.randrange(P) for _ in range(l)])
+    ev(R.EV_VSET, 0); host_row([rng.randrange(P) for _ in range(l)], False)            # v0
+    ev(R.EV_VSET, 1); host_row([rng.randrange(1, P) for _ in range(l)], False)         # v1 (non-zero: it divides below)
+    ev(R.EV_VMUL, 2, 0, 1)                                                              # v2 = v0 * v1
+    x = [rng.randrange(P) for _ in range(l)]; y = [rng.randrange(P) for _ in range(l)]
+    ev(R.EV_QUAD); host_row(x); host_row(y); host_row([a * b % P for a, b in zip(x, y)])
+    ev(R.EV_VCOPY, 3, 2)                                                                # v3 = v2
+    ev(R.EV_VDIV, 4, 3, 1)                                                              # v4 = v3 / v1 (= v0)
+    ev(R.EV_VASSERT_EQ, 4, 0)                                                           # holds on all k elements
+    ev(R.EV_VSET, 5); host_row([rng.randrange(2) for _ in range(l)], False)            # bits
+    ev(R.EV_VBIT, 6, 5, 0)                                                              # v6 = bit 0 of v5 (pads: bit 0 of random pads)
+    ev(R.EV_VMUL, 7, 0, 0)                                                              # a square: x == y
+    c1 = rng.randrange(P)
+    ev(R.EV_VADDC, 8, 7, 0, c1); ev(R.EV_VSUBC, 8, 8, 0, c1)                            # v8 = v7
+    ev(R.EV_VASSERT_EQ, 8, 7)
+    ev(R.EV_VADD, 9, 0, 1); ev(R.EV_VSUB, 9, 9, 1); ev(R.EV_VASSERT_EQ, 9, 0)
+    c2 = rng.randrange(1, P)
+    ev(R.EV_VMULC, 10, 0, 0, c2); ev(R.EV_VMONTMULC, 10, 10, 0, pow(c2, -1, P) * (1 << 256) % P); ev(R.EV_VASSERT_EQ, 10, 0)
+    ev(R.EV_VCSUB, 11, 0, 0, 0); ev(R.EV_VADD, 11, 11, 0)                                # (0 - v0) + v0 = 0
+    ev(R.EV_VBIT, 12, 11, 7)                                                            # bit of zero
+    ev(R.EV_LINEAR); host_row([rng.randrange(P) for _ in range(l)])
+    values = np.stack([oracle.to_limbs(r) for r in vals])
+    coef = np.stack([oracle.to_limbs(c) for c in coefs])
+    return (np.array(kinds, np.uint8), values, coef, (-acc) % P, 13, np.array(args, np.uint32),
+            np.stack([oracle.to_limbs([c])[0] for c in consts]))
+
+
+@pytest.mark.parametrize("k,l", [(256, 64), (512, 320)])
+def test_prove_with_vbn254fr_batch_events(lgr, oracle, pr, executor_factory, k, l):
+    """on_batch_init / bit / equal / quadratic rows (nonbatch_context.hpp:497-553,782-847,996-1047) driven by vbn254fr
+    calls on device-resident variables: proof equal to the CPU restatement, self-check and openings valid"""
+    n = 4 * k
+    ex = executor_factory(k, l)
+    kinds, values, coefs, const_sum, slots, args, consts = batch_statement(oracle, l, seed=k)
+    enc_seed = hashlib.sha256(b"batch encoding seed").digest()
+    inst = hashlib.sha256(b"batch instance").digest()
+    proof = pr.prove(ex, kinds, values, coefs, const_sum, enc_seed, inst, generated_at=7, arena_slots=slots, batch_args=args, batch_consts=consts)
+    want = ref.prove(l, k, kinds, values, coefs, const_sum, enc_seed, inst, arena_slots=slots, batch_args=args, batch_consts=consts)
+    info = proof.info()
+    assert want["valid"] == (True, True, True)
+    assert info["valid"] == (True, True, True)
+    assert info["encoded_rows"] == want["encoded_rows"]
+    assert info["stage1_seed"] == want["stage1_seed"] and info["stage2_seed"] == want["stage2_seed"]
+    env = ref.parse_envelope(proof.gzip)
+    pf = env.ligero_proof
+    assert pf.merkle_tree.root.value == want["root"]
+    for name, key in (("encoded_code", "code"), ("encoded_linear", "linear"), ("encoded_quadratic", "quad")):
+        assert np.array_equal(np.array(getattr(pf, name).values, np.uint32).reshape(n, 8), want[key]), name
+    assert np.array_equal(np.array(pf.sampled_data.values, np.uint32).reshape(want["samplings"].shape), want["samplings"])
+    assert ref.verify_openings(env, l, k, kinds, coefs, inst)
+    proof.close()
+    # a violated batch assertion must fail the quadratic test (and only it)
+    bad = kinds.copy()
+    i = [j for j, kd in enumerate(kinds) if kd == ref.EV_VASSERT_EQ][0]
+    bargs = args.copy()
+    bi = int((kinds[:i] >= ref.EV_VSET).sum())
+    bargs[bi] = [4, 1, 0]                                              # v4 (= v0) against v1
+    info = pr.prove(ex, bad, values, coefs, const_sum, enc_seed, inst, arena_slots=slots, batch_args=bargs, batch_consts=consts).info()
+    assert info["valid"] == (True, True, False)
