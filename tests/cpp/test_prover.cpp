@@ -38,7 +38,7 @@ int main(int argc, char **argv) {
         st.l = l; st.k = k;
         size_t row = 0;
         for (uint8_t kind : pk.kinds()) {
-            row_event ev; ev.quadratic = kind != 0;
+            row_event ev; ev.kind = kind ? EV_QUAD : EV_LINEAR;
             for (int j = 0; j < (kind ? 3 : 1); j++, row++) { ev.val[j] = pk.values().data() + row * l * 8; ev.coef[j] = pk.coefs().data() + row * l * 8; }
             st.events.push_back(ev);
         }
