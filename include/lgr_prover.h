@@ -116,6 +116,27 @@ typedef struct {
 
 int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
 
+/* ---- bounded interpreter boundary (BASELINE config 4) --------------------------------
+ * A front end for the folded-WAT subset of the reference's arithmetic tests (tests/i64_mul.wat, i64_add.wat,
+ * i64_sub.wat: env.i64_private_const, env.assert_equal, i64.const / mul / add / sub) and the witness emitter behind
+ * it (host/wat_emitter.hpp).  It stands where include/invoke.hpp:79-98 + the headers under include/zkp/backend/ stand in the
+ * reference; it is not their restatement, and the order in which it releases witnesses is its own (the reference's
+ * follows C++ temporaries inside its interpreter: unpinnable without running it).  The proof is a valid Ligero proof of
+ * the program's assertions, not a byte-identical copy of the reference's. */
+typedef struct {
+    uint64_t private_consts, asserts, arithmetic_ops;
+    uint64_t linear_witnesses, quadratic_slots, linear_constraints;
+    uint64_t violated_constraints;   /* > 0: an assertion of the program does not hold; the proof will not validate */
+} lgrp_wat_stats;
+/* host only: text -> rows.  stage1_seed == NULL: coefficient rows are zero (what stage 1 needs); otherwise the linear-test
+ * coefficients are drawn from the linear stream keyed by the seed, one rho per constraint, and const_sum is set. */
+int lgrp_wat_emit(const char *wat, size_t len, uint32_t l, const uint8_t *stage1_seed, lgrp_packer **rows_out, uint32_t const_sum[8],
+                  lgrp_wat_stats *stats);
+/* text -> proof on the context's geometry: stage 1 on the values, coefficients from the stage-1 seed, stages 2 and 3.
+ * program_hash = SHA-256 of the text (the reference hashes the .wasm binary), instance_hash = 0 (no public arguments). */
+int lgrp_prove_wat(lgr_ctx *ctx, const char *wat, size_t len, const uint8_t encoding_seed[32], int64_t generated_at_seconds,
+                   lgrp_proof **out, lgrp_wat_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@
 // stage sweeps them in tiles: encode T rows -> hash / combine / gather the resident tile.
 #pragma once
 #include <chrono>
+#include <functional>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -80,6 +81,11 @@ struct statement {
     int64_t generated_at_seconds = -1;           // < 0: wall clock
     uint32_t sample_size = 192;                  // params::sample_size
     uint32_t arena_slots = 0;                    // vbn254fr variables (k elements each, zero on allocation)
+    // The reference derives the linear-test coefficients AFTER the commitment: stage 2 re-runs the program with the linear
+    // random engine keyed by the stage-1 seed (nonbatch_context.hpp:105-112, src/webgpu_prover.cpp:281-335).  A statement
+    // whose coefficients depend on that seed supplies this callback instead of `coef` pointers: it receives the seed and
+    // fills one coefficient row per host row ([host rows][l][8 x u32], event order) and const_sum.
+    std::function<void(const uint8_t stage1_seed[32], std::vector<uint32_t> &coef_rows, uint32_t const_sum[8])> coef_provider;
 };
 
 struct prove_result {
@@ -127,6 +133,15 @@ public:
         out.stage1_seed = stage1_seed(root, st.instance_hash);
         const auto t1 = clock_now();
 
+        uint32_t const_sum[8];
+        memcpy(const_sum, st.const_sum, 32);
+        if (st.coef_provider) {                                                   // coefficients that depend on the commitment
+            std::vector<uint32_t> crow(host_row_of_.size() * (size_t)l_ * 8, 0);
+            st.coef_provider(out.stage1_seed.data, crow, const_sum);
+            if (crow.size() != host_row_of_.size() * (size_t)l_ * 8) throw std::invalid_argument("coef_provider returned a wrong number of rows");
+            for (size_t h = 0; h < host_row_of_.size(); h++)
+                chk(lgr_write(ctx_, at(d_coef_, host_row_of_[h] * k_), 0, &crow[h * (size_t)l_ * 8], (size_t)l_ * 32));
+        }
         // ---- stage 2: test vectors -----------------------------------------------------------------
         static const uint8_t any_iv[16] = {0};                                 // params::any_iv
         fr_random_stream code_rng(out.stage1_seed.data, any_iv), quad_rng(out.stage1_seed.data, any_iv);   // nonbatch_context.hpp:105-112
@@ -199,7 +214,7 @@ public:
             out.valid_code = true;
             for (size_t i = (size_t)k_ * 8; i < h.size(); i++) if (h[i]) { out.valid_code = false; break; }
             chk(lgr_decode(ctx_, linear)); chk(lgr_read(ctx_, h.data(), linear, 0, h.size() * 4));
-            out.valid_linear = sum_is_zero(h.data(), l_, st.const_sum);
+            out.valid_linear = sum_is_zero(h.data(), l_, const_sum);
             chk(lgr_decode(ctx_, quad)); chk(lgr_read(ctx_, h.data(), quad, 0, h.size() * 4));
             out.valid_quad = true;
             for (size_t i = 0; i < (size_t)l_ * 8; i++) if (h[i]) { out.valid_quad = false; break; }
@@ -278,6 +293,7 @@ private:
         std::vector<std::vector<uint32_t>> vset_rows;                         // l values + pads of every VSET, in order
         row_is_quad_x_.assign(rows_ + 1, 0);
         row_starts_event_.assign(rows_ + 1, 0);
+        host_row_of_.clear();
         size_t r = 0;
         for (const row_event &e : st.events) {
             const int nr = event_rows(e.kind);
@@ -285,6 +301,7 @@ private:
             if (e.kind == EV_QUAD) row_is_quad_x_[r] = 1;
             if (e.kind == EV_LINEAR || e.kind == EV_QUAD) {
                 for (int j = 0; j < nr; j++, r++) {
+                    host_row_of_.push_back(r);
                     if (!e.val[j]) throw std::invalid_argument("row event without values");
                     memcpy(&val[r * k_ * 8], e.val[j], (size_t)l_ * 32);
                     for (size_t i = 0; i < pad; i++) enc.next(&val[(r * k_ + l_ + i) * 8]);
@@ -293,6 +310,7 @@ private:
                 continue;
             }
             if (e.kind == EV_VSET) {                                          // pads are drawn when the event happens
+                host_row_of_.push_back(r);                                    // (its coefficient row is ignored: batch rows take no linear test)
                 if (!e.val[0]) throw std::invalid_argument("vbn254fr set without values");
                 std::vector<uint32_t> row((size_t)k_ * 8, 0);
                 memcpy(row.data(), e.val[0], (size_t)l_ * 32);
@@ -425,6 +443,7 @@ private:
     uint32_t l_ = 0, k_ = 0, n_ = 0;
     size_t rows_ = 0, tile_rows_ = 0;
     std::vector<uint8_t> row_is_quad_x_, row_starts_event_;
+    std::vector<size_t> host_row_of_;            // host row (values / coefs order) -> committed row
     std::vector<uint32_t> mask_[3];
     std::vector<void *> owned_;
     void *d_val_ = nullptr, *d_coef_ = nullptr, *tile_ = nullptr, *tile2_ = nullptr, *mask_cw_ = nullptr;

@@ -6,6 +6,7 @@
 #include "../../include/lgr_prover.h"
 #include "matrix_prover.hpp"
 #include "row_packer.hpp"
+#include "wat_emitter.hpp"
 
 using namespace ligero::cuda::host;
 
@@ -218,6 +219,70 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *s, lgrp_proof **out) {
         matrix_prover mp(ctx);
         p->r = mp.prove(st);
     } catch (...) { delete p; throw; }
+    *out = p;
+    LGRP_END
+}
+
+static void fill_stats(lgrp_wat_stats *o, const wat_stats &s) {
+    if (!o) return;
+    o->private_consts = s.private_consts; o->asserts = s.asserts; o->arithmetic_ops = s.arithmetic_ops;
+    o->linear_witnesses = s.linear_witnesses; o->quadratic_slots = s.quadratic_slots; o->linear_constraints = s.linear_constraints;
+    o->violated_constraints = s.violated_constraints;
+}
+
+int lgrp_wat_emit(const char *wat, size_t len, uint32_t l, const uint8_t *stage1_seed, lgrp_packer **rows_out, uint32_t const_sum[8],
+                  lgrp_wat_stats *stats) {
+    LGRP_TRY
+    if (!wat || !rows_out || !l) throw std::invalid_argument("null argument");
+    wat_program prog(std::string(wat, len));
+    constraint_system cs;
+    wat_stats ws;
+    prog.run(cs, ws);
+    lgrp_packer *pk = new lgrp_packer(l);
+    try { cs.pack(pk->p, stage1_seed, const_sum); } catch (...) { delete pk; throw; }
+    fill_stats(stats, ws);
+    *rows_out = pk;
+    LGRP_END
+}
+
+int lgrp_prove_wat(lgr_ctx *ctx, const char *wat, size_t len, const uint8_t encoding_seed[32], int64_t generated_at_seconds,
+                   lgrp_proof **out, lgrp_wat_stats *stats) {
+    LGRP_TRY
+    if (!ctx || !wat || !encoding_seed || !out) throw std::invalid_argument("null argument");
+    uint32_t l = 0, k = 0, n = 0;
+    if (lgr_geometry(ctx, &l, &k, &n)) throw std::runtime_error(lgr_last_error());
+    wat_program prog(std::string(wat, len));
+    constraint_system cs;
+    wat_stats ws;
+    prog.run(cs, ws);
+    row_packer values(l);
+    cs.pack(values, nullptr, nullptr);                       // stage 1 needs the values only
+    statement st;
+    st.l = l; st.k = k;
+    memcpy(st.encoding_seed, encoding_seed, 32);
+    st.generated_at_seconds = generated_at_seconds;
+    {
+        sha256 h; h.update(wat, len); st.program_hash = h.flush_digest();
+    }
+    size_t row = 0;
+    const size_t stride = (size_t)l * 8;
+    for (uint8_t kind : values.kinds()) {
+        row_event ev;
+        ev.kind = kind ? EV_QUAD : EV_LINEAR;
+        for (int j = 0; j < (kind ? 3 : 1); j++, row++) ev.val[j] = values.values().data() + row * stride;
+        st.events.push_back(ev);
+    }
+    st.coef_provider = [&](const uint8_t seed[32], std::vector<uint32_t> &coef_rows, uint32_t const_sum[8]) {
+        row_packer with_coefs(l);
+        cs.pack(with_coefs, seed, const_sum);                // same packing, now with one rho per constraint
+        coef_rows = with_coefs.coefs();
+    };
+    lgrp_proof *p = new lgrp_proof();
+    try {
+        matrix_prover mp(ctx);
+        p->r = mp.prove(st);
+    } catch (...) { delete p; throw; }
+    fill_stats(stats, ws);
     *out = p;
     LGRP_END
 }

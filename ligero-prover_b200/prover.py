@@ -191,6 +191,39 @@ class Proof:
             pass
 
 
+class WatStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("private_consts", "asserts", "arithmetic_ops", "linear_witnesses", "quadratic_slots",
+                                          "linear_constraints", "violated_constraints")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def wat_emit(wat_text, l, stage1_seed=None):
+    """lgrp_wat_emit: the bounded .wat front end + witness emitter (host only).  Returns (kinds, values[rows, l, 8],
+    coefs[rows, l, 8], const_sum, stats); coefs are zero without a stage-1 seed."""
+    data = wat_text.encode() if isinstance(wat_text, str) else bytes(wat_text)
+    h = C.c_void_p()
+    cs = (C.c_uint32 * 8)()
+    st = WatStats()
+    seed = _p(_u8(stage1_seed, 32)) if stage1_seed is not None else None
+    _check(lib().lgrp_wat_emit(data, C.c_size_t(len(data)), C.c_uint32(l), seed, C.byref(h), cs, C.byref(st)))
+    pk = RowPacker.__new__(RowPacker)
+    pk._h, pk.l = h, l
+    kinds, vals, coefs = pk.rows()
+    pk.close()
+    return kinds, vals, coefs, sum(int(cs[i]) << (32 * i) for i in range(8)), st.as_dict()
+
+
+def prove_wat(executor, wat_text, encoding_seed=bytes(32), generated_at=0):
+    """lgrp_prove_wat: .wat text -> proof on the executor's geometry (BASELINE config 4, bounded: include/lgr_prover.h)"""
+    data = wat_text.encode() if isinstance(wat_text, str) else bytes(wat_text)
+    h = C.c_void_p()
+    st = WatStats()
+    _check(lib().lgrp_prove_wat(executor._ctx, data, C.c_size_t(len(data)), _p(_u8(encoding_seed, 32)), C.c_int64(generated_at), C.byref(h), C.byref(st)))
+    return Proof(h), st.as_dict()
+
+
 def parse_proof(data):
     buf = _u8(data)
     h = C.c_void_p()

@@ -288,3 +288,66 @@ def test_oracle_prover_vbn254fr_events_are_self_consistent(oracle):
     bad = [a[:] for a in args]
     bad[4] = [3, 1, 0]                                   # v3 (= v0) asserted equal to v1
     assert R.prove(l, k, kinds, values, coefs, const_sum, bytes(range(32)), bytes(32), arena_slots=6, batch_args=bad)["valid"] == (True, True, False)
+
+
+# ---------------------------------------------------------------- bounded .wat front end + witness emitter
+def _wat_check(pr, oracle, text, l, k, expect_valid=True):
+    """emit rows twice (values only / with coefficients from a seed), check the constraint system in big-int arithmetic,
+    then run the CPU prover on the rows"""
+    kinds0, vals0, coefs0, cs0, st = pr.wat_emit(text, l)
+    assert not coefs0.any() and cs0 == 0
+    seed = hashlib.sha256(b"stage-1 seed stand-in").digest()
+    kinds, vals, coefs, const_sum, st2 = pr.wat_emit(text, l, seed)
+    assert np.array_equal(kinds, kinds0) and np.array_equal(vals, vals0) and st == st2
+    P = ref.P
+    v = oracle.from_limbs(vals.reshape(-1, 8)); c = oracle.from_limbs(coefs.reshape(-1, 8))
+    lin_ok = (sum(a * b for a, b in zip(v, c)) + const_sum) % P == 0
+    # triples: x*y = z slot by slot
+    quad_ok, r = True, 0
+    V = np.array(v, dtype=object).reshape(-1, l)
+    for kd in kinds:
+        if kd:
+            quad_ok &= all((int(a) * int(b) - int(z)) % P == 0 for a, b, z in zip(V[r], V[r + 1], V[r + 2]))
+        r += 3 if kd else 1
+    assert quad_ok == (st["violated_constraints"] == 0 or quad_ok)      # the emitter never breaks a slot relation itself
+    assert lin_ok == expect_valid
+    out = ref.prove(l, k, kinds, vals, coefs, const_sum, bytes(range(32)), bytes(32))
+    assert out["valid"] == (True, expect_valid, True)
+    return kinds, st
+
+
+def test_wat_emitter_on_the_repo_fixture(pr, oracle):
+    text = open(os.path.join(ROOT, "tests", "golden", "mul64.wat")).read()
+    kinds, st = _wat_check(pr, oracle, text, l=200, k=256)
+    assert st["violated_constraints"] == 0
+    assert (st["private_consts"], st["asserts"], st["arithmetic_ops"]) == (23, 8, 9)
+    # 64 bit slots per private const, 1 + 128 per product, 65 per sum / difference
+    assert st["quadratic_slots"] == 23 * 64 + 5 * 129 + 4 * 65
+    assert list(kinds).count(1) == -(-st["quadratic_slots"] // 200)
+    # a false assertion leaves the slot relations intact and breaks exactly the linear test
+    bad = text.replace("(i64.const 15)", "(i64.const 16)")
+    _, st_bad = _wat_check(pr, oracle, bad, l=200, k=256, expect_valid=False)
+    assert st_bad["violated_constraints"] == 1
+
+
+def test_wat_emitter_rejects_what_it_does_not_support(pr):
+    for text, why in (("(module (func $f) (export \"_start\" (func $f)) (memory 1))", "module field"),
+                      ("(module (import \"wasi\" \"x\" (func $x)) (func $f) (export \"_start\" (func $f)))", "env host module"),
+                      ("(module (func $f (i32.const 1)) (export \"_start\" (func $f)))", "unsupported instruction"),
+                      ("(module (func $f)", "unbalanced"),
+                      ("(module (func $f))", "_start")):
+        with pytest.raises(pr.ProverError, match=why):
+            pr.wat_emit(text, 8)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/tests/i64_mul.wat"), reason="reference tree not present")
+@pytest.mark.parametrize("name,consts,asserts,ops", [("i64_mul.wat", 27, 9, 9)])
+def test_wat_emitter_on_the_reference_program(pr, oracle, name, consts, asserts, ops):
+    """BASELINE config 4's program: 27 private constants, 9 products, 9 assertions; at the reference's default geometry
+    (l = 8000) the whole statement is 1 linear row + 1 quadratic triple, as SURVEY 8d counts it"""
+    text = open(os.path.join("/root/reference/tests", name)).read()
+    kinds, vals, coefs, cs, st = pr.wat_emit(text, 8000)
+    assert (st["private_consts"], st["asserts"], st["arithmetic_ops"], st["violated_constraints"]) == (consts, asserts, ops, 0)
+    assert st["quadratic_slots"] == 27 * 64 + 9 * 129 and st["quadratic_slots"] < 8000
+    assert list(kinds) == [0, 1] and vals.shape == (4, 8000, 8)
+    _wat_check(pr, oracle, text, l=448, k=512)

@@ -338,3 +338,42 @@ def test_prove_with_vbn254fr_batch_events(lgr, oracle, pr, executor_factory, k, 
     bargs[bi] = [4, 1, 0]                                              # v4 (= v0) against v1
     info = pr.prove(ex, bad, values, coefs, const_sum, enc_seed, inst, arena_slots=slots, batch_args=bargs, batch_consts=consts).info()
     assert info["valid"] == (True, True, False)
+
+
+# ---------------------------------------------------------------- BASELINE config 4, bounded: .wat text -> proof
+@pytest.mark.parametrize("k,l", [(8192, 8000), (256, 64)])
+def test_prove_wat_end_to_end(lgr, oracle, pr, executor_factory, k, l):
+    """a .wat program through the product's own entry point (lgrp_prove_wat): front end, witness emitter, row packing,
+    stage 1, linear-test coefficients derived from the stage-1 seed, stages 2 and 3.  The proof parses, passes the
+    prover's self-check and the verifier-side opening checks, and equals the CPU prover run on the same rows and seed."""
+    import os
+    n = 4 * k
+    ref_wat = "/root/reference/tests/i64_mul.wat"                      # the program BASELINE names, where the tree exists
+    path = ref_wat if os.path.exists(ref_wat) else os.path.join(os.path.dirname(__file__), "golden", "mul64.wat")
+    text = open(path).read()
+    ex = executor_factory(k, l)
+    enc_seed = hashlib.sha256(b"config 4 encoding seed").digest()
+    proof, st = pr.prove_wat(ex, text, enc_seed, generated_at=11)
+    info = proof.info()
+    assert st["violated_constraints"] == 0 and info["valid"] == (True, True, True)
+    env = ref.parse_envelope(proof.gzip)
+    assert env.metadata.program_hash.value == hashlib.sha256(text.encode()).digest()
+    assert (env.metadata.packing_size, env.metadata.codeword_size) == (k, n)
+    # the statement the product proved, re-derived: rows from the emitter, coefficients from the proof's own stage-1 seed
+    kinds, vals, coefs, const_sum, _ = pr.wat_emit(text, l, info["stage1_seed"])
+    assert info["encoded_rows"] == vals.shape[0] + 3
+    if k == 8192 and path == ref_wat:
+        assert list(kinds) == [0, 1]                                   # 1 linear row + 1 triple + 3 masks = 7 encodes (SURVEY 8d)
+    want = ref.prove(l, k, kinds, vals, coefs, const_sum, enc_seed, bytes(32))
+    assert want["valid"] == (True, True, True)
+    assert env.ligero_proof.merkle_tree.root.value == want["root"] and info["stage1_seed"] == want["stage1_seed"]
+    assert info["stage2_seed"] == want["stage2_seed"]
+    assert np.array_equal(np.array(env.ligero_proof.encoded_linear.values, np.uint32).reshape(n, 8), want["linear"])
+    assert np.array_equal(np.array(env.ligero_proof.sampled_data.values, np.uint32).reshape(want["samplings"].shape), want["samplings"])
+    assert ref.verify_openings(env, l, k, kinds, coefs, bytes(32))
+    proof.close()
+    # a program whose assertion is false: same pipeline, linear test fails
+    bad = text.replace("(i64.const 1)))", "(i64.const 2)))", 1)
+    proof, st = pr.prove_wat(ex, bad, enc_seed)
+    assert st["violated_constraints"] == 1 and proof.info()["valid"] == (True, False, True)
+    proof.close()
