@@ -100,7 +100,7 @@ struct cuda_context {
     cuda_context() = default;
     cuda_context(const cuda_context &) = delete;
     cuda_context &operator=(const cuda_context &) = delete;
-    ~cuda_context() { if (ctx_) lgr_destroy(ctx_); }
+    ~cuda_context() = default;                       // the lgr_ctx dies with the LAST owner: this executor or any buffer it handed out
 
     // ---- lifecycle (wgpu.hpp:73-82) ----
     void webgpu_init(size_t /*num_hardware_cores*/, std::filesystem::path /*shader_root_path*/ = "") {}
@@ -111,6 +111,7 @@ struct cuda_context {
         device_bignum_type P(p), wk(root_k), w2k(root_2k), wn(root_n);
         if (lgr_create(&ctx_, device_, origin_size, padded_size, code_size, P.data(), wk.data(), w2k.data(), wn.data()) != LGR_OK)
             throw std::runtime_error(std::string("Cannot initialise the CUDA executor: ") + lgr_last_error());
+        owner_ = std::shared_ptr<lgr_ctx>(ctx_, [](lgr_ctx *c) { lgr_destroy(c); });
         size_l_ = origin_size; size_k_ = padded_size; size_n_ = code_size;
     }
     void device_synchronize() { cuda::check(lgr_sync(ctx_), "device_synchronize"); }
@@ -124,8 +125,10 @@ struct cuda_context {
     buffer_type make_device_buffer(size_t num_bytes) {
         void *p = nullptr;
         cuda::check(lgr_alloc(ctx_, num_bytes, &p), "make_device_buffer");
-        lgr_ctx *c = ctx_;
-        return buffer_type(std::shared_ptr<void>(p, [c](void *q) { lgr_free(c, q); }), 0, num_bytes);
+        // the deleter co-owns the context: a buffer_view / buffer_binding that outlives the executor (stage contexts keep
+        // them as members) releases into a live context; lgr_free is stream-ordered, so temporaries cost no synchronisation
+        std::shared_ptr<lgr_ctx> c = owner_;
+        return buffer_type(std::shared_ptr<void>(p, [c](void *q) { lgr_free(c.get(), q); }), 0, num_bytes);
     }
     buffer_type make_uniform_buffer(size_t num_bytes) { return make_device_buffer(num_bytes); }
     buffer_type make_message_buffer() { return make_device_buffer(message_size() * device_bignum_type::num_bytes); }
@@ -261,6 +264,7 @@ private:
     }
 
     lgr_ctx *ctx_ = nullptr;
+    std::shared_ptr<lgr_ctx> owner_;
     int device_ = 0;
     uint32_t size_l_ = 0, size_k_ = 0, size_n_ = 0, sha_instances_ = 0;
     size_t num_samplings_ = 0;
