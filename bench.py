@@ -432,6 +432,7 @@ def main():
                 exact_k8192 = run_exact(lgr, torch, dist, dev, stream, rank, world, 8192, 1 << 15, hbm)
             else:
                 k8192 = run_k8192_single(lgr, torch, dev, stream, 1 << 15)
+                k8192["per_row_drop_in"] = run_per_row(local_rank)
 
     if rank == 0:
         line = {
@@ -580,6 +581,20 @@ def run_k8192_single(lgr, torch, dev, stream, total_rows):
     del host
     ex.close()
     return out
+
+
+def run_per_row(device_index):
+    """the per-row schedule the reference's stage contexts issue (one row per callback, nonbatch_context.hpp:445-451,673-780)
+    through the C++ drop-in adapter (ligero::cuda_context): tests/cpp/per_row_bench.cpp, k = 8192"""
+    exe = os.path.join(ROOT, "tests", "cpp", "per_row_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "tests/cpp/per_row_bench is not built (make -C tests/cpp)"}
+    try:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device_index)))
+        out = subprocess.run([exe, "4096", "512"], capture_output=True, text=True, timeout=120, env=env)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:                                   # noqa: BLE001 -- an auxiliary measurement must not sink the bench line
+        return {"unavailable": "per_row_bench failed: %s" % e}
 
 
 def run_config5(ex, torch, dist, stream, dev, witness, wbuf, rank, world, k, n):

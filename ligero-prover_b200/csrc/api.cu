@@ -75,8 +75,15 @@ struct lgr_ctx {
     fr_mem *scratch = nullptr; size_t scratch_elems = 0;
     fr_mem *tile[2] = {nullptr, nullptr}; size_t tile_elems = 0;
     uint32_t *commit_sha = nullptr;
-    void *staging = nullptr; size_t staging_bytes = 0;      // pinned host staging for lgr_write
-    cudaEvent_t ev_staging = nullptr;
+    // pinned host staging for lgr_write: a ring of kStagingSlots slots, each with its own completion event, so that the
+    // host can stage upload i+1 .. i+7 while upload i is still queued behind the kernels of earlier rows
+    static constexpr int kStagingSlots = 8;
+    void *staging = nullptr; size_t staging_bytes = 0;      // bytes per slot
+    cudaEvent_t ev_staging[kStagingSlots] = {};
+    int staging_next = 0;
+    // one-row encodes at large k are 5 small launches: replayed as a CUDA graph per codeword buffer (lgr_encode)
+    std::map<void *, cudaGraphExec_t> encode_graphs;
+    std::map<void *, int> encode_seen;
     uint32_t *sample_idx = nullptr; uint32_t sample_count = 0;
     // per-kernel timing of the commit pipeline (lgr_profile): events on the launching streams
     bool profiling = false;
@@ -106,6 +113,8 @@ static int upload(lgr_ctx *c, const std::vector<Fr> &v, DevTable &t) {
 static int ensure_scratch(lgr_ctx *c, size_t elems) {
     if (c->scratch_elems >= elems) return LGR_OK;
     if (c->scratch) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->scratch)); c->scratch = nullptr; c->scratch_elems = 0; }
+    for (auto &g : c->encode_graphs) cudaGraphExecDestroy(g.second);        // they hold the old scratch address
+    c->encode_graphs.clear();
     CU(cudaMalloc((void **)&c->scratch, elems * 32));
     c->scratch_elems = elems;
     return LGR_OK;
@@ -329,6 +338,23 @@ static int encode_rows_impl(lgr_ctx *c, const fr_mem *rows, size_t row_stride, u
     REQUIRE(c->logk > ntt_tile_max_logm(), "internal: small k takes the fused encoder");
     const size_t k = c->k;
     int rc;
+    // a handful of rows (the per-row schedule of the reference's stage contexts): ONE launch on thread-block clusters, the row
+    // resident in distributed shared memory (cluster_encode_kernel.cu).  Measured on B200 (profiles/r02_per_row.md): 75 us per
+    // one-row launch against 54 us for the five latency-kernel launches of the path below (26 dependent butterfly stages on
+    // 32 SMs at 4 warps per scheduler), so it is OFF by default; LGR_CLUSTER_ENCODE_ROWS=<rows> turns it on for up to that
+    // many rows per call (the parity suite runs it that way once).
+    static const uint32_t cluster_max_rows = getenv("LGR_CLUSTER_ENCODE_ROWS") ? (uint32_t)atoi(getenv("LGR_CLUSTER_ENCODE_ROWS")) : 0u;
+    if (nrows <= cluster_max_rows && encode_rows_cluster_ok(c->logk)) {
+        if ((rc = build_encode_tables(c))) return rc;
+        const fr_mem *src = rows; long long src_stride = (long long)row_stride;
+        if (!sink.nslabs && rows == cw) {                       // in place: the clusters of a row read it while others write the codeword
+            if ((rc = ensure_scratch(c, (size_t)nrows * k))) return rc;
+            CU(cudaMemcpy2DAsync(c->scratch, k * 32, rows, row_stride * 32, k * 32, nrows, cudaMemcpyDeviceToDevice, st));
+            src = c->scratch; src_stride = (long long)k;
+        }
+        CU(launch_encode_rows_cluster(src, src_stride, sink, (int)nrows, c->logk, c->enc, st)); c->launches++;
+        return LGR_OK;
+    }
     if ((rc = build_large_encode_tables(c))) return rc;
     NttPlan *pi, *pf;
     if ((rc = get_plan(c, c->logk, c->root_k, true, &pi))) return rc;
@@ -367,7 +393,7 @@ static int create_body(lgr_ctx *c, int device, uint32_t l, uint32_t k, uint32_t 
     }
     CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_staging, cudaEventDisableTiming));
+    for (int i = 0; i < lgr_ctx::kStagingSlots; i++) CU(cudaEventCreateWithFlags(&c->ev_staging[i], cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
@@ -424,7 +450,8 @@ int lgr_destroy(lgr_ctx *c) {
     if (c->staging) cudaFreeHost(c->staging);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_staging) cudaEventDestroy(c->ev_staging);
+    for (int i = 0; i < lgr_ctx::kStagingSlots; i++) if (c->ev_staging[i]) cudaEventDestroy(c->ev_staging[i]);
+    for (auto &g : c->encode_graphs) cudaGraphExecDestroy(g.second);
     for (int i = 0; i < 2; i++) { if (c->h2d_buf[i]) cudaFree(c->h2d_buf[i]); if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if (c->ev_h2d_free[i]) cudaEventDestroy(c->ev_h2d_free[i]); }
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (auto &pr : c->prof_enc) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -462,18 +489,24 @@ int lgr_free(lgr_ctx *c, void *dptr) { ENTER(c);
 int lgr_write(lgr_ctx *c, void *dst, size_t off, const void *src, size_t bytes) { ENTER(c);
     REQUIRE(c && dst && (src || !bytes), "null argument");
     if (!bytes) return LGR_OK;
-    // the caller may reuse `src` immediately (nonbatch_context.hpp:455-468): stage through pinned memory
+    // the caller may reuse `src` immediately (nonbatch_context.hpp:455-468): stage through pinned memory.  Each slot of
+    // the ring waits only for ITS previous upload, so the host runs up to kStagingSlots uploads ahead of the device.
     if (c->staging_bytes < bytes) {
-        if (c->staging) { CU(cudaEventSynchronize(c->ev_staging)); CU(cudaFreeHost(c->staging)); c->staging = nullptr; c->staging_bytes = 0; }
+        if (c->staging) {
+            for (int i = 0; i < lgr_ctx::kStagingSlots; i++) CU(cudaEventSynchronize(c->ev_staging[i]));
+            CU(cudaFreeHost(c->staging)); c->staging = nullptr; c->staging_bytes = 0;
+        }
         size_t cap = std::max(bytes, (size_t)1 << 20);
-        CU(cudaMallocHost(&c->staging, cap));
+        CU(cudaMallocHost(&c->staging, cap * lgr_ctx::kStagingSlots));
         c->staging_bytes = cap;
-    } else {
-        CU(cudaEventSynchronize(c->ev_staging));       // previous upload must have left the staging buffer
     }
-    memcpy(c->staging, src, bytes);
-    CU(cudaMemcpyAsync((char *)dst + off, c->staging, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaEventRecord(c->ev_staging, c->stream));
+    const int slot = c->staging_next;
+    c->staging_next = (slot + 1) % lgr_ctx::kStagingSlots;
+    CU(cudaEventSynchronize(c->ev_staging[slot]));
+    char *stage = (char *)c->staging + (size_t)slot * c->staging_bytes;
+    memcpy(stage, src, bytes);
+    CU(cudaMemcpyAsync((char *)dst + off, stage, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev_staging[slot], c->stream));
     return LGR_OK;
 }
 int lgr_clear(lgr_ctx *c, void *dst, size_t off, size_t bytes) { ENTER(c);
@@ -483,6 +516,14 @@ int lgr_clear(lgr_ctx *c, void *dst, size_t off, size_t bytes) { ENTER(c);
 }
 int lgr_write_clear(lgr_ctx *c, void *dst, size_t dst_bytes, const void *src, size_t bytes) { ENTER(c);
     REQUIRE(bytes <= dst_bytes, "write_buffer_clear: source larger than destination");
+    // The stage contexts export every row into a 2k-element scratch whose tail is zero (nonbatch_context.hpp:415,455-468):
+    // trailing zero elements are not staged or sent -- the clear below covers them.
+    if (src && (bytes & 31) == 0 && (((uintptr_t)src) & 7) == 0) {
+        const uint64_t *w = (const uint64_t *)src;
+        size_t e = bytes / 32;
+        while (e > 0 && !(w[4 * e - 1] | w[4 * e - 2] | w[4 * e - 3] | w[4 * e - 4])) e--;
+        bytes = e * 32;
+    }
     int rc = lgr_write(c, dst, 0, src, bytes);
     if (rc) return rc;
     return lgr_clear(c, dst, bytes, dst_bytes - bytes);
@@ -523,6 +564,34 @@ int lgr_ntt_pow2(lgr_ctx *c, void *buf, uint32_t logn, uint32_t batch, const uin
 }
 int lgr_encode(lgr_ctx *c, void *buf) { ENTER(c);
     REQUIRE(c && buf, "null argument");
+    // Large k: a one-row encode is 5 small launches + a copy on the tile engine.  The stage contexts call it on the same
+    // few codeword buffers for every row (nonbatch_context.hpp:445-468), so from the third call on a buffer the sequence is
+    // replayed as ONE CUDA-graph launch.  Only on the context's own stream (a caller-provided stream may be capturing).
+    static const bool use_graphs = !getenv("LGR_NO_ENCODE_GRAPH");
+    if (use_graphs && !fused_encode_ok(c) && c->stream == c->own_stream) {
+        auto it = c->encode_graphs.find(buf);
+        if (it != c->encode_graphs.end()) { CU(cudaGraphLaunch(it->second, c->stream)); c->launches += 6; return LGR_OK; }
+        if (++c->encode_seen[buf] >= 3 && c->encode_graphs.size() < 64) {       // tables, plans and scratch exist by now
+            const uint64_t before = c->launches;
+            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = encode_rows_impl(c, (const fr_mem *)buf, c->n, 1, plain_sink((fr_mem *)buf, c->n), c->stream);
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            c->launches = before;
+            if (rc == LGR_OK && e == cudaSuccess && g) {
+                cudaGraphExec_t ge = nullptr;
+                e = cudaGraphInstantiate(&ge, g, 0);
+                cudaGraphDestroy(g);
+                if (e == cudaSuccess) {
+                    c->encode_graphs[buf] = ge;
+                    CU(cudaGraphLaunch(ge, c->stream)); c->launches += 6;
+                    return LGR_OK;
+                }
+            } else if (g) cudaGraphDestroy(g);
+            cudaGetLastError();                                                  // capture refused: fall through to plain launches
+            c->encode_seen[buf] = -1000000;
+        }
+    }
     return encode_rows_impl(c, (const fr_mem *)buf, c->n, 1, plain_sink((fr_mem *)buf, c->n), c->stream);
 }
 int lgr_encode_rows(lgr_ctx *c, const void *rows, uint64_t row_stride, uint32_t nrows, void *cw) { ENTER(c);

@@ -1,5 +1,6 @@
 // Size dispatch for the per-size translation units (encode_kernels.cu, ntt_kernels.cu are each
 // compiled once per log2 size, see Makefile).
+#include <cstdlib>
 #include "kernels.h"
 
 namespace lgr {
@@ -23,7 +24,16 @@ cudaError_t launch_encode_rows(const fr_mem *rows_in, long long in_row_stride, c
     }
 }
 
+cudaError_t launch_ntt_lat(const NttTileParams &p, cudaStream_t st);
+
+// jobs of at most this many points go to the latency-oriented kernel (lat_ntt_kernel.cu); LGR_NTT_LAT_MAX=0 disables it
+static long long lat_max_points() {
+    static const long long v = getenv("LGR_NTT_LAT_MAX") ? atoll(getenv("LGR_NTT_LAT_MAX")) : (1ll << 16);
+    return v;
+}
+
 cudaError_t launch_ntt_tile(const NttTileParams &p, cudaStream_t st) {
+    if (((long long)p.total_lanes << p.logm) <= lat_max_points()) return launch_ntt_lat(p, st);
     switch (p.logm) {
 #define LGR_CASE_NTT(L) case L: return launch_ntt_tile_##L(p, st);
         LGR_CASE_NTT(1) LGR_CASE_NTT(2) LGR_CASE_NTT(3) LGR_CASE_NTT(4) LGR_CASE_NTT(5) LGR_CASE_NTT(6) LGR_CASE_NTT(7) LGR_CASE_NTT(8) LGR_CASE_NTT(9) LGR_CASE_NTT(10) LGR_CASE_NTT(11)

@@ -69,6 +69,10 @@ cudaError_t launch_encode_rows(const fr_mem *rows_in, long long in_row_stride, c
                                int R, int logk, const EncodeTables &t, cudaStream_t st);
 // coset 0 of the large-k encoder: codeword[row][4m] = canonical(rows[row][c*m mod k])
 cudaError_t launch_sys_copy(const fr_mem *rows, long long row_stride, const CodewordSink &sink, int R, int logk, uint32_t c, cudaStream_t st);
+// one-launch encode of a few rows at k = 4096 / 8192 on thread-block clusters (cluster_encode_kernel.cu); rows must not alias the sink
+bool encode_rows_cluster_ok(int logk);
+cudaError_t launch_encode_rows_cluster(const fr_mem *rows, long long row_stride, const CodewordSink &sink, int R, int logk,
+                                       const EncodeTables &t, cudaStream_t st);
 int encode_rows_max_logk();
 int encode_rows_min_logk();
 

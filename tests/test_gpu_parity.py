@@ -802,3 +802,38 @@ def test_peer_wait_times_out_instead_of_hanging(lgr, executor_factory):
     ex.read_into(host, ptr + 192, 4)
     assert int(host[0]) == 0
     ex.ipc_free(ptr)
+
+
+@pytest.mark.parametrize("env", [{"LGR_CLUSTER_ENCODE_ROWS": "4"}, {"LGR_NTT_LAT_MAX": "0"}, {"LGR_NO_ENCODE_GRAPH": "1"}],
+                         ids=["cluster-encoder", "no-latency-kernel", "no-graph-replay"])
+def test_alternative_encode_paths_forced(env):
+    """the encode paths that are not the default for their size must stay bit-exact: the thread-block-cluster one-launch
+    encoder (csrc/cluster_encode_kernel.cu, off by default), the throughput tile kernel for small jobs (latency kernel off),
+    plain launches instead of the CUDA-graph replay of one-row encodes"""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, %r)
+        import numpy as np
+        import __graft_entry__ as ge
+        from oracle import lgo
+        lgr = ge._load_package()
+        for k in (4096, 8192):
+            n = 4 * k
+            ex = lgr.make_executor(k - 192, k)            # own stream: the graph replay path is live
+            rows = lgo.synth(11, 0, 3, k)
+            want = [lgo.encode(rows[r], k) for r in range(3)]
+            dev = ex.make_codeword_buffer(); bind = ex.bind_ntt(dev)
+            for rep in range(5):                          # the 3rd call on a buffer captures, later ones replay
+                ex.write_buffer_clear(dev, rows[rep %% 3]); ex.encode_ntt_device(bind)
+                assert np.array_equal(ex.read_elements(dev), want[rep %% 3]), (k, rep)
+            rb = ex.make_device_buffer(3 * k * 32); ex.write_buffer(rb, rows)
+            cw = ex.make_device_buffer(3 * n * 32); ex.encode_rows(rb, 3, cw)
+            assert np.array_equal(ex.read_elements(cw).reshape(3, n, 8), np.stack(want)), k
+            ex.decode_ntt_device(bind)
+            assert np.array_equal(ex.read_elements(dev)[:k], rows[4 %% 3]), k
+            ex.close()
+        print("ok")
+    """) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
