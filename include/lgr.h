@@ -190,12 +190,7 @@ int lgr_combine_linear(lgr_ctx *ctx, const void *tile_a, const void *tile_b, uin
 /* uniform canonical elements keyed by (seed,row,col): 256 bits >> 2, one conditional subtract
  * (include/zkp/finite_field_gmp.hpp:70-78); identical to the oracle's generator */
 int lgr_synth(lgr_ctx *ctx, void *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols);
-/* which: 0 = IMAD.WIDE chains, 1 = Montgomery multiply, 2 = SHA-256 compression, 3 = IMAD (low word)
- * chains, 4 = double-precision FMA chains, 5 = Shoup (table-constant) multiply; returns ops/s chip-wide */
-int lgr_ubench(lgr_ctx *ctx, int which, double *ops_per_sec);
-/* occupancy / ILP sweep of the Montgomery multiply; cycles per SHA-256 compression of a lone warp (ubench.cu) */
-int lgr_ubench_mont_occ(lgr_ctx *ctx, int nchain, int warps_per_sm, double *ops_per_sec);
-int lgr_ubench_chain(lgr_ctx *ctx, int variant, int warps_per_cta, int active_lanes, double *cycles);
+/* (micro-benchmarks live in include/lgr_ubench.h / liblgr_ubench.so, outside the drop-in library) */
 
 #ifdef __cplusplus
 }

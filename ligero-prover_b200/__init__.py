@@ -540,15 +540,49 @@ class Executor:
         _check(lib().lgr_synth(self._ctx, out.ptr(), C.c_uint64(seed), C.c_uint64(row0), C.c_uint64(nrows), C.c_uint64(ncols)))
 
     def ubench(self, which):
+        """chip-wide operations per second of one primitive (include/lgr_ubench.h, liblgr_ubench.so)"""
         v = C.c_double()
-        _check(lib().lgr_ubench(self._ctx, C.c_int(which), C.byref(v)))
+        _ucheck(ulib().lgru_ubench(C.c_int(self._device), C.c_int(which), C.byref(v)))
         return v.value
 
     def ubench_chain(self, variant, warps_per_cta=1, active_lanes=32):
         """cycles per SHA-256 compression of a lone warp (csrc/ubench.cu variants)"""
         v = C.c_double()
-        _check(lib().lgr_ubench_chain(self._ctx, C.c_int(variant), C.c_int(warps_per_cta), C.c_int(active_lanes), C.byref(v)))
+        _ucheck(ulib().lgru_chain(C.c_int(self._device), C.c_int(variant), C.c_int(warps_per_cta), C.c_int(active_lanes), C.byref(v)))
         return v.value
+
+    def ubench_overlap(self):
+        """(mont alone, sha alone, both) milliseconds: lgru_overlap"""
+        ms = (C.c_double * 3)()
+        _ucheck(ulib().lgru_overlap(C.c_int(self._device), ms))
+        return {"mont_alone_ms": ms[0], "sha_alone_ms": ms[1], "both_ms": ms[2], "overlap_efficiency": (ms[0] + ms[1] - ms[2]) / min(ms[0], ms[1])}
+
+    def dpf_mul(self, a, b):
+        """a*b*2^-260 mod p through the FP64-pipe Montgomery multiplication (csrc/dpf_mont.cuh); numpy [n, 8] uint32 in / out"""
+        a = np.ascontiguousarray(a, np.uint32).reshape(-1, 8); b = np.ascontiguousarray(b, np.uint32).reshape(-1, 8)
+        out = np.zeros_like(a)
+        _ucheck(ulib().lgru_dpf_mul(C.c_int(self._device), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_uint32(a.shape[0])))
+        return out
+
+
+_ulib = None
+
+
+def ulib():
+    """liblgr_ubench.so: micro-benchmarks, outside the drop-in library"""
+    global _ulib
+    if _ulib is None:
+        path = os.path.join(_HERE, "liblgr_ubench.so")
+        if not os.path.exists(path):
+            raise ImportError("liblgr_ubench.so is missing (%s); build it with `make -C %s`" % (path, _HERE))
+        _ulib = C.CDLL(path)
+        _ulib.lgru_last_error.restype = C.c_char_p
+    return _ulib
+
+
+def _ucheck(rc):
+    if rc != 0:
+        raise LgrError("lgr ubench error: %s" % ulib().lgru_last_error().decode())
 
 
 def make_executor(l, k, n=None, device=0):

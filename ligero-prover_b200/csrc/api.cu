@@ -833,12 +833,14 @@ static int upload_scalars(lgr_ctx *c, const uint32_t *host_r, uint32_t nrows, si
 int lgr_combine_code(lgr_ctx *c, const void *tile, uint32_t nrows, const uint32_t *host_r, void *acc) { ENTER(c);
     REQUIRE(c && tile && host_r && acc, "null argument");
     if (!nrows) return LGR_OK;
+    // scratch: partial sums | scaled scalars (T) | their Karatsuba halves (1.5 T) | raw scalars (T)
     const size_t part = combine_scratch_elems((int)nrows, (int)c->n);
-    int rc = ensure_scratch(c, part + 2 * (size_t)nrows);
+    int rc = ensure_scratch(c, part + 4 * (size_t)nrows);
     if (rc) return rc;
-    if ((rc = upload_scalars(c, host_r, nrows, part + nrows))) return rc;
-    CU(launch_combine_code((const fr_mem *)tile, (long long)c->n, (int)nrows, (int)c->n, c->scratch + part + nrows, (fr_mem *)acc, c->scratch, part + nrows, c->stream));
-    c->launches += 3;
+    if ((rc = upload_scalars(c, host_r, nrows, part + 3 * (size_t)nrows))) return rc;
+    CU(launch_combine_code((const fr_mem *)tile, (long long)c->n, (int)nrows, (int)c->n, c->scratch + part + 3 * (size_t)nrows, (fr_mem *)acc, c->scratch,
+                           part + 3 * (size_t)nrows, c->stream));
+    c->launches += 4;
     return LGR_OK;
 }
 int lgr_combine_quad(lgr_ctx *c, const void *x, const void *y, const void *z, uint32_t nrows, const uint32_t *host_r, void *acc) { ENTER(c);
@@ -961,67 +963,10 @@ int lgr_peer_wait(lgr_ctx *c, const void *flags, uint32_t nflags, uint64_t value
     return LGR_OK;
 }
 
-// ---- synthetic data / micro-benchmarks ---------------------------------------------------------
+// ---- synthetic data ---------------------------------------------------------
 int lgr_synth(lgr_ctx *c, void *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols) { ENTER(c);
     REQUIRE(c && out, "null argument");
     CU(launch_synth((fr_mem *)out, seed, row0, nrows, ncols, c->stream)); c->launches++;
     return LGR_OK;
 }
-int lgr_ubench(lgr_ctx *c, int which, double *ops) { ENTER(c);
-    REQUIRE(c && ops, "null argument");
-    REQUIRE(which >= 0 && which <= 5, "unknown micro-benchmark");
-    uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
-    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    const int blocks = 148 * 8, threads = 256;
-    const bool mulbench = (which == 1 || which == 5);           // Montgomery / Shoup multiplications, 4 per iteration
-    const int iters = mulbench ? 512 : ((which == 0 || which >= 3) ? 4096 : 256);
-    CU(launch_ubench(which, d, iters, blocks, threads, c->stream));           // warm-up
-    CU(cudaEventRecord(e0, c->stream));
-    for (int i = 0; i < 5; i++) CU(launch_ubench(which, d, iters, blocks, threads, c->stream));
-    CU(cudaEventRecord(e1, c->stream));
-    CU(cudaEventSynchronize(e1));
-    c->launches += 6;
-    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
-    const double per_thread = mulbench ? 4.0 * iters : ((which == 0 || which >= 3) ? 8.0 * iters : (double)iters);
-    *ops = 5.0 * per_thread * blocks * threads / (ms * 1e-3);
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
-    return LGR_OK;
-}
-
-// Montgomery multiplications per second with `warps_per_sm` resident warps and `nchain` independent
-// multiplications per thread (occupancy / ILP sweep)
-int lgr_ubench_mont_occ(lgr_ctx *c, int nchain, int warps_per_sm, double *ops) { ENTER(c);
-    REQUIRE(c && ops, "null argument");
-    REQUIRE((nchain == 1 || nchain == 2 || nchain == 4) && warps_per_sm >= 1 && warps_per_sm <= 32, "bad arguments");
-    uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 1024 * 4));
-    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    const int iters = 2048 / nchain;
-    CU(launch_ubench_mont_occ(nchain, warps_per_sm, d, iters, c->stream));
-    CU(cudaEventRecord(e0, c->stream));
-    CU(launch_ubench_mont_occ(nchain, warps_per_sm, d, iters, c->stream));
-    CU(cudaEventRecord(e1, c->stream));
-    CU(cudaEventSynchronize(e1));
-    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
-    *ops = (double)iters * nchain * 148.0 * warps_per_sm * 32 / (ms * 1e-3);
-    c->launches += 2;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
-    return LGR_OK;
-}
-
-// cycles per SHA-256 compression of one warp owning a scheduler (variant 3/4/5, see ubench.cu)
-int lgr_ubench_chain(lgr_ctx *c, int variant, int warps_per_cta, int active_lanes, double *cycles) { ENTER(c);
-    REQUIRE(c && cycles, "null argument");
-    REQUIRE(variant >= 3 && variant <= 25 && warps_per_cta >= 1 && warps_per_cta <= 4 && active_lanes >= 1 && active_lanes <= 32, "bad arguments");
-    uint32_t *d; CU(cudaMalloc((void **)&d, 148 * 8 * 256 * 4));
-    CU(launch_ubench_chain(variant, d, 64, warps_per_cta, active_lanes, c->stream));
-    CU(launch_ubench_chain(variant, d, 512, warps_per_cta, active_lanes, c->stream));
-    uint32_t cyc = 0;
-    CU(cudaMemcpyAsync(&cyc, d + 148 * 8 * 256 - 1, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    c->launches += 2;
-    *cycles = cyc;
-    cudaFree(d);
-    return LGR_OK;
-}
-
 }  // extern "C"

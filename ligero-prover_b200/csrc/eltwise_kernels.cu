@@ -7,6 +7,7 @@
 // for canonical inputs.  A canonical product x*y is two Montgomery multiplications
 // (x*y/R, then *R^2/R); a product with a host constant c is one (c is pre-multiplied by R).
 #include <algorithm>
+#include <cstdlib>
 #include "kernels.h"
 #include "ntt.cuh"
 
@@ -154,6 +155,49 @@ __global__ void combine_scale_kernel(const fr_mem *__restrict__ r, int T, fr_mem
     if (t < T) fr_stg(r_scaled + t, fr_reduce_p(fr_mont_mul(fr_ldg(r + t), fr_2p544())));
 }
 
+// r_kara[3t .. 3t+2] = halves of r_scaled[t] split at bit 127 and their sum (fr.cuh: kara_split), 16 bytes each
+__global__ void combine_split_kernel(const fr_mem *__restrict__ r_scaled, int T, uint4 *__restrict__ r_kara) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    fr_half r0, r1, rs;
+    kara_split(fr_ldg(r_scaled + t), r0, r1, rs);
+    r_kara[3 * t] = make_uint4(r0.v[0], r0.v[1], r0.v[2], r0.v[3]);
+    r_kara[3 * t + 1] = make_uint4(r1.v[0], r1.v[1], r1.v[2], r1.v[3]);
+    r_kara[3 * t + 2] = make_uint4(rs.v[0], rs.v[1], rs.v[2], rs.v[3]);
+}
+__device__ __forceinline__ fr_half half_ldc(const uint4 *p) { const uint4 q = __ldg(p); fr_half h; h.v[0] = q.x; h.v[1] = q.y; h.v[2] = q.z; h.v[3] = q.w; return h; }
+
+// check_code over a resident tile, Karatsuba form: per element three 128 x 128 products (48 wide multiply-adds) instead of
+// one 256 x 256 (64); the three partial sums are recombined and reduced once per 64-row chunk (fr.cuh: kara_reduce9)
+__global__ void __launch_bounds__(128) combine_code_kara_kernel(const fr_mem *__restrict__ a, long long row_stride, int T, int n,
+                                                                const uint4 *__restrict__ r_kara, fr_mem *__restrict__ partial) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.y;
+    if (j >= n) return;
+    const int t0 = chunk * kCombineChunk, t1 = min(T, t0 + kCombineChunk);
+    fr_kara_wide wl, wh, wm;
+    kara_zero(wl); kara_zero(wh); kara_zero(wm);
+    const fr_mem *pa = a + (long long)t0 * row_stride + j;
+    const uint4 *pr = r_kara + 3 * t0;
+    int t = t0;
+    for (; t + 1 < t1; t += 2) {                               // two rows in flight per thread
+        const fr_t e0 = fr_ldg(pa), e1 = fr_ldg(pa + row_stride);
+        fr_half x0, x1, xs;
+        kara_split(e0, x0, x1, xs);
+        kara_mad(wl, x0, half_ldc(pr)); kara_mad(wh, x1, half_ldc(pr + 1)); kara_mad(wm, xs, half_ldc(pr + 2));
+        kara_split(e1, x0, x1, xs);
+        kara_mad(wl, x0, half_ldc(pr + 3)); kara_mad(wh, x1, half_ldc(pr + 4)); kara_mad(wm, xs, half_ldc(pr + 5));
+        pa += 2 * row_stride;
+        pr += 6;
+    }
+    if (t < t1) {
+        fr_half x0, x1, xs;
+        kara_split(fr_ldg(pa), x0, x1, xs);
+        kara_mad(wl, x0, half_ldc(pr)); kara_mad(wh, x1, half_ldc(pr + 1)); kara_mad(wm, xs, half_ldc(pr + 2));
+    }
+    fr_stg(partial + (size_t)chunk * n + j, fr_reduce_p(kara_reduce9(wl, wh, wm)));
+}
+
 template <bool LINEAR>
 __global__ void __launch_bounds__(128) combine_partial_kernel(const fr_mem *__restrict__ a, const fr_mem *__restrict__ b, long long row_stride,
                                                               int T, int n, const fr_mem *__restrict__ r_scaled, fr_mem *__restrict__ partial) {
@@ -243,11 +287,18 @@ cudaError_t launch_combine_code(const fr_mem *tile, long long row_stride, int T,
                                 fr_mem *scratch, size_t scratch_elems, cudaStream_t st) {
     if (T <= 0 || n <= 0) return cudaSuccess;
     const int chunks = (T + kCombineChunk - 1) / kCombineChunk;
-    if (scratch_elems < (size_t)chunks * n + T) return cudaErrorInvalidValue;
+    if (scratch_elems < (size_t)chunks * n + 3 * (size_t)T) return cudaErrorInvalidValue;
     dim3 grid((n + 127) / 128, chunks);
     fr_mem *r_scaled = scratch + (size_t)chunks * n;
     combine_scale_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_raw, T, r_scaled);
-    combine_partial_kernel<false><<<grid, 128, 0, st>>>(tile, nullptr, row_stride, T, n, r_scaled, scratch);
+    static const bool kara = !(getenv("LGR_COMBINE_KARATSUBA") && atoi(getenv("LGR_COMBINE_KARATSUBA")) == 0);   // A/B knob
+    if (kara) {
+        uint4 *r_kara = reinterpret_cast<uint4 *>(r_scaled + T);             // 48 bytes per row, after the T scaled scalars
+        combine_split_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_scaled, T, r_kara);
+        combine_code_kara_kernel<<<grid, 128, 0, st>>>(tile, row_stride, T, n, r_kara, scratch);
+    } else {
+        combine_partial_kernel<false><<<grid, 128, 0, st>>>(tile, nullptr, row_stride, T, n, r_scaled, scratch);
+    }
     launch_fold(scratch, chunks, n, acc, st);
     return cudaGetLastError();
 }

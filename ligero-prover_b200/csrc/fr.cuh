@@ -301,20 +301,8 @@ LGR_DEV void wide_mad(fr_wide &w, const fr_t &a, const fr_t &b) {
         detail::cmad_n(w.e + i + 2, a.v + 1, b.v[i + 1]); w.c[i + 10] = addc(w.c[i + 10], 0); // odd j: limbs i+2..i+9
     }
 }
-LGR_DEV fr_t wide_reduce9(const fr_wide &w) {
-    uint32_t v[18];
-    // v = E + (O << 32) + (C << 32*limb)
-    v[0] = w.e[0];
-    v[1] = add_cc(w.e[1], w.o[0]);
-#pragma unroll
-    for (int i = 2; i < 16; i++) v[i] = addc_cc(w.e[i], w.o[i - 1]);
-    v[16] = addc_cc(0, 0);
-    v[17] = 0;
-    v[8] = add_cc(v[8], w.c[8]);
-#pragma unroll
-    for (int i = 9; i < 17; i++) v[i] = addc_cc(v[i], w.c[i]);
-    v[17] = addc(v[17], 0);
-    // 9 Montgomery rounds: v[r] becomes 0, the value shifts down by 288 bits in total
+// 9 Montgomery rounds on an 18-limb value: v[r] becomes 0, the value shifts down by 288 bits in total
+LGR_DEV fr_t reduce9_rounds(uint32_t *v) {
 #pragma unroll
     for (int r = 0; r < 9; r++) {
         const uint32_t m = mul_lo(v[r], LGR_M0);
@@ -335,6 +323,119 @@ LGR_DEV fr_t wide_reduce9(const fr_wide &w) {
 #pragma unroll
     for (int i = 0; i < 8; i++) res.v[i] = v[9 + i];
     return res;
+}
+LGR_DEV fr_t wide_reduce9(const fr_wide &w) {
+    uint32_t v[18];
+    // v = E + (O << 32) + (C << 32*limb)
+    v[0] = w.e[0];
+    v[1] = add_cc(w.e[1], w.o[0]);
+#pragma unroll
+    for (int i = 2; i < 16; i++) v[i] = addc_cc(w.e[i], w.o[i - 1]);
+    v[16] = addc_cc(0, 0);
+    v[17] = 0;
+    v[8] = add_cc(v[8], w.c[8]);
+#pragma unroll
+    for (int i = 9; i < 17; i++) v[i] = addc_cc(v[i], w.c[i]);
+    v[17] = addc(v[17], 0);
+    return reduce9_rounds(v);
+}
+
+// ---- Karatsuba form of the wide accumulation (check_code over a resident tile) ---------------------
+// Elements are < p < 2^254, so they split at bit 127 into two halves < 2^127 whose SUM still fits 128 bits:
+//   x = x0 + x1 * 2^127,   r * x = r0 x0 + [(r0 + r1)(x0 + x1) - r0 x0 - r1 x1] * 2^127 + r1 x1 * 2^254
+// Three 128 x 128 products (48 wide multiply-adds) instead of one 256 x 256 (64); the three partial sums are accumulated
+// unreduced over the rows of a chunk and recombined once per chunk.  The multiplier is what bounds the sweep
+// (DESIGN.md section 4), so the sweep gets 4/3 closer to the HBM roofline.
+struct fr_half { uint32_t v[4]; };
+struct fr_kara_wide { uint32_t e[8], o[7], c[9]; };        // 128x128 products: limbs 0..7, odd-aligned set, carries of limbs 4..8
+LGR_DEV void kara_zero(fr_kara_wide &w) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) w.e[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) w.o[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) w.c[i] = 0;
+}
+namespace detail {
+LGR_DEV void cmad_4(uint32_t *acc, const uint32_t *a, uint32_t bi) {      // acc[0..3] += {a[0], a[2]} * bi
+    acc[0] = mad_lo_cc(a[0], bi, acc[0]);
+    acc[1] = madc_hi_cc(a[0], bi, acc[1]);
+    acc[2] = madc_lo_cc(a[2], bi, acc[2]);
+    acc[3] = madc_hi_cc(a[2], bi, acc[3]);
+}
+}  // namespace detail
+LGR_DEV void kara_mad(fr_kara_wide &w, const fr_half &a, const fr_half &b) {
+    // a is read as a[0..4]: index 4 (beyond the half) is only touched by the odd rows through a+1 -> a[1], a[3]
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+        detail::cmad_4(w.e + i, a.v, b.v[i]);             w.c[i + 4] = addc(w.c[i + 4], 0);
+        detail::cmad_4(w.o + i, a.v + 1, b.v[i]);         w.c[i + 5] = addc(w.c[i + 5], 0);
+        detail::cmad_4(w.o + i, a.v, b.v[i + 1]);         w.c[i + 5] = addc(w.c[i + 5], 0);
+        detail::cmad_4(w.e + i + 2, a.v + 1, b.v[i + 1]); w.c[i + 6] = addc(w.c[i + 6], 0);
+    }
+}
+// x -> (x0, x1, x0 + x1) with x0 = x mod 2^127, x1 = x >> 127  (x < 2^254)
+LGR_DEV void kara_split(const fr_t &x, fr_half &x0, fr_half &x1, fr_half &xs) {
+    x0.v[0] = x.v[0]; x0.v[1] = x.v[1]; x0.v[2] = x.v[2]; x0.v[3] = x.v[3] & 0x7FFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 3; i++) x1.v[i] = (x.v[3 + i] >> 31) | (x.v[4 + i] << 1);
+    x1.v[3] = (x.v[6] >> 31) | (x.v[7] << 1);
+    xs.v[0] = add_cc(x0.v[0], x1.v[0]);
+    xs.v[1] = addc_cc(x0.v[1], x1.v[1]);
+    xs.v[2] = addc_cc(x0.v[2], x1.v[2]);
+    xs.v[3] = addc(x0.v[3], x1.v[3]);
+}
+LGR_DEV void kara_merge(uint32_t *v9, const fr_kara_wide &w) {             // 9 limbs: E + (O << 32) + carries
+    v9[0] = w.e[0];
+    v9[1] = add_cc(w.e[1], w.o[0]);
+#pragma unroll
+    for (int i = 2; i < 8; i++) v9[i] = addc_cc(w.e[i], w.o[i - 1]);
+    v9[8] = addc(0, 0);
+    v9[4] = add_cc(v9[4], w.c[4]);
+#pragma unroll
+    for (int i = 5; i < 8; i++) v9[i] = addc_cc(v9[i], w.c[i]);
+    v9[8] = addc(v9[8], w.c[8]);
+}
+// (L + (M - L - H) * 2^127 + H * 2^254) * 2^-288 mod p, in [0,2p); L, H, M: sums of at most 2^6 products
+LGR_DEV fr_t kara_reduce9(const fr_kara_wide &wl, const fr_kara_wide &wh, const fr_kara_wide &wm) {
+    uint32_t L[9], H[9], M[9];
+    kara_merge(L, wl); kara_merge(H, wh); kara_merge(M, wm);
+    // M -= L + H  (non-negative)
+    M[0] = sub_cc(M[0], L[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) M[i] = subc_cc(M[i], L[i]);
+    M[8] = subc(M[8], L[8]);
+    M[0] = sub_cc(M[0], H[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) M[i] = subc_cc(M[i], H[i]);
+    M[8] = subc(M[8], H[8]);
+    uint32_t v[18];
+#pragma unroll
+    for (int i = 0; i < 9; i++) v[i] = L[i];
+#pragma unroll
+    for (int i = 9; i < 18; i++) v[i] = 0;
+    // + M << 127 = (M << 31) placed at limb 3: limbs 3..12
+    uint32_t s[10];
+    s[0] = M[0] << 31;
+#pragma unroll
+    for (int i = 1; i < 9; i++) s[i] = (M[i - 1] >> 1) | (M[i] << 31);
+    s[9] = M[8] >> 1;
+    v[3] = add_cc(v[3], s[0]);
+#pragma unroll
+    for (int i = 1; i < 10; i++) v[3 + i] = addc_cc(v[3 + i], s[i]);
+#pragma unroll
+    for (int i = 13; i < 17; i++) v[i] = addc_cc(v[i], 0);
+    v[17] = addc(v[17], 0);
+    // + H << 254 = (H << 30) placed at limb 7: limbs 7..16
+    s[0] = H[0] << 30;
+#pragma unroll
+    for (int i = 1; i < 9; i++) s[i] = (H[i - 1] >> 2) | (H[i] << 30);
+    s[9] = H[8] >> 2;
+    v[7] = add_cc(v[7], s[0]);
+#pragma unroll
+    for (int i = 1; i < 10; i++) v[7 + i] = addc_cc(v[7 + i], s[i]);
+    v[17] = addc(v[17], 0);
+    return reduce9_rounds(v);
 }
 
 LGR_DEV bool fr_eq(const fr_t &a, const fr_t &b) {

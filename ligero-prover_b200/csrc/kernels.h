@@ -125,9 +125,12 @@ cudaError_t launch_peer_wait(const unsigned long long *flags, int n, unsigned lo
 // ---- synthetic witness generator (sha_kernels.cu; bench / tests only) ------------------------
 cudaError_t launch_synth(fr_mem *out, uint64_t seed, uint64_t row0, uint64_t nrows, uint64_t ncols, cudaStream_t st);
 
-// ---- micro-benchmarks (ubench.cu) ------------------------------------------------------------
+// ---- micro-benchmarks (ubench.cu, ubench_dpf.cu; linked into liblgr_ubench.so only) ------------------------------------------------------------
 cudaError_t launch_ubench(int which, uint32_t *out, int iters, int blocks, int threads, cudaStream_t st);
 cudaError_t launch_ubench_mont_occ(int nchain, int warps_per_sm, uint32_t *out, int iters, cudaStream_t st);
 cudaError_t launch_ubench_chain(int variant, uint32_t *out, int iters, int warps_per_cta, int active_lanes, cudaStream_t st);
+cudaError_t launch_ubench_dpf(int which, uint32_t *out, int iters, int blocks, int threads, cudaStream_t st);      // ubench_dpf.cu
+cudaError_t launch_ubench_mont_sha(uint32_t *out, int iters_mont, int iters_sha, int blocks, cudaStream_t st);
+cudaError_t launch_dpf_mul(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, cudaStream_t st);
 
 }  // namespace lgr

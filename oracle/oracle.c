@@ -176,13 +176,13 @@ static void make_twiddles(uint64_t (*tw)[4], size_t half, const lgo_fr *omega, i
 
 static void ntt_with_tw(lgo_fr *x, size_t N, const uint64_t (*tw)[4], int inverse) {
     uint64_t (*a)[4] = (uint64_t (*)[4])x;
-    for (size_t i = 0; i < N; i++) to_mont(a[i], a[i]);
+    /* values stay canonical throughout, exactly as in the reference: only the twiddles carry the factor R
+     * (engine.cpp:1397-1401), so montgomery_mul(y, wR) = y*w needs no conversion of the data */
     ntt_mont(a, N, tw);
-    if (inverse) {                                /* kernels.wgsl.in:92-102 ntt_adjust_inverse_reduce */
+    if (inverse) {                                /* kernels.wgsl.in:92-102 ntt_adjust_inverse_reduce: N^-1 * R (engine.cpp:1476-1482) */
         lgo_fr n = {{N, 0, 0, 0}}, ninv; lgo_fr_inv(&ninv, &n);
-        for (size_t i = 0; i < N; i++) montmul(a[i], a[i], ninv.v);   /* (xR)*ninv*R^-1 = x*ninv */
-    } else {
-        for (size_t i = 0; i < N; i++) from_mont(a[i], a[i]);
+        uint64_t ninv_m[4]; to_mont(ninv_m, ninv.v);
+        for (size_t i = 0; i < N; i++) montmul(a[i], a[i], ninv_m);
     }
 }
 
@@ -494,7 +494,12 @@ static int encode_commit_impl(const lgo_fr *rows, uint64_t seed, size_t R, size_
             ntt_with_tw(buf, k, ET.inv_k, 1);
             ntt_with_tw(buf, n, ET.fwd_n, 0);
         }
-        const size_t CB = n < 64 ? n : 64;         /* column block */
+        /* column block: at least two blocks per thread so that narrow matrices (n = 1024) keep every core busy */
+        size_t CB = n / (2 * (size_t)lgo_num_threads());
+        while (CB & (CB - 1)) CB &= CB - 1;        /* power of two: divides n */
+        if (CB > 64) CB = 64;
+        if (CB < 8) CB = 8;
+        if (CB > n) CB = n;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif

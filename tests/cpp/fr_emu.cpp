@@ -18,6 +18,20 @@ void emu_wide_dot(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T,
         for (int j = 0; j < 8; j++) out[8*c+j] = r.v[j];
     }
 }
+// the same dot product through the Karatsuba accumulators (kara_mad: three 128x128 products per element)
+void emu_kara_dot(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, size_t ncols) {
+    for (size_t c = 0; c < ncols; c++) {
+        fr_kara_wide wl, wh, wm; kara_zero(wl); kara_zero(wh); kara_zero(wm);
+        for (size_t t = 0; t < T; t++) {
+            fr_t x, y; for (int j = 0; j < 8; j++) { x.v[j] = a[8*(t*ncols+c)+j]; y.v[j] = b[8*(t*ncols+c)+j]; }
+            fr_half x0, x1, xs, y0, y1, ys;
+            kara_split(x, x0, x1, xs); kara_split(y, y0, y1, ys);
+            kara_mad(wl, x0, y0); kara_mad(wh, x1, y1); kara_mad(wm, xs, ys);
+        }
+        fr_t r = kara_reduce9(wl, wh, wm);
+        for (int j = 0; j < 8; j++) out[8*c+j] = r.v[j];
+    }
+}
 // out[i] = fr_mont_mul(a[i], b[i]) raw (in [0,2p))
 void emu_mont_mul(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t n, int canon) {
     for (size_t i = 0; i < n; i++) {

@@ -837,3 +837,16 @@ def test_alternative_encode_paths_forced(env):
     """) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_fp64_pipe_montgomery_matches_bigint(lgr, executor_factory):
+    """csrc/dpf_mont.cuh (52-bit limbs as doubles, product halves from DFMA round-toward-zero pairs): a*b*2^-260 mod p
+    against Python big integers, edge values included -- the measured alternative to the IMAD CIOS is at least correct"""
+    ex = executor_factory(256)
+    rng = random.Random(77)
+    edge = [0, 1, 2, P - 1, P - 2, (1 << 52) - 1, 1 << 52, (1 << 104) - 1, (1 << 208) + 12345, (1 << 253) % P, P >> 1]
+    a = [x for x in edge for _ in edge] + [rng.randrange(P) for _ in range(4000)]
+    b = [y for _ in edge for y in edge] + [rng.randrange(P) for _ in range(4000)]
+    got = lgr.array_to_ints(ex.dpf_mul(lgr.ints_to_array(a), lgr.ints_to_array(b)))
+    rinv = pow(1 << 260, -1, P)
+    assert got == [x * y * rinv % P for x, y in zip(a, b)]

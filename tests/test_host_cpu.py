@@ -320,3 +320,23 @@ def test_shard_rows_partition():
             assert ranges[0][0] == 0 and ranges[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
             assert max(e - b for b, e in ranges) - min(e - b for b, e in ranges) <= 1
+
+
+def test_wide_and_karatsuba_accumulators_under_emulation(emu, oracle):
+    """fr.cuh's unreduced dot products (the tile combiners): 64 plain products, and the Karatsuba form (split at bit 127,
+    three 128x128 products, recombined once per chunk) give sum a*b * 2^-288 mod p for 64-row chunks of edge and random values"""
+    rng = random.Random(12)
+    T, ncols = 64, 9
+    edge = [0, 1, P - 1, (1 << 127) - 1, 1 << 127, (1 << 128) - 1, P >> 1, (1 << 253) + 5]
+    a = [[edge[(t + c) % len(edge)] if c < 3 else rng.randrange(P) for c in range(ncols)] for t in range(T)]
+    b = [[edge[(3 * t + c) % len(edge)] if c < 3 else rng.randrange(P) for c in range(ncols)] for t in range(T)]
+    a[5] = [P - 1] * ncols; b[5] = [P - 1] * ncols
+    A = oracle.to_limbs([x for row in a for x in row]); B = oracle.to_limbs([x for row in b for x in row])
+    rinv = pow(1 << 288, -1, P)
+    want = [sum(a[t][c] * b[t][c] for t in range(T)) * rinv % P for c in range(ncols)]
+    for fn in (emu.emu_wide_dot, emu.emu_kara_dot):
+        O = np.zeros((ncols, 8), np.uint32)
+        fn(O.ctypes.data_as(C.c_void_p), A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), C.c_size_t(T), C.c_size_t(ncols))
+        got = oracle.from_limbs(O)
+        assert all(g < 2 * P for g in got)
+        assert [g % P for g in got] == want
