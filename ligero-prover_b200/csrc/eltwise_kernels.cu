@@ -8,8 +8,10 @@
 // (x*y/R, then *R^2/R); a product with a host constant c is one (c is pre-multiplied by R).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include "kernels.h"
 #include "ntt.cuh"
+#include "dpf_mont.cuh"
 
 namespace lgr {
 
@@ -198,6 +200,95 @@ __global__ void __launch_bounds__(128) combine_code_kara_kernel(const fr_mem *__
     fr_stg(partial + (size_t)chunk * n + j, fr_reduce_p(kara_reduce9(wl, wh, wm)));
 }
 
+// check_code over a resident tile on the FP64 pipe.  The sweep is bound by the 32x32->64 multiplier (IMAD.WIDE issues at a
+// quarter of the lane rate: 6.5e12/s chip-wide, 64 per element = 3.3 TB/s of codeword, half the HBM roofline).  An UNREDUCED
+// dot product needs no Montgomery step per element, which is where the double-precision formulation (dpf_mont.cuh) wins:
+// 5 x 5 products of 52-bit limbs = 50 DFMA + 25 DADD on the FP64 pipe, their exact halves accumulated as 64-bit integers
+// (two adds each on the ALU pipe), the exponent constants taken out once per 64-row chunk, one 9-round Montgomery
+// reduction per chunk as before.  r_dpf[5t .. 5t+4] = the 52-bit limbs of r_scaled[t] as doubles.
+__global__ void combine_dpf_scalars_kernel(const fr_mem *__restrict__ r_scaled, int T, double *__restrict__ r_dpf) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const fr_t r = fr_ldg(r_scaled + t);
+    const dpf_t d = dpf_from_u32(r.v);
+#pragma unroll
+    for (int j = 0; j < 5; j++) r_dpf[5 * t + j] = d.l[j];
+}
+__global__ void __launch_bounds__(128) combine_code_dpf_kernel(const fr_mem *__restrict__ a, long long row_stride, int T, int n,
+                                                               const double *__restrict__ r_dpf, fr_mem *__restrict__ partial) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.y;
+    if (j >= n) return;
+    const int t0 = chunk * kCombineChunk, t1 = min(T, t0 + kCombineChunk);
+    unsigned long long col[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) col[i] = 0;
+    const fr_mem *pa = a + (long long)t0 * row_stride + j;
+    const double *pr = r_dpf + 5 * t0;
+    // LGR_DPF_ROWS rows in flight per thread: the sweep needs ~7 MB of loads in flight chip-wide to cover HBM latency
+    // (Little: 6.5 TB/s x ~1 us), i.e. more than one or two 32-byte loads per thread
+    constexpr int RF = 4;
+    int t = t0;
+    for (; t + RF <= t1; t += RF) {
+        fr_t e[RF];
+#pragma unroll
+        for (int u = 0; u < RF; u++) e[u] = fr_ldg(pa + (long long)u * row_stride);
+#pragma unroll
+        for (int u = 0; u < RF; u++) {
+            const dpf_t x = dpf_from_u32(e[u].v);
+            double r[5];
+#pragma unroll
+            for (int q = 0; q < 5; q++) r[q] = __ldg(pr + 5 * u + q);
+#pragma unroll
+            for (int p = 0; p < 5; p++)
+#pragma unroll
+                for (int q = 0; q < 5; q++) dpf_mac(col[p + q], col[p + q + 1], x.l[p], r[q]);
+        }
+        pa += (long long)RF * row_stride;
+        pr += 5 * RF;
+    }
+    for (; t < t1; t++) {
+        const fr_t e = fr_ldg(pa);
+        const dpf_t x = dpf_from_u32(e.v);
+        double r[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) r[q] = __ldg(pr + q);
+#pragma unroll
+        for (int p = 0; p < 5; p++)
+#pragma unroll
+            for (int q = 0; q < 5; q++) dpf_mac(col[p + q], col[p + q + 1], x.l[p], r[q]);
+        pa += row_stride;
+        pr += 5;
+    }
+    // take out the exponent constants: column c received (number of (p,q) with p+q == c) low halves and
+    // (number with p+q == c-1) high halves per row
+    const unsigned long long rows = (unsigned long long)(t1 - t0);
+    const unsigned long long KH = 0x4670000000000000ull, KL = 0x4330000000000000ull;
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
+        const int nlo = (c <= 4) ? c + 1 : ((c <= 8) ? 9 - c : 0);
+        const int nhi = (c >= 1) ? ((c - 1 <= 4) ? c : 10 - c) : 0;
+        col[c] -= rows * ((unsigned long long)nlo * KL + (unsigned long long)nhi * KH);
+    }
+    // sum col[c] * 2^(52 c) as 18 x 32-bit limbs (every column < 2^62)
+    uint32_t v[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) v[i] = 0;
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
+        const int bit = 52 * c, limb = bit >> 5, sh = bit & 31;
+        // col[c] << sh spans up to 3 limbs (62 + 31 bits)
+        const unsigned long long lo = col[c] << sh;
+        const uint32_t hi = sh ? (uint32_t)(col[c] >> (64 - sh)) : 0u;
+        v[limb] = add_cc(v[limb], (uint32_t)lo);
+        v[limb + 1] = addc_cc(v[limb + 1], (uint32_t)(lo >> 32));
+        if (limb + 2 < 18) v[limb + 2] = addc_cc(v[limb + 2], hi);
+#pragma unroll
+        for (int i = limb + 3; i < 18; i++) v[i] = addc_cc(v[i], 0);
+    }
+    fr_stg(partial + (size_t)chunk * n + j, fr_reduce_p(reduce9_rounds(v)));
+}
+
 template <bool LINEAR>
 __global__ void __launch_bounds__(128) combine_partial_kernel(const fr_mem *__restrict__ a, const fr_mem *__restrict__ b, long long row_stride,
                                                               int T, int n, const fr_mem *__restrict__ r_scaled, fr_mem *__restrict__ partial) {
@@ -210,7 +301,18 @@ __global__ void __launch_bounds__(128) combine_partial_kernel(const fr_mem *__re
     const fr_mem *pa = a + (long long)t0 * row_stride + j;
     const fr_mem *pb = LINEAR ? b + (long long)t0 * row_stride + j : r_scaled + t0;
     int t = t0;
-    for (; t + 1 < t1; t += 2) {                               // two rows in flight per thread
+    if (!LINEAR) {
+        for (; t + 3 < t1; t += 4) {                           // four rows in flight per thread (memory-level parallelism)
+            const fr_t e0 = fr_ldg(pa), e1 = fr_ldg(pa + row_stride), e2 = fr_ldg(pa + 2 * row_stride), e3 = fr_ldg(pa + 3 * row_stride);
+            wide_mad(w, e0, fr_ldc(pb));
+            wide_mad(w, e1, fr_ldc(pb + 1));
+            wide_mad(w, e2, fr_ldc(pb + 2));
+            wide_mad(w, e3, fr_ldc(pb + 3));
+            pa += 4 * row_stride;
+            pb += 4;
+        }
+    }
+    for (; t + 1 < t1; t += 2) {                               // two rows (four loads for the linear form) in flight per thread
         fr_t e0 = fr_ldg(pa), e1 = fr_ldg(pa + row_stride);
         fr_t m0 = LINEAR ? fr_ldg(pb) : fr_ldc(pb);
         fr_t m1 = LINEAR ? fr_ldg(pb + row_stride) : fr_ldc(pb + 1);
@@ -291,8 +393,18 @@ cudaError_t launch_combine_code(const fr_mem *tile, long long row_stride, int T,
     dim3 grid((n + 127) / 128, chunks);
     fr_mem *r_scaled = scratch + (size_t)chunks * n;
     combine_scale_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_raw, T, r_scaled);
-    static const bool kara = !(getenv("LGR_COMBINE_KARATSUBA") && atoi(getenv("LGR_COMBINE_KARATSUBA")) == 0);   // A/B knob
-    if (kara) {
+    // Three formulations of the same sweep, measured on B200 (k = 256, 65536-row tile, 2.15 GB; ncu gpu__time_duration,
+    // profiles/r02_combine_formulations.md):  plain 64 IMAD.WIDE per element 561 us (3.83 TB/s, 58 % of HBM) -- the default;
+    // Karatsuba (48 IMAD.WIDE + splits and carries) 635 us;  FP64 pipe (50 DFMA + 25 DADD + 100 integer adds) 606 us.
+    // Fewer multiplier operations did not pay: the extra ALU work costs more issue slots than the multiplies it saves.
+    // LGR_COMBINE_CODE = plain | kara | dpf selects one (the parity suite runs all three).
+    static const char *mode_env = getenv("LGR_COMBINE_CODE");
+    static const int mode = !mode_env ? 0 : (!strcmp(mode_env, "dpf") ? 2 : (!strcmp(mode_env, "kara") ? 1 : 0));
+    if (mode == 2) {
+        double *r_dpf = reinterpret_cast<double *>(r_scaled + T);            // 40 bytes per row, after the T scaled scalars
+        combine_dpf_scalars_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_scaled, T, r_dpf);
+        combine_code_dpf_kernel<<<grid, 128, 0, st>>>(tile, row_stride, T, n, r_dpf, scratch);
+    } else if (mode == 1) {
         uint4 *r_kara = reinterpret_cast<uint4 *>(r_scaled + T);             // 48 bytes per row, after the T scaled scalars
         combine_split_kernel<<<(T + 127) / 128, 128, 0, st>>>(r_scaled, T, r_kara);
         combine_code_kara_kernel<<<grid, 128, 0, st>>>(tile, row_stride, T, n, r_kara, scratch);

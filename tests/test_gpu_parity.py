@@ -804,6 +804,17 @@ def test_peer_wait_times_out_instead_of_hanging(lgr, executor_factory):
     ex.ipc_free(ptr)
 
 
+@pytest.mark.parametrize("mode", ["kara", "dpf"])
+def test_alternative_check_code_formulations_forced(mode):
+    """check_code over a resident tile through the Karatsuba accumulators and through the FP64 pipe (both measured slower
+    than the plain form, so not the default): still bit-exact against the per-row reference schedule"""
+    import subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k", "test_tile_combiners"],
+                         env=dict(os.environ, LGR_COMBINE_CODE=mode), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("env", [{"LGR_CLUSTER_ENCODE_ROWS": "4"}, {"LGR_NTT_LAT_MAX": "0"}, {"LGR_NO_ENCODE_GRAPH": "1"}],
                          ids=["cluster-encoder", "no-latency-kernel", "no-graph-replay"])
 def test_alternative_encode_paths_forced(env):
