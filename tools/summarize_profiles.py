@@ -1,9 +1,10 @@
 """Turn gpurun_out/{launches.csv,prof_*.ncu-rep} (tools/profile.sh) into the tracked summaries under profiles/."""
 import collections, csv, os, shutil, subprocess, sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+src = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/prof"
 os.makedirs("profiles", exist_ok=True)
-rows = [r for r in csv.reader(open("gpurun_out/launches.csv")) if len(r) > 5]
+rows = [r for r in csv.reader(open(os.path.join(src, "launches.csv"))) if len(r) > 5]
 hdr = None
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows:
@@ -28,7 +29,7 @@ out = ["# %s: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-e2e 
 for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
     out.append("\"%s\",%d,%.1f,%.1f,%.3f" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
 open("profiles/%s_launches_summary.csv" % tag, "w").write("\n".join(out) + "\n")
-shutil.copy("gpurun_out/launches.csv", "profiles/%s_launches_raw.csv" % tag)
+shutil.copy(os.path.join(src, "launches.csv"), "profiles/%s_launches_raw.csv" % tag)
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
@@ -36,21 +37,37 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 lines = ["# %s: key metrics from `ncu --set full --clock-control none --import-source on` (tools/profile.sh), one B200" % tag, "file,kernel,metric,value,unit"]
-for f in sorted(os.listdir("gpurun_out")):
+for f in sorted(os.listdir(src)):
     if not f.endswith(".ncu-rep"):
         continue
-    p = subprocess.run(["ncu", "-i", os.path.join("gpurun_out", f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    p = subprocess.run(["ncu", "-i", os.path.join(src, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(p.splitlines()))
     if len(rr) < 3:
         continue
     h = rr[0]
     r = rr[2]
     kn = r[h.index("Kernel Name")].split("(")[0]
-    for w in want:
+    import re
+    extra = [m for m in h if re.search(r"sm__inst_executed_pipe_(alu|fma|fp64|lsu|xu)\.sum$|sm__pipe_(fmaheavy|fp64|xu)_cycles_active.avg.pct_of_peak_sustained_active|"
+                                       r"l1tex__data_pipe_lsu_wavefronts_mem_shared.sum$|smsp__average_warp_latency_per_inst_issued.ratio", m)]
+    for w in want + sorted(extra):
         if w in h:
             lines.append("%s,\"%s\",%s,%s,%s" % (f, kn, w, r[h.index(w)].replace(",", ""), rr[1][h.index(w)]))
+    # warp stall reasons from the PC sampler: share of all samples, reasons >= 3 %
+    samp = {}
+    for m in h:
+        mm = re.fullmatch(r"smsp__pcsamp_warps_issue_stalled_([a-z_]+?)", m)
+        if mm and not m.endswith("_not_issued"):
+            try:
+                samp[mm.group(1)] = float(r[h.index(m)].replace(",", ""))
+            except ValueError:
+                pass
+    tot_s = sum(samp.values())
+    for reason, v in sorted(samp.items(), key=lambda kv: -kv[1]):
+        if tot_s and v / tot_s >= 0.03:
+            lines.append("%s,\"%s\",stall_%s,%.1f,%% of pc samples" % (f, kn, reason, 100.0 * v / tot_s))
 open("profiles/%s_ncu_full_summary.csv" % tag, "w").write("\n".join(lines) + "\n")
-for j in ("ntt_bench.json", "combine_bench.json", "chain_ubench.json", "sha_bench.json", "encode_bench.json"):
-    if os.path.exists(os.path.join("gpurun_out", j)):
-        shutil.copy(os.path.join("gpurun_out", j), "profiles/%s_%s" % (tag, j))
+for j in ("ntt_bench.json", "combine_bench.json", "chain_ubench.json", "sha_bench.json", "encode_bench.json", "mul_ubench.json", "per_row.json"):
+    if os.path.exists(os.path.join(src, j)):
+        shutil.copy(os.path.join(src, j), "profiles/%s_%s" % (tag, j))
 print("profiles/ updated for", tag)
