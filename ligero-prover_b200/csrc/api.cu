@@ -722,7 +722,22 @@ static size_t commit_tile_rows(const lgr_ctx *c, uint64_t nrows) {
 
 // rows: device-resident (host_rows == nullptr) or host-resident (pinned or pageable) row-major R x k.
 // ext_sha != nullptr: absorb into the caller's column-hash context and stop there (no init, no final, no tree)
+static int encode_commit_body(lgr_ctx *c, const fr_mem *rows, const fr_mem *host_rows, uint64_t nrows, void *digests, void *nodes, uint32_t *ext_sha, bool *forked);
+// Any failure after the aux / copy streams were forked joins them back before returning, so that a later call cannot
+// reuse tile[] / h2d_buf[] while a stream of the failed call is still working on them.
 static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host_rows, uint64_t nrows, void *digests, void *nodes, uint32_t *ext_sha = nullptr) {
+    bool forked = false;
+    const int rc = encode_commit_body(c, rows, host_rows, nrows, digests, nodes, ext_sha, &forked);
+    if (rc != LGR_OK && forked) {
+        const std::string keep = g_err;
+        cudaStreamSynchronize(c->aux_stream);
+        cudaStreamSynchronize(c->copy_stream);
+        cudaGetLastError();
+        g_err = keep;
+    }
+    return rc;
+}
+static int encode_commit_body(lgr_ctx *c, const fr_mem *rows, const fr_mem *host_rows, uint64_t nrows, void *digests, void *nodes, uint32_t *ext_sha, bool *forked) {
     REQUIRE(nrows < (1ull << 40), "too many rows");
     const size_t n = c->n, k = c->k;
     const size_t T = commit_tile_rows(c, nrows);
@@ -743,6 +758,7 @@ static int encode_commit_impl(lgr_ctx *c, const fr_mem *rows, const fr_mem *host
     uint32_t *sha = ext_sha ? ext_sha : c->commit_sha;
     cudaStream_t es = c->stream, hs = overlap ? c->aux_stream : c->stream, cs = c->copy_stream;
     CU(cudaEventRecord(c->ev_fork, es));
+    *forked = true;
     if (overlap) CU(cudaStreamWaitEvent(hs, c->ev_fork, 0));
     if (host_rows) CU(cudaStreamWaitEvent(cs, c->ev_fork, 0));
     if (!ext_sha) { CU(launch_sha_init(sha, (int)n, hs)); c->launches++; }
