@@ -5,6 +5,7 @@
 // (profiles/r02_per_row_launches.csv).  Here a lane of M points is worked by M/2 threads, ONE butterfly per thread per
 // stage in a rolled loop (a few KB of code, resident after the first stage), so a launch is bound by ~log2(M) dependent
 // Montgomery multiplications plus barriers.  Selected by launch_ntt_tile for jobs of at most 2^16 points.
+#include <cstdlib>
 #include "kernels.h"
 #include "ntt.cuh"
 
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(1024, 1) ntt_lat_kernel(const __grid_constant_
 cudaError_t launch_ntt_lat(const NttTileParams &q, cudaStream_t st) {
     NttTileParams p = q;
     const int M = 1 << p.logm;
-    int C = M >= 512 ? 1 : 512 / M;
+    static const int cta_points = getenv("LGR_LAT_CTA_POINTS") ? atoi(getenv("LGR_LAT_CTA_POINTS")) : 512;   // tuning knob
+    int C = M >= cta_points ? 1 : cta_points / M;
     if (C > p.total_lanes) C = p.total_lanes;
     p.lanes_per_cta = C;
     const int threads = std::max(32, std::min(1024, (C * M) / 2));

@@ -69,7 +69,7 @@ class GpuEngine:
         self.send = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)]       # [G][T][n/G]
         self.recv = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else self.send
         self.enc_stream = torch.cuda.Stream(device=dev)
-        self.hash_stream = torch.cuda.Stream(device=dev)
+        self.hash_stream = torch.cuda.Stream(device=dev, priority=int(__import__("os").environ.get("LGR_EXACT_HASH_PRIORITY", "0")))   # -1 (high) measured no better: the kernels contend, DESIGN.md section 6
         self.enc_done = [torch.cuda.Event() for _ in range(2)]
         self.hash_done = [torch.cuda.Event() for _ in range(2)]
         ex.sha256_init(self.slab)
@@ -189,7 +189,7 @@ class PeerStoreEngine(GpuEngine):
             raise RuntimeError(getattr(self, "fail", "a peer could not map this rank's memory"))
         self.q = 0                                                    # rounds issued so far (global, monotone)
         self.enc_stream = torch.cuda.Stream(device=dev)
-        self.hash_stream = torch.cuda.Stream(device=dev)
+        self.hash_stream = torch.cuda.Stream(device=dev, priority=int(__import__("os").environ.get("LGR_EXACT_HASH_PRIORITY", "0")))   # -1 (high) measured no better: the kernels contend, DESIGN.md section 6
         ex.sha256_init(self.slab)
         self.sha_ctx = ex.make_device_buffer(ex.sha256_context_bytes(self.slab))
         self.sha_dig = ex.make_device_buffer(self.slab * 32)
