@@ -13,8 +13,11 @@
 
 namespace lgr {
 
+#ifndef LGR_NTT_MINBLOCKS
+#define LGR_NTT_MINBLOCKS 2          // tuning knob (A/B builds): minimum resident 256-thread CTAs per SM => register cap
+#endif
 template <int LOGM>
-__global__ void __launch_bounds__(256, 2) ntt_tile_kernel(const __grid_constant__ NttTileParams p) {
+__global__ void __launch_bounds__(256, LGR_NTT_MINBLOCKS) ntt_tile_kernel(const __grid_constant__ NttTileParams p) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     fr_mem *sm = reinterpret_cast<fr_mem *>(smem_raw);
     constexpr int M = 1 << LOGM;
