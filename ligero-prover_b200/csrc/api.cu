@@ -712,7 +712,8 @@ int lgr_sample_gather_rows(lgr_ctx *c, const void *tile, uint64_t row_stride, ui
 // tile: even number of rows, 2^23 codeword elements (256 MiB) per buffer: at k = 256 that is 8192 rows
 // = 2048 encoder CTAs (4.6 waves of 444 resident CTAs; a 2^21 tile was 1.15 waves and lost 40% to the tail)
 static size_t commit_tile_rows(const lgr_ctx *c, uint64_t nrows) {
-    size_t T = ((size_t)1 << 23) / c->n;
+    static const int tile_log = getenv("LGR_COMMIT_TILE_LOG") ? atoi(getenv("LGR_COMMIT_TILE_LOG")) : 23;   // tuning knob
+    size_t T = ((size_t)1 << tile_log) / c->n;
     if (T < 2) T = 2;
     T &= ~(size_t)1;
     if (T > nrows) T = (size_t)nrows;
