@@ -187,29 +187,43 @@ __device__ __forceinline__ void load_virtual_row(uint32_t *dst, int v, int p, co
     }
 }
 
-template <bool REASSOC, int G>
-__global__ void __launch_bounds__(128, 1) sha_chain_kernel(uint32_t *ctx, int n, const fr_mem *__restrict__ tile, long long row_stride, int T, const uint32_t one, const uint32_t mone) {
+// C = chain warps per CTA.  C = 1: the CTA (1 chain + 3 schedule warps) has its SM to itself -- fastest chain, one SM per 32
+// columns.  C = 4: four chains per SM, one per scheduler, each sharing its scheduler with its own three schedule warps (warp w
+// runs on scheduler w mod 4): the chain slows by the schedule's ALU work (1582 -> ~2300 cycles per block) but 4096 columns
+// take 32 SMs instead of 128 and leave the rest to the encoder of the next tile.  The ring is split between the chains.
+template <bool REASSOC, int G, int C>
+__global__ void __launch_bounds__(128 * C, 1) sha_chain_kernel(uint32_t *ctx, int n, const fr_mem *__restrict__ tile, long long row_stride, int T, const uint32_t one, const uint32_t mone) {
+    constexpr int SL = kChainSlots / C;                        // ring slots per chain
+    static_assert(SL % G == 0 && SL / G >= 2, "ring too shallow for this hand-over group");
     extern __shared__ __align__(16) unsigned char chain_smem[];
-    uint32_t *ring = reinterpret_cast<uint32_t *>(chain_smem);
-    uint64_t *full = reinterpret_cast<uint64_t *>(chain_smem + (size_t)kChainSlots * 64 * 32 * 4);
-    uint64_t *empty = full + kChainSlots;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = blockIdx.x * 32 + lane;                   // n is a multiple of 32
+    const bool is_chain = warp < C;
+    const int cid = is_chain ? warp : (warp - C) % C;          // which chain of the CTA this warp serves
+    const int hsel = is_chain ? 0 : (warp - C) / C;            // helper index 0..2
+    uint32_t *ring = reinterpret_cast<uint32_t *>(chain_smem) + (size_t)cid * SL * 64 * 32;
+    uint64_t *full = reinterpret_cast<uint64_t *>(chain_smem + (size_t)kChainSlots * 64 * 32 * 4) + cid * SL;
+    uint64_t *empty = reinterpret_cast<uint64_t *>(chain_smem + (size_t)kChainSlots * 64 * 32 * 4) + kChainSlots + cid * SL;
+    const int cta32 = blockIdx.x * C + cid;                   // 32-column group of this chain
+    const bool live = cta32 * 32 < n;                         // n is a multiple of 32; the last CTA may hold idle chains
+    const int col = cta32 * 32 + lane;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kChainSlots / G; s++) { mbar_init(full + s, 32 * G); mbar_init(empty + s, 1); }
+        uint64_t *f0 = reinterpret_cast<uint64_t *>(chain_smem + (size_t)kChainSlots * 64 * 32 * 4);
+        for (int c = 0; c < C; c++)
+            for (int s = 0; s < SL / G; s++) { mbar_init(f0 + c * SL + s, 32 * G); mbar_init(f0 + kChainSlots + c * SL + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (!live) return;
     const uint32_t rows_lo = ctx[(size_t)16 * n + col], rows_hi = ctx[(size_t)17 * n + col];
     const int p = (int)(rows_lo & 1u);
     const int nblk = (p + T) >> 1;
-    if (warp == 0) {
+    if (is_chain) {
         uint32_t st[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) st[i] = ctx[(size_t)i * n + col];
         // ring slots are handed over in groups of G blocks: one barrier round trip per G compressions
         // (measured, 8192-row tiles: G = 1 3.63 ms, 2 3.48, 4 3.34, 8 3.31 per launch)
-        constexpr int NG = kChainSlots / G;
+        constexpr int NG = SL / G;
         int grp = 0; uint32_t phase = 0;
         for (int b0 = 0; b0 < nblk; b0 += G) {
             mbar_wait(full + grp, phase);
@@ -233,7 +247,6 @@ __global__ void __launch_bounds__(128, 1) sha_chain_kernel(uint32_t *ctx, int n,
         ctx[(size_t)17 * n + col] = rows_hi + (lo < rows_lo ? 1u : 0u);
     } else {
         constexpr uint32_t K[64] = {LGR_K256_LIST};
-        const int hsel = warp - 1;
         uint32_t w[16], nx[16];
         if (hsel < nblk) {
             load_virtual_row(nx, 2 * hsel, p, ctx, n, col, tile, row_stride);
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(128, 1) sha_chain_kernel(uint32_t *ctx, int n,
                 load_virtual_row(nx, 2 * bn, p, ctx, n, col, tile, row_stride);
                 load_virtual_row(nx + 8, 2 * bn + 1, p, ctx, n, col, tile, row_stride);
             }
-            constexpr int NG = kChainSlots / G;
+            constexpr int NG = SL / G;
             const int gi = b / G, grp = gi % NG;
             const uint32_t phase = (uint32_t)(gi / NG) & 1u;
             mbar_wait(empty + grp, phase ^ 1u);                // passes immediately the first time round
@@ -590,18 +603,24 @@ cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long lon
         // narrow matrix: producer/consumer CTAs, one chain warp per SM
         static const bool textbook = getenv("LGR_CHAIN_TEXTBOOK") != nullptr;   // A/B knobs: textbook round association, blocks per hand-over
         static const int group = getenv("LGR_CHAIN_GROUP") ? atoi(getenv("LGR_CHAIN_GROUP")) : 8;
-#define LGR_CHAIN_LAUNCH(RE, G)                                                                                                         \
+#define LGR_CHAIN_LAUNCH(RE, G, C)                                                                                                      \
     {                                                                                                                                   \
-        cudaError_t e = cudaFuncSetAttribute(sha_chain_kernel<RE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem);    \
+        cudaError_t e = cudaFuncSetAttribute(sha_chain_kernel<RE, G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem); \
         if (e != cudaSuccess) return e;                                                                                                 \
-        sha_chain_kernel<RE, G><<<n / 32, 128, kChainSmem, st>>>(ctx, n, tile, row_stride, T, 1u, 0xFFFFFFFFu);                         \
+        sha_chain_kernel<RE, G, C><<<(n / 32 + (C) - 1) / (C), 128 * (C), kChainSmem, st>>>(ctx, n, tile, row_stride, T, 1u, 0xFFFFFFFFu); \
         return cudaGetLastError();                                                                                                      \
     }
-        if (textbook) LGR_CHAIN_LAUNCH(false, 1)
-        if (group == 1) LGR_CHAIN_LAUNCH(true, 1)
-        if (group == 2) LGR_CHAIN_LAUNCH(true, 2)
-        if (group == 4) LGR_CHAIN_LAUNCH(true, 4)
-        LGR_CHAIN_LAUNCH(true, 8)
+        // more than LGR_CHAIN_PACK_CTAS 32-column groups (default 64, i.e. n > 2048): four chains per SM instead of one.  The
+        // chain is 1.5x slower (1.42 vs 0.94 ms per 2048 rows x 4096 columns alone) but holds 32 SMs instead of 128, so the
+        // encoder of the next tile runs beside it: k = 1024 commit 1.28 -> 1.48e9 elem/s; one rank's round of the exact 8-GPU
+        // layout 2.17 -> 1.63 ms (tools/exact_round_sim.py)
+        static const int pack_ctas = getenv("LGR_CHAIN_PACK_CTAS") ? atoi(getenv("LGR_CHAIN_PACK_CTAS")) : 64;
+        if (n / 32 > pack_ctas && !textbook) LGR_CHAIN_LAUNCH(true, 2, 4)
+        if (textbook) LGR_CHAIN_LAUNCH(false, 1, 1)
+        if (group == 1) LGR_CHAIN_LAUNCH(true, 1, 1)
+        if (group == 2) LGR_CHAIN_LAUNCH(true, 2, 1)
+        if (group == 4) LGR_CHAIN_LAUNCH(true, 4, 1)
+        LGR_CHAIN_LAUNCH(true, 8, 1)
     }
     // few columns: one warp per CTA so that every chain gets its own scheduler slot
     const int threads = (n <= 148 * 4 * 32) ? 32 : 128;

@@ -69,7 +69,7 @@ class GpuEngine:
         self.send = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)]       # [G][T][n/G]
         self.recv = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else self.send
         self.enc_stream = torch.cuda.Stream(device=dev)
-        self.hash_stream = torch.cuda.Stream(device=dev, priority=int(__import__("os").environ.get("LGR_EXACT_HASH_PRIORITY", "0")))   # -1 (high) measured no better: the kernels contend, DESIGN.md section 6
+        self.hash_stream = torch.cuda.Stream(device=dev, priority=int(__import__("os").environ.get("LGR_EXACT_HASH_PRIORITY", "-1")))   # high: with the gate, the hash CTAs take their SMs first
         self.enc_done = [torch.cuda.Event() for _ in range(2)]
         self.hash_done = [torch.cuda.Event() for _ in range(2)]
         ex.sha256_init(self.slab)
@@ -115,10 +115,16 @@ class GpuEngine:
                 src = self.send[b]
             self.ex.use_torch_stream()
             self.ex.sha256_init(self.slab)
-            rv = src.view(self.G, self.T * self.slab * 8)
-            for h in range(self.G):
-                if rows_per_rank[h]:
-                    self.ex.sha256_digest_update_rows(self.bind, self.ex.wrap(rv[h]), rows_per_rank[h], self.slab)
+            if all(r == self.T for r in rows_per_rank):
+                # full round: the G chunks are one contiguous [G*T][n/G] matrix in global row order -> ONE launch.  (With
+                # one launch per chunk the encoder of the next round refills the SMs in the gap between two launches and
+                # the SM-owning chain CTAs of the next chunk wait for it to drain: tools/exact_round_sim.py.)
+                self.ex.sha256_digest_update_rows(self.bind, self.ex.wrap(src), self.G * self.T, self.slab)
+            else:
+                rv = src.view(self.G, self.T * self.slab * 8)
+                for h in range(self.G):
+                    if rows_per_rank[h]:
+                        self.ex.sha256_digest_update_rows(self.bind, self.ex.wrap(rv[h]), rows_per_rank[h], self.slab)
             self.hash_done[b].record(self.hash_stream)
 
     def finish(self, dist):
@@ -189,12 +195,16 @@ class PeerStoreEngine(GpuEngine):
             raise RuntimeError(getattr(self, "fail", "a peer could not map this rank's memory"))
         self.q = 0                                                    # rounds issued so far (global, monotone)
         self.enc_stream = torch.cuda.Stream(device=dev)
-        self.hash_stream = torch.cuda.Stream(device=dev, priority=int(__import__("os").environ.get("LGR_EXACT_HASH_PRIORITY", "0")))   # -1 (high) measured no better: the kernels contend, DESIGN.md section 6
+        self.hash_stream = torch.cuda.Stream(device=dev, priority=int(__import__("os").environ.get("LGR_EXACT_HASH_PRIORITY", "-1")))   # high: with the gate, the hash CTAs take their SMs first
         ex.sha256_init(self.slab)
         self.sha_ctx = ex.make_device_buffer(ex.sha256_context_bytes(self.slab))
         self.sha_dig = ex.make_device_buffer(self.slab * 32)
         self.bind = ex.bind_sha256_context(self.sha_ctx, self.sha_dig)
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        # encode(r+1) is released together with hash(r) (when every rank's slabs of round r have arrived), not earlier:
+        # otherwise its grid has filled every SM by then and the SM-owning chain CTAs of the hash wait for it to drain
+        self.gate = __import__("os").environ.get("LGR_EXACT_GATE", "1") != "0"
+        self.hash_go = [torch.cuda.Event() for _ in range(2)]
 
     def begin(self):
         super().begin()
@@ -208,6 +218,8 @@ class PeerStoreEngine(GpuEngine):
             self.ex.use_torch_stream()
             if q > 2:                                                 # every peer has hashed what round q-2 left in its recv[b]
                 self.ex.peer_wait(self.local_ptr + self.off_consumed, self.G, q - 2, self.local_ptr + self.off_err)
+            if self.gate and rnd >= 1:
+                self.enc_stream.wait_event(self.hash_go[(rnd - 1) & 1])
             if nrows:
                 chunk = b * self.buf_bytes + self.rank * self.T * self.slab * 32
                 self.ex.encode_rows_slabs(rows_buf, nrows, [self.peer[h] + chunk for h in range(self.G)])
@@ -222,10 +234,14 @@ class PeerStoreEngine(GpuEngine):
             self.ex.use_torch_stream()
             self.ex.sha256_init(self.slab)
             self.ex.peer_wait(self.local_ptr + self.off_ready, self.G, q, self.local_ptr + self.off_err)
-            for g in range(self.G):
-                if rows_per_rank[g]:
-                    chunk = RawSlice(self.local_ptr + b * self.buf_bytes + g * self.T * self.slab * 32, self.T * self.slab * 32)
-                    self.ex.sha256_digest_update_rows(self.bind, chunk, rows_per_rank[g], self.slab)
+            self.hash_go[rnd & 1].record(self.hash_stream)
+            if all(r == self.T for r in rows_per_rank):             # full round: one [G*T][n/G] matrix, one launch (see GpuEngine)
+                self.ex.sha256_digest_update_rows(self.bind, RawSlice(self.local_ptr + b * self.buf_bytes, self.buf_bytes), self.G * self.T, self.slab)
+            else:
+                for g in range(self.G):
+                    if rows_per_rank[g]:
+                        chunk = RawSlice(self.local_ptr + b * self.buf_bytes + g * self.T * self.slab * 32, self.T * self.slab * 32)
+                        self.ex.sha256_digest_update_rows(self.bind, chunk, rows_per_rank[g], self.slab)
             self.ex.peer_signal([self.peer[g] + self.off_consumed + 8 * self.rank for g in range(self.G)], q)
 
     def finish(self, dist):

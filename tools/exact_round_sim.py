@@ -21,6 +21,8 @@ send = [torch.empty(T * n * 8, dtype=torch.int32, device=dev) for _ in range(2)]
 enc_s, hash_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1)
 enc_done = [torch.cuda.Event() for _ in range(2)]
 hash_done = [torch.cuda.Event() for _ in range(2)]
+hash_go = [torch.cuda.Event() for _ in range(2)]
+GATE = os.environ.get("LGR_EXACT_GATE", "1") != "0"      # release encode(r+1) together with hash(r) so that the hash CTAs are placed first
 ex.sha256_init(slab)
 ctx = ex.make_device_buffer(ex.sha256_context_bytes(slab))
 dig = ex.make_device_buffer(slab * 32)
@@ -29,23 +31,34 @@ ex.sha256_digest_init(bind)
 torch.cuda.synchronize()
 
 
+ONLY = os.environ.get("LGR_SIM_ONLY", "")            # "enc" / "hash": time one side alone
+
+
 def run(nr):
     for r in range(nr):
         b = r & 1
         with torch.cuda.stream(enc_s):
             if r >= 2:
                 enc_s.wait_event(hash_done[b])
+            if GATE and r >= 1:
+                enc_s.wait_event(hash_go[(r - 1) & 1])
             ex.use_torch_stream()
             base = send[b].data_ptr()
-            ex.encode_rows_slabs(rows, T, [base + h * T * slab * 32 for h in range(G)])
+            if ONLY != "hash":
+                ex.encode_rows_slabs(rows, T, [base + h * T * slab * 32 for h in range(G)])
             enc_done[b].record(enc_s)
         with torch.cuda.stream(hash_s):
             hash_s.wait_event(enc_done[b])
+            hash_go[b].record(hash_s)
             ex.use_torch_stream()
             ex.sha256_init(slab)
             v = send[b].view(G, T * slab * 8)
-            for h in range(G):
-                ex.sha256_digest_update_rows(bind, ex.wrap(v[h]), T, slab)
+            if ONLY != "enc":
+                if os.environ.get("LGR_SIM_ONE_LAUNCH", "1") != "0":     # the G chunks are one contiguous [G*T][slab] matrix
+                    ex.sha256_digest_update_rows(bind, ex.wrap(send[b]), G * T, slab)
+                else:
+                    for h in range(G):
+                        ex.sha256_digest_update_rows(bind, ex.wrap(v[h]), T, slab)
             hash_done[b].record(hash_s)
     torch.cuda.synchronize()
 
