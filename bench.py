@@ -357,7 +357,7 @@ def main():
             by = rows_per_launch * n * 32                                        # every codeword element read once
             split = os.environ.get("LGR_CHAIN_SPLIT")
             lane_split = (n // 16 <= 64) if split is None else (split != "0")       # launch_sha_update's choice (csrc/sha_kernels.cu)
-            sha_name = "sha_update_kernel" if n > 4736 else ("sha_chain16_kernel" if (lane_split and n % 16 == 0 and n // 16 <= 148) else "sha_chain_kernel")
+            sha_name = "sha_update_kernel" if n > 18944 else ("sha_chain16_kernel" if (lane_split and n % 16 == 0 and n // 16 <= 148) else "sha_chain_kernel")
             kern[sha_name] = {"ms_per_launch": per, "launches": prof["sha_launches"], "algorithmic_bytes_per_launch": by,
                                          "achieved_gbs": by / (per * 1e-3) / 1e9, "frac_hbm": by / (per * 1e-3) / 1e9 / hbm,
                                          "share_of_step": prof["sha_ms"] / (ms_step * args.steps)}

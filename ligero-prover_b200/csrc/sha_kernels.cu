@@ -599,7 +599,11 @@ cudaError_t launch_sha_update(uint32_t *ctx, int n, const fr_mem *tile, long lon
         if (group16 == 8) LGR_C16_LAUNCH(8, 8)
         LGR_C16_LAUNCH(16, 8)                                  // hand-over group: 1 / 4 / 8 / 12 / 16 / 24 blocks -> 1511 / 1482 / 1450 / 1441 / 1431 / 1440 cycles
     }
-    if (n % 32 == 0 && n / 32 <= 148 && T >= 4) {
+    // widest matrix the chain kernel takes, in 32-column groups: 592 = 148 SMs x 4 chains per CTA (n <= 18944).  Measured
+    // against the thread-per-column kernel (LGR_CHAIN_MAX_GROUPS=148): k = 2048 commit 1.17 -> 1.47e9 elem/s, k = 4096 commit
+    // 1.30 -> 1.41e9; one rank's round of the exact layout at n/G = 8192 / 16384 columns 2.05 -> 1.53 ms / 1.69 -> 1.52 ms
+    static const int max_groups = getenv("LGR_CHAIN_MAX_GROUPS") ? atoi(getenv("LGR_CHAIN_MAX_GROUPS")) : 592;
+    if (n % 32 == 0 && n / 32 <= max_groups && T >= 4) {
         // narrow matrix: producer/consumer CTAs, one chain warp per SM
         static const bool textbook = getenv("LGR_CHAIN_TEXTBOOK") != nullptr;   // A/B knobs: textbook round association, blocks per hand-over
         static const int group = getenv("LGR_CHAIN_GROUP") ? atoi(getenv("LGR_CHAIN_GROUP")) : 8;

@@ -203,8 +203,8 @@ class PeerStoreEngine(GpuEngine):
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         # encode(r+1) is released together with hash(r) (when every rank's slabs of round r have arrived), not earlier:
         # otherwise its grid has filled every SM by then and the SM-owning chain CTAs of the hash wait for it to drain
-        # (only where the hash is the chain kernel, n/G <= 4736 columns; the thread-per-column hash shares SMs: N = 2 lost 3 %)
-        self.gate = __import__("os").environ.get("LGR_EXACT_GATE", "1") != "0" and self.slab <= 4736
+        # (only where the hash is the SM-owning chain kernel, n/G <= 18944 columns: csrc/sha_kernels.cu launch_sha_update)
+        self.gate = __import__("os").environ.get("LGR_EXACT_GATE", "1") != "0" and self.slab <= 18944
         self.hash_go = [torch.cuda.Event() for _ in range(2)]
 
     def begin(self):
