@@ -15,9 +15,10 @@ every codeword column SHA-256 hashed over all rows in order, Merkle tree over th
           of every shard are all-gathered over NCCL and every rank builds the tree over the G*n
           leaves (DESIGN.md "Multi-GPU").  value = G*R*k / max-over-ranks device time.
 
-`--impl reference` times the CPU oracle (the reference has no CPU implementation of this path and
-cannot be built here -- DESIGN.md "Oracle") on the host cores, on a bounded sample of the same
-workload.  Only that leg and the cpu_baseline leg touch oracle/.
+`--impl reference` times the CPU oracle port (the reference has no CPU implementation of this path; what can be
+built from its sources here is its shaders run scalar on the host, oracle/_ref -- a checker, not a baseline:
+DESIGN.md "Oracle") on the host cores, on a bounded sample of the same workload.  Only that leg and the
+cpu_baseline leg touch oracle/; the bench line's `parity_check` compares the CPU leg's root with the GPU's.
 """
 import argparse
 import importlib.util
@@ -161,7 +162,7 @@ def run_reference(args, rank):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": "ligero encode+commit, R=2^%d rows x k=%d (n=%d) per GPU, BN254 Fr, seed %d" % (LOG_ROWS, K, 4 * K, SEED),
                    "rows_per_gpu": 1 << LOG_ROWS, "k": K, "n": 4 * K, "sample_rows_per_step": rows,
-                   "note": "reference has no CPU path for these kernels and cannot be built here; this is the CPU oracle port"},
+                   "note": "the reference has no CPU path for these kernels; this is the CPU oracle port (pinned to the reference's shaders, tests/test_wgslref_cpu.py)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -6,14 +6,16 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  * The product (ligero-prover_b200/csrc) never links, includes or calls anything in oracle/.
  *
- * Parity status: the reference ships NO golden vectors / KATs for NTT, SHA leaf format, Merkle
- * root or combiners and cannot be built here (Dawn, wabt, GMP headers,
- * Boost absent).  The oracle is therefore pinned by (1) the standard definitions the WGSL
- * implements (DFT over BN254 Fr with the roots of src/bn254.cpp:36-43, FIPS 180-4 SHA-256),
- * (2) an independent pure-Python big-int / hashlib restatement (oracle/pyref.py), (3) the
- * derived seed vectors of SURVEY.md section 8c (tests/golden/survey_vectors.json), and (4) the
- * reference's only device KAT (tests/webgpu/test_powmod.cpp: coeff*base^exp vs mpz_powm_ui).
- * "parity unpinned by reference-run outputs" -- see DESIGN.md.
+ * Parity status: PINNED to the reference's own shaders.  The reference ships no golden vectors / KATs for NTT, SHA leaf
+ * format, Merkle root or combiners and its C++ host side cannot be built here (Dawn, wabt, GMP
+ * headers, Boost absent), but its arithmetic is first-party WGSL text: oracle/wgsl2cpp.py transliterates
+ * shader/{bigint,bn254fr,kernels}.wgsl.in and shader/sha256.wgsl to C++, oracle/wgslref.cpp drives them in
+ * src/webgpu/engine.cpp's dispatch order (oracle/_ref/libwgslref.so), and tests/test_wgslref_cpu.py checks every function
+ * below against them -- live where the library is present, and against committed outputs of those shaders
+ * (tests/golden/wgslref_vectors.json) everywhere.  Also kept: (1) the standard definitions (DFT over BN254 Fr with the
+ * roots of src/bn254.cpp:36-43, FIPS 180-4 SHA-256), (2) an independent pure-Python restatement (oracle/pyref.py),
+ * (3) the derived seed vectors of SURVEY.md section 8c (tests/golden/survey_vectors.json), (4) the reference's own device
+ * KATs (tests/webgpu/test_powmod.cpp).  See DESIGN.md section 2.
  *
  * Element format everywhere: 8 x u32 little-endian limbs = 4 x u64 little-endian limbs = 32 bytes,
  * canonical value in [0,p), NOT Montgomery form
