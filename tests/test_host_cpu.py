@@ -160,6 +160,19 @@ def test_c_abi_exports_every_declared_symbol(lgr):
     assert lib.lgr_merkle_node_count(C.c_uint32(1024)) == 2047 and lib.lgr_merkle_node_count(C.c_uint32(1025)) == 4095
 
 
+@pytest.mark.parametrize("hdr", ["lgr.h", "lgr_prover.h", "lgr_ubench.h"])
+def test_public_headers_are_plain_c(hdr, tmp_path):
+    """the drop-in boundary is a C ABI: every header under include/ must parse as strict C99 (what cgo / a C FFI sees)"""
+    import shutil, subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "hc.c"
+    src.write_text('#include "%s"\nint main(void) { return 0; }\n' % hdr)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_no_cpu_fallback_create_fails_loudly_without_gpu(lgr):
     import torch
     if torch.cuda.is_available():
