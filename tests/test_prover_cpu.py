@@ -351,3 +351,33 @@ def test_wat_emitter_on_the_reference_program(pr, oracle, name, consts, asserts,
     assert st["quadratic_slots"] == 27 * 64 + 9 * 129 and st["quadratic_slots"] < 8000
     assert list(kinds) == [0, 1] and vals.shape == (4, 8000, 8)
     _wat_check(pr, oracle, text, l=448, k=512)
+
+
+def _rand_wat_expr(rng, depth):
+    """(text, value mod 2^64) of a random folded i64 expression over private and public constants"""
+    M = 1 << 64
+    if depth == 0 or rng.random() < 0.25:
+        v = rng.choice([0, 1, 2, M - 1, 1 << 63, (1 << 63) - 1, 1 << 32, rng.getrandbits(64), rng.getrandbits(20)])
+        lit = rng.choice([str(v), hex(v), str(v - M) if v >= 1 << 63 else str(v)])
+        return ("(call $i64_private_const (i64.const %s))" if rng.random() < 0.7 else "(i64.const %s)") % lit, v
+    op = rng.choice(["mul", "add", "sub"])
+    (ta, va), (tb, vb) = _rand_wat_expr(rng, depth - 1), _rand_wat_expr(rng, depth - 1)
+    return "(i64.%s %s %s)" % (op, ta, tb), {"mul": va * vb, "add": va + vb, "sub": va - vb}[op] % M
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_wat_emitter_on_random_expression_trees(pr, oracle, seed):
+    """wrap-around semantics of nested products / sums / differences: every assertion against the value Python computes
+    holds in the emitted constraint system, and moving one expected value by one breaks exactly the linear test"""
+    rng = random.Random(1000 + seed)
+    cases = [_rand_wat_expr(rng, rng.randrange(1, 4)) for _ in range(5)]
+    head = ('(module (import "env" "i64_private_const" (func $i64_private_const (param i64) (result i64)))\n'
+            '(import "env" "assert_equal" (func $assert_equal (param i64 i64)))\n(func $t\n')
+    tail = ')\n(export "_start" (func $t)))\n'
+    body = lambda cs: "".join("(call $assert_equal %s (i64.const %d))\n" % (t, v) for t, v in cs)
+    _, st = _wat_check(pr, oracle, head + body(cases) + tail, l=256, k=256)
+    assert st["violated_constraints"] == 0 and st["asserts"] == 5
+    j = rng.randrange(5)
+    wrong = list(cases); wrong[j] = (cases[j][0], (cases[j][1] + 1) % (1 << 64))
+    _, st_bad = _wat_check(pr, oracle, head + body(wrong) + tail, l=256, k=256, expect_valid=False)
+    assert st_bad["violated_constraints"] == 1
