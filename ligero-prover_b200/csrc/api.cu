@@ -28,7 +28,11 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
     } while (0)
 #define REQUIRE(cond, msg) do { if (!(cond)) return fail(LGR_ERR_INVALID, msg); } while (0)
 // every ABI entry point runs with its context's device current, whatever the caller's current device is
-#define ENTER(c) do { REQUIRE((c) != nullptr, "null context"); CU(cudaSetDevice((c)->device)); } while (0)
+#define ENTER_NOFLUSH(c) do { REQUIRE((c) != nullptr, "null context"); CU(cudaSetDevice((c)->device)); } while (0)
+// ... and with the one-row encodes lgr_encode deferred (see flush_encodes) enqueued first, so stream order is call order
+#define ENTER(c) do { ENTER_NOFLUSH(c); if (!(c)->enc_pending.empty()) { int rc_ = flush_encodes(c); if (rc_) return rc_; } } while (0)
+struct lgr_ctx;
+static int flush_encodes(lgr_ctx *c);
 
 namespace {
 
@@ -81,9 +85,17 @@ struct lgr_ctx {
     void *staging = nullptr; size_t staging_bytes = 0;      // bytes per slot
     cudaEvent_t ev_staging[kStagingSlots] = {};
     int staging_next = 0;
-    // one-row encodes at large k are 5 small launches: replayed as a CUDA graph per codeword buffer (lgr_encode)
-    std::map<void *, cudaGraphExec_t> encode_graphs;
+    // one-row encodes at large k are 5 small launches each.  lgr_encode defers them; consecutive encodes of DISTINCT codeword
+    // buffers (the reference's stage-2 callbacks issue two or six in a row, nonbatch_context.hpp:667-668,715-720) are replayed
+    // as ONE CUDA graph with a parallel branch per buffer, each branch on its own scratch (flush_encodes)
+    static constexpr int kEncodeLanes = 8;
+    struct EncodeGraph { cudaGraphExec_t exec = nullptr; fr_mem *scratch = nullptr; };
+    std::map<std::vector<void *>, EncodeGraph> encode_graphs;
     std::map<void *, int> encode_seen;
+    std::vector<void *> enc_pending;
+    bool enc_tables_warm = false;            // one plain large-k encode has run: tables, plans exist, capture allocates nothing
+    cudaStream_t lane_stream[kEncodeLanes - 1] = {};
+    cudaEvent_t ev_lane[kEncodeLanes - 1] = {}, ev_lane_fork = nullptr;
     uint32_t *sample_idx = nullptr; uint32_t sample_count = 0;
     // per-kernel timing of the commit pipeline (lgr_profile): events on the launching streams
     bool profiling = false;
@@ -113,8 +125,6 @@ static int upload(lgr_ctx *c, const std::vector<Fr> &v, DevTable &t) {
 static int ensure_scratch(lgr_ctx *c, size_t elems) {
     if (c->scratch_elems >= elems) return LGR_OK;
     if (c->scratch) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->scratch)); c->scratch = nullptr; c->scratch_elems = 0; }
-    for (auto &g : c->encode_graphs) cudaGraphExecDestroy(g.second);        // they hold the old scratch address
-    c->encode_graphs.clear();
     CU(cudaMalloc((void **)&c->scratch, elems * 32));
     c->scratch_elems = elems;
     return LGR_OK;
@@ -412,6 +422,67 @@ static int create_body(lgr_ctx *c, int device, uint32_t l, uint32_t k, uint32_t 
 }
 
 // ================================================================================================
+// Enqueue the one-row encodes lgr_encode deferred (large k only).  They are replayed as ONE CUDA graph per distinct sequence of
+// codeword buffers: a branch per buffer -- captured on lane streams forked from and joined back into the main stream -- so the
+// two or six rows of a stage-2 callback run side by side instead of back to back (each is ~26 dependent butterfly stages on a
+// few dozen CTAs: latency, not throughput).  Every branch has its own scratch; the tables the branches share are read-only.
+// The graph is launched on the main stream at the point of the flush, i.e. before anything the caller enqueues after the
+// encodes and after everything it enqueued before them: stream order stays call order.
+static int flush_encodes(lgr_ctx *c) {
+    std::vector<void *> bufs;
+    bufs.swap(c->enc_pending);                                                   // whatever happens below, nothing stays deferred
+    const size_t m = bufs.size();
+    const uint64_t launches = c->launches;                                       // counted when the encodes were deferred
+    auto it = c->encode_graphs.find(bufs);
+    if (it != c->encode_graphs.end()) { CU(cudaGraphLaunch(it->second.exec, c->stream)); return LGR_OK; }
+    auto plain = [&]() -> int {
+        int rc = LGR_OK;
+        for (size_t i = 0; i < m && rc == LGR_OK; i++) rc = encode_rows_impl(c, (const fr_mem *)bufs[i], c->n, 1, plain_sink((fr_mem *)bufs[i], c->n), c->stream);
+        c->launches = launches;
+        return rc;
+    };
+    if (c->encode_graphs.size() >= 64) return plain();
+    for (size_t i = 0; i + 1 < m; i++) if (!c->lane_stream[i]) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CU(cudaStreamCreateWithPriority(&c->lane_stream[i], cudaStreamNonBlocking, lo));
+        CU(cudaEventCreateWithFlags(&c->ev_lane[i], cudaEventDisableTiming));
+    }
+    if (!c->ev_lane_fork) CU(cudaEventCreateWithFlags(&c->ev_lane_fork, cudaEventDisableTiming));
+    const size_t per_row = (size_t)c->k * 5;        // coefficients + four cosets, or + three cosets + the kept row (encode_rows_impl)
+    lgr_ctx::EncodeGraph eg;
+    CU(cudaMalloc((void **)&eg.scratch, m * per_row * 32));
+    fr_mem *const keep_scratch = c->scratch; const size_t keep_elems = c->scratch_elems; cudaStream_t const main_stream = c->stream;
+    int rc = LGR_OK;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(main_stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        if (m > 1) e = cudaEventRecord(c->ev_lane_fork, main_stream);
+        for (size_t i = 0; i < m && rc == LGR_OK && e == cudaSuccess; i++) {
+            cudaStream_t st = i ? c->lane_stream[i - 1] : main_stream;
+            if (i) e = cudaStreamWaitEvent(st, c->ev_lane_fork, 0);
+            if (e != cudaSuccess) break;
+            c->stream = st; c->scratch = eg.scratch + i * per_row; c->scratch_elems = per_row;
+            rc = encode_rows_impl(c, (const fr_mem *)bufs[i], c->n, 1, plain_sink((fr_mem *)bufs[i], c->n), st);
+            if (i && rc == LGR_OK) { e = cudaEventRecord(c->ev_lane[i - 1], st); if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, c->ev_lane[i - 1], 0); }
+        }
+        c->stream = main_stream; c->scratch = keep_scratch; c->scratch_elems = keep_elems; c->launches = launches;
+        const cudaError_t e2 = cudaStreamEndCapture(main_stream, &g);                // also ends a capture that failed half-way
+        if (e == cudaSuccess) e = e2;
+    }
+    if (rc == LGR_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&eg.exec, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (rc != LGR_OK || e != cudaSuccess || !eg.exec) {                             // capture refused: plain launches, one row after the other
+        cudaGetLastError();
+        cudaFree(eg.scratch);
+        for (void *b : bufs) c->encode_seen[b] = -1000000;
+        return plain();
+    }
+    c->encode_graphs[bufs] = eg;
+    CU(cudaGraphLaunch(eg.exec, c->stream));
+    return LGR_OK;
+}
+
 extern "C" {
 
 const char *lgr_last_error(void) { return g_err.c_str(); }
@@ -451,7 +522,9 @@ int lgr_destroy(lgr_ctx *c) {
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int i = 0; i < lgr_ctx::kStagingSlots; i++) if (c->ev_staging[i]) cudaEventDestroy(c->ev_staging[i]);
-    for (auto &g : c->encode_graphs) cudaGraphExecDestroy(g.second);
+    for (auto &g : c->encode_graphs) { cudaGraphExecDestroy(g.second.exec); if (g.second.scratch) cudaFree(g.second.scratch); }
+    for (int i = 0; i < lgr_ctx::kEncodeLanes - 1; i++) { if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]); if (c->ev_lane[i]) cudaEventDestroy(c->ev_lane[i]); }
+    if (c->ev_lane_fork) cudaEventDestroy(c->ev_lane_fork);
     for (int i = 0; i < 2; i++) { if (c->h2d_buf[i]) cudaFree(c->h2d_buf[i]); if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if (c->ev_h2d_free[i]) cudaEventDestroy(c->ev_h2d_free[i]); }
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (auto &pr : c->prof_enc) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -562,37 +635,29 @@ int lgr_ntt_pow2(lgr_ctx *c, void *buf, uint32_t logn, uint32_t batch, const uin
     if (rc) return rc;
     return run_ntt(c, (fr_mem *)buf, *p, batch, (size_t)1 << logn);
 }
-int lgr_encode(lgr_ctx *c, void *buf) { ENTER(c);
-    REQUIRE(c && buf, "null argument");
+int lgr_encode(lgr_ctx *c, void *buf) { ENTER_NOFLUSH(c);
+    REQUIRE(buf, "null argument");
     // Large k: a one-row encode is 5 small launches + a copy on the tile engine.  The stage contexts call it on the same
-    // few codeword buffers for every row (nonbatch_context.hpp:445-468), so from the third call on a buffer the sequence is
-    // replayed as ONE CUDA-graph launch.  Only on the context's own stream (a caller-provided stream may be capturing).
+    // few codeword buffers for every row (nonbatch_context.hpp:445-468,667-668,715-720), so from the third call on a buffer
+    // it is deferred until the next call of any other kind and replayed from a CUDA graph (flush_encodes).  Only on the
+    // context's own stream (a caller-provided stream may be capturing).  LGR_ENCODE_LANES=1 keeps one row per graph.
     static const bool use_graphs = !getenv("LGR_NO_ENCODE_GRAPH");
-    if (use_graphs && !fused_encode_ok(c) && c->stream == c->own_stream) {
-        auto it = c->encode_graphs.find(buf);
-        if (it != c->encode_graphs.end()) { CU(cudaGraphLaunch(it->second, c->stream)); c->launches += 6; return LGR_OK; }
-        if (++c->encode_seen[buf] >= 3 && c->encode_graphs.size() < 64) {       // tables, plans and scratch exist by now
-            const uint64_t before = c->launches;
-            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = encode_rows_impl(c, (const fr_mem *)buf, c->n, 1, plain_sink((fr_mem *)buf, c->n), c->stream);
-            cudaGraph_t g = nullptr;
-            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-            c->launches = before;
-            if (rc == LGR_OK && e == cudaSuccess && g) {
-                cudaGraphExec_t ge = nullptr;
-                e = cudaGraphInstantiate(&ge, g, 0);
-                cudaGraphDestroy(g);
-                if (e == cudaSuccess) {
-                    c->encode_graphs[buf] = ge;
-                    CU(cudaGraphLaunch(ge, c->stream)); c->launches += 6;
-                    return LGR_OK;
-                }
-            } else if (g) cudaGraphDestroy(g);
-            cudaGetLastError();                                                  // capture refused: fall through to plain launches
-            c->encode_seen[buf] = -1000000;
+    static const int lanes = std::min(std::max(getenv("LGR_ENCODE_LANES") ? atoi(getenv("LGR_ENCODE_LANES")) : lgr_ctx::kEncodeLanes, 1), (int)lgr_ctx::kEncodeLanes);
+    int rc;
+    if (use_graphs && !fused_encode_ok(c) && c->stream == c->own_stream && c->enc_tables_warm) {
+        if (c->encode_seen.size() > 4096) c->encode_seen.clear();
+        if (++c->encode_seen[buf] >= 3) {
+            // a second encode of the same (or an overlapping) codeword depends on the first: those two stay in order
+            const char *b = (const char *)buf; const ptrdiff_t span = (ptrdiff_t)c->n * 32;
+            for (void *q : c->enc_pending) if (b - (const char *)q < span && (const char *)q - b < span) { if ((rc = flush_encodes(c))) return rc; break; }
+            c->enc_pending.push_back(buf); c->launches += 6;
+            return (int)c->enc_pending.size() >= lanes ? flush_encodes(c) : LGR_OK;
         }
     }
-    return encode_rows_impl(c, (const fr_mem *)buf, c->n, 1, plain_sink((fr_mem *)buf, c->n), c->stream);
+    if (!c->enc_pending.empty() && (rc = flush_encodes(c))) return rc;
+    rc = encode_rows_impl(c, (const fr_mem *)buf, c->n, 1, plain_sink((fr_mem *)buf, c->n), c->stream);
+    if (rc == LGR_OK && !fused_encode_ok(c)) c->enc_tables_warm = true;      // tables, plans and the lazily set kernel attributes exist from here on
+    return rc;
 }
 int lgr_encode_rows(lgr_ctx *c, const void *rows, uint64_t row_stride, uint32_t nrows, void *cw) { ENTER(c);
     REQUIRE(c && rows && cw, "null argument");

@@ -850,6 +850,77 @@ def test_alternative_encode_paths_forced(env):
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("k", [4096, 8192])
+def test_consecutive_one_row_encodes_share_one_graph(lgr, oracle, k):
+    """lgr_encode defers one-row encodes at large k and replays consecutive ones as one CUDA graph with a branch per
+    codeword buffer (api.cu flush_encodes) -- the six encodes of a quadratic callback, the two of a linear one
+    (nonbatch_context.hpp:667-668,715-720).  Whatever the grouping, results equal the oracle's row by row, and stream order
+    stays call order: repeated, overlapping and more-than-eight buffers, other operations in between."""
+    import torch
+    n = 4 * k
+    ex = lgr.make_executor(k - 192, k)                     # the context's own stream: deferral and graph replay are live
+    try:
+        nbuf = 10
+        devs = [ex.make_codeword_buffer() for _ in range(nbuf)]
+        big = ex.make_device_buffer((n + k) * 32)
+        acc = ex.make_codeword_buffer()
+        torch.cuda.synchronize()
+        binds = [ex.bind_ntt(d) for d in devs]
+        rows = oracle.synth(23, 0, 12, k)
+        want = [oracle.encode(rows[r], k) for r in range(12)]
+        # rounds of 6 / 2 / 1 / 10 consecutive encodes; the first rounds run plain, later ones capture, then replay
+        for rep, m in enumerate([6, 6, 6, 6, 6, 2, 2, 2, 2, 1, 1, 1, 1, 10, 10, 10, 10, 6, 2, 6]):
+            for j in range(m):
+                ex.write_buffer_clear(devs[j], rows[(rep + j) % 12])
+            for j in range(m):
+                ex.encode_ntt_device(binds[j])
+            if rep % 3 == 0:                               # an element-wise op right behind the encodes must see all of them
+                ex.clear_buffer(acc)
+                for j in range(m):
+                    ex.EltwiseAddAssignMod(ex.bind_eltwise2(devs[j], acc))
+                tot = oracle.from_limbs(ex.read_elements(acc))
+                cols = [oracle.from_limbs(want[(rep + j) % 12]) for j in range(m)]
+                assert tot == [sum(c[i] for c in cols) % P for i in range(n)], (k, rep, m)
+            for j in range(m):
+                assert np.array_equal(ex.read_elements(devs[j]), want[(rep + j) % 12]), (k, rep, m, j)
+        assert ex.launch_count() > 0
+        # the same buffer twice in a row: the second encode takes the first k elements of the first one's codeword
+        for rep in range(2):
+            ex.write_buffer_clear(devs[0], rows[3]); ex.write_buffer_clear(devs[1], rows[4])
+            ex.encode_ntt_device(binds[0]); ex.encode_ntt_device(binds[1]); ex.encode_ntt_device(binds[0])
+            assert np.array_equal(ex.read_elements(devs[0]), oracle.encode(want[3][:k], k)), (k, rep)
+            assert np.array_equal(ex.read_elements(devs[1]), want[4])
+        # overlapping windows of one allocation: B = [k, k+n) starts inside A = [0, n)
+        A, B = big.slice(0, n * 32), big.slice(k * 32, (k + n) * 32)
+        for rep in range(5):
+            ex.write_buffer_clear(big, rows[5 + rep])
+            ex.encode_ntt_device(ex.bind_ntt(A)); ex.encode_ntt_device(ex.bind_ntt(B))
+            got = ex.read_elements(big)
+            cwA = want[5 + rep]
+            assert np.array_equal(got[:k], cwA[:k]) and np.array_equal(got[k:], oracle.encode(cwA[k:2 * k], k)), (k, rep)
+        # deferred work is not lost at a synchronise, a stream switch or a decode
+        ex.write_buffer_clear(devs[2], rows[7]); ex.encode_ntt_device(binds[2]); ex.device_synchronize()
+        got = devs[2].storage.cpu().numpy().view(np.uint32).reshape(-1, 8)
+        assert np.array_equal(got, want[7])
+        ex.write_buffer_clear(devs[2], rows[8]); ex.encode_ntt_device(binds[2]); ex.decode_ntt_device(binds[2])
+        assert np.array_equal(ex.read_elements(devs[2])[:k], rows[8])
+        ex.write_buffer_clear(devs[2], rows[9]); ex.encode_ntt_device(binds[2]); ex.use_torch_stream()
+        torch.cuda.synchronize()
+        assert np.array_equal(devs[2].storage.cpu().numpy().view(np.uint32).reshape(-1, 8), want[9])
+    finally:
+        ex.close()
+
+
+@pytest.mark.parametrize("lanes", ["1", "3"])
+def test_encode_graph_lane_limits_forced(lanes):
+    """LGR_ENCODE_LANES=1 (one row per graph, the round-2 schedule) and 3 (a callback's six encodes split in two graphs)"""
+    import subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k", "test_consecutive_one_row_encodes_share_one_graph"],
+                         env=dict(os.environ, LGR_ENCODE_LANES=lanes), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_fp64_pipe_montgomery_matches_bigint(lgr, executor_factory):
     """csrc/dpf_mont.cuh (52-bit limbs as doubles, product halves from DFMA round-toward-zero pairs): a*b*2^-260 mod p
     against Python big integers, edge values included -- the measured alternative to the IMAD CIOS is at least correct"""
