@@ -15,7 +15,10 @@
  *   - `void *` buffer arguments are DEVICE pointers (from lgr_alloc or any CUDA allocation, e.g. a
  *     torch tensor's data_ptr()), 32-byte aligned.  Host pointers are named host_*.
  *   - All work is enqueued on the context's stream and returns immediately (WebGPU queue semantics,
- *     src/webgpu/device_context.cpp:344-354); lgr_read and lgr_sync block.
+ *     src/webgpu/device_context.cpp:344-354); lgr_read and lgr_sync block.  On the context's OWN stream a call may be
+ *     held back until the next call on the context (lgr_encode, below) -- order on the stream is always call order, and
+ *     lgr_sync / lgr_read / lgr_set_stream enqueue everything held back first.  A caller that shares the stream with
+ *     other CUDA code uses lgr_set_stream, where nothing is held back.
  *   - Return value: 0 = LGR_OK, otherwise an error code; lgr_last_error() gives the text for the
  *     calling thread.  (The reference aborts on device errors, device_context.cpp:121-128; a C ABI
  *     reports instead.)  Not thread-safe per context, like the reference.
@@ -75,7 +78,9 @@ int lgr_read(lgr_ctx *ctx, void *host_dst, const void *src, size_t src_off, size
 
 /* ---- transforms ------------------------------------------------------------------------------ */
 /* encode_ntt_device (engine.cpp:755-770): buf = n elements, buf[0:k) message, buf[k:n) zero on
- * entry; on return buf = codeword.  In place. */
+ * entry; on return buf = codeword.  In place.  At k > 2048 on the context's own stream, consecutive calls on distinct
+ * buffers (nonbatch_context.hpp:667-668,715-720 issues two or six) are enqueued together, as one CUDA graph in which
+ * the rows run side by side, by the next call of any other kind. */
 int lgr_encode(lgr_ctx *ctx, void *buf);
 /* decode_ntt_device (engine.cpp:772-796): iNTT_n, fold, NTT_k on buf[0:k); buf[k:n) = coefficients */
 int lgr_decode(lgr_ctx *ctx, void *buf);
