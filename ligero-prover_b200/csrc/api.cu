@@ -613,7 +613,7 @@ int lgr_copy_clear(lgr_ctx *c, const void *src, size_t src_bytes, void *dst, siz
     return lgr_clear(c, dst, src_bytes, dst_bytes - src_bytes);
 }
 int lgr_read(lgr_ctx *c, void *host_dst, const void *src, size_t off, size_t bytes) { ENTER(c);
-    REQUIRE(c && host_dst && src, "null argument");
+    REQUIRE(c && src && (host_dst || !bytes), "null argument");
     if (bytes) CU(cudaMemcpyAsync(host_dst, (const char *)src + off, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return LGR_OK;

@@ -146,6 +146,7 @@ struct cuda_context {
     void copy_buffer_clear(buffer_type from, buffer_type to) { cuda::check(lgr_copy_clear(ctx_, from.get(), from.size(), to.get(), to.size()), "copy_buffer_clear"); }
     template <typename T> std::vector<T> copy_to_host(buffer_type buf) {
         std::vector<T> v(buf.size() / sizeof(T));
+        if (v.empty()) { device_synchronize(); return v; }     // an empty slice (stage 3 flushes one when no row is pending) still blocks
         cuda::check(lgr_read(ctx_, v.data(), buf.get(), 0, v.size() * sizeof(T)), "copy_to_host");
         return v;
     }
@@ -246,20 +247,22 @@ private:
     struct A3 { void *x, *y, *o; size_t n; };
     struct A2 { void *x, *o; size_t n; };
     static void *at(const buffer_type &b, uint32_t elem) { return static_cast<char *>(b.get()) + (size_t)elem * 32; }
-    static size_t elems(const buffer_type &b, uint32_t off) { return b.size() / 32 - off; }
-    // the reference dispatches over arrayLength(vector_x) (kernels.wgsl.in:330); with element offsets the
-    // bound window of every operand is the arena variable, so the common length is the minimum
+    static size_t elems(const buffer_type &b) { return b.size() / 32; }
+    // The reference passes element offsets as DYNAMIC binding offsets (engine.cpp:432-446): every bound window keeps its
+    // length and slides by its offset, and the kernels loop over arrayLength(vector_x) (kernels.wgsl.in:330).  So the
+    // count is the window length of x -- capped by the other windows, where WebGPU would drop the out-of-range accesses --
+    // and the offsets only move the base pointers (vbn254fr binds the first k elements of its arena and slides them).
     A3 a3(const cuda::buffer_binding &b, cuda::eltwise_offset o) const {
         const auto &v = b.buffers();
-        size_t n = elems(v[0], o.x);
-        if (elems(v[1], o.y) < n) n = elems(v[1], o.y);
-        if (elems(v[2], o.z) < n) n = elems(v[2], o.z);
+        size_t n = elems(v[0]);
+        if (elems(v[1]) < n) n = elems(v[1]);
+        if (elems(v[2]) < n) n = elems(v[2]);
         return A3{at(v[0], o.x), at(v[1], o.y), at(v[2], o.z), n};
     }
     A2 a2(const cuda::buffer_binding &b, cuda::eltwise_offset o) const {
         const auto &v = b.buffers();
-        size_t n = elems(v[0], o.x);
-        if (elems(v[1], o.z) < n) n = elems(v[1], o.z);
+        size_t n = elems(v[0]);
+        if (elems(v[1]) < n) n = elems(v[1]);
         return A2{at(v[0], o.x), at(v[1], o.z), n};
     }
 

@@ -1,0 +1,426 @@
+// ref_contexts.cpp -- the REFERENCE's own prover layers run over an executor of our choice.  TEST INFRASTRUCTURE.
+//
+// What is compiled here is the reference's code where it lies under /root/reference (never copied into the repo):
+//   include/zkp/nonbatch_context.hpp   stage 1/2/3 contexts (the row schedule)
+//   include/zkp/backend/*.hpp          ligetron_backend + witness_manager (witness -> row packing, masks, randomness)
+//   include/interpreter*.hpp           the WASM interpreter's opcode semantics over witnesses
+//   include/host_modules/{env,vbn254fr}.hpp   the two host modules the test programs call
+//   include/zkp/{hash,merkle_tree,random}.hpp, src/bn254.cpp   transcript, tree, field
+// and what this file adds is ONLY what `main` of src/webgpu_prover.cpp:228-471 does around them (the three passes, the
+// seeds, the self-check) plus a hand-assembled instruction list where the reference would call wabt (absent here).
+//
+// Two builds (oracle/Makefile, target `refctx`):
+//   -DREFCTX_CUDA   Executor = ligero::webgpu_context, which ligero-prover_b200/host/compat/wgpu.hpp makes the CUDA
+//                   executor: the drop-in boundary compiled AND run inside the reference's translation unit (B200 only);
+//   (default)       Executor = ligero::oracle_context (tests/refctx/oracle_executor.hpp): the same program on the CPU
+//                   oracle, which is how tests/golden/refctx_*.json are produced in this GPU-less container.
+// Output: one JSON file with the statement the stage contexts saw (row events, values, coefficient rows) and everything
+// they produced (root, test vectors, openings).  tests/test_refctx_*.py compare the CUDA path and the restatements with it.
+#include <algorithm>
+#include <cstring>
+#include <format>
+#include <fstream>
+#include <iomanip>
+#include <memory>
+#include <stdexcept>
+
+#include <params.hpp>
+#include <interpreter.hpp>
+#include <wgpu.hpp>
+#include <zkp/common.hpp>
+#include <zkp/finite_field_gmp.hpp>
+#include <zkp/nonbatch_context.hpp>
+#include <host_modules/env.hpp>
+#include <host_modules/vbn254fr.hpp>
+
+#include <fiat_shamir.hpp>   // ligero-prover_b200/host: the sampler only (portable_sample needs Boost)
+
+#ifdef REFCTX_CUDA
+using executor_t = ligero::webgpu_context;
+static const char *kExecutorName = "cuda";
+#else
+#include "oracle_executor.hpp"
+using executor_t = ligero::oracle_context;
+static const char *kExecutorName = "oracle";
+#endif
+
+using namespace ligero;
+using namespace ligero::vm;
+using field_t = zkp::bn254_gmp;
+using buffer_t = executor_t::buffer_type;
+
+// ---------------------------------------------------------------------------------------------------------------
+// the log: what the stage contexts were asked to commit, in real-time order
+enum { EV_LINEAR = 0, EV_QUAD = 1, EV_VSET = 2, EV_VCOPY = 3, EV_VADD = 4, EV_VSUB = 5, EV_VMUL = 6, EV_VDIV = 7, EV_VASSERT_EQ = 8, EV_VBIT = 9,
+       EV_VADDC = 10, EV_VSUBC = 11, EV_VCSUB = 12, EV_VMULC = 13, EV_VMONTMULC = 14 };
+
+struct run_log {
+    std::vector<int> kinds;
+    std::vector<uint32_t> rows;          // [rows][l][8]: first l elements of every scalar row / the l values of a VSET
+    std::vector<uint32_t> batch_args;    // 3 per vbn254fr event
+    std::vector<uint32_t> batch_consts;  // 8 per constant-taking event
+    size_t l = 0;
+    void row(const mpz_vector &v) {
+        for (size_t i = 0; i < l; i++) {
+            uint32_t limbs[8] = {0};
+            if (i < v.size()) mpz_export(limbs, nullptr, -1, sizeof(uint32_t), 0, 0, v[i].get_mpz_t());
+            rows.insert(rows.end(), limbs, limbs + 8);
+        }
+    }
+};
+
+// a stage context that writes down the rows it is handed, then does what the reference does
+template <typename Base>
+struct recording : Base {
+    using witness_row_type = typename Base::witness_row_type;
+    template <typename... A> explicit recording(run_log *lg, bool want_coefs, A &&...a) : Base(std::forward<A>(a)...), log_(lg), coefs_(want_coefs) {}
+    void linear_callback(witness_row_type row) override {
+        log_->kinds.push_back(EV_LINEAR);
+        log_->row(coefs_ ? row.second : row.first);
+        Base::linear_callback(row);
+    }
+    void quadratic_callback(witness_row_type x, witness_row_type y, witness_row_type z) override {
+        log_->kinds.push_back(EV_QUAD);
+        for (auto *r : {&x, &y, &z}) log_->row(coefs_ ? r->second : r->first);
+        Base::quadratic_callback(x, y, z);
+    }
+    run_log *log_;
+    bool coefs_;
+};
+
+using stage1_t = recording<zkp::nonbatch_stage1_context<field_t, executor_t, zkp::stage1_random_policy, params::hasher>>;
+using stage2_t = recording<zkp::nonbatch_stage2_context<field_t, executor_t, zkp::stage2_random_policy>>;
+using stage3_t = recording<zkp::nonbatch_stage3_context<field_t, executor_t, zkp::stage3_random_policy>>;
+
+// ---------------------------------------------------------------------------------------------------------------
+// programs.  Each one is a function template over the stage context, like run_program (include/invoke.hpp:79-98).
+
+// the module store the reference's instantiate() would build (include/runtime.hpp:345-604) for a module that imports
+// env.i64_private_const (func 0) and env.assert_equal (func 1), has one 64 KiB memory and one function `_start` (func 2)
+struct tiny_module {
+    store_t store;
+    module_instance inst;
+    explicit tiny_module(std::vector<instr_ptr> body) {
+        function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_start({}, {});
+        inst.types = {k_pc, k_eq, k_start};
+        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("i64_private_const"), k_pc, &inst, function_instance::host_code{0, "env", "i64_private_const"}));
+        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("assert_equal"), k_eq, &inst, function_instance::host_code{1, "env", "assert_equal"}));
+        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("_start"), k_start, &inst, function_instance::func_code{2, {}, std::move(body)}));
+        inst.memaddrs.push_back(store.emplace_back<memory_instance>(memory_kind(limits(1)), memory_instance::page_size));
+        inst.exports["_start"] = 2;
+    }
+};
+
+// What transpile() (include/transpiler.hpp:741-776) emits for the folded text
+//   (call $assert_equal (i64.OP (call $pc (i64.const a)) (call $pc (i64.const b))) (call $pc (i64.const c)))
+// : runs of plain opcodes become basic blocks, calls stand alone.
+static void emit_assert_binop(std::vector<instr_ptr> &body, size_t &bb_id, opcode::kind op, uint64_t a, uint64_t b, uint64_t c) {
+    auto block = [&](std::vector<opcode> ops) {
+        auto bb = std::make_unique<basic_block>();
+        bb->id = bb_id++;
+        bb->body = std::move(ops);
+        body.push_back(std::move(bb));
+    };
+    auto i64c = [](uint64_t v) { return opcode(opcode::inn_const, value_kind::i64, v); };
+    block({i64c(a)});
+    body.push_back(make_instr<call>(0));
+    block({i64c(b)});
+    body.push_back(make_instr<call>(0));
+    block({opcode(op, value_kind::i64), i64c(c)});
+    body.push_back(make_instr<call>(0));
+    body.push_back(make_instr<call>(1));
+}
+
+struct binop_case { uint64_t a, b, c; };
+
+// tests/i64_mul.wat:5-14, the nine assertions in order
+static const binop_case kI64Mul[] = {
+    {1, 1, 1},
+    {1, 0, 0},
+    {~0ULL, ~0ULL, 1},
+    {0x1000000000000000ULL, 4096, 0},
+    {0x8000000000000000ULL, 0, 0},
+    {0x8000000000000000ULL, ~0ULL, 0x8000000000000000ULL},
+    {0x7fffffffffffffffULL, ~0ULL, 0x8000000000000001ULL},
+    {0x0123456789abcdefULL, 0xfedcba9876543210ULL, 0x2236d88fe5618cf0ULL},
+    {0x7fffffffffffffffULL, 0x7fffffffffffffffULL, 1},
+};
+
+template <typename Ctx>
+static void run_wasm_binops(Ctx &ctx, opcode::kind op, const binop_case *cases, size_t ncases) {
+    std::vector<instr_ptr> body;
+    size_t bb_id = 0;
+    for (size_t i = 0; i < ncases; i++) emit_assert_binop(body, bb_id, op, cases[i].a, cases[i].b, cases[i].c);
+    tiny_module m(std::move(body));
+    wasm_interpreter<Ctx> interp(ctx);
+    ctx.store(&m.store);
+    ctx.module(&m.inst);
+    // invoke() (include/invoke.hpp:34-77)
+    auto dummy = ctx.make_frame();
+    dummy->module = &m.inst;
+    ctx.set_current_frame(dummy.get());
+    ctx.stack_push(std::move(dummy));
+    ctx.template add_host_module<env_module<Ctx>>(&ctx);
+    ctx.template add_host_module<vbn254fr_module<Ctx>>(&ctx);
+    auto result = interp.run(call{m.inst.exports["_start"]});
+    if (result.is_exit()) throw std::runtime_error("program exited");
+    ctx.stack_pop();
+    ctx.finalize();
+}
+
+// vbn254fr host calls on device-resident variables, driven through the module's own call table with the arguments on
+// the interpreter stack and the handles in WASM memory, as compiled guest code would (include/host_modules/vbn254fr.hpp)
+template <typename Ctx>
+struct vbn_driver {
+    Ctx &ctx;
+    run_log *log;
+    uint32_t k, l;
+    uint32_t next_addr = 64;             // guest addresses of the 4-byte handles
+    uint32_t scratch = 4096;             // guest scratch for constants / strings
+    uint32_t new_var() {
+        uint32_t a = next_addr; next_addr += 4;
+        ctx.stack_push(a);
+        call("vbn254fr_alloc");
+        return a;
+    }
+    uint32_t slot(uint32_t addr) { return ctx.template memory_load<uint32_t>(addr) / k; }
+    void call(const char *fn) { ctx.call_host(0, "vbn254fr", fn); }
+    void ev(int kind, uint32_t a0, uint32_t a1, uint32_t a2) {
+        if (!log) return;
+        log->kinds.push_back(kind);
+        log->batch_args.insert(log->batch_args.end(), {a0, a1, a2});
+    }
+    void set_ui_scalar(uint32_t out, uint32_t v) {
+        ev(EV_VSET, slot(out), 0, 0);
+        if (log) { mpz_vector row; for (uint32_t i = 0; i < l; i++) row.push_back(mpz_class(v)); log->row(row); }
+        ctx.stack_push(out); ctx.stack_push(v);
+        call("vbn254fr_set_ui_scalar");
+    }
+    void set_str_scalar(uint32_t out, const std::string &s, uint32_t base) {
+        mpz_class val(s, (int)base);
+        ev(EV_VSET, slot(out), 0, 0);
+        if (log) { mpz_vector row; for (uint32_t i = 0; i < l; i++) row.push_back(val); log->row(row); }
+        std::memcpy(ctx.memory_data().data() + scratch, s.c_str(), s.size() + 1);
+        ctx.stack_push(out); ctx.stack_push(scratch); ctx.stack_push(base);
+        call("vbn254fr_set_str_scalar");
+        ctx.stack_pop();                                      // the error code the call leaves behind
+    }
+    void op3(int kind, const char *fn, uint32_t out, uint32_t x, uint32_t y) {
+        ev(kind, slot(out), slot(x), slot(y));
+        ctx.stack_push(out); ctx.stack_push(x); ctx.stack_push(y);
+        call(fn);
+    }
+    void opc(int kind, const char *fn, uint32_t out, uint32_t x, const mpz_class &c, bool const_first = false) {
+        ev(kind, slot(out), slot(x), 0);
+        uint32_t limbs[8] = {0};
+        mpz_export(limbs, nullptr, -1, sizeof(uint32_t), 0, 0, c.get_mpz_t());
+        if (log) log->batch_consts.insert(log->batch_consts.end(), limbs, limbs + 8);
+        std::memcpy(ctx.memory_data().data() + scratch, limbs, 32);
+        ctx.stack_push(out);
+        if (const_first) { ctx.stack_push(scratch); ctx.stack_push(x); }
+        else { ctx.stack_push(x); ctx.stack_push(scratch); }
+        call(fn);
+    }
+    void copy(uint32_t out, uint32_t in) {
+        ev(EV_VCOPY, slot(out), slot(in), 0);
+        ctx.stack_push(out); ctx.stack_push(in);
+        call("vbn254fr_copy");
+    }
+    void assert_equal(uint32_t x, uint32_t y) {
+        ev(EV_VASSERT_EQ, slot(x), slot(y), 0);
+        ctx.stack_push(x); ctx.stack_push(y);
+        call("vbn254fr_assert_equal");
+    }
+    // all 254 bits: the call commits one row per bit (vbn254fr.hpp:548-565)
+    void bit_decompose(uint32_t arr_addr, const std::vector<uint32_t> &outs, uint32_t x) {
+        for (uint32_t i = 0; i < outs.size(); i++) {
+            ev(EV_VBIT, slot(outs[i]), slot(x), i);
+            ctx.template memory_store<uint32_t>(arr_addr + 4 * i, ctx.template memory_load<uint32_t>(outs[i]));
+        }
+        ctx.stack_push(arr_addr); ctx.stack_push(x);
+        call("vbn254fr_bit_decompose");
+    }
+};
+
+template <typename Ctx>
+static void run_vbn_program(Ctx &ctx, run_log *log, uint32_t l, uint32_t k) {
+    tiny_module m({});
+    ctx.store(&m.store);
+    ctx.module(&m.inst);
+    auto dummy = ctx.make_frame();
+    dummy->module = &m.inst;
+    ctx.set_current_frame(dummy.get());
+    ctx.stack_push(std::move(dummy));
+    ctx.template add_host_module<env_module<Ctx>>(&ctx);
+    ctx.template add_host_module<vbn254fr_module<Ctx>>(&ctx);
+
+    vbn_driver<Ctx> v{ctx, log, k, l};
+    uint32_t a = v.new_var(), b = v.new_var(), c = v.new_var(), d = v.new_var(), e = v.new_var(), f = v.new_var(), g = v.new_var();
+    v.set_ui_scalar(a, 0x12345u);
+    v.set_str_scalar(b, "1234567890123456789012345678901234567890123456789012345678901234567", 10);
+    v.op3(EV_VADD, "vbn254fr_addmod", c, a, b);
+    v.op3(EV_VMUL, "vbn254fr_mulmod", d, c, b);
+    v.op3(EV_VMUL, "vbn254fr_mulmod", e, a, a);               // x == y: the y row is a copy of the encoded x
+    v.op3(EV_VSUB, "vbn254fr_submod", f, d, e);
+    v.op3(EV_VDIV, "vbn254fr_divmod", g, f, b);
+    v.op3(EV_VMUL, "vbn254fr_mulmod", c, g, b);
+    v.assert_equal(c, f);
+    v.copy(d, g);
+    v.opc(EV_VADDC, "vbn254fr_addmod_constant", e, d, mpz_class("987654321987654321987654321", 10));
+    v.opc(EV_VSUBC, "vbn254fr_submod_constant", e, e, mpz_class(77));
+    v.opc(EV_VCSUB, "vbn254fr_constant_submod", f, e, mpz_class("123456789123456789", 10), true);
+    v.opc(EV_VMULC, "vbn254fr_mulmod_constant", f, f, mpz_class("55555555555555555555", 10));
+    v.opc(EV_VMONTMULC, "vbn254fr_mont_mul_constant", g, f, mpz_class("31415926535897932384626433832795", 10));
+    std::vector<uint32_t> bits;
+    for (uint32_t i = 0; i < field_t::num_bits; i++) bits.push_back(v.new_var());
+    v.bit_decompose(8192, bits, a);
+    // a few scalar witnesses between and after the batch rows, so both kinds of row interleave
+    {
+        auto x = ctx.backend().acquire_witness(); x.val(123456789u);
+        auto y = ctx.backend().acquire_witness(); y.val(987654321u);
+        auto z = ctx.backend().eval(x * y);
+        auto w = ctx.backend().acquire_witness(); w.val(121932631112635269ull);
+        ctx.backend().assert_equal(z, w);
+    }
+    ctx.stack_pop();
+    ctx.finalize();
+}
+
+template <typename Ctx>
+static void run_named(const std::string &prog, Ctx &ctx, run_log *log, uint32_t l, uint32_t k) {
+    if (prog == "i64_mul") run_wasm_binops(ctx, opcode::inn_mul, kI64Mul, std::size(kI64Mul));
+    else if (prog == "i64_mul3") run_wasm_binops(ctx, opcode::inn_mul, kI64Mul + 6, 3);
+    else if (prog == "vbn") run_vbn_program(ctx, log, l, k);
+    else throw std::runtime_error("unknown program " + prog);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static std::string hex(const void *p, size_t n) {
+    static const char d[] = "0123456789abcdef";
+    std::string s(2 * n, '0');
+    for (size_t i = 0; i < n; i++) { unsigned char c = ((const unsigned char *)p)[i]; s[2 * i] = d[c >> 4]; s[2 * i + 1] = d[c & 15]; }
+    return s;
+}
+template <typename T> static std::string hexv(const std::vector<T> &v) { return hex(v.data(), v.size() * sizeof(T)); }
+
+int main(int argc, char **argv) {
+    if (argc < 4) { std::fprintf(stderr, "usage: %s <program> <k> <out.json> [seed byte]\n", argv[0]); return 2; }
+    const std::string prog = argv[1];
+    const size_t k = std::stoul(argv[2]), l = k - params::sample_size, n = 4 * k;
+    const unsigned seed_byte = argc > 4 ? std::stoul(argv[4]) : 7;
+    std::streambuf *chatter = std::cout.rdbuf();                 // the reference prints statistics on stdout; keep them off the JSON
+    std::ofstream devnull("/dev/null");
+    if (!std::getenv("REFCTX_VERBOSE")) std::cout.rdbuf(devnull.rdbuf());
+
+    // src/webgpu_prover.cpp:228-245
+    auto [omega_k, omega_2k, omega_4k] = field_t::generate_omegas(k, n);
+    executor_t executor;
+    executor.webgpu_init(1, "");
+    executor.ntt_init(l, k, n, field_t::modulus, field_t::barrett_factor, omega_k, omega_2k, omega_4k);
+    unsigned char encoding_random_seed[32];
+    for (int i = 0; i < 32; i++) encoding_random_seed[i] = (unsigned char)(seed_byte * 31 + i * 7 + 1);
+    params::hasher::digest instance_hash;                         // no public arguments: hash of nothing, as a fixed 32-byte string here
+    for (size_t i = 0; i < params::hasher::digest_size; i++) instance_hash.data[i] = (unsigned char)(0xA0 + i);
+
+    run_log log1, log2, log3;
+    log1.l = log2.l = log3.l = l;
+
+    // stage 1 (src/webgpu_prover.cpp:249-282)
+    zkp::merkle_tree<params::hasher> tree;
+    std::vector<params::hasher::digest> digests;
+    {
+        auto ctx = std::make_unique<stage1_t>(&log1, false, executor);
+        ctx->init_encoding_random(encoding_random_seed, params::any_iv);
+        run_named(prog, *ctx, &log1, l, k);
+        digests = ctx->flush_digests();
+        tree = digests;
+        executor.device_synchronize();
+    }
+    params::hasher::digest stage1_root = tree.root();
+    auto stage1_seed = zkp::hash<params::hasher>("LigetronStage1", stage1_root, instance_hash);
+
+    // stage 2 (:284-341)
+    unsigned char seed[params::hasher::digest_size];
+    std::copy(stage1_seed.begin(), stage1_seed.end(), seed);
+    std::vector<uint32_t> code_limbs, linear_limbs, quad_limbs, dec_code, dec_linear, dec_quad;
+    mpz_class linear_sum;
+    {
+        auto ctx2 = std::make_unique<stage2_t>(&log2, true, executor);
+        ctx2->init_encoding_random(encoding_random_seed, params::any_iv);
+        ctx2->init_witness_random(seed, params::any_iv);
+        run_named(prog, *ctx2, &log2, l, k);
+        linear_sum = ctx2->linear_sums();
+        buffer_t code_poly = ctx2->code(), linear_poly = ctx2->linear(), quad_poly = ctx2->quadratic();
+        code_limbs = executor.template copy_to_host<uint32_t>(code_poly);
+        linear_limbs = executor.template copy_to_host<uint32_t>(linear_poly);
+        quad_limbs = executor.template copy_to_host<uint32_t>(quad_poly);
+        // the prover's self-check (:355-388,465-471)
+        executor.decode_ntt_device(executor.bind_ntt(code_poly));
+        executor.decode_ntt_device(executor.bind_ntt(linear_poly));
+        executor.decode_ntt_device(executor.bind_ntt(quad_poly));
+        dec_code = executor.template copy_to_host<uint32_t>(code_poly);
+        dec_linear = executor.template copy_to_host<uint32_t>(linear_poly);
+        dec_quad = executor.template copy_to_host<uint32_t>(quad_poly);
+        executor.device_synchronize();
+    }
+    auto stage2_seed = zkp::hash<params::hasher>("LigetronStage2", stage1_root, code_limbs, linear_limbs, quad_limbs);
+    mpz_vector host_code, host_linear, host_quad;
+    host_code.import_limbs(dec_code.data(), dec_code.size(), sizeof(uint32_t), field_t::num_u32_limbs);
+    host_linear.import_limbs(dec_linear.data(), dec_linear.size(), sizeof(uint32_t), field_t::num_u32_limbs);
+    host_linear.resize(l);
+    host_quad.import_limbs(dec_quad.data(), dec_quad.size(), sizeof(uint32_t), field_t::num_u32_limbs);
+    host_quad.resize(l);
+    const bool valid_code = std::all_of(host_code.begin() + k, host_code.end(), [](const auto &x) { return x == 0; });
+    const bool valid_linear = zkp::validate_sum<field_t>(host_linear, linear_sum);
+    const bool valid_quad = zkp::validate(host_quad);
+
+    // sampling (:343-353): the reference's hash engine would feed boost's uniform_int_distribution; Boost is absent, the
+    // repo's restatement of it stands in (its parity is unpinned -- DESIGN.md section 2)
+    cuda::host::digest s2;
+    std::memcpy(s2.data, stage2_seed.data, 32);
+    std::vector<uint64_t> sample64 = cuda::host::sample_indices(s2, n, params::sample_size);
+    std::vector<size_t> sample_index(sample64.begin(), sample64.end());
+    auto decommit = tree.decommit(sample_index);
+
+    // stage 3 (:393-407)
+    std::vector<uint32_t> samplings;
+    {
+        auto ctx3 = std::make_unique<stage3_t>(&log3, false, executor, sample_index);
+        ctx3->init_encoding_random(encoding_random_seed, params::any_iv);
+        run_named(prog, *ctx3, &log3, l, k);
+        samplings = ctx3->host_samplings();
+    }
+    if (log1.kinds != log2.kinds || log1.kinds != log3.kinds || log1.rows != log3.rows || log1.batch_args != log2.batch_args)
+        throw std::runtime_error("the three passes did not see the same rows");
+
+    std::cout.rdbuf(chatter);
+    uint32_t const_sum[8] = {0};
+    mpz_export(const_sum, nullptr, -1, sizeof(uint32_t), 0, 0, linear_sum.get_mpz_t());
+    std::vector<std::pair<size_t, params::hasher::digest>> nodes(decommit.nodes().begin(), decommit.nodes().end());
+    std::sort(nodes.begin(), nodes.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+
+    std::ofstream out(argv[3]);
+    out << "{\n";
+    out << "\"program\": \"" << prog << "\", \"executor\": \"" << kExecutorName << "\", \"l\": " << l << ", \"k\": " << k << ", \"n\": " << n << ",\n";
+    out << "\"encoding_seed\": \"" << hex(encoding_random_seed, 32) << "\", \"instance_hash\": \"" << hex(instance_hash.data, 32) << "\",\n";
+    out << "\"kinds\": [";
+    for (size_t i = 0; i < log1.kinds.size(); i++) out << (i ? "," : "") << log1.kinds[i];
+    out << "],\n";
+    out << "\"values\": \"" << hexv(log1.rows) << "\",\n";
+    out << "\"coefs\": \"" << hexv(log2.rows) << "\",\n";
+    out << "\"batch_args\": \"" << hexv(log1.batch_args) << "\", \"batch_consts\": \"" << hexv(log1.batch_consts) << "\",\n";
+    out << "\"const_sum\": \"" << hex(const_sum, 32) << "\",\n";
+    out << "\"digests\": \"" << hex(digests.data(), digests.size() * sizeof(digests[0])) << "\",\n";
+    out << "\"root\": \"" << hex(stage1_root.data, 32) << "\", \"stage1_seed\": \"" << hex(stage1_seed.data, 32) << "\", \"stage2_seed\": \"" << hex(stage2_seed.data, 32) << "\",\n";
+    out << "\"code\": \"" << hexv(code_limbs) << "\",\n\"linear\": \"" << hexv(linear_limbs) << "\",\n\"quad\": \"" << hexv(quad_limbs) << "\",\n";
+    out << "\"valid\": [" << valid_code << "," << valid_linear << "," << valid_quad << "],\n";
+    out << "\"sample_index\": [";
+    for (size_t i = 0; i < sample_index.size(); i++) out << (i ? "," : "") << sample_index[i];
+    out << "],\n\"decommit_total\": " << decommit.size() << ", \"decommit_nodes\": {";
+    for (size_t i = 0; i < nodes.size(); i++) out << (i ? "," : "") << "\"" << nodes[i].first << "\": \"" << hex(nodes[i].second.data, 32) << "\"";
+    out << "},\n\"samplings\": \"" << hexv(samplings) << "\"\n}\n";
+    out.close();
+    std::printf("%s k=%zu on %s: %zu events, root %s, valid %d%d%d\n", prog.c_str(), k, kExecutorName, log1.kinds.size(), hex(stage1_root.data, 32).c_str(),
+                (int)valid_code, (int)valid_linear, (int)valid_quad);
+    return (valid_code && valid_linear && valid_quad) ? 0 : 1;
+}

@@ -1,0 +1,119 @@
+"""The REFERENCE's own prover layers as the checker (CPU part).
+
+tests/golden/refctx_*.json hold what the reference's stage contexts (include/zkp/nonbatch_context.hpp), its backend and
+witness manager (include/zkp/backend/), its interpreter's opcode semantics (include/interpreter_impl.hpp) and its env /
+vbn254fr host modules commit for three programs, when compiled where they lie and run over the CPU oracle as executor
+(tests/refctx/ref_contexts.cpp, oracle/Makefile target `refctx`).  Here: the CPU restatement of the prover
+(oracle/prover_ref.py, what the GPU prover is checked against elsewhere) must reproduce those runs bit for bit; the harness
+must regenerate the committed vectors; and, where /root/reference is present, the reference's stage contexts must COMPILE
+against the CUDA executor through the compat headers (the drop-in boundary as a build result, not a reading)."""
+import json
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import prover_ref as ref
+import refctx_util as U
+
+REFERENCE = os.environ.get("LGR_REFERENCE_ROOT", "/root/reference")
+
+
+@pytest.mark.parametrize("case", U.CASES)
+def test_restatement_reproduces_the_reference_run(oracle, case):
+    """root, seeds, code / linear / quadratic test vectors, sampled columns and Merkle openings of the reference's own
+    three passes == oracle/prover_ref.py on the statement those passes saw"""
+    st = U.load(case)
+    fx = st["fx"]
+    out = ref.prove(st["l"], st["k"], st["kinds"], st["values"], st["coefs"], st["const_sum"], st["encoding_seed"], st["instance_hash"],
+                    arena_slots=st["slots"], batch_args=st["args"], batch_consts=st["consts"])
+    assert out["root"].hex() == fx["root"]
+    assert U.sha(out["digests"]) == fx["sha256"]["digests"]
+    assert out["stage1_seed"].hex() == fx["stage1_seed"]
+    for name in ("code", "linear", "quad"):
+        assert U.sha(out[name]) == fx["sha256"][name], name
+    assert out["stage2_seed"].hex() == fx["stage2_seed"]
+    assert [int(i) for i in out["sample"]] == fx["sample_index"]
+    assert U.sha(out["samplings"]) == fx["sha256"]["samplings"]
+    assert out["encoded_rows"] == out["samplings"].shape[0]
+    assert list(out["valid"]) == [bool(v) for v in fx["valid"]] == [True, True, True]
+    # openings: merkle_tree::decommit of the reference (merkle_tree.hpp:155-215) against the restated level walk
+    assert out["total_count"] == fx["decommit_total"]
+    assert sorted(out["positions"]) == fx["decommit_positions"]
+    by_pos = dict(zip(out["positions"], out["siblings"]))
+    assert U.sha(np.frombuffer(b"".join(by_pos[p] for p in fx["decommit_positions"]), np.uint8)) == fx["sha256"]["decommit_siblings"]
+    # the same through the proof container (the check the GPU prover's envelope goes through in tests/test_refctx_gpu.py)
+    meta = {"prover_version": "0", "program_hash": bytes(32), "generated_at": 1, "k": st["k"], "n": st["n"], "sample_size": 192}
+    env = ref.build_envelope(meta, out["root"], out["siblings"], out["sample"], out["code"], out["linear"], out["quad"], out["samplings"])
+    U.check_envelope(ref.parse_envelope(env), fx, ref.sibling_positions)
+
+
+def test_i64_mul_row_counts_at_the_default_geometry():
+    """BASELINE config 4 (tests/i64_mul.wat at k = 8192): the reference commits 1 linear row + 1 quadratic triple + 3 masks"""
+    st = U.load("i64_mul_k8192")
+    assert list(st["kinds"]) == [ref.EV_LINEAR, ref.EV_QUAD]
+    assert st["values"].shape[0] == 4
+    # 27 private constants of 64 bits + 9 products of 128 bits, every bit slot b*b = b, plus the 9 products themselves
+    quad_slots = int(st["values"][1].any(axis=1).sum())
+    assert quad_slots <= 27 * 64 + 9 * 128 + 9 and (st["values"][3] != 0).any()
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("case", ["i64_mul3_k256", "vbn_k256"])
+def test_harness_regenerates_the_committed_vectors(oracle, case):
+    """the committed JSON is exactly what the harness writes today (same reference sources, same oracle)"""
+    gen = U.compact_module()
+    prog, k = case.rsplit("_k", 1)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "out.json")
+        subprocess.check_call([U.REF_BIN_CPU, prog, k, path], stdout=subprocess.DEVNULL)
+        got = gen.compact(json.load(open(path)))
+    want = U.load(case)["fx"]
+    for key in want:
+        assert got[key] == want[key], key
+
+
+BOUNDARY_TU = r"""
+#include <algorithm>
+#include <cstring>
+#include <format>
+#include <fstream>
+#include <iomanip>
+#include <memory>
+#include <stdexcept>
+#include <params.hpp>
+#include <interpreter.hpp>
+#include <wgpu.hpp>                       // ligero-prover_b200/host/compat: webgpu_context = cuda_context
+#include <zkp/finite_field_gmp.hpp>
+#include <zkp/nonbatch_context.hpp>
+#include <host_modules/vbn254fr.hpp>
+using namespace ligero; using namespace ligero::vm;
+using field_t = zkp::bn254_gmp;
+static_assert(std::is_same_v<webgpu_context, cuda_context>);
+using ctx1_t = zkp::nonbatch_stage1_context<field_t, webgpu_context, zkp::stage1_random_policy, params::hasher>;
+template struct zkp::nonbatch_stage1_context<field_t, webgpu_context, zkp::stage1_random_policy, params::hasher>;
+template struct zkp::nonbatch_stage2_context<field_t, webgpu_context, zkp::stage2_random_policy>;
+template struct zkp::nonbatch_stage3_context<field_t, webgpu_context, zkp::stage3_random_policy>;
+template struct zkp::nonbatch_verifier_context<field_t, webgpu_context, zkp::verifier_random_policy, params::hasher>;
+template struct ligero::vm::vbn254fr_module<ctx1_t>;
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "include", "zkp")) or shutil.which("g++") is None,
+                    reason="needs the reference tree and g++ (build container only)")
+def test_reference_contexts_compile_against_the_cuda_executor(tmp_path):
+    """explicit instantiation of the reference's stage 1/2/3 contexts, its verifier context and its vbn254fr module with
+    Executor = ligero::webgpu_context, which the compat include directory makes the CUDA adapter: every member function
+    (some 40 executor call sites) must type-check -- with NO edit to the reference's headers"""
+    gen = os.path.join(U.ROOT, "oracle", "_ref", "gen")
+    subprocess.check_call(["python3", os.path.join(U.ROOT, "oracle", "refgen.py"), REFERENCE, gen])
+    tu = tmp_path / "boundary.cpp"
+    tu.write_text(BOUNDARY_TU)
+    cmd = ["g++", "-std=c++20", "-fsyntax-only", "-I", gen, "-I", os.path.join(U.ROOT, "ligero-prover_b200", "host", "compat"),
+           "-I", os.path.join(U.ROOT, "ligero-prover_b200", "host"), "-I", os.path.join(REFERENCE, "include"),
+           "-I", os.path.join(U.ROOT, "tests", "stubs"), str(tu)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-4000:]

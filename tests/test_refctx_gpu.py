@@ -1,0 +1,61 @@
+"""The REFERENCE's own prover layers as the checker (B200 part).
+
+(1) The GPU prover (lgrp_prove: the batched path over lgr.h) must reproduce, bit for bit, what the reference's own stage
+    contexts / backend / interpreter committed for the same statement (tests/golden/refctx_*.json, generated from the
+    reference's sources by tests/golden/make_refctx_vectors.py) -- incl. BASELINE config 4, tests/i64_mul.wat at k = 8192.
+(2) oracle/_ref/refctx_cuda is the reference's stage contexts, vbn254fr module and interpreter compiled with
+    Executor = ligero::webgpu_context := the CUDA executor (ligero-prover_b200/host/compat): the unchanged reference code
+    drives liblgr.so one row at a time, and must arrive at the same vectors."""
+import importlib
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import prover_ref as ref
+import refctx_util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pr(lgr):
+    return importlib.import_module("ligero_prover_b200.prover")
+
+
+@pytest.mark.parametrize("case", U.CASES)
+def test_gpu_prover_reproduces_the_reference_run(lgr, pr, executor_factory, case):
+    st = U.load(case)
+    fx, l, k, n = st["fx"], st["l"], st["k"], st["n"]
+    ex = executor_factory(k, l)
+    proof = pr.prove(ex, st["kinds"], st["values"], st["coefs"], st["const_sum"], st["encoding_seed"], st["instance_hash"], generated_at=1,
+                     arena_slots=st["slots"], batch_args=st["args"] if len(st["args"]) else None,
+                     batch_consts=st["consts"] if len(st["consts"]) else None)
+    info = proof.info()
+    assert list(info["valid"]) == [True, True, True]
+    assert info["stage1_seed"].hex() == fx["stage1_seed"] and info["stage2_seed"].hex() == fx["stage2_seed"]
+    U.check_envelope(ref.parse_envelope(proof.gzip), fx, ref.sibling_positions)
+    proof.close()
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CUDA), reason="oracle/_ref/refctx_cuda not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("case", U.CASES)
+def test_reference_stage_contexts_run_on_the_cuda_executor(case):
+    """the drop-in boundary, run: the reference's unchanged stage-1/2/3 contexts, witness manager, interpreter and vbn254fr
+    module, with liblgr.so behind `webgpu_context`, give the vectors they give over the CPU oracle"""
+    gen = U.compact_module()
+    prog, k = case.rsplit("_k", 1)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "out.json")
+        res = subprocess.run([U.REF_BIN_CUDA, prog, k, path], capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
+        raw = json.load(open(path))
+    assert raw["executor"] == "cuda"
+    got = gen.compact(raw)
+    want = U.load(case)["fx"]
+    for key in want:
+        if key != "generated_by":
+            assert got[key] == want[key], key
