@@ -235,11 +235,13 @@ int lgrp_wat_emit(const char *wat, size_t len, uint32_t l, const uint8_t *stage1
     LGRP_TRY
     if (!wat || !rows_out || !l) throw std::invalid_argument("null argument");
     wat_program prog(std::string(wat, len));
-    constraint_system cs;
     wat_stats ws;
-    prog.run(cs, ws);
     lgrp_packer *pk = new lgrp_packer(l);
-    try { cs.pack(pk->p, stage1_seed, const_sum); } catch (...) { delete pk; throw; }
+    try {
+        witness_machine m(pk->p, stage1_seed);
+        prog.run(m, ws);
+        m.finish(const_sum);
+    } catch (...) { delete pk; throw; }
     fill_stats(stats, ws);
     *rows_out = pk;
     LGRP_END
@@ -252,11 +254,13 @@ int lgrp_prove_wat(lgr_ctx *ctx, const char *wat, size_t len, const uint8_t enco
     uint32_t l = 0, k = 0, n = 0;
     if (lgr_geometry(ctx, &l, &k, &n)) throw std::runtime_error(lgr_last_error());
     wat_program prog(std::string(wat, len));
-    constraint_system cs;
     wat_stats ws;
-    prog.run(cs, ws);
     row_packer values(l);
-    cs.pack(values, nullptr, nullptr);                       // stage 1 needs the values only
+    {
+        witness_machine m(values, nullptr);                  // stage 1 needs the values only
+        prog.run(m, ws);
+        m.finish(nullptr);
+    }
     statement st;
     st.l = l; st.k = k;
     memcpy(st.encoding_seed, encoding_seed, 32);
@@ -273,8 +277,11 @@ int lgrp_prove_wat(lgr_ctx *ctx, const char *wat, size_t len, const uint8_t enco
         st.events.push_back(ev);
     }
     st.coef_provider = [&](const uint8_t seed[32], std::vector<uint32_t> &coef_rows, uint32_t const_sum[8]) {
-        row_packer with_coefs(l);
-        cs.pack(with_coefs, seed, const_sum);                // same packing, now with one rho per constraint
+        row_packer with_coefs(l);                            // the program again, now drawing the linear-test randomness
+        witness_machine m(with_coefs, seed);
+        wat_stats again;
+        prog.run(m, again);
+        m.finish(const_sum);
         coef_rows = with_coefs.coefs();
     };
     lgrp_proof *p = new lgrp_proof();

@@ -1,27 +1,33 @@
 // Bounded interpreter boundary (BASELINE config 4): a front end for the folded-WAT subset the reference's
 // arithmetic tests use (tests/i64_mul.wat, i64_add.wat, i64_sub.wat: imports env.i64_private_const / env.assert_equal,
 // one exported function of folded i64.const / i64.mul / i64.add / i64.sub / call forms) and the witness emitter behind it.
-// It is NOT the reference's interpreter (include/interpreter_impl.hpp + include/zkp/backend/*.hpp, out of scope): it produces
-// a constraint system with the same meaning and feeds it through row_packer -> matrix_prover, so that a .wat goes from text
-// to a verifying proof through the product's own entry point.
+// It is NOT the reference's interpreter (include/interpreter_impl.hpp + include/zkp/backend/*.hpp: a general WASM machine over
+// an expression-template backend, out of scope); it is a small witness machine that gives every form of the subset the
+// meaning the reference gives it -- which witnesses exist, which linear-test randomness lands on them, and WHEN each one is
+// released into a row:
+//   (call $i64_private_const (i64.const v))   env.hpp:178-188: witness x = v, 64-bit decomposition (core.hpp:714-741: one
+//                                             draw rho, x gets -rho, bit i gets +rho*2^i; every bit b is a slot (b', b'', b)
+//                                             with two clones tied to it by one draw each, witness_manager.hpp:431-441);
+//                                             x is released when the call returns, the bits travel on the stack
+//   (i64.mul a b)                             interpreter_impl.hpp:351-391: operands recomposed (core.hpp:761-781: sum witness,
+//                                             one draw, bits get +rho*2^i), slot (x, y, x*y), 128-bit decomposition of the
+//                                             product, top 64 bits released at once, then product, y, x -- so the slot lands
+//                                             after them -- and only then the operands' bits (a's, then b's, each most
+//                                             significant first: the handler's popped stack values die last)
+//   (i64.add a b) / (i64.sub a b)             :262-349: s = x + y resp. (2^64 - y) + x with one draw (the constant lands in
+//                                             const_sum), 65-bit decomposition, top bit released, then s, y, x
+//   (call $assert_equal a b)                  env.hpp:64-77: both sides recomposed, one draw ties them, b's witness is
+//                                             released before a's
+//   a literal operand                         a bare witness (nonbatch_context.hpp:275-299): no constraint of its own
+// Linear-test randomness comes from the LINEAR stream (AES-CTR keyed with the stage-1 seed, nonbatch_context.hpp:105-112),
+// drawn in execution order, so the program is run again once the seed exists (as the reference re-runs it in stage 2).
 //
-// What each form contributes (cf. include/host_modules/env.hpp:64-77,178-188 and the backend's bit_decompose,
-// include/zkp/backend/ligero.hpp:862-890):
-//   (call $i64_private_const (i64.const v))   witness x = v, range-checked by a 64-bit decomposition: 64 bit slots b_i with
-//                                             b_i * b_i = b_i and the linear constraint x - sum 2^i b_i = 0
-//   (i64.mul a b)                             slot (a', b', p) with a' = a, b' = b, p = a*b in the field (< 2^128), p decomposed
-//                                             into 128 bits, result = the low 64 bits recomposed (wrap-around of i64.mul)
-//   (i64.add a b) / (i64.sub a b)             s = a + b resp. a - b + 2^64 (a constant term: it lands in const_sum), 65-bit
-//                                             decomposition, result = low 64 bits
-//   (call $assert_equal a b)                  linear constraint a - b = 0
-// A quadratic slot holds three field elements (x, y, z) with x*y = z enforced by the quadratic test; "b*b = b" therefore
-// also needs x = y and x = z as linear constraints.  Every linear constraint c gets its own random rho_c from the LINEAR
-// stream (AES-CTR keyed with the stage-1 seed, nonbatch_context.hpp:105-112); the coefficient of a slot is
-// sum_c rho_c * (multiplier of the slot in c), and const_sum = sum_c rho_c * constant_c (zkp/common.hpp:68-79).
-//
-// Parity statement: the ORDER in which the reference releases witnesses (and so the row order) follows the
-// lifetime of C++ temporaries inside its interpreter and cannot be pinned without running it; this emitter releases them in
-// creation order.  The proof it leads to is a valid Ligero proof of the same statement, not a byte-identical one.
+// Parity statement: pinned to a run of the reference itself.  tests/refctx/ref_contexts.cpp compiles the reference's own
+// interpreter, env module, backend and witness manager and runs programs of this subset through them; on tests/i64_mul.wat
+// (tests/golden/refctx_i64_mul_k8192.json), on the repo's mul64.wat and on random expression trees this emitter produces the
+// same rows, the same coefficient rows and the same const_sum, element for element (tests/test_refctx_cpu.py).  The
+// release order follows the lifetimes of the reference's C++ objects as GCC orders them; another compiler's unspecified
+// evaluation order could move witnesses inside a row.
 #pragma once
 #include <array>
 #include <cstdint>
@@ -105,112 +111,139 @@ private:
     size_t pos_ = 0;
 };
 
-// ---- the constraint system ----------------------------------------------------------------------------------
+// ---- the witness machine ------------------------------------------------------------------------------------
 struct wat_stats {
     uint64_t private_consts = 0, asserts = 0, arithmetic_ops = 0;
-    uint64_t linear_witnesses = 0, quadratic_slots = 0, linear_constraints = 0;
+    uint64_t linear_witnesses = 0, quadratic_slots = 0, linear_constraints = 0;   // linear_constraints = draws from the linear stream
     uint64_t violated_constraints = 0;           // > 0: the program's assertions do not hold (the proof will not validate)
 };
 
-class constraint_system {
+class witness_machine {
 public:
-    struct ref { bool quad = false; uint32_t pos = 0; size_t index = 0; };           // a slot: linear[index] or quad[index].{x,y,z}
-    struct term { ref slot; Fr mult; };
-    struct constraint { std::vector<term> terms; Fr constant{{0, 0, 0, 0}}; };       // sum mult * value(slot) + constant == 0
+    using wid = uint32_t;
 
-    ref new_linear(const Fr &v) { lin_.push_back(v); return ref{false, 0, lin_.size() - 1}; }
-    size_t new_slot(const Fr &x, const Fr &y, const Fr &z) { quad_.push_back({x, y, z}); return quad_.size() - 1; }
-    static ref at(size_t slot, uint32_t pos) { return ref{true, pos, slot}; }
-    const Fr &value(const ref &r) const { return r.quad ? quad_[r.index][r.pos] : lin_[r.index]; }
-    void equal(const ref &a, const ref &b) { constraint c; c.terms = {{a, one()}, {b, minus_one()}}; cons_.push_back(std::move(c)); }
-    void add(constraint c) { cons_.push_back(std::move(c)); }
-
-    // bit slot: (b, b, b) with x = y and x = z; returns the x position
-    ref new_bit(uint64_t bit) {
-        const Fr b = lgr::host::from_u64(bit);
-        const size_t s = new_slot(b, b, b);
-        equal(at(s, 0), at(s, 1));
-        equal(at(s, 0), at(s, 2));
-        return at(s, 0);
+    // rows go to `pk` as witnesses are released; with a stage-1 seed the linear-test coefficients are drawn as the reference draws them
+    witness_machine(row_packer &pk, const uint8_t *stage1_seed) : pk_(pk), seeded_(stage1_seed != nullptr) {
+        static const uint8_t any_iv[16] = {0};
+        if (seeded_) rng_.init(stage1_seed, any_iv);
     }
-    // v (an integer < 2^nbits held in `holder`) = sum 2^i bit_i; returns the bit slots
-    std::vector<ref> decompose(const ref &holder, unsigned __int128 v, int nbits) {
-        std::vector<ref> bits;
-        constraint c;
-        c.terms.push_back({holder, one()});
-        Fr w = minus_one();                                                         // -(2^i)
-        for (int i = 0; i < nbits; i++) {
-            bits.push_back(new_bit((uint64_t)((v >> i) & 1)));
-            c.terms.push_back({bits.back(), w});
-            w = lgr::host::add(w, w);
+
+    wid acquire(const Fr &v) { w_.push_back(wit{v, zero(), -1, 0}); return (wid)(w_.size() - 1); }
+    const Fr &value(wid w) const { return w_[w].val; }
+
+    Fr draw() {                                               // generate_linear_random (witness_manager.hpp:344-348)
+        draws_++;
+        if (!seeded_) return zero();
+        uint32_t limbs[8];
+        rng_.next(limbs);
+        return lgr::host::from_u32(limbs);
+    }
+    void coef_add(wid w, const Fr &r) { w_[w].coef = lgr::host::add(w_[w].coef, r); }
+    void coef_sub(wid w, const Fr &r) { w_[w].coef = sub(w_[w].coef, r); }
+    void const_add(const Fr &r) { const_sum_ = lgr::host::add(const_sum_, r); }
+
+    // constrain_equal (witness_manager.hpp:421-429): one draw, +r on a, -r on b
+    void equal(wid a, wid b) {
+        if (!(w_[a].val == w_[b].val)) violated_++;
+        const Fr r = draw();
+        coef_add(a, r);
+        coef_sub(b, r);
+    }
+    wid clone(wid w) { const wid c = acquire(w_[w].val); equal(w, c); return c; }       // clone_witness (:393-397)
+
+    // constrain_quadratic (:474-492): slot positions (a, b, c); a witness that already sits in a slot is replaced by a clone
+    void quadratic(wid c, wid a, wid b) {
+        if (!(lgr::host::mul(w_[a].val, w_[b].val) == w_[c].val)) violated_++;
+        slots_.push_back(slot{});
+        const int s = (int)slots_.size() - 1;
+        const wid arr[3] = {a, b, c};
+        for (int i = 0; i < 3; i++) {
+            wid w = arr[i];
+            const bool taken = w_[w].slot >= 0;
+            if (taken) w = clone(arr[i]);
+            w_[w].slot = s; w_[w].pos = i;
+            slots_[(size_t)s].w[i] = w;
+            if (taken) release(w);
         }
-        cons_.push_back(std::move(c));
+    }
+
+    // commit_release_witness (:117-186)
+    void release(wid w) {
+        wit &x = w_[w];
+        uint32_t v[3][8], c[3][8];
+        if (x.slot < 0) {
+            lgr::host::to_u32(v[0], x.val); lgr::host::to_u32(c[0], x.coef);
+            pk_.push_linear(v[0], c[0]);
+            return;
+        }
+        slot &s = slots_[(size_t)x.slot];
+        s.ready[x.pos] = true;
+        if (!(s.ready[0] && s.ready[1] && s.ready[2])) return;
+        for (int j = 0; j < 3; j++) { lgr::host::to_u32(v[j], w_[s.w[j]].val); lgr::host::to_u32(c[j], w_[s.w[j]].coef); }
+        pk_.push_quadratic(v[0], v[1], v[2], c[0], c[1], c[2]);
+    }
+
+    // bit_decompose (core.hpp:714-741) with constrain_bit (witness_manager.hpp:431-441) per bit
+    std::vector<wid> decompose(wid x, int nbits) {
+        const Fr rho = draw();
+        coef_sub(x, rho);
+        const Fr v = w_[x].val;
+        std::vector<wid> bits;
+        for (int i = 0; i < nbits; i++) {
+            const wid b = acquire(lgr::host::from_u64((v.v[i >> 6] >> (i & 63)) & 1));
+            const wid b1 = clone(b), b2 = clone(b);
+            quadratic(b, b1, b2);
+            release(b1);
+            release(b2);
+            coef_add(b, shl(rho, i));
+            bits.push_back(b);
+        }
         return bits;
     }
-    // new linear witness = sum_{i < n} 2^i bits[i]
-    ref compose(const std::vector<ref> &bits, int n, uint64_t v) {
-        const ref z = new_linear(lgr::host::from_u64(v));
-        constraint c;
-        c.terms.push_back({z, minus_one()});
-        Fr w = one();
-        for (int i = 0; i < n; i++) { c.terms.push_back({bits[(size_t)i], w}); w = lgr::host::add(w, w); }
-        cons_.push_back(std::move(c));
-        return z;
+    // bit_compose (core.hpp:761-781); the caller releases the bits
+    wid compose(const std::vector<wid> &bits) {
+        const wid sum = acquire(zero());
+        const Fr rho = draw();
+        coef_sub(sum, rho);
+        Fr acc = zero();
+        for (size_t i = 0; i < bits.size(); i++) {
+            acc = lgr::host::add(acc, shl(w_[bits[i]].val, (int)i));
+            coef_add(bits[i], shl(rho, (int)i));
+        }
+        w_[sum].val = acc;
+        return sum;
     }
 
-    size_t num_linear() const { return lin_.size(); }
-    size_t num_slots() const { return quad_.size(); }
-    size_t num_constraints() const { return cons_.size(); }
-    uint64_t violated() const {
-        uint64_t bad = 0;
-        for (const constraint &c : cons_) {
-            Fr acc = c.constant;
-            for (const term &t : c.terms) acc = lgr::host::add(acc, lgr::host::mul(t.mult, value(t.slot)));
-            if (acc.v[0] | acc.v[1] | acc.v[2] | acc.v[3]) bad++;
-        }
-        for (const auto &q : quad_) if (!(lgr::host::mul(q[0], q[1]) == q[2])) bad++;
-        return bad;
+    // witness_manager::finalize (the mask rows are the prover's business)
+    void finish(uint32_t const_sum[8]) {
+        pk_.finalize();
+        if (const_sum) lgr::host::to_u32(const_sum, const_sum_);
     }
+    uint64_t draws() const { return draws_; }
+    uint64_t violated() const { return violated_; }
 
-    // rows in creation order through the reference's packing rule; with a stage-1 seed also the linear-test coefficients
-    void pack(row_packer &pk, const uint8_t *stage1_seed, uint32_t const_sum[8]) const {
-        std::vector<Fr> cl(lin_.size(), zero());
-        std::vector<std::array<Fr, 3>> cq(quad_.size(), std::array<Fr, 3>{zero(), zero(), zero()});
-        Fr cs = zero();
-        if (stage1_seed) {
-            static const uint8_t any_iv[16] = {0};
-            fr_random_stream rng(stage1_seed, any_iv);                                // the linear engine of nonbatch_context.hpp:105-112
-            for (const constraint &c : cons_) {
-                uint32_t limbs[8];
-                rng.next(limbs);
-                const Fr rho = lgr::host::to_mont(lgr::host::from_u32(limbs));
-                for (const term &t : c.terms) {
-                    Fr &dst = t.slot.quad ? cq[t.slot.index][t.slot.pos] : cl[t.slot.index];
-                    dst = lgr::host::add(dst, lgr::host::montmul(rho, t.mult));
-                }
-                cs = lgr::host::add(cs, lgr::host::montmul(rho, c.constant));
-            }
-        }
-        uint32_t v[3][8], c[3][8];
-        for (size_t i = 0; i < lin_.size(); i++) {
-            lgr::host::to_u32(v[0], lin_[i]); lgr::host::to_u32(c[0], cl[i]);
-            pk.push_linear(v[0], c[0]);
-        }
-        for (size_t i = 0; i < quad_.size(); i++) {
-            for (int j = 0; j < 3; j++) { lgr::host::to_u32(v[j], quad_[i][j]); lgr::host::to_u32(c[j], cq[i][j]); }
-            pk.push_quadratic(v[0], v[1], v[2], c[0], c[1], c[2]);
-        }
-        pk.finalize();
-        if (const_sum) lgr::host::to_u32(const_sum, cs);
+    static Fr zero() { return Fr{{0, 0, 0, 0}}; }
+    static Fr sub(const Fr &a, const Fr &b) {
+        Fr r;
+        if (lgr::host::sub4(r.v, a.v, b.v)) lgr::host::add4(r.v, r.v, lgr::host::kP);
+        return r;
+    }
+    static Fr shl(const Fr &a, int i) {                       // a * 2^i mod p, i < 254
+        Fr p2 = zero();
+        p2.v[i >> 6] = 1ULL << (i & 63);
+        return lgr::host::mul(a, p2);
     }
 
 private:
-    static Fr zero() { return Fr{{0, 0, 0, 0}}; }
-    static Fr one() { return Fr{{1, 0, 0, 0}}; }
-    static Fr minus_one() { Fr r; const uint64_t o[4] = {1, 0, 0, 0}; lgr::host::sub4(r.v, lgr::host::kP, o); return r; }
-    std::vector<Fr> lin_;
-    std::vector<std::array<Fr, 3>> quad_;
-    std::vector<constraint> cons_;
+    struct wit { Fr val, coef; int slot; int pos; };
+    struct slot { wid w[3] = {0, 0, 0}; bool ready[3] = {false, false, false}; };
+    row_packer &pk_;
+    bool seeded_;
+    fr_random_stream rng_;
+    std::vector<wit> w_;
+    std::vector<slot> slots_;
+    Fr const_sum_ = zero();
+    uint64_t draws_ = 0, violated_ = 0;
 };
 
 // ---- front end ------------------------------------------------------------------------------------------------
@@ -244,7 +277,8 @@ public:
         start_ = start;
     }
 
-    void run(constraint_system &cs, wat_stats &st) const {
+    // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
+    void run(witness_machine &m, wat_stats &st) const {
         const sexpr &f = *funcs_.at(start_);
         for (size_t i = 2; i < f.list.size(); i++) {
             const std::string &h = f.list[i].head();
@@ -252,16 +286,17 @@ public:
                 if (h != "type" && f.list[i].list.size() > 1) throw std::invalid_argument("wat: _start with parameters / locals is not supported");
                 continue;
             }
-            eval(f.list[i], cs, st);
+            value leftover = eval(f.list[i], m, st);
+            drop(leftover, m);                                // a value nobody consumed dies with the frame
         }
-        st.linear_witnesses = cs.num_linear();
-        st.quadratic_slots = cs.num_slots();
-        st.linear_constraints = cs.num_constraints();
-        st.violated_constraints = cs.violated();
+        st.linear_constraints = m.draws();
+        st.violated_constraints = m.violated();
     }
 
 private:
-    struct value { bool present = false, witness = false; uint64_t v = 0; constraint_system::ref slot; };
+    using wid = witness_machine::wid;
+    // a stack value: nothing, a literal, or the bit witnesses of a 64-bit result (decomposed_bits, least significant first)
+    struct value { bool present = false, bits = false; uint64_t v = 0; std::vector<wid> b; };
     static std::string unquote(const std::string &s) { return (s.size() >= 2 && s.front() == '"') ? s.substr(1, s.size() - 2) : s; }
     static uint64_t parse_i64(const std::string &t) {
         std::string s;
@@ -290,60 +325,76 @@ private:
         return neg ? (uint64_t)(0 - u) : u;
     }
     static value concrete(uint64_t v) { value r; r.present = true; r.v = v; return r; }
-    static value witness(uint64_t v, const constraint_system::ref &slot) { value r; r.present = r.witness = true; r.v = v; r.slot = slot; return r; }
-
+    static value decomposed(uint64_t v, std::vector<wid> b) { value r; r.present = r.bits = true; r.v = v; r.b = std::move(b); return r; }
+    // ~decomposed_bits (core.hpp:100-105): most significant bit first
+    static void drop(value &a, witness_machine &m) {
+        for (size_t i = a.b.size(); i-- > 0;) m.release(a.b[i]);
+        a.b.clear();
+    }
+    // make_witness (nonbatch_context.hpp:275-299): a literal becomes a bare witness, bits are recomposed.  The bits do
+    // NOT die here: decomposed_bits has a destructor and therefore no move constructor, so the popped stack value the
+    // opcode handler holds keeps a copy until the handler returns -- after its witnesses, first operand first (sx is
+    // declared after sy).
+    static wid make_witness(const value &a, witness_machine &m, wat_stats &st) {
+        st.linear_witnesses++;
+        return a.bits ? m.compose(a.b) : m.acquire(lgr::host::from_u64(a.v));
+    }
     // i64_private_const (env.hpp:178-188): a fresh witness with a 64-bit range check
-    static value private_const(uint64_t v, constraint_system &cs, wat_stats &st) {
+    static value private_const(uint64_t v, witness_machine &m, wat_stats &st) {
         st.private_consts++;
-        const constraint_system::ref x = cs.new_linear(lgr::host::from_u64(v));
-        cs.decompose(x, v, 64);
-        return witness(v, x);
-    }
-    static value promote(const value &a, constraint_system &cs) {        // a compile-time constant entering a constraint
-        if (a.witness) return a;
-        const constraint_system::ref x = cs.new_linear(lgr::host::from_u64(a.v));
-        constraint_system::constraint c;                                  // x - v = 0 pins it to the public constant
-        c.terms.push_back({x, Fr{{1, 0, 0, 0}}});
-        const Fr fv = lgr::host::from_u64(a.v);
-        const uint64_t z[4] = {0, 0, 0, 0};
-        Fr neg; if (a.v) lgr::host::sub4(neg.v, lgr::host::kP, fv.v); else memcpy(neg.v, z, 32);
-        c.constant = neg;
-        cs.add(std::move(c));
-        return witness(a.v, x);
+        st.linear_witnesses++;
+        st.quadratic_slots += 64;
+        const wid x = m.acquire(lgr::host::from_u64(v));
+        std::vector<wid> bits = m.decompose(x, 64);
+        m.release(x);
+        return decomposed(v, std::move(bits));
     }
 
-    value binop(const std::string &op, value a, value b, constraint_system &cs, wat_stats &st) const {
+    // exec_inn_mul / exec_inn_add / exec_inn_sub on 64-bit operands (interpreter_impl.hpp:262-391)
+    value binop(const std::string &op, value a, value b, witness_machine &m, wat_stats &st) const {
         if (!a.present || !b.present) throw std::invalid_argument("wat: " + op + " needs two operands");
-        if (!a.witness && !b.witness) {
+        if (!a.bits && !b.bits) {
             return concrete(op == "i64.mul" ? a.v * b.v : (op == "i64.add" ? a.v + b.v : a.v - b.v));
         }
-        a = promote(a, cs); b = promote(b, cs);
         st.arithmetic_ops++;
+        const uint64_t av = a.v, bv = b.v;
+        const wid x = make_witness(a, m, st), y = make_witness(b, m, st);
         if (op == "i64.mul") {
-            const unsigned __int128 p = (unsigned __int128)a.v * b.v;
-            Fr fp{{(uint64_t)p, (uint64_t)(p >> 64), 0, 0}};
-            const size_t s = cs.new_slot(lgr::host::from_u64(a.v), lgr::host::from_u64(b.v), fp);
-            cs.equal(constraint_system::at(s, 0), a.slot);
-            cs.equal(constraint_system::at(s, 1), b.slot);
-            const std::vector<constraint_system::ref> bits = cs.decompose(constraint_system::at(s, 2), p, 128);
-            return witness((uint64_t)p, cs.compose(bits, 64, (uint64_t)p));
+            const unsigned __int128 p = (unsigned __int128)av * bv;
+            const wid z = m.acquire(Fr{{(uint64_t)p, (uint64_t)(p >> 64), 0, 0}});
+            m.quadratic(z, x, y);
+            st.quadratic_slots += 129;
+            std::vector<wid> bits = m.decompose(z, 128);
+            for (int i = 127; i >= 64; i--) m.release(bits[(size_t)i]);      // drop_msb(64)
+            bits.resize(64);
+            m.release(z); m.release(y); m.release(x);                         // big_result, y, x leave scope in that order,
+            drop(a, m); drop(b, m);                                           // then the popped operands: sx (declared last), sy
+            return decomposed((uint64_t)p, std::move(bits));
         }
-        // add: s = a + b;  sub: s = a - b + 2^64 (never negative)
         const bool sub = op == "i64.sub";
-        const unsigned __int128 sv = sub ? ((unsigned __int128)a.v + (((unsigned __int128)1) << 64) - b.v) : ((unsigned __int128)a.v + b.v);
-        const constraint_system::ref sslot = cs.new_linear(Fr{{(uint64_t)sv, (uint64_t)(sv >> 64), 0, 0}});
-        constraint_system::constraint c;
-        Fr m1; const uint64_t o[4] = {1, 0, 0, 0}; lgr::host::sub4(m1.v, lgr::host::kP, o);
-        c.terms.push_back({sslot, Fr{{1, 0, 0, 0}}});
-        c.terms.push_back({a.slot, m1});
-        c.terms.push_back({b.slot, sub ? Fr{{1, 0, 0, 0}} : m1});
-        if (sub) { const uint64_t two64[4] = {0, 1, 0, 0}; lgr::host::sub4(c.constant.v, lgr::host::kP, two64); }   // - 2^64
-        cs.add(std::move(c));
-        const std::vector<constraint_system::ref> bits = cs.decompose(sslot, sv, 65);
-        return witness((uint64_t)sv, cs.compose(bits, 64, (uint64_t)sv));
+        const unsigned __int128 sv = sub ? ((unsigned __int128)av + (((unsigned __int128)1) << 64) - bv) : ((unsigned __int128)av + bv);
+        const wid sw = m.acquire(Fr{{(uint64_t)sv, (uint64_t)(sv >> 64), 0, 0}});
+        st.linear_witnesses++;
+        const Fr r = m.draw();
+        m.coef_sub(sw, r);
+        if (sub) {                                                            // (2^64 - y) + x: y takes -r, the constant adds 2^64 * r
+            m.coef_sub(y, r);
+            m.const_add(witness_machine::shl(r, 64));
+            m.coef_add(x, r);
+        } else {
+            m.coef_add(x, r);
+            m.coef_add(y, r);
+        }
+        st.quadratic_slots += 65;
+        std::vector<wid> bits = m.decompose(sw, 65);
+        m.release(bits[64]);                                                  // drop_msb(1)
+        bits.resize(64);
+        m.release(sw); m.release(y); m.release(x);
+        drop(a, m); drop(b, m);
+        return decomposed((uint64_t)sv, std::move(bits));
     }
 
-    value eval(const sexpr &e, constraint_system &cs, wat_stats &st) const {
+    value eval(const sexpr &e, witness_machine &m, wat_stats &st) const {
         if (!e.is_list) throw std::invalid_argument("wat: only folded instructions are supported (" + e.atom + ")");
         const std::string &h = e.head();
         if (h == "i64.const") {
@@ -352,25 +403,27 @@ private:
         }
         if (h == "i64.mul" || h == "i64.add" || h == "i64.sub") {
             if (e.list.size() != 3) throw std::invalid_argument("wat: " + h + " takes two folded operands");
-            const value a = eval(e.list[1], cs, st);
-            const value b = eval(e.list[2], cs, st);
-            return binop(h, a, b, cs, st);
+            value a = eval(e.list[1], m, st);
+            value b = eval(e.list[2], m, st);
+            return binop(h, std::move(a), std::move(b), m, st);
         }
         if (h == "call") {
             if (e.list.size() < 2) throw std::invalid_argument("wat: call without a target");
             const auto it = imports_.find(e.list[1].atom);
             if (it == imports_.end()) throw std::invalid_argument("wat: call of a non-imported function is not supported (" + e.list[1].atom + ")");
             std::vector<value> args;
-            for (size_t i = 2; i < e.list.size(); i++) args.push_back(eval(e.list[i], cs, st));
+            for (size_t i = 2; i < e.list.size(); i++) args.push_back(eval(e.list[i], m, st));
             if (it->second == "i64_private_const") {
-                if (args.size() != 1 || args[0].witness) throw std::invalid_argument("wat: i64_private_const takes one constant");
-                return private_const(args[0].v, cs, st);
+                if (args.size() != 1 || args[0].bits) throw std::invalid_argument("wat: i64_private_const takes one constant");
+                return private_const(args[0].v, m, st);
             }
-            if (it->second == "assert_equal") {
+            if (it->second == "assert_equal") {                                // env.hpp:64-77
                 if (args.size() != 2) throw std::invalid_argument("wat: assert_equal takes two operands");
                 st.asserts++;
-                const value a = promote(args[0], cs), b = promote(args[1], cs);   // make_witness on both sides (env.hpp:68-69)
-                cs.equal(a.slot, b.slot);
+                const wid wx = make_witness(args[0], m, st), wy = make_witness(args[1], m, st);
+                m.equal(wx, wy);
+                m.release(wy); m.release(wx);
+                drop(args[0], m); drop(args[1], m);
                 return value{};
             }
             throw std::invalid_argument("wat: env." + it->second + " is not supported by the bounded front end");

@@ -27,6 +27,9 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "refctx_cpu")
 # masks); its last three assertions at k = 256 (l = 64: 17 row events, so rows of both kinds interleave); the vbn254fr
 # batch calls at k = 256 (271 events: init / equal / quadratic / bit rows between scalar rows)
 CASES = [("i64_mul", 8192), ("i64_mul3", 256), ("vbn", 256)]
+# programs given as text: the repo's own tests/golden/mul64.wat (products, sums, differences, nested forms, literal
+# operands) goes through the reference's interpreter as a token stream (tests/refctx_util.py: wat_to_tokens)
+WAT_CASES = [("mul64", os.path.join(HERE, "mul64.wat"), 256)]
 
 
 def zb64(hexstr):
@@ -50,19 +53,29 @@ def compact(raw):
     return out
 
 
+def write(name, k, raw):
+    assert raw["valid"] == [1, 1, 1], "the reference's self-check must pass on an honest run"
+    path = os.path.join(HERE, "refctx_%s_k%d.json" % (name, k))
+    with open(path, "w") as f:
+        json.dump(compact(raw), f, separators=(",", ":"))
+        f.write("\n")
+    print(path, os.path.getsize(path), "bytes")
+
+
 def main():
     if not os.path.exists(BIN):
         sys.exit("build it first: make -C oracle refctx (needs /root/reference)")
+    sys.path.insert(0, os.path.dirname(HERE))
+    import refctx_util
+    for name, wat, k in WAT_CASES:
+        raw = refctx_util.run_reference_on_wat(open(wat).read(), k)
+        raw["program"] = name
+        write(name, k, raw)
     for prog, k in CASES:
         with tempfile.NamedTemporaryFile(suffix=".json") as tmp:
             subprocess.check_call([BIN, prog, str(k), tmp.name])
             raw = json.load(open(tmp.name))
-        assert raw["valid"] == [1, 1, 1], "the reference's self-check must pass on an honest run"
-        path = os.path.join(HERE, "refctx_%s_k%d.json" % (prog, k))
-        with open(path, "w") as f:
-            json.dump(compact(raw), f, separators=(",", ":"))
-            f.write("\n")
-        print(path, os.path.getsize(path), "bytes")
+        write(prog, k, raw)
 
 
 if __name__ == "__main__":

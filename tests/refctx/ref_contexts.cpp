@@ -111,24 +111,32 @@ struct tiny_module {
     }
 };
 
-// What transpile() (include/transpiler.hpp:741-776) emits for the folded text
-//   (call $assert_equal (i64.OP (call $pc (i64.const a)) (call $pc (i64.const b))) (call $pc (i64.const c)))
-// : runs of plain opcodes become basic blocks, calls stand alone.
-static void emit_assert_binop(std::vector<instr_ptr> &body, size_t &bb_id, opcode::kind op, uint64_t a, uint64_t b, uint64_t c) {
-    auto block = [&](std::vector<opcode> ops) {
-        auto bb = std::make_unique<basic_block>();
-        bb->id = bb_id++;
-        bb->body = std::move(ops);
-        body.push_back(std::move(bb));
+// A program of the arithmetic-test subset as the flat instruction stream its folded text denotes (operands first):
+//   c <u64>  i64.const      pc  call $i64_private_const      eq  call $assert_equal      mul | add | sub  i64.mul / add / sub
+// assembled the way transpile() (include/transpiler.hpp:741-776) would: runs of plain opcodes become basic blocks, calls
+// stand alone.
+struct wasm_token { std::string op; uint64_t imm = 0; };
+
+static std::vector<instr_ptr> assemble(const std::vector<wasm_token> &toks) {
+    std::vector<instr_ptr> body;
+    std::unique_ptr<basic_block> bb;
+    size_t bb_id = 0;
+    auto flush = [&] { if (bb) body.push_back(std::move(bb)); };
+    auto plain = [&](opcode o) {
+        if (!bb) { bb = std::make_unique<basic_block>(); bb->id = bb_id++; }
+        bb->body.push_back(o);
     };
-    auto i64c = [](uint64_t v) { return opcode(opcode::inn_const, value_kind::i64, v); };
-    block({i64c(a)});
-    body.push_back(make_instr<call>(0));
-    block({i64c(b)});
-    body.push_back(make_instr<call>(0));
-    block({opcode(op, value_kind::i64), i64c(c)});
-    body.push_back(make_instr<call>(0));
-    body.push_back(make_instr<call>(1));
+    for (const wasm_token &t : toks) {
+        if (t.op == "c") plain(opcode(opcode::inn_const, value_kind::i64, t.imm));
+        else if (t.op == "mul") plain(opcode(opcode::inn_mul, value_kind::i64));
+        else if (t.op == "add") plain(opcode(opcode::inn_add, value_kind::i64));
+        else if (t.op == "sub") plain(opcode(opcode::inn_sub, value_kind::i64));
+        else if (t.op == "pc") { flush(); body.push_back(make_instr<call>(0)); }
+        else if (t.op == "eq") { flush(); body.push_back(make_instr<call>(1)); }
+        else throw std::runtime_error("unknown token " + t.op);
+    }
+    flush();
+    return body;
 }
 
 struct binop_case { uint64_t a, b, c; };
@@ -146,12 +154,35 @@ static const binop_case kI64Mul[] = {
     {0x7fffffffffffffffULL, 0x7fffffffffffffffULL, 1},
 };
 
+// (call $assert_equal (i64.OP (call $pc (i64.const a)) (call $pc (i64.const b))) (call $pc (i64.const c)))
+static std::vector<wasm_token> binop_tokens(const char *op, const binop_case *cases, size_t ncases) {
+    std::vector<wasm_token> t;
+    for (size_t i = 0; i < ncases; i++) {
+        t.push_back({"c", cases[i].a}); t.push_back({"pc"});
+        t.push_back({"c", cases[i].b}); t.push_back({"pc"});
+        t.push_back({op});
+        t.push_back({"c", cases[i].c}); t.push_back({"pc"});
+        t.push_back({"eq"});
+    }
+    return t;
+}
+
+static std::vector<wasm_token> read_tokens(const std::string &path) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("cannot read " + path);
+    std::vector<wasm_token> t;
+    std::string op;
+    while (in >> op) {
+        wasm_token tok{op};
+        if (op == "c") { std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0); }
+        t.push_back(tok);
+    }
+    return t;
+}
+
 template <typename Ctx>
-static void run_wasm_binops(Ctx &ctx, opcode::kind op, const binop_case *cases, size_t ncases) {
-    std::vector<instr_ptr> body;
-    size_t bb_id = 0;
-    for (size_t i = 0; i < ncases; i++) emit_assert_binop(body, bb_id, op, cases[i].a, cases[i].b, cases[i].c);
-    tiny_module m(std::move(body));
+static void run_wasm_tokens(Ctx &ctx, const std::vector<wasm_token> &toks) {
+    tiny_module m(assemble(toks));
     wasm_interpreter<Ctx> interp(ctx);
     ctx.store(&m.store);
     ctx.module(&m.inst);
@@ -288,8 +319,9 @@ static void run_vbn_program(Ctx &ctx, run_log *log, uint32_t l, uint32_t k) {
 
 template <typename Ctx>
 static void run_named(const std::string &prog, Ctx &ctx, run_log *log, uint32_t l, uint32_t k) {
-    if (prog == "i64_mul") run_wasm_binops(ctx, opcode::inn_mul, kI64Mul, std::size(kI64Mul));
-    else if (prog == "i64_mul3") run_wasm_binops(ctx, opcode::inn_mul, kI64Mul + 6, 3);
+    if (prog == "i64_mul") run_wasm_tokens(ctx, binop_tokens("mul", kI64Mul, std::size(kI64Mul)));
+    else if (prog == "i64_mul3") run_wasm_tokens(ctx, binop_tokens("mul", kI64Mul + 6, 3));
+    else if (prog.rfind("ops:", 0) == 0) run_wasm_tokens(ctx, read_tokens(prog.substr(4)));   // any program of the subset, as tokens
     else if (prog == "vbn") run_vbn_program(ctx, log, l, k);
     else throw std::runtime_error("unknown program " + prog);
 }
@@ -401,7 +433,7 @@ int main(int argc, char **argv) {
 
     std::ofstream out(argv[3]);
     out << "{\n";
-    out << "\"program\": \"" << prog << "\", \"executor\": \"" << kExecutorName << "\", \"l\": " << l << ", \"k\": " << k << ", \"n\": " << n << ",\n";
+    out << "\"program\": \"" << (prog.rfind("ops:", 0) == 0 ? std::string("ops") : prog) << "\", \"executor\": \"" << kExecutorName << "\", \"l\": " << l << ", \"k\": " << k << ", \"n\": " << n << ",\n";
     out << "\"encoding_seed\": \"" << hex(encoding_random_seed, 32) << "\", \"instance_hash\": \"" << hex(instance_hash.data, 32) << "\",\n";
     out << "\"kinds\": [";
     for (size_t i = 0; i < log1.kinds.size(); i++) out << (i ? "," : "") << log1.kinds[i];

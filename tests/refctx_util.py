@@ -11,7 +11,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-CASES = ["i64_mul_k8192", "i64_mul3_k256", "vbn_k256"]
+CASES = ["i64_mul_k8192", "i64_mul3_k256", "vbn_k256", "mul64_k256"]
+WAT_TEXT = {"mul64": os.path.join(HERE, "golden", "mul64.wat")}          # cases whose program is a .wat file of the repo
 REF_BIN_CPU = os.path.join(ROOT, "oracle", "_ref", "refctx_cpu")
 REF_BIN_CUDA = os.path.join(ROOT, "oracle", "_ref", "refctx_cuda")
 
@@ -63,3 +64,93 @@ def check_envelope(env, fx, sibling_positions):
     assert sorted(pos) == fx["decommit_positions"]
     by_pos = dict(zip(pos, [s.value for s in pf.merkle_tree.sibling_hashes]))
     assert sha(np.frombuffer(b"".join(by_pos[p] for p in fx["decommit_positions"]), np.uint8)) == fx["sha256"]["decommit_siblings"]
+
+
+# ---- folded WAT of the arithmetic-test subset -> the flat token stream tests/refctx/ref_contexts.cpp assembles ("ops:" programs)
+def _sexpr(text):
+    import re
+    text = re.sub(r"\(;.*?;\)", " ", text, flags=re.S)
+    text = re.sub(r";;[^\n]*", " ", text)
+    toks = re.findall(r'"[^"]*"|[()]|[^\s()]+', text)
+    pos = 0
+
+    def parse():
+        nonlocal pos
+        t = toks[pos]; pos += 1
+        if t != "(":
+            return t
+        out = []
+        while toks[pos] != ")":
+            out.append(parse())
+        pos += 1
+        return out
+    return parse()
+
+
+def wat_to_tokens(text):
+    """'c <u64>' / pc / eq / mul / add / sub, operands first -- what the folded text of the exported function denotes"""
+    mod = _sexpr(text)
+    imports = {f[3][1]: f[2].strip('"') for f in mod[1:] if f[0] == "import"}
+    start = next(f[2][1] for f in mod[1:] if f[0] == "export" and f[1] == '"_start"')
+    func = next(f for f in mod[1:] if f[0] == "func" and f[1] == start)
+    out = []
+
+    def lit(s):
+        s = s.replace("_", "")
+        v = int(s, 0)
+        return v % (1 << 64)
+
+    def emit(e):
+        if e[0] == "i64.const":
+            out.append("c %d" % lit(e[1]))
+        elif e[0] in ("i64.mul", "i64.add", "i64.sub"):
+            emit(e[1]); emit(e[2]); out.append(e[0][4:])
+        elif e[0] == "call":
+            for a in e[2:]:
+                emit(a)
+            out.append({"i64_private_const": "pc", "assert_equal": "eq"}[imports[e[1]]])
+        else:
+            raise ValueError("unsupported form " + str(e[0]))
+    for e in func[2:]:
+        if isinstance(e, list) and e[0] not in ("param", "result", "local", "type"):
+            emit(e)
+    return out
+
+
+def run_reference_on_wat(text, k, seed_byte=7):
+    """the reference's interpreter / backend / stage contexts over the CPU oracle on a program of the subset -> raw dict"""
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        ops = os.path.join(tmp, "prog.ops")
+        with open(ops, "w") as f:
+            f.write("\n".join(wat_to_tokens(text)) + "\n")
+        out = os.path.join(tmp, "out.json")
+        subprocess.check_call([REF_BIN_CPU, "ops:" + ops, str(k), out, str(seed_byte)], stdout=subprocess.DEVNULL)
+        return json.load(open(out))
+
+
+def harness_args(case, tmpdir):
+    """(program argument, k) for oracle/_ref/refctx_{cpu,cuda}: built-in programs by name, .wat programs as a token file"""
+    prog, k = case.rsplit("_k", 1)
+    if prog in WAT_TEXT:
+        ops = os.path.join(tmpdir, prog + ".ops")
+        with open(ops, "w") as f:
+            f.write("\n".join(wat_to_tokens(open(WAT_TEXT[prog]).read())) + "\n")
+        return "ops:" + ops, k, prog
+    return prog, k, prog
+
+
+# tests/i64_mul.wat of the reference (BASELINE config 4): the nine (a, b, a*b mod 2^64) cases of its single function,
+# so that the program can be written out where /root/reference is absent
+I64_MUL_CASES = [(1, 1, 1), (1, 0, 0), (2**64 - 1, 2**64 - 1, 1), (0x1000000000000000, 4096, 0), (0x8000000000000000, 0, 0),
+                 (0x8000000000000000, 2**64 - 1, 0x8000000000000000), (0x7fffffffffffffff, 2**64 - 1, 0x8000000000000001),
+                 (0x0123456789abcdef, 0xfedcba9876543210, 0x2236d88fe5618cf0), (0x7fffffffffffffff, 0x7fffffffffffffff, 1)]
+WAT_HEAD = ('(module (import "env" "i64_private_const" (func $i64_private_const (param i64) (result i64)))\n'
+            '(import "env" "assert_equal" (func $assert_equal (param i64 i64)))\n(func $t\n')
+WAT_TAIL = ')\n(export "_start" (func $t)))\n'
+
+
+def binop_wat(op, cases):
+    pc = lambda v: "(call $i64_private_const (i64.const %d))" % v
+    return WAT_HEAD + "".join("(call $assert_equal (i64.%s %s %s) %s)\n" % (op, pc(a), pc(b), pc(c)) for a, b, c in cases) + WAT_TAIL

@@ -62,18 +62,87 @@ def test_i64_mul_row_counts_at_the_default_geometry():
 
 
 @pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("case", ["i64_mul3_k256", "vbn_k256"])
+@pytest.mark.parametrize("case", ["i64_mul3_k256", "vbn_k256", "mul64_k256"])
 def test_harness_regenerates_the_committed_vectors(oracle, case):
     """the committed JSON is exactly what the harness writes today (same reference sources, same oracle)"""
     gen = U.compact_module()
-    prog, k = case.rsplit("_k", 1)
     with tempfile.TemporaryDirectory() as tmp:
+        prog, k, name = U.harness_args(case, tmp)
         path = os.path.join(tmp, "out.json")
         subprocess.check_call([U.REF_BIN_CPU, prog, k, path], stdout=subprocess.DEVNULL)
-        got = gen.compact(json.load(open(path)))
+        raw = json.load(open(path))
+        raw["program"] = name
+        got = gen.compact(raw)
     want = U.load(case)["fx"]
     for key in want:
         assert got[key] == want[key], key
+
+
+# ---------------------------------------------------------------- the .wat front end against the reference's interpreter
+@pytest.fixture(scope="module")
+def pr(lgr):
+    import importlib
+    return importlib.import_module("ligero_prover_b200.prover")
+
+
+def _emitter_equals_reference_rows(pr, text, st):
+    fx = st["fx"]
+    kinds, vals, coefs, const_sum, stats = pr.wat_emit(text, st["l"], bytes.fromhex(fx["stage1_seed"]))
+    assert list(kinds) == list(st["kinds"])
+    assert np.array_equal(vals, st["values"]), "rows differ from what the reference's interpreter + witness manager emit"
+    assert np.array_equal(coefs, st["coefs"]), "linear-test coefficient rows differ from the reference's"
+    assert const_sum == st["const_sum"]
+    assert stats["violated_constraints"] == 0
+    return stats
+
+
+def test_wat_emitter_reproduces_the_reference_rows_for_i64_mul(pr):
+    """BASELINE config 4: tests/i64_mul.wat at the default geometry.  The rows and the stage-2 coefficient rows that
+    lgrp_wat_emit / lgrp_prove_wat feed the prover are, element for element, the ones the reference's own interpreter, env
+    module, backend and witness manager hand to its stage contexts (tests/golden/refctx_i64_mul_k8192.json)"""
+    st = U.load("i64_mul_k8192")
+    path = os.path.join(REFERENCE, "tests", "i64_mul.wat")
+    text = open(path).read() if os.path.exists(path) else U.binop_wat("mul", U.I64_MUL_CASES)
+    stats = _emitter_equals_reference_rows(pr, text, st)
+    assert (stats["private_consts"], stats["asserts"], stats["arithmetic_ops"], stats["quadratic_slots"]) == (27, 9, 9, 2889)
+    assert _emitter_equals_reference_rows(pr, U.binop_wat("mul", U.I64_MUL_CASES), st) == stats
+    # the last three assertions at l = 64: 17 row events, rows of both kinds interleaved
+    _emitter_equals_reference_rows(pr, U.binop_wat("mul", U.I64_MUL_CASES[6:]), U.load("i64_mul3_k256"))
+
+
+def test_wat_emitter_reproduces_the_reference_rows_for_the_repo_program(pr):
+    """tests/golden/mul64.wat: products, sums, differences, nested forms and literal operands, 39 row events at l = 64"""
+    st = U.load("mul64_k256")
+    _emitter_equals_reference_rows(pr, open(U.WAT_TEXT["mul64"]).read(), st)
+
+
+def _rand_expr(rng, depth):
+    if depth == 0 or rng.random() < 0.25:
+        v = rng.choice([0, 1, 2, 2**64 - 1, 1 << 63, (1 << 63) - 1, 1 << 32, rng.getrandbits(64), rng.getrandbits(20)])
+        return ("(call $i64_private_const (i64.const %d))" if rng.random() < 0.7 else "(i64.const %d)") % v, v
+    op = rng.choice(["mul", "add", "sub"])
+    (ta, va), (tb, vb) = _rand_expr(rng, depth - 1), _rand_expr(rng, depth - 1)
+    return "(i64.%s %s %s)" % (op, ta, tb), {"mul": va * vb, "add": va + vb, "sub": va - vb}[op] % 2**64
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("seed", range(4))
+def test_wat_emitter_against_the_reference_interpreter_on_random_programs(oracle, pr, seed):
+    """differential: random expression trees (private and literal operands, nested mul / add / sub) run through the
+    reference's interpreter + backend (oracle/_ref/refctx_cpu) and through the emitter give the same rows"""
+    import random
+    rng = random.Random(4200 + seed)
+    exprs = [_rand_expr(rng, rng.randrange(1, 4)) for _ in range(4)]
+    text = U.WAT_HEAD + "".join("(call $assert_equal %s %s)\n" % (t, ("(i64.const %d)" if rng.random() < 0.5 else "(call $i64_private_const (i64.const %d))") % v)
+                                for t, v in exprs) + U.WAT_TAIL
+    k = rng.choice([256, 512])
+    raw = U.run_reference_on_wat(text, k, seed_byte=seed + 1)
+    assert raw["valid"] == [1, 1, 1]
+    l = raw["l"]
+    u32 = lambda h: np.frombuffer(bytes.fromhex(h), np.uint32)
+    st = {"fx": raw, "l": l, "kinds": raw["kinds"], "values": u32(raw["values"]).reshape(-1, l, 8), "coefs": u32(raw["coefs"]).reshape(-1, l, 8),
+          "const_sum": int.from_bytes(bytes.fromhex(raw["const_sum"]), "little")}
+    _emitter_equals_reference_rows(pr, text, st)
 
 
 BOUNDARY_TU = r"""

@@ -47,15 +47,32 @@ def test_reference_stage_contexts_run_on_the_cuda_executor(case):
     """the drop-in boundary, run: the reference's unchanged stage-1/2/3 contexts, witness manager, interpreter and vbn254fr
     module, with liblgr.so behind `webgpu_context`, give the vectors they give over the CPU oracle"""
     gen = U.compact_module()
-    prog, k = case.rsplit("_k", 1)
     with tempfile.TemporaryDirectory() as tmp:
+        prog, k, name = U.harness_args(case, tmp)
         path = os.path.join(tmp, "out.json")
         res = subprocess.run([U.REF_BIN_CUDA, prog, k, path], capture_output=True, text=True, timeout=600)
         assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
         raw = json.load(open(path))
     assert raw["executor"] == "cuda"
+    raw["program"] = name
     got = gen.compact(raw)
     want = U.load(case)["fx"]
     for key in want:
         if key != "generated_by":
             assert got[key] == want[key], key
+
+
+@pytest.mark.parametrize("case,wat", [("i64_mul_k8192", None), ("mul64_k256", "mul64")])
+def test_prove_wat_commits_to_the_root_of_the_reference_run(lgr, pr, executor_factory, case, wat):
+    """BASELINE config 4 through the product's entry point: lgrp_prove_wat on the text of tests/i64_mul.wat, with the
+    encoding seed of the reference run, arrives at the Merkle root the reference's own interpreter + stage-1 context
+    arrive at (the root depends on every committed row and pad, not on the instance hash, which the two runs choose
+    differently)"""
+    st = U.load(case)
+    text = open(U.WAT_TEXT[wat]).read() if wat else U.binop_wat("mul", U.I64_MUL_CASES)
+    ex = executor_factory(st["k"], st["l"])
+    proof, stats = pr.prove_wat(ex, text, st["encoding_seed"], generated_at=3)
+    assert stats["violated_constraints"] == 0 and proof.info()["valid"] == (True, True, True)
+    env = ref.parse_envelope(proof.gzip)
+    assert env.ligero_proof.merkle_tree.root.value.hex() == st["fx"]["root"]
+    proof.close()
