@@ -27,7 +27,7 @@ def build(force=False):
         return _SO if available() else None
     srcs = [os.path.join(_HERE, f) for f in ("wgsl2cpp.py", "wgslref.cpp", "wgsl_shim.hpp", "Makefile")]
     if force or not available() or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REF={REF_ROOT}"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", "_ref/libwgslref.so", f"REF={REF_ROOT}"])
     return _SO
 
 

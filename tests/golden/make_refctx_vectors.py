@@ -42,7 +42,7 @@ def sha(hexstr):
 
 def compact(raw):
     out = {key: raw[key] for key in ("program", "l", "k", "n", "encoding_seed", "instance_hash", "kinds", "const_sum", "root", "stage1_seed",
-                                     "stage2_seed", "valid", "sample_index", "decommit_total")}
+                                     "stage2_seed", "valid", "verifier", "sample_index", "decommit_total")}
     out["generated_by"] = "tests/golden/make_refctx_vectors.py <- oracle/_ref/refctx_cpu (reference headers + CPU oracle executor)"
     for key in ("values", "coefs", "batch_args", "batch_consts"):
         out[key + "_zb64"] = zb64(raw[key])
@@ -55,6 +55,7 @@ def compact(raw):
 
 def write(name, k, raw):
     assert raw["valid"] == [1, 1, 1], "the reference's self-check must pass on an honest run"
+    assert raw["verifier"] == [1] * 7, "the reference's verifier must accept the proof of its own prover passes"
     path = os.path.join(HERE, "refctx_%s_k%d.json" % (name, k))
     with open(path, "w") as f:
         json.dump(compact(raw), f, separators=(",", ":"))

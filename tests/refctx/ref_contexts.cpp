@@ -335,9 +335,126 @@ static std::string hex(const void *p, size_t n) {
 }
 template <typename T> static std::string hexv(const std::vector<T> &v) { return hex(v.data(), v.size() * sizeof(T)); }
 
+// ---------------------------------------------------------------------------------------------------------------
+// the reference's verifier (src/webgpu_verifier.cpp:262-449) around its own nonbatch_verifier_context
+using verifier_t = zkp::nonbatch_verifier_context<field_t, executor_t, zkp::verifier_random_policy, params::hasher>;
+
+struct proof_fields {
+    params::hasher::digest root;
+    std::vector<uint32_t> code, linear, quad, samplings;
+    std::vector<std::pair<size_t, params::hasher::digest>> siblings;      // tree position -> digest
+    size_t total_count = 0;
+};
+
+struct verdict { bool merkle, code, linear, quad, code_eq, linear_eq, quad_eq; bool all() const { return merkle && code && linear && quad && code_eq && linear_eq && quad_eq; } };
+
+static verdict verify(const std::string &prog, executor_t &executor, size_t l, size_t k, size_t n, const params::hasher::digest &instance_hash,
+                      const proof_fields &pf) {
+    auto stage1_seed = zkp::hash<params::hasher>("LigetronStage1", pf.root, instance_hash);
+    auto sample_seed = zkp::hash<params::hasher>("LigetronStage2", pf.root, pf.code, pf.linear, pf.quad);
+    unsigned char seed[params::hasher::digest_size];
+    std::memcpy(seed, stage1_seed.data, params::hasher::digest_size);
+    cuda::host::digest s2;
+    std::memcpy(s2.data, sample_seed.data, 32);
+    std::vector<uint64_t> sample64 = cuda::host::sample_indices(s2, n, params::sample_size);       // (Boost-free sampler, see main)
+    std::vector<size_t> sample_index(sample64.begin(), sample64.end());
+
+    zkp::merkle_tree<params::hasher>::decommitment decommit(pf.total_count, sample_index);
+    for (const auto &sb : pf.siblings) decommit.insert(sb.first, sb.second);
+
+    auto vctx = std::make_unique<verifier_t>(executor, sample_index, pf.samplings);
+    vctx->init_witness_random(seed, params::any_iv);
+    run_log unused;
+    unused.l = l;
+    run_named(prog, *vctx, nullptr, l, k);
+    auto vs1_root = zkp::merkle_tree<params::hasher>::recommit(vctx->flush_digests(), decommit);
+
+    auto linear_sums = vctx->linear_sums();
+    mpz_vector vsample_code, vsample_linear, vsample_quad;
+    auto vc = executor.template copy_to_host<uint32_t>(vctx->code());
+    auto vl = executor.template copy_to_host<uint32_t>(vctx->linear());
+    auto vq = executor.template copy_to_host<uint32_t>(vctx->quadratic());
+    vsample_code.import_limbs(vc.data(), vc.size(), sizeof(uint32_t), field_t::num_u32_limbs);
+    vsample_linear.import_limbs(vl.data(), vl.size(), sizeof(uint32_t), field_t::num_u32_limbs);
+    vsample_quad.import_limbs(vq.data(), vq.size(), sizeof(uint32_t), field_t::num_u32_limbs);
+
+    buffer_t device_code = executor.make_codeword_buffer(), device_linear = executor.make_codeword_buffer(), device_quad = executor.make_codeword_buffer();
+    executor.write_buffer(device_code, pf.code.data(), pf.code.size());
+    executor.write_buffer(device_linear, pf.linear.data(), pf.linear.size());
+    executor.write_buffer(device_quad, pf.quad.data(), pf.quad.size());
+    executor.decode_ntt_device(executor.bind_ntt(device_code));
+    executor.decode_ntt_device(executor.bind_ntt(device_linear));
+    executor.decode_ntt_device(executor.bind_ntt(device_quad));
+    mpz_vector prover_code, prover_linear, prover_quad, enc_code, enc_linear, enc_quad;
+    { auto limbs = executor.template copy_to_host<uint32_t>(device_code); prover_code.import_limbs(limbs.data(), limbs.size(), sizeof(uint32_t), field_t::num_u32_limbs); }
+    { auto limbs = executor.template copy_to_host<uint32_t>(device_linear); prover_linear.import_limbs(limbs.data(), limbs.size(), sizeof(uint32_t), field_t::num_u32_limbs); prover_linear.resize(l); }
+    { auto limbs = executor.template copy_to_host<uint32_t>(device_quad); prover_quad.import_limbs(limbs.data(), limbs.size(), sizeof(uint32_t), field_t::num_u32_limbs); prover_quad.resize(l); }
+    enc_code.import_limbs(pf.code.data(), pf.code.size(), sizeof(uint32_t), field_t::num_u32_limbs);
+    enc_linear.import_limbs(pf.linear.data(), pf.linear.size(), sizeof(uint32_t), field_t::num_u32_limbs);
+    enc_quad.import_limbs(pf.quad.data(), pf.quad.size(), sizeof(uint32_t), field_t::num_u32_limbs);
+
+    verdict v;
+    v.merkle = pf.root == vs1_root;
+    v.code = std::all_of(prover_code.begin() + k, prover_code.end(), [](const auto &x) { return x == 0; });
+    v.linear = zkp::validate_sum<field_t>(prover_linear, linear_sums);
+    v.quad = zkp::validate(prover_quad);
+    v.code_eq = v.linear_eq = v.quad_eq = true;
+    for (size_t i = 0; i < params::sample_size; i++) {
+        v.code_eq &= enc_code[sample_index[i]] == vsample_code[i];
+        v.linear_eq &= enc_linear[sample_index[i]] == vsample_linear[i];
+        v.quad_eq &= enc_quad[sample_index[i]] == vsample_quad[i];
+    }
+    return v;
+}
+
+static std::vector<unsigned char> unhex(const std::string &h) {
+    std::vector<unsigned char> out(h.size() / 2);
+    auto nib = [](char c) { return (unsigned)(c <= '9' ? c - '0' : (c | 32) - 'a' + 10); };
+    for (size_t i = 0; i < out.size(); i++) out[i] = (unsigned char)(nib(h[2 * i]) << 4 | nib(h[2 * i + 1]));
+    return out;
+}
+template <typename T> static std::vector<T> unhex_as(const std::string &h) {
+    std::vector<unsigned char> b = unhex(h);
+    std::vector<T> v(b.size() / sizeof(T));
+    std::memcpy(v.data(), b.data(), v.size() * sizeof(T));
+    return v;
+}
+
+// a proof handed in from outside (e.g. the envelope of lgrp_prove): lines of `key hex...`
+static proof_fields read_proof(const std::string &path, params::hasher::digest &instance_hash) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("cannot read " + path);
+    proof_fields pf;
+    std::string key;
+    while (in >> key) {
+        if (key == "total") { in >> pf.total_count; continue; }
+        if (key == "sibling") {
+            size_t pos; std::string h; in >> pos >> h;
+            params::hasher::digest d; auto b = unhex(h); std::memcpy(d.data, b.data(), 32);
+            pf.siblings.emplace_back(pos, d);
+            continue;
+        }
+        std::string h; in >> h;
+        if (key == "root") { auto b = unhex(h); std::memcpy(pf.root.data, b.data(), 32); }
+        else if (key == "instance") { auto b = unhex(h); std::memcpy(instance_hash.data, b.data(), 32); }
+        else if (key == "code") pf.code = unhex_as<uint32_t>(h);
+        else if (key == "linear") pf.linear = unhex_as<uint32_t>(h);
+        else if (key == "quad") pf.quad = unhex_as<uint32_t>(h);
+        else if (key == "samplings") pf.samplings = unhex_as<uint32_t>(h);
+        else throw std::runtime_error("unknown key " + key);
+    }
+    return pf;
+}
+
 int main(int argc, char **argv) {
-    if (argc < 4) { std::fprintf(stderr, "usage: %s <program> <k> <out.json> [seed byte]\n", argv[0]); return 2; }
-    const std::string prog = argv[1];
+    if (argc < 4) {
+        std::fprintf(stderr, "usage: %s <program> <k> <out.json> [seed byte]\n       %s verify:<proof file> <program> <k>\n", argv[0], argv[0]);
+        return 2;
+    }
+    const bool verify_only = std::string(argv[1]).rfind("verify:", 0) == 0;
+    const std::string proof_path = verify_only ? std::string(argv[1]).substr(7) : std::string();
+    const std::string prog = verify_only ? argv[2] : argv[1];
+    if (verify_only) { argv[2] = argv[3]; argc = 4; }
     const size_t k = std::stoul(argv[2]), l = k - params::sample_size, n = 4 * k;
     const unsigned seed_byte = argc > 4 ? std::stoul(argv[4]) : 7;
     std::streambuf *chatter = std::cout.rdbuf();                 // the reference prints statistics on stdout; keep them off the JSON
@@ -353,6 +470,23 @@ int main(int argc, char **argv) {
     for (int i = 0; i < 32; i++) encoding_random_seed[i] = (unsigned char)(seed_byte * 31 + i * 7 + 1);
     params::hasher::digest instance_hash;                         // no public arguments: hash of nothing, as a fixed 32-byte string here
     for (size_t i = 0; i < params::hasher::digest_size; i++) instance_hash.data[i] = (unsigned char)(0xA0 + i);
+
+    if (verify_only) {
+        // the reference's VERIFIER on somebody else's proof of the same program: accept = exit code 0
+        proof_fields pf = read_proof(proof_path, instance_hash);
+        verdict v{};
+        try {
+            v = verify(prog, executor, l, k, n, instance_hash, pf);
+        } catch (const std::exception &e) {                       // e.g. openings that do not belong to the re-derived sample positions
+            std::cout.rdbuf(chatter);
+            std::printf("verifier on %s: rejected (%s)\n", kExecutorName, e.what());
+            return 1;
+        }
+        std::cout.rdbuf(chatter);
+        std::printf("verifier on %s: merkle %d code %d linear %d quad %d code_eq %d linear_eq %d quad_eq %d\n", kExecutorName, v.merkle, v.code, v.linear,
+                    v.quad, v.code_eq, v.linear_eq, v.quad_eq);
+        return v.all() ? 0 : 1;
+    }
 
     run_log log1, log2, log3;
     log1.l = log2.l = log3.l = l;
@@ -425,6 +559,13 @@ int main(int argc, char **argv) {
     if (log1.kinds != log2.kinds || log1.kinds != log3.kinds || log1.rows != log3.rows || log1.batch_args != log2.batch_args)
         throw std::runtime_error("the three passes did not see the same rows");
 
+    // and the reference's verifier on the proof the three passes made
+    proof_fields pf;
+    pf.root = stage1_root; pf.code = code_limbs; pf.linear = linear_limbs; pf.quad = quad_limbs; pf.samplings = samplings;
+    pf.total_count = decommit.size();
+    pf.siblings.assign(decommit.nodes().begin(), decommit.nodes().end());
+    const verdict vd = verify(prog, executor, l, k, n, instance_hash, pf);
+
     std::cout.rdbuf(chatter);
     uint32_t const_sum[8] = {0};
     mpz_export(const_sum, nullptr, -1, sizeof(uint32_t), 0, 0, linear_sum.get_mpz_t());
@@ -446,6 +587,7 @@ int main(int argc, char **argv) {
     out << "\"root\": \"" << hex(stage1_root.data, 32) << "\", \"stage1_seed\": \"" << hex(stage1_seed.data, 32) << "\", \"stage2_seed\": \"" << hex(stage2_seed.data, 32) << "\",\n";
     out << "\"code\": \"" << hexv(code_limbs) << "\",\n\"linear\": \"" << hexv(linear_limbs) << "\",\n\"quad\": \"" << hexv(quad_limbs) << "\",\n";
     out << "\"valid\": [" << valid_code << "," << valid_linear << "," << valid_quad << "],\n";
+    out << "\"verifier\": [" << vd.merkle << "," << vd.code << "," << vd.linear << "," << vd.quad << "," << vd.code_eq << "," << vd.linear_eq << "," << vd.quad_eq << "],\n";
     out << "\"sample_index\": [";
     for (size_t i = 0; i < sample_index.size(); i++) out << (i ? "," : "") << sample_index[i];
     out << "],\n\"decommit_total\": " << decommit.size() << ", \"decommit_nodes\": {";
@@ -454,5 +596,5 @@ int main(int argc, char **argv) {
     out.close();
     std::printf("%s k=%zu on %s: %zu events, root %s, valid %d%d%d\n", prog.c_str(), k, kExecutorName, log1.kinds.size(), hex(stage1_root.data, 32).c_str(),
                 (int)valid_code, (int)valid_linear, (int)valid_quad);
-    return (valid_code && valid_linear && valid_quad) ? 0 : 1;
+    return (valid_code && valid_linear && valid_quad && vd.all()) ? 0 : 1;
 }

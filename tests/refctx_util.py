@@ -154,3 +154,31 @@ WAT_TAIL = ')\n(export "_start" (func $t)))\n'
 def binop_wat(op, cases):
     pc = lambda v: "(call $i64_private_const (i64.const %d))" % v
     return WAT_HEAD + "".join("(call $assert_equal (i64.%s %s %s) %s)\n" % (op, pc(a), pc(b), pc(c)) for a, b, c in cases) + WAT_TAIL
+
+
+# ---- the reference's VERIFIER (src/webgpu_verifier.cpp:262-449 around nonbatch_verifier_context) on a proof from outside
+def write_proof_file(path, root, code, linear, quad, samplings, positions, siblings, total_count, instance_hash):
+    """the `key hex` lines tests/refctx/ref_contexts.cpp reads in verify: mode"""
+    hx = lambda a: np.ascontiguousarray(a).tobytes().hex()
+    with open(path, "w") as f:
+        f.write("root %s\ninstance %s\ntotal %d\n" % (bytes(root).hex(), bytes(instance_hash).hex(), total_count))
+        for name, v in (("code", code), ("linear", linear), ("quad", quad), ("samplings", samplings)):
+            f.write("%s %s\n" % (name, hx(np.asarray(v, np.uint32))))
+        for p, s in zip(positions, siblings):
+            f.write("sibling %d %s\n" % (p, bytes(s).hex()))
+
+
+def envelope_to_proof_file(path, env, sibling_positions, total_count, instance_hash):
+    pf = env.ligero_proof
+    leaf = [int(i) for i in pf.merkle_tree.leaf_indices]
+    pos = sibling_positions(leaf, total_count)
+    write_proof_file(path, pf.merkle_tree.root.value, list(pf.encoded_code.values), list(pf.encoded_linear.values), list(pf.encoded_quadratic.values),
+                     list(pf.sampled_data.values), pos, [s.value for s in pf.merkle_tree.sibling_hashes], total_count, instance_hash)
+
+
+def reference_verifier(binary, case, proof_path, tmpdir):
+    """exit code and message of the reference's verifier run on `proof_path` for the program of `case`"""
+    import subprocess
+    prog, k, _ = harness_args(case, tmpdir)
+    res = subprocess.run([binary, "verify:" + proof_path, prog, k], capture_output=True, text=True, timeout=900)
+    return res.returncode, (res.stdout + res.stderr)[-2000:]

@@ -40,6 +40,7 @@ def test_restatement_reproduces_the_reference_run(oracle, case):
     assert U.sha(out["samplings"]) == fx["sha256"]["samplings"]
     assert out["encoded_rows"] == out["samplings"].shape[0]
     assert list(out["valid"]) == [bool(v) for v in fx["valid"]] == [True, True, True]
+    assert fx["verifier"] == [1] * 7            # ... and the reference's verifier accepted that run
     # openings: merkle_tree::decommit of the reference (merkle_tree.hpp:155-215) against the restated level walk
     assert out["total_count"] == fx["decommit_total"]
     assert sorted(out["positions"]) == fx["decommit_positions"]
@@ -49,6 +50,35 @@ def test_restatement_reproduces_the_reference_run(oracle, case):
     meta = {"prover_version": "0", "program_hash": bytes(32), "generated_at": 1, "k": st["k"], "n": st["n"], "sample_size": 192}
     env = ref.build_envelope(meta, out["root"], out["siblings"], out["sample"], out["code"], out["linear"], out["quad"], out["samplings"])
     U.check_envelope(ref.parse_envelope(env), fx, ref.sibling_positions)
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("case", ["i64_mul3_k256", "vbn_k256"])
+def test_reference_verifier_accepts_the_restated_prover_and_rejects_tampering(oracle, case, tmp_path):
+    """the reference's own verifier (nonbatch_verifier_context re-running the program over the sampled columns, recommit,
+    the seven checks of src/webgpu_verifier.cpp:412-442) accepts the proof oracle/prover_ref.py makes -- the proof the
+    GPU prover is held to byte for byte -- and rejects it when one sampled value, one test-vector element or the
+    instance hash is changed"""
+    st = U.load(case)
+    out = ref.prove(st["l"], st["k"], st["kinds"], st["values"], st["coefs"], st["const_sum"], st["encoding_seed"], st["instance_hash"],
+                    arena_slots=st["slots"], batch_args=st["args"], batch_consts=st["consts"])
+
+    def verdict(tag, **change):
+        f = dict(root=out["root"], code=out["code"], linear=out["linear"], quad=out["quad"], samplings=out["samplings"], positions=out["positions"],
+                 siblings=out["siblings"], total_count=out["total_count"], instance_hash=st["instance_hash"])
+        f.update(change)
+        path = str(tmp_path / (tag + ".proof"))
+        U.write_proof_file(path, **f)
+        return U.reference_verifier(U.REF_BIN_CPU, case, path, str(tmp_path))
+
+    rc, msg = verdict("honest")
+    assert rc == 0, msg
+    bad = out["samplings"].copy(); bad[1, 5, 0] ^= 1
+    rc, msg = verdict("sample", samplings=bad)
+    assert rc == 1 and "merkle 0" in msg, msg
+    bad = out["quad"].copy(); bad[3, 0] ^= 1
+    assert verdict("quad", quad=bad)[0] == 1
+    assert verdict("instance", instance_hash=bytes(32))[0] == 1
 
 
 def test_i64_mul_row_counts_at_the_default_geometry():

@@ -76,3 +76,25 @@ def test_prove_wat_commits_to_the_root_of_the_reference_run(lgr, pr, executor_fa
     env = ref.parse_envelope(proof.gzip)
     assert env.ligero_proof.merkle_tree.root.value.hex() == st["fx"]["root"]
     proof.close()
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("case", ["i64_mul_k8192", "vbn_k256", "mul64_k256"])
+def test_reference_verifier_accepts_the_gpu_proof(lgr, pr, executor_factory, case, tmp_path):
+    """the proof lgrp_prove makes on the B200 goes to the REFERENCE's verifier (its nonbatch_verifier_context re-running the
+    program over the opened columns, merkle_tree::recommit, the seven checks of src/webgpu_verifier.cpp:412-442): accepted
+    by the verifier running over the CPU oracle and, where built, by the same verifier running over the CUDA executor"""
+    st = U.load(case)
+    ex = executor_factory(st["k"], st["l"])
+    proof = pr.prove(ex, st["kinds"], st["values"], st["coefs"], st["const_sum"], st["encoding_seed"], st["instance_hash"], generated_at=5,
+                     arena_slots=st["slots"], batch_args=st["args"] if len(st["args"]) else None,
+                     batch_consts=st["consts"] if len(st["consts"]) else None)
+    env = ref.parse_envelope(proof.gzip)
+    proof.close()
+    path = str(tmp_path / "gpu.proof")
+    U.envelope_to_proof_file(path, env, ref.sibling_positions, st["fx"]["decommit_total"], st["instance_hash"])
+    rc, msg = U.reference_verifier(U.REF_BIN_CPU, case, path, str(tmp_path))
+    assert rc == 0, msg
+    if os.path.exists(U.REF_BIN_CUDA):
+        rc, msg = U.reference_verifier(U.REF_BIN_CUDA, case, path, str(tmp_path))
+        assert rc == 0, msg
