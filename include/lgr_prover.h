@@ -119,10 +119,12 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
 /* ---- bounded interpreter boundary (BASELINE config 4) --------------------------------
  * A front end for the folded-WAT subset of the reference's arithmetic tests (tests/i64_mul.wat, i64_add.wat,
  * i64_sub.wat: env.i64_private_const, env.assert_equal, i64.const / mul / add / sub) and the witness emitter behind
- * it (host/wat_emitter.hpp).  It stands where include/invoke.hpp:79-98 + the headers under include/zkp/backend/ stand in the
- * reference; it is not their restatement, and the order in which it releases witnesses is its own (the reference's
- * follows C++ temporaries inside its interpreter: unpinnable without running it).  The proof is a valid Ligero proof of
- * the program's assertions, not a byte-identical copy of the reference's. */
+ * it (host/wat_emitter.hpp).  It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under
+ * include/zkp/backend/ stand in the reference.  It is not a general WASM machine, but for this subset it gives every form
+ * the reference's meaning -- the same witnesses, released in the same order, with the same linear-test randomness -- so
+ * the rows, the stage-2 coefficient rows and const_sum are the reference's, element for element: checked against runs of
+ * the reference's own interpreter / backend / witness manager (tests/refctx/ref_contexts.cpp, tests/golden/refctx_*.json,
+ * tests/test_refctx_cpu.py), on tests/i64_mul.wat at the default geometry and on random programs of the subset. */
 typedef struct {
     uint64_t private_consts, asserts, arithmetic_ops;
     uint64_t linear_witnesses, quadratic_slots, linear_constraints;

@@ -5,9 +5,10 @@
 // 392,586,875), `nonbatch_verifier_context` (:1077), `vbn254fr_module`
 // (include/host_modules/vbn254fr.hpp:33-66) and `main` (src/webgpu_prover.cpp:228-237,316-388) call.
 //
-// Drop-in recipe: `using executor_t = ligero::cuda_context;` in
-// src/webgpu_prover.cpp:54 and `namespace webgpu = ::ligero::cuda;` for the three places where
-// nonbatch_context.hpp spells `webgpu::buffer_binding` instead of `Executor::...` (:578-580,863-871).
+// Drop-in recipe: put host/compat/ before the reference's include/ on the include path.  Its shadows
+// of wgpu.hpp and ligetron/webgpu/buffer_{binding,view}.hpp make `webgpu_context` this class and `webgpu::buffer_binding`
+// (nonbatch_context.hpp:578-580,863-871, vbn254fr.hpp:620) this file's binding, with no edit to the reference's sources.
+// Built and run that way inside the reference's translation unit by tests/refctx/ref_contexts.cpp (oracle/_ref/refctx_cuda).
 //
 // Same names, argument meaning and error behaviour as the reference: operations enqueue and return;
 // copy_to_host and device_synchronize block; init failures throw std::runtime_error
