@@ -98,3 +98,22 @@ def test_reference_verifier_accepts_the_gpu_proof(lgr, pr, executor_factory, cas
     if os.path.exists(U.REF_BIN_CUDA):
         rc, msg = U.reference_verifier(U.REF_BIN_CUDA, case, path, str(tmp_path))
         assert rc == 0, msg
+
+
+@pytest.mark.skipif(not (os.path.exists(U.REF_BIN_CUDA) and os.path.exists(U.REF_BIN_CPU)), reason="oracle/_ref/refctx_{cpu,cuda} not built")
+@pytest.mark.parametrize("prog,k", [("i64_mul3", 512), ("vbn", 1024), ("i64_mul3", 2048), ("i64_mul3", 4096), ("vbn", 8192)])
+def test_reference_contexts_on_cuda_equal_reference_contexts_on_the_oracle(prog, k, tmp_path):
+    """live differential at geometries without a committed fixture: the same reference code (stage contexts, witness
+    manager, interpreter / vbn254fr module, verifier) over the CUDA executor and over the CPU oracle writes the same
+    file -- every row event, the root, the leaf digests, the three test vectors, all openings.  k = 512 ... 2048 run the
+    fused encoder one row at a time, k = 4096 / 8192 the tile engine with deferred one-row encodes"""
+    outs = {}
+    for name, binary in (("oracle", U.REF_BIN_CPU), ("cuda", U.REF_BIN_CUDA)):
+        path = str(tmp_path / (name + ".json"))
+        res = subprocess.run([binary, prog, str(k), path, "11"], capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, (name, (res.stdout + res.stderr)[-3000:])
+        outs[name] = json.load(open(path))
+    assert outs["cuda"].pop("executor") == "cuda" and outs["oracle"].pop("executor") == "oracle"
+    assert outs["cuda"]["verifier"] == [1] * 7
+    for key in outs["oracle"]:
+        assert outs["cuda"][key] == outs["oracle"][key], key
