@@ -118,7 +118,8 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
 
 /* ---- bounded interpreter boundary (BASELINE config 4) --------------------------------
  * A front end for the folded-WAT subset of the reference's arithmetic tests (tests/i64_mul.wat, i64_add.wat,
- * i64_sub.wat: env.i64_private_const, env.assert_equal, i64.const / mul / add / sub) and the witness emitter behind
+ * i64_sub.wat and their i32 twins: env.i64_private_const, env.i32_private_const, env.assert_equal, iNN.const / mul /
+ * add / sub) and the witness emitter behind
  * it (host/wat_emitter.hpp).  It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under
  * include/zkp/backend/ stand in the reference.  It is not a general WASM machine, but for this subset it gives every form
  * the reference's meaning -- the same witnesses, released in the same order, with the same linear-test randomness -- so

@@ -1,6 +1,7 @@
 // Bounded interpreter boundary (BASELINE config 4): a front end for the folded-WAT subset the reference's
-// arithmetic tests use (tests/i64_mul.wat, i64_add.wat, i64_sub.wat: imports env.i64_private_const / env.assert_equal,
-// one exported function of folded i64.const / i64.mul / i64.add / i64.sub / call forms) and the witness emitter behind it.
+// arithmetic tests use (tests/i64_mul.wat, i64_add.wat, i64_sub.wat and their i32 twins: imports env.i64_private_const /
+// env.i32_private_const / env.assert_equal, one exported function of folded iNN.const / iNN.mul / iNN.add / iNN.sub / call
+// forms) and the witness emitter behind it.
 // It is NOT the reference's interpreter (include/interpreter_impl.hpp + include/zkp/backend/*.hpp: a general WASM machine over
 // an expression-template backend, out of scope); it is a small witness machine that gives every form of the subset the
 // meaning the reference gives it -- which witnesses exist, which linear-test randomness lands on them, and WHEN each one is
@@ -296,7 +297,7 @@ public:
 private:
     using wid = witness_machine::wid;
     // a stack value: nothing, a literal, or the bit witnesses of a 64-bit result (decomposed_bits, least significant first)
-    struct value { bool present = false, bits = false; uint64_t v = 0; std::vector<wid> b; };
+    struct value { bool present = false, bits = false; uint64_t v = 0; std::vector<wid> b; };   // v is kept reduced to the value's width
     static std::string unquote(const std::string &s) { return (s.size() >= 2 && s.front() == '"') ? s.substr(1, s.size() - 2) : s; }
     static uint64_t parse_i64(const std::string &t) {
         std::string s;
@@ -339,73 +340,78 @@ private:
         st.linear_witnesses++;
         return a.bits ? m.compose(a.b) : m.acquire(lgr::host::from_u64(a.v));
     }
-    // i64_private_const (env.hpp:178-188): a fresh witness with a 64-bit range check
-    static value private_const(uint64_t v, witness_machine &m, wat_stats &st) {
+    // i32_private_const / i64_private_const (env.hpp:166-188): a fresh witness with a range check of its width
+    static value private_const(uint64_t v, int width, witness_machine &m, wat_stats &st) {
         st.private_consts++;
         st.linear_witnesses++;
-        st.quadratic_slots += 64;
+        st.quadratic_slots += (uint64_t)width;
         const wid x = m.acquire(lgr::host::from_u64(v));
-        std::vector<wid> bits = m.decompose(x, 64);
+        std::vector<wid> bits = m.decompose(x, width);
         m.release(x);
         return decomposed(v, std::move(bits));
     }
 
-    // exec_inn_mul / exec_inn_add / exec_inn_sub on 64-bit operands (interpreter_impl.hpp:262-391)
-    value binop(const std::string &op, value a, value b, witness_machine &m, wat_stats &st) const {
+    // exec_inn_mul / exec_inn_add / exec_inn_sub on operands of `width` = 32 or 64 bits (interpreter_impl.hpp:262-391)
+    value binop(const std::string &op, int width, value a, value b, witness_machine &m, wat_stats &st) const {
         if (!a.present || !b.present) throw std::invalid_argument("wat: " + op + " needs two operands");
+        const uint64_t mask = width == 64 ? ~0ULL : 0xFFFFFFFFULL;
+        const std::string f = op.substr(4);
         if (!a.bits && !b.bits) {
-            return concrete(op == "i64.mul" ? a.v * b.v : (op == "i64.add" ? a.v + b.v : a.v - b.v));
+            return concrete((f == "mul" ? a.v * b.v : (f == "add" ? a.v + b.v : a.v - b.v)) & mask);
         }
         st.arithmetic_ops++;
         const uint64_t av = a.v, bv = b.v;
         const wid x = make_witness(a, m, st), y = make_witness(b, m, st);
-        if (op == "i64.mul") {
+        if (f == "mul") {
             const unsigned __int128 p = (unsigned __int128)av * bv;
             const wid z = m.acquire(Fr{{(uint64_t)p, (uint64_t)(p >> 64), 0, 0}});
             m.quadratic(z, x, y);
-            st.quadratic_slots += 129;
-            std::vector<wid> bits = m.decompose(z, 128);
-            for (int i = 127; i >= 64; i--) m.release(bits[(size_t)i]);      // drop_msb(64)
-            bits.resize(64);
+            st.quadratic_slots += 2 * (uint64_t)width + 1;
+            std::vector<wid> bits = m.decompose(z, 2 * width);
+            for (int i = 2 * width - 1; i >= width; i--) m.release(bits[(size_t)i]);      // drop_msb(width)
+            bits.resize((size_t)width);
             m.release(z); m.release(y); m.release(x);                         // big_result, y, x leave scope in that order,
             drop(a, m); drop(b, m);                                           // then the popped operands: sx (declared last), sy
-            return decomposed((uint64_t)p, std::move(bits));
+            return decomposed((uint64_t)p & mask, std::move(bits));
         }
-        const bool sub = op == "i64.sub";
-        const unsigned __int128 sv = sub ? ((unsigned __int128)av + (((unsigned __int128)1) << 64) - bv) : ((unsigned __int128)av + bv);
+        // add: s = x + y;  sub: s = (2^width - y) + x (never negative)
+        const bool sub = f == "sub";
+        const unsigned __int128 sv = sub ? ((unsigned __int128)av + (((unsigned __int128)1) << width) - bv) : ((unsigned __int128)av + bv);
         const wid sw = m.acquire(Fr{{(uint64_t)sv, (uint64_t)(sv >> 64), 0, 0}});
         st.linear_witnesses++;
         const Fr r = m.draw();
         m.coef_sub(sw, r);
-        if (sub) {                                                            // (2^64 - y) + x: y takes -r, the constant adds 2^64 * r
+        if (sub) {                                                            // y takes -r, the constant adds 2^width * r, x takes +r
             m.coef_sub(y, r);
-            m.const_add(witness_machine::shl(r, 64));
+            m.const_add(witness_machine::shl(r, width));
             m.coef_add(x, r);
         } else {
             m.coef_add(x, r);
             m.coef_add(y, r);
         }
-        st.quadratic_slots += 65;
-        std::vector<wid> bits = m.decompose(sw, 65);
-        m.release(bits[64]);                                                  // drop_msb(1)
-        bits.resize(64);
+        st.quadratic_slots += (uint64_t)width + 1;
+        std::vector<wid> bits = m.decompose(sw, width + 1);
+        m.release(bits[(size_t)width]);                                       // drop_msb(1)
+        bits.resize((size_t)width);
         m.release(sw); m.release(y); m.release(x);
         drop(a, m); drop(b, m);
-        return decomposed((uint64_t)sv, std::move(bits));
+        return decomposed((uint64_t)sv & mask, std::move(bits));
     }
 
     value eval(const sexpr &e, witness_machine &m, wat_stats &st) const {
         if (!e.is_list) throw std::invalid_argument("wat: only folded instructions are supported (" + e.atom + ")");
         const std::string &h = e.head();
-        if (h == "i64.const") {
-            if (e.list.size() != 2) throw std::invalid_argument("wat: i64.const takes one literal");
-            return concrete(parse_i64(e.list[1].atom));
+        if (h == "i64.const" || h == "i32.const") {
+            if (e.list.size() != 2) throw std::invalid_argument("wat: " + h + " takes one literal");
+            const uint64_t v = parse_i64(e.list[1].atom);
+            if (h == "i32.const" && v > 0xFFFFFFFFULL && v < 0xFFFFFFFF80000000ULL) throw std::invalid_argument("wat: integer literal out of range " + e.list[1].atom);
+            return concrete(h == "i32.const" ? (v & 0xFFFFFFFFULL) : v);
         }
-        if (h == "i64.mul" || h == "i64.add" || h == "i64.sub") {
+        if (h == "i64.mul" || h == "i64.add" || h == "i64.sub" || h == "i32.mul" || h == "i32.add" || h == "i32.sub") {
             if (e.list.size() != 3) throw std::invalid_argument("wat: " + h + " takes two folded operands");
             value a = eval(e.list[1], m, st);
             value b = eval(e.list[2], m, st);
-            return binop(h, std::move(a), std::move(b), m, st);
+            return binop(h, h[1] == '3' ? 32 : 64, std::move(a), std::move(b), m, st);
         }
         if (h == "call") {
             if (e.list.size() < 2) throw std::invalid_argument("wat: call without a target");
@@ -413,9 +419,10 @@ private:
             if (it == imports_.end()) throw std::invalid_argument("wat: call of a non-imported function is not supported (" + e.list[1].atom + ")");
             std::vector<value> args;
             for (size_t i = 2; i < e.list.size(); i++) args.push_back(eval(e.list[i], m, st));
-            if (it->second == "i64_private_const") {
-                if (args.size() != 1 || args[0].bits) throw std::invalid_argument("wat: i64_private_const takes one constant");
-                return private_const(args[0].v, m, st);
+            if (it->second == "i64_private_const" || it->second == "i32_private_const") {
+                if (args.size() != 1 || args[0].bits) throw std::invalid_argument("wat: " + it->second + " takes one constant");
+                const int width = it->second[1] == '3' ? 32 : 64;
+                return private_const(width == 32 ? (args[0].v & 0xFFFFFFFFULL) : args[0].v, width, m, st);
             }
             if (it->second == "assert_equal") {                                // env.hpp:64-77
                 if (args.size() != 2) throw std::invalid_argument("wat: assert_equal takes two operands");

@@ -27,9 +27,9 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "refctx_cpu")
 # masks); its last three assertions at k = 256 (l = 64: 17 row events, so rows of both kinds interleave); the vbn254fr
 # batch calls at k = 256 (271 events: init / equal / quadratic / bit rows between scalar rows)
 CASES = [("i64_mul", 8192), ("i64_mul3", 256), ("vbn", 256)]
-# programs given as text: the repo's own tests/golden/mul64.wat (products, sums, differences, nested forms, literal
-# operands) goes through the reference's interpreter as a token stream (tests/refctx_util.py: wat_to_tokens)
-WAT_CASES = [("mul64", os.path.join(HERE, "mul64.wat"), 256)]
+# programs given as text: the repo's own tests/golden/mul64.wat and arith32.wat (products, sums, differences, nested forms,
+# literal operands; 64- and 32-bit) go through the reference's interpreter as a token stream (tests/refctx_util.py: wat_to_tokens)
+WAT_CASES = [("mul64", os.path.join(HERE, "mul64.wat"), 256), ("arith32", os.path.join(HERE, "arith32.wat"), 256)]
 
 
 def zb64(hexstr):

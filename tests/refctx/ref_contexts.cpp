@@ -96,23 +96,26 @@ using stage3_t = recording<zkp::nonbatch_stage3_context<field_t, executor_t, zkp
 // programs.  Each one is a function template over the stage context, like run_program (include/invoke.hpp:79-98).
 
 // the module store the reference's instantiate() would build (include/runtime.hpp:345-604) for a module that imports
-// env.i64_private_const (func 0) and env.assert_equal (func 1), has one 64 KiB memory and one function `_start` (func 2)
+// env.i64_private_const (func 0), env.assert_equal (func 1) and env.i32_private_const (func 2), has one 64 KiB memory and one
+// function `_start` (func 3)
 struct tiny_module {
     store_t store;
     module_instance inst;
     explicit tiny_module(std::vector<instr_ptr> body) {
-        function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_start({}, {});
-        inst.types = {k_pc, k_eq, k_start};
+        function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_pc32({value_kind::i32}, {value_kind::i32}), k_start({}, {});
+        inst.types = {k_pc, k_eq, k_pc32, k_start};
         inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("i64_private_const"), k_pc, &inst, function_instance::host_code{0, "env", "i64_private_const"}));
         inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("assert_equal"), k_eq, &inst, function_instance::host_code{1, "env", "assert_equal"}));
-        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("_start"), k_start, &inst, function_instance::func_code{2, {}, std::move(body)}));
+        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("i32_private_const"), k_pc32, &inst, function_instance::host_code{2, "env", "i32_private_const"}));
+        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("_start"), k_start, &inst, function_instance::func_code{3, {}, std::move(body)}));
         inst.memaddrs.push_back(store.emplace_back<memory_instance>(memory_kind(limits(1)), memory_instance::page_size));
-        inst.exports["_start"] = 2;
+        inst.exports["_start"] = 3;
     }
 };
 
 // A program of the arithmetic-test subset as the flat instruction stream its folded text denotes (operands first):
 //   c <u64>  i64.const      pc  call $i64_private_const      eq  call $assert_equal      mul | add | sub  i64.mul / add / sub
+//   c32 <u32> / pc32 / mul32 | add32 | sub32: the i32 forms
 // assembled the way transpile() (include/transpiler.hpp:741-776) would: runs of plain opcodes become basic blocks, calls
 // stand alone.
 struct wasm_token { std::string op; uint64_t imm = 0; };
@@ -131,6 +134,11 @@ static std::vector<instr_ptr> assemble(const std::vector<wasm_token> &toks) {
         else if (t.op == "mul") plain(opcode(opcode::inn_mul, value_kind::i64));
         else if (t.op == "add") plain(opcode(opcode::inn_add, value_kind::i64));
         else if (t.op == "sub") plain(opcode(opcode::inn_sub, value_kind::i64));
+        else if (t.op == "c32") plain(opcode(opcode::inn_const, value_kind::i32, (uint32_t)t.imm));
+        else if (t.op == "mul32") plain(opcode(opcode::inn_mul, value_kind::i32));
+        else if (t.op == "add32") plain(opcode(opcode::inn_add, value_kind::i32));
+        else if (t.op == "sub32") plain(opcode(opcode::inn_sub, value_kind::i32));
+        else if (t.op == "pc32") { flush(); body.push_back(make_instr<call>(2)); }
         else if (t.op == "pc") { flush(); body.push_back(make_instr<call>(0)); }
         else if (t.op == "eq") { flush(); body.push_back(make_instr<call>(1)); }
         else throw std::runtime_error("unknown token " + t.op);
@@ -174,7 +182,7 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
     std::string op;
     while (in >> op) {
         wasm_token tok{op};
-        if (op == "c") { std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0); }
+        if (op == "c" || op == "c32") { std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0); }
         t.push_back(tok);
     }
     return t;

@@ -11,8 +11,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-CASES = ["i64_mul_k8192", "i64_mul3_k256", "vbn_k256", "mul64_k256"]
-WAT_TEXT = {"mul64": os.path.join(HERE, "golden", "mul64.wat")}          # cases whose program is a .wat file of the repo
+CASES = ["i64_mul_k8192", "i64_mul3_k256", "vbn_k256", "mul64_k256", "arith32_k256"]
+WAT_TEXT = {"mul64": os.path.join(HERE, "golden", "mul64.wat"), "arith32": os.path.join(HERE, "golden", "arith32.wat")}          # cases whose program is a .wat file of the repo
 REF_BIN_CPU = os.path.join(ROOT, "oracle", "_ref", "refctx_cpu")
 REF_BIN_CUDA = os.path.join(ROOT, "oracle", "_ref", "refctx_cuda")
 
@@ -88,7 +88,8 @@ def _sexpr(text):
 
 
 def wat_to_tokens(text):
-    """'c <u64>' / pc / eq / mul / add / sub, operands first -- what the folded text of the exported function denotes"""
+    """'c <u64>' / pc / eq / mul / add / sub (and c32 / pc32 / mul32 / add32 / sub32), operands first -- what the folded text
+    of the exported function denotes"""
     mod = _sexpr(text)
     imports = {f[3][1]: f[2].strip('"') for f in mod[1:] if f[0] == "import"}
     start = next(f[2][1] for f in mod[1:] if f[0] == "export" and f[1] == '"_start"')
@@ -103,12 +104,16 @@ def wat_to_tokens(text):
     def emit(e):
         if e[0] == "i64.const":
             out.append("c %d" % lit(e[1]))
+        elif e[0] == "i32.const":
+            out.append("c32 %d" % (lit(e[1]) % (1 << 32)))
         elif e[0] in ("i64.mul", "i64.add", "i64.sub"):
             emit(e[1]); emit(e[2]); out.append(e[0][4:])
+        elif e[0] in ("i32.mul", "i32.add", "i32.sub"):
+            emit(e[1]); emit(e[2]); out.append(e[0][4:] + "32")
         elif e[0] == "call":
             for a in e[2:]:
                 emit(a)
-            out.append({"i64_private_const": "pc", "assert_equal": "eq"}[imports[e[1]]])
+            out.append({"i64_private_const": "pc", "i32_private_const": "pc32", "assert_equal": "eq"}[imports[e[1]]])
         else:
             raise ValueError("unsupported form " + str(e[0]))
     for e in func[2:]:
@@ -149,6 +154,9 @@ I64_MUL_CASES = [(1, 1, 1), (1, 0, 0), (2**64 - 1, 2**64 - 1, 1), (0x10000000000
 WAT_HEAD = ('(module (import "env" "i64_private_const" (func $i64_private_const (param i64) (result i64)))\n'
             '(import "env" "assert_equal" (func $assert_equal (param i64 i64)))\n(func $t\n')
 WAT_TAIL = ')\n(export "_start" (func $t)))\n'
+
+
+WAT_HEAD32 = WAT_HEAD.replace("i64", "i32")
 
 
 def binop_wat(op, cases):

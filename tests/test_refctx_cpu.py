@@ -92,7 +92,7 @@ def test_i64_mul_row_counts_at_the_default_geometry():
 
 
 @pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("case", ["i64_mul3_k256", "vbn_k256", "mul64_k256"])
+@pytest.mark.parametrize("case", ["i64_mul3_k256", "vbn_k256", "mul64_k256", "arith32_k256"])
 def test_harness_regenerates_the_committed_vectors(oracle, case):
     """the committed JSON is exactly what the harness writes today (same reference sources, same oracle)"""
     gen = U.compact_module()
@@ -140,34 +140,59 @@ def test_wat_emitter_reproduces_the_reference_rows_for_i64_mul(pr):
     _emitter_equals_reference_rows(pr, U.binop_wat("mul", U.I64_MUL_CASES[6:]), U.load("i64_mul3_k256"))
 
 
-def test_wat_emitter_reproduces_the_reference_rows_for_the_repo_program(pr):
-    """tests/golden/mul64.wat: products, sums, differences, nested forms and literal operands, 39 row events at l = 64"""
-    st = U.load("mul64_k256")
-    _emitter_equals_reference_rows(pr, open(U.WAT_TEXT["mul64"]).read(), st)
+@pytest.mark.parametrize("name", ["mul64", "arith32"])
+def test_wat_emitter_reproduces_the_reference_rows_for_the_repo_programs(pr, name):
+    """tests/golden/mul64.wat and arith32.wat: products, sums, differences, nested forms and literal operands in 64 and 32
+    bits (39 and 19 row events at l = 64)"""
+    st = U.load(name + "_k256")
+    _emitter_equals_reference_rows(pr, open(U.WAT_TEXT[name]).read(), st)
 
 
-def _rand_expr(rng, depth):
+def _rand_expr(rng, depth, w=64):
+    """(text, value mod 2^w) of a random folded expression over private and literal operands of width w"""
+    M = 1 << w
     if depth == 0 or rng.random() < 0.25:
-        v = rng.choice([0, 1, 2, 2**64 - 1, 1 << 63, (1 << 63) - 1, 1 << 32, rng.getrandbits(64), rng.getrandbits(20)])
-        return ("(call $i64_private_const (i64.const %d))" if rng.random() < 0.7 else "(i64.const %d)") % v, v
+        v = rng.choice([0, 1, 2, M - 1, M >> 1, (M >> 1) - 1, 1 << (w // 2), rng.getrandbits(w), rng.getrandbits(20)])
+        lit = "(i%d.const %d)" % (w, v)
+        return ("(call $i%d_private_const %s)" % (w, lit) if rng.random() < 0.7 else lit), v
     op = rng.choice(["mul", "add", "sub"])
-    (ta, va), (tb, vb) = _rand_expr(rng, depth - 1), _rand_expr(rng, depth - 1)
-    return "(i64.%s %s %s)" % (op, ta, tb), {"mul": va * vb, "add": va + vb, "sub": va - vb}[op] % 2**64
+    (ta, va), (tb, vb) = _rand_expr(rng, depth - 1, w), _rand_expr(rng, depth - 1, w)
+    return "(i%d.%s %s %s)" % (w, op, ta, tb), {"mul": va * vb, "add": va + vb, "sub": va - vb}[op] % M
+
+
+def _rand_program(rng, w):
+    exprs = [_rand_expr(rng, rng.randrange(1, 4), w) for _ in range(4)]
+    rhs = lambda v: ("(i%d.const %d)" % (w, v)) if rng.random() < 0.5 else ("(call $i%d_private_const (i%d.const %d))" % (w, w, v))
+    head = U.WAT_HEAD if w == 64 else U.WAT_HEAD32
+    return head + "".join("(call $assert_equal %s %s)\n" % (t, rhs(v)) for t, v in exprs) + U.WAT_TAIL
 
 
 @pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("seed", range(4))
-def test_wat_emitter_against_the_reference_interpreter_on_random_programs(oracle, pr, seed):
-    """differential: random expression trees (private and literal operands, nested mul / add / sub) run through the
-    reference's interpreter + backend (oracle/_ref/refctx_cpu) and through the emitter give the same rows"""
+@pytest.mark.parametrize("seed,w", [(0, 64), (1, 64), (2, 64), (3, 32), (4, 32), (5, 32)])
+def test_wat_emitter_against_the_reference_interpreter_on_random_programs(oracle, pr, seed, w):
+    """differential: random expression trees (private and literal operands, nested mul / add / sub, 64- and 32-bit) run
+    through the reference's interpreter + backend (oracle/_ref/refctx_cpu) and through the emitter give the same rows"""
     import random
     rng = random.Random(4200 + seed)
-    exprs = [_rand_expr(rng, rng.randrange(1, 4)) for _ in range(4)]
-    text = U.WAT_HEAD + "".join("(call $assert_equal %s %s)\n" % (t, ("(i64.const %d)" if rng.random() < 0.5 else "(call $i64_private_const (i64.const %d))") % v)
-                                for t, v in exprs) + U.WAT_TAIL
+    text = _rand_program(rng, w)
     k = rng.choice([256, 512])
     raw = U.run_reference_on_wat(text, k, seed_byte=seed + 1)
-    assert raw["valid"] == [1, 1, 1]
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    l = raw["l"]
+    u32 = lambda h: np.frombuffer(bytes.fromhex(h), np.uint32)
+    st = {"fx": raw, "l": l, "kinds": raw["kinds"], "values": u32(raw["values"]).reshape(-1, l, 8), "coefs": u32(raw["coefs"]).reshape(-1, l, 8),
+          "const_sum": int.from_bytes(bytes.fromhex(raw["const_sum"]), "little")}
+    _emitter_equals_reference_rows(pr, text, st)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "tests")) or not os.path.exists(U.REF_BIN_CPU), reason="needs the reference tree and oracle/_ref/refctx_cpu")
+@pytest.mark.parametrize("name", ["i64_mul", "i64_add", "i64_sub", "i32_mul", "i32_add", "i32_sub"])
+def test_wat_emitter_on_the_reference_test_programs(oracle, pr, name):
+    """the six arithmetic programs of the reference's tests/ that lie in the subset, read where they lie: the reference's
+    own interpreter and the emitter agree on every row at l = 64 (many rows) -- and the reference's verifier accepts"""
+    text = open(os.path.join(REFERENCE, "tests", name + ".wat")).read()
+    raw = U.run_reference_on_wat(text, 256)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
     l = raw["l"]
     u32 = lambda h: np.frombuffer(bytes.fromhex(h), np.uint32)
     st = {"fx": raw, "l": l, "kinds": raw["kinds"], "values": u32(raw["values"]).reshape(-1, l, 8), "coefs": u32(raw["coefs"]).reshape(-1, l, 8),
