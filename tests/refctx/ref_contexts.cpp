@@ -21,6 +21,7 @@
 #include <format>
 #include <fstream>
 #include <iomanip>
+#include <map>
 #include <memory>
 #include <stdexcept>
 
@@ -114,8 +115,8 @@ struct tiny_module {
 };
 
 // A program of the arithmetic-test subset as the flat instruction stream its folded text denotes (operands first):
-//   c <u64>  i64.const      pc  call $i64_private_const      eq  call $assert_equal      mul | add | sub  i64.mul / add / sub
-//   c32 <u32> / pc32 / mul32 | add32 | sub32: the i32 forms
+//   iNN.const <value>    iNN.<op> (every integer instruction of the reference's tests)    call:<env function>
+// (plus the short forms c / pc / eq / mul of the built-in i64_mul program)
 // assembled the way transpile() (include/transpiler.hpp:741-776) would: runs of plain opcodes become basic blocks, calls
 // stand alone.
 struct wasm_token { std::string op; uint64_t imm = 0; };
@@ -129,18 +130,43 @@ static std::vector<instr_ptr> assemble(const std::vector<wasm_token> &toks) {
         if (!bb) { bb = std::make_unique<basic_block>(); bb->id = bb_id++; }
         bb->body.push_back(o);
     };
+    // what transpile_opcode (include/transpiler.hpp:95-371) emits for the integer instructions
+    static const std::map<std::string, std::pair<opcode::kind, sign_kind>> table = {
+        {"clz", {opcode::inn_clz, sign_kind::unspecified}}, {"ctz", {opcode::inn_ctz, sign_kind::unspecified}},
+        {"popcnt", {opcode::inn_popcnt, sign_kind::unspecified}}, {"eqz", {opcode::inn_eqz, sign_kind::unspecified}},
+        {"add", {opcode::inn_add, sign_kind::unspecified}}, {"sub", {opcode::inn_sub, sign_kind::unspecified}},
+        {"mul", {opcode::inn_mul, sign_kind::unspecified}},
+        {"div_s", {opcode::inn_div_sx, sign_kind::sign}}, {"div_u", {opcode::inn_div_sx, sign_kind::unsign}},
+        {"rem_s", {opcode::inn_rem_sx, sign_kind::sign}}, {"rem_u", {opcode::inn_rem_sx, sign_kind::unsign}},
+        {"and", {opcode::inn_and, sign_kind::unspecified}}, {"or", {opcode::inn_or, sign_kind::unspecified}},
+        {"xor", {opcode::inn_xor, sign_kind::unspecified}}, {"shl", {opcode::inn_shl, sign_kind::unspecified}},
+        {"shr_s", {opcode::inn_shr_sx, sign_kind::sign}}, {"shr_u", {opcode::inn_shr_sx, sign_kind::unsign}},
+        {"rotl", {opcode::inn_rotl, sign_kind::unspecified}}, {"rotr", {opcode::inn_rotr, sign_kind::unspecified}},
+        {"eq", {opcode::inn_eq, sign_kind::unspecified}}, {"ne", {opcode::inn_ne, sign_kind::unspecified}},
+        {"lt_s", {opcode::inn_lt_sx, sign_kind::sign}}, {"lt_u", {opcode::inn_lt_sx, sign_kind::unsign}},
+        {"gt_s", {opcode::inn_gt_sx, sign_kind::sign}}, {"gt_u", {opcode::inn_gt_sx, sign_kind::unsign}},
+        {"le_s", {opcode::inn_le_sx, sign_kind::sign}}, {"le_u", {opcode::inn_le_sx, sign_kind::unsign}},
+        {"ge_s", {opcode::inn_ge_sx, sign_kind::sign}}, {"ge_u", {opcode::inn_ge_sx, sign_kind::unsign}},
+        {"extend8_s", {opcode::inn_extend8_s, sign_kind::unspecified}}, {"extend16_s", {opcode::inn_extend16_s, sign_kind::unspecified}},
+    };
     for (const wasm_token &t : toks) {
-        if (t.op == "c") plain(opcode(opcode::inn_const, value_kind::i64, t.imm));
+        const bool typed = t.op.size() > 4 && (t.op.rfind("i32.", 0) == 0 || t.op.rfind("i64.", 0) == 0);
+        const value_kind vk = (typed && t.op[1] == '3') ? value_kind::i32 : value_kind::i64;
+        const std::string name = typed ? t.op.substr(4) : std::string();
+        if (typed && name == "const") plain(vk == value_kind::i32 ? opcode(opcode::inn_const, value_kind::i32, (uint32_t)t.imm) : opcode(opcode::inn_const, value_kind::i64, t.imm));
+        else if (t.op == "i64.extend32_s") plain(opcode(opcode::i64_extend32_s));
+        else if (t.op == "i64.extend_i32_s") plain(opcode(opcode::i64_extend_i32_sx, value_kind::i64, sign_kind::sign));
+        else if (t.op == "i64.extend_i32_u") plain(opcode(opcode::i64_extend_i32_sx, value_kind::i64, sign_kind::unsign));
+        else if (t.op == "i32.wrap_i64") plain(opcode(opcode::i32_wrap_i64));
+        else if (typed && table.count(name)) {
+            const auto &e = table.at(name);
+            plain(e.second == sign_kind::unspecified ? opcode(e.first, vk) : opcode(e.first, vk, e.second));
+        }
+        else if (t.op == "c") plain(opcode(opcode::inn_const, value_kind::i64, t.imm));
         else if (t.op == "mul") plain(opcode(opcode::inn_mul, value_kind::i64));
-        else if (t.op == "add") plain(opcode(opcode::inn_add, value_kind::i64));
-        else if (t.op == "sub") plain(opcode(opcode::inn_sub, value_kind::i64));
-        else if (t.op == "c32") plain(opcode(opcode::inn_const, value_kind::i32, (uint32_t)t.imm));
-        else if (t.op == "mul32") plain(opcode(opcode::inn_mul, value_kind::i32));
-        else if (t.op == "add32") plain(opcode(opcode::inn_add, value_kind::i32));
-        else if (t.op == "sub32") plain(opcode(opcode::inn_sub, value_kind::i32));
-        else if (t.op == "pc32") { flush(); body.push_back(make_instr<call>(2)); }
-        else if (t.op == "pc") { flush(); body.push_back(make_instr<call>(0)); }
-        else if (t.op == "eq") { flush(); body.push_back(make_instr<call>(1)); }
+        else if (t.op == "pc32" || t.op == "call:i32_private_const") { flush(); body.push_back(make_instr<call>(2)); }
+        else if (t.op == "pc" || t.op == "call:i64_private_const") { flush(); body.push_back(make_instr<call>(0)); }
+        else if (t.op == "eq" || t.op == "call:assert_equal") { flush(); body.push_back(make_instr<call>(1)); }
         else throw std::runtime_error("unknown token " + t.op);
     }
     flush();
@@ -182,7 +208,7 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
     std::string op;
     while (in >> op) {
         wasm_token tok{op};
-        if (op == "c" || op == "c32") { std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0); }
+        if (op == "c" || op == "i32.const" || op == "i64.const") { std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0); }
         t.push_back(tok);
     }
     return t;

@@ -88,8 +88,7 @@ def _sexpr(text):
 
 
 def wat_to_tokens(text):
-    """'c <u64>' / pc / eq / mul / add / sub (and c32 / pc32 / mul32 / add32 / sub32), operands first -- what the folded text
-    of the exported function denotes"""
+    """'iNN.const <v>' / 'iNN.<op>' / 'call:<env function>', operands first -- what the folded text of the exported function denotes"""
     mod = _sexpr(text)
     imports = {f[3][1]: f[2].strip('"') for f in mod[1:] if f[0] == "import"}
     start = next(f[2][1] for f in mod[1:] if f[0] == "export" and f[1] == '"_start"')
@@ -102,18 +101,16 @@ def wat_to_tokens(text):
         return v % (1 << 64)
 
     def emit(e):
-        if e[0] == "i64.const":
-            out.append("c %d" % lit(e[1]))
-        elif e[0] == "i32.const":
-            out.append("c32 %d" % (lit(e[1]) % (1 << 32)))
-        elif e[0] in ("i64.mul", "i64.add", "i64.sub"):
-            emit(e[1]); emit(e[2]); out.append(e[0][4:])
-        elif e[0] in ("i32.mul", "i32.add", "i32.sub"):
-            emit(e[1]); emit(e[2]); out.append(e[0][4:] + "32")
+        if e[0] in ("i64.const", "i32.const"):
+            out.append("%s %d" % (e[0], lit(e[1]) % (1 << int(e[0][1:3]))))
         elif e[0] == "call":
             for a in e[2:]:
                 emit(a)
-            out.append({"i64_private_const": "pc", "i32_private_const": "pc32", "assert_equal": "eq"}[imports[e[1]]])
+            out.append("call:" + imports[e[1]])
+        elif e[0][:4] in ("i32.", "i64."):
+            for a in e[1:]:
+                emit(a)
+            out.append(e[0])
         else:
             raise ValueError("unsupported form " + str(e[0]))
     for e in func[2:]:
