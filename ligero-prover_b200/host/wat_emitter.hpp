@@ -34,6 +34,7 @@
 #include <cstdint>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -115,21 +116,107 @@ private:
 // ---- the witness machine ------------------------------------------------------------------------------------
 struct wat_stats {
     uint64_t private_consts = 0, asserts = 0, arithmetic_ops = 0;
-    uint64_t linear_witnesses = 0, quadratic_slots = 0, linear_constraints = 0;   // linear_constraints = draws from the linear stream
+    uint64_t linear_witnesses = 0, quadratic_slots = 0, linear_constraints = 0;   // witnesses committed to linear rows; slots; draws from the linear stream
     uint64_t violated_constraints = 0;           // > 0: the program's assertions do not hold (the proof will not validate)
 };
 
+// What the reference spreads over witness_manager (pools, constraints, release into rows), ligetron_backend (expression
+// evaluation, bit (de)composition, the bitwise / comparison / division gadgets) and the C++ object lifetimes that decide WHEN
+// a witness is released (shared_ptr<lazy_witness> with a committing deleter, core.hpp:60-100,277-300).  Here: witnesses are
+// indices into one table with a reference count; `wref` is the counted handle (the last one to die releases the witness
+// into the packer), `bitvec` a vector of handles that dies most-significant-bit first and -- like the reference's
+// decomposed_bits, which has a destructor and hence no move constructor -- can only be copied, `expr` a small run-time tree
+// in place of the reference's expression templates.  The gadgets below are written so that handles are created, copied and
+// dropped where the reference's are; the C++ rules (temporaries die at the end of the full expression, locals in reverse
+// order of declaration) then produce the reference's release order without it being spelled out.
 class witness_machine {
 public:
     using wid = uint32_t;
+    static constexpr wid none = 0xFFFFFFFFu;
+
+    class wref {
+    public:
+        wref() = default;
+        wref(witness_machine *m, wid w) : m_(m), w_(w) { m_->w_[w_].refs++; }
+        wref(const wref &o) : m_(o.m_), w_(o.w_) { if (m_) m_->w_[w_].refs++; }
+        wref(wref &&o) noexcept : m_(o.m_), w_(o.w_) { o.m_ = nullptr; }
+        wref &operator=(const wref &o) { wref t(o); swap(t); return *this; }           // the old witness goes before the
+        wref &operator=(wref &&o) noexcept { wref t(std::move(o)); swap(t); return *this; }   // assignment returns (shared_ptr)
+        ~wref() { reset(); }
+        void reset() {
+            if (!m_) return;
+            witness_machine *m = m_;
+            m_ = nullptr;
+            if (--m->w_[w_].refs == 0) m->release(w_);
+        }
+        explicit operator bool() const { return m_ != nullptr; }
+        wid id() const { return w_; }
+        const Fr &val() const { return m_->w_[w_].val; }
+
+    private:
+        void swap(wref &o) { std::swap(m_, o.m_); std::swap(w_, o.w_); }
+        witness_machine *m_ = nullptr;
+        wid w_ = 0;
+    };
+
+    // decomposed_bits (core.hpp:93-150): least significant bit first
+    class bitvec {
+    public:
+        bitvec() = default;
+        bitvec(const bitvec &) = default;                    // copy only: "moving" a bitvec shares its witnesses with the source
+        bitvec &operator=(const bitvec &) = default;
+        ~bitvec() { while (!b_.empty()) b_.pop_back(); }
+        size_t size() const { return b_.size(); }
+        wref &operator[](size_t i) { return b_[i]; }
+        const wref &operator[](size_t i) const { return b_[i]; }
+        void push_back(wref w) { b_.push_back(std::move(w)); }
+        void push_lsb(wref w, size_t n) { b_.insert(b_.begin(), n, w); }
+        void push_msb(wref w, size_t n) { b_.insert(b_.end(), n, w); }
+        void drop_lsb(size_t n) {
+            for (size_t i = n; i-- > 0;) b_[i].reset();
+            b_.erase(b_.begin(), b_.begin() + (ptrdiff_t)n);
+        }
+        void drop_msb(size_t n) { for (size_t i = 0; i < n; i++) b_.pop_back(); }
+
+    private:
+        std::vector<wref> b_;
+    };
+
+    // an expression over witnesses and constants (core.hpp:152-270); children die first operand first, as a std::tuple does
+    struct expr {
+        enum kind_t : uint8_t { WIT, CONST, ADD, SUB, MUL, NOT, AND };
+        kind_t kind;
+        wref w;
+        Fr k{};
+        std::unique_ptr<expr> a, b;
+        expr(const wref &x) : kind(WIT), w(x) {}             // NOLINT: implicit on purpose (x & ~y reads like the reference)
+        expr(wref &&x) : kind(WIT), w(std::move(x)) {}       // NOLINT
+        explicit expr(const Fr &c) : kind(CONST), k(c) {}
+        expr(kind_t kd, expr &&x) : kind(kd), a(new expr(std::move(x))) {}
+        expr(kind_t kd, expr &&x, expr &&y) : kind(kd), a(new expr(std::move(x))), b(new expr(std::move(y))) {}
+        expr(expr &&) = default;
+        expr &operator=(expr &&) = delete;
+        ~expr() { w.reset(); a.reset(); b.reset(); }
+    };
+    static expr K(uint64_t v) { return expr(lgr::host::from_u64(v)); }
+    static expr K(const Fr &v) { return expr(v); }
 
     // rows go to `pk` as witnesses are released; with a stage-1 seed the linear-test coefficients are drawn as the reference draws them
     witness_machine(row_packer &pk, const uint8_t *stage1_seed) : pk_(pk), seeded_(stage1_seed != nullptr) {
         static const uint8_t any_iv[16] = {0};
         if (seeded_) rng_.init(stage1_seed, any_iv);
     }
+    witness_machine(const witness_machine &) = delete;
+    witness_machine &operator=(const witness_machine &) = delete;
 
-    wid acquire(const Fr &v) { w_.push_back(wit{v, zero(), -1, 0}); return (wid)(w_.size() - 1); }
+    // ---- witness_manager --------------------------------------------------------------------------------------
+    wid acquire_raw(const Fr &v) {
+        wid w;
+        if (!free_w_.empty()) { w = free_w_.back(); free_w_.pop_back(); w_[w] = wit{v, zero(), none, 0, 0}; }
+        else { w_.push_back(wit{v, zero(), none, 0, 0}); w = (wid)(w_.size() - 1); }
+        return w;
+    }
+    wref acquire(const Fr &v) { return wref(this, acquire_raw(v)); }
     const Fr &value(wid w) const { return w_[w].val; }
 
     Fr draw() {                                               // generate_linear_random (witness_manager.hpp:344-348)
@@ -142,78 +229,195 @@ public:
     void coef_add(wid w, const Fr &r) { w_[w].coef = lgr::host::add(w_[w].coef, r); }
     void coef_sub(wid w, const Fr &r) { w_[w].coef = sub(w_[w].coef, r); }
     void const_add(const Fr &r) { const_sum_ = lgr::host::add(const_sum_, r); }
+    void const_sub(const Fr &r) { const_sum_ = sub(const_sum_, r); }
 
     // constrain_equal (witness_manager.hpp:421-429): one draw, +r on a, -r on b
-    void equal(wid a, wid b) {
+    void constrain_equal(wid a, wid b) {
         if (!(w_[a].val == w_[b].val)) violated_++;
         const Fr r = draw();
         coef_add(a, r);
         coef_sub(b, r);
     }
-    wid clone(wid w) { const wid c = acquire(w_[w].val); equal(w, c); return c; }       // clone_witness (:393-397)
+    // constrain_constant (:399-419): one draw, +r on the witness, -v*r on the constant
+    void constrain_constant(wid w, const Fr &v) {
+        if (!(w_[w].val == v)) violated_++;
+        const Fr r = draw();
+        coef_add(w, r);
+        const_sub(lgr::host::mul(v, r));
+    }
+    wid clone_raw(wid w) { const wid c = acquire_raw(w_[w].val); constrain_equal(w, c); return c; }       // clone_witness (:393-397)
 
     // constrain_quadratic (:474-492): slot positions (a, b, c); a witness that already sits in a slot is replaced by a clone
-    void quadratic(wid c, wid a, wid b) {
+    void constrain_quadratic(wid c, wid a, wid b) {
         if (!(lgr::host::mul(w_[a].val, w_[b].val) == w_[c].val)) violated_++;
-        slots_.push_back(slot{});
-        const int s = (int)slots_.size() - 1;
+        uint32_t s;
+        if (!free_s_.empty()) { s = free_s_.back(); free_s_.pop_back(); slots_[s] = slot{}; }
+        else { slots_.push_back(slot{}); s = (uint32_t)slots_.size() - 1; }
+        nslots_++;
         const wid arr[3] = {a, b, c};
         for (int i = 0; i < 3; i++) {
             wid w = arr[i];
-            const bool taken = w_[w].slot >= 0;
-            if (taken) w = clone(arr[i]);
+            const bool taken = w_[w].slot != none;
+            if (taken) w = clone_raw(arr[i]);
             w_[w].slot = s; w_[w].pos = i;
-            slots_[(size_t)s].w[i] = w;
+            slots_[s].w[i] = w;
             if (taken) release(w);
         }
+    }
+    // constrain_bit (:431-441)
+    void constrain_bit(wid b) {
+        const wid b1 = clone_raw(b), b2 = clone_raw(b);
+        constrain_quadratic(b, b1, b2);
+        release(b1);
+        release(b2);
     }
 
     // commit_release_witness (:117-186)
     void release(wid w) {
-        wit &x = w_[w];
         uint32_t v[3][8], c[3][8];
-        if (x.slot < 0) {
-            lgr::host::to_u32(v[0], x.val); lgr::host::to_u32(c[0], x.coef);
+        if (w_[w].slot == none) {
+            lgr::host::to_u32(v[0], w_[w].val); lgr::host::to_u32(c[0], w_[w].coef);
             pk_.push_linear(v[0], c[0]);
+            nlinear_++;
+            free_w_.push_back(w);
             return;
         }
-        slot &s = slots_[(size_t)x.slot];
-        s.ready[x.pos] = true;
+        const uint32_t si = w_[w].slot;
+        slot &s = slots_[si];
+        s.ready[w_[w].pos] = true;
         if (!(s.ready[0] && s.ready[1] && s.ready[2])) return;
         for (int j = 0; j < 3; j++) { lgr::host::to_u32(v[j], w_[s.w[j]].val); lgr::host::to_u32(c[j], w_[s.w[j]].coef); }
         pk_.push_quadratic(v[0], v[1], v[2], c[0], c[1], c[2]);
+        for (int j = 0; j < 3; j++) free_w_.push_back(s.w[j]);
+        free_s_.push_back(si);
     }
 
-    // bit_decompose (core.hpp:714-741) with constrain_bit (witness_manager.hpp:431-441) per bit
-    std::vector<wid> decompose(wid x, int nbits) {
+    // ---- ligetron_backend ---------------------------------------------------------------------------------------
+    // eval(expr) -> a witness holding its value (core.hpp:303-311 and the eval_impl overloads :319-690)
+    wref eval(const expr &e) {
+        switch (e.kind) {
+        case expr::WIT: return e.w;
+        case expr::CONST: {                                   // zkexpr<constant>::eval (:179-184)
+            const wid w = acquire_raw(e.k);
+            constrain_constant(w, e.k);
+            return wref(this, w);
+        }
+        case expr::MUL:
+            if (e.b->kind == expr::CONST) break;
+            [[fallthrough]];
+        case expr::AND: {                                     // :537-550, :637-652: operands materialised, slot (x, y, z)
+            wref x = eval(*e.a);
+            wref y = eval(*e.b);
+            const Fr zv = e.kind == expr::AND ? lgr::host::from_u64(x.val().v[0] & y.val().v[0]) : lgr::host::mul(x.val(), y.val());
+            const wid z = acquire_raw(zv);
+            constrain_quadratic(z, x.id(), y.id());
+            return wref(this, z);
+        }
+        default: break;
+        }
+        // linear forms: a fresh witness takes -r, the leaves take +-r (scaled), constants go to const_sum
+        const wid w = acquire_raw(zero());
+        const Fr r = draw();
+        coef_sub(w, r);
+        const Fr out = spread(e, r);
+        w_[w].val = out;
+        return wref(this, w);
+    }
+    // eval(expr, result, rand): value of the expression, `r` handed down to its leaves
+    Fr spread(const expr &e, const Fr &r) {
+        using lgr::host::add; using lgr::host::mul;
+        switch (e.kind) {
+        case expr::WIT: coef_add(e.w.id(), r); return e.w.val();
+        case expr::ADD: {
+            const Fr x = spread(*e.a, r);
+            if (e.b->kind == expr::CONST) { const_add(mul(e.b->k, r)); return add(x, e.b->k); }
+            const Fr y = spread(*e.b, r);
+            return add(x, y);
+        }
+        case expr::SUB: {
+            if (e.a->kind == expr::CONST) {                   // K - x
+                const Fr x = spread(*e.b, neg(r));
+                const_add(mul(e.a->k, r));
+                return sub(e.a->k, x);
+            }
+            const Fr x = spread(*e.a, r);
+            if (e.b->kind == expr::CONST) { const_sub(mul(e.b->k, r)); return sub(x, e.b->k); }
+            const Fr y = spread(*e.b, neg(r));
+            return sub(x, y);
+        }
+        case expr::NOT: {                                     // 1 - x
+            const Fr x = spread(*e.a, neg(r));
+            const_add(r);
+            return lgr::host::from_u64(1 - x.v[0]);
+        }
+        case expr::MUL:
+            if (e.b->kind == expr::CONST) {                   // x * K: the leaf takes K*r
+                const Fr x = spread(*e.a, mul(e.b->k, r));
+                return mul(x, e.b->k);
+            }
+            [[fallthrough]];
+        case expr::AND: {                                     // a product inside a linear form: its own witness takes r
+            wref z = eval(e);
+            const Fr out = z.val();
+            coef_add(z.id(), r);
+            return out;
+        }
+        default: throw std::logic_error("wat: a bare constant inside an expression");
+        }
+    }
+
+    wref duplicate(const wref &w) { return wref(this, clone_raw(w.id())); }
+    void assert_const(const wref &w, uint64_t v) { constrain_constant(w.id(), lgr::host::from_u64(v)); }
+    void assert_equal(const wref &x, const wref &y) { constrain_equal(x.id(), y.id()); }
+
+    // bit_decompose (core.hpp:714-741) with constrain_bit per bit
+    bitvec bit_decompose(const wref &x, size_t nbits) {
+        bitvec bits;
         const Fr rho = draw();
-        coef_sub(x, rho);
-        const Fr v = w_[x].val;
-        std::vector<wid> bits;
-        for (int i = 0; i < nbits; i++) {
-            const wid b = acquire(lgr::host::from_u64((v.v[i >> 6] >> (i & 63)) & 1));
-            const wid b1 = clone(b), b2 = clone(b);
-            quadratic(b, b1, b2);
-            release(b1);
-            release(b2);
-            coef_add(b, shl(rho, i));
-            bits.push_back(b);
+        coef_sub(x.id(), rho);
+        for (size_t i = 0; i < nbits; i++) {
+            const wid b = acquire_raw(lgr::host::from_u64(i < 256 ? (w_[x.id()].val.v[i >> 6] >> (i & 63)) & 1 : 0));
+            constrain_bit(b);
+            coef_add(b, shl(rho, (int)i));
+            bits.push_back(wref(this, b));
         }
         return bits;
     }
-    // bit_compose (core.hpp:761-781); the caller releases the bits
-    wid compose(const std::vector<wid> &bits) {
-        const wid sum = acquire(zero());
+    // bit_decompose_constant (:743-759)
+    bitvec bit_decompose_constant(uint64_t k, size_t nbits) {
+        bitvec bits;
+        for (size_t i = 0; i < nbits; i++) {
+            const Fr bit = lgr::host::from_u64(i < 64 ? (k >> i) & 1 : 0);
+            const wid b = acquire_raw(bit);
+            constrain_constant(b, bit);
+            bits.push_back(wref(this, b));
+        }
+        return bits;
+    }
+    // bit_compose (:761-781); the bits stay with the caller
+    wref bit_compose(const bitvec &bits) {
+        const wid sum = acquire_raw(zero());
         const Fr rho = draw();
         coef_sub(sum, rho);
         Fr acc = zero();
         for (size_t i = 0; i < bits.size(); i++) {
-            acc = lgr::host::add(acc, shl(w_[bits[i]].val, (int)i));
-            coef_add(bits[i], shl(rho, (int)i));
+            acc = lgr::host::add(acc, shl(bits[i].val(), (int)i));
+            coef_add(bits[i].id(), shl(rho, (int)i));
         }
         w_[sum].val = acc;
-        return sum;
+        return wref(this, sum);
     }
+    static uint64_t bit_compose_constant(const bitvec &bits) {           // :783-787, low 64 bits
+        uint64_t v = 0;
+        for (size_t i = 0; i < bits.size() && i < 64; i++) v |= (bits[i].val().v[0] & 1) << i;
+        return v;
+    }
+
+    wref bitwise_xor(const wref &x, const wref &y);
+    wref bitwise_xnor(const wref &x, const wref &y);
+    wref bitwise_eq(const bitvec &x, const bitvec &y);
+    std::pair<wref, wref> bitwise_gt(const bitvec &x, const bitvec &y, bool is_signed);
+    std::pair<wref, wref> idivide_qr(const wref &x, const wref &y);
 
     // witness_manager::finalize (the mask rows are the prover's business)
     void finish(uint32_t const_sum[8]) {
@@ -222,6 +426,8 @@ public:
     }
     uint64_t draws() const { return draws_; }
     uint64_t violated() const { return violated_; }
+    uint64_t slots_made() const { return nslots_; }
+    uint64_t linear_released() const { return nlinear_; }
 
     static Fr zero() { return Fr{{0, 0, 0, 0}}; }
     static Fr sub(const Fr &a, const Fr &b) {
@@ -229,6 +435,7 @@ public:
         if (lgr::host::sub4(r.v, a.v, b.v)) lgr::host::add4(r.v, r.v, lgr::host::kP);
         return r;
     }
+    static Fr neg(const Fr &a) { return sub(zero(), a); }
     static Fr shl(const Fr &a, int i) {                       // a * 2^i mod p, i < 254
         Fr p2 = zero();
         p2.v[i >> 6] = 1ULL << (i & 63);
@@ -236,16 +443,60 @@ public:
     }
 
 private:
-    struct wit { Fr val, coef; int slot; int pos; };
+    struct wit { Fr val, coef; uint32_t slot; int pos; uint32_t refs; };
     struct slot { wid w[3] = {0, 0, 0}; bool ready[3] = {false, false, false}; };
     row_packer &pk_;
     bool seeded_;
     fr_random_stream rng_;
     std::vector<wit> w_;
     std::vector<slot> slots_;
+    std::vector<wid> free_w_;
+    std::vector<uint32_t> free_s_;
     Fr const_sum_ = zero();
-    uint64_t draws_ = 0, violated_ = 0;
+    uint64_t draws_ = 0, violated_ = 0, nslots_ = 0, nlinear_ = 0;
 };
+
+using wexpr = witness_machine::expr;
+inline wexpr operator+(wexpr x, wexpr y) { return wexpr(wexpr::ADD, std::move(x), std::move(y)); }
+inline wexpr operator-(wexpr x, wexpr y) { return wexpr(wexpr::SUB, std::move(x), std::move(y)); }
+inline wexpr operator*(wexpr x, wexpr y) { return wexpr(wexpr::MUL, std::move(x), std::move(y)); }
+inline wexpr operator&(wexpr x, wexpr y) { return wexpr(wexpr::AND, std::move(x), std::move(y)); }
+inline wexpr operator~(wexpr x) { return wexpr(wexpr::NOT, std::move(x)); }
+
+// the bit gadgets (core.hpp:789-852)
+inline witness_machine::wref witness_machine::bitwise_xor(const wref &x, const wref &y) { return eval(x + y - (x & y) * K(2)); }
+inline witness_machine::wref witness_machine::bitwise_xnor(const wref &x, const wref &y) { return eval(~(x + y - (x & y) * K(2))); }
+inline witness_machine::wref witness_machine::bitwise_eq(const bitvec &x, const bitvec &y) {
+    wref eq = bitwise_xnor(x[0], y[0]);
+    for (size_t i = 1; i < x.size(); i++) eq = eval(eq & bitwise_xnor(x[i], y[i]));
+    return eq;
+}
+inline std::pair<witness_machine::wref, witness_machine::wref> witness_machine::bitwise_gt(const bitvec &x, const bitvec &y, bool is_signed) {
+    const size_t msb = x.size() - 1;
+    wref gt, eq;
+    if (is_signed) gt = eval(~x[msb] & y[msb]);
+    else gt = eval(x[msb] & ~y[msb]);
+    eq = bitwise_xnor(x[msb], y[msb]);
+    for (size_t i = msb; i-- > 0;) {
+        wref same = bitwise_xnor(x[i], y[i]);
+        gt = eval(gt + (eq & x[i] & ~y[i]));
+        eq = eval(eq & same);
+    }
+    return std::make_pair(std::move(gt), std::move(eq));
+}
+// idivide_qr (core.hpp:692-712): q, r with q*y + r tied to x (the caller range-checks q and r)
+inline std::pair<witness_machine::wref, witness_machine::wref> witness_machine::idivide_qr(const wref &x, const wref &y) {
+    const Fr xv = x.val(), yv = y.val();
+    if (xv.v[2] | xv.v[3] | yv.v[2] | yv.v[3]) throw std::invalid_argument("wat: division operands beyond 128 bits");
+    const unsigned __int128 xn = ((unsigned __int128)xv.v[1] << 64) | xv.v[0], yn = ((unsigned __int128)yv.v[1] << 64) | yv.v[0];
+    if (!yn) throw std::invalid_argument("wat: integer divide by zero");
+    const unsigned __int128 qn = xn / yn, rn = xn % yn;
+    wref q = acquire(Fr{{(uint64_t)qn, (uint64_t)(qn >> 64), 0, 0}});
+    wref r = acquire(Fr{{(uint64_t)rn, (uint64_t)(rn >> 64), 0, 0}});
+    wref tmp = eval(q * y + r);
+    constrain_equal(tmp.id(), x.id());
+    return std::make_pair(std::move(q), std::move(r));
+}
 
 // ---- front end ------------------------------------------------------------------------------------------------
 class wat_program {
@@ -281,23 +532,74 @@ public:
     // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
     void run(witness_machine &m, wat_stats &st) const {
         const sexpr &f = *funcs_.at(start_);
+        run_state rs{m, st, {}};
         for (size_t i = 2; i < f.list.size(); i++) {
             const std::string &h = f.list[i].head();
             if (h == "param" || h == "result" || h == "local" || h == "type") {
                 if (h != "type" && f.list[i].list.size() > 1) throw std::invalid_argument("wat: _start with parameters / locals is not supported");
                 continue;
             }
-            value leftover = eval(f.list[i], m, st);
-            drop(leftover, m);                                // a value nobody consumed dies with the frame
+            exec(f.list[i], rs);
+            while (!rs.stack.empty()) rs.stack.pop_back();    // a value nobody consumed dies with the frame
         }
         st.linear_constraints = m.draws();
         st.violated_constraints = m.violated();
+        st.quadratic_slots = m.slots_made();
+        st.linear_witnesses = m.linear_released();
     }
 
 private:
-    using wid = witness_machine::wid;
-    // a stack value: nothing, a literal, or the bit witnesses of a 64-bit result (decomposed_bits, least significant first)
-    struct value { bool present = false, bits = false; uint64_t v = 0; std::vector<wid> b; };   // v is kept reduced to the value's width
+    using wref = witness_machine::wref;
+    using bitvec = witness_machine::bitvec;
+    // stack_value (stack_value.hpp:84-110) restricted to what the integer subset puts on the stack: a native number
+    // (tagged i32 / i64 like native_numeric), one witness, or the bit witnesses of a value.  Moving a value moves the
+    // witness handle and COPIES the bits (see bitvec), which is what keeps popped operand bits alive until a handler returns.
+    struct value {
+        enum kind_t : uint8_t { NUM, WIT, BITS } kind = NUM;
+        bool is64 = false;
+        uint64_t num = 0;
+        wref wit;
+        bitvec bits;
+        value() = default;
+        value(value &&) = default;
+        value &operator=(value &&) = default;
+        value(const value &) = delete;
+        static value u32(uint32_t v) { value r; r.num = v; return r; }
+        static value u64(uint64_t v) { value r; r.is64 = true; r.num = v; return r; }
+        static value of(wref w) { value r; r.kind = WIT; r.wit = std::move(w); return r; }
+        static value of(bitvec b) { value r; r.kind = BITS; r.bits = b; return r; }
+        uint32_t as_u32() const { return (uint32_t)num; }
+        uint64_t as_u64() const { return num; }
+    };
+    struct run_state {
+        witness_machine &m;
+        wat_stats &st;
+        std::vector<value> stack;
+        void push(value v) { stack.push_back(std::move(v)); }
+        value pop() {
+            if (stack.empty()) throw std::invalid_argument("wat: operand stack underflow");
+            value top = std::move(stack.back());
+            stack.pop_back();
+            return top;
+        }
+        // nonbatch_context.hpp:249-316
+        uint64_t make_numeric(value s) {
+            if (s.kind == value::NUM) return s.num;
+            if (s.kind == value::WIT) return s.wit.val().v[0];
+            return witness_machine::bit_compose_constant(s.bits);
+        }
+        wref make_witness(value s) {
+            if (s.kind == value::NUM) return m.acquire(lgr::host::from_u64(s.is64 ? s.as_u64() : s.as_u32()));
+            if (s.kind == value::WIT) return std::move(s.wit);
+            return m.bit_compose(s.bits);
+        }
+        bitvec make_decomposed(value s, size_t nbits) {
+            if (s.kind == value::NUM) return m.bit_decompose_constant(s.as_u64(), nbits);
+            if (s.kind == value::WIT) return m.bit_decompose(s.wit, nbits);
+            return s.bits;
+        }
+    };
+
     static std::string unquote(const std::string &s) { return (s.size() >= 2 && s.front() == '"') ? s.substr(1, s.size() - 2) : s; }
     static uint64_t parse_i64(const std::string &t) {
         std::string s;
@@ -325,113 +627,352 @@ private:
         const uint64_t u = (uint64_t)acc;
         return neg ? (uint64_t)(0 - u) : u;
     }
-    static value concrete(uint64_t v) { value r; r.present = true; r.v = v; return r; }
-    static value decomposed(uint64_t v, std::vector<wid> b) { value r; r.present = r.bits = true; r.v = v; r.b = std::move(b); return r; }
-    // ~decomposed_bits (core.hpp:100-105): most significant bit first
-    static void drop(value &a, witness_machine &m) {
-        for (size_t i = a.b.size(); i-- > 0;) m.release(a.b[i]);
-        a.b.clear();
-    }
-    // make_witness (nonbatch_context.hpp:275-299): a literal becomes a bare witness, bits are recomposed.  The bits do
-    // NOT die here: decomposed_bits has a destructor and therefore no move constructor, so the popped stack value the
-    // opcode handler holds keeps a copy until the handler returns -- after its witnesses, first operand first (sx is
-    // declared after sy).
-    static wid make_witness(const value &a, witness_machine &m, wat_stats &st) {
-        st.linear_witnesses++;
-        return a.bits ? m.compose(a.b) : m.acquire(lgr::host::from_u64(a.v));
-    }
-    // i32_private_const / i64_private_const (env.hpp:166-188): a fresh witness with a range check of its width
-    static value private_const(uint64_t v, int width, witness_machine &m, wat_stats &st) {
-        st.private_consts++;
-        st.linear_witnesses++;
-        st.quadratic_slots += (uint64_t)width;
-        const wid x = m.acquire(lgr::host::from_u64(v));
-        std::vector<wid> bits = m.decompose(x, width);
-        m.release(x);
-        return decomposed(v, std::move(bits));
+    static value numeric(bool is64, uint64_t v) { return is64 ? value::u64(v) : value::u32((uint32_t)v); }
+    static int64_t sext(uint64_t v, int w) { return w == 64 ? (int64_t)v : (int64_t)(int32_t)(uint32_t)v; }
+
+    // ---- the integer instructions (interpreter_impl.hpp:155-1309).  Locals are declared in the reference's order: that
+    // order is the release order of whatever they still hold when the handler returns.
+    enum class op { clz, ctz, popcnt, add, sub, mul, div, rem, and_, or_, xor_, shl, shr, rotl, rotr, eqz, eq, ne, lt, gt, le, ge,
+                    extend8, extend16, extend32, extend_i32, wrap };
+
+    static void unary(op o, int w, bool sgn, run_state &rs) {
+        witness_machine &m = rs.m;
+        value sx = rs.pop();
+        const uint64_t mask = w == 64 ? ~0ULL : 0xFFFFFFFFULL;
+        if (sx.kind == value::NUM) {
+            const uint64_t x = sx.num & mask;
+            switch (o) {
+            case op::clz: rs.push(value::u32(x ? (uint32_t)(__builtin_clzll(x) - (64 - w)) : (uint32_t)w)); break;
+            case op::ctz: rs.push(value::u32(x ? (uint32_t)__builtin_ctzll(x) : (uint32_t)w)); break;
+            case op::popcnt: rs.push(value::u32((uint32_t)__builtin_popcountll(x))); break;
+            case op::eqz: rs.push(numeric(w == 64, x == 0)); break;
+            case op::extend8: rs.push(numeric(w == 64, (uint64_t)(int64_t)(int8_t)x)); break;
+            case op::extend16: rs.push(numeric(w == 64, w == 64 ? (uint64_t)(uint16_t)x : (uint64_t)(int64_t)(int16_t)x)); break;   // (sic: the i64 form zero-extends, :1208)
+            case op::extend32: rs.push(value::u64((uint64_t)(int64_t)(int32_t)x)); break;
+            case op::extend_i32: rs.push(value::u64(sgn ? (uint64_t)(int64_t)(int32_t)(uint32_t)sx.num : (uint64_t)(uint32_t)sx.num)); break;
+            case op::wrap: rs.push(value::u32((uint32_t)sx.num)); break;
+            default: throw std::logic_error("wat: not a unary instruction");
+            }
+            return;
+        }
+        rs.st.arithmetic_ops++;
+        const size_t nb = (size_t)w, msb = nb - 1;
+        switch (o) {
+        case op::clz: case op::ctz: {                          // :155-227: running "all zero so far" flag, summed
+            bitvec bits = rs.make_decomposed(std::move(sx), nb);
+            const bool up = o == op::ctz;
+            wref acc = m.eval(~bits[up ? 0 : msb]);
+            wref cont = m.duplicate(acc);
+            for (size_t j = 1; j < nb; j++) {
+                const size_t i = up ? j : msb - j;
+                cont = m.eval(cont & ~bits[i]);
+                acc = m.eval(acc + cont);
+            }
+            rs.push(value::of(std::move(acc)));
+            break;
+        }
+        case op::popcnt: {                                     // :230-262
+            bitvec bits = rs.make_decomposed(std::move(sx), nb);
+            wref acc = m.eval(witness_machine::K(0));
+            for (size_t i = 0; i < nb; i++) acc = m.eval(acc + bits[i]);
+            rs.push(value::of(std::move(acc)));
+            break;
+        }
+        case op::eqz: {                                        // :889-916
+            bitvec x = rs.make_decomposed(std::move(sx), nb);
+            wref acc = m.eval(~x[0]);
+            for (size_t i = 1; i < nb; i++) acc = m.eval(acc & ~x[i]);
+            rs.push(value::of(std::move(acc)));
+            break;
+        }
+        case op::extend8: case op::extend16: case op::extend32: {   // :1164-1255: the sign bit cloned upwards
+            const size_t from = o == op::extend8 ? 8 : (o == op::extend16 ? 16 : 32);
+            bitvec bits = rs.make_decomposed(std::move(sx), nb);
+            bits.drop_msb(nb - from);
+            for (size_t i = from; i < nb; i++) bits.push_back(m.duplicate(bits[from - 1]));
+            rs.push(value::of(bits));
+            break;
+        }
+        case op::extend_i32: {                                 // :1258-1289
+            bitvec bits = rs.make_decomposed(std::move(sx), 32);
+            if (sgn) {
+                for (size_t i = 32; i < 64; i++) bits.push_back(m.duplicate(bits[31]));
+            } else {
+                wref zero = m.eval(witness_machine::K(0));
+                bits.push_msb(zero, 32);
+            }
+            rs.push(value::of(bits));
+            break;
+        }
+        case op::wrap: {                                       // :1292-1309
+            bitvec bits = rs.make_decomposed(std::move(sx), 64);
+            bits.drop_msb(32);
+            rs.push(value::of(bits));
+            break;
+        }
+        default: throw std::logic_error("wat: not a unary instruction");
+        }
     }
 
-    // exec_inn_mul / exec_inn_add / exec_inn_sub on operands of `width` = 32 or 64 bits (interpreter_impl.hpp:262-391)
-    value binop(const std::string &op, int width, value a, value b, witness_machine &m, wat_stats &st) const {
-        if (!a.present || !b.present) throw std::invalid_argument("wat: " + op + " needs two operands");
-        const uint64_t mask = width == 64 ? ~0ULL : 0xFFFFFFFFULL;
-        const std::string f = op.substr(4);
-        if (!a.bits && !b.bits) {
-            return concrete((f == "mul" ? a.v * b.v : (f == "add" ? a.v + b.v : a.v - b.v)) & mask);
+    // shl / shr_s / shr_u / rotl / rotr (:706-886): the count is read off its witnesses (no constraint), the bits are re-wired
+    static void shift(op o, int w, bool sgn, run_state &rs) {
+        witness_machine &m = rs.m;
+        value cnt = rs.pop();
+        value sx = rs.pop();
+        const size_t nb = (size_t)w, msb = nb - 1;
+        const uint32_t n = (uint32_t)rs.make_numeric(std::move(cnt)) % (uint32_t)nb;
+        if (sx.kind == value::NUM) {
+            const uint64_t mask = w == 64 ? ~0ULL : 0xFFFFFFFFULL, x = sx.num & mask;
+            uint64_t r = 0;
+            switch (o) {
+            case op::shl: r = x << n; break;
+            case op::shr: r = sgn ? (uint64_t)(sext(x, w) >> n) : x >> n; break;
+            case op::rotl: r = n ? (x << n) | (x >> (nb - n)) : x; break;
+            case op::rotr: r = n ? (x >> n) | (x << (nb - n)) : x; break;
+            default: throw std::logic_error("wat: not a shift");
+            }
+            rs.push(numeric(w == 64, r & mask));
+            return;
         }
-        st.arithmetic_ops++;
-        const uint64_t av = a.v, bv = b.v;
-        const wid x = make_witness(a, m, st), y = make_witness(b, m, st);
-        if (f == "mul") {
-            const unsigned __int128 p = (unsigned __int128)av * bv;
-            const wid z = m.acquire(Fr{{(uint64_t)p, (uint64_t)(p >> 64), 0, 0}});
-            m.quadratic(z, x, y);
-            st.quadratic_slots += 2 * (uint64_t)width + 1;
-            std::vector<wid> bits = m.decompose(z, 2 * width);
-            for (int i = 2 * width - 1; i >= width; i--) m.release(bits[(size_t)i]);      // drop_msb(width)
-            bits.resize((size_t)width);
-            m.release(z); m.release(y); m.release(x);                         // big_result, y, x leave scope in that order,
-            drop(a, m); drop(b, m);                                           // then the popped operands: sx (declared last), sy
-            return decomposed((uint64_t)p & mask, std::move(bits));
-        }
-        // add: s = x + y;  sub: s = (2^width - y) + x (never negative)
-        const bool sub = f == "sub";
-        const unsigned __int128 sv = sub ? ((unsigned __int128)av + (((unsigned __int128)1) << width) - bv) : ((unsigned __int128)av + bv);
-        const wid sw = m.acquire(Fr{{(uint64_t)sv, (uint64_t)(sv >> 64), 0, 0}});
-        st.linear_witnesses++;
-        const Fr r = m.draw();
-        m.coef_sub(sw, r);
-        if (sub) {                                                            // y takes -r, the constant adds 2^width * r, x takes +r
-            m.coef_sub(y, r);
-            m.const_add(witness_machine::shl(r, width));
-            m.coef_add(x, r);
+        rs.st.arithmetic_ops++;
+        bitvec x = rs.make_decomposed(std::move(sx), nb);
+        if (o == op::shl) {
+            wref zero = m.eval(witness_machine::K(0));
+            x.push_lsb(zero, n);
+            x.drop_msb(n);
+            rs.push(value::of(x));
+        } else if (o == op::shr) {
+            bitvec unused;
+            if (sgn) {
+                wref pad = m.duplicate(x[msb]);
+                x.drop_lsb(n);
+                x.push_msb(pad, n);
+            } else {
+                wref zero = m.eval(witness_machine::K(0));
+                x.drop_lsb(n);
+                x.push_msb(zero, n);
+            }
+            rs.push(value::of(x));
         } else {
-            m.coef_add(x, r);
-            m.coef_add(y, r);
+            bitvec moved;
+            if (o == op::rotl) {
+                for (size_t i = 0; i < n; i++) moved.push_back(std::move(x[nb - n + i]));
+                for (size_t i = n; i < nb; i++) moved.push_back(std::move(x[i - n]));
+            } else {
+                for (size_t i = n; i < nb; i++) moved.push_back(std::move(x[i]));
+                for (size_t i = 0; i < n; i++) moved.push_back(std::move(x[i]));
+            }
+            rs.push(value::of(moved));
         }
-        st.quadratic_slots += (uint64_t)width + 1;
-        std::vector<wid> bits = m.decompose(sw, width + 1);
-        m.release(bits[(size_t)width]);                                       // drop_msb(1)
-        bits.resize((size_t)width);
-        m.release(sw); m.release(y); m.release(x);
-        drop(a, m); drop(b, m);
-        return decomposed((uint64_t)sv & mask, std::move(bits));
     }
 
-    value eval(const sexpr &e, witness_machine &m, wat_stats &st) const {
+    static void binary(op o, int w, bool sgn, run_state &rs) {
+        witness_machine &m = rs.m;
+        value sy = rs.pop();
+        value sx = rs.pop();
+        const size_t nb = (size_t)w, msb = nb - 1;
+        const uint64_t mask = w == 64 ? ~0ULL : 0xFFFFFFFFULL;
+        if (sx.kind == value::NUM && sy.kind == value::NUM) {
+            const uint64_t x = sx.num & mask, y = sy.num & mask;
+            const int64_t xs = sext(x, w), ys = sext(y, w);
+            const bool is64 = w == 64;
+            switch (o) {
+            case op::add: rs.push(numeric(is64, (x + y) & mask)); break;
+            case op::sub: rs.push(numeric(is64, (x - y) & mask)); break;
+            case op::mul: rs.push(numeric(is64, (x * y) & mask)); break;
+            case op::div: case op::rem: {
+                if (!y) throw std::invalid_argument("wat: integer divide by zero");
+                uint64_t r;
+                if (sgn) {
+                    if (ys == -1) r = o == op::div ? (uint64_t)(0 - (uint64_t)xs) : 0;    // (INT_MIN / -1 traps in WASM; wraps here)
+                    else r = (uint64_t)(o == op::div ? xs / ys : xs % ys);
+                } else r = o == op::div ? x / y : x % y;
+                rs.push(numeric(is64, r & mask));
+                break;
+            }
+            case op::and_: rs.push(numeric(is64, x & y)); break;
+            case op::or_: rs.push(numeric(is64, x | y)); break;
+            case op::xor_: rs.push(numeric(is64, x ^ y)); break;
+            case op::eq: rs.push(value::u32(x == y)); break;
+            case op::ne: rs.push(value::u32(x != y)); break;
+            case op::lt: rs.push(numeric(is64, sgn ? xs < ys : x < y)); break;
+            case op::gt: rs.push(numeric(is64, sgn ? xs > ys : x > y)); break;
+            case op::le: rs.push(numeric(is64, sgn ? xs <= ys : x <= y)); break;
+            case op::ge: rs.push(numeric(is64, sgn ? xs >= ys : x >= y)); break;
+            default: throw std::logic_error("wat: not a binary instruction");
+            }
+            return;
+        }
+        rs.st.arithmetic_ops++;
+        switch (o) {
+        case op::add: case op::sub: case op::mul: {            // :265-392: the overflowing result, decomposed, top bits dropped
+            wref x = rs.make_witness(std::move(sx));
+            wref y = rs.make_witness(std::move(sy));
+            Fr pow2 = witness_machine::zero();
+            pow2.v[nb >> 6] = 1ULL << (nb & 63);               // 2^nb
+            wref wide = o == op::add ? m.eval(x + y) : (o == op::sub ? m.eval(witness_machine::K(pow2) - y + x) : m.eval(x * y));
+            const size_t extra = o == op::mul ? nb : 1;
+            bitvec bits = m.bit_decompose(wide, nb + extra);
+            bits.drop_msb(extra);
+            rs.push(value::of(bits));
+            break;
+        }
+        case op::div: case op::rem: divide(o, nb, sgn, sx, sy, rs); break;
+        case op::and_: case op::or_: case op::xor_: {          // :597-703: bit by bit
+            bitvec x = rs.make_decomposed(std::move(sx), nb);
+            bitvec y = rs.make_decomposed(std::move(sy), nb);
+            bitvec out;
+            for (size_t i = 0; i < nb; i++) {
+                if (o == op::and_) out.push_back(m.eval(x[i] & y[i]));
+                else if (o == op::or_) out.push_back(m.eval(x[i] + y[i] - (x[i] & y[i])));
+                else { wref b = m.bitwise_xor(x[i], y[i]); out.push_back(std::move(b)); }
+            }
+            rs.push(value::of(out));
+            break;
+        }
+        case op::eq: case op::ne: {                            // :919-978
+            bitvec x = rs.make_decomposed(std::move(sx), nb);
+            bitvec y = rs.make_decomposed(std::move(sy), nb);
+            wref r = o == op::eq ? m.bitwise_eq(x, y) : m.eval(~m.bitwise_eq(x, y));
+            rs.push(value::of(std::move(r)));
+            break;
+        }
+        case op::lt: case op::gt: case op::le: case op::ge: {  // :981-1161: (gt, eq) scanned from the top bit down
+            bitvec x = rs.make_decomposed(std::move(sx), nb);
+            bitvec y = rs.make_decomposed(std::move(sy), nb);
+            std::pair<wref, wref> ge = m.bitwise_gt(x, y, sgn);
+            if (o == op::gt) { rs.push(value::of(std::move(ge.first))); break; }
+            wref r = o == op::lt ? m.eval(~(ge.first + ge.second)) : (o == op::le ? m.eval(~ge.first) : m.eval(ge.first + ge.second));
+            rs.push(value::of(std::move(r)));
+            break;
+        }
+        default: throw std::logic_error("wat: not a binary instruction");
+        }
+        (void)msb;
+    }
+
+    // div_s / div_u / rem_s / rem_u (:395-594): quotient and remainder as fresh witnesses with q*y + r = x, both range-checked,
+    // r < y by the comparison gadget; the signed forms divide absolute values and put the sign back
+    static void divide(op o, size_t nb, bool sgn, value &sx, value &sy, run_state &rs) {
+        witness_machine &m = rs.m;
+        const size_t msb = nb - 1;
+        wref x = rs.make_witness(std::move(sx));
+        wref y = rs.make_witness(std::move(sy));
+        if (!sgn) {
+            std::pair<wref, wref> qr = m.idivide_qr(x, y);
+            { bitvec range_q = m.bit_decompose(qr.first, nb); }
+            bitvec by = m.bit_decompose(y, nb);
+            bitvec br = m.bit_decompose(qr.second, nb);
+            std::pair<wref, wref> ge = m.bitwise_gt(by, br, sgn);
+            m.assert_const(ge.first, 1);
+            m.assert_const(ge.second, 0);
+            rs.push(value::of(std::move(o == op::div ? qr.first : qr.second)));
+            return;
+        }
+        bitvec bx = m.bit_decompose(x, nb);
+        bitvec by = m.bit_decompose(y, nb);
+        Fr pow2 = witness_machine::zero();
+        pow2.v[nb >> 6] = 1ULL << (nb & 63);
+        const auto K = [](const Fr &v) { return witness_machine::K(v); };
+        wref abs_x = m.eval(bx[msb] * (K(pow2) - x) + ~bx[msb] * x);
+        wref abs_y = m.eval(by[msb] * (K(pow2) - y) + ~by[msb] * y);
+        std::pair<wref, wref> qr = m.idivide_qr(abs_x, abs_y);
+        { bitvec range_q = m.bit_decompose(qr.first, nb); }
+        bitvec abs_y_bits = m.bit_decompose(abs_y, nb);
+        bitvec br = m.bit_decompose(qr.second, nb);
+        std::pair<wref, wref> ge = m.bitwise_gt(abs_y_bits, br, sgn);
+        m.assert_const(ge.first, 1);
+        m.assert_const(ge.second, 0);
+        if (o == op::div) {
+            wref negative = m.bitwise_xor(bx[msb], by[msb]);
+            wref ovf_q = m.eval(K(pow2) - qr.first);
+            bitvec bneg_q = m.bit_decompose(ovf_q, nb + 1);
+            bneg_q.drop_msb(1);
+            wref neg_q = m.bit_compose(bneg_q);
+            wref res_q = m.eval(negative * neg_q + ~negative * qr.first);
+            rs.push(value::of(std::move(res_q)));
+        } else {
+            wref ovf_r = m.eval(K(pow2) - qr.second);
+            bitvec bneg_r = m.bit_decompose(ovf_r, nb + 1);
+            bneg_r.drop_msb(1);
+            wref neg_r = m.bit_compose(bneg_r);
+            wref res_r = m.eval(bx[msb] * neg_r + ~bx[msb] * qr.second);
+            rs.push(value::of(std::move(res_r)));
+        }
+    }
+
+    struct opinfo { op o; int arity; bool sgn; };
+    static bool lookup(const std::string &name, opinfo &out) {
+        static const std::map<std::string, opinfo> table = {
+            {"clz", {op::clz, 1, false}}, {"ctz", {op::ctz, 1, false}}, {"popcnt", {op::popcnt, 1, false}}, {"eqz", {op::eqz, 1, false}},
+            {"extend8_s", {op::extend8, 1, true}}, {"extend16_s", {op::extend16, 1, true}}, {"extend32_s", {op::extend32, 1, true}},
+            {"extend_i32_s", {op::extend_i32, 1, true}}, {"extend_i32_u", {op::extend_i32, 1, false}}, {"wrap_i64", {op::wrap, 1, false}},
+            {"add", {op::add, 2, false}}, {"sub", {op::sub, 2, false}}, {"mul", {op::mul, 2, false}},
+            {"div_s", {op::div, 2, true}}, {"div_u", {op::div, 2, false}}, {"rem_s", {op::rem, 2, true}}, {"rem_u", {op::rem, 2, false}},
+            {"and", {op::and_, 2, false}}, {"or", {op::or_, 2, false}}, {"xor", {op::xor_, 2, false}},
+            {"shl", {op::shl, 3, false}}, {"shr_s", {op::shr, 3, true}}, {"shr_u", {op::shr, 3, false}}, {"rotl", {op::rotl, 3, false}}, {"rotr", {op::rotr, 3, false}},
+            {"eq", {op::eq, 2, false}}, {"ne", {op::ne, 2, false}},
+            {"lt_s", {op::lt, 2, true}}, {"lt_u", {op::lt, 2, false}}, {"gt_s", {op::gt, 2, true}}, {"gt_u", {op::gt, 2, false}},
+            {"le_s", {op::le, 2, true}}, {"le_u", {op::le, 2, false}}, {"ge_s", {op::ge, 2, true}}, {"ge_u", {op::ge, 2, false}},
+        };
+        const auto it = table.find(name);
+        if (it == table.end()) return false;
+        out = it->second;
+        return true;
+    }
+
+    // one folded instruction: operands first (each leaves one value on the stack), then the instruction itself
+    void exec(const sexpr &e, run_state &rs) const {
         if (!e.is_list) throw std::invalid_argument("wat: only folded instructions are supported (" + e.atom + ")");
         const std::string &h = e.head();
         if (h == "i64.const" || h == "i32.const") {
             if (e.list.size() != 2) throw std::invalid_argument("wat: " + h + " takes one literal");
             const uint64_t v = parse_i64(e.list[1].atom);
             if (h == "i32.const" && v > 0xFFFFFFFFULL && v < 0xFFFFFFFF80000000ULL) throw std::invalid_argument("wat: integer literal out of range " + e.list[1].atom);
-            return concrete(h == "i32.const" ? (v & 0xFFFFFFFFULL) : v);
+            rs.push(numeric(h[1] == '6', h == "i32.const" ? (v & 0xFFFFFFFFULL) : v));
+            return;
         }
-        if (h == "i64.mul" || h == "i64.add" || h == "i64.sub" || h == "i32.mul" || h == "i32.add" || h == "i32.sub") {
-            if (e.list.size() != 3) throw std::invalid_argument("wat: " + h + " takes two folded operands");
-            value a = eval(e.list[1], m, st);
-            value b = eval(e.list[2], m, st);
-            return binop(h, h[1] == '3' ? 32 : 64, std::move(a), std::move(b), m, st);
+        if (h.size() > 4 && (h.compare(0, 4, "i32.") == 0 || h.compare(0, 4, "i64.") == 0)) {
+            opinfo oi;
+            if (!lookup(h.substr(4), oi)) throw std::invalid_argument("wat: unsupported instruction " + h);
+            const int operands = oi.arity == 1 ? 1 : 2;
+            if ((int)e.list.size() != 1 + operands) throw std::invalid_argument("wat: " + h + " takes " + (operands == 1 ? "one folded operand" : "two folded operands"));
+            const size_t depth = rs.stack.size();
+            for (int i = 1; i <= operands; i++) exec(e.list[(size_t)i], rs);
+            if (rs.stack.size() != depth + (size_t)operands) throw std::invalid_argument("wat: " + h + " needs " + (operands == 1 ? "one operand" : "two operands"));
+            const int w = h[1] == '3' ? 32 : 64;
+            if (oi.arity == 1) unary(oi.o, w, oi.sgn, rs);
+            else if (oi.arity == 3) shift(oi.o, w, oi.sgn, rs);
+            else binary(oi.o, w, oi.sgn, rs);
+            return;
         }
         if (h == "call") {
             if (e.list.size() < 2) throw std::invalid_argument("wat: call without a target");
             const auto it = imports_.find(e.list[1].atom);
             if (it == imports_.end()) throw std::invalid_argument("wat: call of a non-imported function is not supported (" + e.list[1].atom + ")");
-            std::vector<value> args;
-            for (size_t i = 2; i < e.list.size(); i++) args.push_back(eval(e.list[i], m, st));
-            if (it->second == "i64_private_const" || it->second == "i32_private_const") {
-                if (args.size() != 1 || args[0].bits) throw std::invalid_argument("wat: " + it->second + " takes one constant");
+            const size_t depth = rs.stack.size();
+            for (size_t i = 2; i < e.list.size(); i++) exec(e.list[i], rs);
+            const size_t nargs = rs.stack.size() - depth;
+            witness_machine &m = rs.m;
+            if (it->second == "i64_private_const" || it->second == "i32_private_const") {   // env.hpp:166-188: a fresh witness, range-checked by its decomposition
+                if (nargs != 1 || rs.stack.back().kind != value::NUM) throw std::invalid_argument("wat: " + it->second + " takes one constant");
                 const int width = it->second[1] == '3' ? 32 : 64;
-                return private_const(width == 32 ? (args[0].v & 0xFFFFFFFFULL) : args[0].v, width, m, st);
+                const value lit = rs.pop();
+                rs.st.private_consts++;
+                wref x = m.acquire(lgr::host::from_u64(width == 32 ? lit.as_u32() : lit.as_u64()));
+                bitvec checked = m.bit_decompose(x, (size_t)width);
+                rs.push(value::of(checked));
+                return;
             }
             if (it->second == "assert_equal") {                                // env.hpp:64-77
-                if (args.size() != 2) throw std::invalid_argument("wat: assert_equal takes two operands");
-                st.asserts++;
-                const wid wx = make_witness(args[0], m, st), wy = make_witness(args[1], m, st);
-                m.equal(wx, wy);
-                m.release(wy); m.release(wx);
-                drop(args[0], m); drop(args[1], m);
-                return value{};
+                if (nargs != 2) throw std::invalid_argument("wat: assert_equal takes two operands");
+                rs.st.asserts++;
+                value sy = rs.pop();
+                value sx = rs.pop();
+                wref wx = rs.make_witness(std::move(sx));
+                wref wy = rs.make_witness(std::move(sy));
+                m.assert_equal(wx, wy);
+                return;
             }
             throw std::invalid_argument("wat: env." + it->second + " is not supported by the bounded front end");
         }
