@@ -29,7 +29,8 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "refctx_cpu")
 CASES = [("i64_mul", 8192), ("i64_mul3", 256), ("vbn", 256)]
 # programs given as text: the repo's own tests/golden/mul64.wat and arith32.wat (products, sums, differences, nested forms,
 # literal operands; 64- and 32-bit) go through the reference's interpreter as a token stream (tests/refctx_util.py: wat_to_tokens)
-WAT_CASES = [("mul64", os.path.join(HERE, "mul64.wat"), 256), ("arith32", os.path.join(HERE, "arith32.wat"), 256)]
+WAT_CASES = [("mul64", os.path.join(HERE, "mul64.wat"), 256), ("arith32", os.path.join(HERE, "arith32.wat"), 256),
+             ("intops", os.path.join(HERE, "intops.wat"), 256)]       # every other integer instruction (tests/golden/make_intops_wat.py)
 
 
 def zb64(hexstr):

@@ -11,8 +11,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-CASES = ["i64_mul_k8192", "i64_mul3_k256", "vbn_k256", "mul64_k256", "arith32_k256"]
-WAT_TEXT = {"mul64": os.path.join(HERE, "golden", "mul64.wat"), "arith32": os.path.join(HERE, "golden", "arith32.wat")}          # cases whose program is a .wat file of the repo
+CASES = ["i64_mul_k8192", "i64_mul3_k256", "vbn_k256", "mul64_k256", "arith32_k256", "intops_k256"]
+WAT_TEXT = {"mul64": os.path.join(HERE, "golden", "mul64.wat"), "arith32": os.path.join(HERE, "golden", "arith32.wat"),
+            "intops": os.path.join(HERE, "golden", "intops.wat")}          # cases whose program is a .wat file of the repo
 REF_BIN_CPU = os.path.join(ROOT, "oracle", "_ref", "refctx_cpu")
 REF_BIN_CUDA = os.path.join(ROOT, "oracle", "_ref", "refctx_cuda")
 
@@ -187,3 +188,86 @@ def reference_verifier(binary, case, proof_path, tmpdir):
     prog, k, _ = harness_args(case, tmpdir)
     res = subprocess.run([binary, "verify:" + proof_path, prog, k], capture_output=True, text=True, timeout=900)
     return res.returncode, (res.stdout + res.stderr)[-2000:]
+
+
+# ---- WebAssembly integer semantics (for expected values in generated programs) and a random program generator
+UNARY_OPS = ["clz", "ctz", "popcnt", "eqz", "extend8_s", "extend16_s"]
+BINARY_OPS = ["add", "sub", "mul", "and", "or", "xor", "shl", "shr_s", "shr_u", "rotl", "rotr", "eq", "ne",
+              "lt_s", "lt_u", "gt_s", "gt_u", "le_s", "le_u", "ge_s", "ge_u", "div_s", "div_u", "rem_s", "rem_u"]
+
+
+def wasm_op(op, w, a, b=None):
+    """value of iW.op on unsigned operands a, b < 2^w (None where WebAssembly traps)"""
+    M = 1 << w
+    s = lambda v: v - M if v >> (w - 1) else v
+    if op == "clz": return w - a.bit_length()
+    if op == "ctz": return w if a == 0 else (a & -a).bit_length() - 1
+    if op == "popcnt": return bin(a).count("1")
+    if op == "eqz": return int(a == 0)
+    if op in ("extend8_s", "extend16_s", "extend32_s"):
+        n = int(op[6:-2]); v = a & ((1 << n) - 1)
+        return (v - (1 << n) if v >> (n - 1) else v) % M
+    if op == "add": return (a + b) % M
+    if op == "sub": return (a - b) % M
+    if op == "mul": return (a * b) % M
+    if op == "and": return a & b
+    if op == "or": return a | b
+    if op == "xor": return a ^ b
+    n = b % w if b is not None else 0
+    if op == "shl": return (a << n) % M
+    if op == "shr_u": return a >> n
+    if op == "shr_s": return (s(a) >> n) % M
+    if op == "rotl": return ((a << n) | (a >> (w - n))) % M if n else a
+    if op == "rotr": return ((a >> n) | (a << (w - n))) % M if n else a
+    if op == "eq": return int(a == b)
+    if op == "ne": return int(a != b)
+    if op[:2] in ("lt", "gt", "le", "ge"):
+        x, y = (s(a), s(b)) if op.endswith("_s") else (a, b)
+        return int({"lt": x < y, "gt": x > y, "le": x <= y, "ge": x >= y}[op[:2]])
+    if op in ("div_u", "rem_u"):
+        if b == 0: return None
+        return a // b if op == "div_u" else a % b
+    if op in ("div_s", "rem_s"):
+        x, y = s(a), s(b)
+        if y == 0 or (op == "div_s" and x == -(M >> 1) and y == -1): return None
+        if y == -(M >> 1): return None      # (the reference's gadget compares |y| = 2^(w-1) as a SIGNED number and rejects its own witness)
+        q = abs(x) // abs(y) * (1 if (x < 0) == (y < 0) else -1)
+        return (q if op == "div_s" else x - q * y) % M
+    raise ValueError(op)
+
+
+def _rand_operand(rng, w):
+    M = 1 << w
+    return rng.choice([0, 1, 2, 3, M - 1, M >> 1, (M >> 1) - 1, 1 << (w // 2), 0x80, 0xff7f, rng.getrandbits(w), rng.getrandbits(w), rng.getrandbits(7), M - 1 - rng.getrandbits(5)])
+
+
+def rand_int_expr(rng, depth, w, ops=None):
+    """(folded text, value) of a random expression of width w over every integer instruction: private and literal leaves,
+    results that live as bit vectors (arithmetic, bitwise, shifts) and as single witnesses (counts, comparisons) mixed freely"""
+    if depth == 0 or rng.random() < 0.2:
+        v = _rand_operand(rng, w)
+        lit = "(i%d.const %d)" % (w, v)
+        return ("(call $i%d_private_const %s)" % (w, lit) if rng.random() < 0.75 else lit), v
+    for _ in range(100):
+        op = rng.choice(ops or (UNARY_OPS + BINARY_OPS * 2))
+        ta, va = rand_int_expr(rng, depth - 1, w, ops)
+        if op in UNARY_OPS:
+            return "(i%d.%s %s)" % (w, op, ta), wasm_op(op, w, va)
+        tb, vb = rand_int_expr(rng, depth - 1, w, ops)
+        if op in ("div_s", "div_u", "rem_s", "rem_u") and "private" not in ta + tb:
+            continue                                            # (both concrete: plain host division; nothing to check)
+        v = wasm_op(op, w, va, vb)
+        if v is not None:
+            return "(i%d.%s %s %s)" % (w, op, ta, tb), v
+    raise RuntimeError("no valid expression found")
+
+
+WAT_HEAD_BOTH = ('(module (import "env" "i32_private_const" (func $i32_private_const (param i32) (result i32)))\n'
+                 '(import "env" "i64_private_const" (func $i64_private_const (param i64) (result i64)))\n'
+                 '(import "env" "assert_equal" (func $assert_equal (param i64 i64)))\n(func $t\n')
+
+
+def rand_int_program(rng, w, nexpr=3, depth=2, ops=None):
+    exprs = [rand_int_expr(rng, rng.randrange(1, depth + 1), w, ops) for _ in range(nexpr)]
+    rhs = lambda v: ("(i%d.const %d)" % (w, v)) if rng.random() < 0.5 else ("(call $i%d_private_const (i%d.const %d))" % (w, w, v))
+    return WAT_HEAD_BOTH + "".join("(call $assert_equal %s %s)\n" % (t, rhs(v)) for t, v in exprs) + WAT_TAIL, exprs

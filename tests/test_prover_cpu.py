@@ -365,6 +365,30 @@ def _rand_wat_expr(rng, depth):
     return "(i64.%s %s %s)" % (op, ta, tb), {"mul": va * vb, "add": va + vb, "sub": va - vb}[op] % M
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_wat_emitter_constraint_system_over_every_integer_instruction(pr, oracle, seed):
+    """needs no reference run: random trees over the whole integer instruction set (tests/refctx_util.py: rand_int_program,
+    expected values from WebAssembly's semantics).  Every assertion holds in the emitted constraint system -- the linear
+    combination with the drawn coefficients vanishes, every slot is a product -- and the CPU prover's three checks pass;
+    moving one expected value by one breaks exactly the linear test"""
+    import refctx_util as U
+    rng = random.Random(5100 + seed)
+    w = (32, 64)[seed & 1]
+    text, exprs = U.rand_int_program(rng, w, nexpr=3, depth=2)
+    _, st = _wat_check(pr, oracle, text, l=256, k=512)
+    assert st["violated_constraints"] == 0 and st["asserts"] == 3
+    t, v = exprs[rng.randrange(3)]
+    for rhs in ("(i%d.const %d)" % (w, v), "(call $i%d_private_const (i%d.const %d))" % (w, w, v)):
+        stmt = "(call $assert_equal %s %s)" % (t, rhs)
+        if stmt in text:
+            wrong = text.replace(stmt, "(call $assert_equal %s %s)" % (t, rhs.replace("const %d)" % v, "const %d)" % ((v + 1) % (1 << w)))), 1)
+            _, st_bad = _wat_check(pr, oracle, wrong, l=256, k=512, expect_valid=False)
+            assert st_bad["violated_constraints"] >= 1
+            break
+    else:
+        raise AssertionError("assertion text not found")
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_wat_emitter_on_random_expression_trees(pr, oracle, seed):
     """wrap-around semantics of nested products / sums / differences: every assertion against the value Python computes

@@ -140,10 +140,11 @@ def test_wat_emitter_reproduces_the_reference_rows_for_i64_mul(pr):
     _emitter_equals_reference_rows(pr, U.binop_wat("mul", U.I64_MUL_CASES[6:]), U.load("i64_mul3_k256"))
 
 
-@pytest.mark.parametrize("name", ["mul64", "arith32"])
+@pytest.mark.parametrize("name", ["mul64", "arith32", "intops"])
 def test_wat_emitter_reproduces_the_reference_rows_for_the_repo_programs(pr, name):
     """tests/golden/mul64.wat and arith32.wat: products, sums, differences, nested forms and literal operands in 64 and 32
-    bits (39 and 19 row events at l = 64)"""
+    bits (39 and 19 row events at l = 64); intops.wat: every other integer instruction -- bitwise, shifts, rotates,
+    comparisons, counts, division, extensions -- and forms that chain them (109 row events)"""
     st = U.load(name + "_k256")
     _emitter_equals_reference_rows(pr, open(U.WAT_TEXT[name]).read(), st)
 
@@ -178,26 +179,57 @@ def test_wat_emitter_against_the_reference_interpreter_on_random_programs(oracle
     k = rng.choice([256, 512])
     raw = U.run_reference_on_wat(text, k, seed_byte=seed + 1)
     assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    _emitter_equals_reference_rows(pr, text, _reference_rows(raw))
+
+
+def _reference_rows(raw):
     l = raw["l"]
     u32 = lambda h: np.frombuffer(bytes.fromhex(h), np.uint32)
-    st = {"fx": raw, "l": l, "kinds": raw["kinds"], "values": u32(raw["values"]).reshape(-1, l, 8), "coefs": u32(raw["coefs"]).reshape(-1, l, 8),
-          "const_sum": int.from_bytes(bytes.fromhex(raw["const_sum"]), "little")}
-    _emitter_equals_reference_rows(pr, text, st)
+    return {"fx": raw, "l": l, "kinds": raw["kinds"], "values": u32(raw["values"]).reshape(-1, l, 8), "coefs": u32(raw["coefs"]).reshape(-1, l, 8),
+            "const_sum": int.from_bytes(bytes.fromhex(raw["const_sum"]), "little")}
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("seed", range(12))
+def test_wat_emitter_against_the_reference_interpreter_on_every_integer_instruction(oracle, pr, seed):
+    """differential over the whole integer instruction set: random trees of clz / ctz / popcnt / eqz / extend / add / sub / mul /
+    and / or / xor / shifts / rotates / comparisons / div / rem with private and literal leaves -- so bit-vector results,
+    single-witness results and concrete numbers meet in every combination -- through the reference's interpreter + backend
+    and through the emitter: same rows, same coefficient rows, same const_sum, and the reference's verifier accepts"""
+    import random
+    rng = random.Random(7700 + seed)
+    w = (32, 64)[seed & 1]
+    text, _ = U.rand_int_program(rng, w, nexpr=rng.randrange(1, 4), depth=rng.randrange(1, 4))
+    raw = U.run_reference_on_wat(text, 256, seed_byte=seed + 1)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    _emitter_equals_reference_rows(pr, text, _reference_rows(raw))
+
+
+def test_signed_division_by_the_most_negative_number_is_rejected_as_the_reference_rejects_it(pr):
+    """a quirk kept: the reference's div_s / rem_s gadget range-checks the remainder against |y| with a SIGNED comparison
+    (interpreter_impl.hpp:452-456), so y = -2^(w-1), whose absolute value has the top bit set, fails the reference's own
+    self-check ("valid 101" from refctx_cpu); the emitter flags the same constraint instead of emitting a proof that
+    cannot verify"""
+    text = U.WAT_HEAD_BOTH + "(call $assert_equal (i32.rem_s (call $i32_private_const (i32.const 3)) (call $i32_private_const (i32.const 0x80000000))) (i32.const 3))\n" + U.WAT_TAIL
+    assert pr.wat_emit(text, 64)[4]["violated_constraints"] == 1
+    ok = text.replace("0x80000000", "0x80000001")
+    assert pr.wat_emit(ok, 64)[4]["violated_constraints"] == 0
+
+
+REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
+    "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
+    "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "tests")) or not os.path.exists(U.REF_BIN_CPU), reason="needs the reference tree and oracle/_ref/refctx_cpu")
-@pytest.mark.parametrize("name", ["i64_mul", "i64_add", "i64_sub", "i32_mul", "i32_add", "i32_sub"])
+@pytest.mark.parametrize("name", REFERENCE_INTEGER_PROGRAMS)
 def test_wat_emitter_on_the_reference_test_programs(oracle, pr, name):
-    """the six arithmetic programs of the reference's tests/ that lie in the subset, read where they lie: the reference's
-    own interpreter and the emitter agree on every row at l = 64 (many rows) -- and the reference's verifier accepts"""
+    """all 65 integer programs of the reference's tests/ (every iNN instruction it tests), read where they lie: the
+    reference's own interpreter and the emitter agree on every row at l = 64 -- and the reference's verifier accepts"""
     text = open(os.path.join(REFERENCE, "tests", name + ".wat")).read()
     raw = U.run_reference_on_wat(text, 256)
     assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
-    l = raw["l"]
-    u32 = lambda h: np.frombuffer(bytes.fromhex(h), np.uint32)
-    st = {"fx": raw, "l": l, "kinds": raw["kinds"], "values": u32(raw["values"]).reshape(-1, l, 8), "coefs": u32(raw["coefs"]).reshape(-1, l, 8),
-          "const_sum": int.from_bytes(bytes.fromhex(raw["const_sum"]), "little")}
-    _emitter_equals_reference_rows(pr, text, st)
+    _emitter_equals_reference_rows(pr, text, _reference_rows(raw))
 
 
 BOUNDARY_TU = r"""

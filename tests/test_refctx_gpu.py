@@ -62,7 +62,7 @@ def test_reference_stage_contexts_run_on_the_cuda_executor(case):
             assert got[key] == want[key], key
 
 
-@pytest.mark.parametrize("case,wat", [("i64_mul_k8192", None), ("mul64_k256", "mul64"), ("arith32_k256", "arith32")])
+@pytest.mark.parametrize("case,wat", [("i64_mul_k8192", None), ("mul64_k256", "mul64"), ("arith32_k256", "arith32"), ("intops_k256", "intops")])
 def test_prove_wat_commits_to_the_root_of_the_reference_run(lgr, pr, executor_factory, case, wat):
     """BASELINE config 4 through the product's entry point: lgrp_prove_wat on the text of tests/i64_mul.wat, with the
     encoding seed of the reference run, arrives at the Merkle root the reference's own interpreter + stage-1 context
