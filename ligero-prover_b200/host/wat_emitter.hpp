@@ -499,54 +499,39 @@ inline std::pair<witness_machine::wref, witness_machine::wref> witness_machine::
 }
 
 // ---- front end ------------------------------------------------------------------------------------------------
+// A program is the flat instruction list of its exported `_start` function, read either from WebAssembly text (the folded
+// style of the reference's tests/*.wat, plain instruction sequences too) or from a WebAssembly binary (the other input the
+// reference's prover takes, src/webgpu_prover.cpp:189-207): type, import, function, export and code sections of a module
+// whose `_start` is straight-line integer code calling env functions.  No wabt on either path.
 class wat_program {
 public:
-    explicit wat_program(const std::string &text) {
-        sexpr_parser p(text);
-        const sexpr top = p.parse_top();
-        if (top.head() != "module") throw std::invalid_argument("wat: expected (module ...)");
-        std::string start;
-        for (size_t i = 1; i < top.list.size(); i++) {
-            const sexpr &f = top.list[i];
-            if (f.head() == "import") {
-                // (import "env" "name" (func $id ...))
-                if (f.list.size() < 4 || f.list[3].head() != "func" || f.list[3].list.size() < 2) throw std::invalid_argument("wat: unsupported import");
-                if (f.list[1].atom != "\"env\"") throw std::invalid_argument("wat: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
-                imports_[f.list[3].list[1].atom] = unquote(f.list[2].atom);
-            } else if (f.head() == "func") {
-                if (f.list.size() < 2 || f.list[1].is_list) throw std::invalid_argument("wat: functions must be named");
-                funcs_[f.list[1].atom] = &f;
-            } else if (f.head() == "export") {
-                if (f.list.size() >= 3 && unquote(f.list[1].atom) == "_start" && f.list[2].head() == "func" && f.list[2].list.size() == 2) start = f.list[2].list[1].atom;
-            } else {
-                throw std::invalid_argument("wat: unsupported module field (" + f.head() + ")");
-            }
-        }
-        if (start.empty() || !funcs_.count(start)) throw std::invalid_argument("wat: no exported _start function");
-        module_ = top;                      // keep the tree alive; re-point the function table into the copy
-        funcs_.clear();
-        for (size_t i = 1; i < module_.list.size(); i++) if (module_.list[i].head() == "func") funcs_[module_.list[i].list[1].atom] = &module_.list[i];
-        start_ = start;
+    explicit wat_program(const std::string &data) {
+        if (data.size() >= 4 && data.compare(0, 4, std::string("\0asm", 4)) == 0) parse_binary(data);
+        else parse_text(data);
     }
 
     // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
     void run(witness_machine &m, wat_stats &st) const {
-        const sexpr &f = *funcs_.at(start_);
         run_state rs{m, st, {}};
-        for (size_t i = 2; i < f.list.size(); i++) {
-            const std::string &h = f.list[i].head();
-            if (h == "param" || h == "result" || h == "local" || h == "type") {
-                if (h != "type" && f.list[i].list.size() > 1) throw std::invalid_argument("wat: _start with parameters / locals is not supported");
-                continue;
+        for (const ins &i : code_) {
+            switch (i.kind) {
+            case ins::konst: rs.push(numeric(i.width == 64, i.imm)); break;
+            case ins::unary_op: unary((op)i.o, i.width, i.sgn, rs); break;
+            case ins::shift_op: shift((op)i.o, i.width, i.sgn, rs); break;
+            case ins::binary_op: binary((op)i.o, i.width, i.sgn, rs); break;
+            case ins::host_call: host((host_fn)i.o, rs); break;
+            case ins::drop: rs.pop(); break;                  // exec_drop (interpreter_impl.hpp:112-116)
+            case ins::nop: break;
+            case ins::end_of_statement: while (!rs.stack.empty()) rs.stack.pop_back(); break;
             }
-            exec(f.list[i], rs);
-            while (!rs.stack.empty()) rs.stack.pop_back();    // a value nobody consumed dies with the frame
         }
+        while (!rs.stack.empty()) rs.stack.pop_back();        // a value nobody consumed dies with the frame
         st.linear_constraints = m.draws();
         st.violated_constraints = m.violated();
         st.quadratic_slots = m.slots_made();
         st.linear_witnesses = m.linear_released();
     }
+    size_t instructions() const { return code_.size(); }
 
 private:
     using wref = witness_machine::wref;
@@ -901,7 +886,7 @@ private:
         }
     }
 
-    struct opinfo { op o; int arity; bool sgn; };
+    struct opinfo { op o; int arity; bool sgn; };           // arity 3 marks the shifts / rotates (two operands, the count is read as a number)
     static bool lookup(const std::string &name, opinfo &out) {
         static const std::map<std::string, opinfo> table = {
             {"clz", {op::clz, 1, false}}, {"ctz", {op::ctz, 1, false}}, {"popcnt", {op::popcnt, 1, false}}, {"eqz", {op::eqz, 1, false}},
@@ -921,15 +906,169 @@ private:
         return true;
     }
 
+    // env host functions (include/host_modules/env.hpp:40-110,160-190)
+    enum class host_fn : uint8_t { i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast, assert_is_concrete };
+    static bool host_lookup(const std::string &name, host_fn &out) {
+        static const std::map<std::string, host_fn> table = {
+            {"i32_private_const", host_fn::i32_private_const}, {"i64_private_const", host_fn::i64_private_const}, {"assert_equal", host_fn::assert_equal},
+            {"assert_zero", host_fn::assert_zero}, {"assert_one", host_fn::assert_one}, {"assert_constant", host_fn::assert_constant},
+            {"witness_cast_u32", host_fn::witness_cast}, {"witness_cast_u64", host_fn::witness_cast}, {"assert_is_concrete", host_fn::assert_is_concrete},
+        };
+        const auto it = table.find(name);
+        if (it == table.end()) return false;
+        out = it->second;
+        return true;
+    }
+    static void host(host_fn f, run_state &rs) {
+        witness_machine &m = rs.m;
+        switch (f) {
+        case host_fn::i32_private_const: case host_fn::i64_private_const: {   // a fresh witness, range-checked by its decomposition
+            const int width = f == host_fn::i32_private_const ? 32 : 64;
+            const value lit = rs.pop();
+            if (lit.kind != value::NUM) throw std::invalid_argument(std::string("wat: ") + (width == 32 ? "i32" : "i64") + "_private_const takes one constant");
+            rs.st.private_consts++;
+            wref x = m.acquire(lgr::host::from_u64(width == 32 ? lit.as_u32() : lit.as_u64()));
+            bitvec checked = m.bit_decompose(x, (size_t)width);
+            rs.push(value::of(checked));
+            break;
+        }
+        case host_fn::assert_equal: {
+            rs.st.asserts++;
+            value sy = rs.pop();
+            value sx = rs.pop();
+            wref wx = rs.make_witness(std::move(sx));
+            wref wy = rs.make_witness(std::move(sy));
+            m.assert_equal(wx, wy);
+            break;
+        }
+        case host_fn::assert_zero: case host_fn::assert_one: {
+            rs.st.asserts++;
+            value s = rs.pop();
+            wref w = rs.make_witness(std::move(s));
+            m.assert_const(w, f == host_fn::assert_one ? 1 : 0);
+            break;
+        }
+        case host_fn::assert_constant: {                       // ties the witness to the value it holds
+            rs.st.asserts++;
+            value s = rs.pop();
+            wref w = rs.make_witness(std::move(s));
+            m.constrain_constant(w.id(), w.val());
+            break;
+        }
+        case host_fn::witness_cast: {                          // the value as ONE witness (the stack keeps a second handle)
+            value sx = rs.pop();
+            wref wx = rs.make_witness(std::move(sx));
+            rs.push(value::of(wx));
+            break;
+        }
+        case host_fn::assert_is_concrete: {
+            value s = rs.pop();
+            if (s.kind != value::NUM) throw std::invalid_argument("wat: assert_is_concrete: value is a witness");
+            break;
+        }
+        }
+    }
+
+    struct ins {
+        enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, drop, nop, end_of_statement } kind;
+        uint8_t o = 0;                                        // op or host_fn
+        uint8_t width = 0;
+        bool sgn = false;
+        uint64_t imm = 0;
+    };
+    void emit_op(const std::string &name, int width, const std::string &shown) {
+        opinfo oi;
+        if (!lookup(name, oi)) throw std::invalid_argument("wat: unsupported instruction " + shown);
+        if ((oi.o == op::extend32 || oi.o == op::extend_i32) && width != 64) throw std::invalid_argument("wat: unsupported instruction " + shown);
+        if (oi.o == op::wrap && width != 32) throw std::invalid_argument("wat: unsupported instruction " + shown);
+        ins i;
+        i.kind = oi.arity == 1 ? ins::unary_op : (oi.arity == 3 ? ins::shift_op : ins::binary_op);
+        i.o = (uint8_t)oi.o; i.width = (uint8_t)width; i.sgn = oi.sgn;
+        code_.push_back(i);
+    }
+    void emit_const(int width, uint64_t v) { ins i; i.kind = ins::konst; i.width = (uint8_t)width; i.imm = width == 32 ? (v & 0xFFFFFFFFULL) : v; code_.push_back(i); }
+    void emit_host(const std::string &module, const std::string &field) {
+        if (module != "env") throw std::invalid_argument("wat: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
+        host_fn f;
+        if (!host_lookup(field, f)) throw std::invalid_argument("wat: env." + field + " is not supported by the bounded front end");
+        ins i; i.kind = ins::host_call; i.o = (uint8_t)f; code_.push_back(i);
+    }
+    void emit_plain(ins::kind_t k) { ins i; i.kind = k; code_.push_back(i); }
+
+    // ---- text ------------------------------------------------------------------------------------------------
+    struct import_t { std::string module, field; };
+    void parse_text(const std::string &text) {
+        sexpr_parser p(text);
+        const sexpr top = p.parse_top();
+        if (top.head() != "module") throw std::invalid_argument("wat: expected (module ...)");
+        std::vector<import_t> imports;
+        std::map<std::string, size_t> import_ids;
+        std::map<std::string, const sexpr *> funcs;
+        std::string start;
+        for (size_t i = 1; i < top.list.size(); i++) {
+            const sexpr &f = top.list[i];
+            if (f.head() == "import") {
+                // (import "env" "name" (func $id ...))
+                if (f.list.size() < 4 || f.list[3].head() != "func") throw std::invalid_argument("wat: unsupported import");
+                if (f.list[1].atom != "\"env\"") throw std::invalid_argument("wat: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
+                if (f.list[3].list.size() >= 2 && !f.list[3].list[1].is_list) import_ids[f.list[3].list[1].atom] = imports.size();
+                imports.push_back(import_t{unquote(f.list[1].atom), unquote(f.list[2].atom)});
+            } else if (f.head() == "func") {
+                if (f.list.size() < 2 || f.list[1].is_list) throw std::invalid_argument("wat: functions must be named");
+                funcs[f.list[1].atom] = &f;
+            } else if (f.head() == "export") {
+                if (f.list.size() >= 3 && unquote(f.list[1].atom) == "_start" && f.list[2].head() == "func" && f.list[2].list.size() == 2) start = f.list[2].list[1].atom;
+            } else {
+                throw std::invalid_argument("wat: unsupported module field (" + f.head() + ")");
+            }
+        }
+        if (start.empty() || !funcs.count(start)) throw std::invalid_argument("wat: no exported _start function");
+        const sexpr &f = *funcs.at(start);
+        const auto callee = [&](const std::string &id) -> const import_t & {
+            const auto it = import_ids.find(id);
+            if (it != import_ids.end()) return imports[it->second];
+            if (!id.empty() && id[0] >= '0' && id[0] <= '9' && parse_i64(id) < imports.size()) return imports[(size_t)parse_i64(id)];
+            throw std::invalid_argument("wat: call of a non-imported function is not supported (" + id + ")");
+        };
+        for (size_t i = 2; i < f.list.size(); i++) {
+            const sexpr &e = f.list[i];
+            if (e.is_list) {
+                const std::string &h = e.head();
+                if (h == "param" || h == "result" || h == "local" || h == "type") {
+                    if (h != "type" && e.list.size() > 1) throw std::invalid_argument("wat: _start with parameters / locals is not supported");
+                    continue;
+                }
+                flatten(e, callee);
+                emit_plain(ins::end_of_statement);
+                continue;
+            }
+            // plain (unfolded) instructions: immediates follow their instruction
+            const std::string &a = e.atom;
+            const auto next = [&]() -> const std::string & {
+                if (i + 1 >= f.list.size() || f.list[i + 1].is_list) throw std::invalid_argument("wat: " + a + " needs an immediate");
+                return f.list[++i].atom;
+            };
+            if (a == "i32.const" || a == "i64.const") emit_const(a[1] == '3' ? 32 : 64, literal(a, next()));
+            else if (a == "call") { const import_t &c = callee(next()); emit_host(c.module, c.field); }
+            else if (a == "drop") emit_plain(ins::drop);
+            else if (a == "nop") emit_plain(ins::nop);
+            else if (a.size() > 4 && (a.compare(0, 4, "i32.") == 0 || a.compare(0, 4, "i64.") == 0)) emit_op(a.substr(4), a[1] == '3' ? 32 : 64, a);
+            else throw std::invalid_argument("wat: unsupported instruction " + a);
+        }
+    }
+    static uint64_t literal(const std::string &instr, const std::string &lit) {
+        const uint64_t v = parse_i64(lit);
+        if (instr[1] == '3' && v > 0xFFFFFFFFULL && v < 0xFFFFFFFF80000000ULL) throw std::invalid_argument("wat: integer literal out of range " + lit);
+        return v;
+    }
     // one folded instruction: operands first (each leaves one value on the stack), then the instruction itself
-    void exec(const sexpr &e, run_state &rs) const {
-        if (!e.is_list) throw std::invalid_argument("wat: only folded instructions are supported (" + e.atom + ")");
+    template <typename Callee>
+    void flatten(const sexpr &e, const Callee &callee) {
+        if (!e.is_list) throw std::invalid_argument("wat: only folded instructions are supported inside a folded form (" + e.atom + ")");
         const std::string &h = e.head();
         if (h == "i64.const" || h == "i32.const") {
             if (e.list.size() != 2) throw std::invalid_argument("wat: " + h + " takes one literal");
-            const uint64_t v = parse_i64(e.list[1].atom);
-            if (h == "i32.const" && v > 0xFFFFFFFFULL && v < 0xFFFFFFFF80000000ULL) throw std::invalid_argument("wat: integer literal out of range " + e.list[1].atom);
-            rs.push(numeric(h[1] == '6', h == "i32.const" ? (v & 0xFFFFFFFFULL) : v));
+            emit_const(h[1] == '3' ? 32 : 64, literal(h, e.list[1].atom));
             return;
         }
         if (h.size() > 4 && (h.compare(0, 4, "i32.") == 0 || h.compare(0, 4, "i64.") == 0)) {
@@ -937,52 +1076,149 @@ private:
             if (!lookup(h.substr(4), oi)) throw std::invalid_argument("wat: unsupported instruction " + h);
             const int operands = oi.arity == 1 ? 1 : 2;
             if ((int)e.list.size() != 1 + operands) throw std::invalid_argument("wat: " + h + " takes " + (operands == 1 ? "one folded operand" : "two folded operands"));
-            const size_t depth = rs.stack.size();
-            for (int i = 1; i <= operands; i++) exec(e.list[(size_t)i], rs);
-            if (rs.stack.size() != depth + (size_t)operands) throw std::invalid_argument("wat: " + h + " needs " + (operands == 1 ? "one operand" : "two operands"));
-            const int w = h[1] == '3' ? 32 : 64;
-            if (oi.arity == 1) unary(oi.o, w, oi.sgn, rs);
-            else if (oi.arity == 3) shift(oi.o, w, oi.sgn, rs);
-            else binary(oi.o, w, oi.sgn, rs);
+            for (int i = 1; i <= operands; i++) flatten(e.list[(size_t)i], callee);
+            emit_op(h.substr(4), h[1] == '3' ? 32 : 64, h);
             return;
         }
         if (h == "call") {
-            if (e.list.size() < 2) throw std::invalid_argument("wat: call without a target");
-            const auto it = imports_.find(e.list[1].atom);
-            if (it == imports_.end()) throw std::invalid_argument("wat: call of a non-imported function is not supported (" + e.list[1].atom + ")");
-            const size_t depth = rs.stack.size();
-            for (size_t i = 2; i < e.list.size(); i++) exec(e.list[i], rs);
-            const size_t nargs = rs.stack.size() - depth;
-            witness_machine &m = rs.m;
-            if (it->second == "i64_private_const" || it->second == "i32_private_const") {   // env.hpp:166-188: a fresh witness, range-checked by its decomposition
-                if (nargs != 1 || rs.stack.back().kind != value::NUM) throw std::invalid_argument("wat: " + it->second + " takes one constant");
-                const int width = it->second[1] == '3' ? 32 : 64;
-                const value lit = rs.pop();
-                rs.st.private_consts++;
-                wref x = m.acquire(lgr::host::from_u64(width == 32 ? lit.as_u32() : lit.as_u64()));
-                bitvec checked = m.bit_decompose(x, (size_t)width);
-                rs.push(value::of(checked));
-                return;
-            }
-            if (it->second == "assert_equal") {                                // env.hpp:64-77
-                if (nargs != 2) throw std::invalid_argument("wat: assert_equal takes two operands");
-                rs.st.asserts++;
-                value sy = rs.pop();
-                value sx = rs.pop();
-                wref wx = rs.make_witness(std::move(sx));
-                wref wy = rs.make_witness(std::move(sy));
-                m.assert_equal(wx, wy);
-                return;
-            }
-            throw std::invalid_argument("wat: env." + it->second + " is not supported by the bounded front end");
+            if (e.list.size() < 2 || e.list[1].is_list) throw std::invalid_argument("wat: call without a target");
+            const import_t &c = callee(e.list[1].atom);
+            for (size_t i = 2; i < e.list.size(); i++) flatten(e.list[i], callee);
+            emit_host(c.module, c.field);
+            return;
         }
+        if (h == "drop") {
+            for (size_t i = 1; i < e.list.size(); i++) flatten(e.list[i], callee);
+            emit_plain(ins::drop);
+            return;
+        }
+        if (h == "nop") { emit_plain(ins::nop); return; }
         throw std::invalid_argument("wat: unsupported instruction " + h);
     }
 
-    sexpr module_;
-    std::map<std::string, std::string> imports_;
-    std::map<std::string, const sexpr *> funcs_;
-    std::string start_;
+    // ---- binary (WebAssembly 1.0 module format + the sign-extension operators) ---------------------------------
+    struct reader {
+        const uint8_t *p, *end;
+        uint8_t byte() { if (p >= end) throw std::invalid_argument("wasm: unexpected end of the module"); return *p++; }
+        uint64_t uleb(int bits = 32) {
+            uint64_t v = 0;
+            for (int shift = 0;; shift += 7) {
+                const uint8_t b = byte();
+                if (shift >= bits + 7) throw std::invalid_argument("wasm: malformed LEB128 integer");
+                v |= (uint64_t)(b & 0x7f) << (shift < 64 ? shift : 63);
+                if (!(b & 0x80)) return v;
+            }
+        }
+        int64_t sleb(int bits) {
+            int64_t v = 0;
+            int shift = 0;
+            uint8_t b;
+            do {
+                b = byte();
+                if (shift >= bits + 7) throw std::invalid_argument("wasm: malformed LEB128 integer");
+                if (shift < 64) v |= (int64_t)((uint64_t)(b & 0x7f) << shift);
+                shift += 7;
+            } while (b & 0x80);
+            if (shift < 64 && (b & 0x40)) v |= -((int64_t)1 << shift);
+            return v;
+        }
+        std::string name() {
+            const size_t n = (size_t)uleb();
+            if ((size_t)(end - p) < n) throw std::invalid_argument("wasm: unexpected end of the module");
+            std::string s((const char *)p, n);
+            p += n;
+            return s;
+        }
+        reader sub(size_t n) {
+            if ((size_t)(end - p) < n) throw std::invalid_argument("wasm: section runs past the end of the module");
+            reader r{p, p + n};
+            p += n;
+            return r;
+        }
+    };
+    void parse_binary(const std::string &data) {
+        reader r{(const uint8_t *)data.data(), (const uint8_t *)data.data() + data.size()};
+        r.p += 4;
+        if (r.sub(4).p[0] != 1) throw std::invalid_argument("wasm: unsupported binary version");
+        std::vector<import_t> imports;
+        size_t nfuncs = 0;
+        int64_t start = -1;
+        std::vector<reader> bodies;
+        while (r.p < r.end) {
+            const uint8_t id = r.byte();
+            reader s = r.sub((size_t)r.uleb());
+            switch (id) {
+            case 0: case 1: case 3: case 12: {                // custom / type / function / data count: nothing the straight-line subset needs
+                if (id == 3) nfuncs = (size_t)s.uleb();
+                break;
+            }
+            case 2: {                                         // imports: functions of env only
+                const size_t n = (size_t)s.uleb();
+                for (size_t i = 0; i < n; i++) {
+                    import_t im{s.name(), s.name()};
+                    if (s.byte() != 0x00) throw std::invalid_argument("wasm: only function imports are supported (" + im.module + "." + im.field + ")");
+                    s.uleb();
+                    if (im.module != "env") throw std::invalid_argument("wasm: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
+                    imports.push_back(im);
+                }
+                break;
+            }
+            case 7: {                                         // exports: the function called _start
+                const size_t n = (size_t)s.uleb();
+                for (size_t i = 0; i < n; i++) {
+                    const std::string nm = s.name();
+                    const uint8_t kind = s.byte();
+                    const uint64_t idx = s.uleb();
+                    if (kind == 0x00 && nm == "_start") start = (int64_t)idx;
+                }
+                break;
+            }
+            case 10: {                                        // code
+                const size_t n = (size_t)s.uleb();
+                for (size_t i = 0; i < n; i++) bodies.push_back(s.sub((size_t)s.uleb()));
+                break;
+            }
+            default:
+                throw std::invalid_argument("wasm: unsupported module section (id " + std::to_string(id) + ")");
+            }
+        }
+        if (start < 0 || (size_t)start < imports.size() || (size_t)start - imports.size() >= bodies.size() || bodies.size() != nfuncs)
+            throw std::invalid_argument("wasm: no exported _start function");
+        reader b = bodies[(size_t)start - imports.size()];
+        if (b.uleb() != 0) throw std::invalid_argument("wasm: _start with locals is not supported");
+        static const char *const int_ops[] = {"clz", "ctz", "popcnt", "add", "sub", "mul", "div_s", "div_u", "rem_s", "rem_u", "and", "or", "xor", "shl", "shr_s", "shr_u", "rotl", "rotr"};
+        static const char *const cmp_ops[] = {"eqz", "eq", "ne", "lt_s", "lt_u", "gt_s", "gt_u", "le_s", "le_u", "ge_s", "ge_u"};
+        for (;;) {
+            const uint8_t c = b.byte();
+            if (c == 0x0B) break;                             // end
+            const std::string shown = "0x" + std::string(1, "0123456789abcdef"[c >> 4]) + std::string(1, "0123456789abcdef"[c & 15]);
+            if (c == 0x01) emit_plain(ins::nop);
+            else if (c == 0x1A) emit_plain(ins::drop);
+            else if (c == 0x10) {
+                const uint64_t f = b.uleb();
+                if (f >= imports.size()) throw std::invalid_argument("wasm: call of a non-imported function is not supported (" + std::to_string(f) + ")");
+                emit_host(imports[(size_t)f].module, imports[(size_t)f].field);
+            }
+            else if (c == 0x41) emit_const(32, (uint64_t)b.sleb(32));
+            else if (c == 0x42) emit_const(64, (uint64_t)b.sleb(64));
+            else if (c >= 0x45 && c <= 0x4F) emit_op(cmp_ops[c - 0x45], 32, shown);
+            else if (c >= 0x50 && c <= 0x5A) emit_op(cmp_ops[c - 0x50], 64, shown);
+            else if (c >= 0x67 && c <= 0x78) emit_op(int_ops[c - 0x67], 32, shown);
+            else if (c >= 0x79 && c <= 0x8A) emit_op(int_ops[c - 0x79], 64, shown);
+            else if (c == 0xA7) emit_op("wrap_i64", 32, shown);
+            else if (c == 0xAC) emit_op("extend_i32_s", 64, shown);
+            else if (c == 0xAD) emit_op("extend_i32_u", 64, shown);
+            else if (c == 0xC0) emit_op("extend8_s", 32, shown);
+            else if (c == 0xC1) emit_op("extend16_s", 32, shown);
+            else if (c == 0xC2) emit_op("extend8_s", 64, shown);
+            else if (c == 0xC3) emit_op("extend16_s", 64, shown);
+            else if (c == 0xC4) emit_op("extend32_s", 64, shown);
+            else throw std::invalid_argument("wasm: unsupported instruction " + shown);
+        }
+        if (b.p != b.end) throw std::invalid_argument("wasm: bytes after the end of _start");
+    }
+
+    std::vector<ins> code_;
 };
 
 }  // namespace ligero::cuda::host

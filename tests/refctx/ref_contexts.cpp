@@ -102,15 +102,30 @@ using stage3_t = recording<zkp::nonbatch_stage3_context<field_t, executor_t, zkp
 struct tiny_module {
     store_t store;
     module_instance inst;
+    // env functions in import order: the call token "call:<name>" becomes call <index>
+    static const std::vector<std::pair<std::string, int>> &env_imports() {      // name, shape: 0 = (i64)->(i64), 1 = (i64 i64)->(), 2 = (i32)->(i32), 3 = (i64)->()
+        static const std::vector<std::pair<std::string, int>> t = {
+            {"i64_private_const", 0}, {"assert_equal", 1}, {"i32_private_const", 2}, {"assert_zero", 3}, {"assert_one", 3}, {"assert_constant", 3},
+            {"witness_cast_u32", 2}, {"witness_cast_u64", 0}, {"assert_is_concrete", 3}};
+        return t;
+    }
+    static int import_index(const std::string &name) {
+        const auto &t = env_imports();
+        for (size_t i = 0; i < t.size(); i++) if (t[i].first == name) return (int)i;
+        return -1;
+    }
     explicit tiny_module(std::vector<instr_ptr> body) {
-        function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_pc32({value_kind::i32}, {value_kind::i32}), k_start({}, {});
-        inst.types = {k_pc, k_eq, k_pc32, k_start};
-        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("i64_private_const"), k_pc, &inst, function_instance::host_code{0, "env", "i64_private_const"}));
-        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("assert_equal"), k_eq, &inst, function_instance::host_code{1, "env", "assert_equal"}));
-        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("i32_private_const"), k_pc32, &inst, function_instance::host_code{2, "env", "i32_private_const"}));
-        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("_start"), k_start, &inst, function_instance::func_code{3, {}, std::move(body)}));
+        function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_pc32({value_kind::i32}, {value_kind::i32}),
+            k_one({value_kind::i64}, {}), k_start({}, {});
+        inst.types = {k_pc, k_eq, k_pc32, k_one, k_start};
+        const function_kind *shapes[4] = {&k_pc, &k_eq, &k_pc32, &k_one};
+        const auto &t = env_imports();
+        for (size_t i = 0; i < t.size(); i++)
+            inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t(t[i].first), *shapes[t[i].second], &inst, function_instance::host_code{(index_t)i, "env", t[i].first}));
+        const index_t start = (index_t)t.size();
+        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("_start"), k_start, &inst, function_instance::func_code{start, {}, std::move(body)}));
         inst.memaddrs.push_back(store.emplace_back<memory_instance>(memory_kind(limits(1)), memory_instance::page_size));
-        inst.exports["_start"] = 3;
+        inst.exports["_start"] = start;
     }
 };
 
@@ -164,9 +179,12 @@ static std::vector<instr_ptr> assemble(const std::vector<wasm_token> &toks) {
         }
         else if (t.op == "c") plain(opcode(opcode::inn_const, value_kind::i64, t.imm));
         else if (t.op == "mul") plain(opcode(opcode::inn_mul, value_kind::i64));
-        else if (t.op == "pc32" || t.op == "call:i32_private_const") { flush(); body.push_back(make_instr<call>(2)); }
-        else if (t.op == "pc" || t.op == "call:i64_private_const") { flush(); body.push_back(make_instr<call>(0)); }
-        else if (t.op == "eq" || t.op == "call:assert_equal") { flush(); body.push_back(make_instr<call>(1)); }
+        else if (t.op == "pc32") { flush(); body.push_back(make_instr<call>(2)); }
+        else if (t.op == "pc") { flush(); body.push_back(make_instr<call>(0)); }
+        else if (t.op == "eq") { flush(); body.push_back(make_instr<call>(1)); }
+        else if (t.op.rfind("call:", 0) == 0 && tiny_module::import_index(t.op.substr(5)) >= 0) { flush(); body.push_back(make_instr<call>((index_t)tiny_module::import_index(t.op.substr(5)))); }
+        else if (t.op == "drop") plain(opcode(opcode::drop));
+        else if (t.op == "nop") plain(opcode(opcode::nop));
         else throw std::runtime_error("unknown token " + t.op);
     }
     flush();

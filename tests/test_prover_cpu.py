@@ -405,3 +405,73 @@ def test_wat_emitter_on_random_expression_trees(pr, oracle, seed):
     wrong = list(cases); wrong[j] = (cases[j][0], (cases[j][1] + 1) % (1 << 64))
     _, st_bad = _wat_check(pr, oracle, head + body(wrong) + tail, l=256, k=256, expect_valid=False)
     assert st_bad["violated_constraints"] == 1
+
+
+# ---------------------------------------------------------------- the other two spellings of a program: binary and plain text
+def _same_rows(pr, a, b, l=64):
+    seed = hashlib.sha256(b"spellings").digest()
+    ra, rb = pr.wat_emit(a, l, seed), pr.wat_emit(b, l, seed)
+    assert list(ra[0]) == list(rb[0]) and np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2]) and ra[3] == rb[3] and ra[4] == rb[4]
+    return ra[4]
+
+
+@pytest.mark.parametrize("name", ["mul64", "arith32", "intops"])
+def test_wasm_binary_and_plain_text_give_the_rows_of_the_folded_text(pr, name):
+    """the reference's prover takes .wat and .wasm (src/webgpu_prover.cpp:189-207); so does lgrp_wat_emit / lgrp_prove_wat: the
+    binary module of a program (assembled by tests/refctx_util.py: wat_to_wasm -- there is no wabt here) and its plain,
+    unfolded text go through the same instruction list as the folded text and give the same rows, coefficients and const_sum"""
+    import refctx_util as U
+    text = open(U.WAT_TEXT[name]).read()
+    wasm = U.wat_to_wasm(text)
+    assert wasm[:8] == b"\0asm\x01\0\0\0"
+    st = _same_rows(pr, text, wasm)
+    assert st["violated_constraints"] == 0 and st["asserts"] > 0
+    _same_rows(pr, text, U.wat_to_plain(text))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_wasm_binary_front_end_on_random_programs(pr, seed):
+    import refctx_util as U
+    rng = random.Random(900 + seed)
+    text, _ = U.rand_int_program(rng, (32, 64)[seed & 1], nexpr=3, depth=3)
+    _same_rows(pr, text, U.wat_to_wasm(text, custom_section=bool(seed & 2)))
+
+
+def test_wasm_binary_front_end_rejects_what_it_does_not_support(pr):
+    import refctx_util as U
+    good = U.wat_to_wasm(open(U.WAT_TEXT["arith32"]).read(), custom_section=False)
+    pr.wat_emit(good, 64)
+    sec = lambda sid, body: bytes([sid, len(body)]) + body
+    for data, why in ((good[:-3], "section runs past the end|unexpected end"),
+                      (good[:8] + sec(5, b"\x01\x00\x01") + good[8:], "unsupported module section"),           # a memory
+                      (b"\0asm\x02\0\0\0" + good[8:], "binary version"),
+                      (good[:-1] + b"\x28\x0b", "section runs past|unexpected end|unsupported"),
+                      (b"\0asm\x01\0\0\0", "_start")):
+        with pytest.raises(pr.ProverError, match=why):
+            pr.wat_emit(data, 64)
+    # an opcode outside the subset inside _start (i32.load = 0x28)
+    text = '(module (import "env" "assert_equal" (func $e (param i32 i32))) (func $f (call $e (i32.const 1) (i32.const 1))) (export "_start" (func $f)))'
+    wasm = bytearray(U.wat_to_wasm(text, custom_section=False))
+    at = wasm.rindex(b"\x41\x01\x41\x01")
+    wasm[at] = 0x28
+    with pytest.raises(pr.ProverError, match="unsupported instruction 0x28"):
+        pr.wat_emit(bytes(wasm), 64)
+
+
+def test_env_assertions_and_drop(pr, oracle):
+    """env.assert_zero / assert_one / assert_constant / witness_cast_u64 / assert_is_concrete and `drop` (env.hpp:40-110,160-170):
+    the constraint system holds, and a false assert_one breaks exactly the linear test"""
+    head = ('(module (import "env" "i64_private_const" (func $pc (param i64) (result i64)))\n(import "env" "assert_zero" (func $z (param i64)))\n'
+            '(import "env" "assert_one" (func $o (param i64)))\n(import "env" "assert_constant" (func $c (param i64)))\n'
+            '(import "env" "witness_cast_u64" (func $cast (param i64) (result i64)))\n(import "env" "assert_is_concrete" (func $conc (param i64)))\n'
+            '(import "env" "assert_equal" (func $eq (param i64 i64)))\n(func $t\n')
+    body = ('(call $z (i64.sub (call $pc (i64.const 9)) (call $pc (i64.const 9))))\n(call $o (i64.eqz (call $pc (i64.const 0))))\n'
+            '(call $c (i64.add (call $pc (i64.const 40)) (i64.const 2)))\n(call $eq (call $cast (call $pc (i64.const 77))) (i64.const 77))\n'
+            '(call $conc (i64.mul (i64.const 6) (i64.const 7)))\n(drop (call $pc (i64.const 5)))\n(call $z (call $cast (i64.const 0)))\n')
+    tail = ')\n(export "_start" (func $t)))\n'
+    _, st = _wat_check(pr, oracle, head + body + tail, l=128, k=256)
+    assert st["violated_constraints"] == 0 and st["asserts"] == 5 and st["private_consts"] == 6
+    _, st_bad = _wat_check(pr, oracle, head + body.replace("(i64.eqz (call $pc (i64.const 0)))", "(i64.eqz (call $pc (i64.const 4)))") + tail, l=128, k=256, expect_valid=False)
+    assert st_bad["violated_constraints"] == 1
+    with pytest.raises(pr.ProverError, match="assert_is_concrete"):
+        pr.wat_emit(head + "(call $conc (call $pc (i64.const 1)))\n" + tail, 64)

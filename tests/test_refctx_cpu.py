@@ -216,6 +216,29 @@ def test_signed_division_by_the_most_negative_number_is_rejected_as_the_referenc
     assert pr.wat_emit(ok, 64)[4]["violated_constraints"] == 0
 
 
+ENV_PROGRAM = ('(module (import "env" "i64_private_const" (func $pc (param i64) (result i64)))\n(import "env" "assert_zero" (func $z (param i64)))\n'
+               '(import "env" "assert_one" (func $o (param i64)))\n(import "env" "assert_constant" (func $c (param i64)))\n'
+               '(import "env" "witness_cast_u64" (func $cast (param i64) (result i64)))\n(import "env" "assert_is_concrete" (func $conc (param i64)))\n'
+               '(import "env" "assert_equal" (func $eq (param i64 i64)))\n(func $t\n'
+               '(call $z (i64.sub (call $pc (i64.const 9)) (call $pc (i64.const 9))))\n(call $o (i64.eqz (call $pc (i64.const 0))))\n'
+               '(call $c (i64.add (call $pc (i64.const 40)) (i64.const 2)))\n(call $eq (call $cast (call $pc (i64.const 77))) (i64.const 77))\n'
+               '(call $conc (i64.mul (i64.const 6) (i64.const 7)))\n(drop (call $pc (i64.const 5)))\n(call $z (call $cast (i64.const 0)))\n'
+               '(call $o (call $cast (i64.popcnt (call $pc (i64.const 256)))))\n(call $c (i64.const 12))\n(drop (i64.clz (call $pc (i64.const 3))))\n(nop)\n'
+               ')\n(export "_start" (func $t)))\n')
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+def test_wat_emitter_env_assertions_casts_and_drop_against_the_reference(oracle, pr):
+    """env.assert_zero / assert_one / assert_constant / witness_cast_u64 / assert_is_concrete, `drop` and `nop` through the
+    reference's env module + interpreter and through the emitter: same rows, coefficient rows and const_sum; the binary
+    spelling of the program too"""
+    raw = U.run_reference_on_wat(ENV_PROGRAM, 256, seed_byte=9)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    _emitter_equals_reference_rows(pr, ENV_PROGRAM, st)
+    _emitter_equals_reference_rows(pr, U.wat_to_wasm(ENV_PROGRAM), st)
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
