@@ -116,16 +116,20 @@ typedef struct {
 
 int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
 
-/* ---- bounded interpreter boundary (BASELINE config 4) --------------------------------
- * A front end for the folded-WAT subset of the reference's arithmetic tests (tests/i64_mul.wat, i64_add.wat,
- * i64_sub.wat and their i32 twins: env.i64_private_const, env.i32_private_const, env.assert_equal, iNN.const / mul /
- * add / sub) and the witness emitter behind
- * it (host/wat_emitter.hpp).  It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under
- * include/zkp/backend/ stand in the reference.  It is not a general WASM machine, but for this subset it gives every form
- * the reference's meaning -- the same witnesses, released in the same order, with the same linear-test randomness -- so
- * the rows, the stage-2 coefficient rows and const_sum are the reference's, element for element: checked against runs of
- * the reference's own interpreter / backend / witness manager (tests/refctx/ref_contexts.cpp, tests/golden/refctx_*.json,
- * tests/test_refctx_cpu.py), on tests/i64_mul.wat at the default geometry and on random programs of the subset. */
+/* ---- interpreter boundary (BASELINE config 4) ------------------------------------------
+ * A front end for straight-line integer programs over the env host module and the witness emitter behind it
+ * (host/wat_emitter.hpp).  `wat` is WebAssembly text (folded like the .wat files under the reference's tests/, or plain) or a WebAssembly
+ * binary (it starts with "\0asm"): the reference's prover takes both (src/webgpu_prover.cpp:189-207).  Supported: every
+ * integer instruction the reference implements (interpreter_impl.hpp:155-1309: const, add sub mul, div / rem, and or xor,
+ * shifts and rotates, comparisons, clz ctz popcnt, extend / wrap; 32 and 64 bits), drop, nop, and env.i32_private_const,
+ * i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast_u32 / _u64, assert_is_concrete.
+ * Not supported (LGRP error naming the construct): control flow, locals, memory, tables, floating point, other host modules.
+ * It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under include/zkp/backend/ stand in
+ * the reference.  It is not a general WASM machine, but for what it takes it gives every instruction the reference's
+ * meaning -- the same witnesses, released in the same order, with the same linear-test randomness -- so the rows, the
+ * stage-2 coefficient rows and const_sum are the reference's, element for element: checked against runs of the
+ * reference's own interpreter / env module / backend / witness manager (tests/refctx/ref_contexts.cpp,
+ * tests/golden/refctx_*.json, tests/test_refctx_cpu.py) on all 65 integer programs of its tests/ and on random programs. */
 typedef struct {
     uint64_t private_consts, asserts, arithmetic_ops;
     uint64_t linear_witnesses, quadratic_slots, linear_constraints;
@@ -135,8 +139,8 @@ typedef struct {
  * coefficients are drawn from the linear stream keyed by the seed, one rho per constraint, and const_sum is set. */
 int lgrp_wat_emit(const char *wat, size_t len, uint32_t l, const uint8_t *stage1_seed, lgrp_packer **rows_out, uint32_t const_sum[8],
                   lgrp_wat_stats *stats);
-/* text -> proof on the context's geometry: stage 1 on the values, coefficients from the stage-1 seed, stages 2 and 3.
- * program_hash = SHA-256 of the text (the reference hashes the .wasm binary), instance_hash = 0 (no public arguments). */
+/* text or binary -> proof on the context's geometry: stage 1 on the values, coefficients from the stage-1 seed, stages 2 and 3.
+ * program_hash = SHA-256 of the bytes handed in, instance_hash = 0 (no public arguments). */
 int lgrp_prove_wat(lgr_ctx *ctx, const char *wat, size_t len, const uint8_t encoding_seed[32], int64_t generated_at_seconds,
                    lgrp_proof **out, lgrp_wat_stats *stats);
 

@@ -1,34 +1,25 @@
-// Bounded interpreter boundary (BASELINE config 4): a front end for the folded-WAT subset the reference's
-// arithmetic tests use (tests/i64_mul.wat, i64_add.wat, i64_sub.wat and their i32 twins: imports env.i64_private_const /
-// env.i32_private_const / env.assert_equal, one exported function of folded iNN.const / iNN.mul / iNN.add / iNN.sub / call
-// forms) and the witness emitter behind it.
-// It is NOT the reference's interpreter (include/interpreter_impl.hpp + include/zkp/backend/*.hpp: a general WASM machine over
-// an expression-template backend, out of scope); it is a small witness machine that gives every form of the subset the
-// meaning the reference gives it -- which witnesses exist, which linear-test randomness lands on them, and WHEN each one is
-// released into a row:
-//   (call $i64_private_const (i64.const v))   env.hpp:178-188: witness x = v, 64-bit decomposition (core.hpp:714-741: one
-//                                             draw rho, x gets -rho, bit i gets +rho*2^i; every bit b is a slot (b', b'', b)
-//                                             with two clones tied to it by one draw each, witness_manager.hpp:431-441);
-//                                             x is released when the call returns, the bits travel on the stack
-//   (i64.mul a b)                             interpreter_impl.hpp:351-391: operands recomposed (core.hpp:761-781: sum witness,
-//                                             one draw, bits get +rho*2^i), slot (x, y, x*y), 128-bit decomposition of the
-//                                             product, top 64 bits released at once, then product, y, x -- so the slot lands
-//                                             after them -- and only then the operands' bits (a's, then b's, each most
-//                                             significant first: the handler's popped stack values die last)
-//   (i64.add a b) / (i64.sub a b)             :262-349: s = x + y resp. (2^64 - y) + x with one draw (the constant lands in
-//                                             const_sum), 65-bit decomposition, top bit released, then s, y, x
-//   (call $assert_equal a b)                  env.hpp:64-77: both sides recomposed, one draw ties them, b's witness is
-//                                             released before a's
-//   a literal operand                         a bare witness (nonbatch_context.hpp:275-299): no constraint of its own
+// Interpreter boundary (BASELINE config 4): a front end for straight-line integer programs over the env host
+// module -- WebAssembly text (folded, as the reference's tests/*.wat are written, or plain) and WebAssembly binaries, both of
+// which the reference's prover takes (src/webgpu_prover.cpp:189-207) -- and the witness machine behind it.
+// It is NOT the reference's interpreter (include/interpreter_impl.hpp + include/zkp/backend/*.hpp: a general WASM machine with
+// control flow, locals, memory and tables over an expression-template backend; out of scope).  For the instructions it
+// takes -- every integer instruction the reference implements (interpreter_impl.hpp:155-1309), drop, nop, and the env
+// functions iNN_private_const / assert_equal / assert_zero / assert_one / assert_constant / witness_cast / assert_is_concrete
+// (host_modules/env.hpp) -- it gives each one the meaning the reference gives it: which witnesses exist, which draws of the
+// linear stream land on them, and WHEN each one is released into a row.  That order is decided in the reference by C++
+// object lifetimes (a witness is committed when the last shared_ptr to it dies), so the machine below is built from counted
+// handles with the same copy / move / destruction behaviour and its gadgets mirror where the reference creates, copies and
+// drops them; see the comments at witness_machine.
 // Linear-test randomness comes from the LINEAR stream (AES-CTR keyed with the stage-1 seed, nonbatch_context.hpp:105-112),
 // drawn in execution order, so the program is run again once the seed exists (as the reference re-runs it in stage 2).
 //
-// Parity statement: pinned to a run of the reference itself.  tests/refctx/ref_contexts.cpp compiles the reference's own
-// interpreter, env module, backend and witness manager and runs programs of this subset through them; on tests/i64_mul.wat
-// (tests/golden/refctx_i64_mul_k8192.json), on the repo's mul64.wat and on random expression trees this emitter produces the
-// same rows, the same coefficient rows and the same const_sum, element for element (tests/test_refctx_cpu.py).  The
-// release order follows the lifetimes of the reference's C++ objects as GCC orders them; another compiler's unspecified
-// evaluation order could move witnesses inside a row.
+// Parity statement: pinned to runs of the reference itself.  tests/refctx/ref_contexts.cpp compiles the reference's own
+// interpreter, env module, backend and witness manager and runs programs through them as token streams; on all 65 integer
+// programs of the reference's tests/ (tests/i64_mul.wat = BASELINE config 4 among them), on the repo's mul64.wat / arith32.wat /
+// intops.wat (tests/golden/refctx_*.json) and on random expression trees over the whole instruction set this emitter produces
+// the same rows, the same coefficient rows and the same const_sum, element for element (tests/test_refctx_cpu.py).
+// The release order follows the lifetimes of C++ objects as GCC orders them (parameters, temporaries, structured
+// bindings); this file leans on the same rules and is built with the same compiler.
 #pragma once
 #include <array>
 #include <cstdint>

@@ -76,6 +76,11 @@ def test_prove_wat_commits_to_the_root_of_the_reference_run(lgr, pr, executor_fa
     env = ref.parse_envelope(proof.gzip)
     assert env.ligero_proof.merkle_tree.root.value.hex() == st["fx"]["root"]
     proof.close()
+    if wat == "arith32":                                      # the same program as a WebAssembly binary (the reference takes both)
+        proof, stats = pr.prove_wat(ex, U.wat_to_wasm(text), st["encoding_seed"], generated_at=3)
+        assert stats["violated_constraints"] == 0 and proof.info()["valid"] == (True, True, True)
+        assert ref.parse_envelope(proof.gzip).ligero_proof.merkle_tree.root.value.hex() == st["fx"]["root"]
+        proof.close()
 
 
 @pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
