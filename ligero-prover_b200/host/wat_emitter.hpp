@@ -78,12 +78,13 @@ private:
         if (pos_ >= s_.size()) throw std::invalid_argument("wat: unexpected end of text");
         sexpr e;
         if (s_[pos_] == '(') {
+            if (++depth_ > 2000) throw std::invalid_argument("wat: forms nested too deeply");
             pos_++;
             e.is_list = true;
             for (;;) {
                 skip();
                 if (pos_ >= s_.size()) throw std::invalid_argument("wat: unbalanced parenthesis");
-                if (s_[pos_] == ')') { pos_++; return e; }
+                if (s_[pos_] == ')') { pos_++; depth_--; return e; }
                 e.list.push_back(parse());
             }
         }
@@ -102,6 +103,7 @@ private:
     }
     const std::string &s_;
     size_t pos_ = 0;
+    int depth_ = 0;
 };
 
 // ---- the witness machine ------------------------------------------------------------------------------------
@@ -967,24 +969,60 @@ private:
         bool sgn = false;
         uint64_t imm = 0;
     };
+    // A light validator rides along with the instruction list: the static width (32 / 64) of every stack slot.  wabt would
+    // have validated the module for the reference; here an instruction applied to a value of the other width is rejected
+    // (the handlers index operand bits by the instruction's width).  Host calls are checked for operand COUNT only: the
+    // reference's own tests call assert_equal (param i64 i64) with i32 operands.
+    uint8_t pop_type(const std::string &shown) {
+        if (types_.empty()) throw std::invalid_argument("wat: operand stack underflow at " + shown);
+        const uint8_t t = types_.back();
+        types_.pop_back();
+        return t;
+    }
+    void want(int width, const std::string &shown) {
+        const uint8_t t = pop_type(shown);
+        if (t != width) throw std::invalid_argument("wat: type mismatch: " + shown + " applied to an i" + std::to_string((int)t) + " value");
+    }
     void emit_op(const std::string &name, int width, const std::string &shown) {
         opinfo oi;
         if (!lookup(name, oi)) throw std::invalid_argument("wat: unsupported instruction " + shown);
         if ((oi.o == op::extend32 || oi.o == op::extend_i32) && width != 64) throw std::invalid_argument("wat: unsupported instruction " + shown);
         if (oi.o == op::wrap && width != 32) throw std::invalid_argument("wat: unsupported instruction " + shown);
+        const int in_width = oi.o == op::extend_i32 ? 32 : (oi.o == op::wrap ? 64 : width);
+        if (oi.arity != 1) want(in_width, shown);
+        want(in_width, shown);
+        const bool predicate = oi.o == op::eqz || oi.o == op::eq || oi.o == op::ne || oi.o == op::lt || oi.o == op::gt || oi.o == op::le || oi.o == op::ge;
+        types_.push_back(predicate ? 32 : (uint8_t)width);
         ins i;
         i.kind = oi.arity == 1 ? ins::unary_op : (oi.arity == 3 ? ins::shift_op : ins::binary_op);
         i.o = (uint8_t)oi.o; i.width = (uint8_t)width; i.sgn = oi.sgn;
         code_.push_back(i);
     }
-    void emit_const(int width, uint64_t v) { ins i; i.kind = ins::konst; i.width = (uint8_t)width; i.imm = width == 32 ? (v & 0xFFFFFFFFULL) : v; code_.push_back(i); }
+    void emit_const(int width, uint64_t v) {
+        types_.push_back((uint8_t)width);
+        ins i; i.kind = ins::konst; i.width = (uint8_t)width; i.imm = width == 32 ? (v & 0xFFFFFFFFULL) : v; code_.push_back(i);
+    }
     void emit_host(const std::string &module, const std::string &field) {
         if (module != "env") throw std::invalid_argument("wat: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
         host_fn f;
-        if (!host_lookup(field, f)) throw std::invalid_argument("wat: env." + field + " is not supported by the bounded front end");
+        if (!host_lookup(field, f)) throw std::invalid_argument("wat: env." + printable(field) + " is not supported by the front end");
+        const std::string shown = "call env." + field;
+        pop_type(shown);
+        if (f == host_fn::assert_equal) pop_type(shown);
+        if (f == host_fn::i32_private_const || f == host_fn::i64_private_const) types_.push_back(f == host_fn::i32_private_const ? 32 : 64);
+        if (f == host_fn::witness_cast) types_.push_back(field == "witness_cast_u32" ? 32 : 64);
         ins i; i.kind = ins::host_call; i.o = (uint8_t)f; code_.push_back(i);
     }
-    void emit_plain(ins::kind_t k) { ins i; i.kind = k; code_.push_back(i); }
+    void emit_plain(ins::kind_t k) {
+        if (k == ins::drop) pop_type("drop");
+        if (k == ins::end_of_statement) types_.clear();
+        ins i; i.kind = k; code_.push_back(i);
+    }
+    static std::string printable(const std::string &s) {      // names from a binary go into error messages
+        std::string o;
+        for (size_t i = 0; i < s.size() && i < 64; i++) o.push_back((s[i] >= 0x20 && s[i] < 0x7f) ? s[i] : '?');
+        return o;
+    }
 
     // ---- text ------------------------------------------------------------------------------------------------
     struct import_t { std::string module, field; };
@@ -1110,7 +1148,7 @@ private:
                 if (shift < 64) v |= (int64_t)((uint64_t)(b & 0x7f) << shift);
                 shift += 7;
             } while (b & 0x80);
-            if (shift < 64 && (b & 0x40)) v |= -((int64_t)1 << shift);
+            if (shift < 64 && (b & 0x40)) v = (int64_t)((uint64_t)v | (~0ULL << shift));
             return v;
         }
         std::string name() {
@@ -1147,7 +1185,7 @@ private:
                 const size_t n = (size_t)s.uleb();
                 for (size_t i = 0; i < n; i++) {
                     import_t im{s.name(), s.name()};
-                    if (s.byte() != 0x00) throw std::invalid_argument("wasm: only function imports are supported (" + im.module + "." + im.field + ")");
+                    if (s.byte() != 0x00) throw std::invalid_argument("wasm: only function imports are supported (" + printable(im.module + "." + im.field) + ")");
                     s.uleb();
                     if (im.module != "env") throw std::invalid_argument("wasm: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
                     imports.push_back(im);
@@ -1210,6 +1248,7 @@ private:
     }
 
     std::vector<ins> code_;
+    std::vector<uint8_t> types_;                              // static operand widths while the list is built (see pop_type)
 };
 
 }  // namespace ligero::cuda::host

@@ -30,7 +30,7 @@ def lib():
 
 def _check(rc):
     if rc:
-        raise ProverError(lib().lgrp_last_error().decode())
+        raise ProverError(lib().lgrp_last_error().decode("utf-8", "replace"))
 
 
 def _u8(b, n=None):

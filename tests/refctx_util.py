@@ -241,6 +241,11 @@ def _rand_operand(rng, w):
     return rng.choice([0, 1, 2, 3, M - 1, M >> 1, (M >> 1) - 1, 1 << (w // 2), 0x80, 0xff7f, rng.getrandbits(w), rng.getrandbits(w), rng.getrandbits(7), M - 1 - rng.getrandbits(5)])
 
 
+def _typed(w, op, text):
+    """predicates give an i32: widened where the program goes on in 64 bits, so that the module stays valid WebAssembly"""
+    return "(i64.extend_i32_u %s)" % text if w == 64 and (op in ("eqz", "eq", "ne") or op[:2] in ("lt", "gt", "le", "ge")) else text
+
+
 def rand_int_expr(rng, depth, w, ops=None):
     """(folded text, value) of a random expression of width w over every integer instruction: private and literal leaves,
     results that live as bit vectors (arithmetic, bitwise, shifts) and as single witnesses (counts, comparisons) mixed freely"""
@@ -250,26 +255,27 @@ def rand_int_expr(rng, depth, w, ops=None):
         return ("(call $i%d_private_const %s)" % (w, lit) if rng.random() < 0.75 else lit), v
     if ops is None and rng.random() < 0.1:                    # the value as ONE witness (env.witness_cast): a third kind of stack value
         t, v = rand_int_expr(rng, depth - 1, w, ops)
-        return ("(call $cast %s)" % t if "private" in t else t), v
+        return ("(call $cast%d %s)" % (w, t) if "private" in t else t), v
     for _ in range(100):
         op = rng.choice(ops or (UNARY_OPS + BINARY_OPS * 2))
         ta, va = rand_int_expr(rng, depth - 1, w, ops)
         if op in UNARY_OPS:
             if op == "extend16_s" and w == 64 and "private" not in ta:
                 continue                                        # (the reference ZERO-extends a concrete i64 here, interpreter_impl.hpp:1208; the emitter follows it)
-            return "(i%d.%s %s)" % (w, op, ta), wasm_op(op, w, va)
+            return _typed(w, op, "(i%d.%s %s)" % (w, op, ta)), wasm_op(op, w, va)
         tb, vb = rand_int_expr(rng, depth - 1, w, ops)
         if op in ("div_s", "div_u", "rem_s", "rem_u") and "private" not in ta + tb:
             continue                                            # (both concrete: plain host division; nothing to check)
         v = wasm_op(op, w, va, vb)
         if v is not None:
-            return "(i%d.%s %s %s)" % (w, op, ta, tb), v
+            return _typed(w, op, "(i%d.%s %s %s)" % (w, op, ta, tb)), v
     raise RuntimeError("no valid expression found")
 
 
 WAT_HEAD_BOTH = ('(module (import "env" "i32_private_const" (func $i32_private_const (param i32) (result i32)))\n'
                  '(import "env" "i64_private_const" (func $i64_private_const (param i64) (result i64)))\n'
-                 '(import "env" "witness_cast_u64" (func $cast (param i64) (result i64)))\n'
+                 '(import "env" "witness_cast_u64" (func $cast64 (param i64) (result i64)))\n'
+                 '(import "env" "witness_cast_u32" (func $cast32 (param i32) (result i32)))\n'
                  '(import "env" "assert_equal" (func $assert_equal (param i64 i64)))\n(func $t\n')
 
 

@@ -53,7 +53,7 @@ def test_restatement_reproduces_the_reference_run(oracle, case):
 
 
 @pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("case", ["i64_mul3_k256", "vbn_k256"])
+@pytest.mark.parametrize("case", ["i64_mul3_k256", "vbn_k256", "intops_k256"])
 def test_reference_verifier_accepts_the_restated_prover_and_rejects_tampering(oracle, case, tmp_path):
     """the reference's own verifier (nonbatch_verifier_context re-running the program over the sampled columns, recommit,
     the seven checks of src/webgpu_verifier.cpp:412-442) accepts the proof oracle/prover_ref.py makes -- the proof the

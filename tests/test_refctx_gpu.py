@@ -84,7 +84,7 @@ def test_prove_wat_commits_to_the_root_of_the_reference_run(lgr, pr, executor_fa
 
 
 @pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("case", ["i64_mul_k8192", "vbn_k256", "mul64_k256"])
+@pytest.mark.parametrize("case", ["i64_mul_k8192", "vbn_k256", "mul64_k256", "intops_k256"])
 def test_reference_verifier_accepts_the_gpu_proof(lgr, pr, executor_factory, case, tmp_path):
     """the proof lgrp_prove makes on the B200 goes to the REFERENCE's verifier (its nonbatch_verifier_context re-running the
     program over the opened columns, merkle_tree::recommit, the seven checks of src/webgpu_verifier.cpp:412-442): accepted
