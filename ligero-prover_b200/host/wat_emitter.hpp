@@ -2,8 +2,9 @@
 // module -- WebAssembly text (folded, as the reference's tests/*.wat are written, or plain) and WebAssembly binaries, both of
 // which the reference's prover takes (src/webgpu_prover.cpp:189-207) -- and the witness machine behind it.
 // It is NOT the reference's interpreter (include/interpreter_impl.hpp + include/zkp/backend/*.hpp: a general WASM machine with
-// control flow, locals, memory and tables over an expression-template backend; out of scope).  For the instructions it
-// takes -- every integer instruction the reference implements (interpreter_impl.hpp:155-1309), drop, nop, and the env
+// control flow, memory and tables over an expression-template backend; out of scope).  For the instructions it
+// takes -- every integer instruction the reference implements (interpreter_impl.hpp:155-1309), select, drop, nop, locals,
+// calls of the module's own functions, and the env
 // functions iNN_private_const / assert_equal / assert_zero / assert_one / assert_constant / witness_cast / assert_is_concrete
 // (host_modules/env.hpp) -- it gives each one the meaning the reference gives it: which witnesses exist, which draws of the
 // linear stream land on them, and WHEN each one is released into a row.  That order is decided in the reference by C++
@@ -21,6 +22,7 @@
 // The release order follows the lifetimes of C++ objects as GCC orders them (parameters, temporaries, structured
 // bindings); this file leans on the same rules and is built with the same compiler.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -170,6 +172,7 @@ public:
             b_.erase(b_.begin(), b_.begin() + (ptrdiff_t)n);
         }
         void drop_msb(size_t n) { for (size_t i = 0; i < n; i++) b_.pop_back(); }
+        void clear() { while (!b_.empty()) b_.pop_back(); }
 
     private:
         std::vector<wref> b_;
@@ -408,6 +411,7 @@ public:
 
     wref bitwise_xor(const wref &x, const wref &y);
     wref bitwise_xnor(const wref &x, const wref &y);
+    wref bitwise_eqz(const bitvec &x);
     wref bitwise_eq(const bitvec &x, const bitvec &y);
     std::pair<wref, wref> bitwise_gt(const bitvec &x, const bitvec &y, bool is_signed);
     std::pair<wref, wref> idivide_qr(const wref &x, const wref &y);
@@ -459,6 +463,11 @@ inline wexpr operator~(wexpr x) { return wexpr(wexpr::NOT, std::move(x)); }
 // the bit gadgets (core.hpp:789-852)
 inline witness_machine::wref witness_machine::bitwise_xor(const wref &x, const wref &y) { return eval(x + y - (x & y) * K(2)); }
 inline witness_machine::wref witness_machine::bitwise_xnor(const wref &x, const wref &y) { return eval(~(x + y - (x & y) * K(2))); }
+inline witness_machine::wref witness_machine::bitwise_eqz(const bitvec &x) {
+    wref eqz = eval(~x[0]);
+    for (size_t i = 1; i < x.size(); i++) eqz = eval(eqz & ~x[i]);
+    return eqz;
+}
 inline witness_machine::wref witness_machine::bitwise_eq(const bitvec &x, const bitvec &y) {
     wref eq = bitwise_xnor(x[0], y[0]);
     for (size_t i = 1; i < x.size(); i++) eq = eval(eq & bitwise_xnor(x[i], y[i]));
@@ -506,25 +515,14 @@ public:
     // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
     void run(witness_machine &m, wat_stats &st) const {
         run_state rs{m, st, {}};
-        for (const ins &i : code_) {
-            switch (i.kind) {
-            case ins::konst: rs.push(numeric(i.width == 64, i.imm)); break;
-            case ins::unary_op: unary((op)i.o, i.width, i.sgn, rs); break;
-            case ins::shift_op: shift((op)i.o, i.width, i.sgn, rs); break;
-            case ins::binary_op: binary((op)i.o, i.width, i.sgn, rs); break;
-            case ins::host_call: host((host_fn)i.o, rs); break;
-            case ins::drop: rs.pop(); break;                  // exec_drop (interpreter_impl.hpp:112-116)
-            case ins::nop: break;
-            case ins::end_of_statement: while (!rs.stack.empty()) rs.stack.pop_back(); break;
-            }
-        }
-        while (!rs.stack.empty()) rs.stack.pop_back();        // a value nobody consumed dies with the frame
+        call(start_, rs, 0);
+        while (!rs.stack.empty()) rs.stack.pop_back();
         st.linear_constraints = m.draws();
         st.violated_constraints = m.violated();
         st.quadratic_slots = m.slots_made();
         st.linear_witnesses = m.linear_released();
     }
-    size_t instructions() const { return code_.size(); }
+    size_t instructions() const { size_t n = 0; for (const func_t &f : funcs_) n += f.code.size(); return n; }
 
 private:
     using wref = witness_machine::wref;
@@ -540,8 +538,22 @@ private:
         bitvec bits;
         value() = default;
         value(value &&) = default;
-        value &operator=(value &&) = default;
         value(const value &) = delete;
+        // std::variant's move assignment: the same alternative is assigned member-wise (bits element by element), another one
+        // destroys what is held first (a witness is dropped, bits die most significant first) and then takes the new value
+        value &operator=(value &&o) {
+            if (kind != o.kind) {
+                if (kind == WIT) wit.reset();
+                else if (kind == BITS) bits.clear();
+                kind = o.kind;
+            }
+            is64 = o.is64; num = o.num;
+            if (kind == WIT) wit = std::move(o.wit);
+            else if (kind == BITS) bits = o.bits;
+            return *this;
+        }
+        // local.get / local.tee (interpreter_impl.hpp:1855-1900): another handle on the same witnesses
+        value share() const { value r; r.kind = kind; r.is64 = is64; r.num = num; r.wit = wit; r.bits = bits; return r; }
         static value u32(uint32_t v) { value r; r.num = v; return r; }
         static value u64(uint64_t v) { value r; r.is64 = true; r.num = v; return r; }
         static value of(wref w) { value r; r.kind = WIT; r.wit = std::move(w); return r; }
@@ -963,18 +975,81 @@ private:
     }
 
     struct ins {
-        enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, drop, nop, end_of_statement } kind;
+        enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, func_call, local_get, local_set, local_tee, select, drop, nop, end_of_statement } kind;
         uint8_t o = 0;                                        // op or host_fn
         uint8_t width = 0;
         bool sgn = false;
-        uint64_t imm = 0;
+        uint64_t imm = 0;                                     // literal, local index, or function index (module functions from 0)
     };
-    // A light validator rides along with the instruction list: the static width (32 / 64) of every stack slot.  wabt would
-    // have validated the module for the reference; here an instruction applied to a value of the other width is rejected
-    // (the handlers index operand bits by the instruction's width).  Host calls are checked for operand COUNT only: the
-    // reference's own tests call assert_equal (param i64 i64) with i32 operands.
+    // a module function: signature, locals (parameters first), flat body
+    struct func_t {
+        std::vector<uint8_t> params, results, locals;         // widths (32 / 64); locals = params + declared locals
+        std::vector<ins> code;
+    };
+
+    // run_call (interpreter.hpp:274-345): arguments become the first locals, declared locals start at zero, the frame --
+    // and with it whatever the locals still hold, last local first -- dies when the body is through
+    void call(size_t fi, run_state &rs, int depth) const {
+        if (depth > 200) throw std::invalid_argument("wat: call depth exceeded");
+        const func_t &f = funcs_[fi];
+        std::vector<value> arguments;
+        for (size_t i = 0; i < f.params.size(); i++) arguments.emplace_back(rs.pop());
+        std::reverse(arguments.begin(), arguments.end());
+        struct frame {                                         // ~wasm_frame (stack_value.hpp:261-266): the last local dies first
+            std::vector<value> locals;
+            ~frame() { while (!locals.empty()) locals.pop_back(); }
+        } fr;
+        fr.locals = std::move(arguments);
+        for (size_t i = f.params.size(); i < f.locals.size(); i++) fr.locals.emplace_back(numeric(f.locals[i] == 64, 0));
+        for (const ins &i : f.code) {
+            switch (i.kind) {
+            case ins::konst: rs.push(numeric(i.width == 64, i.imm)); break;
+            case ins::unary_op: unary((op)i.o, i.width, i.sgn, rs); break;
+            case ins::shift_op: shift((op)i.o, i.width, i.sgn, rs); break;
+            case ins::binary_op: binary((op)i.o, i.width, i.sgn, rs); break;
+            case ins::host_call: host((host_fn)i.o, rs); break;
+            case ins::func_call: call((size_t)i.imm, rs, depth + 1); break;
+            case ins::local_get: rs.push(fr.locals[(size_t)i.imm].share()); break;
+            case ins::local_set: fr.locals[(size_t)i.imm] = rs.pop(); break;
+            case ins::local_tee: fr.locals[(size_t)i.imm] = rs.stack.back().share(); break;
+            case ins::select: select(rs); break;
+            case ins::drop: rs.pop(); break;                  // exec_drop (interpreter_impl.hpp:112-116)
+            case ins::nop: break;
+            case ins::end_of_statement: while (rs.stack.size() > (size_t)i.imm) rs.stack.pop_back(); break;
+            }
+        }
+    }
+    // exec_select (interpreter_impl.hpp:118-140): a concrete condition removes one of the two values from the stack; a witness
+    // condition is compared with zero bit by bit and the result is is_zero * second + ~is_zero * first, one new witness
+    static void select(run_state &rs) {
+        witness_machine &m = rs.m;
+        value sc = rs.pop();
+        if (sc.kind == value::NUM) {
+            const size_t victim = rs.stack.size() - (sc.as_u32() ? 1 : 2);
+            { value gone(std::move(rs.stack[victim])); }
+            rs.stack.erase(rs.stack.begin() + (ptrdiff_t)victim);
+            return;
+        }
+        rs.st.arithmetic_ops++;
+        bitvec c = rs.make_decomposed(std::move(sc), 32);
+        wref f = rs.make_witness(rs.pop());
+        wref t = rs.make_witness(rs.pop());
+        wref is_zero = m.bitwise_eqz(c);
+        wref v = m.eval(is_zero * f + ~is_zero * t);
+        rs.push(value::of(std::move(v)));
+    }
+
+    // ---- building the instruction lists.  A light validator rides along: the static width (32 / 64) of every stack slot.
+    // wabt would have parsed (not validated) the module for the reference; here an instruction applied to a value of the
+    // other width is rejected (the handlers index operand bits by the instruction's width).  Host calls are checked for
+    // operand COUNT only: the reference's own tests call assert_equal (param i64 i64) with i32 operands.
+    struct import_t { std::string module, field; };
+    func_t *cur_ = nullptr;                                   // the function being built
+    std::vector<uint8_t> types_;
+    size_t floor_ = 0;                                        // stack height below which the current statement may not reach
+
     uint8_t pop_type(const std::string &shown) {
-        if (types_.empty()) throw std::invalid_argument("wat: operand stack underflow at " + shown);
+        if (types_.size() <= floor_) throw std::invalid_argument("wat: operand stack underflow at " + shown);
         const uint8_t t = types_.back();
         types_.pop_back();
         return t;
@@ -983,6 +1058,7 @@ private:
         const uint8_t t = pop_type(shown);
         if (t != width) throw std::invalid_argument("wat: type mismatch: " + shown + " applied to an i" + std::to_string((int)t) + " value");
     }
+    void put(ins::kind_t k, uint64_t imm = 0) { ins i; i.kind = k; i.imm = imm; cur_->code.push_back(i); }
     void emit_op(const std::string &name, int width, const std::string &shown) {
         opinfo oi;
         if (!lookup(name, oi)) throw std::invalid_argument("wat: unsupported instruction " + shown);
@@ -996,11 +1072,11 @@ private:
         ins i;
         i.kind = oi.arity == 1 ? ins::unary_op : (oi.arity == 3 ? ins::shift_op : ins::binary_op);
         i.o = (uint8_t)oi.o; i.width = (uint8_t)width; i.sgn = oi.sgn;
-        code_.push_back(i);
+        cur_->code.push_back(i);
     }
     void emit_const(int width, uint64_t v) {
         types_.push_back((uint8_t)width);
-        ins i; i.kind = ins::konst; i.width = (uint8_t)width; i.imm = width == 32 ? (v & 0xFFFFFFFFULL) : v; code_.push_back(i);
+        ins i; i.kind = ins::konst; i.width = (uint8_t)width; i.imm = width == 32 ? (v & 0xFFFFFFFFULL) : v; cur_->code.push_back(i);
     }
     void emit_host(const std::string &module, const std::string &field) {
         if (module != "env") throw std::invalid_argument("wat: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
@@ -1011,28 +1087,66 @@ private:
         if (f == host_fn::assert_equal) pop_type(shown);
         if (f == host_fn::i32_private_const || f == host_fn::i64_private_const) types_.push_back(f == host_fn::i32_private_const ? 32 : 64);
         if (f == host_fn::witness_cast) types_.push_back(field == "witness_cast_u32" ? 32 : 64);
-        ins i; i.kind = ins::host_call; i.o = (uint8_t)f; code_.push_back(i);
+        ins i; i.kind = ins::host_call; i.o = (uint8_t)f; cur_->code.push_back(i);
+    }
+    // a call by function index: imports first, then the module's own functions
+    void emit_call(uint64_t index, const std::vector<import_t> &imports) {
+        if (index < imports.size()) { emit_host(imports[(size_t)index].module, imports[(size_t)index].field); return; }
+        const uint64_t fi = index - imports.size();
+        if (fi >= funcs_.size()) throw std::invalid_argument("wat: call of an unknown function (" + std::to_string(index) + ")");
+        const func_t &f = funcs_[(size_t)fi];
+        for (size_t i = f.params.size(); i-- > 0;) want(f.params[i], "call " + std::to_string(index));
+        for (uint8_t r : f.results) types_.push_back(r);
+        put(ins::func_call, fi);
+    }
+    void emit_local(ins::kind_t k, uint64_t index) {
+        if (index >= cur_->locals.size()) throw std::invalid_argument("wat: unknown local " + std::to_string(index));
+        const uint8_t t = cur_->locals[(size_t)index];
+        if (k == ins::local_get) types_.push_back(t);
+        else { want(t, k == ins::local_set ? "local.set" : "local.tee"); if (k == ins::local_tee) types_.push_back(t); }
+        put(k, index);
     }
     void emit_plain(ins::kind_t k) {
         if (k == ins::drop) pop_type("drop");
-        if (k == ins::end_of_statement) types_.clear();
-        ins i; i.kind = k; code_.push_back(i);
+        if (k == ins::select) {
+            want(32, "select");
+            const uint8_t b = pop_type("select");
+            want(b, "select");
+            types_.push_back(b);
+        }
+        if (k == ins::end_of_statement) { types_.resize(floor_); put(k, floor_); return; }
+        put(k);
+    }
+    void begin_body(func_t &f) { cur_ = &f; types_.clear(); floor_ = 0; }
+    void end_body(const std::string &name) {
+        if (types_.size() != cur_->results.size()) throw std::invalid_argument("wat: " + name + " leaves " + std::to_string(types_.size()) + " values, its type says " + std::to_string(cur_->results.size()));
+        for (size_t i = 0; i < types_.size(); i++) if (types_[i] != cur_->results[i]) throw std::invalid_argument("wat: " + name + " returns a value of the wrong width");
+        cur_ = nullptr;
     }
     static std::string printable(const std::string &s) {      // names from a binary go into error messages
         std::string o;
         for (size_t i = 0; i < s.size() && i < 64; i++) o.push_back((s[i] >= 0x20 && s[i] < 0x7f) ? s[i] : '?');
         return o;
     }
+    static uint8_t width_of(const std::string &t) {
+        if (t == "i32") return 32;
+        if (t == "i64") return 64;
+        throw std::invalid_argument("wat: only i32 and i64 values are supported (" + printable(t) + ")");
+    }
 
     // ---- text ------------------------------------------------------------------------------------------------
-    struct import_t { std::string module, field; };
+    struct text_scope {
+        const std::vector<import_t> &imports;
+        const std::map<std::string, size_t> &func_ids;        // $name -> function index (imports first)
+        std::map<std::string, size_t> local_ids;
+    };
     void parse_text(const std::string &text) {
         sexpr_parser p(text);
         const sexpr top = p.parse_top();
         if (top.head() != "module") throw std::invalid_argument("wat: expected (module ...)");
         std::vector<import_t> imports;
-        std::map<std::string, size_t> import_ids;
-        std::map<std::string, const sexpr *> funcs;
+        std::map<std::string, size_t> func_ids;
+        std::vector<const sexpr *> bodies;
         std::string start;
         for (size_t i = 1; i < top.list.size(); i++) {
             const sexpr &f = top.list[i];
@@ -1040,49 +1154,80 @@ private:
                 // (import "env" "name" (func $id ...))
                 if (f.list.size() < 4 || f.list[3].head() != "func") throw std::invalid_argument("wat: unsupported import");
                 if (f.list[1].atom != "\"env\"") throw std::invalid_argument("wat: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
-                if (f.list[3].list.size() >= 2 && !f.list[3].list[1].is_list) import_ids[f.list[3].list[1].atom] = imports.size();
+                if (!bodies.empty()) throw std::invalid_argument("wat: imports must come before the module's functions");
+                if (f.list[3].list.size() >= 2 && !f.list[3].list[1].is_list) func_ids[f.list[3].list[1].atom] = imports.size();
                 imports.push_back(import_t{unquote(f.list[1].atom), unquote(f.list[2].atom)});
             } else if (f.head() == "func") {
-                if (f.list.size() < 2 || f.list[1].is_list) throw std::invalid_argument("wat: functions must be named");
-                funcs[f.list[1].atom] = &f;
+                if (f.list.size() >= 2 && !f.list[1].is_list) func_ids[f.list[1].atom] = imports.size() + bodies.size();
+                bodies.push_back(&f);
             } else if (f.head() == "export") {
                 if (f.list.size() >= 3 && unquote(f.list[1].atom) == "_start" && f.list[2].head() == "func" && f.list[2].list.size() == 2) start = f.list[2].list[1].atom;
             } else {
                 throw std::invalid_argument("wat: unsupported module field (" + f.head() + ")");
             }
         }
-        if (start.empty() || !funcs.count(start)) throw std::invalid_argument("wat: no exported _start function");
-        const sexpr &f = *funcs.at(start);
-        const auto callee = [&](const std::string &id) -> const import_t & {
-            const auto it = import_ids.find(id);
-            if (it != import_ids.end()) return imports[it->second];
-            if (!id.empty() && id[0] >= '0' && id[0] <= '9' && parse_i64(id) < imports.size()) return imports[(size_t)parse_i64(id)];
-            throw std::invalid_argument("wat: call of a non-imported function is not supported (" + id + ")");
-        };
-        for (size_t i = 2; i < f.list.size(); i++) {
-            const sexpr &e = f.list[i];
-            if (e.is_list) {
+        // signatures first (a body may call a later function), then the bodies
+        funcs_.resize(bodies.size());
+        std::vector<std::map<std::string, size_t>> local_ids(bodies.size());
+        std::vector<size_t> first_instr(bodies.size());
+        for (size_t k = 0; k < bodies.size(); k++) {
+            const sexpr &f = *bodies[k];
+            func_t &fn = funcs_[k];
+            size_t i = (f.list.size() >= 2 && !f.list[1].is_list) ? 2 : 1;
+            for (; i < f.list.size() && f.list[i].is_list; i++) {
+                const sexpr &e = f.list[i];
                 const std::string &h = e.head();
-                if (h == "param" || h == "result" || h == "local" || h == "type") {
-                    if (h != "type" && e.list.size() > 1) throw std::invalid_argument("wat: _start with parameters / locals is not supported");
+                if (h == "type") continue;
+                if (h != "param" && h != "result" && h != "local") break;
+                if (h != "param" && fn.locals.size() < fn.params.size()) throw std::invalid_argument("wat: malformed function header");
+                size_t j = 1;
+                if (h != "result" && e.list.size() == 3 && !e.list[1].atom.empty() && e.list[1].atom[0] == '$') { local_ids[k][e.list[1].atom] = fn.locals.size(); j = 2; }
+                for (; j < e.list.size(); j++) {
+                    const uint8_t w = width_of(e.list[j].atom);
+                    if (h == "result") { fn.results.push_back(w); continue; }
+                    if (h == "param") { if (fn.locals.size() != fn.params.size()) throw std::invalid_argument("wat: parameters must come before locals"); fn.params.push_back(w); }
+                    fn.locals.push_back(w);
+                }
+            }
+            first_instr[k] = i;
+        }
+        if (start.empty()) throw std::invalid_argument("wat: no exported _start function");
+        const auto sit = func_ids.find(start);
+        size_t start_index;
+        if (sit != func_ids.end()) start_index = sit->second;
+        else if (start[0] >= '0' && start[0] <= '9') start_index = (size_t)parse_i64(start);
+        else throw std::invalid_argument("wat: no exported _start function");
+        if (start_index < imports.size() || start_index - imports.size() >= funcs_.size()) throw std::invalid_argument("wat: no exported _start function");
+        start_ = start_index - imports.size();
+        if (!funcs_[start_].params.empty() || !funcs_[start_].results.empty()) throw std::invalid_argument("wat: _start with parameters / results is not supported");
+        for (size_t k = 0; k < bodies.size(); k++) {
+            const sexpr &f = *bodies[k];
+            func_t &fn = funcs_[k];
+            text_scope sc{imports, func_ids, local_ids[k]};
+            begin_body(fn);
+            for (size_t i = first_instr[k]; i < f.list.size(); i++) {
+                const sexpr &e = f.list[i];
+                if (e.is_list) {
+                    flatten(e, sc);
+                    if (fn.results.empty()) emit_plain(ins::end_of_statement);   // a value nobody consumed dies here
                     continue;
                 }
-                flatten(e, callee);
-                emit_plain(ins::end_of_statement);
-                continue;
+                // plain (unfolded) instructions: immediates follow their instruction
+                const std::string &a = e.atom;
+                const auto next = [&]() -> const std::string & {
+                    if (i + 1 >= f.list.size() || f.list[i + 1].is_list) throw std::invalid_argument("wat: " + a + " needs an immediate");
+                    return f.list[++i].atom;
+                };
+                if (a == "i32.const" || a == "i64.const") emit_const(a[1] == '3' ? 32 : 64, literal(a, next()));
+                else if (a == "call") emit_call(func_index(next(), sc), imports);
+                else if (a == "local.get" || a == "local.set" || a == "local.tee") emit_local(a == "local.get" ? ins::local_get : (a == "local.set" ? ins::local_set : ins::local_tee), local_index(next(), sc));
+                else if (a == "select") emit_plain(ins::select);
+                else if (a == "drop") emit_plain(ins::drop);
+                else if (a == "nop") emit_plain(ins::nop);
+                else if (a.size() > 4 && (a.compare(0, 4, "i32.") == 0 || a.compare(0, 4, "i64.") == 0)) emit_op(a.substr(4), a[1] == '3' ? 32 : 64, a);
+                else throw std::invalid_argument("wat: unsupported instruction " + a);
             }
-            // plain (unfolded) instructions: immediates follow their instruction
-            const std::string &a = e.atom;
-            const auto next = [&]() -> const std::string & {
-                if (i + 1 >= f.list.size() || f.list[i + 1].is_list) throw std::invalid_argument("wat: " + a + " needs an immediate");
-                return f.list[++i].atom;
-            };
-            if (a == "i32.const" || a == "i64.const") emit_const(a[1] == '3' ? 32 : 64, literal(a, next()));
-            else if (a == "call") { const import_t &c = callee(next()); emit_host(c.module, c.field); }
-            else if (a == "drop") emit_plain(ins::drop);
-            else if (a == "nop") emit_plain(ins::nop);
-            else if (a.size() > 4 && (a.compare(0, 4, "i32.") == 0 || a.compare(0, 4, "i64.") == 0)) emit_op(a.substr(4), a[1] == '3' ? 32 : 64, a);
-            else throw std::invalid_argument("wat: unsupported instruction " + a);
+            end_body(f.list.size() >= 2 && !f.list[1].is_list ? f.list[1].atom : "function " + std::to_string(k));
         }
     }
     static uint64_t literal(const std::string &instr, const std::string &lit) {
@@ -1090,11 +1235,23 @@ private:
         if (instr[1] == '3' && v > 0xFFFFFFFFULL && v < 0xFFFFFFFF80000000ULL) throw std::invalid_argument("wat: integer literal out of range " + lit);
         return v;
     }
-    // one folded instruction: operands first (each leaves one value on the stack), then the instruction itself
-    template <typename Callee>
-    void flatten(const sexpr &e, const Callee &callee) {
+    static uint64_t func_index(const std::string &id, const text_scope &sc) {
+        const auto it = sc.func_ids.find(id);
+        if (it != sc.func_ids.end()) return it->second;
+        if (!id.empty() && id[0] >= '0' && id[0] <= '9') return parse_i64(id);
+        throw std::invalid_argument("wat: call of an unknown function (" + id + ")");
+    }
+    static uint64_t local_index(const std::string &id, const text_scope &sc) {
+        const auto it = sc.local_ids.find(id);
+        if (it != sc.local_ids.end()) return it->second;
+        if (!id.empty() && id[0] >= '0' && id[0] <= '9') return parse_i64(id);
+        throw std::invalid_argument("wat: unknown local " + id);
+    }
+    // one folded instruction: operands first (each leaves its value on the stack), then the instruction itself
+    void flatten(const sexpr &e, const text_scope &sc) {
         if (!e.is_list) throw std::invalid_argument("wat: only folded instructions are supported inside a folded form (" + e.atom + ")");
         const std::string &h = e.head();
+        const auto operands = [&](size_t from) { for (size_t i = from; i < e.list.size(); i++) flatten(e.list[i], sc); };
         if (h == "i64.const" || h == "i32.const") {
             if (e.list.size() != 2) throw std::invalid_argument("wat: " + h + " takes one literal");
             emit_const(h[1] == '3' ? 32 : 64, literal(h, e.list[1].atom));
@@ -1103,24 +1260,32 @@ private:
         if (h.size() > 4 && (h.compare(0, 4, "i32.") == 0 || h.compare(0, 4, "i64.") == 0)) {
             opinfo oi;
             if (!lookup(h.substr(4), oi)) throw std::invalid_argument("wat: unsupported instruction " + h);
-            const int operands = oi.arity == 1 ? 1 : 2;
-            if ((int)e.list.size() != 1 + operands) throw std::invalid_argument("wat: " + h + " takes " + (operands == 1 ? "one folded operand" : "two folded operands"));
-            for (int i = 1; i <= operands; i++) flatten(e.list[(size_t)i], callee);
+            const int n = oi.arity == 1 ? 1 : 2;
+            if ((int)e.list.size() != 1 + n) throw std::invalid_argument("wat: " + h + " takes " + (n == 1 ? "one folded operand" : "two folded operands"));
+            operands(1);
             emit_op(h.substr(4), h[1] == '3' ? 32 : 64, h);
             return;
         }
         if (h == "call") {
             if (e.list.size() < 2 || e.list[1].is_list) throw std::invalid_argument("wat: call without a target");
-            const import_t &c = callee(e.list[1].atom);
-            for (size_t i = 2; i < e.list.size(); i++) flatten(e.list[i], callee);
-            emit_host(c.module, c.field);
+            const uint64_t index = func_index(e.list[1].atom, sc);
+            operands(2);
+            emit_call(index, sc.imports);
             return;
         }
-        if (h == "drop") {
-            for (size_t i = 1; i < e.list.size(); i++) flatten(e.list[i], callee);
-            emit_plain(ins::drop);
+        if (h == "local.get" || h == "local.set" || h == "local.tee") {
+            if (e.list.size() < 2 || e.list[1].is_list || e.list.size() != (h == "local.get" ? 2u : 3u)) throw std::invalid_argument("wat: malformed " + h);
+            operands(2);
+            emit_local(h == "local.get" ? ins::local_get : (h == "local.set" ? ins::local_set : ins::local_tee), local_index(e.list[1].atom, sc));
             return;
         }
+        if (h == "select") {
+            if (e.list.size() != 4) throw std::invalid_argument("wat: select takes three folded operands");
+            operands(1);
+            emit_plain(ins::select);
+            return;
+        }
+        if (h == "drop") { operands(1); emit_plain(ins::drop); return; }
         if (h == "nop") { emit_plain(ins::nop); return; }
         throw std::invalid_argument("wat: unsupported instruction " + h);
     }
@@ -1145,7 +1310,7 @@ private:
             do {
                 b = byte();
                 if (shift >= bits + 7) throw std::invalid_argument("wasm: malformed LEB128 integer");
-                if (shift < 64) v |= (int64_t)((uint64_t)(b & 0x7f) << shift);
+                if (shift < 64) v = (int64_t)((uint64_t)v | ((uint64_t)(b & 0x7f) << shift));
                 shift += 7;
             } while (b & 0x80);
             if (shift < 64 && (b & 0x40)) v = (int64_t)((uint64_t)v | (~0ULL << shift));
@@ -1164,21 +1329,43 @@ private:
             p += n;
             return r;
         }
+        uint8_t valtype() {
+            const uint8_t t = byte();
+            if (t == 0x7f) return 32;
+            if (t == 0x7e) return 64;
+            throw std::invalid_argument("wasm: only i32 and i64 values are supported");
+        }
     };
     void parse_binary(const std::string &data) {
         reader r{(const uint8_t *)data.data(), (const uint8_t *)data.data() + data.size()};
         r.p += 4;
         if (r.sub(4).p[0] != 1) throw std::invalid_argument("wasm: unsupported binary version");
+        struct sig { std::vector<uint8_t> params, results; bool usable = true; };
+        std::vector<sig> types;
         std::vector<import_t> imports;
-        size_t nfuncs = 0;
+        std::vector<uint64_t> func_types;
         int64_t start = -1;
         std::vector<reader> bodies;
         while (r.p < r.end) {
             const uint8_t id = r.byte();
             reader s = r.sub((size_t)r.uleb());
             switch (id) {
-            case 0: case 1: case 3: case 12: {                // custom / type / function / data count: nothing the straight-line subset needs
-                if (id == 3) nfuncs = (size_t)s.uleb();
+            case 0: case 12: break;                           // custom / data count: nothing the subset needs
+            case 1: {                                         // types (a type naming other value types only matters if a module function uses it)
+                const size_t n = (size_t)s.uleb();
+                for (size_t i = 0; i < n; i++) {
+                    if (s.byte() != 0x60) throw std::invalid_argument("wasm: malformed type section");
+                    sig t;
+                    for (int part = 0; part < 2; part++) {
+                        const size_t cnt = (size_t)s.uleb();
+                        for (size_t j = 0; j < cnt; j++) {
+                            const uint8_t v = s.byte();
+                            if (v != 0x7f && v != 0x7e) t.usable = false;
+                            (part ? t.results : t.params).push_back(v == 0x7f ? 32 : 64);
+                        }
+                    }
+                    types.push_back(t);
+                }
                 break;
             }
             case 2: {                                         // imports: functions of env only
@@ -1190,6 +1377,11 @@ private:
                     if (im.module != "env") throw std::invalid_argument("wasm: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
                     imports.push_back(im);
                 }
+                break;
+            }
+            case 3: {
+                const size_t n = (size_t)s.uleb();
+                for (size_t i = 0; i < n; i++) func_types.push_back(s.uleb());
                 break;
             }
             case 7: {                                         // exports: the function called _start
@@ -1211,44 +1403,61 @@ private:
                 throw std::invalid_argument("wasm: unsupported module section (id " + std::to_string(id) + ")");
             }
         }
-        if (start < 0 || (size_t)start < imports.size() || (size_t)start - imports.size() >= bodies.size() || bodies.size() != nfuncs)
-            throw std::invalid_argument("wasm: no exported _start function");
-        reader b = bodies[(size_t)start - imports.size()];
-        if (b.uleb() != 0) throw std::invalid_argument("wasm: _start with locals is not supported");
+        if (bodies.size() != func_types.size()) throw std::invalid_argument("wasm: function and code sections disagree");
+        if (start < 0 || (size_t)start < imports.size() || (size_t)start - imports.size() >= bodies.size()) throw std::invalid_argument("wasm: no exported _start function");
+        start_ = (size_t)start - imports.size();
+        funcs_.resize(bodies.size());
+        for (size_t k = 0; k < bodies.size(); k++) {
+            if (func_types[k] >= types.size() || !types[(size_t)func_types[k]].usable) throw std::invalid_argument("wasm: function " + std::to_string(k) + " has an unsupported type");
+            funcs_[k].params = funcs_[k].locals = types[(size_t)func_types[k]].params;
+            funcs_[k].results = types[(size_t)func_types[k]].results;
+            reader &b = bodies[k];
+            const size_t groups = (size_t)b.uleb();
+            for (size_t g = 0; g < groups; g++) {
+                const uint64_t cnt = b.uleb();
+                const uint8_t w = b.valtype();
+                if (cnt > 10000 || funcs_[k].locals.size() + cnt > 10000) throw std::invalid_argument("wasm: too many locals");
+                funcs_[k].locals.insert(funcs_[k].locals.end(), (size_t)cnt, w);
+            }
+        }
+        if (!funcs_[start_].params.empty() || !funcs_[start_].results.empty()) throw std::invalid_argument("wasm: _start with parameters / results is not supported");
         static const char *const int_ops[] = {"clz", "ctz", "popcnt", "add", "sub", "mul", "div_s", "div_u", "rem_s", "rem_u", "and", "or", "xor", "shl", "shr_s", "shr_u", "rotl", "rotr"};
         static const char *const cmp_ops[] = {"eqz", "eq", "ne", "lt_s", "lt_u", "gt_s", "gt_u", "le_s", "le_u", "ge_s", "ge_u"};
-        for (;;) {
-            const uint8_t c = b.byte();
-            if (c == 0x0B) break;                             // end
-            const std::string shown = "0x" + std::string(1, "0123456789abcdef"[c >> 4]) + std::string(1, "0123456789abcdef"[c & 15]);
-            if (c == 0x01) emit_plain(ins::nop);
-            else if (c == 0x1A) emit_plain(ins::drop);
-            else if (c == 0x10) {
-                const uint64_t f = b.uleb();
-                if (f >= imports.size()) throw std::invalid_argument("wasm: call of a non-imported function is not supported (" + std::to_string(f) + ")");
-                emit_host(imports[(size_t)f].module, imports[(size_t)f].field);
+        for (size_t k = 0; k < bodies.size(); k++) {
+            reader &b = bodies[k];
+            begin_body(funcs_[k]);
+            for (;;) {
+                const uint8_t c = b.byte();
+                if (c == 0x0B) break;                         // end
+                const std::string shown = "0x" + std::string(1, "0123456789abcdef"[c >> 4]) + std::string(1, "0123456789abcdef"[c & 15]);
+                if (c == 0x01) emit_plain(ins::nop);
+                else if (c == 0x1A) emit_plain(ins::drop);
+                else if (c == 0x1B) emit_plain(ins::select);
+                else if (c == 0x10) emit_call(b.uleb(), imports);
+                else if (c == 0x20 || c == 0x21 || c == 0x22) emit_local(c == 0x20 ? ins::local_get : (c == 0x21 ? ins::local_set : ins::local_tee), b.uleb());
+                else if (c == 0x41) emit_const(32, (uint64_t)b.sleb(32));
+                else if (c == 0x42) emit_const(64, (uint64_t)b.sleb(64));
+                else if (c >= 0x45 && c <= 0x4F) emit_op(cmp_ops[c - 0x45], 32, shown);
+                else if (c >= 0x50 && c <= 0x5A) emit_op(cmp_ops[c - 0x50], 64, shown);
+                else if (c >= 0x67 && c <= 0x78) emit_op(int_ops[c - 0x67], 32, shown);
+                else if (c >= 0x79 && c <= 0x8A) emit_op(int_ops[c - 0x79], 64, shown);
+                else if (c == 0xA7) emit_op("wrap_i64", 32, shown);
+                else if (c == 0xAC) emit_op("extend_i32_s", 64, shown);
+                else if (c == 0xAD) emit_op("extend_i32_u", 64, shown);
+                else if (c == 0xC0) emit_op("extend8_s", 32, shown);
+                else if (c == 0xC1) emit_op("extend16_s", 32, shown);
+                else if (c == 0xC2) emit_op("extend8_s", 64, shown);
+                else if (c == 0xC3) emit_op("extend16_s", 64, shown);
+                else if (c == 0xC4) emit_op("extend32_s", 64, shown);
+                else throw std::invalid_argument("wasm: unsupported instruction " + shown);
             }
-            else if (c == 0x41) emit_const(32, (uint64_t)b.sleb(32));
-            else if (c == 0x42) emit_const(64, (uint64_t)b.sleb(64));
-            else if (c >= 0x45 && c <= 0x4F) emit_op(cmp_ops[c - 0x45], 32, shown);
-            else if (c >= 0x50 && c <= 0x5A) emit_op(cmp_ops[c - 0x50], 64, shown);
-            else if (c >= 0x67 && c <= 0x78) emit_op(int_ops[c - 0x67], 32, shown);
-            else if (c >= 0x79 && c <= 0x8A) emit_op(int_ops[c - 0x79], 64, shown);
-            else if (c == 0xA7) emit_op("wrap_i64", 32, shown);
-            else if (c == 0xAC) emit_op("extend_i32_s", 64, shown);
-            else if (c == 0xAD) emit_op("extend_i32_u", 64, shown);
-            else if (c == 0xC0) emit_op("extend8_s", 32, shown);
-            else if (c == 0xC1) emit_op("extend16_s", 32, shown);
-            else if (c == 0xC2) emit_op("extend8_s", 64, shown);
-            else if (c == 0xC3) emit_op("extend16_s", 64, shown);
-            else if (c == 0xC4) emit_op("extend32_s", 64, shown);
-            else throw std::invalid_argument("wasm: unsupported instruction " + shown);
+            if (b.p != b.end) throw std::invalid_argument("wasm: bytes after the end of a function body");
+            end_body("function " + std::to_string(k));
         }
-        if (b.p != b.end) throw std::invalid_argument("wasm: bytes after the end of _start");
     }
 
-    std::vector<ins> code_;
-    std::vector<uint8_t> types_;                              // static operand widths while the list is built (see pop_type)
+    std::vector<func_t> funcs_;
+    size_t start_ = 0;
 };
 
 }  // namespace ligero::cuda::host

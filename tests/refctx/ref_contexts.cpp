@@ -114,18 +114,34 @@ struct tiny_module {
         for (size_t i = 0; i < t.size(); i++) if (t[i].first == name) return (int)i;
         return -1;
     }
-    explicit tiny_module(std::vector<instr_ptr> body) {
+    // a function of the module itself: signature, declared locals, body; `_start` is functions[start]
+    struct module_func {
+        std::vector<value_kind> params, results, locals;
+        std::vector<instr_ptr> body;
+    };
+    explicit tiny_module(std::vector<module_func> functions, size_t start_function) {
         function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_pc32({value_kind::i32}, {value_kind::i32}),
-            k_one({value_kind::i64}, {}), k_start({}, {});
-        inst.types = {k_pc, k_eq, k_pc32, k_one, k_start};
+            k_one({value_kind::i64}, {});
+        inst.types = {k_pc, k_eq, k_pc32, k_one};
         const function_kind *shapes[4] = {&k_pc, &k_eq, &k_pc32, &k_one};
         const auto &t = env_imports();
         for (size_t i = 0; i < t.size(); i++)
             inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t(t[i].first), *shapes[t[i].second], &inst, function_instance::host_code{(index_t)i, "env", t[i].first}));
-        const index_t start = (index_t)t.size();
-        inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("_start"), k_start, &inst, function_instance::func_code{start, {}, std::move(body)}));
+        for (size_t k = 0; k < functions.size(); k++) {
+            function_kind kind(functions[k].params, functions[k].results);
+            inst.types.push_back(kind);
+            const index_t index = (index_t)(t.size() + k);
+            inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("f" + std::to_string(k)), kind, &inst,
+                                                                           function_instance::func_code{index, functions[k].locals, std::move(functions[k].body)}));
+        }
         inst.memaddrs.push_back(store.emplace_back<memory_instance>(memory_kind(limits(1)), memory_instance::page_size));
-        inst.exports["_start"] = start;
+        inst.exports["_start"] = (index_t)(t.size() + start_function);
+    }
+    explicit tiny_module(std::vector<instr_ptr> body) : tiny_module(single(std::move(body)), 0) {}
+    static std::vector<module_func> single(std::vector<instr_ptr> body) {
+        std::vector<module_func> f(1);
+        f[0].body = std::move(body);
+        return f;
     }
 };
 
@@ -134,7 +150,7 @@ struct tiny_module {
 // (plus the short forms c / pc / eq / mul of the built-in i64_mul program)
 // assembled the way transpile() (include/transpiler.hpp:741-776) would: runs of plain opcodes become basic blocks, calls
 // stand alone.
-struct wasm_token { std::string op; uint64_t imm = 0; };
+struct wasm_token { std::string op; uint64_t imm = 0; std::vector<std::string> types; };
 
 static std::vector<instr_ptr> assemble(const std::vector<wasm_token> &toks) {
     std::vector<instr_ptr> body;
@@ -185,6 +201,11 @@ static std::vector<instr_ptr> assemble(const std::vector<wasm_token> &toks) {
         else if (t.op.rfind("call:", 0) == 0 && tiny_module::import_index(t.op.substr(5)) >= 0) { flush(); body.push_back(make_instr<call>((index_t)tiny_module::import_index(t.op.substr(5)))); }
         else if (t.op == "drop") plain(opcode(opcode::drop));
         else if (t.op == "nop") plain(opcode(opcode::nop));
+        else if (t.op == "select") plain(opcode(opcode::select, value_kind::unit, value_kind::unit));
+        else if (t.op == "local.get") plain(opcode(opcode::local_get, (index_t)t.imm));
+        else if (t.op == "local.set") plain(opcode(opcode::local_set, (index_t)t.imm));
+        else if (t.op == "local.tee") plain(opcode(opcode::local_tee, (index_t)t.imm));
+        else if (t.op == "callf") { flush(); body.push_back(make_instr<call>((index_t)(tiny_module::env_imports().size() + t.imm))); }
         else throw std::runtime_error("unknown token " + t.op);
     }
     flush();
@@ -226,15 +247,54 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
     std::string op;
     while (in >> op) {
         wasm_token tok{op};
-        if (op == "c" || op == "i32.const" || op == "i64.const") { std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0); }
+        if (op == "c" || op == "i32.const" || op == "i64.const" || op == "local.get" || op == "local.set" || op == "local.tee" || op == "callf" || op == "start") {
+            std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0);
+        }
+        if (op == "func") {                                   // func <params> <results> <locals>, e.g. "func i64,i32 i64 -": a new module function starts
+            for (int j = 0; j < 3; j++) { std::string part; in >> part; tok.types.push_back(part); }
+        }
         t.push_back(tok);
     }
     return t;
 }
 
+// a token stream with "func" headers is a module of several functions ("start K" names _start); without, one function
+static tiny_module build_module(const std::vector<wasm_token> &toks) {
+    bool structured = false;
+    for (const wasm_token &t : toks) structured |= t.op == "func";
+    if (!structured) return tiny_module(assemble(toks));
+    const auto kinds = [](const std::string &list) {
+        std::vector<value_kind> out;
+        if (list == "-") return out;
+        size_t b = 0;
+        while (b <= list.size()) {
+            const size_t e = list.find(',', b);
+            const std::string t = list.substr(b, e == std::string::npos ? std::string::npos : e - b);
+            out.push_back(t == "i32" ? value_kind::i32 : value_kind::i64);
+            if (e == std::string::npos) break;
+            b = e + 1;
+        }
+        return out;
+    };
+    std::vector<tiny_module::module_func> functions;
+    std::vector<wasm_token> body;
+    size_t start = 0;
+    const auto close = [&] { if (!functions.empty()) functions.back().body = assemble(body); body.clear(); };
+    for (const wasm_token &t : toks) {
+        if (t.op == "func") {
+            close();
+            functions.emplace_back();
+            functions.back().params = kinds(t.types[0]); functions.back().results = kinds(t.types[1]); functions.back().locals = kinds(t.types[2]);
+        } else if (t.op == "start") start = (size_t)t.imm;
+        else body.push_back(t);
+    }
+    close();
+    return tiny_module(std::move(functions), start);
+}
+
 template <typename Ctx>
 static void run_wasm_tokens(Ctx &ctx, const std::vector<wasm_token> &toks) {
-    tiny_module m(assemble(toks));
+    tiny_module m = build_module(toks);
     wasm_interpreter<Ctx> interp(ctx);
     ctx.store(&m.store);
     ctx.module(&m.inst);

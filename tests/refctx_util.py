@@ -88,35 +88,89 @@ def _sexpr(text):
     return parse()
 
 
-def wat_to_tokens(text):
-    """'iNN.const <v>' / 'iNN.<op>' / 'call:<env function>', operands first -- what the folded text of the exported function denotes"""
+def wat_module(text):
+    """the parts of a module of the subset: imports (id -> (env name, function index)), functions (id, params, results, locals,
+    body forms, local name -> index) in order, and the index of _start among the module's own functions"""
     mod = _sexpr(text)
-    imports = {f[3][1]: f[2].strip('"') for f in mod[1:] if f[0] == "import"}
-    start = next(f[2][1] for f in mod[1:] if f[0] == "export" and f[1] == '"_start"')
-    func = next(f for f in mod[1:] if f[0] == "func" and f[1] == start)
-    out = []
+    imports, funcs = {}, []
+    for f in mod[1:]:
+        if f[0] == "import":
+            imports[f[3][1]] = (f[2].strip('"'), len(imports))
+    for f in mod[1:]:
+        if f[0] != "func":
+            continue
+        fn = {"id": f[1] if isinstance(f[1], str) else None, "params": [], "results": [], "locals": [], "names": {}, "body": []}
+        for e in f[2 if fn["id"] else 1:]:
+            if isinstance(e, list) and e[0] in ("param", "local"):
+                rest = e[1:]
+                if len(rest) == 2 and rest[0].startswith("$"):
+                    fn["names"][rest[0]] = len(fn["params"]) + len(fn["locals"])
+                    rest = rest[1:]
+                fn["params" if e[0] == "param" else "locals"].extend(rest)
+            elif isinstance(e, list) and e[0] == "result":
+                fn["results"].extend(e[1:])
+            elif isinstance(e, list) and e[0] == "type":
+                pass
+            else:
+                fn["body"].append(e)
+        funcs.append(fn)
+    start_id = next(f[2][1] for f in mod[1:] if f[0] == "export" and f[1] == '"_start"')
+    ids = {fn["id"]: k for k, fn in enumerate(funcs)}
+    return imports, funcs, ids, ids[start_id]
 
-    def lit(s):
-        s = s.replace("_", "")
-        v = int(s, 0)
-        return v % (1 << 64)
+
+def _lit(s):
+    return int(s.replace("_", ""), 0) % (1 << 64)
+
+
+def _walk(fn, imports, ids, visit):
+    """post-order walk of a function's folded body: visit(kind, name, immediate)"""
+    def local(x):
+        return fn["names"][x] if x in fn["names"] else int(x)
 
     def emit(e):
-        if e[0] in ("i64.const", "i32.const"):
-            out.append("%s %d" % (e[0], lit(e[1]) % (1 << int(e[0][1:3]))))
-        elif e[0] == "call":
+        if isinstance(e, str):
+            raise ValueError("plain instructions are not handled by the test helpers: " + e)
+        h = e[0]
+        if h in ("i64.const", "i32.const"):
+            visit("const", h, _lit(e[1]) % (1 << int(h[1:3])))
+        elif h == "call":
             for a in e[2:]:
                 emit(a)
-            out.append("call:" + imports[e[1]])
-        elif e[0][:4] in ("i32.", "i64.") or e[0] in ("drop", "nop"):
+            if e[1] in imports:
+                visit("host", imports[e[1]][0], imports[e[1]][1])
+            else:
+                visit("callf", e[1], ids[e[1]])
+        elif h in ("local.get", "local.set", "local.tee"):
+            for a in e[2:]:
+                emit(a)
+            visit("local", h, local(e[1]))
+        elif h[:4] in ("i32.", "i64.") or h in ("drop", "nop", "select"):
             for a in e[1:]:
                 emit(a)
-            out.append(e[0])
+            visit("op", h, None)
         else:
-            raise ValueError("unsupported form " + str(e[0]))
-    for e in func[2:]:
-        if isinstance(e, list) and e[0] not in ("param", "result", "local", "type"):
-            emit(e)
+            raise ValueError("unsupported form " + str(h))
+    for e in fn["body"]:
+        emit(e)
+
+
+def wat_to_tokens(text):
+    """'iNN.const <v>' / 'iNN.<op>' / 'call:<env function>' / 'local.get <i>' / 'select' / 'callf <k>', operands first -- what the
+    folded text denotes.  A module with several functions, parameters or locals gets 'func <params> <results> <locals>' headers
+    and 'start <k>' (tests/refctx/ref_contexts.cpp: build_module)"""
+    imports, funcs, ids, start = wat_module(text)
+    out = []
+
+    def visit(kind, name, imm):
+        out.append({"const": "%s %d" % (name, imm or 0), "host": "call:" + name, "callf": "callf %s" % imm, "local": "%s %s" % (name, imm), "op": name}[kind])
+    structured = len(funcs) > 1 or funcs[0]["params"] or funcs[0]["locals"]
+    for fn in funcs:
+        if structured:
+            out.append("func %s %s %s" % tuple(",".join(fn[key]) or "-" for key in ("params", "results", "locals")))
+        _walk(fn, imports, ids, visit)
+    if structured:
+        out.append("start %d" % start)
     return out
 
 
@@ -316,73 +370,152 @@ _OTHER_OPS = {"i32.wrap_i64": 0xA7, "i64.extend_i32_s": 0xAC, "i64.extend_i32_u"
 def wat_to_wasm(text, custom_section=True):
     """binary module for a program of the subset: type, import, function, export and code sections (+ a custom section)"""
     mod = _sexpr(text)
+    imports, funcs, ids, start = wat_module(text)
     vt = {"i32": 0x7f, "i64": 0x7e}
-    types, imports = [], []
-    names = {}
+    types, import_list = [], []
 
-    def functype(f):
-        params = [vt[t] for part in f if isinstance(part, list) and part[0] == "param" for t in part[1:] if t in vt]
-        results = [vt[t] for part in f if isinstance(part, list) and part[0] == "result" for t in part[1:] if t in vt]
-        sig = (tuple(params), tuple(results))
+    def typeidx(params, results):
+        sig = (tuple(vt[t] for t in params), tuple(vt[t] for t in results))
         if sig not in types:
             types.append(sig)
         return types.index(sig)
     for f in mod[1:]:
         if f[0] == "import":
-            names[f[3][1]] = len(imports)
-            imports.append((f[1].strip('"'), f[2].strip('"'), functype(f[3])))
-    start = next(f[2][1] for f in mod[1:] if f[0] == "export" and f[1] == '"_start"')
-    func = next(f for f in mod[1:] if f[0] == "func" and f[1] == start)
-    start_type = functype([])
-    code = bytearray()
-
-    def emit(e):
-        if e[0] in ("i32.const", "i64.const"):
-            w = int(e[0][1:3]); v = int(e[1].replace("_", ""), 0) % (1 << w)
-            code.extend(bytes([0x41 if w == 32 else 0x42]) + _sleb(v - (1 << w) if v >> (w - 1) else v))
-            return
-        for a in (e[2:] if e[0] == "call" else e[1:]):
-            emit(a)
-        if e[0] == "call":
-            code.extend(b"\x10" + _uleb(names[e[1]]))
-        elif e[0] == "drop":
-            code.append(0x1A)
-        elif e[0] == "nop":
-            code.append(0x01)
-        elif e[0] in _OTHER_OPS:
-            code.append(_OTHER_OPS[e[0]])
-        else:
-            w, op = e[0][:3], e[0][4:]
-            if op in _CMP_OPS:
-                code.append((0x45 if w == "i32" else 0x50) + _CMP_OPS.index(op))
-            else:
-                code.append((0x67 if w == "i32" else 0x79) + _INT_OPS.index(op))
-    for e in func[2:]:
-        if isinstance(e, list) and e[0] not in ("param", "result", "local", "type"):
-            emit(e)
-    code.append(0x0B)
+            params = [t for part in f[3] if isinstance(part, list) and part[0] == "param" for t in part[1:] if t in vt]
+            results = [t for part in f[3] if isinstance(part, list) and part[0] == "result" for t in part[1:] if t in vt]
+            import_list.append((f[1].strip('"'), f[2].strip('"'), typeidx(params, results)))
+    func_types = [typeidx(fn["params"], fn["results"]) for fn in funcs]
     vec = lambda items: _uleb(len(items)) + b"".join(items)
     name = lambda s: _uleb(len(s.encode())) + s.encode()
     section = lambda sid, body: bytes([sid]) + _uleb(len(body)) + body
+    bodies = []
+    for fn in funcs:
+        code = bytearray()
+
+        def visit(kind, nm, imm):
+            if kind == "const":
+                w = int(nm[1:3])
+                code.extend(bytes([0x41 if w == 32 else 0x42]) + _sleb(imm - (1 << w) if imm >> (w - 1) else imm))
+            elif kind == "host":
+                code.extend(b"\x10" + _uleb(imm))
+            elif kind == "callf":
+                code.extend(b"\x10" + _uleb(len(import_list) + imm))
+            elif kind == "local":
+                code.extend(bytes([{"local.get": 0x20, "local.set": 0x21, "local.tee": 0x22}[nm]]) + _uleb(imm))
+            elif nm in ("drop", "nop", "select"):
+                code.append({"drop": 0x1A, "nop": 0x01, "select": 0x1B}[nm])
+            elif nm in _OTHER_OPS:
+                code.append(_OTHER_OPS[nm])
+            else:
+                w, op = nm[:3], nm[4:]
+                code.append((0x45 if w == "i32" else 0x50) + _CMP_OPS.index(op) if op in _CMP_OPS else (0x67 if w == "i32" else 0x79) + _INT_OPS.index(op))
+        _walk(fn, imports, ids, visit)
+        code.append(0x0B)
+        body = vec([_uleb(1) + bytes([vt[t]]) for t in fn["locals"]]) + bytes(code)
+        bodies.append(_uleb(len(body)) + body)
     out = b"\0asm\x01\0\0\0"
     out += section(1, vec([b"\x60" + vec([bytes([t]) for t in p]) + vec([bytes([t]) for t in r]) for p, r in types]))
-    out += section(2, vec([name(m) + name(f) + b"\x00" + _uleb(t) for m, f, t in imports]))
-    out += section(3, vec([_uleb(start_type)]))
-    out += section(7, vec([name("_start") + b"\x00" + _uleb(len(imports))]))
-    body = _uleb(0) + bytes(code)
-    out += section(10, vec([_uleb(len(body)) + body]))
+    out += section(2, vec([name(m) + name(f) + b"\x00" + _uleb(t) for m, f, t in import_list]))
+    out += section(3, vec([_uleb(t) for t in func_types]))
+    out += section(7, vec([name("_start") + b"\x00" + _uleb(len(import_list) + start)]))
+    out += section(10, vec(bodies))
     if custom_section:
         out += section(0, name("producer") + b"tests/refctx_util.py")
     return out
 
 
 def wat_to_plain(text):
-    """the same module with the body of _start written as a plain instruction sequence instead of folded forms"""
-    mod = _sexpr(text)
-    imports = {f[3][1]: f[2].strip('"') for f in mod[1:] if f[0] == "import"}
-    ids = {v: k for k, v in imports.items()}
-    head = "(module\n" + "".join('(import "env" "%s" (func %s))\n' % (name, fid) for fid, name in imports.items())
+    """the same module with every function body written as a plain instruction sequence instead of folded forms"""
+    imports, funcs, ids, start = wat_module(text)
+    by_index = {index: fid for fid, (_, index) in imports.items()}
+    out = ["(module"] + ['(import "env" "%s" (func %s))' % (nm, fid) for fid, (nm, _) in imports.items()]
+    for k, fn in enumerate(funcs):
+        fid = fn["id"] or "$f%d" % k
+        head = "(func %s" % fid + "".join(" (param %s)" % t for t in fn["params"]) + "".join(" (result %s)" % t for t in fn["results"]) + "".join(" (local %s)" % t for t in fn["locals"])
+        body = []
+
+        def visit(kind, nm, imm):
+            body.append({"const": "%s %d" % (nm, imm or 0), "host": "call %s" % by_index.get(imm), "callf": "call %s" % nm, "local": "%s %s" % (nm, imm), "op": nm}[kind])
+        _walk(fn, imports, ids, visit)
+        out.append(head + "\n" + "\n".join(body) + "\n)")
+    out.append('(export "_start" (func %s)))' % (funcs[start]["id"] or "$f%d" % start))
+    return "\n".join(out) + "\n"
+
+
+# ---- programs with locals, select and module functions on top of the integer instructions
+def _helpers(w):
+    """module functions of width w: (text, python model)"""
+    W = "i%d" % w
+    g = lambda n: "(local.get $%s)" % n
+    return [
+        ("(func $h0 (param $a %s) (param $b %s) (result %s) (%s.xor (%s.mul %s %s) (%s.add %s %s)))" % (W, W, W, W, W, g("a"), g("b"), W, g("a"), g("b")),
+         lambda a, b: wasm_op("xor", w, wasm_op("mul", w, a, b), wasm_op("add", w, a, b))),
+        ("(func $h1 (param $a %s) (param $b %s) (result %s) (local $t %s) (local.set $t (%s.popcnt %s)) (%s.add (local.get $t) (%s.clz %s)))"
+         % (W, W, W, W, W, g("a"), W, W, g("b")),
+         lambda a, b: wasm_op("add", w, wasm_op("popcnt", w, a), wasm_op("clz", w, b))),
+        ("(func $h2 (param $a %s) (param $b %s) (result %s) (select %s (call $h0 %s %s) (%s.lt_u %s %s)))" % (W, W, W, g("a"), g("b"), g("a"), W, g("a"), g("b")),
+         lambda a, b: a if wasm_op("lt_u", w, a, b) else wasm_op("xor", w, wasm_op("mul", w, b, a), wasm_op("add", w, b, a))),
+    ]
+
+
+def rand_struct_expr(rng, depth, w, env, helpers):
+    """like rand_int_expr, plus local.get / local.tee of the locals in `env` (name -> current value, updated in evaluation
+    order), select on concrete and private conditions, and calls of the helper functions"""
+    r = rng.random()
+    if depth > 0 and r < 0.15:
+        k = rng.randrange(len(helpers))
+        (ta, va), (tb, vb) = rand_struct_expr(rng, depth - 1, w, env, helpers), rand_struct_expr(rng, depth - 1, w, env, helpers)
+        return "(call $h%d %s %s)" % (k, ta, tb), helpers[k][1](va, vb)
+    if depth > 0 and r < 0.30:
+        (ta, va), (tb, vb) = rand_struct_expr(rng, depth - 1, w, env, helpers), rand_struct_expr(rng, depth - 1, w, env, helpers)
+        c = rng.randrange(2)
+        form = rng.randrange(3)
+        cond = ["(i32.const %d)" % (c * 5), "(call $i32_private_const (i32.const %d))" % (c * 9), None][form]
+        if cond is None:
+            tc, vc = rand_struct_expr(rng, depth - 1, w, env, helpers)
+            cond, c = "(i%d.eqz %s)" % (w, tc), int(vc == 0)
+        return "(select %s %s %s)" % (ta, tb, cond), (va if c else vb)
+    if r < 0.45 and env:
+        name = rng.choice(sorted(env))
+        return "(local.get $%s)" % name, env[name]
+    if depth > 0 and r < 0.55 and env:
+        name = rng.choice(sorted(env))
+        t, v = rand_struct_expr(rng, depth - 1, w, env, helpers)
+        env[name] = v
+        return "(local.tee $%s %s)" % (name, t), v
+    if depth == 0 or r < 0.65:
+        return rand_int_expr(rng, 0, w)
+    for _ in range(100):
+        op = rng.choice(UNARY_OPS + BINARY_OPS * 2)
+        saved = dict(env)
+        ta, va = rand_struct_expr(rng, depth - 1, w, env, helpers)
+        if op in UNARY_OPS:
+            if op == "extend16_s" and w == 64 and "private" not in ta and "local" not in ta and "call" not in ta:
+                env.clear(); env.update(saved)
+                continue
+            return _typed(w, op, "(i%d.%s %s)" % (w, op, ta)), wasm_op(op, w, va)
+        tb, vb = rand_struct_expr(rng, depth - 1, w, env, helpers)
+        v = wasm_op(op, w, va, vb)
+        concrete = not any(key in ta + tb for key in ("private", "local", "call"))
+        if v is not None and not (op in ("div_s", "div_u", "rem_s", "rem_u") and concrete):
+            return _typed(w, op, "(i%d.%s %s %s)" % (w, op, ta, tb)), v
+        env.clear(); env.update(saved)
+    raise RuntimeError("no valid expression found")
+
+
+def rand_struct_program(rng, w, nstmt=5, depth=2):
+    W = "i%d" % w
+    helpers = _helpers(w)
+    env = {"x": 0, "y": 0, "z": 0}
     body = []
-    for t in wat_to_tokens(text):
-        body.append("call " + ids[t[5:]] if t.startswith("call:") else t)
-    return head + "(func $plain\n" + "\n".join(body) + "\n)\n(export \"_start\" (func $plain)))\n"
+    for _ in range(nstmt):
+        t, v = rand_struct_expr(rng, rng.randrange(1, depth + 1), w, env, helpers)
+        if rng.random() < 0.45:
+            name = rng.choice(sorted(env))
+            env[name] = v
+            body.append("(local.set $%s %s)" % (name, t))
+        else:
+            rhs = ("(%s.const %d)" % (W, v)) if rng.random() < 0.5 else ("(call $%s_private_const (%s.const %d))" % (W, W, v))
+            body.append("(call $assert_equal %s %s)" % (t, rhs))
+    head = WAT_HEAD_BOTH[:WAT_HEAD_BOTH.index("(func $t")]
+    return (head + "\n".join(h[0] for h in helpers) + "\n(func $t (local $x %s) (local $y %s) (local $z %s)\n" % (W, W, W) + "\n".join(body) + "\n" + WAT_TAIL)

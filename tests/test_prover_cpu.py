@@ -513,3 +513,31 @@ def test_front_ends_survive_mutated_inputs_under_sanitizers(tmp_path):
     for seed in ("seed.wat", "seed.wasm"):
         res = subprocess.run([exe, str(tmp_path / seed), "3000"], capture_output=True, text=True, timeout=600)
         assert res.returncode == 0 and "accepted" in res.stdout, (res.stdout + res.stderr)[-3000:]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_structured_programs_constraint_system(pr, oracle, seed):
+    """needs no reference run: random programs with locals, select, helper functions and every integer instruction; all
+    assertions (expected values from WebAssembly's semantics) hold in the emitted constraint system and the binary spelling
+    gives the same rows"""
+    import refctx_util as U
+    rng = random.Random(6100 + seed)
+    text = U.rand_struct_program(rng, (32, 64)[seed & 1], nstmt=5, depth=2)
+    _, st = _wat_check(pr, oracle, text, l=256, k=512)
+    assert st["violated_constraints"] == 0
+    _same_rows(pr, text, U.wat_to_wasm(text), l=256)
+
+
+def test_front_end_rejects_malformed_functions(pr):
+    head = '(module (import "env" "i64_private_const" (func $pc (param i64) (result i64)))\n(import "env" "assert_equal" (func $eq (param i64 i64)))\n'
+    tail = '(export "_start" (func $t)))'
+    for body, why in (("(func $t (local $x i32) (local.set $x (call $pc (i64.const 1))))", "type mismatch: local.set"),
+                      ("(func $t (drop (local.get 3)))", "unknown local"),
+                      ("(func $t (param i64))", "_start with parameters"),
+                      ("(func $f (param i64) (result i64) (i64.const 1) (i64.const 2)) (func $t (drop (call $f (i64.const 1))))", "leaves 2 values"),
+                      ("(func $f (result i32) (i64.const 1)) (func $t (drop (call $f)))", "wrong width"),
+                      ("(func $t (drop (call $nowhere)))", "unknown function"),
+                      ("(func $t (call $t))", "call depth"),
+                      ("(func $t (drop (select (i64.const 1) (i32.const 2) (i32.const 1))))", "type mismatch: select")):
+        with pytest.raises(pr.ProverError, match=why):
+            pr.wat_emit(head + body + tail, 64)

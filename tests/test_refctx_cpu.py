@@ -239,6 +239,58 @@ def test_wat_emitter_env_assertions_casts_and_drop_against_the_reference(oracle,
     _emitter_equals_reference_rows(pr, U.wat_to_wasm(ENV_PROGRAM), st)
 
 
+STRUCT_PROGRAM = """(module
+ (import "env" "i64_private_const" (func $pc (param i64) (result i64)))
+ (import "env" "i32_private_const" (func $pc32 (param i32) (result i32)))
+ (import "env" "assert_equal" (func $eq (param i64 i64)))
+ (func $sq (param $a i64) (result i64) (i64.mul (local.get $a) (local.get $a)))
+ (func $mix (param $a i64) (param $b i64) (result i64) (local $t i64)
+   (local.set $t (i64.xor (local.get $a) (local.get $b)))
+   (i64.add (local.get $t) (call $sq (local.get $b))))
+ (func $main (local $x i64) (local $y i64) (local $c i32)
+   (local.set $x (call $pc (i64.const 7)))
+   (local.set $y (i64.add (local.tee $x (i64.add (local.get $x) (i64.const 1))) (call $pc (i64.const 5))))
+   (call $eq (local.get $y) (i64.const 13))
+   (call $eq (call $mix (local.get $x) (local.get $y)) (i64.const 174))
+   (local.set $c (i64.lt_u (local.get $x) (local.get $y)))
+   (call $eq (select (local.get $x) (local.get $y) (local.get $c)) (i64.const 8))
+   (call $eq (select (local.get $x) (local.get $y) (i32.const 0)) (i64.const 13))
+   (call $eq (select (call $pc (i64.const 1)) (i64.const 2) (call $pc32 (i32.const 0))) (call $pc (i64.const 2)))
+   (local.set $x (i64.const 3))
+   (local.set $y (i64.clz (local.get $y)))
+   (call $eq (local.get $y) (i64.const 60))
+ )
+ (export "_start" (func $main)))
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+def test_wat_emitter_locals_select_and_module_functions_against_the_reference(oracle, pr):
+    """locals (get / set / tee, overwritten while they hold bits, witnesses and numbers, alive at the end of the frame), select
+    on concrete and on witness conditions, calls of module functions with parameters, locals and nested calls: through the
+    reference's interpreter (frames, run_call, exec_select, exec_local_*) and through the emitter in all three spellings"""
+    raw = U.run_reference_on_wat(STRUCT_PROGRAM, 256, seed_byte=5)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    for spelling in (STRUCT_PROGRAM, U.wat_to_wasm(STRUCT_PROGRAM), U.wat_to_plain(STRUCT_PROGRAM)):
+        _emitter_equals_reference_rows(pr, spelling, st)
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("seed", range(10))
+def test_wat_emitter_against_the_reference_interpreter_on_structured_programs(oracle, pr, seed):
+    """differential: random programs with three locals, helper functions, select, local.tee inside expressions and every
+    integer instruction (tests/refctx_util.py: rand_struct_program), text and binary"""
+    import random
+    rng = random.Random(8800 + seed)
+    text = U.rand_struct_program(rng, (32, 64)[seed & 1], nstmt=rng.randrange(2, 7), depth=rng.randrange(1, 4))
+    raw = U.run_reference_on_wat(text, 256, seed_byte=seed + 1)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    _emitter_equals_reference_rows(pr, text, st)
+    _emitter_equals_reference_rows(pr, U.wat_to_wasm(text), st)
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
