@@ -2,9 +2,9 @@
 // module -- WebAssembly text (folded, as the reference's tests/*.wat are written, or plain) and WebAssembly binaries, both of
 // which the reference's prover takes (src/webgpu_prover.cpp:189-207) -- and the witness machine behind it.
 // It is NOT the reference's interpreter (include/interpreter_impl.hpp + include/zkp/backend/*.hpp: a general WASM machine with
-// control flow, memory and tables over an expression-template backend; out of scope).  For the instructions it
+// control flow, globals and tables over an expression-template backend; out of scope).  For the instructions it
 // takes -- every integer instruction the reference implements (interpreter_impl.hpp:155-1309), select, drop, nop, locals,
-// calls of the module's own functions, and the env
+// calls of the module's own functions, linear memory (loads, stores, memory.size / grow / fill / copy / init, data segments), and the env
 // functions iNN_private_const / assert_equal / assert_zero / assert_one / assert_constant / witness_cast / assert_is_concrete
 // (host_modules/env.hpp) -- it gives each one the meaning the reference gives it: which witnesses exist, which draws of the
 // linear stream land on them, and WHEN each one is released into a row.  That order is decided in the reference by C++
@@ -16,7 +16,7 @@
 //
 // Parity statement: pinned to runs of the reference itself.  tests/refctx/ref_contexts.cpp compiles the reference's own
 // interpreter, env module, backend and witness manager and runs programs through them as token streams; on all 65 integer
-// programs of the reference's tests/ (tests/i64_mul.wat = BASELINE config 4 among them), on the repo's mul64.wat / arith32.wat /
+// programs and both memory programs of the reference's tests/ (tests/i64_mul.wat = BASELINE config 4 among them), on the repo's mul64.wat / arith32.wat /
 // intops.wat (tests/golden/refctx_*.json) and on random expression trees over the whole instruction set this emitter produces
 // the same rows, the same coefficient rows and the same const_sum, element for element (tests/test_refctx_cpu.py).
 // The release order follows the lifetimes of C++ objects as GCC orders them (parameters, temporaries, structured
@@ -514,7 +514,16 @@ public:
 
     // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
     void run(witness_machine &m, wat_stats &st) const {
-        run_state rs{m, st, {}};
+        run_state rs{m, st, {}, {}, {}, {}, 0};
+        rs.memory.assign((size_t)mem_pages_ * 65536, 0);
+        rs.max_pages = mem_max_;
+        for (const data_t &d : datas_) {                      // instantiate (runtime.hpp:537-556): active segments are copied in and dropped
+            rs.datas.emplace_back(d.bytes.begin(), d.bytes.end());
+            if (!d.active) continue;
+            if ((uint64_t)d.offset + d.bytes.size() > rs.memory.size()) throw std::invalid_argument("wat: data segment does not fit the memory");
+            std::copy(d.bytes.begin(), d.bytes.end(), rs.memory.begin() + d.offset);
+            rs.datas.back().clear();
+        }
         call(start_, rs, 0);
         while (!rs.stack.empty()) rs.stack.pop_back();
         st.linear_constraints = m.draws();
@@ -561,10 +570,44 @@ private:
         uint32_t as_u32() const { return (uint32_t)num; }
         uint64_t as_u64() const { return num; }
     };
+    // memory_instance (runtime.hpp:106-176): concrete bytes plus the set of byte ranges a witness was stored to.  A load that
+    // touches such a range yields a FRESH witness holding the concrete value (nothing ties it to the stored one -- the
+    // reference's model, kept); stores of numbers, memory.fill and memory.init clear the mark, memory.copy carries it along.
+    struct secret_ranges {
+        std::map<uint32_t, uint32_t> iv;                      // begin -> end, right-open, disjoint, touching ranges joined
+        void add(uint32_t b, uint32_t e) {
+            if (b >= e) return;
+            auto it = iv.lower_bound(b);
+            if (it != iv.begin() && std::prev(it)->second >= b) { --it; b = it->first; }
+            while (it != iv.end() && it->first <= e) { e = std::max(e, it->second); it = iv.erase(it); }
+            iv[b] = e;
+        }
+        void subtract(uint32_t b, uint32_t e) {
+            if (b >= e) return;
+            auto it = iv.lower_bound(b);
+            if (it != iv.begin() && std::prev(it)->second > b) --it;
+            while (it != iv.end() && it->first < e) {
+                const uint32_t ib = it->first, ie = it->second;
+                it = iv.erase(it);
+                if (ib < b) iv[ib] = b;
+                if (ie > e) { iv[e] = ie; break; }
+            }
+        }
+        bool intersects(uint32_t b, uint32_t e) const {
+            if (b >= e) return false;
+            auto it = iv.lower_bound(b);
+            if (it != iv.begin() && std::prev(it)->second > b) return true;
+            return it != iv.end() && it->first < e;
+        }
+    };
     struct run_state {
         witness_machine &m;
         wat_stats &st;
         std::vector<value> stack;
+        std::vector<uint8_t> memory;
+        secret_ranges secrets;
+        std::vector<std::vector<uint8_t>> datas;
+        uint32_t max_pages = 0;
         void push(value v) { stack.push_back(std::move(v)); }
         value pop() {
             if (stack.empty()) throw std::invalid_argument("wat: operand stack underflow");
@@ -975,11 +1018,12 @@ private:
     }
 
     struct ins {
-        enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, func_call, local_get, local_set, local_tee, select, drop, nop, end_of_statement } kind;
-        uint8_t o = 0;                                        // op or host_fn
+        enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, func_call, local_get, local_set, local_tee, select, drop, nop, end_of_statement,
+                                load, store, memory_size, memory_grow, memory_fill, memory_copy, memory_init, data_drop } kind;
+        uint8_t o = 0;                                        // op or host_fn; bytes moved by a load / store
         uint8_t width = 0;
         bool sgn = false;
-        uint64_t imm = 0;                                     // literal, local index, or function index (module functions from 0)
+        uint64_t imm = 0;                                     // literal, local / function / data index (module functions from 0), memory offset
     };
     // a module function: signature, locals (parameters first), flat body
     struct func_t {
@@ -1016,9 +1060,84 @@ private:
             case ins::drop: rs.pop(); break;                  // exec_drop (interpreter_impl.hpp:112-116)
             case ins::nop: break;
             case ins::end_of_statement: while (rs.stack.size() > (size_t)i.imm) rs.stack.pop_back(); break;
+            case ins::load: load(i, rs); break;
+            case ins::store: store(i, rs); break;
+            default: bulk_memory(i, rs); break;
             }
         }
     }
+    // do_load (interpreter_impl.hpp:2206-2228): the address is read as a number; a range that holds a stored witness gives a new witness
+    static void load(const ins &i, run_state &rs) {
+        value tmp = rs.pop();
+        const uint64_t ea = (uint64_t)(uint32_t)rs.make_numeric(std::move(tmp)) + i.imm, n = i.o;
+        if (ea + n > rs.memory.size()) throw std::invalid_argument("wat: invalid memory address");
+        uint64_t c = 0;
+        memcpy(&c, rs.memory.data() + ea, (size_t)n);
+        if (i.sgn && n < 8 && (c >> (8 * n - 1)) & 1) c |= ~0ULL << (8 * n);
+        if (i.width == 32) c &= 0xFFFFFFFFULL;
+        if (rs.secrets.intersects((uint32_t)ea, (uint32_t)(ea + n))) rs.push(value::of(rs.make_witness(numeric(i.width == 64, c))));
+        else rs.push(numeric(i.width == 64, c));
+    }
+    // do_store (:2310-2344): the value is read as a number and its witnesses are let go; the range is marked iff it was not a number
+    static void store(const ins &i, run_state &rs) {
+        value tmp = rs.pop();
+        value addr = rs.pop();
+        const uint64_t ea = (uint64_t)(uint32_t)rs.make_numeric(std::move(addr)) + i.imm, n = i.o;
+        if (ea + n > rs.memory.size()) throw std::invalid_argument("wat: invalid memory address");
+        if (tmp.kind == value::NUM) rs.secrets.subtract((uint32_t)ea, (uint32_t)(ea + n));
+        else rs.secrets.add((uint32_t)ea, (uint32_t)(ea + n));
+        uint64_t c = rs.make_numeric(std::move(tmp));
+        if (i.width == 32) c &= 0xFFFFFFFFULL;
+        memcpy(rs.memory.data() + ea, &c, (size_t)n);
+    }
+    // memory.size / grow / fill / copy / init, data.drop (:2108-2204): operands must be numbers (the reference reads them with std::get)
+    static uint32_t concrete(run_state &rs, const char *what) {
+        value v = rs.pop();
+        if (v.kind != value::NUM) throw std::invalid_argument(std::string("wat: ") + what + " takes concrete operands");
+        return v.as_u32();
+    }
+    static void bulk_memory(const ins &i, run_state &rs) {
+        const uint32_t page = 65536;
+        switch (i.kind) {
+        case ins::memory_size: rs.push(value::u32((uint32_t)(rs.memory.size() / page))); break;
+        case ins::memory_grow: {
+            const uint32_t sz = (uint32_t)(rs.memory.size() / page), n = concrete(rs, "memory.grow");
+            const uint64_t len = (uint64_t)sz + n;
+            if (len > 4096 || (rs.max_pages && len > rs.max_pages)) rs.push(value::u32(0xFFFFFFFFu));   // (the front end caps memory at 256 MiB; the reference at 4 GiB)
+            else { rs.memory.resize((size_t)len * page); rs.push(value::u32(sz)); }
+            break;
+        }
+        case ins::memory_fill: {
+            const uint32_t n = concrete(rs, "memory.fill"), val = concrete(rs, "memory.fill"), d = concrete(rs, "memory.fill");
+            if ((uint64_t)d + n > rs.memory.size()) throw std::invalid_argument("wat: memory.fill: invalid address");
+            std::fill_n(rs.memory.begin() + d, n, (uint8_t)val);
+            rs.secrets.subtract(d, d + n);
+            break;
+        }
+        case ins::memory_copy: {                              // memcpy_secrets (runtime.hpp:136-172)
+            const uint32_t count = concrete(rs, "memory.copy"), src = concrete(rs, "memory.copy"), dst = concrete(rs, "memory.copy");
+            if ((uint64_t)src + count > rs.memory.size() || (uint64_t)dst + count > rs.memory.size()) throw std::invalid_argument("wat: memory.copy: out of range");
+            secret_ranges moved;
+            const uint32_t offset = dst - src;                // wraps, as in the reference: a marked range that starts more than `dst` bytes before `src` wraps to an empty range and loses its mark
+            for (const auto &r : rs.secrets.iv) if (r.first < src + count && r.second > src) moved.add(r.first + offset, r.second + offset);
+            rs.secrets.subtract(dst, dst + count);
+            for (const auto &r : moved.iv) rs.secrets.add(std::max(r.first, dst), std::min(r.second, dst + count));
+            memmove(rs.memory.data() + dst, rs.memory.data() + src, count);
+            break;
+        }
+        case ins::memory_init: {
+            const uint32_t n = concrete(rs, "memory.init"), sidx = concrete(rs, "memory.init"), d = concrete(rs, "memory.init");
+            const std::vector<uint8_t> &data = rs.datas[(size_t)i.imm];
+            if ((uint64_t)sidx + n > data.size() || (uint64_t)d + n > rs.memory.size()) throw std::invalid_argument("wat: memory.init: invalid address");
+            std::copy(data.begin() + sidx, data.begin() + sidx + n, rs.memory.begin() + d);
+            rs.secrets.subtract(d, d + n);
+            break;
+        }
+        case ins::data_drop: rs.datas[(size_t)i.imm].clear(); break;
+        default: throw std::logic_error("wat: unknown instruction kind");
+        }
+    }
+
     // exec_select (interpreter_impl.hpp:118-140): a concrete condition removes one of the two values from the stack; a witness
     // condition is compared with zero bit by bit and the result is is_zero * second + ~is_zero * first, one new witness
     static void select(run_state &rs) {
@@ -1106,6 +1225,37 @@ private:
         else { want(t, k == ins::local_set ? "local.set" : "local.tee"); if (k == ins::local_tee) types_.push_back(t); }
         put(k, index);
     }
+    // iNN.load* / iNN.store* (name without the "iNN." prefix); false if it is not a memory access
+    bool emit_access(const std::string &name, int width, uint64_t offset, const std::string &shown) {
+        static const std::map<std::string, std::pair<int, int>> table = {      // bytes (0 = the full width), sign: 1 signed, 0 unsigned
+            {"load", {0, 0}}, {"load8_s", {1, 1}}, {"load8_u", {1, 0}}, {"load16_s", {2, 1}}, {"load16_u", {2, 0}}, {"load32_s", {4, 1}}, {"load32_u", {4, 0}},
+            {"store", {0, 0}}, {"store8", {1, 0}}, {"store16", {2, 0}}, {"store32", {4, 0}}};
+        const auto it = table.find(name);
+        if (it == table.end()) return false;
+        const int bytes = it->second.first ? it->second.first : width / 8;
+        if (bytes == 4 && it->second.first && width != 64) return false;      // load32_* / store32 exist for i64 only
+        if (!has_memory_) throw std::invalid_argument("wat: " + shown + " in a module without a memory");
+        if (offset > 0xFFFFFFFFULL) throw std::invalid_argument("wat: memory offset out of range");
+        const bool is_store = name[0] == 's';
+        if (is_store) want(width, shown);
+        want(32, shown);
+        if (!is_store) types_.push_back((uint8_t)width);
+        ins i;
+        i.kind = is_store ? ins::store : ins::load;
+        i.o = (uint8_t)bytes; i.width = (uint8_t)width; i.sgn = it->second.second != 0; i.imm = offset;
+        cur_->code.push_back(i);
+        return true;
+    }
+    void emit_bulk(ins::kind_t k, uint64_t index = 0) {
+        if (!has_memory_) throw std::invalid_argument("wat: memory instruction in a module without a memory");
+        const char *shown = k == ins::memory_size ? "memory.size" : k == ins::memory_grow ? "memory.grow" : k == ins::memory_fill ? "memory.fill"
+                          : k == ins::memory_copy ? "memory.copy" : k == ins::memory_init ? "memory.init" : "data.drop";
+        if ((k == ins::memory_init || k == ins::data_drop) && index >= datas_.size()) throw std::invalid_argument(std::string("wat: ") + shown + " of an unknown data segment");
+        if (k == ins::memory_grow) want(32, shown);
+        if (k == ins::memory_fill || k == ins::memory_copy || k == ins::memory_init) for (int j = 0; j < 3; j++) want(32, shown);
+        if (k == ins::memory_size || k == ins::memory_grow) types_.push_back(32);
+        put(k, index);
+    }
     void emit_plain(ins::kind_t k) {
         if (k == ins::drop) pop_type("drop");
         if (k == ins::select) {
@@ -1138,14 +1288,52 @@ private:
     struct text_scope {
         const std::vector<import_t> &imports;
         const std::map<std::string, size_t> &func_ids;        // $name -> function index (imports first)
+        const std::map<std::string, size_t> &data_ids;
         std::map<std::string, size_t> local_ids;
     };
+    void set_memory(uint64_t pages, uint64_t max_pages) {
+        if (pages > 4096) throw std::invalid_argument("wat: memories beyond 256 MiB are not supported");
+        has_memory_ = true; mem_pages_ = (uint32_t)pages; mem_max_ = (uint32_t)std::min<uint64_t>(max_pages, 65536);
+    }
+    static std::string decode_string(const std::string &quoted) {           // WebAssembly text string literal -> bytes
+        std::string out;
+        const auto hex = [](char ch) { return (ch >= '0' && ch <= '9') ? ch - '0' : ((ch >= 'a' && ch <= 'f') ? ch - 'a' + 10 : ((ch >= 'A' && ch <= 'F') ? ch - 'A' + 10 : -1)); };
+        for (size_t i = 1; i + 1 < quoted.size(); i++) {
+            if (quoted[i] != '\\') { out.push_back(quoted[i]); continue; }
+            if (++i >= quoted.size() - 1) throw std::invalid_argument("wat: bad escape in a string");
+            const char ch = quoted[i];
+            if (ch == 'n') out.push_back('\n');
+            else if (ch == 't') out.push_back('\t');
+            else if (ch == 'r') out.push_back('\r');
+            else if (ch == '"' || ch == '\'' || ch == '\\') out.push_back(ch);
+            else if (hex(ch) >= 0 && i + 1 < quoted.size() - 1 && hex(quoted[i + 1]) >= 0) { out.push_back((char)(hex(ch) * 16 + hex(quoted[i + 1]))); i++; }
+            else throw std::invalid_argument("wat: unsupported escape in a string");
+        }
+        return out;
+    }
+    static uint64_t data_index(const std::string &id, const text_scope &sc) {
+        const auto it = sc.data_ids.find(id);
+        if (it != sc.data_ids.end()) return it->second;
+        if (!id.empty() && id[0] >= '0' && id[0] <= '9') return parse_i64(id);
+        throw std::invalid_argument("wat: unknown data segment " + id);
+    }
+    // offset=N / align=N after a memory access; returns the offset and steps `j` past them
+    static uint64_t memarg(const std::vector<sexpr> &list, size_t &j) {
+        uint64_t offset = 0;
+        for (; j < list.size() && !list[j].is_list; j++) {
+            const std::string &a = list[j].atom;
+            if (a.compare(0, 7, "offset=") == 0) offset = parse_i64(a.substr(7));
+            else if (a.compare(0, 6, "align=") == 0) (void)parse_i64(a.substr(6));
+            else break;
+        }
+        return offset;
+    }
     void parse_text(const std::string &text) {
         sexpr_parser p(text);
         const sexpr top = p.parse_top();
         if (top.head() != "module") throw std::invalid_argument("wat: expected (module ...)");
         std::vector<import_t> imports;
-        std::map<std::string, size_t> func_ids;
+        std::map<std::string, size_t> func_ids, data_ids;
         std::vector<const sexpr *> bodies;
         std::string start;
         for (size_t i = 1; i < top.list.size(); i++) {
@@ -1162,10 +1350,31 @@ private:
                 bodies.push_back(&f);
             } else if (f.head() == "export") {
                 if (f.list.size() >= 3 && unquote(f.list[1].atom) == "_start" && f.list[2].head() == "func" && f.list[2].list.size() == 2) start = f.list[2].list[1].atom;
+            } else if (f.head() == "memory") {                 // (memory [$id] min [max])
+                size_t j = (f.list.size() >= 2 && !f.list[1].is_list && f.list[1].atom[0] == '$') ? 2 : 1;
+                if (has_memory_ || j >= f.list.size() || f.list[j].is_list) throw std::invalid_argument("wat: unsupported memory declaration");
+                set_memory(parse_i64(f.list[j].atom), j + 1 < f.list.size() && !f.list[j + 1].is_list ? parse_i64(f.list[j + 1].atom) : 0);
+            } else if (f.head() == "data") {                   // (data [$id] "bytes"...) passive; (data [$id] (i32.const off) "bytes"...) active
+                data_t d;
+                size_t j = 1;
+                if (j < f.list.size() && !f.list[j].is_list && f.list[j].atom[0] == '$') data_ids[f.list[j++].atom] = datas_.size();
+                if (j < f.list.size() && f.list[j].is_list) {
+                    const sexpr *off = &f.list[j++];
+                    if (off->head() == "offset" && off->list.size() == 2) off = &off->list[1];
+                    if (off->head() != "i32.const" || off->list.size() != 2) throw std::invalid_argument("wat: a data segment's offset must be an i32.const");
+                    d.active = true;
+                    d.offset = (uint32_t)parse_i64(off->list[1].atom);
+                }
+                for (; j < f.list.size(); j++) {
+                    if (f.list[j].is_list || f.list[j].atom.empty() || f.list[j].atom[0] != '"') throw std::invalid_argument("wat: malformed data segment");
+                    d.bytes += decode_string(f.list[j].atom);
+                }
+                datas_.push_back(d);
             } else {
                 throw std::invalid_argument("wat: unsupported module field (" + f.head() + ")");
             }
         }
+        for (const data_t &d : datas_) if (d.active && !has_memory_) throw std::invalid_argument("wat: an active data segment needs a memory");
         // signatures first (a body may call a later function), then the bodies
         funcs_.resize(bodies.size());
         std::vector<std::map<std::string, size_t>> local_ids(bodies.size());
@@ -1203,7 +1412,7 @@ private:
         for (size_t k = 0; k < bodies.size(); k++) {
             const sexpr &f = *bodies[k];
             func_t &fn = funcs_[k];
-            text_scope sc{imports, func_ids, local_ids[k]};
+            text_scope sc{imports, func_ids, data_ids, local_ids[k]};
             begin_body(fn);
             for (size_t i = first_instr[k]; i < f.list.size(); i++) {
                 const sexpr &e = f.list[i];
@@ -1224,7 +1433,18 @@ private:
                 else if (a == "select") emit_plain(ins::select);
                 else if (a == "drop") emit_plain(ins::drop);
                 else if (a == "nop") emit_plain(ins::nop);
-                else if (a.size() > 4 && (a.compare(0, 4, "i32.") == 0 || a.compare(0, 4, "i64.") == 0)) emit_op(a.substr(4), a[1] == '3' ? 32 : 64, a);
+                else if (a == "memory.size") emit_bulk(ins::memory_size);
+                else if (a == "memory.grow") emit_bulk(ins::memory_grow);
+                else if (a == "memory.fill") emit_bulk(ins::memory_fill);
+                else if (a == "memory.copy") emit_bulk(ins::memory_copy);
+                else if (a == "memory.init") emit_bulk(ins::memory_init, data_index(next(), sc));
+                else if (a == "data.drop") emit_bulk(ins::data_drop, data_index(next(), sc));
+                else if (a.size() > 4 && (a.compare(0, 4, "i32.") == 0 || a.compare(0, 4, "i64.") == 0)) {
+                    size_t j = i + 1;
+                    const uint64_t offset = memarg(f.list, j);
+                    if (emit_access(a.substr(4), a[1] == '3' ? 32 : 64, offset, a)) i = j - 1;
+                    else emit_op(a.substr(4), a[1] == '3' ? 32 : 64, a);
+                }
                 else throw std::invalid_argument("wat: unsupported instruction " + a);
             }
             end_body(f.list.size() >= 2 && !f.list[1].is_list ? f.list[1].atom : "function " + std::to_string(k));
@@ -1255,6 +1475,27 @@ private:
         if (h == "i64.const" || h == "i32.const") {
             if (e.list.size() != 2) throw std::invalid_argument("wat: " + h + " takes one literal");
             emit_const(h[1] == '3' ? 32 : 64, literal(h, e.list[1].atom));
+            return;
+        }
+        if (h.size() >= 8 && (h.compare(0, 8, "i32.load") == 0 || h.compare(0, 8, "i64.load") == 0 || h.compare(0, 9, "i32.store") == 0 || h.compare(0, 9, "i64.store") == 0)) {
+            size_t j = 1;
+            const uint64_t offset = memarg(e.list, j);
+            if (e.list.size() - j != (h[4] == 's' ? 2u : 1u)) throw std::invalid_argument("wat: " + h + " takes " + (h[4] == 's' ? "two folded operands" : "one folded operand"));
+            operands(j);
+            if (!emit_access(h.substr(4), h[1] == '3' ? 32 : 64, offset, h)) throw std::invalid_argument("wat: unsupported instruction " + h);
+            return;
+        }
+        if (h == "memory.size" || h == "memory.grow" || h == "memory.fill" || h == "memory.copy") {
+            const size_t n = h == "memory.size" ? 0 : (h == "memory.grow" ? 1 : 3);
+            if (e.list.size() != 1 + n) throw std::invalid_argument("wat: malformed " + h);
+            operands(1);
+            emit_bulk(h == "memory.size" ? ins::memory_size : (h == "memory.grow" ? ins::memory_grow : (h == "memory.fill" ? ins::memory_fill : ins::memory_copy)));
+            return;
+        }
+        if (h == "memory.init" || h == "data.drop") {
+            if (e.list.size() != (h == "memory.init" ? 5u : 2u) || e.list[1].is_list) throw std::invalid_argument("wat: malformed " + h);
+            operands(2);
+            emit_bulk(h == "memory.init" ? ins::memory_init : ins::data_drop, data_index(e.list[1].atom, sc));
             return;
         }
         if (h.size() > 4 && (h.compare(0, 4, "i32.") == 0 || h.compare(0, 4, "i64.") == 0)) {
@@ -1351,6 +1592,37 @@ private:
             reader s = r.sub((size_t)r.uleb());
             switch (id) {
             case 0: case 12: break;                           // custom / data count: nothing the subset needs
+            case 5: {                                         // memory: at most one
+                const size_t n = (size_t)s.uleb();
+                if (n > 1 || (n && has_memory_)) throw std::invalid_argument("wasm: more than one memory");
+                if (n) {
+                    const uint8_t flags = s.byte();
+                    if (flags > 1) throw std::invalid_argument("wasm: unsupported memory limits");
+                    const uint64_t lo = s.uleb();
+                    set_memory(lo, flags ? s.uleb() : 0);
+                }
+                break;
+            }
+            case 11: {                                        // data segments
+                const size_t n = (size_t)s.uleb();
+                for (size_t i = 0; i < n; i++) {
+                    data_t d;
+                    const uint64_t mode = s.uleb();
+                    if (mode > 2) throw std::invalid_argument("wasm: malformed data segment");
+                    if (mode == 2 && s.uleb() != 0) throw std::invalid_argument("wasm: data segment for an unknown memory");
+                    if (mode != 1) {
+                        if (s.byte() != 0x41) throw std::invalid_argument("wasm: a data segment's offset must be an i32.const");
+                        d.active = true;
+                        d.offset = (uint32_t)s.sleb(32);
+                        if (s.byte() != 0x0B) throw std::invalid_argument("wasm: a data segment's offset must be an i32.const");
+                    }
+                    const size_t len = (size_t)s.uleb();
+                    reader bytes = s.sub(len);
+                    d.bytes.assign((const char *)bytes.p, len);
+                    datas_.push_back(d);
+                }
+                break;
+            }
             case 1: {                                         // types (a type naming other value types only matters if a module function uses it)
                 const size_t n = (size_t)s.uleb();
                 for (size_t i = 0; i < n; i++) {
@@ -1404,6 +1676,7 @@ private:
             }
         }
         if (bodies.size() != func_types.size()) throw std::invalid_argument("wasm: function and code sections disagree");
+        for (const data_t &d : datas_) if (d.active && !has_memory_) throw std::invalid_argument("wasm: an active data segment needs a memory");
         if (start < 0 || (size_t)start < imports.size() || (size_t)start - imports.size() >= bodies.size()) throw std::invalid_argument("wasm: no exported _start function");
         start_ = (size_t)start - imports.size();
         funcs_.resize(bodies.size());
@@ -1435,6 +1708,25 @@ private:
                 else if (c == 0x1B) emit_plain(ins::select);
                 else if (c == 0x10) emit_call(b.uleb(), imports);
                 else if (c == 0x20 || c == 0x21 || c == 0x22) emit_local(c == 0x20 ? ins::local_get : (c == 0x21 ? ins::local_set : ins::local_tee), b.uleb());
+                else if (c >= 0x28 && c <= 0x3E) {
+                    static const char *const access[] = {"i32.load", "i64.load", nullptr, nullptr, "i32.load8_s", "i32.load8_u", "i32.load16_s", "i32.load16_u", "i64.load8_s", "i64.load8_u",
+                                                         "i64.load16_s", "i64.load16_u", "i64.load32_s", "i64.load32_u", "i32.store", "i64.store", nullptr, nullptr, "i32.store8", "i32.store16",
+                                                         "i64.store8", "i64.store16", "i64.store32"};
+                    const char *nm = access[c - 0x28];
+                    if (!nm) throw std::invalid_argument("wasm: unsupported instruction " + shown);
+                    b.uleb();                                 // alignment hint
+                    const uint64_t offset = b.uleb();
+                    if (!emit_access(std::string(nm).substr(4), nm[1] == '3' ? 32 : 64, offset, nm)) throw std::invalid_argument("wasm: unsupported instruction " + shown);
+                }
+                else if (c == 0x3F || c == 0x40) { if (b.byte() != 0) throw std::invalid_argument("wasm: unknown memory"); emit_bulk(c == 0x3F ? ins::memory_size : ins::memory_grow); }
+                else if (c == 0xFC) {
+                    const uint64_t sub = b.uleb();
+                    if (sub == 8) { const uint64_t d = b.uleb(); if (b.byte() != 0) throw std::invalid_argument("wasm: unknown memory"); emit_bulk(ins::memory_init, d); }
+                    else if (sub == 9) emit_bulk(ins::data_drop, b.uleb());
+                    else if (sub == 10) { if (b.byte() != 0 || b.byte() != 0) throw std::invalid_argument("wasm: unknown memory"); emit_bulk(ins::memory_copy); }
+                    else if (sub == 11) { if (b.byte() != 0) throw std::invalid_argument("wasm: unknown memory"); emit_bulk(ins::memory_fill); }
+                    else throw std::invalid_argument("wasm: unsupported instruction 0xfc " + std::to_string(sub));
+                }
                 else if (c == 0x41) emit_const(32, (uint64_t)b.sleb(32));
                 else if (c == 0x42) emit_const(64, (uint64_t)b.sleb(64));
                 else if (c >= 0x45 && c <= 0x4F) emit_op(cmp_ops[c - 0x45], 32, shown);
@@ -1456,8 +1748,12 @@ private:
         }
     }
 
+    struct data_t { std::string bytes; bool active = false; uint32_t offset = 0; };
     std::vector<func_t> funcs_;
     size_t start_ = 0;
+    bool has_memory_ = false;
+    uint32_t mem_pages_ = 0, mem_max_ = 0;
+    std::vector<data_t> datas_;
 };
 
 }  // namespace ligero::cuda::host

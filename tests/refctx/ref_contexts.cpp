@@ -119,7 +119,8 @@ struct tiny_module {
         std::vector<value_kind> params, results, locals;
         std::vector<instr_ptr> body;
     };
-    explicit tiny_module(std::vector<module_func> functions, size_t start_function) {
+    struct data_seg { std::vector<u8> bytes; bool active = false; u32 offset = 0; };
+    explicit tiny_module(std::vector<module_func> functions, size_t start_function, u32 mem_pages = 1, u32 mem_max = 0, const std::vector<data_seg> &datas = {}) {
         function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_pc32({value_kind::i32}, {value_kind::i32}),
             k_one({value_kind::i64}, {});
         inst.types = {k_pc, k_eq, k_pc32, k_one};
@@ -134,7 +135,18 @@ struct tiny_module {
             inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t("f" + std::to_string(k)), kind, &inst,
                                                                            function_instance::func_code{index, functions[k].locals, std::move(functions[k].body)}));
         }
-        inst.memaddrs.push_back(store.emplace_back<memory_instance>(memory_kind(limits(1)), memory_instance::page_size));
+        inst.memaddrs.push_back(store.emplace_back<memory_instance>(mem_max ? memory_kind(limits(mem_pages, mem_max)) : memory_kind(limits(mem_pages)), (size_t)mem_pages * memory_instance::page_size));
+        // data segments as instantiate() leaves them (include/runtime.hpp:537-556): active ones copied in (memory_init clears marks, none exist yet) and dropped
+        for (const data_seg &d : datas) {
+            const u32 i = store.emplace_back<data_instance>(d.bytes);
+            inst.dataaddrs.push_back(i);
+            if (d.active) {
+                auto &mem = store.memorys[inst.memaddrs[0]];
+                if ((size_t)d.offset + d.bytes.size() > mem.data.size()) throw std::runtime_error("data segment does not fit");
+                std::copy(d.bytes.begin(), d.bytes.end(), mem.data.begin() + d.offset);
+                store.datas[i].data.clear();
+            }
+        }
         inst.exports["_start"] = (index_t)(t.size() + start_function);
     }
     explicit tiny_module(std::vector<instr_ptr> body) : tiny_module(single(std::move(body)), 0) {}
@@ -205,6 +217,27 @@ static std::vector<instr_ptr> assemble(const std::vector<wasm_token> &toks) {
         else if (t.op == "local.get") plain(opcode(opcode::local_get, (index_t)t.imm));
         else if (t.op == "local.set") plain(opcode(opcode::local_set, (index_t)t.imm));
         else if (t.op == "local.tee") plain(opcode(opcode::local_tee, (index_t)t.imm));
+        else if (typed && (name.rfind("load", 0) == 0 || name.rfind("store", 0) == 0)) {
+            const u32 align = 0, offset = (u32)t.imm;
+            const sign_kind sg = name.size() > 2 && name.substr(name.size() - 2) == "_s" ? sign_kind::sign : (name.size() > 2 && name.substr(name.size() - 2) == "_u" ? sign_kind::unsign : sign_kind::unspecified);
+            opcode::kind kd;
+            if (name == "load") kd = opcode::inn_load;
+            else if (name.rfind("load8", 0) == 0) kd = opcode::inn_load8_sx;
+            else if (name.rfind("load16", 0) == 0) kd = opcode::inn_load16_sx;
+            else if (name.rfind("load32", 0) == 0) kd = opcode::i64_load32_sx;
+            else if (name == "store") kd = opcode::inn_store;
+            else if (name == "store8") kd = opcode::inn_store8;
+            else if (name == "store16") kd = opcode::inn_store16;
+            else if (name == "store32") kd = opcode::i64_store32;
+            else throw std::runtime_error("unknown token " + t.op);
+            plain(opcode(kd, vk, sg, align, offset));
+        }
+        else if (t.op == "memory.size") plain(opcode(opcode::memory_size, (index_t)0));
+        else if (t.op == "memory.grow") plain(opcode(opcode::memory_grow, (index_t)0));
+        else if (t.op == "memory.fill") plain(opcode(opcode::memory_fill, (index_t)0));
+        else if (t.op == "memory.copy") plain(opcode(opcode::memory_copy, (index_t)0, (index_t)0));
+        else if (t.op == "memory.init") plain(opcode(opcode::memory_init, (index_t)t.imm));
+        else if (t.op == "data.drop") plain(opcode(opcode::data_drop, (index_t)t.imm));
         else if (t.op == "callf") { flush(); body.push_back(make_instr<call>((index_t)(tiny_module::env_imports().size() + t.imm))); }
         else throw std::runtime_error("unknown token " + t.op);
     }
@@ -247,22 +280,28 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
     std::string op;
     while (in >> op) {
         wasm_token tok{op};
-        if (op == "c" || op == "i32.const" || op == "i64.const" || op == "local.get" || op == "local.set" || op == "local.tee" || op == "callf" || op == "start") {
+        if (op == "c" || op == "i32.const" || op == "i64.const" || op == "local.get" || op == "local.set" || op == "local.tee" || op == "callf" || op == "start" || op == "memory.init" || op == "data.drop" ||
+            ((op.rfind("i32.", 0) == 0 || op.rfind("i64.", 0) == 0) && (op.find(".load") != std::string::npos || op.find(".store") != std::string::npos))) {
             std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0);
         }
         if (op == "func") {                                   // func <params> <results> <locals>, e.g. "func i64,i32 i64 -": a new module function starts
             for (int j = 0; j < 3; j++) { std::string part; in >> part; tok.types.push_back(part); }
+        }
+        if (op == "memory") {                                 // memory <pages> <max pages or 0>
+            for (int j = 0; j < 2; j++) { std::string part; in >> part; tok.types.push_back(part); }
+        }
+        if (op == "data") {                                   // data passive <hex or -> | data active <offset> <hex or ->
+            std::string mode; in >> mode; tok.types.push_back(mode);
+            for (int j = 0; j < (mode == "active" ? 2 : 1); j++) { std::string part; in >> part; tok.types.push_back(part); }
         }
         t.push_back(tok);
     }
     return t;
 }
 
-// a token stream with "func" headers is a module of several functions ("start K" names _start); without, one function
+// a token stream with "func" headers is a module of several functions ("start K" names _start); without, one function.
+// "memory" and "data" directives describe the module's memory and data segments
 static tiny_module build_module(const std::vector<wasm_token> &toks) {
-    bool structured = false;
-    for (const wasm_token &t : toks) structured |= t.op == "func";
-    if (!structured) return tiny_module(assemble(toks));
     const auto kinds = [](const std::string &list) {
         std::vector<value_kind> out;
         if (list == "-") return out;
@@ -277,8 +316,13 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
         return out;
     };
     std::vector<tiny_module::module_func> functions;
+    std::vector<tiny_module::data_seg> datas;
     std::vector<wasm_token> body;
     size_t start = 0;
+    u32 pages = 1, max_pages = 0;
+    bool structured = false;
+    for (const wasm_token &t : toks) structured |= t.op == "func";
+    if (!structured) functions.emplace_back();
     const auto close = [&] { if (!functions.empty()) functions.back().body = assemble(body); body.clear(); };
     for (const wasm_token &t : toks) {
         if (t.op == "func") {
@@ -286,10 +330,19 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
             functions.emplace_back();
             functions.back().params = kinds(t.types[0]); functions.back().results = kinds(t.types[1]); functions.back().locals = kinds(t.types[2]);
         } else if (t.op == "start") start = (size_t)t.imm;
+        else if (t.op == "memory") { pages = (u32)std::stoul(t.types[0]); max_pages = (u32)std::stoul(t.types[1]); }
+        else if (t.op == "data") {
+            tiny_module::data_seg d;
+            d.active = t.types[0] == "active";
+            if (d.active) d.offset = (u32)std::stoul(t.types[1]);
+            const std::string &hx = t.types.back();
+            if (hx != "-") for (size_t i = 0; i + 1 < hx.size(); i += 2) d.bytes.push_back((u8)std::stoul(hx.substr(i, 2), nullptr, 16));
+            datas.push_back(d);
+        }
         else body.push_back(t);
     }
     close();
-    return tiny_module(std::move(functions), start);
+    return tiny_module(std::move(functions), start, pages, max_pages, datas);
 }
 
 template <typename Ctx>

@@ -119,12 +119,49 @@ def wat_module(text):
     return imports, funcs, ids, ids[start_id]
 
 
+def _wat_string(tok):
+    """bytes of a WebAssembly text string literal"""
+    out, i, body = bytearray(), 0, tok[1:-1]
+    while i < len(body):
+        ch = body[i]
+        if ch != "\\":
+            out += ch.encode(); i += 1
+        elif body[i + 1] in "ntr":
+            out.append({"n": 10, "t": 9, "r": 13}[body[i + 1]]); i += 2
+        elif body[i + 1] in "\"'\\":
+            out += body[i + 1].encode(); i += 2
+        else:
+            out.append(int(body[i + 1:i + 3], 16)); i += 3
+    return bytes(out)
+
+
+def wat_memory(text):
+    """(pages, max pages or 0) or None, and the data segments [(id, active, offset, bytes)] of a module"""
+    mod = _sexpr(text)
+    memory, datas = None, []
+    for f in mod[1:]:
+        if f[0] == "memory":
+            nums = [int(x, 0) for x in f[1:] if isinstance(x, str) and not x.startswith("$")]
+            memory = (nums[0], nums[1] if len(nums) > 1 else 0)
+        elif f[0] == "data":
+            rest = f[1:]
+            did = rest.pop(0) if rest and isinstance(rest[0], str) and rest[0].startswith("$") else None
+            active, offset = False, 0
+            if rest and isinstance(rest[0], list):
+                off = rest.pop(0)
+                off = off[1] if off[0] == "offset" else off
+                active, offset = True, _lit(off[1]) % (1 << 32)
+            datas.append((did, active, offset, b"".join(_wat_string(t) for t in rest)))
+    return memory, datas
+
+
 def _lit(s):
     return int(s.replace("_", ""), 0) % (1 << 64)
 
 
-def _walk(fn, imports, ids, visit):
+def _walk(fn, imports, ids, visit, data_ids=None):
     """post-order walk of a function's folded body: visit(kind, name, immediate)"""
+    data_ids = data_ids or {}
     def local(x):
         return fn["names"][x] if x in fn["names"] else int(x)
 
@@ -145,6 +182,23 @@ def _walk(fn, imports, ids, visit):
             for a in e[2:]:
                 emit(a)
             visit("local", h, local(e[1]))
+        elif h[:4] in ("i32.", "i64.") and (h[4:8] == "load" or h[4:9] == "store"):
+            offset, rest = 0, e[1:]
+            while rest and isinstance(rest[0], str):
+                key, _, val = rest.pop(0).partition("=")
+                if key == "offset":
+                    offset = int(val, 0)
+            for a in rest:
+                emit(a)
+            visit("access", h, offset)
+        elif h in ("memory.init", "data.drop"):
+            for a in e[2:]:
+                emit(a)
+            visit("segment", h, data_ids[e[1]] if e[1] in data_ids else int(e[1]))
+        elif h in ("memory.size", "memory.grow", "memory.fill", "memory.copy"):
+            for a in e[1:]:
+                emit(a)
+            visit("op", h, None)
         elif h[:4] in ("i32.", "i64.") or h in ("drop", "nop", "select"):
             for a in e[1:]:
                 emit(a)
@@ -160,15 +214,22 @@ def wat_to_tokens(text):
     folded text denotes.  A module with several functions, parameters or locals gets 'func <params> <results> <locals>' headers
     and 'start <k>' (tests/refctx/ref_contexts.cpp: build_module)"""
     imports, funcs, ids, start = wat_module(text)
+    memory, datas = wat_memory(text)
+    data_ids = {d[0]: k for k, d in enumerate(datas) if d[0]}
     out = []
+    if memory:
+        out.append("memory %d %d" % memory)
+    for _, active, offset, data in datas:
+        out.append(("data active %d %s" % (offset, data.hex() or "-")) if active else ("data passive %s" % (data.hex() or "-")))
 
     def visit(kind, name, imm):
-        out.append({"const": "%s %d" % (name, imm or 0), "host": "call:" + name, "callf": "callf %s" % imm, "local": "%s %s" % (name, imm), "op": name}[kind])
+        out.append({"const": "%s %d" % (name, imm or 0), "host": "call:" + name, "callf": "callf %s" % imm, "local": "%s %s" % (name, imm), "op": name,
+                    "access": "%s %s" % (name, imm), "segment": "%s %s" % (name, imm)}[kind])
     structured = len(funcs) > 1 or funcs[0]["params"] or funcs[0]["locals"]
     for fn in funcs:
         if structured:
             out.append("func %s %s %s" % tuple(",".join(fn[key]) or "-" for key in ("params", "results", "locals")))
-        _walk(fn, imports, ids, visit)
+        _walk(fn, imports, ids, visit, data_ids)
     if structured:
         out.append("start %d" % start)
     return out
@@ -371,6 +432,10 @@ def wat_to_wasm(text, custom_section=True):
     """binary module for a program of the subset: type, import, function, export and code sections (+ a custom section)"""
     mod = _sexpr(text)
     imports, funcs, ids, start = wat_module(text)
+    memory, datas = wat_memory(text)
+    data_ids = {d[0]: k for k, d in enumerate(datas) if d[0]}
+    access = ["i32.load", "i64.load", None, None, "i32.load8_s", "i32.load8_u", "i32.load16_s", "i32.load16_u", "i64.load8_s", "i64.load8_u", "i64.load16_s",
+              "i64.load16_u", "i64.load32_s", "i64.load32_u", "i32.store", "i64.store", None, None, "i32.store8", "i32.store16", "i64.store8", "i64.store16", "i64.store32"]
     vt = {"i32": 0x7f, "i64": 0x7e}
     types, import_list = [], []
 
@@ -402,6 +467,14 @@ def wat_to_wasm(text, custom_section=True):
                 code.extend(b"\x10" + _uleb(len(import_list) + imm))
             elif kind == "local":
                 code.extend(bytes([{"local.get": 0x20, "local.set": 0x21, "local.tee": 0x22}[nm]]) + _uleb(imm))
+            elif kind == "access":
+                code.extend(bytes([0x28 + access.index(nm)]) + _uleb(0) + _uleb(imm))
+            elif kind == "segment":
+                code.extend(b"\xfc" + (_uleb(8) + _uleb(imm) + b"\x00" if nm == "memory.init" else _uleb(9) + _uleb(imm)))
+            elif nm in ("memory.size", "memory.grow"):
+                code.extend(bytes([0x3F if nm == "memory.size" else 0x40, 0]))
+            elif nm in ("memory.copy", "memory.fill"):
+                code.extend(b"\xfc" + (_uleb(10) + b"\x00\x00" if nm == "memory.copy" else _uleb(11) + b"\x00"))
             elif nm in ("drop", "nop", "select"):
                 code.append({"drop": 0x1A, "nop": 0x01, "select": 0x1B}[nm])
             elif nm in _OTHER_OPS:
@@ -409,7 +482,7 @@ def wat_to_wasm(text, custom_section=True):
             else:
                 w, op = nm[:3], nm[4:]
                 code.append((0x45 if w == "i32" else 0x50) + _CMP_OPS.index(op) if op in _CMP_OPS else (0x67 if w == "i32" else 0x79) + _INT_OPS.index(op))
-        _walk(fn, imports, ids, visit)
+        _walk(fn, imports, ids, visit, data_ids)
         code.append(0x0B)
         body = vec([_uleb(1) + bytes([vt[t]]) for t in fn["locals"]]) + bytes(code)
         bodies.append(_uleb(len(body)) + body)
@@ -417,8 +490,14 @@ def wat_to_wasm(text, custom_section=True):
     out += section(1, vec([b"\x60" + vec([bytes([t]) for t in p]) + vec([bytes([t]) for t in r]) for p, r in types]))
     out += section(2, vec([name(m) + name(f) + b"\x00" + _uleb(t) for m, f, t in import_list]))
     out += section(3, vec([_uleb(t) for t in func_types]))
+    if memory:
+        out += section(5, vec([(b"\x01" + _uleb(memory[0]) + _uleb(memory[1])) if memory[1] else (b"\x00" + _uleb(memory[0]))]))
     out += section(7, vec([name("_start") + b"\x00" + _uleb(len(import_list) + start)]))
+    if datas:
+        out += section(12, _uleb(len(datas)))
     out += section(10, vec(bodies))
+    if datas:
+        out += section(11, vec([(b"\x00\x41" + _sleb(off - (1 << 32) if off >> 31 else off) + b"\x0b" if active else b"\x01") + _uleb(len(data)) + data for _, active, off, data in datas]))
     if custom_section:
         out += section(0, name("producer") + b"tests/refctx_util.py")
     return out
@@ -428,15 +507,22 @@ def wat_to_plain(text):
     """the same module with every function body written as a plain instruction sequence instead of folded forms"""
     imports, funcs, ids, start = wat_module(text)
     by_index = {index: fid for fid, (_, index) in imports.items()}
+    memory, datas = wat_memory(text)
+    data_ids = {d[0]: k for k, d in enumerate(datas) if d[0]}
     out = ["(module"] + ['(import "env" "%s" (func %s))' % (nm, fid) for fid, (nm, _) in imports.items()]
+    if memory:
+        out.append("(memory %d%s)" % (memory[0], " %d" % memory[1] if memory[1] else ""))
+    for _, active, off, data in datas:
+        out.append("(data %s\"%s\")" % ("(i32.const %d) " % off if active else "", "".join("\\%02x" % b for b in data)))
     for k, fn in enumerate(funcs):
         fid = fn["id"] or "$f%d" % k
         head = "(func %s" % fid + "".join(" (param %s)" % t for t in fn["params"]) + "".join(" (result %s)" % t for t in fn["results"]) + "".join(" (local %s)" % t for t in fn["locals"])
         body = []
 
         def visit(kind, nm, imm):
-            body.append({"const": "%s %d" % (nm, imm or 0), "host": "call %s" % by_index.get(imm), "callf": "call %s" % nm, "local": "%s %s" % (nm, imm), "op": nm}[kind])
-        _walk(fn, imports, ids, visit)
+            body.append({"const": "%s %d" % (nm, imm or 0), "host": "call %s" % by_index.get(imm), "callf": "call %s" % nm, "local": "%s %s" % (nm, imm), "op": nm,
+                         "access": "%s offset=%s" % (nm, imm), "segment": "%s %s" % (nm, imm)}[kind])
+        _walk(fn, imports, ids, visit, data_ids)
         out.append(head + "\n" + "\n".join(body) + "\n)")
     out.append('(export "_start" (func %s)))' % (funcs[start]["id"] or "$f%d" % start))
     return "\n".join(out) + "\n"
@@ -519,3 +605,53 @@ def rand_struct_program(rng, w, nstmt=5, depth=2):
             body.append("(call $assert_equal %s %s)" % (t, rhs))
     head = WAT_HEAD_BOTH[:WAT_HEAD_BOTH.index("(func $t")]
     return (head + "\n".join(h[0] for h in helpers) + "\n(func $t (local $x %s) (local $y %s) (local $z %s)\n" % (W, W, W) + "\n".join(body) + "\n" + WAT_TAIL)
+
+
+# ---- programs over linear memory: stores of witnesses and numbers, loads of every width, fill / copy / init
+def rand_memory_program(rng, nstmt=14):
+    """random stores, loads (asserted against a byte-array model), memory.fill / copy / init over a 96-byte window, so that
+    marked ranges are split, joined, overwritten, copied over themselves and cleared in every order"""
+    mem = bytearray(65536)
+    seg = bytes(rng.getrandbits(8) for _ in range(12))
+    body = []
+    P = lambda w, v: "(call $i%d_private_const (i%d.const %d))" % (w, w, v)
+    L = lambda w, v: "(i%d.const %d)" % (w, v)
+    addr = lambda a: L(32, a) if rng.random() < 0.8 else P(32, a)
+    for _ in range(nstmt):
+        r = rng.random()
+        if r < 0.35:
+            w = rng.choice([32, 64])
+            nbytes = rng.choice([1, 2, w // 8] + ([4] if w == 64 else []))
+            a, off = rng.randrange(0, 80), rng.choice([0, 0, 3, 8])
+            v = rng.getrandbits(w)
+            val = P(w, v) if rng.random() < 0.6 else L(w, v)
+            if rng.random() < 0.2:
+                val = "(i%d.add %s %s)" % (w, val, L(w, 1)); v = (v + 1) % (1 << w)
+            name = "store" if nbytes == w // 8 else "store%d" % (8 * nbytes)
+            body.append("(i%d.%s%s %s %s)" % (w, name, " offset=%d" % off if off else "", addr(a), val))
+            mem[a + off:a + off + nbytes] = (v % (1 << (8 * nbytes))).to_bytes(nbytes, "little")
+        elif r < 0.75:
+            w = rng.choice([32, 64])
+            nbytes = rng.choice([1, 2, w // 8] + ([4] if w == 64 else []))
+            signed = rng.random() < 0.5
+            a, off = rng.randrange(0, 80), rng.choice([0, 0, 5])
+            v = int.from_bytes(mem[a + off:a + off + nbytes], "little")
+            if nbytes < w // 8 and signed and v >> (8 * nbytes - 1):
+                v -= 1 << (8 * nbytes)
+            name = "load" if nbytes == w // 8 else "load%d_%s" % (8 * nbytes, "s" if signed else "u")
+            rhs = L(w, v % (1 << w)) if rng.random() < 0.6 else P(w, v % (1 << w))
+            body.append("(call $assert_equal (i%d.%s%s %s) %s)" % (w, name, " offset=%d" % off if off else "", addr(a), rhs))
+        elif r < 0.83:
+            d, n, val = rng.randrange(0, 88), rng.randrange(0, 9), rng.getrandbits(9)
+            body.append("(memory.fill (i32.const %d) (i32.const %d) (i32.const %d))" % (d, val, n))
+            mem[d:d + n] = bytes([val & 0xff]) * n
+        elif r < 0.95:
+            d, sA, n = rng.randrange(0, 80), rng.randrange(0, 80), rng.randrange(0, 17)
+            body.append("(memory.copy (i32.const %d) (i32.const %d) (i32.const %d))" % (d, sA, n))
+            mem[d:d + n] = bytes(mem[sA:sA + n])
+        else:
+            d, sA, n = rng.randrange(0, 88), rng.randrange(0, 8), rng.randrange(0, 5)
+            body.append("(memory.init $seg (i32.const %d) (i32.const %d) (i32.const %d))" % (d, sA, n))
+            mem[d:d + n] = seg[sA:sA + n]
+    head = WAT_HEAD_BOTH[:WAT_HEAD_BOTH.index("(func $t")]
+    return (head + '(memory 1)\n(data $seg "%s")\n(func $t\n' % "".join("\\%02x" % b for b in seg) + "\n".join(body) + "\n" + WAT_TAIL)

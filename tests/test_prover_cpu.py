@@ -333,9 +333,10 @@ def test_wat_emitter_on_the_repo_fixture(pr, oracle):
 
 
 def test_wat_emitter_rejects_what_it_does_not_support(pr):
-    for text, why in (("(module (func $f) (export \"_start\" (func $f)) (memory 1))", "module field"),
+    for text, why in (("(module (func $f) (export \"_start\" (func $f)) (table 1 funcref))", "module field"),
                       ("(module (import \"wasi\" \"x\" (func $x)) (func $f) (export \"_start\" (func $f)))", "env host module"),
-                      ("(module (func $f (i64.load (i32.const 0))) (export \"_start\" (func $f)))", "unsupported instruction"),
+                      ("(module (func $f (drop (f64.add (f64.const 1) (f64.const 2)))) (export \"_start\" (func $f)))", "unsupported instruction"),
+                      ("(module (func $f (drop (i64.load (i32.const 0)))) (export \"_start\" (func $f)))", "without a memory"),
                       ("(module (func $f)", "unbalanced"),
                       ("(module (func $f))", "_start")):
         with pytest.raises(pr.ProverError, match=why):
@@ -445,18 +446,18 @@ def test_wasm_binary_front_end_rejects_what_it_does_not_support(pr):
     pr.wat_emit(good, 64)
     sec = lambda sid, body: bytes([sid, len(body)]) + body
     for data, why in ((good[:-3], "section runs past the end|unexpected end"),
-                      (good[:8] + sec(5, b"\x01\x00\x01") + good[8:], "unsupported module section"),           # a memory
+                      (good[:8] + sec(4, b"\x01\x70\x00\x01") + good[8:], "unsupported module section"),       # a table
                       (b"\0asm\x02\0\0\0" + good[8:], "binary version"),
                       (good[:-1] + b"\x28\x0b", "section runs past|unexpected end|unsupported"),
                       (b"\0asm\x01\0\0\0", "_start")):
         with pytest.raises(pr.ProverError, match=why):
             pr.wat_emit(data, 64)
-    # an opcode outside the subset inside _start (i32.load = 0x28)
+    # an opcode outside the subset inside _start (block = 0x02)
     text = '(module (import "env" "assert_equal" (func $e (param i32 i32))) (func $f (call $e (i32.const 1) (i32.const 1))) (export "_start" (func $f)))'
     wasm = bytearray(U.wat_to_wasm(text, custom_section=False))
     at = wasm.rindex(b"\x41\x01\x41\x01")
-    wasm[at] = 0x28
-    with pytest.raises(pr.ProverError, match="unsupported instruction 0x28"):
+    wasm[at] = 0x02
+    with pytest.raises(pr.ProverError, match="unsupported instruction 0x02"):
         pr.wat_emit(bytes(wasm), 64)
 
 
@@ -507,12 +508,15 @@ def test_front_ends_survive_mutated_inputs_under_sanitizers(tmp_path):
     if res.returncode != 0 and "sanitize" in res.stderr:
         pytest.skip("sanitizer runtime not available")
     assert res.returncode == 0, res.stderr[-2000:]
-    text = open(U.WAT_TEXT["arith32"]).read()
-    (tmp_path / "seed.wat").write_text(text)
-    (tmp_path / "seed.wasm").write_bytes(U.wat_to_wasm(text))
-    for seed in ("seed.wat", "seed.wasm"):
-        res = subprocess.run([exe, str(tmp_path / seed), "3000"], capture_output=True, text=True, timeout=600)
-        assert res.returncode == 0 and "accepted" in res.stdout, (res.stdout + res.stderr)[-3000:]
+    seeds = {"arith": open(U.WAT_TEXT["arith32"]).read(),
+             "struct": U.rand_struct_program(random.Random(1), 64, nstmt=4, depth=2),      # locals, select, module functions
+             "memory": U.rand_memory_program(random.Random(2), nstmt=12)}                  # loads, stores, fill / copy / init, data
+    for name, text in seeds.items():
+        (tmp_path / (name + ".wat")).write_text(text)
+        (tmp_path / (name + ".wasm")).write_bytes(U.wat_to_wasm(text))
+        for seed in (name + ".wat", name + ".wasm"):
+            res = subprocess.run([exe, str(tmp_path / seed), "1500"], capture_output=True, text=True, timeout=600)
+            assert res.returncode == 0 and "accepted" in res.stdout, (res.stdout + res.stderr)[-3000:]
 
 
 @pytest.mark.parametrize("seed", range(6))
@@ -541,3 +545,31 @@ def test_front_end_rejects_malformed_functions(pr):
                       ("(func $t (drop (select (i64.const 1) (i32.const 2) (i32.const 1))))", "type mismatch: select")):
         with pytest.raises(pr.ProverError, match=why):
             pr.wat_emit(head + body + tail, 64)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_memory_programs_constraint_system(pr, oracle, seed):
+    """needs no reference run: random memory programs; every load assertion (expected bytes from a byte-array model) holds
+    in the emitted constraint system, and the binary spelling gives the same rows"""
+    import refctx_util as U
+    rng = random.Random(7300 + seed)
+    text = U.rand_memory_program(rng, nstmt=16)
+    _, st = _wat_check(pr, oracle, text, l=256, k=512)
+    assert st["violated_constraints"] == 0
+    _same_rows(pr, text, U.wat_to_wasm(text), l=256)
+
+
+def test_memory_front_end_errors(pr):
+    head = '(module (import "env" "i32_private_const" (func $pc (param i32) (result i32)))\n(memory 1)\n(data $d "abcd")\n'
+    tail = '(export "_start" (func $t)))'
+    for body, why in (("(func $t (drop (i32.load (i32.const 65533))))", "invalid memory address"),
+                      ("(func $t (i32.store (i32.const 0) (i64.const 1)))", "type mismatch: i32.store"),
+                      ("(func $t (memory.fill (i32.const 0) (call $pc (i32.const 1)) (i32.const 4)))", "concrete operands"),
+                      ("(func $t (memory.init $d (i32.const 0) (i32.const 2) (i32.const 3)))", "memory.init: invalid address"),
+                      ("(func $t (memory.init $nope (i32.const 0) (i32.const 0) (i32.const 1)))", "unknown data segment"),
+                      ("(func $t (memory.copy (i32.const 65530) (i32.const 0) (i32.const 8)))", "memory.copy: out of range"),
+                      ("(func $t (drop (i32.load32_u (i32.const 0))))", "unsupported instruction")):
+        with pytest.raises(pr.ProverError, match=why):
+            pr.wat_emit(head + body + tail, 64)
+    with pytest.raises(pr.ProverError, match="256 MiB"):
+        pr.wat_emit('(module (memory 65536) (func $t) (export "_start" (func $t)))', 64)

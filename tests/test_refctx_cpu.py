@@ -291,6 +291,92 @@ def test_wat_emitter_against_the_reference_interpreter_on_structured_programs(or
     _emitter_equals_reference_rows(pr, U.wat_to_wasm(text), st)
 
 
+MEMORY_PROGRAM = """(module
+ (import "env" "i64_private_const" (func $pc (param i64) (result i64)))
+ (import "env" "i32_private_const" (func $pc32 (param i32) (result i32)))
+ (import "env" "assert_equal" (func $eq (param i64 i64)))
+ (memory 1 2)
+ (data (i32.const 64) "\\01\\02\\03\\04\\05\\06\\07\\08")
+ (data $seg "ab\\ff\\00")
+ (func $main (local $p i32)
+   (i64.store (i32.const 8) (call $pc (i64.const 0x1122334455667788)))
+   (call $eq (i64.load (i32.const 8)) (i64.const 0x1122334455667788))
+   (call $eq (i32.load offset=4 (i32.const 8)) (i32.const 0x11223344))
+   (call $eq (i64.load8_s offset=7 (i32.const 4)) (i64.const 0x55))
+   (call $eq (i32.load16_u (i32.const 8)) (i32.const 0x7788))
+   (call $eq (i32.load (i32.const 64)) (i32.const 0x04030201))
+   (i32.store16 (i32.const 10) (i32.const 0xbeef))
+   (call $eq (i64.load (i32.const 8)) (call $pc (i64.const 0x11223344beef7788)))
+   (memory.copy (i32.const 32) (i32.const 8) (i32.const 8))
+   (call $eq (i64.load (i32.const 32)) (i64.const 0x11223344beef7788))
+   (call $eq (i32.load (i32.const 34)) (i32.const 0x3344beef))
+   (memory.fill (i32.const 36) (i32.const 0xAA) (i32.const 2))
+   (call $eq (i64.load (i32.const 32)) (i64.const 0x1122aaaabeef7788))
+   (memory.init $seg (i32.const 100) (i32.const 1) (i32.const 3))
+   (call $eq (i32.load (i32.const 100)) (i32.const 0x00ff62))
+   (data.drop $seg)
+   (i32.store8 (i32.const 101) (call $pc32 (i32.const 0x1ff)))
+   (call $eq (i32.load8_s (i32.const 101)) (i32.const -1))
+   (call $eq (i32.load (i32.const 100)) (i32.const 0xff62))
+   (local.set $p (call $pc32 (i32.const 200)))
+   (i64.store32 (local.get $p) (i64.const 0x9988776655443322))
+   (call $eq (i64.load32_u (i32.const 200)) (i64.const 0x55443322))
+   (call $eq (i64.load32_s offset=0 (local.get $p)) (i64.const 0x55443322))
+   (call $eq (memory.size) (i32.const 1))
+   (call $eq (memory.grow (i32.const 1)) (i32.const 1))
+   (call $eq (memory.grow (i32.const 1)) (i32.const -1))
+   (i64.store (i32.const 70000) (call $pc (i64.const 5)))
+   (call $eq (i64.load (i32.const 70000)) (i64.const 5))
+   (memory.copy (i32.const 4) (i32.const 8) (i32.const 8))
+   (call $eq (i64.load (i32.const 4)) (i64.const 0x11223344beef7788))
+   (memory.copy (i32.const 12) (i32.const 8) (i32.const 8))
+   (call $eq (i32.load (i32.const 16)) (i32.const 0x11223344))
+ )
+ (export "_start" (func $main)))
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+def test_wat_emitter_linear_memory_against_the_reference(oracle, pr):
+    """loads and stores of every width (with offsets, through witness addresses), memory.size / grow / fill / copy / init,
+    data.drop, active and passive data segments: the reference's memory keeps concrete bytes plus the set of ranges a
+    witness was stored to; a load touching such a range yields a fresh witness (so the marks decide which rows exist).
+    Same rows through the reference's interpreter and through the emitter, in all three spellings"""
+    raw = U.run_reference_on_wat(MEMORY_PROGRAM, 256, seed_byte=3)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    for spelling in (MEMORY_PROGRAM, U.wat_to_wasm(MEMORY_PROGRAM), U.wat_to_plain(MEMORY_PROGRAM)):
+        _emitter_equals_reference_rows(pr, spelling, st)
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("seed", range(10))
+def test_wat_emitter_against_the_reference_interpreter_on_memory_programs(oracle, pr, seed):
+    """differential: random stores / loads / fills / overlapping copies / inits over a small window (tests/refctx_util.py:
+    rand_memory_program): marked ranges are split, joined, moved and cleared in every order; text and binary"""
+    import random
+    rng = random.Random(9900 + seed)
+    text = U.rand_memory_program(rng, nstmt=rng.randrange(6, 24))
+    raw = U.run_reference_on_wat(text, 256, seed_byte=seed + 1)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    _emitter_equals_reference_rows(pr, text, st)
+    _emitter_equals_reference_rows(pr, U.wat_to_wasm(text), st)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "tests")) or not os.path.exists(U.REF_BIN_CPU), reason="needs the reference tree and oracle/_ref/refctx_cpu")
+@pytest.mark.parametrize("name", ["memory_fill_clears_secret_tag", "memory_init_clears_secret_tag"])
+def test_wat_emitter_on_the_reference_memory_programs(oracle, pr, name):
+    """the two memory programs of the reference's tests/: with them, every program of that directory that commits a
+    witness goes through the emitter (f32.wat / f64.wat compute on concrete numbers only and commit nothing)"""
+    text = open(os.path.join(REFERENCE, "tests", name + ".wat")).read()
+    raw = U.run_reference_on_wat(text, 256)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    _emitter_equals_reference_rows(pr, text, st)
+    _emitter_equals_reference_rows(pr, U.wat_to_wasm(text), st)
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
