@@ -514,7 +514,7 @@ public:
 
     // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
     void run(witness_machine &m, wat_stats &st) const {
-        run_state rs{m, st, {}, {}, {}, {}, 0};
+        run_state rs{m, st, {}, {}, {}, {}, 0, {}};
         rs.memory.assign((size_t)mem_pages_ * 65536, 0);
         rs.max_pages = mem_max_;
         for (const data_t &d : datas_) {                      // instantiate (runtime.hpp:537-556): active segments are copied in and dropped
@@ -539,28 +539,42 @@ private:
     // stack_value (stack_value.hpp:84-110) restricted to what the integer subset puts on the stack: a native number
     // (tagged i32 / i64 like native_numeric), one witness, or the bit witnesses of a value.  Moving a value moves the
     // witness handle and COPIES the bits (see bitvec), which is what keeps popped operand bits alive until a handler returns.
+    struct value;
+    // wasm_frame (stack_value.hpp:72-80,261-266): the locals of one activation; the last local dies first.  The frame lives ON
+    // the operand stack (as in the reference), below the activation's values, and dies when that slot is dropped
+    struct frame_t {
+        std::vector<value> locals;
+        uint32_t arity = 0;
+        ~frame_t() { while (!locals.empty()) locals.pop_back(); }
+    };
     struct value {
-        enum kind_t : uint8_t { NUM, WIT, BITS } kind = NUM;
+        enum kind_t : uint8_t { NUM, WIT, BITS, LABEL, FRAME } kind = NUM;
         bool is64 = false;
-        uint64_t num = 0;
+        uint64_t num = 0;                                     // NUM: the number; LABEL: the arity of the block it closes
         wref wit;
         bitvec bits;
+        std::unique_ptr<frame_t> frame;
         value() = default;
         value(value &&) = default;
         value(const value &) = delete;
         // std::variant's move assignment: the same alternative is assigned member-wise (bits element by element), another one
-        // destroys what is held first (a witness is dropped, bits die most significant first) and then takes the new value
+        // destroys what is held first (a witness is dropped, bits die most significant first, a frame takes its locals with
+        // it) and then takes the new value
         value &operator=(value &&o) {
             if (kind != o.kind) {
                 if (kind == WIT) wit.reset();
                 else if (kind == BITS) bits.clear();
+                else if (kind == FRAME) frame.reset();
                 kind = o.kind;
             }
             is64 = o.is64; num = o.num;
             if (kind == WIT) wit = std::move(o.wit);
             else if (kind == BITS) bits = o.bits;
+            else if (kind == FRAME) frame = std::move(o.frame);
             return *this;
         }
+        static value label(uint32_t arity) { value r; r.kind = LABEL; r.num = arity; return r; }
+        static value of(std::unique_ptr<frame_t> f) { value r; r.kind = FRAME; r.frame = std::move(f); return r; }
         // local.get / local.tee (interpreter_impl.hpp:1855-1900): another handle on the same witnesses
         value share() const { value r; r.kind = kind; r.is64 = is64; r.num = num; r.wit = wit; r.bits = bits; return r; }
         static value u32(uint32_t v) { value r; r.num = v; return r; }
@@ -608,7 +622,26 @@ private:
         secret_ranges secrets;
         std::vector<std::vector<uint8_t>> datas;
         uint32_t max_pages = 0;
+        std::vector<frame_t *> frames;                        // current_frame() = frames.back()
         void push(value v) { stack.push_back(std::move(v)); }
+        // drop_n_below (nonbatch_context.hpp:128-138): the `n` values under the top `pos` leave the stack.  First every one of
+        // them is handed to destroy_value BY VALUE (:238-247) -- a witness or a frame moves into that parameter and dies
+        // there, bits are only copied -- then the range is erased: what is left of it dies as std::vector::erase moves the
+        // upper values down (assignment rules of `value`) and destroys the tail
+        void drop_n_below(size_t n, size_t pos) {
+            if (n + pos > stack.size()) throw std::logic_error("wat: operand stack underflow while unwinding");
+            const size_t end = stack.size() - pos, begin = end - n;
+            for (size_t i = begin; i < end; i++) {
+                value gone(std::move(stack[i]));
+                if (gone.kind == value::FRAME) frames.pop_back();
+            }
+            stack.erase(stack.begin() + (ptrdiff_t)begin, stack.begin() + (ptrdiff_t)end);
+        }
+        // block_entry (:153-155): the label goes under the block's parameters
+        void block_entry(size_t params, size_t arity) {
+            if (params > stack.size()) throw std::logic_error("wat: operand stack underflow at a block");
+            stack.insert(stack.end() - (ptrdiff_t)params, value::label((uint32_t)arity));
+        }
         value pop() {
             if (stack.empty()) throw std::invalid_argument("wat: operand stack underflow");
             value top = std::move(stack.back());
@@ -1019,52 +1052,157 @@ private:
 
     struct ins {
         enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, func_call, local_get, local_set, local_tee, select, drop, nop, end_of_statement,
-                                load, store, memory_size, memory_grow, memory_fill, memory_copy, memory_init, data_drop } kind;
+                                load, store, memory_size, memory_grow, memory_fill, memory_copy, memory_init, data_drop,
+                                block, loop, if_, else_, end, br, br_if, br_table, return_, unreachable } kind;
         uint8_t o = 0;                                        // op or host_fn; bytes moved by a load / store
         uint8_t width = 0;
         bool sgn = false;
-        uint64_t imm = 0;                                     // literal, local / function / data index (module functions from 0), memory offset
+        uint64_t imm = 0;                                     // literal, local / function / data index (module functions from 0), memory offset,
+                                                              // branch depth / table; block, loop, if: index of the matching `end`, o = parameters, width = results
+        uint32_t aux = 0;                                     // if: index of its `else` (of its `end` when there is none)
     };
     // a module function: signature, locals (parameters first), flat body
     struct func_t {
         std::vector<uint8_t> params, results, locals;         // widths (32 / 64); locals = params + declared locals
         std::vector<ins> code;
+        std::vector<std::vector<uint32_t>> tables;            // br_table targets, the default last
     };
 
-    // run_call (interpreter.hpp:274-345): arguments become the first locals, declared locals start at zero, the frame --
-    // and with it whatever the locals still hold, last local first -- dies when the body is through
+    // exec_result (types.hpp:53-86): how an instruction ended -- fell through, jumps `label` more blocks out, or returns
+    struct flow {
+        enum { ok, jump, ret } kind = ok;
+        uint32_t label = 0;
+        bool unwind() {                                       // one block left behind; true when the jump ends here
+            if (kind != jump) return false;
+            if (label == 0) { kind = ok; return true; }
+            --label;
+            return false;
+        }
+    };
+    // run_call (interpreter.hpp:274-345): arguments become the first locals, declared locals start at zero, the frame goes on
+    // the stack; when the body is through it is dropped from under the results -- and with it whatever the locals still
+    // hold, last local first.  `return` has dropped it already
     void call(size_t fi, run_state &rs, int depth) const {
         if (depth > 200) throw std::invalid_argument("wat: call depth exceeded");
         const func_t &f = funcs_[fi];
         std::vector<value> arguments;
         for (size_t i = 0; i < f.params.size(); i++) arguments.emplace_back(rs.pop());
         std::reverse(arguments.begin(), arguments.end());
-        struct frame {                                         // ~wasm_frame (stack_value.hpp:261-266): the last local dies first
-            std::vector<value> locals;
-            ~frame() { while (!locals.empty()) locals.pop_back(); }
-        } fr;
-        fr.locals = std::move(arguments);
-        for (size_t i = f.params.size(); i < f.locals.size(); i++) fr.locals.emplace_back(numeric(f.locals[i] == 64, 0));
-        for (const ins &i : f.code) {
-            switch (i.kind) {
-            case ins::konst: rs.push(numeric(i.width == 64, i.imm)); break;
-            case ins::unary_op: unary((op)i.o, i.width, i.sgn, rs); break;
-            case ins::shift_op: shift((op)i.o, i.width, i.sgn, rs); break;
-            case ins::binary_op: binary((op)i.o, i.width, i.sgn, rs); break;
-            case ins::host_call: host((host_fn)i.o, rs); break;
-            case ins::func_call: call((size_t)i.imm, rs, depth + 1); break;
-            case ins::local_get: rs.push(fr.locals[(size_t)i.imm].share()); break;
-            case ins::local_set: fr.locals[(size_t)i.imm] = rs.pop(); break;
-            case ins::local_tee: fr.locals[(size_t)i.imm] = rs.stack.back().share(); break;
-            case ins::select: select(rs); break;
-            case ins::drop: rs.pop(); break;                  // exec_drop (interpreter_impl.hpp:112-116)
-            case ins::nop: break;
-            case ins::end_of_statement: while (rs.stack.size() > (size_t)i.imm) rs.stack.pop_back(); break;
-            case ins::load: load(i, rs); break;
-            case ins::store: store(i, rs); break;
-            default: bulk_memory(i, rs); break;
+        auto frame = std::make_unique<frame_t>();
+        frame->arity = (uint32_t)f.results.size();
+        frame->locals = std::move(arguments);
+        for (size_t i = f.params.size(); i < f.locals.size(); i++) frame->locals.emplace_back(numeric(f.locals[i] == 64, 0));
+        rs.frames.push_back(frame.get());
+        rs.push(value::of(std::move(frame)));
+        const size_t base = rs.stack.size();
+        for (size_t pc = 0; pc < f.code.size(); pc++) {
+            const flow r = step(f, pc, rs, depth, base);
+            if (r.kind == flow::ret) return;                  // (a jump that leaves the body is not caught by the reference either; the validator rejects it)
+        }
+        rs.drop_n_below(1, f.results.size());
+    }
+    // the body of a block / of one arm of an if (run_scoped_block, run_if_then_else: interpreter.hpp:91-131,175-214)
+    flow run_body(const func_t &f, size_t lo, size_t hi, size_t results, run_state &rs, int depth, size_t base) const {
+        for (size_t pc = lo; pc < hi; pc++) {
+            flow r = step(f, pc, rs, depth, base);
+            if (r.kind != flow::ok) { r.unwind(); return r; }
+        }
+        rs.drop_n_below(1, results);                          // the label leaves from under the results
+        return flow{};
+    }
+    // one instruction; `pc` is left on its last index (the `end` of a block)
+    flow step(const func_t &f, size_t &pc, run_state &rs, int depth, size_t base) const {
+        const ins &i = f.code[pc];
+        switch (i.kind) {
+        case ins::konst: rs.push(numeric(i.width == 64, i.imm)); break;
+        case ins::unary_op: unary((op)i.o, i.width, i.sgn, rs); break;
+        case ins::shift_op: shift((op)i.o, i.width, i.sgn, rs); break;
+        case ins::binary_op: binary((op)i.o, i.width, i.sgn, rs); break;
+        case ins::host_call: host((host_fn)i.o, rs); break;
+        case ins::func_call: call((size_t)i.imm, rs, depth + 1); break;
+        case ins::local_get: rs.push(rs.frames.back()->locals[(size_t)i.imm].share()); break;
+        case ins::local_set: rs.frames.back()->locals[(size_t)i.imm] = rs.pop(); break;
+        case ins::local_tee: rs.frames.back()->locals[(size_t)i.imm] = rs.stack.back().share(); break;
+        case ins::select: select(rs); break;
+        case ins::drop: rs.pop(); break;                      // exec_drop (interpreter_impl.hpp:112-116)
+        case ins::nop: break;
+        case ins::end_of_statement: while (rs.stack.size() > base) rs.stack.pop_back(); break;
+        case ins::load: load(i, rs); break;
+        case ins::store: store(i, rs); break;
+        case ins::block: {
+            const size_t end = (size_t)i.imm;
+            rs.block_entry(i.o, i.width);
+            const flow r = run_body(f, pc + 1, end, i.width, rs, depth, base);
+            pc = end;
+            return r;
+        }
+        case ins::loop: {                                     // run_loop (:133-173): the label is re-entered on every round, with the parameters as its arity
+            const size_t end = (size_t)i.imm;
+            for (;;) {
+                rs.block_entry(i.o, i.o);
+                bool again = false;
+                for (size_t q = pc + 1; q < end; q++) {
+                    flow r = step(f, q, rs, depth, base);
+                    if (r.kind == flow::ok) continue;
+                    if (r.unwind()) { again = true; break; }
+                    pc = end;
+                    return r;
+                }
+                if (again) continue;
+                rs.drop_n_below(1, i.width);
+                pc = end;
+                return flow{};
             }
         }
+        case ins::if_: {
+            const size_t end = (size_t)i.imm, els = (size_t)i.aux;
+            value tmp = rs.pop();
+            const uint32_t c = (uint32_t)rs.make_numeric(std::move(tmp));
+            rs.block_entry(i.o, i.width);
+            const flow r = c ? run_body(f, pc + 1, els, i.width, rs, depth, base) : run_body(f, std::min(els + 1, end), end, i.width, rs, depth, base);
+            pc = end;
+            return r;
+        }
+        case ins::br: return branch((uint32_t)i.imm, rs);
+        case ins::br_if: {                                    // run_br_if (:232-240)
+            value v = rs.pop();
+            const uint32_t cond = (uint32_t)rs.make_numeric(std::move(v));
+            if (cond) return branch((uint32_t)i.imm, rs);
+            break;
+        }
+        case ins::br_table: {                                 // run_br_table (:242-253)
+            value v = rs.pop();
+            const uint32_t k = (uint32_t)rs.make_numeric(std::move(v));
+            const std::vector<uint32_t> &t = f.tables[(size_t)i.imm];
+            return branch(k + 1 < t.size() ? t[k] : t.back(), rs);
+        }
+        case ins::return_: {                                  // run_return (:255-272): everything down to and including the frame leaves, the results stay
+            const size_t arity = rs.frames.back()->arity;
+            size_t distance = 0;
+            while (distance < rs.stack.size() && rs.stack[rs.stack.size() - 1 - distance].kind != value::FRAME) distance++;
+            if (distance >= rs.stack.size() || distance < arity) throw std::logic_error("wat: return without a frame");
+            rs.drop_n_below(distance - arity + 1, arity);
+            flow r; r.kind = flow::ret;
+            return r;
+        }
+        case ins::unreachable: throw std::invalid_argument("wat: unreachable executed");
+        case ins::else_: case ins::end: throw std::logic_error("wat: stray block delimiter");
+        default: bulk_memory(i, rs); break;
+        }
+        return flow{};
+    }
+    // run_br (interpreter.hpp:216-230): find the label `l` blocks out, drop it and everything above it except its arity
+    static flow branch(uint32_t l, run_state &rs) {
+        size_t distance = 0, seen = 0;
+        for (;; distance++) {
+            if (distance >= rs.stack.size()) throw std::logic_error("wat: branch target not on the stack");
+            if (rs.stack[rs.stack.size() - 1 - distance].kind == value::LABEL && seen++ == l) break;
+        }
+        const size_t n = (size_t)rs.stack[rs.stack.size() - 1 - distance].num;
+        if (distance < n) throw std::logic_error("wat: branch without its operands");
+        rs.drop_n_below(distance - n + 1, n);
+        flow r; r.kind = flow::jump; r.label = l;
+        return r;
     }
     // do_load (interpreter_impl.hpp:2206-2228): the address is read as a number; a range that holds a stored witness gives a new witness
     static void load(const ins &i, run_state &rs) {
@@ -1144,9 +1282,7 @@ private:
         witness_machine &m = rs.m;
         value sc = rs.pop();
         if (sc.kind == value::NUM) {
-            const size_t victim = rs.stack.size() - (sc.as_u32() ? 1 : 2);
-            { value gone(std::move(rs.stack[victim])); }
-            rs.stack.erase(rs.stack.begin() + (ptrdiff_t)victim);
+            rs.drop_n_below(1, sc.as_u32() ? 0 : 1);
             return;
         }
         rs.st.arithmetic_ops++;
