@@ -514,7 +514,7 @@ public:
 
     // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
     void run(witness_machine &m, wat_stats &st) const {
-        run_state rs{m, st, {}, {}, {}, {}, 0, {}};
+        run_state rs{m, st, {}, {}, {}, {}, 0, {}, 0, step_limit_};
         rs.memory.assign((size_t)mem_pages_ * 65536, 0);
         rs.max_pages = mem_max_;
         for (const data_t &d : datas_) {                      // instantiate (runtime.hpp:537-556): active segments are copied in and dropped
@@ -532,6 +532,7 @@ public:
         st.linear_witnesses = m.linear_released();
     }
     size_t instructions() const { size_t n = 0; for (const func_t &f : funcs_) n += f.code.size(); return n; }
+    void set_step_limit(uint64_t n) { step_limit_ = n; }      // loops make running time a property of the program: executed instructions are bounded
 
 private:
     using wref = witness_machine::wref;
@@ -623,6 +624,7 @@ private:
         std::vector<std::vector<uint8_t>> datas;
         uint32_t max_pages = 0;
         std::vector<frame_t *> frames;                        // current_frame() = frames.back()
+        uint64_t steps = 0, step_limit = 0;
         void push(value v) { stack.push_back(std::move(v)); }
         // drop_n_below (nonbatch_context.hpp:128-138): the `n` values under the top `pos` leave the stack.  First every one of
         // them is handed to destroy_value BY VALUE (:238-247) -- a witness or a frame moves into that parameter and dies
@@ -1051,7 +1053,7 @@ private:
     }
 
     struct ins {
-        enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, func_call, local_get, local_set, local_tee, select, drop, nop, end_of_statement,
+        enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, func_call, local_get, local_set, local_tee, select, drop, nop,
                                 load, store, memory_size, memory_grow, memory_fill, memory_copy, memory_init, data_drop,
                                 block, loop, if_, else_, end, br, br_if, br_table, return_, unreachable } kind;
         uint8_t o = 0;                                        // op or host_fn; bytes moved by a load / store
@@ -1113,6 +1115,7 @@ private:
     // one instruction; `pc` is left on its last index (the `end` of a block)
     flow step(const func_t &f, size_t &pc, run_state &rs, int depth, size_t base) const {
         const ins &i = f.code[pc];
+        if (++rs.steps > rs.step_limit) throw std::invalid_argument("wat: step budget exceeded (" + std::to_string(rs.step_limit) + " instructions)");
         switch (i.kind) {
         case ins::konst: rs.push(numeric(i.width == 64, i.imm)); break;
         case ins::unary_op: unary((op)i.o, i.width, i.sgn, rs); break;
@@ -1126,7 +1129,6 @@ private:
         case ins::select: select(rs); break;
         case ins::drop: rs.pop(); break;                      // exec_drop (interpreter_impl.hpp:112-116)
         case ins::nop: break;
-        case ins::end_of_statement: while (rs.stack.size() > base) rs.stack.pop_back(); break;
         case ins::load: load(i, rs); break;
         case ins::store: store(i, rs); break;
         case ins::block: {
@@ -1300,18 +1302,104 @@ private:
     // operand COUNT only: the reference's own tests call assert_equal (param i64 i64) with i32 operands.
     struct import_t { std::string module, field; };
     func_t *cur_ = nullptr;                                   // the function being built
-    std::vector<uint8_t> types_;
-    size_t floor_ = 0;                                        // stack height below which the current statement may not reach
+    std::vector<uint8_t> types_;                              // 32 / 64; 0 = any (a value popped in unreachable code)
+    // the enclosing blocks of the instruction being added (the function body is the outermost), as WebAssembly validation keeps them
+    struct ctrl_t {
+        ins::kind_t kind;                                     // block, loop, if_, else_ (the second arm of an if); nop for the function body
+        std::vector<uint8_t> start, end;                      // parameter / result widths
+        size_t height;                                        // of types_ when the block was entered (below its parameters)
+        bool unreachable;
+        size_t pc;                                            // where its opening instruction sits
+        std::string name;                                     // $label in text
+    };
+    std::vector<ctrl_t> ctrl_;
 
     uint8_t pop_type(const std::string &shown) {
-        if (types_.size() <= floor_) throw std::invalid_argument("wat: operand stack underflow at " + shown);
+        if (types_.size() <= ctrl_.back().height) {
+            if (ctrl_.back().unreachable) return 0;
+            throw std::invalid_argument("wat: operand stack underflow at " + shown);
+        }
         const uint8_t t = types_.back();
         types_.pop_back();
         return t;
     }
     void want(int width, const std::string &shown) {
         const uint8_t t = pop_type(shown);
-        if (t != width) throw std::invalid_argument("wat: type mismatch: " + shown + " applied to an i" + std::to_string((int)t) + " value");
+        if (t && t != width) throw std::invalid_argument("wat: type mismatch: " + shown + " applied to an i" + std::to_string((int)t) + " value");
+    }
+    void want_all(const std::vector<uint8_t> &ts, const std::string &shown) { for (size_t i = ts.size(); i-- > 0;) want(ts[i], shown); }
+    void dead_code() { types_.resize(ctrl_.back().height); ctrl_.back().unreachable = true; }
+    // block / loop / if with its block type; `name` is the $label of the text format
+    void emit_block(ins::kind_t k, const std::vector<uint8_t> &params, const std::vector<uint8_t> &results, const std::string &name) {
+        const char *shown = k == ins::block ? "block" : (k == ins::loop ? "loop" : "if");
+        if (params.size() > 255 || results.size() > 255 || ctrl_.size() > 500) throw std::invalid_argument("wat: block too large or nested too deeply");
+        if (k == ins::if_) want(32, shown);
+        want_all(params, shown);
+        ctrl_.push_back(ctrl_t{k, params, results, types_.size(), false, cur_->code.size(), name});
+        types_.insert(types_.end(), params.begin(), params.end());
+        ins i; i.kind = k; i.o = (uint8_t)params.size(); i.width = (uint8_t)results.size();
+        cur_->code.push_back(i);
+    }
+    void close_arm(const char *shown) {                       // the values a block leaves must be exactly its results
+        ctrl_t &c = ctrl_.back();
+        want_all(c.end, shown);
+        if (types_.size() != c.height) throw std::invalid_argument(std::string("wat: values left on the stack at ") + shown);
+    }
+    void emit_else() {
+        if (ctrl_.size() < 2 || ctrl_.back().kind != ins::if_) throw std::invalid_argument("wat: else without an if");
+        close_arm("else");
+        ctrl_t &c = ctrl_.back();
+        c.kind = ins::else_; c.unreachable = false;
+        types_.insert(types_.end(), c.start.begin(), c.start.end());
+        cur_->code[c.pc].aux = (uint32_t)cur_->code.size();
+        put(ins::else_);
+    }
+    void emit_end() {
+        if (ctrl_.size() < 2) throw std::invalid_argument("wat: end without a block");
+        if (ctrl_.back().kind == ins::if_ && ctrl_.back().start != ctrl_.back().end) throw std::invalid_argument("wat: an if without an else must leave what it takes");
+        close_arm("end");
+        const ctrl_t c = ctrl_.back();
+        ctrl_.pop_back();
+        types_.insert(types_.end(), c.end.begin(), c.end.end());
+        ins &open = cur_->code[c.pc];
+        open.imm = cur_->code.size();
+        if (c.kind != ins::else_) open.aux = (uint32_t)cur_->code.size();
+        put(ins::end);
+    }
+    // the values a branch to the block `depth` levels out carries
+    const std::vector<uint8_t> &label_types(uint64_t depth, const std::string &shown) {
+        if (depth + 1 >= ctrl_.size()) throw std::invalid_argument("wat: " + shown + ": no such enclosing block (a branch out of the function body is not supported; use return)");
+        const ctrl_t &c = ctrl_[ctrl_.size() - 1 - (size_t)depth];
+        return c.kind == ins::loop ? c.start : c.end;
+    }
+    void emit_br(ins::kind_t k, uint64_t depth) {
+        const std::string shown = k == ins::br ? "br" : "br_if";
+        if (k == ins::br_if) want(32, shown);
+        const std::vector<uint8_t> ts = label_types(depth, shown);
+        want_all(ts, shown);
+        if (k == ins::br) dead_code();
+        else types_.insert(types_.end(), ts.begin(), ts.end());
+        put(k, depth);
+    }
+    void emit_br_table(const std::vector<uint32_t> &targets) {            // the default last
+        if (targets.empty() || targets.size() > 100000) throw std::invalid_argument("wat: malformed br_table");
+        want(32, "br_table");
+        const std::vector<uint8_t> ts = label_types(targets.back(), "br_table");
+        for (uint32_t t : targets) if (label_types(t, "br_table") != ts) throw std::invalid_argument("wat: br_table targets disagree");
+        want_all(ts, "br_table");
+        dead_code();
+        cur_->tables.push_back(targets);
+        put(ins::br_table, cur_->tables.size() - 1);
+    }
+    void emit_return() { want_all(cur_->results, "return"); dead_code(); put(ins::return_); }
+    void emit_unreachable() { dead_code(); put(ins::unreachable); }
+    // a $label or a depth -> depth
+    uint64_t label_depth(const std::string &id) const {
+        if (!id.empty() && id[0] == '$') {
+            for (size_t d = 0; d + 1 < ctrl_.size(); d++) if (ctrl_[ctrl_.size() - 1 - d].name == id) return d;
+            throw std::invalid_argument("wat: unknown label " + id);
+        }
+        return parse_i64(id);
     }
     void put(ins::kind_t k, uint64_t imm = 0) { ins i; i.kind = k; i.imm = imm; cur_->code.push_back(i); }
     void emit_op(const std::string &name, int width, const std::string &shown) {
@@ -1396,17 +1484,25 @@ private:
         if (k == ins::drop) pop_type("drop");
         if (k == ins::select) {
             want(32, "select");
-            const uint8_t b = pop_type("select");
-            want(b, "select");
-            types_.push_back(b);
+            const uint8_t b = pop_type("select"), a = pop_type("select");
+            if (a && b && a != b) throw std::invalid_argument("wat: type mismatch: select applied to an i" + std::to_string((int)a) + " and an i" + std::to_string((int)b) + " value");
+            types_.push_back(a ? a : b);
         }
-        if (k == ins::end_of_statement) { types_.resize(floor_); put(k, floor_); return; }
         put(k);
     }
-    void begin_body(func_t &f) { cur_ = &f; types_.clear(); floor_ = 0; }
+    void begin_body(func_t &f) {
+        cur_ = &f; types_.clear(); ctrl_.clear();
+        ctrl_.push_back(ctrl_t{ins::nop, {}, f.results, 0, false, 0, ""});
+    }
     void end_body(const std::string &name) {
-        if (types_.size() != cur_->results.size()) throw std::invalid_argument("wat: " + name + " leaves " + std::to_string(types_.size()) + " values, its type says " + std::to_string(cur_->results.size()));
-        for (size_t i = 0; i < types_.size(); i++) if (types_[i] != cur_->results[i]) throw std::invalid_argument("wat: " + name + " returns a value of the wrong width");
+        if (ctrl_.size() != 1) throw std::invalid_argument("wat: " + name + " ends inside a block");
+        if (!ctrl_.back().unreachable && types_.size() != cur_->results.size())
+            throw std::invalid_argument("wat: " + name + " leaves " + std::to_string(types_.size()) + " values, its type says " + std::to_string(cur_->results.size()));
+        for (size_t i = cur_->results.size(); i-- > 0;) {
+            const uint8_t t = pop_type(name);
+            if (t && t != cur_->results[i]) throw std::invalid_argument("wat: " + name + " returns a value of the wrong width");
+        }
+        if (!types_.empty()) throw std::invalid_argument("wat: " + name + " leaves values behind its results");
         cur_ = nullptr;
     }
     static std::string printable(const std::string &s) {      // names from a binary go into error messages
@@ -1550,40 +1646,70 @@ private:
             func_t &fn = funcs_[k];
             text_scope sc{imports, func_ids, data_ids, local_ids[k]};
             begin_body(fn);
-            for (size_t i = first_instr[k]; i < f.list.size(); i++) {
-                const sexpr &e = f.list[i];
-                if (e.is_list) {
-                    flatten(e, sc);
-                    if (fn.results.empty()) emit_plain(ins::end_of_statement);   // a value nobody consumed dies here
-                    continue;
-                }
-                // plain (unfolded) instructions: immediates follow their instruction
-                const std::string &a = e.atom;
-                const auto next = [&]() -> const std::string & {
-                    if (i + 1 >= f.list.size() || f.list[i + 1].is_list) throw std::invalid_argument("wat: " + a + " needs an immediate");
-                    return f.list[++i].atom;
-                };
-                if (a == "i32.const" || a == "i64.const") emit_const(a[1] == '3' ? 32 : 64, literal(a, next()));
-                else if (a == "call") emit_call(func_index(next(), sc), imports);
-                else if (a == "local.get" || a == "local.set" || a == "local.tee") emit_local(a == "local.get" ? ins::local_get : (a == "local.set" ? ins::local_set : ins::local_tee), local_index(next(), sc));
-                else if (a == "select") emit_plain(ins::select);
-                else if (a == "drop") emit_plain(ins::drop);
-                else if (a == "nop") emit_plain(ins::nop);
-                else if (a == "memory.size") emit_bulk(ins::memory_size);
-                else if (a == "memory.grow") emit_bulk(ins::memory_grow);
-                else if (a == "memory.fill") emit_bulk(ins::memory_fill);
-                else if (a == "memory.copy") emit_bulk(ins::memory_copy);
-                else if (a == "memory.init") emit_bulk(ins::memory_init, data_index(next(), sc));
-                else if (a == "data.drop") emit_bulk(ins::data_drop, data_index(next(), sc));
-                else if (a.size() > 4 && (a.compare(0, 4, "i32.") == 0 || a.compare(0, 4, "i64.") == 0)) {
-                    size_t j = i + 1;
-                    const uint64_t offset = memarg(f.list, j);
-                    if (emit_access(a.substr(4), a[1] == '3' ? 32 : 64, offset, a)) i = j - 1;
-                    else emit_op(a.substr(4), a[1] == '3' ? 32 : 64, a);
-                }
-                else throw std::invalid_argument("wat: unsupported instruction " + a);
-            }
+            parse_seq(f.list, first_instr[k], f.list.size(), sc);
             end_body(f.list.size() >= 2 && !f.list[1].is_list ? f.list[1].atom : "function " + std::to_string(k));
+        }
+    }
+    // (param ..) / (result ..) lists of a block type, from list[j] on
+    static void blocktype(const std::vector<sexpr> &list, size_t &j, std::vector<uint8_t> &params, std::vector<uint8_t> &results) {
+        for (; j < list.size() && list[j].is_list && (list[j].head() == "param" || list[j].head() == "result" || list[j].head() == "type"); j++) {
+            if (list[j].head() == "type") throw std::invalid_argument("wat: block types by index are not supported in text");
+            for (size_t t = 1; t < list[j].list.size(); t++) (list[j].head() == "param" ? params : results).push_back(width_of(list[j].list[t].atom));
+        }
+    }
+    // a sequence of instructions, folded forms and plain ones mixed: list[from, to)
+    void parse_seq(const std::vector<sexpr> &list, size_t from, size_t to, const text_scope &sc) {
+        for (size_t i = from; i < to; i++) {
+            const sexpr &e = list[i];
+            if (e.is_list) {
+                flatten(e, sc);
+                continue;
+            }
+            // plain (unfolded) instructions: immediates follow their instruction
+            const std::string &a = e.atom;
+            const auto next = [&]() -> const std::string & {
+                if (i + 1 >= to || list[i + 1].is_list) throw std::invalid_argument("wat: " + a + " needs an immediate");
+                return list[++i].atom;
+            };
+            const auto label_follows = [&]() { return i + 1 < to && !list[i + 1].is_list && (list[i + 1].atom[0] == '$' || (list[i + 1].atom[0] >= '0' && list[i + 1].atom[0] <= '9')); };
+            if (a == "i32.const" || a == "i64.const") emit_const(a[1] == '3' ? 32 : 64, literal(a, next()));
+            else if (a == "call") emit_call(func_index(next(), sc), sc.imports);
+            else if (a == "local.get" || a == "local.set" || a == "local.tee") emit_local(a == "local.get" ? ins::local_get : (a == "local.set" ? ins::local_set : ins::local_tee), local_index(next(), sc));
+            else if (a == "select") emit_plain(ins::select);
+            else if (a == "drop") emit_plain(ins::drop);
+            else if (a == "nop") emit_plain(ins::nop);
+            else if (a == "block" || a == "loop" || a == "if") {
+                std::string name;
+                if (i + 1 < to && !list[i + 1].is_list && list[i + 1].atom[0] == '$') name = list[++i].atom;
+                std::vector<uint8_t> params, results;
+                size_t j = i + 1;
+                blocktype(list, j, params, results);
+                i = j - 1;
+                emit_block(a == "block" ? ins::block : (a == "loop" ? ins::loop : ins::if_), params, results, name);
+            }
+            else if (a == "else") { if (i + 1 < to && !list[i + 1].is_list && list[i + 1].atom[0] == '$') i++; emit_else(); }
+            else if (a == "end") { if (i + 1 < to && !list[i + 1].is_list && list[i + 1].atom[0] == '$') i++; emit_end(); }
+            else if (a == "br" || a == "br_if") emit_br(a == "br" ? ins::br : ins::br_if, label_depth(next()));
+            else if (a == "br_table") {
+                std::vector<uint32_t> targets;
+                while (label_follows()) targets.push_back((uint32_t)label_depth(list[++i].atom));
+                emit_br_table(targets);
+            }
+            else if (a == "return") emit_return();
+            else if (a == "unreachable") emit_unreachable();
+            else if (a == "memory.size") emit_bulk(ins::memory_size);
+            else if (a == "memory.grow") emit_bulk(ins::memory_grow);
+            else if (a == "memory.fill") emit_bulk(ins::memory_fill);
+            else if (a == "memory.copy") emit_bulk(ins::memory_copy);
+            else if (a == "memory.init") emit_bulk(ins::memory_init, data_index(next(), sc));
+            else if (a == "data.drop") emit_bulk(ins::data_drop, data_index(next(), sc));
+            else if (a.size() > 4 && (a.compare(0, 4, "i32.") == 0 || a.compare(0, 4, "i64.") == 0)) {
+                size_t j = i + 1;
+                const uint64_t offset = memarg(list, j);
+                if (emit_access(a.substr(4), a[1] == '3' ? 32 : 64, offset, a)) i = j - 1;
+                else emit_op(a.substr(4), a[1] == '3' ? 32 : 64, a);
+            }
+            else throw std::invalid_argument("wat: unsupported instruction " + a);
         }
     }
     static uint64_t literal(const std::string &instr, const std::string &lit) {
@@ -1638,7 +1764,7 @@ private:
             opinfo oi;
             if (!lookup(h.substr(4), oi)) throw std::invalid_argument("wat: unsupported instruction " + h);
             const int n = oi.arity == 1 ? 1 : 2;
-            if ((int)e.list.size() != 1 + n) throw std::invalid_argument("wat: " + h + " takes " + (n == 1 ? "one folded operand" : "two folded operands"));
+            if ((int)e.list.size() > 1 + n) throw std::invalid_argument("wat: " + h + " takes " + (n == 1 ? "one folded operand" : "two folded operands"));   // fewer: the rest is on the stack already
             operands(1);
             emit_op(h.substr(4), h[1] == '3' ? 32 : 64, h);
             return;
@@ -1662,6 +1788,53 @@ private:
             emit_plain(ins::select);
             return;
         }
+        if (h == "block" || h == "loop") {                       // (block $l? (param ..)* (result ..)* instr*)
+            size_t j = 1;
+            std::string name;
+            if (j < e.list.size() && !e.list[j].is_list && e.list[j].atom[0] == '$') name = e.list[j++].atom;
+            std::vector<uint8_t> params, results;
+            blocktype(e.list, j, params, results);
+            emit_block(h == "block" ? ins::block : ins::loop, params, results, name);
+            parse_seq(e.list, j, e.list.size(), sc);
+            emit_end();
+            return;
+        }
+        if (h == "if") {                                          // (if $l? (result ..)* condition* (then instr*) (else instr*)?)
+            size_t j = 1;
+            std::string name;
+            if (j < e.list.size() && !e.list[j].is_list && e.list[j].atom[0] == '$') name = e.list[j++].atom;
+            std::vector<uint8_t> params, results;
+            blocktype(e.list, j, params, results);
+            size_t then_at = j;
+            while (then_at < e.list.size() && !(e.list[then_at].is_list && e.list[then_at].head() == "then")) then_at++;
+            if (then_at >= e.list.size()) throw std::invalid_argument("wat: if without a (then ...) arm");
+            for (size_t c = j; c < then_at; c++) flatten(e.list[c], sc);
+            emit_block(ins::if_, params, results, name);
+            parse_seq(e.list[then_at].list, 1, e.list[then_at].list.size(), sc);
+            if (then_at + 1 < e.list.size()) {
+                if (then_at + 2 != e.list.size() || e.list[then_at + 1].head() != "else") throw std::invalid_argument("wat: malformed if");
+                emit_else();
+                parse_seq(e.list[then_at + 1].list, 1, e.list[then_at + 1].list.size(), sc);
+            }
+            emit_end();
+            return;
+        }
+        if (h == "br" || h == "br_if") {
+            if (e.list.size() < 2 || e.list[1].is_list) throw std::invalid_argument("wat: " + h + " without a label");
+            operands(2);
+            emit_br(h == "br" ? ins::br : ins::br_if, label_depth(e.list[1].atom));
+            return;
+        }
+        if (h == "br_table") {
+            std::vector<uint32_t> targets;
+            size_t j = 1;
+            for (; j < e.list.size() && !e.list[j].is_list; j++) targets.push_back((uint32_t)label_depth(e.list[j].atom));
+            operands(j);
+            emit_br_table(targets);
+            return;
+        }
+        if (h == "return") { operands(1); emit_return(); return; }
+        if (h == "unreachable") { emit_unreachable(); return; }
         if (h == "drop") { operands(1); emit_plain(ins::drop); return; }
         if (h == "nop") { emit_plain(ins::nop); return; }
         throw std::invalid_argument("wat: unsupported instruction " + h);
@@ -1837,9 +2010,35 @@ private:
             begin_body(funcs_[k]);
             for (;;) {
                 const uint8_t c = b.byte();
-                if (c == 0x0B) break;                         // end
+                if (c == 0x0B) {                              // end: of a block, or of the function
+                    if (ctrl_.size() == 1) break;
+                    emit_end();
+                    continue;
+                }
                 const std::string shown = "0x" + std::string(1, "0123456789abcdef"[c >> 4]) + std::string(1, "0123456789abcdef"[c & 15]);
                 if (c == 0x01) emit_plain(ins::nop);
+                else if (c == 0x00) emit_unreachable();
+                else if (c == 0x02 || c == 0x03 || c == 0x04) {
+                    std::vector<uint8_t> params, results;
+                    if (b.p < b.end && *b.p == 0x40) b.byte();
+                    else if (b.p < b.end && (*b.p == 0x7f || *b.p == 0x7e)) results.push_back(b.valtype());
+                    else {
+                        const int64_t t = b.sleb(33);
+                        if (t < 0 || (uint64_t)t >= types.size() || !types[(size_t)t].usable) throw std::invalid_argument("wasm: unsupported block type");
+                        params = types[(size_t)t].params; results = types[(size_t)t].results;
+                    }
+                    emit_block(c == 0x02 ? ins::block : (c == 0x03 ? ins::loop : ins::if_), params, results, "");
+                }
+                else if (c == 0x05) emit_else();
+                else if (c == 0x0C || c == 0x0D) emit_br(c == 0x0C ? ins::br : ins::br_if, b.uleb());
+                else if (c == 0x0E) {
+                    const uint64_t n = b.uleb();
+                    if (n > 100000) throw std::invalid_argument("wasm: malformed br_table");
+                    std::vector<uint32_t> targets;
+                    for (uint64_t j = 0; j <= n; j++) targets.push_back((uint32_t)b.uleb());
+                    emit_br_table(targets);
+                }
+                else if (c == 0x0F) emit_return();
                 else if (c == 0x1A) emit_plain(ins::drop);
                 else if (c == 0x1B) emit_plain(ins::select);
                 else if (c == 0x10) emit_call(b.uleb(), imports);
@@ -1887,6 +2086,7 @@ private:
     struct data_t { std::string bytes; bool active = false; uint32_t offset = 0; };
     std::vector<func_t> funcs_;
     size_t start_ = 0;
+    uint64_t step_limit_ = 200000000;
     bool has_memory_ = false;
     uint32_t mem_pages_ = 0, mem_max_ = 0;
     std::vector<data_t> datas_;

@@ -11,6 +11,7 @@ using namespace ligero::cuda::host;
 static int run(const std::string &data) {
     try {
         wat_program p(data);
+        p.set_step_limit(20000);
         row_packer pk(64);
         witness_machine m(pk, nullptr);
         wat_stats st;

@@ -162,10 +162,36 @@ struct tiny_module {
 // (plus the short forms c / pc / eq / mul of the built-in i64_mul program)
 // assembled the way transpile() (include/transpiler.hpp:741-776) would: runs of plain opcodes become basic blocks, calls
 // stand alone.
-struct wasm_token { std::string op; uint64_t imm = 0; std::vector<std::string> types; };
+struct wasm_token { std::string op; uint64_t imm = 0; std::vector<std::string> types; std::vector<uint64_t> targets; };
+
+static std::vector<value_kind> token_kinds(const std::string &list) {      // "i32,i64" or "-"
+    std::vector<value_kind> out;
+    if (list == "-") return out;
+    size_t b = 0;
+    while (b <= list.size()) {
+        const size_t e = list.find(',', b);
+        const std::string t = list.substr(b, e == std::string::npos ? std::string::npos : e - b);
+        out.push_back(t == "i32" ? value_kind::i32 : value_kind::i64);
+        if (e == std::string::npos) break;
+        b = e + 1;
+    }
+    return out;
+}
+
+// tokens from `pos` up to the "end" / "else" that closes the enclosing block (consumed; `stop` says which) or to the last token
+static std::vector<instr_ptr> assemble_until(const std::vector<wasm_token> &toks, size_t &pos, std::string &stop);
 
 static std::vector<instr_ptr> assemble(const std::vector<wasm_token> &toks) {
+    size_t pos = 0;
+    std::string stop;
+    auto body = assemble_until(toks, pos, stop);
+    if (!stop.empty() || pos != toks.size()) throw std::runtime_error("unbalanced block tokens");
+    return body;
+}
+
+static std::vector<instr_ptr> assemble_until(const std::vector<wasm_token> &toks, size_t &pos, std::string &stop) {
     std::vector<instr_ptr> body;
+    stop.clear();
     std::unique_ptr<basic_block> bb;
     size_t bb_id = 0;
     auto flush = [&] { if (bb) body.push_back(std::move(bb)); };
@@ -192,7 +218,38 @@ static std::vector<instr_ptr> assemble(const std::vector<wasm_token> &toks) {
         {"ge_s", {opcode::inn_ge_sx, sign_kind::sign}}, {"ge_u", {opcode::inn_ge_sx, sign_kind::unsign}},
         {"extend8_s", {opcode::inn_extend8_s, sign_kind::unspecified}}, {"extend16_s", {opcode::inn_extend16_s, sign_kind::unspecified}},
     };
-    for (const wasm_token &t : toks) {
+    while (pos < toks.size()) {
+        const wasm_token &t = toks[pos++];
+        if (t.op == "end" || t.op == "else") { stop = t.op; break; }
+        if (t.op == "block" || t.op == "loop" || t.op == "if") {          // block <params> <results>: what transpile_scope / transpile_if build (include/transpiler.hpp:649-700)
+            flush();
+            block_kind kind(token_kinds(t.types[0]), token_kinds(t.types[1]));
+            std::string closed;
+            std::vector<instr_ptr> inner = assemble_until(toks, pos, closed);
+            if (t.op == "if") {
+                if_then_else br;
+                br.type = kind;
+                br.then_body = std::move(inner);
+                if (closed == "else") { br.else_body = assemble_until(toks, pos, closed); }
+                if (closed != "end") throw std::runtime_error("if without end");
+                body.push_back(make_instr<if_then_else>(std::move(br)));
+            } else {
+                if (closed != "end") throw std::runtime_error("block without end");
+                if (t.op == "block") { scoped_block b; b.type = kind; b.body = std::move(inner); body.push_back(make_instr<scoped_block>(std::move(b))); }
+                else { loop b; b.type = kind; b.body = std::move(inner); body.push_back(make_instr<loop>(std::move(b))); }
+            }
+            continue;
+        }
+        if (t.op == "br") { flush(); body.push_back(make_instr<br>((index_t)t.imm)); continue; }
+        if (t.op == "br_if") { flush(); body.push_back(make_instr<br_if>((index_t)t.imm)); continue; }
+        if (t.op == "br_table") {
+            flush();
+            std::vector<index_t> branches(t.targets.begin(), t.targets.end() - 1);
+            body.push_back(make_instr<br_table>(std::move(branches), (index_t)t.targets.back()));
+            continue;
+        }
+        if (t.op == "return") { flush(); body.push_back(make_instr<ret>()); continue; }
+        if (t.op == "unreachable") { plain(opcode(opcode::unreachable)); continue; }
         const bool typed = t.op.size() > 4 && (t.op.rfind("i32.", 0) == 0 || t.op.rfind("i64.", 0) == 0);
         const value_kind vk = (typed && t.op[1] == '3') ? value_kind::i32 : value_kind::i64;
         const std::string name = typed ? t.op.substr(4) : std::string();
@@ -280,12 +337,19 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
     std::string op;
     while (in >> op) {
         wasm_token tok{op};
-        if (op == "c" || op == "i32.const" || op == "i64.const" || op == "local.get" || op == "local.set" || op == "local.tee" || op == "callf" || op == "start" || op == "memory.init" || op == "data.drop" ||
+        if (op == "c" || op == "i32.const" || op == "i64.const" || op == "local.get" || op == "local.set" || op == "local.tee" || op == "callf" || op == "start" || op == "memory.init" || op == "data.drop" || op == "br" || op == "br_if" ||
             ((op.rfind("i32.", 0) == 0 || op.rfind("i64.", 0) == 0) && (op.find(".load") != std::string::npos || op.find(".store") != std::string::npos))) {
             std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0);
         }
         if (op == "func") {                                   // func <params> <results> <locals>, e.g. "func i64,i32 i64 -": a new module function starts
             for (int j = 0; j < 3; j++) { std::string part; in >> part; tok.types.push_back(part); }
+        }
+        if (op == "block" || op == "loop" || op == "if") {    // block <params> <results>
+            for (int j = 0; j < 2; j++) { std::string part; in >> part; tok.types.push_back(part); }
+        }
+        if (op == "br_table") {                               // br_table <count> <targets ... default>
+            size_t n; in >> n;
+            for (size_t j = 0; j < n; j++) { uint64_t l; in >> l; tok.targets.push_back(l); }
         }
         if (op == "memory") {                                 // memory <pages> <max pages or 0>
             for (int j = 0; j < 2; j++) { std::string part; in >> part; tok.types.push_back(part); }

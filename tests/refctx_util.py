@@ -165,11 +165,66 @@ def _walk(fn, imports, ids, visit, data_ids=None):
     def local(x):
         return fn["names"][x] if x in fn["names"] else int(x)
 
+    labels = []
+
+    def depth(x):
+        if x.startswith("$"):
+            return len(labels) - 1 - max(i for i, nm in enumerate(labels) if nm == x)
+        return int(x)
+
+    def blocktype(rest):
+        name = rest.pop(0) if rest and isinstance(rest[0], str) and rest[0].startswith("$") else None
+        params, results = [], []
+        while rest and isinstance(rest[0], list) and rest[0][0] in ("param", "result"):
+            part = rest.pop(0)
+            (params if part[0] == "param" else results).extend(part[1:])
+        return name, params, results
+
     def emit(e):
         if isinstance(e, str):
             raise ValueError("plain instructions are not handled by the test helpers: " + e)
         h = e[0]
-        if h in ("i64.const", "i32.const"):
+        if h in ("block", "loop"):
+            rest = list(e[1:])
+            name, params, results = blocktype(rest)
+            visit("block", h, (params, results))
+            labels.append(name)
+            for a in rest:
+                emit(a)
+            labels.pop()
+            visit("op", "end", None)
+        elif h == "if":
+            rest = list(e[1:])
+            name, params, results = blocktype(rest)
+            arms = [a for a in rest if isinstance(a, list) and a[0] in ("then", "else")]
+            for a in rest:
+                if a not in arms:
+                    emit(a)
+            visit("block", "if", (params, results))
+            labels.append(name)
+            for a in arms[0][1:]:
+                emit(a)
+            if len(arms) > 1:
+                visit("op", "else", None)
+                for a in arms[1][1:]:
+                    emit(a)
+            labels.pop()
+            visit("op", "end", None)
+        elif h in ("br", "br_if"):
+            for a in e[2:]:
+                emit(a)
+            visit("branch", h, depth(e[1]))
+        elif h == "br_table":
+            targets = [depth(x) for x in e[1:] if isinstance(x, str)]
+            for a in e[1:]:
+                if isinstance(a, list):
+                    emit(a)
+            visit("table", h, targets)
+        elif h in ("return", "unreachable"):
+            for a in e[1:]:
+                emit(a)
+            visit("op", h, None)
+        elif h in ("i64.const", "i32.const"):
             visit("const", h, _lit(e[1]) % (1 << int(h[1:3])))
         elif h == "call":
             for a in e[2:]:
@@ -223,8 +278,20 @@ def wat_to_tokens(text):
         out.append(("data active %d %s" % (offset, data.hex() or "-")) if active else ("data passive %s" % (data.hex() or "-")))
 
     def visit(kind, name, imm):
-        out.append({"const": "%s %d" % (name, imm or 0), "host": "call:" + name, "callf": "callf %s" % imm, "local": "%s %s" % (name, imm), "op": name,
-                    "access": "%s %s" % (name, imm), "segment": "%s %s" % (name, imm)}[kind])
+        if kind == "const":
+            out.append("%s %d" % (name, imm))
+        elif kind == "host":
+            out.append("call:" + name)
+        elif kind == "callf":
+            out.append("callf %s" % imm)
+        elif kind in ("local", "access", "segment", "branch"):
+            out.append("%s %s" % (name, imm))
+        elif kind == "block":
+            out.append("%s %s %s" % (name, ",".join(imm[0]) or "-", ",".join(imm[1]) or "-"))
+        elif kind == "table":
+            out.append("%s %d %s" % (name, len(imm), " ".join(map(str, imm))))
+        else:
+            out.append(name)
     structured = len(funcs) > 1 or funcs[0]["params"] or funcs[0]["locals"]
     for fn in funcs:
         if structured:
@@ -467,6 +534,16 @@ def wat_to_wasm(text, custom_section=True):
                 code.extend(b"\x10" + _uleb(len(import_list) + imm))
             elif kind == "local":
                 code.extend(bytes([{"local.get": 0x20, "local.set": 0x21, "local.tee": 0x22}[nm]]) + _uleb(imm))
+            elif kind == "block":
+                params, results = imm
+                bt = b"\x40" if not params and not results else (bytes([vt[results[0]]]) if not params and len(results) == 1 else _sleb(typeidx(params, results)))
+                code.extend(bytes([{"block": 0x02, "loop": 0x03, "if": 0x04}[nm]]) + bt)
+            elif kind == "branch":
+                code.extend(bytes([0x0C if nm == "br" else 0x0D]) + _uleb(imm))
+            elif kind == "table":
+                code.extend(b"\x0e" + _uleb(len(imm) - 1) + b"".join(_uleb(t) for t in imm))
+            elif nm in ("else", "end", "return", "unreachable"):
+                code.append({"else": 0x05, "end": 0x0B, "return": 0x0F, "unreachable": 0x00}[nm])
             elif kind == "access":
                 code.extend(bytes([0x28 + access.index(nm)]) + _uleb(0) + _uleb(imm))
             elif kind == "segment":
@@ -520,8 +597,22 @@ def wat_to_plain(text):
         body = []
 
         def visit(kind, nm, imm):
-            body.append({"const": "%s %d" % (nm, imm or 0), "host": "call %s" % by_index.get(imm), "callf": "call %s" % nm, "local": "%s %s" % (nm, imm), "op": nm,
-                         "access": "%s offset=%s" % (nm, imm), "segment": "%s %s" % (nm, imm)}[kind])
+            if kind == "const":
+                body.append("%s %d" % (nm, imm))
+            elif kind == "host":
+                body.append("call %s" % by_index.get(imm))
+            elif kind == "callf":
+                body.append("call %s" % nm)
+            elif kind in ("local", "segment", "branch"):
+                body.append("%s %s" % (nm, imm))
+            elif kind == "access":
+                body.append("%s offset=%s" % (nm, imm))
+            elif kind == "block":
+                body.append("%s%s%s" % (nm, "".join(" (param %s)" % t for t in imm[0]), "".join(" (result %s)" % t for t in imm[1])))
+            elif kind == "table":
+                body.append("%s %s" % (nm, " ".join(map(str, imm))))
+            else:
+                body.append(nm)
         _walk(fn, imports, ids, visit, data_ids)
         out.append(head + "\n" + "\n".join(body) + "\n)")
     out.append('(export "_start" (func %s)))' % (funcs[start]["id"] or "$f%d" % start))
@@ -655,3 +746,90 @@ def rand_memory_program(rng, nstmt=14):
             mem[d:d + n] = seg[sA:sA + n]
     head = WAT_HEAD_BOTH[:WAT_HEAD_BOTH.index("(func $t")]
     return (head + '(memory 1)\n(data $seg "%s")\n(func $t\n' % "".join("\\%02x" % b for b in seg) + "\n".join(body) + "\n" + WAT_TAIL)
+
+
+# ---- programs with control flow: if / else, blocks left by br / br_if / br_table, counted loops, early returns
+def rand_cf_program(rng, w, nstmt=5, depth=2):
+    """statements of rand_struct_program plus structured control flow around them.  Arms that are not taken and code
+    skipped by a branch are generated on a scratch copy of the model, so their text is arbitrary but never runs"""
+    W = "i%d" % w
+    helpers = _helpers(w)
+    M = 1 << w
+    early = ("(func $h3 (param $a %s) (param $b %s) (result %s) (local $t %s)\n (local.set $t (%s.mul (local.get $a) (local.get $a)))\n"
+             " (if (%s.gt_u (local.get $a) (local.get $b)) (then (return (local.get $t))))\n (%s.add (local.get $t) (local.get $b)))" % (W, W, W, W, W, W, W))
+    env = {"x": 0, "y": 0, "z": 0}
+    P32 = lambda v: "(call $i32_private_const (i32.const %d))" % v
+
+    def cond(env):
+        """(text of an i32 condition, truth)"""
+        r = rng.random()
+        if r < 0.3:
+            c = rng.randrange(2)
+            return "(i32.const %d)" % (c * 3), bool(c)
+        if r < 0.6:
+            c = rng.randrange(2)
+            return P32(c * 7), bool(c)
+        t, v = rand_struct_expr(rng, 1, w, env, helpers)
+        return "(%s.eqz %s)" % (W, t), v == 0
+
+    def simple(env):
+        t, v = rand_struct_expr(rng, rng.randrange(1, depth + 1), w, env, helpers)
+        if rng.random() < 0.5:
+            name = rng.choice(sorted(env))
+            env[name] = v
+            return "(local.set $%s %s)" % (name, t)
+        rhs = ("(%s.const %d)" % (W, v)) if rng.random() < 0.5 else ("(call $%s_private_const (%s.const %d))" % (W, W, v))
+        return "(call $assert_equal %s %s)" % (t, rhs)
+
+    def stmts(env, n, level):
+        return " ".join(stmt(env, level) for _ in range(n))
+
+    def stmt(env, level):
+        r = rng.random()
+        if level >= 2 or r < 0.4:
+            return simple(env)
+        if r < 0.55:                                             # if / else
+            ct, c = cond(env)
+            taken, other = dict(env), dict(env)
+            a = stmts(taken if c else other, rng.randrange(1, 3), level + 1)
+            b = stmts(other if c else taken, rng.randrange(0, 3), level + 1)
+            env.clear(); env.update(taken)
+            return "(if %s (then %s)%s)" % (ct, a, " (else %s)" % b if b or rng.random() < 0.5 else "")
+        if r < 0.68:                                             # a block left early
+            first = stmts(env, rng.randrange(0, 2), level + 1)
+            ct, c = cond(env)
+            scratch = dict(env)
+            rest = stmts(scratch if c else env, rng.randrange(1, 3), level + 1)
+            return "(block $skip %s (br_if $skip %s) %s)" % (first, ct, rest)
+        if r < 0.78:                                             # a block whose result comes from a branch that drops what lies above the label
+            (t1, _), (t2, _), (t3, v3) = (rand_struct_expr(rng, 1, w, env, helpers) for _ in range(3))
+            name = rng.choice(sorted(env))
+            env[name] = v3
+            return "(local.set $%s (block $v (result %s) %s %s %s (br $v)))" % (name, W, t1, t2, t3)
+        if r < 0.86:                                             # br_table over nested blocks
+            k = rng.randrange(4)
+            idx = "(i32.const %d)" % k if rng.random() < 0.5 else P32(k)
+            # (block $a (block $b (block $c (br_table $c $b $a $c idx)) S_c) S_b) S_a : leaving $c runs S_c S_b S_a, $b runs S_b S_a, $a runs S_a
+            target = ["$c", "$b", "$a", "$c"][min(k, 3)]
+            run_c, run_b = target == "$c", target in ("$c", "$b")
+            sc = stmts(env if run_c else dict(env), 1, level + 1)
+            sb = stmts(env if run_b else dict(env), 1, level + 1)
+            return "(block $a (block $b (block $c (br_table $c $b $a $c %s)) %s) %s)" % (idx, sc, sb)
+        if r < 0.94:                                             # a counted loop accumulating into a local
+            n = rng.randrange(1, 4)
+            name = rng.choice(sorted(env))
+            op = rng.choice(["add", "sub", "mul", "xor", "or", "rotl"])
+            leaf_v = _rand_operand(rng, w)
+            leaf = "(call $%s_private_const (%s.const %d))" % (W, W, leaf_v) if rng.random() < 0.6 else "(%s.const %d)" % (W, leaf_v)
+            for _ in range(n):
+                env[name] = wasm_op(op, w, env[name], leaf_v)
+            return ("(local.set $i (i32.const 0)) (block $done (loop $again (br_if $done (i32.ge_u (local.get $i) (i32.const %d))) "
+                    "(local.set $%s (%s.%s (local.get $%s) %s)) (local.set $i (i32.add (local.get $i) (i32.const 1))) (br $again)))" % (n, name, W, op, name, leaf))
+        (ta, va), (tb, vb) = rand_struct_expr(rng, 1, w, env, helpers), rand_struct_expr(rng, 1, w, env, helpers)   # early return in a callee
+        v = (va * va) % M if va > vb else ((va * va) % M + vb) % M
+        return "(call $assert_equal (call $h3 %s %s) (%s.const %d))" % (ta, tb, W, v)
+
+    body = [stmt(env, 0) for _ in range(nstmt)]
+    head = WAT_HEAD_BOTH[:WAT_HEAD_BOTH.index("(func $t")]
+    return (head + "\n".join(h[0] for h in helpers) + "\n" + early + "\n(func $t (local $x %s) (local $y %s) (local $z %s) (local $i i32)\n" % (W, W, W)
+            + "\n".join(body) + "\n" + WAT_TAIL)

@@ -377,6 +377,69 @@ def test_wat_emitter_on_the_reference_memory_programs(oracle, pr, name):
     _emitter_equals_reference_rows(pr, U.wat_to_wasm(text), st)
 
 
+CONTROL_PROGRAM = """(module
+ (import "env" "i64_private_const" (func $pc (param i64) (result i64)))
+ (import "env" "i32_private_const" (func $pc32 (param i32) (result i32)))
+ (import "env" "assert_equal" (func $eq (param i64 i64)))
+ (func $sum (param $n i32) (result i64) (local $acc i64) (local $i i32)
+   (block $done
+     (loop $again
+       (br_if $done (i32.ge_u (local.get $i) (local.get $n)))
+       (local.set $acc (i64.add (local.get $acc) (call $pc (i64.extend_i32_u (local.get $i)))))
+       (local.set $i (i32.add (local.get $i) (i32.const 1)))
+       (br $again)))
+   (local.get $acc))
+ (func $early (param $a i64) (result i64) (local $t i64)
+   (local.set $t (i64.mul (local.get $a) (local.get $a)))
+   (if (i64.gt_u (local.get $a) (i64.const 3)) (then (return (local.get $t))))
+   (i64.add (local.get $t) (i64.const 100)))
+ (func $main (local $x i64) (local $y i64) (local $i i32)
+   (call $eq (call $sum (i32.const 4)) (i64.const 6))
+   (if (i32.const 1) (then (call $eq (call $pc (i64.const 3)) (i64.const 3))) (else (unreachable)))
+   (call $eq (if (result i64) (call $pc32 (i32.const 1)) (then (call $pc (i64.const 7))) (else (i64.const 8))) (i64.const 7))
+   (call $eq (block $b (result i64) (drop (br_if $b (call $pc (i64.const 4)) (i32.const 1))) (i64.const 5)) (i64.const 4))
+   (call $eq (block $b (result i64) (call $pc (i64.const 1)) (call $pc (i64.const 2)) (i64.clz (call $pc (i64.const 9))) (br $b)) (i64.const 60))
+   (local.set $x (call $pc (i64.const 5)))
+   (block $o (block $in (br_table $in $o $in (i32.const 1))) (unreachable))
+   (call $eq (call $early (call $pc (i64.const 5))) (i64.const 25))
+   (call $eq (call $early (call $pc (i64.const 2))) (i64.const 104))
+   (block $b (local.set $y (call $pc (i64.const 6))) (call $pc (i64.const 9)) (i64.popcnt (call $pc (i64.const 7))) (call $pc (i64.const 8)) (br $b))
+   (call $eq (local.get $y) (i64.const 6))
+   (loop $l (result i64) (call $pc (i64.const 3)) (local.set $i (i32.add (local.get $i) (i32.const 1))) (br_if $l (i32.lt_u (local.get $i) (i32.const 3))))
+   (drop)
+ )
+ (export "_start" (func $main)))
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+def test_wat_emitter_control_flow_against_the_reference(oracle, pr):
+    """block / loop / if / else / br / br_if / br_table / return: labels and frames live on the operand stack and a branch
+    drops everything above its label -- witnesses, bit vectors and frames in the order drop_n_below and std::vector::erase
+    give.  Counted loops, conditions that are witnesses (read as numbers), value-carrying blocks, branches over mixed
+    values, early returns: same rows through the reference's interpreter and the emitter, in all three spellings"""
+    raw = U.run_reference_on_wat(CONTROL_PROGRAM, 256, seed_byte=4)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    for spelling in (CONTROL_PROGRAM, U.wat_to_wasm(CONTROL_PROGRAM), U.wat_to_plain(CONTROL_PROGRAM)):
+        _emitter_equals_reference_rows(pr, spelling, st)
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("seed", range(10))
+def test_wat_emitter_against_the_reference_interpreter_on_control_flow_programs(oracle, pr, seed):
+    """differential: random programs with if / else, blocks left early, branches that drop values, br_table over nested
+    blocks, counted loops and early returns around random integer statements (tests/refctx_util.py: rand_cf_program)"""
+    import random
+    rng = random.Random(12300 + seed)
+    text = U.rand_cf_program(rng, (32, 64)[seed & 1], nstmt=rng.randrange(2, 7), depth=rng.randrange(1, 3))
+    raw = U.run_reference_on_wat(text, 256, seed_byte=seed + 1)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    _emitter_equals_reference_rows(pr, text, st)
+    _emitter_equals_reference_rows(pr, U.wat_to_wasm(text), st)
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
