@@ -117,7 +117,7 @@ typedef struct {
 int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
 
 /* ---- interpreter boundary (BASELINE config 4) ------------------------------------------
- * A front end for straight-line integer programs over the env host module and the witness emitter behind it
+ * A front end for integer programs (control flow, locals, functions, linear memory) over the env host module and the witness emitter behind it
  * (host/wat_emitter.hpp).  `wat` is WebAssembly text (folded like the .wat files under the reference's tests/, or plain) or a WebAssembly
  * binary (it starts with "\0asm"): the reference's prover takes both (src/webgpu_prover.cpp:189-207).  Supported: every
  * integer instruction the reference implements (interpreter_impl.hpp:155-1309: const, add sub mul, div / rem, and or xor,
@@ -125,7 +125,7 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
  * calls of the module's own functions, linear memory (loads / stores of every width, memory.size / grow / fill / copy / init,
  * data.drop, data segments), and env.i32_private_const,
  * i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast_u32 / _u64, assert_is_concrete.
- * Not supported (LGRP error naming the construct): control flow, globals, tables, floating point, other host modules.
+ * Not supported (LGRP error naming the construct): globals, tables, floating point, other host modules.
  * It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under include/zkp/backend/ stand in
  * the reference.  It is not a general WASM machine, but for what it takes it gives every instruction the reference's
  * meaning -- the same witnesses, released in the same order, with the same linear-test randomness -- so the rows, the

@@ -1,9 +1,9 @@
-// Interpreter boundary (BASELINE config 4): a front end for straight-line integer programs over the env host
+// Interpreter boundary (BASELINE config 4): a front end for integer programs over the env host
 // module -- WebAssembly text (folded, as the reference's tests/*.wat are written, or plain) and WebAssembly binaries, both of
 // which the reference's prover takes (src/webgpu_prover.cpp:189-207) -- and the witness machine behind it.
 // It is NOT the reference's interpreter (include/interpreter_impl.hpp + include/zkp/backend/*.hpp: a general WASM machine with
-// control flow, globals and tables over an expression-template backend; out of scope).  For the instructions it
-// takes -- every integer instruction the reference implements (interpreter_impl.hpp:155-1309), select, drop, nop, locals,
+// globals, tables and floating point over an expression-template backend; those stay out of scope).  For the instructions it
+// takes -- every integer instruction the reference implements (interpreter_impl.hpp:155-1309), select, drop, nop, locals, structured control flow,
 // calls of the module's own functions, linear memory (loads, stores, memory.size / grow / fill / copy / init, data segments), and the env
 // functions iNN_private_const / assert_equal / assert_zero / assert_one / assert_constant / witness_cast / assert_is_concrete
 // (host_modules/env.hpp) -- it gives each one the meaning the reference gives it: which witnesses exist, which draws of the
@@ -504,7 +504,7 @@ inline std::pair<witness_machine::wref, witness_machine::wref> witness_machine::
 // A program is the flat instruction list of its exported `_start` function, read either from WebAssembly text (the folded
 // style of the reference's tests/*.wat, plain instruction sequences too) or from a WebAssembly binary (the other input the
 // reference's prover takes, src/webgpu_prover.cpp:189-207): type, import, function, export and code sections of a module
-// whose `_start` is straight-line integer code calling env functions.  No wabt on either path.
+// whose `_start` is integer code calling env functions.  No wabt on either path.
 class wat_program {
 public:
     explicit wat_program(const std::string &data) {
