@@ -24,6 +24,7 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -514,7 +515,8 @@ public:
 
     // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
     void run(witness_machine &m, wat_stats &st) const {
-        run_state rs{m, st, {}, {}, {}, {}, 0, {}, 0, step_limit_};
+        run_state rs{m, st, {}, {}, {}, {}, 0, {}, {}, 0, step_limit_};
+        for (const global_t &g : globals_) rs.globals.push_back(g.init);
         rs.memory.assign((size_t)mem_pages_ * 65536, 0);
         rs.max_pages = mem_max_;
         for (const data_t &d : datas_) {                      // instantiate (runtime.hpp:537-556): active segments are copied in and dropped
@@ -551,6 +553,7 @@ private:
     struct value {
         enum kind_t : uint8_t { NUM, WIT, BITS, LABEL, FRAME } kind = NUM;
         bool is64 = false;
+        bool isf = false;                                     // NUM: a floating-point number (native_numeric's f32 / f64 tags); `num` holds its bits
         uint64_t num = 0;                                     // NUM: the number; LABEL: the arity of the block it closes
         wref wit;
         bitvec bits;
@@ -568,7 +571,7 @@ private:
                 else if (kind == FRAME) frame.reset();
                 kind = o.kind;
             }
-            is64 = o.is64; num = o.num;
+            is64 = o.is64; isf = o.isf; num = o.num;
             if (kind == WIT) wit = std::move(o.wit);
             else if (kind == BITS) bits = o.bits;
             else if (kind == FRAME) frame = std::move(o.frame);
@@ -577,9 +580,13 @@ private:
         static value label(uint32_t arity) { value r; r.kind = LABEL; r.num = arity; return r; }
         static value of(std::unique_ptr<frame_t> f) { value r; r.kind = FRAME; r.frame = std::move(f); return r; }
         // local.get / local.tee (interpreter_impl.hpp:1855-1900): another handle on the same witnesses
-        value share() const { value r; r.kind = kind; r.is64 = is64; r.num = num; r.wit = wit; r.bits = bits; return r; }
+        value share() const { value r; r.kind = kind; r.is64 = is64; r.isf = isf; r.num = num; r.wit = wit; r.bits = bits; return r; }
         static value u32(uint32_t v) { value r; r.num = v; return r; }
         static value u64(uint64_t v) { value r; r.is64 = true; r.num = v; return r; }
+        static value f32(float v) { value r; r.isf = true; uint32_t b; memcpy(&b, &v, 4); r.num = b; return r; }
+        static value f64(double v) { value r; r.isf = r.is64 = true; memcpy(&r.num, &v, 8); return r; }
+        float as_f32() const { const uint32_t b = (uint32_t)num; float v; memcpy(&v, &b, 4); return v; }
+        double as_f64() const { double v; memcpy(&v, &num, 8); return v; }
         static value of(wref w) { value r; r.kind = WIT; r.wit = std::move(w); return r; }
         static value of(bitvec b) { value r; r.kind = BITS; r.bits = b; return r; }
         uint32_t as_u32() const { return (uint32_t)num; }
@@ -624,6 +631,7 @@ private:
         std::vector<std::vector<uint8_t>> datas;
         uint32_t max_pages = 0;
         std::vector<frame_t *> frames;                        // current_frame() = frames.back()
+        std::vector<uint64_t> globals;
         uint64_t steps = 0, step_limit = 0;
         void push(value v) { stack.push_back(std::move(v)); }
         // drop_n_below (nonbatch_context.hpp:128-138): the `n` values under the top `pos` leave the stack.  First every one of
@@ -657,6 +665,7 @@ private:
             return witness_machine::bit_compose_constant(s.bits);
         }
         wref make_witness(value s) {
+            if (s.kind == value::NUM && s.isf) throw std::invalid_argument("wat: a floating-point value where a witness is needed (the reference traps: Unexpected numeric)");
             if (s.kind == value::NUM) return m.acquire(lgr::host::from_u64(s.is64 ? s.as_u64() : s.as_u32()));
             if (s.kind == value::WIT) return std::move(s.wit);
             return m.bit_compose(s.bits);
@@ -696,6 +705,16 @@ private:
         return neg ? (uint64_t)(0 - u) : u;
     }
     static value numeric(bool is64, uint64_t v) { return is64 ? value::u64(v) : value::u32((uint32_t)v); }
+    // value types: the integer widths 32 / 64 and, next to them, the two floating-point types
+    static constexpr uint8_t F32 = 33, F64 = 65;
+    static bool is_float(uint8_t t) { return t == F32 || t == F64; }
+    static std::string type_name(uint8_t t) { return t == 32 ? "i32" : (t == 64 ? "i64" : (t == F32 ? "f32" : (t == F64 ? "f64" : "?"))); }
+    static size_t bytes_of(uint8_t t) { return (t == 32 || t == F32) ? 4 : 8; }
+    static value of_bits(uint8_t t, uint64_t bits) {         // a number of type `t` from its bit pattern
+        value r = numeric(t == 64 || t == F64, bits);
+        r.isf = is_float(t);
+        return r;
+    }
     static int64_t sext(uint64_t v, int w) { return w == 64 ? (int64_t)v : (int64_t)(int32_t)(uint32_t)v; }
 
     // ---- the integer instructions (interpreter_impl.hpp:155-1309).  Locals are declared in the reference's order: that
@@ -969,6 +988,70 @@ private:
         }
     }
 
+    // ---- floating point (interpreter_impl.hpp:1314-1853): numbers only.  The reference computes on native float / double
+    // with the <cmath> functions named below and reads every operand with std::get<native_numeric> -- a witness there ends
+    // its run (bad_variant_access), here it is reported.  Nothing of this reaches a row unless a result is converted back
+    // to an integer and committed (iNN.trunc_* / reinterpret -> iNN_private_const); that is how the tests observe it.
+    enum class fop : uint8_t { abs, neg, ceil, floor, trunc, nearest, sqrt, add, sub, mul, div, min, max, copysign, eq, ne, lt, gt, le, ge,
+                               convert, demote, promote, reinterpret, trunc_to_int, trunc_sat };
+    static value pop_number(run_state &rs, const char *what) {
+        value v = rs.pop();
+        if (v.kind != value::NUM) throw std::invalid_argument(std::string("wat: ") + what + " takes concrete operands (a witness here ends the reference's run)");
+        return v;
+    }
+    template <typename F> static F get_float(const value &v) { if constexpr (sizeof(F) == 4) return v.as_f32(); else return v.as_f64(); }
+    template <typename F> static value put_float(F v) { if constexpr (sizeof(F) == 4) return value::f32(v); else return value::f64(v); }
+    template <typename F> static void float_arith(fop o, run_state &rs) {
+        if (o <= fop::sqrt) {
+            const F x = get_float<F>(pop_number(rs, "a floating-point instruction"));
+            switch (o) {
+            case fop::abs: rs.push(put_float<F>(std::fabs(x))); break;
+            case fop::neg: rs.push(put_float<F>(-x)); break;
+            case fop::ceil: rs.push(put_float<F>(std::ceil(x))); break;
+            case fop::floor: rs.push(put_float<F>(std::floor(x))); break;
+            case fop::trunc: rs.push(put_float<F>(std::trunc(x))); break;
+            case fop::nearest: rs.push(put_float<F>(std::nearbyint(x))); break;
+            default: rs.push(put_float<F>(std::sqrt(x))); break;
+            }
+            return;
+        }
+        const F y = get_float<F>(pop_number(rs, "a floating-point instruction"));
+        const F x = get_float<F>(pop_number(rs, "a floating-point instruction"));
+        switch (o) {
+        case fop::add: rs.push(put_float<F>(x + y)); break;
+        case fop::sub: rs.push(put_float<F>(x - y)); break;
+        case fop::mul: rs.push(put_float<F>(x * y)); break;
+        case fop::div: rs.push(put_float<F>(x / y)); break;
+        // min / max (:1524-1562): a NaN operand gives the default NaN, otherwise std::fmin / std::fmax -- which in glibc on x86-64
+        // are MINSS / MAXSS with the second operand as the source: on a tie the SECOND operand is returned, so max(-0, +0) = +0 and
+        // max(+0, -0) = -0 (WebAssembly says +0 for both).  Spelled out, because a compiler that knows no NaN is left may expand the
+        // call itself with the operands the other way round
+        case fop::min: rs.push(put_float<F>((std::isnan(x) || std::isnan(y)) ? std::numeric_limits<F>::quiet_NaN() : (x < y ? x : y))); break;
+        case fop::max: rs.push(put_float<F>((std::isnan(x) || std::isnan(y)) ? std::numeric_limits<F>::quiet_NaN() : (x > y ? x : y))); break;
+        case fop::copysign: rs.push(put_float<F>(std::copysign(x, y))); break;
+        case fop::eq: rs.push(value::u32(x == y)); break;
+        case fop::ne: rs.push(value::u32(x != y)); break;
+        case fop::lt: rs.push(value::u32(x < y)); break;
+        case fop::gt: rs.push(value::u32(x > y)); break;
+        case fop::le: rs.push(value::u32(x <= y)); break;
+        case fop::ge: rs.push(value::u32(x >= y)); break;
+        default: throw std::logic_error("wat: unknown floating-point instruction");
+        }
+    }
+    // iNN.trunc_fMM_s/u and iNN.trunc_sat_fMM_s/u (:1661-1853): the range tests are the reference's (in double; a float widens exactly)
+    static uint64_t float_to_int(double v, int width, bool sgn, bool sat) {
+        const double range = sgn ? (width == 32 ? 2147483648.0 : 9223372036854775808.0) : (width == 32 ? 4294967296.0 : 18446744073709551616.0);
+        const uint64_t top = width == 32 ? (sgn ? 0x7FFFFFFFULL : 0xFFFFFFFFULL) : (sgn ? 0x7FFFFFFFFFFFFFFFULL : ~0ULL);
+        const uint64_t bottom = sgn ? (width == 32 ? 0x80000000ULL : 0x8000000000000000ULL) : 0;
+        const bool low = sgn ? v < -range : v <= -1.0;
+        if (!sat && (std::isnan(v) || v >= range || low)) throw std::invalid_argument("wat: integer overflow in a float-to-integer conversion");
+        if (std::isnan(v)) return 0;
+        if (v >= range) return top;
+        if (low) return bottom;
+        const double t = std::trunc(v);
+        if (!sgn) return width == 32 ? (uint64_t)(uint32_t)t : (uint64_t)t;
+        return width == 32 ? (uint64_t)(uint32_t)(int32_t)t : (uint64_t)(int64_t)t;
+    }
     struct opinfo { op o; int arity; bool sgn; };           // arity 3 marks the shifts / rotates (two operands, the count is read as a number)
     static bool lookup(const std::string &name, opinfo &out) {
         static const std::map<std::string, opinfo> table = {
@@ -1055,13 +1138,13 @@ private:
     struct ins {
         enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, func_call, local_get, local_set, local_tee, select, drop, nop,
                                 load, store, memory_size, memory_grow, memory_fill, memory_copy, memory_init, data_drop,
-                                block, loop, if_, else_, end, br, br_if, br_table, return_, unreachable } kind;
-        uint8_t o = 0;                                        // op or host_fn; bytes moved by a load / store
-        uint8_t width = 0;
+                                block, loop, if_, else_, end, br, br_if, br_table, return_, unreachable, float_op, global_get, global_set } kind;
+        uint8_t o = 0;                                        // op, fop or host_fn; bytes moved by a load / store
+        uint8_t width = 0;                                    // the value type the instruction computes in (32, 64, F32, F64); conversions: of the result
         bool sgn = false;
         uint64_t imm = 0;                                     // literal, local / function / data index (module functions from 0), memory offset,
                                                               // branch depth / table; block, loop, if: index of the matching `end`, o = parameters, width = results
-        uint32_t aux = 0;                                     // if: index of its `else` (of its `end` when there is none)
+        uint32_t aux = 0;                                     // if: index of its `else` (of its `end` when there is none); conversions: the source type
     };
     // a module function: signature, locals (parameters first), flat body
     struct func_t {
@@ -1069,6 +1152,30 @@ private:
         std::vector<ins> code;
         std::vector<std::vector<uint32_t>> tables;            // br_table targets, the default last
     };
+
+    static void floating(const ins &i, run_state &rs) {
+        const fop o = (fop)i.o;
+        if (o <= fop::ge) {
+            if (i.width == F32) float_arith<float>(o, rs); else float_arith<double>(o, rs);
+            return;
+        }
+        const value x = pop_number(rs, "a conversion to or from floating point");
+        switch (o) {
+        case fop::convert:                                    // fNN.convert_iMM_s/u (:1577-1629)
+            if (i.width == F32) rs.push(value::f32(i.aux == 32 ? (i.sgn ? static_cast<float>(static_cast<int32_t>(x.as_u32())) : static_cast<float>(x.as_u32()))
+                                                               : (i.sgn ? static_cast<float>(static_cast<int64_t>(x.as_u64())) : static_cast<float>(x.as_u64()))));
+            else rs.push(value::f64(i.aux == 32 ? (i.sgn ? static_cast<double>(static_cast<int32_t>(x.as_u32())) : static_cast<double>(x.as_u32()))
+                                                : (i.sgn ? static_cast<double>(static_cast<int64_t>(x.as_u64())) : static_cast<double>(x.as_u64()))));
+            break;
+        case fop::demote: rs.push(value::f32(static_cast<float>(x.as_f64()))); break;
+        case fop::promote: rs.push(value::f64(static_cast<double>(x.as_f32()))); break;
+        case fop::reinterpret: rs.push(of_bits(i.width, bytes_of(i.width) == 4 ? (x.num & 0xFFFFFFFFULL) : x.num)); break;
+        case fop::trunc_to_int: case fop::trunc_sat:
+            rs.push(numeric(i.width == 64, float_to_int(i.aux == F32 ? (double)x.as_f32() : x.as_f64(), i.width, i.sgn, o == fop::trunc_sat)));
+            break;
+        default: throw std::logic_error("wat: unknown floating-point instruction");
+        }
+    }
 
     // exec_result (types.hpp:53-86): how an instruction ended -- fell through, jumps `label` more blocks out, or returns
     struct flow {
@@ -1093,7 +1200,7 @@ private:
         auto frame = std::make_unique<frame_t>();
         frame->arity = (uint32_t)f.results.size();
         frame->locals = std::move(arguments);
-        for (size_t i = f.params.size(); i < f.locals.size(); i++) frame->locals.emplace_back(numeric(f.locals[i] == 64, 0));
+        for (size_t i = f.params.size(); i < f.locals.size(); i++) frame->locals.emplace_back(of_bits(f.locals[i], 0));
         rs.frames.push_back(frame.get());
         rs.push(value::of(std::move(frame)));
         const size_t base = rs.stack.size();
@@ -1117,7 +1224,10 @@ private:
         const ins &i = f.code[pc];
         if (++rs.steps > rs.step_limit) throw std::invalid_argument("wat: step budget exceeded (" + std::to_string(rs.step_limit) + " instructions)");
         switch (i.kind) {
-        case ins::konst: rs.push(numeric(i.width == 64, i.imm)); break;
+        case ins::konst: rs.push(of_bits(i.width, i.imm)); break;
+        case ins::float_op: floating(i, rs); break;
+        case ins::global_get: rs.push(of_bits(globals_[(size_t)i.imm].type, rs.globals[(size_t)i.imm])); break;   // exec_global_get / set (interpreter_impl.hpp:1902-1924):
+        case ins::global_set: rs.globals[(size_t)i.imm] = pop_number(rs, "global.set").num; break;                // a global holds a native number
         case ins::unary_op: unary((op)i.o, i.width, i.sgn, rs); break;
         case ins::shift_op: shift((op)i.o, i.width, i.sgn, rs); break;
         case ins::binary_op: binary((op)i.o, i.width, i.sgn, rs); break;
@@ -1214,9 +1324,9 @@ private:
         uint64_t c = 0;
         memcpy(&c, rs.memory.data() + ea, (size_t)n);
         if (i.sgn && n < 8 && (c >> (8 * n - 1)) & 1) c |= ~0ULL << (8 * n);
-        if (i.width == 32) c &= 0xFFFFFFFFULL;
-        if (rs.secrets.intersects((uint32_t)ea, (uint32_t)(ea + n))) rs.push(value::of(rs.make_witness(numeric(i.width == 64, c))));
-        else rs.push(numeric(i.width == 64, c));
+        if (bytes_of(i.width) == 4) c &= 0xFFFFFFFFULL;
+        if (rs.secrets.intersects((uint32_t)ea, (uint32_t)(ea + n))) rs.push(value::of(rs.make_witness(of_bits(i.width, c))));   // (a float here traps, as in the reference)
+        else rs.push(of_bits(i.width, c));
     }
     // do_store (:2310-2344): the value is read as a number and its witnesses are let go; the range is marked iff it was not a number
     static void store(const ins &i, run_state &rs) {
@@ -1227,7 +1337,7 @@ private:
         if (tmp.kind == value::NUM) rs.secrets.subtract((uint32_t)ea, (uint32_t)(ea + n));
         else rs.secrets.add((uint32_t)ea, (uint32_t)(ea + n));
         uint64_t c = rs.make_numeric(std::move(tmp));
-        if (i.width == 32) c &= 0xFFFFFFFFULL;
+        if (bytes_of(i.width) == 4) c &= 0xFFFFFFFFULL;
         memcpy(rs.memory.data() + ea, &c, (size_t)n);
     }
     // memory.size / grow / fill / copy / init, data.drop (:2108-2204): operands must be numbers (the reference reads them with std::get)
@@ -1302,7 +1412,7 @@ private:
     // operand COUNT only: the reference's own tests call assert_equal (param i64 i64) with i32 operands.
     struct import_t { std::string module, field; };
     func_t *cur_ = nullptr;                                   // the function being built
-    std::vector<uint8_t> types_;                              // 32 / 64; 0 = any (a value popped in unreachable code)
+    std::vector<uint8_t> types_;                              // 32 / 64 / F32 / F64; 0 = any (a value popped in unreachable code)
     // the enclosing blocks of the instruction being added (the function body is the outermost), as WebAssembly validation keeps them
     struct ctrl_t {
         ins::kind_t kind;                                     // block, loop, if_, else_ (the second arm of an if); nop for the function body
@@ -1325,7 +1435,7 @@ private:
     }
     void want(int width, const std::string &shown) {
         const uint8_t t = pop_type(shown);
-        if (t && t != width) throw std::invalid_argument("wat: type mismatch: " + shown + " applied to an i" + std::to_string((int)t) + " value");
+        if (t && t != width) throw std::invalid_argument("wat: type mismatch: " + shown + " applied to an " + type_name(t) + " value");
     }
     void want_all(const std::vector<uint8_t> &ts, const std::string &shown) { for (size_t i = ts.size(); i-- > 0;) want(ts[i], shown); }
     void dead_code() { types_.resize(ctrl_.back().height); ctrl_.back().unreachable = true; }
@@ -1417,9 +1527,102 @@ private:
         i.o = (uint8_t)oi.o; i.width = (uint8_t)width; i.sgn = oi.sgn;
         cur_->code.push_back(i);
     }
-    void emit_const(int width, uint64_t v) {
+    void emit_const(int width, uint64_t v) {                  // for F32 / F64: the bit pattern
         types_.push_back((uint8_t)width);
-        ins i; i.kind = ins::konst; i.width = (uint8_t)width; i.imm = width == 32 ? (v & 0xFFFFFFFFULL) : v; cur_->code.push_back(i);
+        ins i; i.kind = ins::konst; i.width = (uint8_t)width; i.imm = bytes_of((uint8_t)width) == 4 ? (v & 0xFFFFFFFFULL) : v; cur_->code.push_back(i);
+    }
+    // a floating-point instruction or a conversion by its full name ("f32.add", "i64.trunc_sat_f64_u"); false if it is none.
+    // `probe`: only say how many operands it takes (0 = not a floating-point instruction)
+    int emit_float(const std::string &full, const std::string &shown, bool probe = false) {
+        if (full.size() < 5 || full[3] != '.') return 0;
+        const std::string ty = full.substr(0, 3), name = full.substr(4);
+        const uint8_t t = ty == "i32" ? 32 : (ty == "i64" ? 64 : (ty == "f32" ? F32 : (ty == "f64" ? F64 : 0)));
+        if (!t) return 0;
+        static const std::map<std::string, fop> arith = {
+            {"abs", fop::abs}, {"neg", fop::neg}, {"ceil", fop::ceil}, {"floor", fop::floor}, {"trunc", fop::trunc}, {"nearest", fop::nearest}, {"sqrt", fop::sqrt},
+            {"add", fop::add}, {"sub", fop::sub}, {"mul", fop::mul}, {"div", fop::div}, {"min", fop::min}, {"max", fop::max}, {"copysign", fop::copysign},
+            {"eq", fop::eq}, {"ne", fop::ne}, {"lt", fop::lt}, {"gt", fop::gt}, {"le", fop::le}, {"ge", fop::ge}};
+        ins i; i.kind = ins::float_op;
+        uint8_t from = 0, to = 0;
+        int arity = 1;
+        const auto type_at = [&](size_t pos) -> uint8_t {    // "i32" / "i64" / "f32" / "f64" inside the name
+            const std::string w = name.substr(pos, 3);
+            return w == "i32" ? 32 : (w == "i64" ? 64 : (w == "f32" ? F32 : (w == "f64" ? F64 : 0)));
+        };
+        if (is_float(t)) {
+            const auto it = arith.find(name);
+            if (it != arith.end()) {
+                i.o = (uint8_t)it->second; i.width = t;
+                arity = it->second <= fop::sqrt ? 1 : 2;
+                from = t; to = it->second >= fop::eq ? 32 : t;
+            } else if (name.compare(0, 8, "convert_") == 0 && name.size() == 13 && (name[12] == 's' || name[12] == 'u') && name[11] == '_' && !is_float(type_at(8)) && type_at(8)) {
+                i.o = (uint8_t)fop::convert; i.width = t; i.aux = type_at(8); i.sgn = name[12] == 's';
+                from = (uint8_t)i.aux; to = t;
+            } else if ((t == F32 && name == "demote_f64") || (t == F64 && name == "promote_f32")) {
+                i.o = (uint8_t)(t == F32 ? fop::demote : fop::promote); i.width = t;
+                from = t == F32 ? F64 : F32; to = t;
+            } else if ((t == F32 && name == "reinterpret_i32") || (t == F64 && name == "reinterpret_i64")) {
+                i.o = (uint8_t)fop::reinterpret; i.width = t;
+                from = t == F32 ? 32 : 64; to = t;
+            } else return 0;
+        } else {
+            if ((t == 32 && name == "reinterpret_f32") || (t == 64 && name == "reinterpret_f64")) {
+                i.o = (uint8_t)fop::reinterpret; i.width = t;
+                from = t == 32 ? F32 : F64; to = t;
+            } else if (name.compare(0, 6, "trunc_") == 0) {
+                const size_t at = name.compare(0, 10, "trunc_sat_") == 0 ? 10 : 6;
+                if (name.size() != at + 5 || name[at + 3] != '_' || (name[at + 4] != 's' && name[at + 4] != 'u') || !is_float(type_at(at))) return 0;
+                i.o = (uint8_t)(at == 10 ? fop::trunc_sat : fop::trunc_to_int); i.width = t; i.aux = type_at(at); i.sgn = name[at + 4] == 's';
+                from = (uint8_t)i.aux; to = t;
+            } else return 0;
+        }
+        if (probe) return arity;
+        if (arity == 2) want(from, shown);
+        want(from, shown);
+        types_.push_back(to);
+        cur_->code.push_back(i);
+        return arity;
+    }
+    void emit_global(ins::kind_t k, uint64_t index) {
+        if (index >= globals_.size()) throw std::invalid_argument("wat: unknown global " + std::to_string(index));
+        const global_t &g = globals_[(size_t)index];
+        if (k == ins::global_get) types_.push_back(g.type);
+        else {
+            if (!g.mut) throw std::invalid_argument("wat: global.set of an immutable global");
+            want(g.type, "global.set");
+        }
+        put(k, index);
+    }
+    void add_global(uint8_t type, bool mut, uint64_t init) {
+        if (type != 32 && type != 64) throw std::invalid_argument("wat: only i32 and i64 globals are supported (the reference traps on others: Unexpected global value type)");
+        if (globals_.size() >= 100000) throw std::invalid_argument("wat: too many globals");
+        globals_.push_back(global_t{type, mut, type == 32 ? (init & 0xFFFFFFFFULL) : init});
+    }
+    // fNN.const literals: decimal and hexadecimal floating point, inf, nan, nan:0x<payload> (underscores allowed) -> bits
+    static uint64_t parse_float(const std::string &lit, bool single) {
+        std::string t;
+        for (char ch : lit) if (ch != '_') t.push_back(ch);
+        size_t p = 0;
+        bool neg = false;
+        if (p < t.size() && (t[p] == '+' || t[p] == '-')) { neg = t[p] == '-'; p++; }
+        const std::string body = t.substr(p);
+        const uint64_t sign = neg ? (single ? 0x80000000ULL : 0x8000000000000000ULL) : 0;
+        if (body == "inf") return sign | (single ? 0x7F800000ULL : 0x7FF0000000000000ULL);
+        if (body == "nan") return sign | (single ? 0x7FC00000ULL : 0x7FF8000000000000ULL);
+        if (body.compare(0, 6, "nan:0x") == 0) {
+            const uint64_t payload = parse_i64(body.substr(4));
+            const uint64_t mask = single ? 0x7FFFFFULL : 0xFFFFFFFFFFFFFULL;
+            if (!payload || payload > mask) throw std::invalid_argument("wat: bad NaN payload " + lit);
+            return sign | (single ? 0x7F800000ULL : 0x7FF0000000000000ULL) | payload;
+        }
+        if (body.empty() || !((body[0] >= '0' && body[0] <= '9'))) throw std::invalid_argument("wat: bad floating-point literal " + lit);
+        for (char ch : body) if (!strchr("0123456789abcdefABCDEFxXpP.+-", ch)) throw std::invalid_argument("wat: bad floating-point literal " + lit);
+        char *end = nullptr;
+        uint64_t bits = 0;
+        if (single) { const float v = strtof(body.c_str(), &end); uint32_t b; memcpy(&b, &v, 4); bits = b; }
+        else { const double v = strtod(body.c_str(), &end); memcpy(&bits, &v, 8); }
+        if (!end || *end) throw std::invalid_argument("wat: bad floating-point literal " + lit);
+        return bits | sign;
     }
     void emit_host(const std::string &module, const std::string &field) {
         if (module != "env") throw std::invalid_argument("wat: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
@@ -1456,8 +1659,9 @@ private:
             {"store", {0, 0}}, {"store8", {1, 0}}, {"store16", {2, 0}}, {"store32", {4, 0}}};
         const auto it = table.find(name);
         if (it == table.end()) return false;
-        const int bytes = it->second.first ? it->second.first : width / 8;
+        const int bytes = it->second.first ? it->second.first : (int)bytes_of((uint8_t)width);
         if (bytes == 4 && it->second.first && width != 64) return false;      // load32_* / store32 exist for i64 only
+        if (is_float((uint8_t)width) && it->second.first) return false;       // floats move whole
         if (!has_memory_) throw std::invalid_argument("wat: " + shown + " in a module without a memory");
         if (offset > 0xFFFFFFFFULL) throw std::invalid_argument("wat: memory offset out of range");
         const bool is_store = name[0] == 's';
@@ -1485,7 +1689,7 @@ private:
         if (k == ins::select) {
             want(32, "select");
             const uint8_t b = pop_type("select"), a = pop_type("select");
-            if (a && b && a != b) throw std::invalid_argument("wat: type mismatch: select applied to an i" + std::to_string((int)a) + " and an i" + std::to_string((int)b) + " value");
+            if (a && b && a != b) throw std::invalid_argument("wat: type mismatch: select applied to an " + type_name(a) + " and an " + type_name(b) + " value");
             types_.push_back(a ? a : b);
         }
         put(k);
@@ -1500,7 +1704,7 @@ private:
             throw std::invalid_argument("wat: " + name + " leaves " + std::to_string(types_.size()) + " values, its type says " + std::to_string(cur_->results.size()));
         for (size_t i = cur_->results.size(); i-- > 0;) {
             const uint8_t t = pop_type(name);
-            if (t && t != cur_->results[i]) throw std::invalid_argument("wat: " + name + " returns a value of the wrong width");
+            if (t && t != cur_->results[i]) throw std::invalid_argument("wat: " + name + " returns a value of the wrong type");
         }
         if (!types_.empty()) throw std::invalid_argument("wat: " + name + " leaves values behind its results");
         cur_ = nullptr;
@@ -1513,7 +1717,9 @@ private:
     static uint8_t width_of(const std::string &t) {
         if (t == "i32") return 32;
         if (t == "i64") return 64;
-        throw std::invalid_argument("wat: only i32 and i64 values are supported (" + printable(t) + ")");
+        if (t == "f32") return F32;
+        if (t == "f64") return F64;
+        throw std::invalid_argument("wat: only i32, i64, f32 and f64 values are supported (" + printable(t) + ")");
     }
 
     // ---- text ------------------------------------------------------------------------------------------------
@@ -1521,6 +1727,7 @@ private:
         const std::vector<import_t> &imports;
         const std::map<std::string, size_t> &func_ids;        // $name -> function index (imports first)
         const std::map<std::string, size_t> &data_ids;
+        const std::map<std::string, size_t> &global_ids;
         std::map<std::string, size_t> local_ids;
     };
     void set_memory(uint64_t pages, uint64_t max_pages) {
@@ -1565,7 +1772,7 @@ private:
         const sexpr top = p.parse_top();
         if (top.head() != "module") throw std::invalid_argument("wat: expected (module ...)");
         std::vector<import_t> imports;
-        std::map<std::string, size_t> func_ids, data_ids;
+        std::map<std::string, size_t> func_ids, data_ids, global_ids;
         std::vector<const sexpr *> bodies;
         std::string start;
         for (size_t i = 1; i < top.list.size(); i++) {
@@ -1602,6 +1809,17 @@ private:
                     d.bytes += decode_string(f.list[j].atom);
                 }
                 datas_.push_back(d);
+            } else if (f.head() == "global") {                 // (global [$id] i32 | (mut i32) (i32.const v)): the initialiser must be a constant
+                size_t j = 1;
+                if (j < f.list.size() && !f.list[j].is_list && f.list[j].atom[0] == '$') global_ids[f.list[j++].atom] = globals_.size();
+                if (j + 2 != f.list.size() || !f.list[j + 1].is_list) throw std::invalid_argument("wat: unsupported global declaration");
+                const sexpr &ty = f.list[j], &init = f.list[j + 1];
+                const bool mut = ty.is_list;
+                if (mut && (ty.head() != "mut" || ty.list.size() != 2 || ty.list[1].is_list)) throw std::invalid_argument("wat: unsupported global declaration");
+                const uint8_t t = width_of(mut ? ty.list[1].atom : ty.atom);
+                if (is_float(t)) add_global(t, mut, 0);         // (throws: the reference takes i32 / i64 globals only)
+                if (init.list.size() != 2 || init.head() != (t == 32 ? "i32.const" : "i64.const") || init.list[1].is_list) throw std::invalid_argument("wat: a global's initialiser must be a constant of its type");
+                add_global(t, mut, literal(init.head(), init.list[1].atom));
             } else {
                 throw std::invalid_argument("wat: unsupported module field (" + f.head() + ")");
             }
@@ -1644,7 +1862,7 @@ private:
         for (size_t k = 0; k < bodies.size(); k++) {
             const sexpr &f = *bodies[k];
             func_t &fn = funcs_[k];
-            text_scope sc{imports, func_ids, data_ids, local_ids[k]};
+            text_scope sc{imports, func_ids, data_ids, global_ids, local_ids[k]};
             begin_body(fn);
             parse_seq(f.list, first_instr[k], f.list.size(), sc);
             end_body(f.list.size() >= 2 && !f.list[1].is_list ? f.list[1].atom : "function " + std::to_string(k));
@@ -1673,6 +1891,8 @@ private:
             };
             const auto label_follows = [&]() { return i + 1 < to && !list[i + 1].is_list && (list[i + 1].atom[0] == '$' || (list[i + 1].atom[0] >= '0' && list[i + 1].atom[0] <= '9')); };
             if (a == "i32.const" || a == "i64.const") emit_const(a[1] == '3' ? 32 : 64, literal(a, next()));
+            else if (a == "f32.const" || a == "f64.const") emit_const(a[1] == '3' ? F32 : F64, parse_float(next(), a[1] == '3'));
+            else if (a == "global.get" || a == "global.set") emit_global(a == "global.get" ? ins::global_get : ins::global_set, global_index(next(), sc));
             else if (a == "call") emit_call(func_index(next(), sc), sc.imports);
             else if (a == "local.get" || a == "local.set" || a == "local.tee") emit_local(a == "local.get" ? ins::local_get : (a == "local.set" ? ins::local_set : ins::local_tee), local_index(next(), sc));
             else if (a == "select") emit_plain(ins::select);
@@ -1703,11 +1923,13 @@ private:
             else if (a == "memory.copy") emit_bulk(ins::memory_copy);
             else if (a == "memory.init") emit_bulk(ins::memory_init, data_index(next(), sc));
             else if (a == "data.drop") emit_bulk(ins::data_drop, data_index(next(), sc));
-            else if (a.size() > 4 && (a.compare(0, 4, "i32.") == 0 || a.compare(0, 4, "i64.") == 0)) {
+            else if (a.size() > 4 && (a.compare(0, 4, "i32.") == 0 || a.compare(0, 4, "i64.") == 0 || a.compare(0, 4, "f32.") == 0 || a.compare(0, 4, "f64.") == 0)) {
                 size_t j = i + 1;
                 const uint64_t offset = memarg(list, j);
-                if (emit_access(a.substr(4), a[1] == '3' ? 32 : 64, offset, a)) i = j - 1;
-                else emit_op(a.substr(4), a[1] == '3' ? 32 : 64, a);
+                if (emit_access(a.substr(4), width_of(a.substr(0, 3)), offset, a)) i = j - 1;
+                else if (emit_float(a, a)) {}
+                else if (a[0] == 'i') emit_op(a.substr(4), a[1] == '3' ? 32 : 64, a);
+                else throw std::invalid_argument("wat: unsupported instruction " + a);
             }
             else throw std::invalid_argument("wat: unsupported instruction " + a);
         }
@@ -1722,6 +1944,12 @@ private:
         if (it != sc.func_ids.end()) return it->second;
         if (!id.empty() && id[0] >= '0' && id[0] <= '9') return parse_i64(id);
         throw std::invalid_argument("wat: call of an unknown function (" + id + ")");
+    }
+    static uint64_t global_index(const std::string &id, const text_scope &sc) {
+        const auto it = sc.global_ids.find(id);
+        if (it != sc.global_ids.end()) return it->second;
+        if (!id.empty() && id[0] >= '0' && id[0] <= '9') return parse_i64(id);
+        throw std::invalid_argument("wat: unknown global " + id);
     }
     static uint64_t local_index(const std::string &id, const text_scope &sc) {
         const auto it = sc.local_ids.find(id);
@@ -1739,12 +1967,33 @@ private:
             emit_const(h[1] == '3' ? 32 : 64, literal(h, e.list[1].atom));
             return;
         }
-        if (h.size() >= 8 && (h.compare(0, 8, "i32.load") == 0 || h.compare(0, 8, "i64.load") == 0 || h.compare(0, 9, "i32.store") == 0 || h.compare(0, 9, "i64.store") == 0)) {
+        if (h == "f32.const" || h == "f64.const") {
+            if (e.list.size() != 2 || e.list[1].is_list) throw std::invalid_argument("wat: " + h + " takes one literal");
+            emit_const(h[1] == '3' ? F32 : F64, parse_float(e.list[1].atom, h[1] == '3'));
+            return;
+        }
+        const bool typed = h.size() > 4 && h[3] == '.' && (h[0] == 'i' || h[0] == 'f') && (h.compare(1, 2, "32") == 0 || h.compare(1, 2, "64") == 0);
+        if (typed && (h.compare(4, 4, "load") == 0 || h.compare(4, 5, "store") == 0)) {
             size_t j = 1;
             const uint64_t offset = memarg(e.list, j);
-            if (e.list.size() - j != (h[4] == 's' ? 2u : 1u)) throw std::invalid_argument("wat: " + h + " takes " + (h[4] == 's' ? "two folded operands" : "one folded operand"));
+            if (e.list.size() - j > (h[4] == 's' ? 2u : 1u)) throw std::invalid_argument("wat: " + h + " takes " + (h[4] == 's' ? "two folded operands" : "one folded operand"));   // fewer: the rest is on the stack already
             operands(j);
-            if (!emit_access(h.substr(4), h[1] == '3' ? 32 : 64, offset, h)) throw std::invalid_argument("wat: unsupported instruction " + h);
+            if (!emit_access(h.substr(4), width_of(h.substr(0, 3)), offset, h)) throw std::invalid_argument("wat: unsupported instruction " + h);
+            return;
+        }
+        if (typed) {
+            const int n = emit_float(h, h, true);
+            if (n) {
+                if ((int)e.list.size() > 1 + n) throw std::invalid_argument("wat: " + h + " takes " + (n == 1 ? "one folded operand" : "two folded operands"));
+                operands(1);
+                emit_float(h, h);
+                return;
+            }
+        }
+        if (h == "global.get" || h == "global.set") {
+            if (e.list.size() < 2 || e.list[1].is_list || e.list.size() > (h == "global.get" ? 2u : 3u)) throw std::invalid_argument("wat: malformed " + h);
+            operands(2);
+            emit_global(h == "global.get" ? ins::global_get : ins::global_set, global_index(e.list[1].atom, sc));
             return;
         }
         if (h == "memory.size" || h == "memory.grow" || h == "memory.fill" || h == "memory.copy") {
@@ -1883,7 +2132,9 @@ private:
             const uint8_t t = byte();
             if (t == 0x7f) return 32;
             if (t == 0x7e) return 64;
-            throw std::invalid_argument("wasm: only i32 and i64 values are supported");
+            if (t == 0x7d) return F32;
+            if (t == 0x7c) return F64;
+            throw std::invalid_argument("wasm: only i32, i64, f32 and f64 values are supported");
         }
     };
     void parse_binary(const std::string &data) {
@@ -1941,8 +2192,8 @@ private:
                         const size_t cnt = (size_t)s.uleb();
                         for (size_t j = 0; j < cnt; j++) {
                             const uint8_t v = s.byte();
-                            if (v != 0x7f && v != 0x7e) t.usable = false;
-                            (part ? t.results : t.params).push_back(v == 0x7f ? 32 : 64);
+                            if (v != 0x7f && v != 0x7e && v != 0x7d && v != 0x7c) t.usable = false;
+                            (part ? t.results : t.params).push_back(v == 0x7f ? 32 : (v == 0x7e ? 64 : (v == 0x7d ? F32 : F64)));
                         }
                     }
                     types.push_back(t);
@@ -1963,6 +2214,19 @@ private:
             case 3: {
                 const size_t n = (size_t)s.uleb();
                 for (size_t i = 0; i < n; i++) func_types.push_back(s.uleb());
+                break;
+            }
+            case 6: {                                         // globals: valtype, mutability, a constant initialiser
+                const size_t n = (size_t)s.uleb();
+                for (size_t i = 0; i < n; i++) {
+                    const uint8_t t = s.valtype(), mut = s.byte();
+                    if (mut > 1) throw std::invalid_argument("wasm: malformed global");
+                    if (is_float(t)) add_global(t, mut != 0, 0);   // (throws)
+                    if (s.byte() != (t == 32 ? 0x41 : 0x42)) throw std::invalid_argument("wasm: a global's initialiser must be a constant of its type");
+                    const uint64_t init = (uint64_t)s.sleb(t == 32 ? 32 : 64);
+                    if (s.byte() != 0x0B) throw std::invalid_argument("wasm: a global's initialiser must be a constant of its type");
+                    add_global(t, mut != 0, init);
+                }
                 break;
             }
             case 7: {                                         // exports: the function called _start
@@ -2021,7 +2285,7 @@ private:
                 else if (c == 0x02 || c == 0x03 || c == 0x04) {
                     std::vector<uint8_t> params, results;
                     if (b.p < b.end && *b.p == 0x40) b.byte();
-                    else if (b.p < b.end && (*b.p == 0x7f || *b.p == 0x7e)) results.push_back(b.valtype());
+                    else if (b.p < b.end && (*b.p == 0x7f || *b.p == 0x7e || *b.p == 0x7d || *b.p == 0x7c)) results.push_back(b.valtype());
                     else {
                         const int64_t t = b.sleb(33);
                         if (t < 0 || (uint64_t)t >= types.size() || !types[(size_t)t].usable) throw std::invalid_argument("wasm: unsupported block type");
@@ -2042,16 +2306,17 @@ private:
                 else if (c == 0x1A) emit_plain(ins::drop);
                 else if (c == 0x1B) emit_plain(ins::select);
                 else if (c == 0x10) emit_call(b.uleb(), imports);
+                else if (c == 0x23 || c == 0x24) emit_global(c == 0x23 ? ins::global_get : ins::global_set, b.uleb());
                 else if (c == 0x20 || c == 0x21 || c == 0x22) emit_local(c == 0x20 ? ins::local_get : (c == 0x21 ? ins::local_set : ins::local_tee), b.uleb());
                 else if (c >= 0x28 && c <= 0x3E) {
-                    static const char *const access[] = {"i32.load", "i64.load", nullptr, nullptr, "i32.load8_s", "i32.load8_u", "i32.load16_s", "i32.load16_u", "i64.load8_s", "i64.load8_u",
-                                                         "i64.load16_s", "i64.load16_u", "i64.load32_s", "i64.load32_u", "i32.store", "i64.store", nullptr, nullptr, "i32.store8", "i32.store16",
+                    static const char *const access[] = {"i32.load", "i64.load", "f32.load", "f64.load", "i32.load8_s", "i32.load8_u", "i32.load16_s", "i32.load16_u", "i64.load8_s", "i64.load8_u",
+                                                         "i64.load16_s", "i64.load16_u", "i64.load32_s", "i64.load32_u", "i32.store", "i64.store", "f32.store", "f64.store", "i32.store8", "i32.store16",
                                                          "i64.store8", "i64.store16", "i64.store32"};
                     const char *nm = access[c - 0x28];
                     if (!nm) throw std::invalid_argument("wasm: unsupported instruction " + shown);
                     b.uleb();                                 // alignment hint
                     const uint64_t offset = b.uleb();
-                    if (!emit_access(std::string(nm).substr(4), nm[1] == '3' ? 32 : 64, offset, nm)) throw std::invalid_argument("wasm: unsupported instruction " + shown);
+                    if (!emit_access(std::string(nm).substr(4), width_of(std::string(nm, 3)), offset, nm)) throw std::invalid_argument("wasm: unsupported instruction " + shown);
                 }
                 else if (c == 0x3F || c == 0x40) { if (b.byte() != 0) throw std::invalid_argument("wasm: unknown memory"); emit_bulk(c == 0x3F ? ins::memory_size : ins::memory_grow); }
                 else if (c == 0xFC) {
@@ -2060,10 +2325,36 @@ private:
                     else if (sub == 9) emit_bulk(ins::data_drop, b.uleb());
                     else if (sub == 10) { if (b.byte() != 0 || b.byte() != 0) throw std::invalid_argument("wasm: unknown memory"); emit_bulk(ins::memory_copy); }
                     else if (sub == 11) { if (b.byte() != 0) throw std::invalid_argument("wasm: unknown memory"); emit_bulk(ins::memory_fill); }
+                    else if (sub <= 7) {                        // iNN.trunc_sat_fMM_s/u
+                        static const char *const sat[] = {"i32.trunc_sat_f32_s", "i32.trunc_sat_f32_u", "i32.trunc_sat_f64_s", "i32.trunc_sat_f64_u",
+                                                          "i64.trunc_sat_f32_s", "i64.trunc_sat_f32_u", "i64.trunc_sat_f64_s", "i64.trunc_sat_f64_u"};
+                        emit_float(sat[sub], sat[sub]);
+                    }
                     else throw std::invalid_argument("wasm: unsupported instruction 0xfc " + std::to_string(sub));
                 }
                 else if (c == 0x41) emit_const(32, (uint64_t)b.sleb(32));
                 else if (c == 0x42) emit_const(64, (uint64_t)b.sleb(64));
+                else if (c == 0x43 || c == 0x44) {              // fNN.const: the bits, little endian
+                    uint64_t bits = 0;
+                    for (int j = 0; j < (c == 0x43 ? 4 : 8); j++) bits |= (uint64_t)b.byte() << (8 * j);
+                    emit_const(c == 0x43 ? F32 : F64, bits);
+                }
+                else if ((c >= 0x5B && c <= 0x66) || (c >= 0x8B && c <= 0xA6)) {
+                    static const char *const fcmp[] = {"eq", "ne", "lt", "gt", "le", "ge"};
+                    static const char *const farith[] = {"abs", "neg", "ceil", "floor", "trunc", "nearest", "sqrt", "add", "sub", "mul", "div", "min", "max", "copysign"};
+                    const bool cmp = c <= 0x66;
+                    const int k = cmp ? c - 0x5B : c - 0x8B, per = cmp ? 6 : 14;
+                    const std::string nm = std::string(k < per ? "f32." : "f64.") + (cmp ? fcmp : farith)[k % per];
+                    emit_float(nm, nm);
+                }
+                else if ((c >= 0xA8 && c <= 0xAB) || (c >= 0xAE && c <= 0xBF)) {
+                    static const char *const conv[] = {"i32.trunc_f32_s", "i32.trunc_f32_u", "i32.trunc_f64_s", "i32.trunc_f64_u", nullptr, nullptr,
+                                                       "i64.trunc_f32_s", "i64.trunc_f32_u", "i64.trunc_f64_s", "i64.trunc_f64_u",
+                                                       "f32.convert_i32_s", "f32.convert_i32_u", "f32.convert_i64_s", "f32.convert_i64_u", "f32.demote_f64",
+                                                       "f64.convert_i32_s", "f64.convert_i32_u", "f64.convert_i64_s", "f64.convert_i64_u", "f64.promote_f32",
+                                                       "i32.reinterpret_f32", "i64.reinterpret_f64", "f32.reinterpret_i32", "f64.reinterpret_i64"};
+                    emit_float(conv[c - 0xA8], conv[c - 0xA8]);
+                }
                 else if (c >= 0x45 && c <= 0x4F) emit_op(cmp_ops[c - 0x45], 32, shown);
                 else if (c >= 0x50 && c <= 0x5A) emit_op(cmp_ops[c - 0x50], 64, shown);
                 else if (c >= 0x67 && c <= 0x78) emit_op(int_ops[c - 0x67], 32, shown);
@@ -2084,6 +2375,8 @@ private:
     }
 
     struct data_t { std::string bytes; bool active = false; uint32_t offset = 0; };
+    struct global_t { uint8_t type = 32; bool mut = false; uint64_t init = 0; };   // global_instance (runtime.hpp:181-187): i32 / i64 only (:441-455)
+    std::vector<global_t> globals_;
     std::vector<func_t> funcs_;
     size_t start_ = 0;
     uint64_t step_limit_ = 200000000;

@@ -120,7 +120,8 @@ struct tiny_module {
         std::vector<instr_ptr> body;
     };
     struct data_seg { std::vector<u8> bytes; bool active = false; u32 offset = 0; };
-    explicit tiny_module(std::vector<module_func> functions, size_t start_function, u32 mem_pages = 1, u32 mem_max = 0, const std::vector<data_seg> &datas = {}) {
+    explicit tiny_module(std::vector<module_func> functions, size_t start_function, u32 mem_pages = 1, u32 mem_max = 0, const std::vector<data_seg> &datas = {},
+                         const std::vector<std::pair<value_kind, uint64_t>> &globals = {}) {
         function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_pc32({value_kind::i32}, {value_kind::i32}),
             k_one({value_kind::i64}, {});
         inst.types = {k_pc, k_eq, k_pc32, k_one};
@@ -147,6 +148,12 @@ struct tiny_module {
                 store.datas[i].data.clear();
             }
         }
+        // globals as instantiate() creates them (include/runtime.hpp:428-456): i32 / i64, holding a native number
+        for (const auto &g : globals) {
+            if (g.first == value_kind::i32) inst.globaladdrs.push_back(store.emplace_back<global_instance>(g.first, (u32)g.second));
+            else if (g.first == value_kind::i64) inst.globaladdrs.push_back(store.emplace_back<global_instance>(g.first, (u64)g.second));
+            else throw std::runtime_error("Unexpected global value type");
+        }
         inst.exports["_start"] = (index_t)(t.size() + start_function);
     }
     explicit tiny_module(std::vector<instr_ptr> body) : tiny_module(single(std::move(body)), 0) {}
@@ -164,6 +171,13 @@ struct tiny_module {
 // stand alone.
 struct wasm_token { std::string op; uint64_t imm = 0; std::vector<std::string> types; std::vector<uint64_t> targets; };
 
+static value_kind token_kind(const std::string &t) {
+    if (t == "i32") return value_kind::i32;
+    if (t == "i64") return value_kind::i64;
+    if (t == "f32") return value_kind::f32;
+    if (t == "f64") return value_kind::f64;
+    throw std::runtime_error("unknown value type " + t);
+}
 static std::vector<value_kind> token_kinds(const std::string &list) {      // "i32,i64" or "-"
     std::vector<value_kind> out;
     if (list == "-") return out;
@@ -171,7 +185,7 @@ static std::vector<value_kind> token_kinds(const std::string &list) {      // "i
     while (b <= list.size()) {
         const size_t e = list.find(',', b);
         const std::string t = list.substr(b, e == std::string::npos ? std::string::npos : e - b);
-        out.push_back(t == "i32" ? value_kind::i32 : value_kind::i64);
+        out.push_back(token_kind(t));
         if (e == std::string::npos) break;
         b = e + 1;
     }
@@ -250,6 +264,39 @@ static std::vector<instr_ptr> assemble_until(const std::vector<wasm_token> &toks
         }
         if (t.op == "return") { flush(); body.push_back(make_instr<ret>()); continue; }
         if (t.op == "unreachable") { plain(opcode(opcode::unreachable)); continue; }
+        // floating point: what transpile_opcode emits for fNN.* and the conversions (include/transpiler.hpp:128-161,237-270,325-352,373-440)
+        static const std::map<std::string, opcode::kind> ftable = {
+            {"abs", opcode::fnn_abs}, {"neg", opcode::fnn_neg}, {"ceil", opcode::fnn_ceil}, {"floor", opcode::fnn_floor}, {"trunc", opcode::fnn_trunc},
+            {"nearest", opcode::fnn_nearest}, {"sqrt", opcode::fnn_sqrt}, {"add", opcode::fnn_add}, {"sub", opcode::fnn_sub}, {"mul", opcode::fnn_mul},
+            {"div", opcode::fnn_div}, {"min", opcode::fnn_min}, {"max", opcode::fnn_max}, {"copysign", opcode::fnn_copysign},
+            {"eq", opcode::fnn_eq}, {"ne", opcode::fnn_ne}, {"lt", opcode::fnn_lt}, {"gt", opcode::fnn_gt}, {"le", opcode::fnn_le}, {"ge", opcode::fnn_ge}};
+        static const std::map<std::string, opcode::kind> plain_conv = {
+            {"f32.demote_f64", opcode::f32_demote_f64}, {"f64.promote_f32", opcode::f64_promote_f32}, {"i32.reinterpret_f32", opcode::i32_reinterpret_f32},
+            {"i64.reinterpret_f64", opcode::i64_reinterpret_f64}, {"f32.reinterpret_i32", opcode::f32_reinterpret_i32}, {"f64.reinterpret_i64", opcode::f64_reinterpret_i64}};
+        static const std::map<std::string, opcode::kind> signed_conv = {
+            {"f32.convert_i32_s", opcode::f32_convert_i32_s}, {"f32.convert_i32_u", opcode::f32_convert_i32_u}, {"f32.convert_i64_s", opcode::f32_convert_i64_s},
+            {"f32.convert_i64_u", opcode::f32_convert_i64_u}, {"f64.convert_i32_s", opcode::f64_convert_i32_s}, {"f64.convert_i32_u", opcode::f64_convert_i32_u},
+            {"f64.convert_i64_s", opcode::f64_convert_i64_s}, {"f64.convert_i64_u", opcode::f64_convert_i64_u},
+            {"i32.trunc_f32_s", opcode::i32_trunc_f32_s}, {"i32.trunc_f32_u", opcode::i32_trunc_f32_u}, {"i32.trunc_f64_s", opcode::i32_trunc_f64_s},
+            {"i32.trunc_f64_u", opcode::i32_trunc_f64_u}, {"i64.trunc_f32_s", opcode::i64_trunc_f32_s}, {"i64.trunc_f32_u", opcode::i64_trunc_f32_u},
+            {"i64.trunc_f64_s", opcode::i64_trunc_f64_s}, {"i64.trunc_f64_u", opcode::i64_trunc_f64_u},
+            {"i32.trunc_sat_f32_s", opcode::i32_trunc_sat_f32_s}, {"i32.trunc_sat_f32_u", opcode::i32_trunc_sat_f32_u}, {"i32.trunc_sat_f64_s", opcode::i32_trunc_sat_f64_s},
+            {"i32.trunc_sat_f64_u", opcode::i32_trunc_sat_f64_u}, {"i64.trunc_sat_f32_s", opcode::i64_trunc_sat_f32_s}, {"i64.trunc_sat_f32_u", opcode::i64_trunc_sat_f32_u},
+            {"i64.trunc_sat_f64_s", opcode::i64_trunc_sat_f64_s}, {"i64.trunc_sat_f64_u", opcode::i64_trunc_sat_f64_u}};
+        if (plain_conv.count(t.op)) { plain(opcode(plain_conv.at(t.op))); continue; }
+        if (signed_conv.count(t.op)) { plain(opcode(signed_conv.at(t.op), token_kind(t.op.substr(0, 3)), t.op.back() == 's' ? sign_kind::sign : sign_kind::unsign)); continue; }
+        if (t.op.size() > 4 && (t.op.rfind("f32.", 0) == 0 || t.op.rfind("f64.", 0) == 0)) {
+            const value_kind fk = token_kind(t.op.substr(0, 3));
+            const std::string fname = t.op.substr(4);
+            if (fname == "const") plain(fk == value_kind::f32 ? opcode(opcode::fnn_const, value_kind::f32, (uint32_t)t.imm) : opcode(opcode::fnn_const, value_kind::f64, t.imm));
+            else if (fname == "load") plain(opcode(opcode::fnn_load, fk, sign_kind::unspecified, (u32)0, (u32)t.imm));
+            else if (fname == "store") plain(opcode(opcode::fnn_store, fk, sign_kind::unspecified, (u32)0, (u32)t.imm));
+            else if (ftable.count(fname)) plain(opcode(ftable.at(fname), fk));
+            else throw std::runtime_error("unknown token " + t.op);
+            continue;
+        }
+        if (t.op == "global.get") { plain(opcode(opcode::global_get, (index_t)t.imm)); continue; }
+        if (t.op == "global.set") { plain(opcode(opcode::global_set, (index_t)t.imm)); continue; }
         const bool typed = t.op.size() > 4 && (t.op.rfind("i32.", 0) == 0 || t.op.rfind("i64.", 0) == 0);
         const value_kind vk = (typed && t.op[1] == '3') ? value_kind::i32 : value_kind::i64;
         const std::string name = typed ? t.op.substr(4) : std::string();
@@ -337,8 +384,8 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
     std::string op;
     while (in >> op) {
         wasm_token tok{op};
-        if (op == "c" || op == "i32.const" || op == "i64.const" || op == "local.get" || op == "local.set" || op == "local.tee" || op == "callf" || op == "start" || op == "memory.init" || op == "data.drop" || op == "br" || op == "br_if" ||
-            ((op.rfind("i32.", 0) == 0 || op.rfind("i64.", 0) == 0) && (op.find(".load") != std::string::npos || op.find(".store") != std::string::npos))) {
+        if (op == "c" || op == "i32.const" || op == "i64.const" || op == "f32.const" || op == "f64.const" || op == "global.get" || op == "global.set" || op == "local.get" || op == "local.set" || op == "local.tee" || op == "callf" || op == "start" || op == "memory.init" || op == "data.drop" || op == "br" || op == "br_if" ||
+            ((op.rfind("i32.", 0) == 0 || op.rfind("i64.", 0) == 0 || op.rfind("f32.", 0) == 0 || op.rfind("f64.", 0) == 0) && (op.find(".load") != std::string::npos || op.find(".store") != std::string::npos))) {
             std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0);
         }
         if (op == "func") {                                   // func <params> <results> <locals>, e.g. "func i64,i32 i64 -": a new module function starts
@@ -350,6 +397,10 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
         if (op == "br_table") {                               // br_table <count> <targets ... default>
             size_t n; in >> n;
             for (size_t j = 0; j < n; j++) { uint64_t l; in >> l; tok.targets.push_back(l); }
+        }
+        if (op == "global") {                                 // global <type> <initial value>
+            std::string part; in >> part; tok.types.push_back(part);
+            std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0);
         }
         if (op == "memory") {                                 // memory <pages> <max pages or 0>
             for (int j = 0; j < 2; j++) { std::string part; in >> part; tok.types.push_back(part); }
@@ -366,21 +417,10 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
 // a token stream with "func" headers is a module of several functions ("start K" names _start); without, one function.
 // "memory" and "data" directives describe the module's memory and data segments
 static tiny_module build_module(const std::vector<wasm_token> &toks) {
-    const auto kinds = [](const std::string &list) {
-        std::vector<value_kind> out;
-        if (list == "-") return out;
-        size_t b = 0;
-        while (b <= list.size()) {
-            const size_t e = list.find(',', b);
-            const std::string t = list.substr(b, e == std::string::npos ? std::string::npos : e - b);
-            out.push_back(t == "i32" ? value_kind::i32 : value_kind::i64);
-            if (e == std::string::npos) break;
-            b = e + 1;
-        }
-        return out;
-    };
+    const auto kinds = [](const std::string &list) { return token_kinds(list); };
     std::vector<tiny_module::module_func> functions;
     std::vector<tiny_module::data_seg> datas;
+    std::vector<std::pair<value_kind, uint64_t>> globals;
     std::vector<wasm_token> body;
     size_t start = 0;
     u32 pages = 1, max_pages = 0;
@@ -394,6 +434,7 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
             functions.emplace_back();
             functions.back().params = kinds(t.types[0]); functions.back().results = kinds(t.types[1]); functions.back().locals = kinds(t.types[2]);
         } else if (t.op == "start") start = (size_t)t.imm;
+        else if (t.op == "global") globals.emplace_back(token_kind(t.types[0]), t.imm);
         else if (t.op == "memory") { pages = (u32)std::stoul(t.types[0]); max_pages = (u32)std::stoul(t.types[1]); }
         else if (t.op == "data") {
             tiny_module::data_seg d;
@@ -406,7 +447,7 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
         else body.push_back(t);
     }
     close();
-    return tiny_module(std::move(functions), start, pages, max_pages, datas);
+    return tiny_module(std::move(functions), start, pages, max_pages, datas, globals);
 }
 
 template <typename Ctx>

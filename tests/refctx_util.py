@@ -159,9 +159,49 @@ def _lit(s):
     return int(s.replace("_", ""), 0) % (1 << 64)
 
 
-def _walk(fn, imports, ids, visit, data_ids=None):
-    """post-order walk of a function's folded body: visit(kind, name, immediate)"""
+def float_bits(lit, single):
+    """bit pattern of an fNN.const literal: decimal / hexadecimal floating point, inf, nan, nan:0x<payload>"""
+    import struct
+    t = lit.replace("_", "")
+    neg = t.startswith("-")
+    t = t.lstrip("+-")
+    sign = (1 << (31 if single else 63)) if neg else 0
+    exp_all = 0x7F800000 if single else 0x7FF0000000000000
+    if t == "inf":
+        return sign | exp_all
+    if t == "nan":
+        return sign | exp_all | (1 << (22 if single else 51))
+    if t.startswith("nan:0x"):
+        return sign | exp_all | int(t[6:], 16)
+    v = float.fromhex(t) if t[:2].lower() == "0x" else float(t)
+    if single:
+        try:
+            raw = struct.pack("<f", v)
+        except OverflowError:
+            raw = struct.pack("<f", float("inf"))
+        return sign | struct.unpack("<I", raw)[0]
+    return sign | struct.unpack("<Q", struct.pack("<d", v))[0]
+
+
+def wat_globals(text):
+    """[(id or None, type, mutable, initial value)] of a module"""
+    out = []
+    for f in _sexpr(text)[1:]:
+        if f[0] != "global":
+            continue
+        rest = f[1:]
+        gid = rest.pop(0) if isinstance(rest[0], str) and rest[0].startswith("$") else None
+        ty, init = rest
+        mut = isinstance(ty, list)
+        ty = ty[1] if mut else ty
+        out.append((gid, ty, mut, _lit(init[1]) % (1 << int(ty[1:]))))
+    return out
+
+
+def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None):
+    """post-order walk of a function's body (folded forms, plain instructions, or both mixed): visit(kind, name, immediate)"""
     data_ids = data_ids or {}
+    global_ids = global_ids or {}
     def local(x):
         return fn["names"][x] if x in fn["names"] else int(x)
 
@@ -180,17 +220,50 @@ def _walk(fn, imports, ids, visit, data_ids=None):
             (params if part[0] == "param" else results).extend(part[1:])
         return name, params, results
 
+    def is_label(x):
+        return isinstance(x, str) and (x.startswith("$") or x[0].isdigit())
+
+    def emit_seq(items):
+        """a sequence in which folded forms and plain instructions (immediates after the instruction) may be mixed"""
+        i = 0
+        while i < len(items):
+            e = items[i]; i += 1
+            if isinstance(e, list):
+                emit(e)
+            elif e in ("block", "loop", "if"):
+                rest = []
+                while i < len(items) and ((isinstance(items[i], str) and items[i].startswith("$") and not rest) or (isinstance(items[i], list) and items[i][0] in ("param", "result"))):
+                    rest.append(items[i]); i += 1
+                name, params, results = blocktype(rest)
+                visit("block", e, (params, results))
+                labels.append(name)
+            elif e in ("else", "end"):
+                if i < len(items) and isinstance(items[i], str) and items[i].startswith("$"):
+                    i += 1
+                if e == "end":
+                    labels.pop()
+                visit("op", e, None)
+            else:
+                n = i
+                if e == "br_table":
+                    while n < len(items) and is_label(items[n]):
+                        n += 1
+                elif e[3:] in (".const",) or e in ("local.get", "local.set", "local.tee", "global.get", "global.set", "call", "br", "br_if", "memory.init", "data.drop"):
+                    n += 1
+                else:
+                    while n < len(items) and isinstance(items[n], str) and items[n].partition("=")[0] in ("offset", "align"):
+                        n += 1
+                emit([e] + items[i:n])
+                i = n
+
     def emit(e):
-        if isinstance(e, str):
-            raise ValueError("plain instructions are not handled by the test helpers: " + e)
         h = e[0]
         if h in ("block", "loop"):
             rest = list(e[1:])
             name, params, results = blocktype(rest)
             visit("block", h, (params, results))
             labels.append(name)
-            for a in rest:
-                emit(a)
+            emit_seq(rest)
             labels.pop()
             visit("op", "end", None)
         elif h == "if":
@@ -202,12 +275,10 @@ def _walk(fn, imports, ids, visit, data_ids=None):
                     emit(a)
             visit("block", "if", (params, results))
             labels.append(name)
-            for a in arms[0][1:]:
-                emit(a)
+            emit_seq(arms[0][1:])
             if len(arms) > 1:
                 visit("op", "else", None)
-                for a in arms[1][1:]:
-                    emit(a)
+                emit_seq(arms[1][1:])
             labels.pop()
             visit("op", "end", None)
         elif h in ("br", "br_if"):
@@ -226,6 +297,12 @@ def _walk(fn, imports, ids, visit, data_ids=None):
             visit("op", h, None)
         elif h in ("i64.const", "i32.const"):
             visit("const", h, _lit(e[1]) % (1 << int(h[1:3])))
+        elif h in ("f64.const", "f32.const"):
+            visit("fconst", h, (float_bits(e[1], h == "f32.const"), e[1]))
+        elif h in ("global.get", "global.set"):
+            for a in e[2:]:
+                emit(a)
+            visit("global", h, global_ids[e[1]] if e[1] in global_ids else int(e[1]))
         elif h == "call":
             for a in e[2:]:
                 emit(a)
@@ -237,7 +314,7 @@ def _walk(fn, imports, ids, visit, data_ids=None):
             for a in e[2:]:
                 emit(a)
             visit("local", h, local(e[1]))
-        elif h[:4] in ("i32.", "i64.") and (h[4:8] == "load" or h[4:9] == "store"):
+        elif h[:4] in ("i32.", "i64.", "f32.", "f64.") and (h[4:8] == "load" or h[4:9] == "store"):
             offset, rest = 0, e[1:]
             while rest and isinstance(rest[0], str):
                 key, _, val = rest.pop(0).partition("=")
@@ -254,14 +331,13 @@ def _walk(fn, imports, ids, visit, data_ids=None):
             for a in e[1:]:
                 emit(a)
             visit("op", h, None)
-        elif h[:4] in ("i32.", "i64.") or h in ("drop", "nop", "select"):
+        elif h[:4] in ("i32.", "i64.", "f32.", "f64.") or h in ("drop", "nop", "select"):
             for a in e[1:]:
                 emit(a)
             visit("op", h, None)
         else:
             raise ValueError("unsupported form " + str(h))
-    for e in fn["body"]:
-        emit(e)
+    emit_seq(fn["body"])
 
 
 def wat_to_tokens(text):
@@ -271,7 +347,9 @@ def wat_to_tokens(text):
     imports, funcs, ids, start = wat_module(text)
     memory, datas = wat_memory(text)
     data_ids = {d[0]: k for k, d in enumerate(datas) if d[0]}
-    out = []
+    globals_ = wat_globals(text)
+    global_ids = {g[0]: k for k, g in enumerate(globals_) if g[0]}
+    out = ["global %s %d" % (ty, init) for _, ty, _, init in globals_]
     if memory:
         out.append("memory %d %d" % memory)
     for _, active, offset, data in datas:
@@ -279,6 +357,10 @@ def wat_to_tokens(text):
 
     def visit(kind, name, imm):
         if kind == "const":
+            out.append("%s %d" % (name, imm))
+        elif kind == "fconst":
+            out.append("%s %d" % (name, imm[0]))
+        elif kind == "global":
             out.append("%s %d" % (name, imm))
         elif kind == "host":
             out.append("call:" + name)
@@ -296,7 +378,7 @@ def wat_to_tokens(text):
     for fn in funcs:
         if structured:
             out.append("func %s %s %s" % tuple(",".join(fn[key]) or "-" for key in ("params", "results", "locals")))
-        _walk(fn, imports, ids, visit, data_ids)
+        _walk(fn, imports, ids, visit, data_ids, global_ids)
     if structured:
         out.append("start %d" % start)
     return out
@@ -495,15 +577,36 @@ _OTHER_OPS = {"i32.wrap_i64": 0xA7, "i64.extend_i32_s": 0xAC, "i64.extend_i32_u"
               "i64.extend8_s": 0xC2, "i64.extend16_s": 0xC3, "i64.extend32_s": 0xC4}
 
 
+_FLOAT_ARITH = ["abs", "neg", "ceil", "floor", "trunc", "nearest", "sqrt", "add", "sub", "mul", "div", "min", "max", "copysign"]
+_FLOAT_CMP = ["eq", "ne", "lt", "gt", "le", "ge"]
+_FLOAT_OPS = {}
+for _k, _ty in enumerate(("f32", "f64")):
+    for _j, _op in enumerate(_FLOAT_CMP):
+        _FLOAT_OPS["%s.%s" % (_ty, _op)] = bytes([0x5B + 6 * _k + _j])
+    for _j, _op in enumerate(_FLOAT_ARITH):
+        _FLOAT_OPS["%s.%s" % (_ty, _op)] = bytes([0x8B + 14 * _k + _j])
+for _j, _nm in enumerate(["i32.trunc_f32_s", "i32.trunc_f32_u", "i32.trunc_f64_s", "i32.trunc_f64_u", None, None, "i64.trunc_f32_s", "i64.trunc_f32_u", "i64.trunc_f64_s",
+                          "i64.trunc_f64_u", "f32.convert_i32_s", "f32.convert_i32_u", "f32.convert_i64_s", "f32.convert_i64_u", "f32.demote_f64", "f64.convert_i32_s",
+                          "f64.convert_i32_u", "f64.convert_i64_s", "f64.convert_i64_u", "f64.promote_f32", "i32.reinterpret_f32", "i64.reinterpret_f64",
+                          "f32.reinterpret_i32", "f64.reinterpret_i64"]):
+    if _nm:
+        _FLOAT_OPS[_nm] = bytes([0xA8 + _j])
+for _j, _nm in enumerate(["i32.trunc_sat_f32_s", "i32.trunc_sat_f32_u", "i32.trunc_sat_f64_s", "i32.trunc_sat_f64_u", "i64.trunc_sat_f32_s", "i64.trunc_sat_f32_u",
+                          "i64.trunc_sat_f64_s", "i64.trunc_sat_f64_u"]):
+    _FLOAT_OPS[_nm] = bytes([0xFC, _j])
+
+
 def wat_to_wasm(text, custom_section=True):
     """binary module for a program of the subset: type, import, function, export and code sections (+ a custom section)"""
     mod = _sexpr(text)
     imports, funcs, ids, start = wat_module(text)
     memory, datas = wat_memory(text)
     data_ids = {d[0]: k for k, d in enumerate(datas) if d[0]}
-    access = ["i32.load", "i64.load", None, None, "i32.load8_s", "i32.load8_u", "i32.load16_s", "i32.load16_u", "i64.load8_s", "i64.load8_u", "i64.load16_s",
-              "i64.load16_u", "i64.load32_s", "i64.load32_u", "i32.store", "i64.store", None, None, "i32.store8", "i32.store16", "i64.store8", "i64.store16", "i64.store32"]
-    vt = {"i32": 0x7f, "i64": 0x7e}
+    globals_ = wat_globals(text)
+    global_ids = {g[0]: k for k, g in enumerate(globals_) if g[0]}
+    access = ["i32.load", "i64.load", "f32.load", "f64.load", "i32.load8_s", "i32.load8_u", "i32.load16_s", "i32.load16_u", "i64.load8_s", "i64.load8_u", "i64.load16_s",
+              "i64.load16_u", "i64.load32_s", "i64.load32_u", "i32.store", "i64.store", "f32.store", "f64.store", "i32.store8", "i32.store16", "i64.store8", "i64.store16", "i64.store32"]
+    vt = {"i32": 0x7f, "i64": 0x7e, "f32": 0x7d, "f64": 0x7c}
     types, import_list = [], []
 
     def typeidx(params, results):
@@ -528,6 +631,12 @@ def wat_to_wasm(text, custom_section=True):
             if kind == "const":
                 w = int(nm[1:3])
                 code.extend(bytes([0x41 if w == 32 else 0x42]) + _sleb(imm - (1 << w) if imm >> (w - 1) else imm))
+            elif kind == "fconst":
+                code.extend(b"\x43" + imm[0].to_bytes(4, "little") if nm == "f32.const" else b"\x44" + imm[0].to_bytes(8, "little"))
+            elif kind == "global":
+                code.extend(bytes([0x23 if nm == "global.get" else 0x24]) + _uleb(imm))
+            elif nm in _FLOAT_OPS:
+                code.extend(_FLOAT_OPS[nm])
             elif kind == "host":
                 code.extend(b"\x10" + _uleb(imm))
             elif kind == "callf":
@@ -559,7 +668,7 @@ def wat_to_wasm(text, custom_section=True):
             else:
                 w, op = nm[:3], nm[4:]
                 code.append((0x45 if w == "i32" else 0x50) + _CMP_OPS.index(op) if op in _CMP_OPS else (0x67 if w == "i32" else 0x79) + _INT_OPS.index(op))
-        _walk(fn, imports, ids, visit, data_ids)
+        _walk(fn, imports, ids, visit, data_ids, global_ids)
         code.append(0x0B)
         body = vec([_uleb(1) + bytes([vt[t]]) for t in fn["locals"]]) + bytes(code)
         bodies.append(_uleb(len(body)) + body)
@@ -569,6 +678,9 @@ def wat_to_wasm(text, custom_section=True):
     out += section(3, vec([_uleb(t) for t in func_types]))
     if memory:
         out += section(5, vec([(b"\x01" + _uleb(memory[0]) + _uleb(memory[1])) if memory[1] else (b"\x00" + _uleb(memory[0]))]))
+    if globals_:
+        out += section(6, vec([bytes([vt[ty], int(mut), 0x41 if ty == "i32" else 0x42]) + _sleb(init - (1 << int(ty[1:])) if init >> (int(ty[1:]) - 1) else init) + b"\x0b"
+                               for _, ty, mut, init in globals_]))
     out += section(7, vec([name("_start") + b"\x00" + _uleb(len(import_list) + start)]))
     if datas:
         out += section(12, _uleb(len(datas)))
@@ -587,6 +699,10 @@ def wat_to_plain(text):
     memory, datas = wat_memory(text)
     data_ids = {d[0]: k for k, d in enumerate(datas) if d[0]}
     out = ["(module"] + ['(import "env" "%s" (func %s))' % (nm, fid) for fid, (nm, _) in imports.items()]
+    globals_ = wat_globals(text)
+    global_ids = {g[0]: k for k, g in enumerate(globals_) if g[0]}
+    for _, ty, mut, init in globals_:
+        out.append("(global %s (%s.const %d))" % ("(mut %s)" % ty if mut else ty, ty, init))
     if memory:
         out.append("(memory %d%s)" % (memory[0], " %d" % memory[1] if memory[1] else ""))
     for _, active, off, data in datas:
@@ -598,6 +714,10 @@ def wat_to_plain(text):
 
         def visit(kind, nm, imm):
             if kind == "const":
+                body.append("%s %d" % (nm, imm))
+            elif kind == "fconst":
+                body.append("%s %s" % (nm, imm[1]))
+            elif kind == "global":
                 body.append("%s %d" % (nm, imm))
             elif kind == "host":
                 body.append("call %s" % by_index.get(imm))
@@ -613,7 +733,7 @@ def wat_to_plain(text):
                 body.append("%s %s" % (nm, " ".join(map(str, imm))))
             else:
                 body.append(nm)
-        _walk(fn, imports, ids, visit, data_ids)
+        _walk(fn, imports, ids, visit, data_ids, global_ids)
         out.append(head + "\n" + "\n".join(body) + "\n)")
     out.append('(export "_start" (func %s)))' % (funcs[start]["id"] or "$f%d" % start))
     return "\n".join(out) + "\n"
@@ -833,3 +953,85 @@ def rand_cf_program(rng, w, nstmt=5, depth=2):
     head = WAT_HEAD_BOTH[:WAT_HEAD_BOTH.index("(func $t")]
     return (head + "\n".join(h[0] for h in helpers) + "\n" + early + "\n(func $t (local $x %s) (local $y %s) (local $z %s) (local $i i32)\n" % (W, W, W)
             + "\n".join(body) + "\n" + WAT_TAIL)
+
+
+# ---- floating point and globals: numbers only in the reference; a result is observed by committing it
+_F_SPECIAL = ["0.0", "-0.0", "inf", "-inf", "nan", "-nan", "nan:0x1", "1.5", "-2.25", "0x1.8p3", "1e30", "-1e-30", "3.0", "0.1", "16777217.0",
+              "4294967296.0", "-2147483649.0", "9223372036854775808.0", "123456789.125", "0x1p-126", "0x1p-1022", "2.5", "3.5", "-0.5"]
+
+
+def rand_float_expr(rng, depth, t, env):
+    """text of a random expression of type t ('f32' / 'f64'); env: the locals per type"""
+    r = rng.random()
+    if depth == 0 or r < 0.2:
+        r2 = rng.random()
+        if r2 < 0.45:
+            lit = rng.choice(_F_SPECIAL)
+            if t == "f32" and lit == "0x1p-1022":
+                lit = "0x1p-149"
+            return "(%s.const %s)" % (t, lit)
+        if r2 < 0.65:
+            bits = rng.getrandbits(32 if t == "f32" else 64)
+            return "(%s.reinterpret_i%s (i%s.const %d))" % (t, t[1:], t[1:], bits)
+        if r2 < 0.8:
+            return "(local.get $%s)" % rng.choice(env[t])
+        if r2 < 0.9:
+            src = rng.choice(["i32", "i64"])
+            gl = {"i32": "$h", "i64": "$g"}[src]
+            operand = "(global.get %s)" % gl if rng.random() < 0.4 else "(%s.const %d)" % (src, rng.choice([0, 1, -1, 7, -1234, 1 << 31, (1 << 53) + 1, rng.getrandbits(int(src[1:]))]) % (1 << int(src[1:])))
+            return "(%s.convert_%s_%s %s)" % (t, src, rng.choice("su"), operand)
+        return "(%s.load offset=%d (i32.const %d))" % (t, rng.choice([0, 4, 8]), rng.choice([64, 72, 80]))
+    if r < 0.4:
+        op = rng.choice(["abs", "neg", "ceil", "floor", "trunc", "nearest", "sqrt"])
+        return "(%s.%s %s)" % (t, op, rand_float_expr(rng, depth - 1, t, env))
+    if r < 0.8:
+        op = rng.choice(["add", "sub", "mul", "div", "min", "max", "copysign"])
+        return "(%s.%s %s %s)" % (t, op, rand_float_expr(rng, depth - 1, t, env), rand_float_expr(rng, depth - 1, t, env))
+    if r < 0.88:
+        other = "f64" if t == "f32" else "f32"
+        return "(%s.%s %s)" % (t, "demote_f64" if t == "f32" else "promote_f32", rand_float_expr(rng, depth - 1, other, env))
+    if r < 0.94:
+        return "(local.tee $%s %s)" % (rng.choice(env[t]), rand_float_expr(rng, depth - 1, t, env))
+    return "(select %s %s (i32.const %d))" % (rand_float_expr(rng, depth - 1, t, env), rand_float_expr(rng, depth - 1, t, env), rng.randrange(2))
+
+
+def rand_float_program(rng, nstmt=10, depth=3):
+    """floating-point arithmetic, conversions, loads / stores, locals, select and globals on numbers; every statement ends in
+    an integer that is committed (iNN_private_const) or kept in a global / local that is committed later, so the rows the
+    reference emits carry the bits of every result"""
+    env = {"f32": ["a", "b"], "f64": ["c", "d"]}
+    F = lambda t, d=depth: rand_float_expr(rng, rng.randrange(1, d + 1), t, env)
+    body = []
+    for _ in range(nstmt):
+        r = rng.random()
+        t = rng.choice(["f32", "f64"])
+        w = t[1:]
+        if r < 0.3:
+            body.append("(drop (call $i%s_private_const (i%s.reinterpret_%s %s)))" % (w, w, t, F(t)))
+        elif r < 0.5:
+            iw = rng.choice(["32", "64"])
+            body.append("(drop (call $i%s_private_const (i%s.trunc_sat_%s_%s %s)))" % (iw, iw, t, rng.choice("su"), F(t)))
+        elif r < 0.62:
+            body.append("(drop (call $i32_private_const (%s.%s %s %s)))" % (t, rng.choice(["eq", "ne", "lt", "gt", "le", "ge"]), F(t, 2), F(t, 2)))
+        elif r < 0.7:                                            # a trapping truncation, on an operand that is in range by construction
+            iw, sg = rng.choice(["32", "64"]), rng.choice("su")
+            small = "(%s.div (%s.convert_i32_%s (i32.const %d)) (%s.const %s))" % (t, t, sg, rng.getrandbits(30), t, rng.choice(["1.0", "3.0", "0.7", "1e3"]))
+            body.append("(drop (call $i%s_private_const (i%s.trunc_%s_%s %s)))" % (iw, iw, t, sg, small))
+        elif r < 0.8:
+            body.append("(local.set $%s %s)" % (rng.choice(env[t]), F(t)))
+        elif r < 0.9:
+            body.append("(%s.store offset=%d (i32.const %d) %s)" % (t, rng.choice([0, 4, 8]), rng.choice([64, 72, 80]), F(t)))
+        elif r < 0.95:
+            body.append("(global.set $g (i64.trunc_sat_%s_%s %s))" % (t, rng.choice("su"), F(t)))
+        else:
+            body.append("(global.set $h (i32.add (global.get $h) (i32.trunc_sat_%s_%s %s)))" % (t, rng.choice("su"), F(t)))
+    body.append("(drop (call $i64_private_const (i64.add (global.get $g) (global.get $k))))")
+    body.append("(drop (call $i32_private_const (global.get $h)))")
+    body.append("(drop (call $i64_private_const (i64.load (i32.const 64))))")
+    body.append("(drop (call $i64_private_const (i64.load (i32.const 80))))")
+    for t in ("f32", "f64"):
+        for name in env[t]:
+            body.append("(drop (call $i%s_private_const (i%s.reinterpret_%s (local.get $%s))))" % (t[1:], t[1:], t, name))
+    head = WAT_HEAD_BOTH[:WAT_HEAD_BOTH.index("(func $t")]
+    return (head + "(global $g (mut i64) (i64.const 5))\n(global $h (mut i32) (i32.const -7))\n(global $k i64 (i64.const 0x123456789))\n(memory 1)\n"
+            "(func $t (local $a f32) (local $b f32) (local $c f64) (local $d f64)\n" + "\n".join(body) + "\n" + WAT_TAIL)

@@ -335,7 +335,8 @@ def test_wat_emitter_on_the_repo_fixture(pr, oracle):
 def test_wat_emitter_rejects_what_it_does_not_support(pr):
     for text, why in (("(module (func $f) (export \"_start\" (func $f)) (table 1 funcref))", "module field"),
                       ("(module (import \"wasi\" \"x\" (func $x)) (func $f) (export \"_start\" (func $f)))", "env host module"),
-                      ("(module (func $f (drop (f64.add (f64.const 1) (f64.const 2)))) (export \"_start\" (func $f)))", "unsupported instruction"),
+                      ("(module (func $f (drop (f64.fma (f64.const 1) (f64.const 2)))) (export \"_start\" (func $f)))", "unsupported instruction"),
+                      ("(module (func $f (drop (ref.null func))) (export \"_start\" (func $f)))", "unsupported instruction"),
                       ("(module (func $f (drop (i64.load (i32.const 0)))) (export \"_start\" (func $f)))", "without a memory"),
                       ("(module (func $f)", "unbalanced"),
                       ("(module (func $f))", "_start")):
@@ -452,12 +453,12 @@ def test_wasm_binary_front_end_rejects_what_it_does_not_support(pr):
                       (b"\0asm\x01\0\0\0", "_start")):
         with pytest.raises(pr.ProverError, match=why):
             pr.wat_emit(data, 64)
-    # an opcode outside the subset inside _start (f32.const = 0x43)
+    # an opcode outside the subset inside _start (table.get = 0x25)
     text = '(module (import "env" "assert_equal" (func $e (param i32 i32))) (func $f (call $e (i32.const 1) (i32.const 1))) (export "_start" (func $f)))'
     wasm = bytearray(U.wat_to_wasm(text, custom_section=False))
     at = wasm.rindex(b"\x41\x01\x41\x01")
-    wasm[at] = 0x43
-    with pytest.raises(pr.ProverError, match="unsupported instruction 0x43"):
+    wasm[at] = 0x25
+    with pytest.raises(pr.ProverError, match="unsupported instruction 0x25"):
         pr.wat_emit(bytes(wasm), 64)
 
 
@@ -503,19 +504,21 @@ def test_front_ends_survive_mutated_inputs_under_sanitizers(tmp_path):
     to the end or are rejected with an error -- no out-of-bounds access, no undefined arithmetic, no leak"""
     import refctx_util as U
     exe = str(tmp_path / "fuzz_wat")
-    res = subprocess.run(["g++", "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-o", exe,
+    res = subprocess.run(["g++", "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined,float-cast-overflow", "-fno-sanitize-recover=all", "-o", exe,
                           os.path.join(ROOT, "tests", "cpp", "fuzz_wat.cpp"), "-lcrypto"], capture_output=True, text=True)
     if res.returncode != 0 and "sanitize" in res.stderr:
         pytest.skip("sanitizer runtime not available")
     assert res.returncode == 0, res.stderr[-2000:]
     seeds = {"arith": open(U.WAT_TEXT["arith32"]).read(),
              "struct": U.rand_struct_program(random.Random(1), 64, nstmt=4, depth=2),      # locals, select, module functions
-             "memory": U.rand_memory_program(random.Random(2), nstmt=12)}                  # loads, stores, fill / copy / init, data
+             "memory": U.rand_memory_program(random.Random(2), nstmt=12),                  # loads, stores, fill / copy / init, data
+             "control": U.rand_cf_program(random.Random(3), 64, nstmt=4, depth=1),         # blocks, loops, branches, returns
+             "float": U.rand_float_program(random.Random(4), nstmt=12)}                    # floating point, conversions, globals
     for name, text in seeds.items():
         (tmp_path / (name + ".wat")).write_text(text)
         (tmp_path / (name + ".wasm")).write_bytes(U.wat_to_wasm(text))
         for seed in (name + ".wat", name + ".wasm"):
-            res = subprocess.run([exe, str(tmp_path / seed), "1500"], capture_output=True, text=True, timeout=600)
+            res = subprocess.run([exe, str(tmp_path / seed), "1200"], capture_output=True, text=True, timeout=600)
             assert res.returncode == 0 and "accepted" in res.stdout, (res.stdout + res.stderr)[-3000:]
 
 
@@ -539,7 +542,7 @@ def test_front_end_rejects_malformed_functions(pr):
                       ("(func $t (drop (local.get 3)))", "unknown local"),
                       ("(func $t (param i64))", "_start with parameters"),
                       ("(func $f (param i64) (result i64) (i64.const 1) (i64.const 2)) (func $t (drop (call $f (i64.const 1))))", "leaves 2 values"),
-                      ("(func $f (result i32) (i64.const 1)) (func $t (drop (call $f)))", "wrong width"),
+                      ("(func $f (result i32) (i64.const 1)) (func $t (drop (call $f)))", "wrong type"),
                       ("(func $t (drop (call $nowhere)))", "unknown function"),
                       ("(func $t (call $t))", "call depth"),
                       ("(func $t (drop (select (i64.const 1) (i32.const 2) (i32.const 1))))", "type mismatch: select")):
@@ -608,3 +611,42 @@ def test_control_flow_validation(pr):
     # code after a branch is type-checked leniently (its operands may come from nowhere) and never runs
     pr.wat_emit(head + "(func $t (block (br 0) (drop (i64.add))))" + tail, 64)
     pr.wat_emit(head + "(func $f (result i64) (return (call $pc (i64.const 1))) (i64.mul)) (func $t (drop (call $f)))" + tail, 64)
+
+
+def test_floating_point_and_globals_front_end(pr):
+    """floating point (numbers only, as in the reference: interpreter_impl.hpp:1314-1853) and globals (native numbers,
+    :1902-1924): results are observed through committed integers; what the reference cannot do is reported, not computed"""
+    import refctx_util as U
+    head = ('(module (import "env" "i32_private_const" (func $p32 (param i32) (result i32)))\n(import "env" "i64_private_const" (func $p64 (param i64) (result i64)))\n'
+            '(import "env" "assert_equal" (func $eq (param i64 i64)))\n(global $g (mut i64) (i64.const -3))\n(global $c i32 (i32.const 9))\n(memory 1)\n(func $t (local $x f64)\n')
+    tail = ')\n(export "_start" (func $t)))\n'
+    body = ('(call $eq (call $p64 (i64.reinterpret_f64 (f64.mul (f64.const 1.5) (f64.const -4)))) (i64.const 0xC018000000000000))\n'
+            '(call $eq (call $p32 (i32.reinterpret_f32 (f32.max (f32.const -0.0) (f32.const 0.0)))) (i32.const 0))\n'                 # the second operand wins a tie
+            '(call $eq (call $p32 (i32.reinterpret_f32 (f32.max (f32.const 0.0) (f32.const -0.0)))) (i32.const 0x80000000))\n'
+            '(call $eq (call $p32 (i32.reinterpret_f32 (f32.min (f32.const nan:0x1) (f32.const 1)))) (i32.const 0x7fc00000))\n'
+            '(call $eq (call $p32 (i32.trunc_sat_f64_s (f64.const -1e300))) (i32.const 0x80000000))\n'
+            '(call $eq (call $p64 (i64.trunc_f32_u (f32.const 0x1p63))) (i64.const 0x8000000000000000))\n'
+            '(call $eq (call $p32 (i32.reinterpret_f32 (f32.demote_f64 (f64.const 16777217)))) (i32.const 0x4b800000))\n'
+            '(call $eq (call $p64 (i64.reinterpret_f64 (f64.nearest (f64.const 2.5)))) (i64.const 0x4000000000000000))\n'
+            '(f64.store (i32.const 8) (f64.sqrt (f64.const 2)))\n(local.set $x (f64.load (i32.const 8)))\n'
+            '(call $eq (call $p64 (i64.load (i32.const 8))) (i64.reinterpret_f64 (local.get $x)))\n'
+            '(global.set $g (i64.add (global.get $g) (i64.extend_i32_u (global.get $c))))\n(call $eq (call $p64 (global.get $g)) (i64.const 6))\n')
+    for spelling in (head + body + tail, U.wat_to_wasm(head + body + tail), U.wat_to_plain(head + body + tail)):
+        _, _, _, _, st = pr.wat_emit(spelling, 64)
+        assert st["violated_constraints"] == 0 and st["asserts"] == 10 and st["private_consts"] == 10
+    for bad, why in (("(drop (i32.trunc_f32_s (f32.const 3e9)))", "integer overflow"),
+                     ("(drop (i64.trunc_f64_u (f64.const -1)))", "integer overflow"),
+                     ("(drop (i32.trunc_f64_u (f64.const nan)))", "integer overflow"),
+                     ("(call $eq (f64.const 1) (f64.const 1))", "floating-point value where a witness is needed"),
+                     ("(drop (f32.convert_i32_s (call $p32 (i32.const 1))))", "concrete operands"),
+                     ("(global.set $g (call $p64 (i64.const 1)))", "global.set takes concrete operands"),
+                     ("(global.set $c (i32.const 1))", "immutable global"),
+                     ("(drop (global.get 7))", "unknown global"),
+                     ("(drop (f32.add (f32.const 1) (f64.const 1)))", "type mismatch: f32.add applied to an f64"),
+                     ("(drop (f64.const 1.0.0))", "bad floating-point literal"),
+                     ("(i32.store (i32.const 0) (call $p32 (i32.const 5)))\n(drop (f32.load (i32.const 0)))", "floating-point value where a witness is needed"),
+                     ("(drop (f32.load8_u (i32.const 0)))", "unsupported instruction")):
+        with pytest.raises(pr.ProverError, match=why):
+            pr.wat_emit(head + bad + tail, 64)
+    with pytest.raises(pr.ProverError, match="only i32 and i64 globals"):
+        pr.wat_emit('(module (global $f f32 (f32.const 1)) (func $t) (export "_start" (func $t)))', 64)

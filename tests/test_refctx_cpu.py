@@ -440,6 +440,43 @@ def test_wat_emitter_against_the_reference_interpreter_on_control_flow_programs(
     _emitter_equals_reference_rows(pr, U.wat_to_wasm(text), st)
 
 
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("seed", range(10))
+def test_wat_emitter_against_the_reference_interpreter_on_floating_point_and_globals(oracle, pr, seed):
+    """differential: random programs of f32 / f64 arithmetic (special values, NaN payloads, signed zeros, subnormals),
+    conversions in every direction, saturating and trapping truncations, float loads / stores / locals / select, and
+    mutable globals -- numbers only in the reference (interpreter_impl.hpp:1314-1853,1902-1924) -- whose results are all
+    committed as integers, so the reference's rows carry every bit of them (tests/refctx_util.py: rand_float_program)"""
+    import random
+    rng = random.Random(4400 + seed)
+    text = U.rand_float_program(rng, nstmt=rng.randrange(4, 14))
+    raw = U.run_reference_on_wat(text, 256, seed_byte=seed + 1)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    for spelling in (text, U.wat_to_wasm(text), U.wat_to_plain(text)):
+        _emitter_equals_reference_rows(pr, spelling, st)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "tests")) or not os.path.exists(U.REF_BIN_CPU), reason="needs the reference tree and oracle/_ref/refctx_cpu")
+@pytest.mark.parametrize("name", ["f32", "f64"])
+def test_wat_emitter_on_the_reference_floating_point_programs(oracle, pr, name):
+    """tests/f32.wat and tests/f64.wat, read where they lie (plain instructions in their helper functions, folded forms in
+    _start): programs that check themselves -- every result is compared with its expected value and `unreachable` ends the
+    run otherwise.  They commit no witness: the reference's interpreter runs them to the end with no row, and so does the
+    emitter, from the text, the binary and the plain spelling"""
+    text = open(os.path.join(REFERENCE, "tests", name + ".wat")).read()
+    raw = U.run_reference_on_wat(text, 256)
+    assert raw["kinds"] == [] and raw["valid"] == [1, 1, 1]
+    for spelling in (text, U.wat_to_wasm(text), U.wat_to_plain(text)):
+        kinds, vals, _, _, stats = pr.wat_emit(spelling, 64, bytes(32))
+        assert len(kinds) == 0 and len(vals) == 0 and stats["violated_constraints"] == 0
+    # and a wrong expectation is noticed: the program runs into its `unreachable`
+    broken = text.replace("(f%s.const 6.5)" % name[1:], "(f%s.const 6.75)" % name[1:], 1)
+    assert broken != text
+    with pytest.raises(pr.ProverError, match="unreachable executed"):
+        pr.wat_emit(broken, 64, bytes(32))
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
