@@ -146,6 +146,27 @@ int lgrp_wat_emit(const char *wat, size_t len, uint32_t l, const uint8_t *stage1
 int lgrp_prove_wat(lgr_ctx *ctx, const char *wat, size_t len, const uint8_t encoding_seed[32], int64_t generated_at_seconds,
                    lgrp_proof **out, lgrp_wat_stats *stats);
 
+/* The guest's arguments, as the reference's prover builds them from its JSON configuration (src/webgpu_prover.cpp:69,110-157):
+ * args[0] is the program name ("Ligero" with its NUL there), {"str": s} is the string with its NUL, {"i64": v} the 8
+ * little-endian bytes, {"hex": h} the decoded bytes; "private-indices" names the secret ones.  The guest receives them through
+ * wasi_snapshot_preview1.args_sizes_get / args_get (include/host_modules/wasi_preview1.hpp:52-100): the bytes of a private
+ * argument are marked in linear memory, so every load that touches them commits a witness -- that is how private inputs
+ * enter a proof.  The public ones are folded into instance_hash (src/webgpu_prover.cpp:160-168), which seeds stage 1. */
+typedef struct {
+    uint32_t nargs;
+    const uint8_t *const *args;     /* nargs byte strings */
+    const size_t *arg_lens;
+    uint32_t nprivate;
+    const int32_t *private_indices;
+} lgrp_wat_args;
+int lgrp_wat_instance_hash(const lgrp_wat_args *args, uint8_t out[32]);
+/* lgrp_wat_emit / lgrp_prove_wat with arguments (args == NULL: none).  exit_code (may be NULL): what the guest passed to
+ * proc_exit, -1 if it returned from _start. */
+int lgrp_wat_emit_args(const char *wat, size_t len, const lgrp_wat_args *args, uint32_t l, const uint8_t *stage1_seed, lgrp_packer **rows_out,
+                       uint32_t const_sum[8], lgrp_wat_stats *stats, int32_t *exit_code);
+int lgrp_prove_wat_args(lgr_ctx *ctx, const char *wat, size_t len, const lgrp_wat_args *args, const uint8_t encoding_seed[32],
+                        int64_t generated_at_seconds, lgrp_proof **out, lgrp_wat_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

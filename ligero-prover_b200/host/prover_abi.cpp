@@ -230,11 +230,55 @@ static void fill_stats(lgrp_wat_stats *o, const wat_stats &s) {
     o->violated_constraints = s.violated_constraints;
 }
 
+// the guest's arguments: argv[0] included, private ones by index
+static void take_args(wat_program &prog, const lgrp_wat_args *a) {
+    if (!a) return;
+    if (a->nargs && (!a->args || !a->arg_lens)) throw std::invalid_argument("null argument list");
+    if (a->nprivate && !a->private_indices) throw std::invalid_argument("null private index list");
+    std::vector<std::vector<uint8_t>> args;
+    for (uint32_t i = 0; i < a->nargs; i++) {
+        if (a->arg_lens[i] && !a->args[i]) throw std::invalid_argument("null argument");
+        args.emplace_back(a->args[i], a->args[i] + a->arg_lens[i]);
+    }
+    std::set<int> priv;
+    for (uint32_t i = 0; i < a->nprivate; i++) priv.insert(a->private_indices[i]);
+    prog.set_args(std::move(args), std::move(priv));
+}
+// instance_hash: the public arguments folded into a zero digest, one hash(instance_hash, argument) each (src/webgpu_prover.cpp:160-168)
+static digest instance_hash_of(const lgrp_wat_args *a) {
+    digest d;
+    if (!a) return d;
+    std::set<int> priv;
+    for (uint32_t i = 0; i < a->nprivate; i++) priv.insert(a->private_indices[i]);
+    for (uint32_t i = 0; i < a->nargs; i++) {
+        if (priv.count((int)i)) continue;
+        sha256 h;
+        h << d;
+        h.update(a->args[i], a->arg_lens[i]);
+        d = h.flush_digest();
+    }
+    return d;
+}
+
+int lgrp_wat_instance_hash(const lgrp_wat_args *args, uint8_t out[32]) {
+    LGRP_TRY
+    if (!out) throw std::invalid_argument("null argument");
+    const digest d = instance_hash_of(args);
+    memcpy(out, d.data, 32);
+    LGRP_END
+}
+
 int lgrp_wat_emit(const char *wat, size_t len, uint32_t l, const uint8_t *stage1_seed, lgrp_packer **rows_out, uint32_t const_sum[8],
                   lgrp_wat_stats *stats) {
+    return lgrp_wat_emit_args(wat, len, nullptr, l, stage1_seed, rows_out, const_sum, stats, nullptr);
+}
+
+int lgrp_wat_emit_args(const char *wat, size_t len, const lgrp_wat_args *args, uint32_t l, const uint8_t *stage1_seed, lgrp_packer **rows_out,
+                       uint32_t const_sum[8], lgrp_wat_stats *stats, int32_t *exit_code) {
     LGRP_TRY
     if (!wat || !rows_out || !l) throw std::invalid_argument("null argument");
     wat_program prog(std::string(wat, len));
+    take_args(prog, args);
     wat_stats ws;
     lgrp_packer *pk = new lgrp_packer(l);
     try {
@@ -243,26 +287,36 @@ int lgrp_wat_emit(const char *wat, size_t len, uint32_t l, const uint8_t *stage1
         m.finish(const_sum);
     } catch (...) { delete pk; throw; }
     fill_stats(stats, ws);
+    if (exit_code) *exit_code = prog.exit_code();
     *rows_out = pk;
     LGRP_END
 }
 
 int lgrp_prove_wat(lgr_ctx *ctx, const char *wat, size_t len, const uint8_t encoding_seed[32], int64_t generated_at_seconds,
                    lgrp_proof **out, lgrp_wat_stats *stats) {
+    return lgrp_prove_wat_args(ctx, wat, len, nullptr, encoding_seed, generated_at_seconds, out, stats);
+}
+
+int lgrp_prove_wat_args(lgr_ctx *ctx, const char *wat, size_t len, const lgrp_wat_args *args, const uint8_t encoding_seed[32],
+                        int64_t generated_at_seconds, lgrp_proof **out, lgrp_wat_stats *stats) {
     LGRP_TRY
     if (!ctx || !wat || !encoding_seed || !out) throw std::invalid_argument("null argument");
     uint32_t l = 0, k = 0, n = 0;
     if (lgr_geometry(ctx, &l, &k, &n)) throw std::runtime_error(lgr_last_error());
     wat_program prog(std::string(wat, len));
+    take_args(prog, args);
     wat_stats ws;
     row_packer values(l);
     {
         witness_machine m(values, nullptr);                  // stage 1 needs the values only
+        prog.set_echo(true);                                 // what the guest prints appears once, not once per stage
         prog.run(m, ws);
+        prog.set_echo(false);
         m.finish(nullptr);
     }
     statement st;
     st.l = l; st.k = k;
+    st.instance_hash = instance_hash_of(args);
     memcpy(st.encoding_seed, encoding_seed, 32);
     st.generated_at_seconds = generated_at_seconds;
     {

@@ -29,6 +29,8 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <random>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -515,7 +517,8 @@ public:
 
     // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
     void run(witness_machine &m, wat_stats &st) const {
-        run_state rs{m, st, {}, {}, {}, {}, 0, {}, {}, 0, step_limit_};
+        run_state rs{m, st};
+        rs.step_limit = step_limit_;
         for (const global_t &g : globals_) rs.globals.push_back(g.init);
         rs.memory.assign((size_t)mem_pages_ * 65536, 0);
         rs.max_pages = mem_max_;
@@ -526,7 +529,9 @@ public:
             std::copy(d.bytes.begin(), d.bytes.end(), rs.memory.begin() + d.offset);
             rs.datas.back().clear();
         }
-        call(start_, rs, 0);
+        exit_code_ = -1;
+        const flow done = call(start_, rs, 0);
+        if (done.kind == flow::exit) exit_code_ = (int)done.label;
         while (!rs.stack.empty()) rs.stack.pop_back();
         st.linear_constraints = m.draws();
         st.violated_constraints = m.violated();
@@ -534,6 +539,11 @@ public:
         st.linear_witnesses = m.linear_released();
     }
     size_t instructions() const { size_t n = 0; for (const func_t &f : funcs_) n += f.code.size(); return n; }
+    // the program's arguments (argv[0] included) and which of them are private: what wasi args_get hands the guest; the bytes of
+    // a private argument are marked in memory, so loading them commits witnesses (host_modules/wasi_preview1.hpp:71-100)
+    void set_args(std::vector<std::vector<uint8_t>> args, std::set<int> private_indices) { args_ = std::move(args); private_ = std::move(private_indices); }
+    void set_echo(bool on) { echo_ = on; }                   // forward what the guest writes to fd 1 / 2 (fd_write) to stdout / stderr
+    int exit_code() const { return exit_code_; }              // of the last run: -1 unless the guest called proc_exit
     void set_step_limit(uint64_t n) { step_limit_ = n; }      // loops make running time a property of the program: executed instructions are bounded
 
 private:
@@ -632,6 +642,7 @@ private:
         uint32_t max_pages = 0;
         std::vector<frame_t *> frames;                        // current_frame() = frames.back()
         std::vector<uint64_t> globals;
+        std::mt19937 rand{1145141919};                        // wasi random_get (wasi_preview1.hpp:47,203-215)
         uint64_t steps = 0, step_limit = 0;
         void push(value v) { stack.push_back(std::move(v)); }
         // drop_n_below (nonbatch_context.hpp:128-138): the `n` values under the top `pos` leave the stack.  First every one of
@@ -1073,7 +1084,8 @@ private:
     }
 
     // env host functions (include/host_modules/env.hpp:40-110,160-190)
-    enum class host_fn : uint8_t { i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast, assert_is_concrete };
+    enum class host_fn : uint8_t { i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast, assert_is_concrete,
+                                   wasi_args_sizes_get, wasi_args_get, wasi_fd_write, wasi_proc_exit, wasi_random_get };
     static bool host_lookup(const std::string &name, host_fn &out) {
         static const std::map<std::string, host_fn> table = {
             {"i32_private_const", host_fn::i32_private_const}, {"i64_private_const", host_fn::i64_private_const}, {"assert_equal", host_fn::assert_equal},
@@ -1132,13 +1144,14 @@ private:
             if (s.kind != value::NUM) throw std::invalid_argument("wat: assert_is_concrete: value is a witness");
             break;
         }
+        default: throw std::logic_error("wat: not an env function");
         }
     }
 
     struct ins {
         enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, func_call, local_get, local_set, local_tee, select, drop, nop,
                                 load, store, memory_size, memory_grow, memory_fill, memory_copy, memory_init, data_drop,
-                                block, loop, if_, else_, end, br, br_if, br_table, return_, unreachable, float_op, global_get, global_set } kind;
+                                block, loop, if_, else_, end, br, br_if, br_table, return_, unreachable, float_op, global_get, global_set, call_indirect } kind;
         uint8_t o = 0;                                        // op, fop or host_fn; bytes moved by a load / store
         uint8_t width = 0;                                    // the value type the instruction computes in (32, 64, F32, F64); conversions: of the result
         bool sgn = false;
@@ -1179,7 +1192,7 @@ private:
 
     // exec_result (types.hpp:53-86): how an instruction ended -- fell through, jumps `label` more blocks out, or returns
     struct flow {
-        enum { ok, jump, ret } kind = ok;
+        enum { ok, jump, ret, exit } kind = ok;               // exit: the guest called proc_exit (exec_exit); `label` carries the code
         uint32_t label = 0;
         bool unwind() {                                       // one block left behind; true when the jump ends here
             if (kind != jump) return false;
@@ -1191,7 +1204,7 @@ private:
     // run_call (interpreter.hpp:274-345): arguments become the first locals, declared locals start at zero, the frame goes on
     // the stack; when the body is through it is dropped from under the results -- and with it whatever the locals still
     // hold, last local first.  `return` has dropped it already
-    void call(size_t fi, run_state &rs, int depth) const {
+    flow call(size_t fi, run_state &rs, int depth) const {
         if (depth > 200) throw std::invalid_argument("wat: call depth exceeded");
         const func_t &f = funcs_[fi];
         std::vector<value> arguments;
@@ -1206,9 +1219,87 @@ private:
         const size_t base = rs.stack.size();
         for (size_t pc = 0; pc < f.code.size(); pc++) {
             const flow r = step(f, pc, rs, depth, base);
-            if (r.kind == flow::ret) return;                  // (a jump that leaves the body is not caught by the reference either; the validator rejects it)
+            if (r.kind == flow::ret) return flow{};           // (a jump that leaves the body is not caught by the reference either; the validator rejects it)
+            if (r.kind == flow::exit) {                       // (:338-349) everything down to and including this activation's frame leaves, then the caller unwinds
+                size_t distance = 0;
+                while (distance < rs.stack.size() && rs.stack[rs.stack.size() - 1 - distance].kind != value::FRAME) distance++;
+                if (distance < rs.stack.size()) rs.drop_n_below(distance + 1, 0);
+                return r;
+            }
         }
         rs.drop_n_below(1, f.results.size());
+        return flow{};
+    }
+    // wasi_snapshot_preview1 (include/host_modules/wasi_preview1.hpp): the functions a guest needs to receive its arguments, print
+    // and stop.  Pointers and lengths are read with as_u32() in the reference, i.e. they must be numbers
+    static uint32_t wasi_u32(run_state &rs) {
+        value v = rs.pop();
+        if (v.kind != value::NUM) throw std::invalid_argument("wat: a WASI call takes concrete operands (a witness here ends the reference's run)");
+        return v.as_u32();
+    }
+    static uint8_t *wasi_mem(run_state &rs, uint64_t at, uint64_t n) {
+        if (at + n > rs.memory.size()) throw std::invalid_argument("wat: a WASI call reaches outside the memory");
+        return rs.memory.data() + at;
+    }
+    static void wasi_put32(run_state &rs, uint32_t at, uint32_t v) { memcpy(wasi_mem(rs, at, 4), &v, 4); }
+    flow host_call(host_fn f, run_state &rs) const {
+        switch (f) {
+        case host_fn::wasi_args_sizes_get: {                  // (:52-69) argc and the total size of the argument bytes
+            const uint32_t size_ptr = wasi_u32(rs), count_ptr = wasi_u32(rs);
+            uint32_t total = 0;
+            for (const auto &a : args_) total += (uint32_t)a.size();
+            wasi_put32(rs, count_ptr, (uint32_t)args_.size());
+            wasi_put32(rs, size_ptr, total);
+            rs.push(value::u32(0));
+            break;
+        }
+        case host_fn::wasi_args_get: {                        // (:71-100) the pointers, the bytes, and the mark on every private argument
+            uint32_t buffer = wasi_u32(rs), argv = wasi_u32(rs);
+            for (size_t i = 0; i < args_.size(); i++) {
+                wasi_put32(rs, argv, buffer);
+                argv += 4;
+                if (!args_[i].empty()) memcpy(wasi_mem(rs, buffer, args_[i].size()), args_[i].data(), args_[i].size());
+                if (private_.count((int)i)) rs.secrets.add(buffer, buffer + (uint32_t)args_[i].size());
+                buffer += (uint32_t)args_[i].size();
+            }
+            rs.push(value::u32(0));
+            break;
+        }
+        case host_fn::wasi_fd_write: {                        // (:167-193) writev; only stdout / stderr exist here
+            const uint32_t nwrite_ptr = wasi_u32(rs), iovec_len = wasi_u32(rs), iovec_ptr = wasi_u32(rs), fd = wasi_u32(rs);
+            wasi_mem(rs, nwrite_ptr, 4);
+            if (iovec_len > 1024) throw std::invalid_argument("wat: fd_write with too many buffers");
+            uint64_t written = 0;
+            std::string text;
+            for (uint32_t i = 0; i < iovec_len; i++) {
+                uint32_t ptr, len;
+                memcpy(&ptr, wasi_mem(rs, (uint64_t)iovec_ptr + 8 * (uint64_t)i, 8), 4);
+                memcpy(&len, wasi_mem(rs, (uint64_t)iovec_ptr + 8 * (uint64_t)i + 4, 4), 4);
+                text.append((const char *)wasi_mem(rs, ptr, len), len);
+                written += len;
+            }
+            const bool known = fd == 1 || fd == 2;
+            if (known && echo_) { fwrite(text.data(), 1, text.size(), fd == 1 ? stdout : stderr); fflush(fd == 1 ? stdout : stderr); }
+            rs.push(value::u32(known ? 0 : 9));               // errno of a failed writev (EBADF), as the reference reports it
+            wasi_put32(rs, nwrite_ptr, known ? (uint32_t)written : 0xFFFFFFFFu);
+            break;
+        }
+        case host_fn::wasi_proc_exit: {                       // (:195-200) ends the run: every activation is unwound (call)
+            value code = rs.pop();
+            flow r; r.kind = flow::exit; r.label = (uint32_t)rs.make_numeric(std::move(code));
+            return r;
+        }
+        case host_fn::wasi_random_get: {                      // (:202-215) NOT random: mt19937 seeded with a constant, one draw per byte
+            const uint32_t len = wasi_u32(rs), ptr = wasi_u32(rs);
+            uint8_t *buf = wasi_mem(rs, ptr, len);
+            std::uniform_int_distribution<> dist(0, 255);
+            for (uint32_t i = 0; i < len; i++) buf[i] = (uint8_t)dist(rs.rand);
+            rs.push(value::u32(0));
+            break;
+        }
+        default: host(f, rs); break;
+        }
+        return flow{};
     }
     // the body of a block / of one arm of an if (run_scoped_block, run_if_then_else: interpreter.hpp:91-131,175-214)
     flow run_body(const func_t &f, size_t lo, size_t hi, size_t results, run_state &rs, int depth, size_t base) const {
@@ -1231,8 +1322,19 @@ private:
         case ins::unary_op: unary((op)i.o, i.width, i.sgn, rs); break;
         case ins::shift_op: shift((op)i.o, i.width, i.sgn, rs); break;
         case ins::binary_op: binary((op)i.o, i.width, i.sgn, rs); break;
-        case ins::host_call: host((host_fn)i.o, rs); break;
-        case ins::func_call: call((size_t)i.imm, rs, depth + 1); break;
+        case ins::host_call: return host_call((host_fn)i.o, rs);
+        case ins::func_call: return call((size_t)i.imm, rs, depth + 1);
+        case ins::call_indirect: {                            // run_call_indirect (interpreter.hpp:372-398): the index is read with as_u32(), i.e. it must be a number
+            value v = rs.pop();
+            if (v.kind != value::NUM) throw std::invalid_argument("wat: call_indirect takes a concrete index (a witness here ends the reference's run)");
+            const uint32_t at = v.as_u32();
+            if (at >= table_.size()) throw std::invalid_argument("wat: call_indirect: index out of bound");
+            if (table_[at] < 0) throw std::invalid_argument("wat: call_indirect: null pointer");
+            const func_t &callee = funcs_[(size_t)table_[at]];
+            const sig_t &want_sig = sigs_[(size_t)i.imm];       // (the reference leaves this check as a TODO; a mismatch would misread its stack.  WebAssembly traps)
+            if (callee.params != want_sig.params || callee.results != want_sig.results) throw std::invalid_argument("wat: call_indirect: indirect call type mismatch");
+            return call((size_t)table_[at], rs, depth + 1);
+        }
         case ins::local_get: rs.push(rs.frames.back()->locals[(size_t)i.imm].share()); break;
         case ins::local_set: rs.frames.back()->locals[(size_t)i.imm] = rs.pop(); break;
         case ins::local_tee: rs.frames.back()->locals[(size_t)i.imm] = rs.stack.back().share(); break;
@@ -1625,7 +1727,19 @@ private:
         return bits | sign;
     }
     void emit_host(const std::string &module, const std::string &field) {
-        if (module != "env") throw std::invalid_argument("wat: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
+        if (module == "wasi_snapshot_preview1") {
+            static const std::map<std::string, std::pair<host_fn, int>> wasi = {       // function, operands (all i32); all but proc_exit return an i32 errno
+                {"args_sizes_get", {host_fn::wasi_args_sizes_get, 2}}, {"args_get", {host_fn::wasi_args_get, 2}}, {"fd_write", {host_fn::wasi_fd_write, 4}},
+                {"proc_exit", {host_fn::wasi_proc_exit, 1}}, {"random_get", {host_fn::wasi_random_get, 2}}};
+            const auto it = wasi.find(field);
+            if (it == wasi.end()) throw std::invalid_argument("wat: wasi_snapshot_preview1." + printable(field) + " is not supported by the front end (args_sizes_get, args_get, fd_write, proc_exit, random_get are)");
+            if (!has_memory_ && it->second.first != host_fn::wasi_proc_exit) throw std::invalid_argument("wat: a WASI call in a module without a memory");
+            for (int j = 0; j < it->second.second; j++) want(32, "call wasi_snapshot_preview1." + field);
+            if (it->second.first != host_fn::wasi_proc_exit) types_.push_back(32);
+            ins i; i.kind = ins::host_call; i.o = (uint8_t)it->second.first; cur_->code.push_back(i);
+            return;
+        }
+        if (module != "env") throw std::invalid_argument("wat: only the env and wasi_snapshot_preview1 host modules are supported (no bn254fr / vbn254fr / uint256 / ecc imports)");
         host_fn f;
         if (!host_lookup(field, f)) throw std::invalid_argument("wat: env." + printable(field) + " is not supported by the front end");
         const std::string shown = "call env." + field;
@@ -1644,6 +1758,38 @@ private:
         for (size_t i = f.params.size(); i-- > 0;) want(f.params[i], "call " + std::to_string(index));
         for (uint8_t r : f.results) types_.push_back(r);
         put(ins::func_call, fi);
+    }
+    void emit_call_indirect(uint64_t type_index, uint64_t table_index) {
+        if (!has_table_ || table_index != 0) throw std::invalid_argument("wat: call_indirect through an unknown table");
+        if (type_index >= sigs_.size()) throw std::invalid_argument("wat: call_indirect with an unknown type (" + std::to_string(type_index) + ")");
+        const sig_t sg = sigs_[(size_t)type_index];
+        want(32, "call_indirect");
+        want_all(sg.params, "call_indirect");
+        types_.insert(types_.end(), sg.results.begin(), sg.results.end());
+        put(ins::call_indirect, type_index);
+    }
+    // the index of a function type with these parameters and results (added if the module has none)
+    uint64_t sig_index(const std::vector<uint8_t> &params, const std::vector<uint8_t> &results) {
+        for (size_t i = 0; i < sigs_.size(); i++) if (sigs_[i].params == params && sigs_[i].results == results) return i;
+        sigs_.push_back(sig_t{params, results});
+        return sigs_.size() - 1;
+    }
+    void set_table(uint64_t min) {
+        if (has_table_) throw std::invalid_argument("wat: more than one table");
+        if (min > 1000000) throw std::invalid_argument("wat: table too large");
+        has_table_ = true;
+        table_.assign((size_t)min, -1);
+    }
+    // an active element segment: module functions (by index among imports + functions) written into the table at `offset`
+    void set_elements(uint64_t offset, const std::vector<int64_t> &funcs, size_t nimports) {
+        if (!has_table_) throw std::invalid_argument("wat: an element segment needs a table");
+        if (offset + funcs.size() > table_.size()) throw std::invalid_argument("wat: table_init: index out of bound");
+        for (size_t i = 0; i < funcs.size(); i++) {
+            if (funcs[i] < 0) { table_[(size_t)offset + i] = -1; continue; }
+            if ((uint64_t)funcs[i] < nimports) throw std::invalid_argument("wat: an imported function in a table is not supported");
+            if ((uint64_t)funcs[i] - nimports >= funcs_.size()) throw std::invalid_argument("wat: an element segment names an unknown function");
+            table_[(size_t)offset + i] = funcs[i] - (int64_t)nimports;
+        }
     }
     void emit_local(ins::kind_t k, uint64_t index) {
         if (index >= cur_->locals.size()) throw std::invalid_argument("wat: unknown local " + std::to_string(index));
@@ -1728,6 +1874,7 @@ private:
         const std::map<std::string, size_t> &func_ids;        // $name -> function index (imports first)
         const std::map<std::string, size_t> &data_ids;
         const std::map<std::string, size_t> &global_ids;
+        const std::map<std::string, size_t> &type_ids;
         std::map<std::string, size_t> local_ids;
     };
     void set_memory(uint64_t pages, uint64_t max_pages) {
@@ -1772,15 +1919,15 @@ private:
         const sexpr top = p.parse_top();
         if (top.head() != "module") throw std::invalid_argument("wat: expected (module ...)");
         std::vector<import_t> imports;
-        std::map<std::string, size_t> func_ids, data_ids, global_ids;
-        std::vector<const sexpr *> bodies;
+        std::map<std::string, size_t> func_ids, data_ids, global_ids, type_ids;
+        std::vector<const sexpr *> bodies, elems, inline_elems;
         std::string start;
         for (size_t i = 1; i < top.list.size(); i++) {
             const sexpr &f = top.list[i];
             if (f.head() == "import") {
                 // (import "env" "name" (func $id ...))
                 if (f.list.size() < 4 || f.list[3].head() != "func") throw std::invalid_argument("wat: unsupported import");
-                if (f.list[1].atom != "\"env\"") throw std::invalid_argument("wat: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
+                if (f.list[1].atom != "\"env\"" && f.list[1].atom != "\"wasi_snapshot_preview1\"") throw std::invalid_argument("wat: only the env and wasi_snapshot_preview1 host modules are supported (no bn254fr / vbn254fr / uint256 / ecc imports)");
                 if (!bodies.empty()) throw std::invalid_argument("wat: imports must come before the module's functions");
                 if (f.list[3].list.size() >= 2 && !f.list[3].list[1].is_list) func_ids[f.list[3].list[1].atom] = imports.size();
                 imports.push_back(import_t{unquote(f.list[1].atom), unquote(f.list[2].atom)});
@@ -1809,6 +1956,29 @@ private:
                     d.bytes += decode_string(f.list[j].atom);
                 }
                 datas_.push_back(d);
+            } else if (f.head() == "type") {                   // (type [$id] (func (param ..)* (result ..)*))
+                size_t j = 1;
+                if (j < f.list.size() && !f.list[j].is_list && f.list[j].atom[0] == '$') type_ids[f.list[j++].atom] = sigs_.size();
+                if (j + 1 != f.list.size() || f.list[j].head() != "func") throw std::invalid_argument("wat: unsupported type definition");
+                sig_t sg;
+                for (size_t q = 1; q < f.list[j].list.size(); q++) {
+                    const sexpr &part = f.list[j].list[q];
+                    if (part.head() != "param" && part.head() != "result") throw std::invalid_argument("wat: unsupported type definition");
+                    for (size_t t = (part.list.size() == 3 && !part.list[1].atom.empty() && part.list[1].atom[0] == '$') ? 2 : 1; t < part.list.size(); t++)
+                        (part.head() == "param" ? sg.params : sg.results).push_back(width_of(part.list[t].atom));
+                }
+                sigs_.push_back(sg);
+            } else if (f.head() == "table") {                  // (table [$id] min [max] funcref) | (table [$id] funcref (elem $f ...))
+                size_t j = (f.list.size() >= 2 && !f.list[1].is_list && f.list[1].atom[0] == '$') ? 2 : 1;
+                if (j < f.list.size() && !f.list[j].is_list && f.list[j].atom == "funcref" && j + 2 == f.list.size() && f.list[j + 1].head() == "elem") {
+                    set_table(f.list[j + 1].list.size() - 1);
+                    inline_elems.push_back(&f.list[j + 1]);
+                } else {
+                    if (j >= f.list.size() || f.list[j].is_list || f.list.back().is_list || f.list.back().atom != "funcref") throw std::invalid_argument("wat: unsupported table declaration");
+                    set_table(parse_i64(f.list[j].atom));
+                }
+            } else if (f.head() == "elem") {
+                elems.push_back(&f);
             } else if (f.head() == "global") {                 // (global [$id] i32 | (mut i32) (i32.const v)): the initialiser must be a constant
                 size_t j = 1;
                 if (j < f.list.size() && !f.list[j].is_list && f.list[j].atom[0] == '$') global_ids[f.list[j++].atom] = globals_.size();
@@ -1850,6 +2020,29 @@ private:
             }
             first_instr[k] = i;
         }
+        // element segments: (elem [$id] [(table ..)] (offset? (i32.const n)) [func] $f ...) writes functions into the table at instantiation
+        const text_scope names{imports, func_ids, data_ids, global_ids, type_ids, {}};
+        const auto functions_from = [&](const sexpr &e, size_t j) {
+            std::vector<int64_t> fs;
+            for (; j < e.list.size(); j++) {
+                if (e.list[j].is_list) throw std::invalid_argument("wat: element expressions are not supported (name the functions)");
+                fs.push_back((int64_t)func_index(e.list[j].atom, names));
+            }
+            return fs;
+        };
+        for (const sexpr *e : inline_elems) set_elements(0, functions_from(*e, 1), imports.size());
+        for (const sexpr *e : elems) {
+            size_t j = 1;
+            if (j + 1 < e->list.size() && !e->list[j].is_list && e->list[j].atom[0] == '$' && e->list[j + 1].is_list) j++;      // the segment's own name
+            if (j < e->list.size() && e->list[j].head() == "table") j++;
+            if (j < e->list.size() && !e->list[j].is_list && e->list[j].atom == "declare") continue;   // declarative: only announces ref.func targets
+            if (j >= e->list.size() || !e->list[j].is_list) throw std::invalid_argument("wat: passive element segments are not supported (no table.init)");
+            const sexpr *off = &e->list[j++];
+            if (off->head() == "offset" && off->list.size() == 2) off = &off->list[1];
+            if (off->head() != "i32.const" || off->list.size() != 2 || off->list[1].is_list) throw std::invalid_argument("wat: an element segment's offset must be an i32.const");
+            if (j < e->list.size() && !e->list[j].is_list && e->list[j].atom == "func") j++;
+            set_elements((uint32_t)parse_i64(off->list[1].atom), functions_from(*e, j), imports.size());
+        }
         if (start.empty()) throw std::invalid_argument("wat: no exported _start function");
         const auto sit = func_ids.find(start);
         size_t start_index;
@@ -1862,7 +2055,7 @@ private:
         for (size_t k = 0; k < bodies.size(); k++) {
             const sexpr &f = *bodies[k];
             func_t &fn = funcs_[k];
-            text_scope sc{imports, func_ids, data_ids, global_ids, local_ids[k]};
+            text_scope sc{imports, func_ids, data_ids, global_ids, type_ids, local_ids[k]};
             begin_body(fn);
             parse_seq(f.list, first_instr[k], f.list.size(), sc);
             end_body(f.list.size() >= 2 && !f.list[1].is_list ? f.list[1].atom : "function " + std::to_string(k));
@@ -1874,6 +2067,26 @@ private:
             if (list[j].head() == "type") throw std::invalid_argument("wat: block types by index are not supported in text");
             for (size_t t = 1; t < list[j].list.size(); t++) (list[j].head() == "param" ? params : results).push_back(width_of(list[j].list[t].atom));
         }
+    }
+    // the type use after call_indirect: (type $t) and / or (param ..)* (result ..)*, from list[j] on -> type index
+    uint64_t type_use(const std::vector<sexpr> &list, size_t &j, const text_scope &sc) {
+        int64_t named = -1;
+        if (j < list.size() && list[j].is_list && list[j].head() == "type" && list[j].list.size() == 2 && !list[j].list[1].is_list) {
+            const std::string &id = list[j++].list[1].atom;
+            const auto it = sc.type_ids.find(id);
+            if (it != sc.type_ids.end()) named = (int64_t)it->second;
+            else if (!id.empty() && id[0] >= '0' && id[0] <= '9') named = (int64_t)parse_i64(id);
+            else throw std::invalid_argument("wat: unknown type " + id);
+            if ((uint64_t)named >= sigs_.size()) throw std::invalid_argument("wat: unknown type " + id);
+        }
+        std::vector<uint8_t> params, results;
+        const size_t before = j;
+        blocktype(list, j, params, results);
+        if (named >= 0) {
+            if (j != before && (sigs_[(size_t)named].params != params || sigs_[(size_t)named].results != results)) throw std::invalid_argument("wat: a type use disagrees with its type");
+            return (uint64_t)named;
+        }
+        return sig_index(params, results);
     }
     // a sequence of instructions, folded forms and plain ones mixed: list[from, to)
     void parse_seq(const std::vector<sexpr> &list, size_t from, size_t to, const text_scope &sc) {
@@ -1894,6 +2107,13 @@ private:
             else if (a == "f32.const" || a == "f64.const") emit_const(a[1] == '3' ? F32 : F64, parse_float(next(), a[1] == '3'));
             else if (a == "global.get" || a == "global.set") emit_global(a == "global.get" ? ins::global_get : ins::global_set, global_index(next(), sc));
             else if (a == "call") emit_call(func_index(next(), sc), sc.imports);
+            else if (a == "call_indirect") {
+                if (i + 1 < to && !list[i + 1].is_list) { if (list[i + 1].atom != "0" && list[i + 1].atom[0] != '$') throw std::invalid_argument("wat: call_indirect through an unknown table"); i++; }
+                size_t j = i + 1;
+                const uint64_t t = type_use(list, j, sc);
+                i = j - 1;
+                emit_call_indirect(t, 0);
+            }
             else if (a == "local.get" || a == "local.set" || a == "local.tee") emit_local(a == "local.get" ? ins::local_get : (a == "local.set" ? ins::local_set : ins::local_tee), local_index(next(), sc));
             else if (a == "select") emit_plain(ins::select);
             else if (a == "drop") emit_plain(ins::drop);
@@ -2025,6 +2245,14 @@ private:
             emit_call(index, sc.imports);
             return;
         }
+        if (h == "call_indirect") {                             // (call_indirect $table? (type $t) operand* index)
+            size_t j = 1;
+            if (j < e.list.size() && !e.list[j].is_list) { if (e.list[j].atom != "0" && e.list[j].atom[0] != '$') throw std::invalid_argument("wat: call_indirect through an unknown table"); j++; }
+            const uint64_t t = type_use(e.list, j, sc);
+            operands(j);
+            emit_call_indirect(t, 0);
+            return;
+        }
         if (h == "local.get" || h == "local.set" || h == "local.tee") {
             if (e.list.size() < 2 || e.list[1].is_list || e.list.size() != (h == "local.get" ? 2u : 3u)) throw std::invalid_argument("wat: malformed " + h);
             operands(2);
@@ -2147,6 +2375,7 @@ private:
         std::vector<uint64_t> func_types;
         int64_t start = -1;
         std::vector<reader> bodies;
+        std::vector<std::pair<uint64_t, std::vector<int64_t>>> pending_elems;   // (offset, functions): written once the functions are known
         while (r.p < r.end) {
             const uint8_t id = r.byte();
             reader s = r.sub((size_t)r.uleb());
@@ -2197,6 +2426,49 @@ private:
                         }
                     }
                     types.push_back(t);
+                    sigs_.push_back(sig_t{t.params, t.results});
+                }
+                break;
+            }
+            case 4: {                                         // tables: at most one, of function references
+                const size_t n = (size_t)s.uleb();
+                if (n > 1) throw std::invalid_argument("wasm: more than one table");
+                if (n) {
+                    if (s.byte() != 0x70) throw std::invalid_argument("wasm: only tables of function references are supported");
+                    const uint8_t flags = s.byte();
+                    if (flags > 1) throw std::invalid_argument("wasm: unsupported table limits");
+                    set_table(s.uleb());
+                    if (flags) s.uleb();
+                }
+                break;
+            }
+            case 9: {                                         // element segments: active ones fill the table; declarative ones say nothing
+                const size_t n = (size_t)s.uleb();
+                for (size_t i = 0; i < n; i++) {
+                    const uint64_t flag = s.uleb();
+                    if (flag > 7) throw std::invalid_argument("wasm: malformed element segment");
+                    const bool active = !(flag & 1), exprs = (flag & 4) != 0;
+                    if (!active && !(flag & 2)) throw std::invalid_argument("wasm: passive element segments are not supported (no table.init)");
+                    uint64_t offset = 0;
+                    if (active) {
+                        if ((flag & 2) && s.uleb() != 0) throw std::invalid_argument("wasm: element segment for an unknown table");
+                        if (s.byte() != 0x41) throw std::invalid_argument("wasm: an element segment's offset must be an i32.const");
+                        offset = (uint32_t)s.sleb(32);
+                        if (s.byte() != 0x0B) throw std::invalid_argument("wasm: an element segment's offset must be an i32.const");
+                    }
+                    if (flag & 3) { const uint8_t kind = s.byte(); if (kind != (exprs ? 0x70 : 0x00)) throw std::invalid_argument("wasm: only function elements are supported"); }
+                    const size_t cnt = (size_t)s.uleb();
+                    if (cnt > 1000000) throw std::invalid_argument("wasm: element segment too large");
+                    std::vector<int64_t> fs;
+                    for (size_t j = 0; j < cnt; j++) {
+                        if (!exprs) { fs.push_back((int64_t)s.uleb()); continue; }
+                        const uint8_t op = s.byte();           // ref.func f | ref.null func
+                        if (op == 0xD2) fs.push_back((int64_t)s.uleb());
+                        else if (op == 0xD0) { if (s.byte() != 0x70) throw std::invalid_argument("wasm: unsupported element expression"); fs.push_back(-1); }
+                        else throw std::invalid_argument("wasm: unsupported element expression");
+                        if (s.byte() != 0x0B) throw std::invalid_argument("wasm: unsupported element expression");
+                    }
+                    if (active) pending_elems.emplace_back(offset, std::move(fs));
                 }
                 break;
             }
@@ -2206,7 +2478,7 @@ private:
                     import_t im{s.name(), s.name()};
                     if (s.byte() != 0x00) throw std::invalid_argument("wasm: only function imports are supported (" + printable(im.module + "." + im.field) + ")");
                     s.uleb();
-                    if (im.module != "env") throw std::invalid_argument("wasm: only the env host module is supported (no WASI, no bn254fr / vbn254fr imports)");
+                    if (im.module != "env" && im.module != "wasi_snapshot_preview1") throw std::invalid_argument("wasm: only the env and wasi_snapshot_preview1 host modules are supported (no bn254fr / vbn254fr / uint256 / ecc imports)");
                     imports.push_back(im);
                 }
                 break;
@@ -2267,6 +2539,7 @@ private:
             }
         }
         if (!funcs_[start_].params.empty() || !funcs_[start_].results.empty()) throw std::invalid_argument("wasm: _start with parameters / results is not supported");
+        for (const auto &pe : pending_elems) set_elements(pe.first, pe.second, imports.size());
         static const char *const int_ops[] = {"clz", "ctz", "popcnt", "add", "sub", "mul", "div_s", "div_u", "rem_s", "rem_u", "and", "or", "xor", "shl", "shr_s", "shr_u", "rotl", "rotr"};
         static const char *const cmp_ops[] = {"eqz", "eq", "ne", "lt_s", "lt_u", "gt_s", "gt_u", "le_s", "le_u", "ge_s", "ge_u"};
         for (size_t k = 0; k < bodies.size(); k++) {
@@ -2306,6 +2579,11 @@ private:
                 else if (c == 0x1A) emit_plain(ins::drop);
                 else if (c == 0x1B) emit_plain(ins::select);
                 else if (c == 0x10) emit_call(b.uleb(), imports);
+                else if (c == 0x11) {
+                    const uint64_t t = b.uleb(), tab = b.uleb();
+                    if (t >= types.size() || !types[(size_t)t].usable) throw std::invalid_argument("wasm: call_indirect with an unsupported type");
+                    emit_call_indirect(t, tab);
+                }
                 else if (c == 0x23 || c == 0x24) emit_global(c == 0x23 ? ins::global_get : ins::global_set, b.uleb());
                 else if (c == 0x20 || c == 0x21 || c == 0x22) emit_local(c == 0x20 ? ins::local_get : (c == 0x21 ? ins::local_set : ins::local_tee), b.uleb());
                 else if (c >= 0x28 && c <= 0x3E) {
@@ -2374,7 +2652,15 @@ private:
         }
     }
 
+    std::vector<std::vector<uint8_t>> args_;
+    std::set<int> private_;
+    bool echo_ = false;
+    mutable int exit_code_ = -1;
     struct data_t { std::string bytes; bool active = false; uint32_t offset = 0; };
+    struct sig_t { std::vector<uint8_t> params, results; };   // the module's function types (call_indirect names one)
+    std::vector<sig_t> sigs_;
+    bool has_table_ = false;
+    std::vector<int64_t> table_;                              // table 0: index among the module's own functions, -1 = null (table_instance, runtime.hpp:96-102)
     struct global_t { uint8_t type = 32; bool mut = false; uint64_t init = 0; };   // global_instance (runtime.hpp:181-187): i32 / i64 only (:441-455)
     std::vector<global_t> globals_;
     std::vector<func_t> funcs_;

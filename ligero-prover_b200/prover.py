@@ -199,28 +199,77 @@ class WatStats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
-def wat_emit(wat_text, l, stage1_seed=None):
-    """lgrp_wat_emit: the bounded .wat front end + witness emitter (host only).  Returns (kinds, values[rows, l, 8],
-    coefs[rows, l, 8], const_sum, stats); coefs are zero without a stage-1 seed."""
+class WatArgs(C.Structure):
+    """lgrp_wat_args (include/lgr_prover.h): the guest's arguments and the indices of the private ones"""
+    _fields_ = [("nargs", C.c_uint32), ("args", C.POINTER(C.c_char_p)), ("arg_lens", C.POINTER(C.c_size_t)),
+                ("nprivate", C.c_uint32), ("private_indices", C.POINTER(C.c_int32))]
+
+
+def config_args(args, program_name=b"Ligero\0"):
+    """the argument byte strings the reference's prover builds from the "args" list of its JSON configuration
+    (src/webgpu_prover.cpp:110-147): argv[0], then {"i64": v} -> 8 little-endian bytes, {"str": s} -> the string and its NUL,
+    {"hex": h} -> the decoded bytes (a leading 0x dropped, an odd digit count padded on the left)"""
+    out = [bytes(program_name)]
+    for a in args:
+        if "i64" in a:
+            out.append(int(a["i64"]).to_bytes(8, "little", signed=True))
+        elif "str" in a:
+            out.append(a["str"].encode() + b"\0")
+        elif "hex" in a:
+            h = a["hex"][2:] if a["hex"].startswith("0x") else a["hex"]
+            out.append(bytes.fromhex(("0" if len(h) % 2 else "") + h))
+        else:
+            raise ProverError("invalid args type: %r" % (a,))
+    return out
+
+
+def _wat_args(args, private_indices):
+    if args is None:
+        return None, None
+    args = [bytes(a) for a in args]
+    priv = sorted(set(int(i) for i in (private_indices or ())))
+    holder = ((C.c_char_p * max(1, len(args)))(*args), (C.c_size_t * max(1, len(args)))(*[len(a) for a in args]), (C.c_int32 * max(1, len(priv)))(*priv))
+    wa = WatArgs(len(args), holder[0], holder[1], len(priv), holder[2])
+    return wa, holder
+
+
+def wat_instance_hash(args, private_indices=()):
+    """lgrp_wat_instance_hash: the public arguments folded into the instance hash (src/webgpu_prover.cpp:160-168)"""
+    wa, _keep = _wat_args(args, private_indices)
+    out = (C.c_uint8 * 32)()
+    _check(lib().lgrp_wat_instance_hash(C.byref(wa) if wa is not None else None, out))
+    return bytes(out)
+
+
+def wat_emit(wat_text, l, stage1_seed=None, args=None, private_indices=(), want_exit_code=False):
+    """lgrp_wat_emit / lgrp_wat_emit_args: the .wat / .wasm front end + witness emitter (host only).  Returns (kinds,
+    values[rows, l, 8], coefs[rows, l, 8], const_sum, stats); coefs are zero without a stage-1 seed.  `args`: the guest's
+    argument byte strings (argv[0] first; see config_args), `private_indices`: which of them are secret."""
     data = wat_text.encode() if isinstance(wat_text, str) else bytes(wat_text)
     h = C.c_void_p()
     cs = (C.c_uint32 * 8)()
     st = WatStats()
     seed = _p(_u8(stage1_seed, 32)) if stage1_seed is not None else None
-    _check(lib().lgrp_wat_emit(data, C.c_size_t(len(data)), C.c_uint32(l), seed, C.byref(h), cs, C.byref(st)))
+    wa, _keep = _wat_args(args, private_indices)
+    code = C.c_int32(-1)
+    _check(lib().lgrp_wat_emit_args(data, C.c_size_t(len(data)), C.byref(wa) if wa is not None else None, C.c_uint32(l), seed, C.byref(h), cs, C.byref(st),
+                                    C.byref(code)))
     pk = RowPacker.__new__(RowPacker)
     pk._h, pk.l = h, l
     kinds, vals, coefs = pk.rows()
     pk.close()
-    return kinds, vals, coefs, sum(int(cs[i]) << (32 * i) for i in range(8)), st.as_dict()
+    out = (kinds, vals, coefs, sum(int(cs[i]) << (32 * i) for i in range(8)), st.as_dict())
+    return out + (int(code.value),) if want_exit_code else out
 
 
-def prove_wat(executor, wat_text, encoding_seed=bytes(32), generated_at=0):
-    """lgrp_prove_wat: .wat text -> proof on the executor's geometry (BASELINE config 4, bounded: include/lgr_prover.h)"""
+def prove_wat(executor, wat_text, encoding_seed=bytes(32), generated_at=0, args=None, private_indices=()):
+    """lgrp_prove_wat / lgrp_prove_wat_args: .wat / .wasm -> proof on the executor's geometry (BASELINE config 4: include/lgr_prover.h)"""
     data = wat_text.encode() if isinstance(wat_text, str) else bytes(wat_text)
     h = C.c_void_p()
     st = WatStats()
-    _check(lib().lgrp_prove_wat(executor._ctx, data, C.c_size_t(len(data)), _p(_u8(encoding_seed, 32)), C.c_int64(generated_at), C.byref(h), C.byref(st)))
+    wa, _keep = _wat_args(args, private_indices)
+    _check(lib().lgrp_prove_wat_args(executor._ctx, data, C.c_size_t(len(data)), C.byref(wa) if wa is not None else None, _p(_u8(encoding_seed, 32)),
+                                     C.c_int64(generated_at), C.byref(h), C.byref(st)))
     return Proof(h), st.as_dict()
 
 

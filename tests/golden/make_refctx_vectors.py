@@ -33,6 +33,11 @@ WAT_CASES = [("mul64", os.path.join(HERE, "mul64.wat"), 256), ("arith32", os.pat
              ("intops", os.path.join(HERE, "intops.wat"), 256)]       # every other integer instruction (tests/golden/make_intops_wat.py)
 
 
+# a guest with arguments (wasi args_get; argv[1] and argv[3] private): what src/webgpu_prover.cpp:110-157 would build from
+# {"args": [{"i64": 400}, {"i64": 600}, {"str": "hello"}], "private-indices": [1, 3]}
+WASI_CASE = ("wasi", os.path.join(HERE, "wasi_args.wat"), 256, [b"Ligero\0", (400).to_bytes(8, "little"), (600).to_bytes(8, "little"), b"hello\0"], [1, 3])
+
+
 def zb64(hexstr):
     return base64.b64encode(zlib.compress(bytes.fromhex(hexstr), 9)).decode()
 
@@ -54,12 +59,12 @@ def compact(raw):
     return out
 
 
-def write(name, k, raw):
+def write(name, k, raw, extra=None):
     assert raw["valid"] == [1, 1, 1], "the reference's self-check must pass on an honest run"
     assert raw["verifier"] == [1] * 7, "the reference's verifier must accept the proof of its own prover passes"
     path = os.path.join(HERE, "refctx_%s_k%d.json" % (name, k))
     with open(path, "w") as f:
-        json.dump(compact(raw), f, separators=(",", ":"))
+        json.dump(dict(compact(raw), **(extra or {})), f, separators=(",", ":"))
         f.write("\n")
     print(path, os.path.getsize(path), "bytes")
 
@@ -73,6 +78,10 @@ def main():
         raw = refctx_util.run_reference_on_wat(open(wat).read(), k)
         raw["program"] = name
         write(name, k, raw)
+    name, wat, k, args, private = WASI_CASE
+    raw = refctx_util.run_reference_on_wat(open(wat).read(), k, args=args, private_indices=private)
+    raw["program"] = name
+    write(name, k, raw, {"args": [a.hex() for a in args], "private_indices": private})
     for prog, k in CASES:
         with tempfile.NamedTemporaryFile(suffix=".json") as tmp:
             subprocess.check_call([BIN, prog, str(k), tmp.name])

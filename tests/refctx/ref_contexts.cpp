@@ -33,6 +33,9 @@
 #include <zkp/nonbatch_context.hpp>
 #include <host_modules/env.hpp>
 #include <host_modules/vbn254fr.hpp>
+#include <filesystem>
+#include <unordered_set>
+#include <host_modules/wasi_preview1.hpp>
 
 #include <fiat_shamir.hpp>   // ligero-prover_b200/host: the sampler only (portable_sample needs Boost)
 
@@ -103,10 +106,13 @@ struct tiny_module {
     store_t store;
     module_instance inst;
     // env functions in import order: the call token "call:<name>" becomes call <index>
-    static const std::vector<std::pair<std::string, int>> &env_imports() {      // name, shape: 0 = (i64)->(i64), 1 = (i64 i64)->(), 2 = (i32)->(i32), 3 = (i64)->()
+    // shape: 0 = (i64)->(i64), 1 = (i64 i64)->(), 2 = (i32)->(i32), 3 = (i64)->(), 4 = (i32 i32)->(i32), 5 = (i32 i32 i32 i32)->(i32), 6 = (i32)->()
+    // names "wasi.<function>" are imports of wasi_snapshot_preview1, the others of env
+    static const std::vector<std::pair<std::string, int>> &env_imports() {
         static const std::vector<std::pair<std::string, int>> t = {
             {"i64_private_const", 0}, {"assert_equal", 1}, {"i32_private_const", 2}, {"assert_zero", 3}, {"assert_one", 3}, {"assert_constant", 3},
-            {"witness_cast_u32", 2}, {"witness_cast_u64", 0}, {"assert_is_concrete", 3}};
+            {"witness_cast_u32", 2}, {"witness_cast_u64", 0}, {"assert_is_concrete", 3},
+            {"wasi.args_sizes_get", 4}, {"wasi.args_get", 4}, {"wasi.fd_write", 5}, {"wasi.proc_exit", 6}, {"wasi.random_get", 4}};
         return t;
     }
     static int import_index(const std::string &name) {
@@ -121,14 +127,19 @@ struct tiny_module {
     };
     struct data_seg { std::vector<u8> bytes; bool active = false; u32 offset = 0; };
     explicit tiny_module(std::vector<module_func> functions, size_t start_function, u32 mem_pages = 1, u32 mem_max = 0, const std::vector<data_seg> &datas = {},
-                         const std::vector<std::pair<value_kind, uint64_t>> &globals = {}) {
+                         const std::vector<std::pair<value_kind, uint64_t>> &globals = {}, const std::vector<reference_t> *table = nullptr) {
         function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_pc32({value_kind::i32}, {value_kind::i32}),
-            k_one({value_kind::i64}, {});
-        inst.types = {k_pc, k_eq, k_pc32, k_one};
-        const function_kind *shapes[4] = {&k_pc, &k_eq, &k_pc32, &k_one};
+            k_one({value_kind::i64}, {}), k_w2({value_kind::i32, value_kind::i32}, {value_kind::i32}),
+            k_w4({value_kind::i32, value_kind::i32, value_kind::i32, value_kind::i32}, {value_kind::i32}), k_w1({value_kind::i32}, {});
+        inst.types = {k_pc, k_eq, k_pc32, k_one, k_w2, k_w4, k_w1};
+        const function_kind *shapes[7] = {&k_pc, &k_eq, &k_pc32, &k_one, &k_w2, &k_w4, &k_w1};
         const auto &t = env_imports();
-        for (size_t i = 0; i < t.size(); i++)
-            inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t(t[i].first), *shapes[t[i].second], &inst, function_instance::host_code{(index_t)i, "env", t[i].first}));
+        for (size_t i = 0; i < t.size(); i++) {
+            const bool wasi = t[i].first.rfind("wasi.", 0) == 0;
+            const std::string fn = wasi ? t[i].first.substr(5) : t[i].first;
+            inst.funcaddrs.push_back(store.emplace_back<function_instance>(name_t(fn), *shapes[t[i].second], &inst,
+                                                                           function_instance::host_code{(index_t)i, wasi ? "wasi_snapshot_preview1" : "env", fn}));
+        }
         for (size_t k = 0; k < functions.size(); k++) {
             function_kind kind(functions[k].params, functions[k].results);
             inst.types.push_back(kind);
@@ -148,6 +159,7 @@ struct tiny_module {
                 store.datas[i].data.clear();
             }
         }
+        if (table) inst.tableaddrs.push_back(store.emplace_back<table_instance>(table_kind{value_kind::funcref, limits((u32)table->size())}, *table));
         // globals as instantiate() creates them (include/runtime.hpp:428-456): i32 / i64, holding a native number
         for (const auto &g : globals) {
             if (g.first == value_kind::i32) inst.globaladdrs.push_back(store.emplace_back<global_instance>(g.first, (u32)g.second));
@@ -295,6 +307,7 @@ static std::vector<instr_ptr> assemble_until(const std::vector<wasm_token> &toks
             else throw std::runtime_error("unknown token " + t.op);
             continue;
         }
+        if (t.op == "call_indirect") { flush(); body.push_back(make_instr<call_indirect>((index_t)0, (index_t)0)); continue; }   // (the type index is not read at run time)
         if (t.op == "global.get") { plain(opcode(opcode::global_get, (index_t)t.imm)); continue; }
         if (t.op == "global.set") { plain(opcode(opcode::global_set, (index_t)t.imm)); continue; }
         const bool typed = t.op.size() > 4 && (t.op.rfind("i32.", 0) == 0 || t.op.rfind("i64.", 0) == 0);
@@ -398,6 +411,15 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
             size_t n; in >> n;
             for (size_t j = 0; j < n; j++) { uint64_t l; in >> l; tok.targets.push_back(l); }
         }
+        if (op == "table") { std::string part; in >> part; tok.imm = std::stoull(part); }          // table <size>
+        if (op == "elem") {                                   // elem <offset> <count> <module function indices, - for null>
+            std::string part; in >> part; tok.imm = std::stoull(part);
+            size_t n; in >> n;
+            for (size_t j = 0; j < n; j++) { in >> part; tok.types.push_back(part); }
+        }
+        if (op == "arg") {                                    // arg public|private <hex or ->: one more argument for wasi args_get
+            for (int j = 0; j < 2; j++) { std::string part; in >> part; tok.types.push_back(part); }
+        }
         if (op == "global") {                                 // global <type> <initial value>
             std::string part; in >> part; tok.types.push_back(part);
             std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0);
@@ -421,6 +443,8 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
     std::vector<tiny_module::module_func> functions;
     std::vector<tiny_module::data_seg> datas;
     std::vector<std::pair<value_kind, uint64_t>> globals;
+    std::vector<reference_t> table;
+    bool has_table = false;
     std::vector<wasm_token> body;
     size_t start = 0;
     u32 pages = 1, max_pages = 0;
@@ -434,6 +458,12 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
             functions.emplace_back();
             functions.back().params = kinds(t.types[0]); functions.back().results = kinds(t.types[1]); functions.back().locals = kinds(t.types[2]);
         } else if (t.op == "start") start = (size_t)t.imm;
+        else if (t.op == "arg") continue;
+        else if (t.op == "table") { has_table = true; table.assign((size_t)t.imm, std::nullopt); }
+        else if (t.op == "elem") {                            // what table_init leaves after instantiation (include/runtime.hpp:518-536): function addresses = indices here
+            for (size_t j = 0; j < t.types.size(); j++)
+                table.at((size_t)t.imm + j) = t.types[j] == "-" ? reference_t{} : reference_t{(index_t)(tiny_module::env_imports().size() + std::stoul(t.types[j]))};
+        }
         else if (t.op == "global") globals.emplace_back(token_kind(t.types[0]), t.imm);
         else if (t.op == "memory") { pages = (u32)std::stoul(t.types[0]); max_pages = (u32)std::stoul(t.types[1]); }
         else if (t.op == "data") {
@@ -447,7 +477,7 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
         else body.push_back(t);
     }
     close();
-    return tiny_module(std::move(functions), start, pages, max_pages, datas, globals);
+    return tiny_module(std::move(functions), start, pages, max_pages, datas, globals, has_table ? &table : nullptr);
 }
 
 template <typename Ctx>
@@ -461,10 +491,21 @@ static void run_wasm_tokens(Ctx &ctx, const std::vector<wasm_token> &toks) {
     dummy->module = &m.inst;
     ctx.set_current_frame(dummy.get());
     ctx.stack_push(std::move(dummy));
+    std::vector<std::vector<u8>> args;
+    std::unordered_set<int> private_indices;
+    for (const wasm_token &t : toks) {
+        if (t.op != "arg") continue;
+        if (t.types[0] == "private") private_indices.insert((int)args.size());
+        std::vector<u8> bytes;
+        const std::string &hx = t.types[1];
+        if (hx != "-") for (size_t i = 0; i + 1 < hx.size(); i += 2) bytes.push_back((u8)std::stoul(hx.substr(i, 2), nullptr, 16));
+        args.push_back(bytes);
+    }
+    ctx.template add_host_module<wasi_preview1_module<Ctx>>(&ctx, args, private_indices);
     ctx.template add_host_module<env_module<Ctx>>(&ctx);
     ctx.template add_host_module<vbn254fr_module<Ctx>>(&ctx);
     auto result = interp.run(call{m.inst.exports["_start"]});
-    if (result.is_exit()) throw std::runtime_error("program exited");
+    if (result.is_exit()) std::cerr << "Exit with code " << result.exit_code() << std::endl;      // as invoke() does: the run ends, the stage goes on
     ctx.stack_pop();
     ctx.finalize();
 }

@@ -94,8 +94,8 @@ def wat_module(text):
     mod = _sexpr(text)
     imports, funcs = {}, []
     for f in mod[1:]:
-        if f[0] == "import":
-            imports[f[3][1]] = (f[2].strip('"'), len(imports))
+        if f[0] == "import":                                   # functions of wasi_snapshot_preview1 are named "wasi.<function>"
+            imports[f[3][1]] = (("wasi." if f[1] == '"wasi_snapshot_preview1"' else "") + f[2].strip('"'), len(imports))
     for f in mod[1:]:
         if f[0] != "func":
             continue
@@ -384,13 +384,16 @@ def wat_to_tokens(text):
     return out
 
 
-def run_reference_on_wat(text, k, seed_byte=7):
-    """the reference's interpreter / backend / stage contexts over the CPU oracle on a program of the subset -> raw dict"""
+def run_reference_on_wat(text, k, seed_byte=7, args=None, private_indices=()):
+    """the reference's interpreter / backend / stage contexts over the CPU oracle on a program of the subset -> raw dict.
+    args: the guest's argument byte strings (for its wasi_preview1 module), private_indices: the secret ones"""
     import subprocess
     import tempfile
     with tempfile.TemporaryDirectory() as tmp:
         ops = os.path.join(tmp, "prog.ops")
         with open(ops, "w") as f:
+            for i, a in enumerate(args or ()):
+                f.write("arg %s %s\n" % ("private" if i in private_indices else "public", bytes(a).hex() or "-"))
             f.write("\n".join(wat_to_tokens(text)) + "\n")
         out = os.path.join(tmp, "out.json")
         subprocess.check_call([REF_BIN_CPU, "ops:" + ops, str(k), out, str(seed_byte)], stdout=subprocess.DEVNULL)
@@ -698,7 +701,7 @@ def wat_to_plain(text):
     by_index = {index: fid for fid, (_, index) in imports.items()}
     memory, datas = wat_memory(text)
     data_ids = {d[0]: k for k, d in enumerate(datas) if d[0]}
-    out = ["(module"] + ['(import "env" "%s" (func %s))' % (nm, fid) for fid, (nm, _) in imports.items()]
+    out = ["(module"] + ['(import "%s" "%s" (func %s))' % ("wasi_snapshot_preview1" if nm.startswith("wasi.") else "env", nm.split(".")[-1], fid) for fid, (nm, _) in imports.items()]
     globals_ = wat_globals(text)
     global_ids = {g[0]: k for k, g in enumerate(globals_) if g[0]}
     for _, ty, mut, init in globals_:

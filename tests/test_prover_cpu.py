@@ -334,7 +334,7 @@ def test_wat_emitter_on_the_repo_fixture(pr, oracle):
 
 def test_wat_emitter_rejects_what_it_does_not_support(pr):
     for text, why in (("(module (func $f) (export \"_start\" (func $f)) (table 1 funcref))", "module field"),
-                      ("(module (import \"wasi\" \"x\" (func $x)) (func $f) (export \"_start\" (func $f)))", "env host module"),
+                      ("(module (import \"wasi\" \"x\" (func $x)) (func $f) (export \"_start\" (func $f)))", "host modules are supported"),
                       ("(module (func $f (drop (f64.fma (f64.const 1) (f64.const 2)))) (export \"_start\" (func $f)))", "unsupported instruction"),
                       ("(module (func $f (drop (ref.null func))) (export \"_start\" (func $f)))", "unsupported instruction"),
                       ("(module (func $f (drop (i64.load (i32.const 0)))) (export \"_start\" (func $f)))", "without a memory"),
@@ -650,3 +650,32 @@ def test_floating_point_and_globals_front_end(pr):
             pr.wat_emit(head + bad + tail, 64)
     with pytest.raises(pr.ProverError, match="only i32 and i64 globals"):
         pr.wat_emit('(module (global $f f32 (f32.const 1)) (func $t) (export "_start" (func $t)))', 64)
+
+
+def test_guest_arguments_and_wasi_front_end(pr):
+    """the argument strings of the reference's JSON configuration (src/webgpu_prover.cpp:110-147), the instance hash folded
+    from the public ones (:160-168), and what the WASI front end refuses"""
+    import hashlib
+    args = pr.config_args([{"i64": -2}, {"str": "abc"}, {"hex": "0x123"}, {"hex": "ff00"}])
+    assert args == [b"Ligero\0", b"\xfe" + b"\xff" * 7, b"abc\0", b"\x01\x23", b"\xff\x00"]
+    want = bytes(32)
+    for i, a in enumerate(args):
+        if i not in (1, 3):
+            want = hashlib.sha256(want + a).digest()
+    assert pr.wat_instance_hash(args, (1, 3)) == want
+    assert pr.wat_instance_hash(None) == bytes(32) and pr.wat_instance_hash([b"x"], (0,)) == bytes(32)
+    head = ('(module (import "wasi_snapshot_preview1" "args_get" (func $args (param i32 i32) (result i32)))\n'
+            '(import "wasi_snapshot_preview1" "proc_exit" (func $exit (param i32)))\n(import "env" "i32_private_const" (func $pc (param i32) (result i32)))\n(memory 1)\n(func $t\n')
+    tail = ')\n(export "_start" (func $t)))\n'
+    _, _, _, _, st, code = pr.wat_emit(head + "(drop (call $args (i32.const 0) (i32.const 64)))\n(drop (i32.load8_u (i32.const 66)))\n(call $exit (i32.const 0))\n(unreachable)" + tail,
+                                       64, args=[b"ab", b"cdef"], private_indices=[1], want_exit_code=True)
+    assert code == 0 and st["linear_witnesses"] == 1            # one byte of the private argument was loaded: one witness
+    for body, why in (("(drop (call $args (call $pc (i32.const 0)) (i32.const 64)))", "WASI call takes concrete operands"),
+                      ("(drop (call $args (i32.const 65532) (i32.const 64)))", "reaches outside the memory"),
+                      ("(drop (call $args (i64.const 0) (i32.const 64)))", "type mismatch")):
+        with pytest.raises(pr.ProverError, match=why):
+            pr.wat_emit(head + body + tail, 64, args=[b"ab", b"cdef"])
+    with pytest.raises(pr.ProverError, match="environ_get is not supported"):
+        pr.wat_emit('(module (import "wasi_snapshot_preview1" "environ_get" (func $e (param i32 i32) (result i32))) (memory 1) (func $t (drop (call $e (i32.const 0) (i32.const 0)))) (export "_start" (func $t)))', 64)
+    with pytest.raises(pr.ProverError, match="env and wasi_snapshot_preview1"):
+        pr.wat_emit('(module (import "bn254fr" "bn254fr_alloc" (func $e (param i32))) (func $t) (export "_start" (func $t)))', 64)

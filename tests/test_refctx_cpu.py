@@ -477,6 +477,47 @@ def test_wat_emitter_on_the_reference_floating_point_programs(oracle, pr, name):
         pr.wat_emit(broken, 64, bytes(32))
 
 
+def _fixture_args(st):
+    return [bytes.fromhex(a) for a in st["fx"]["args"]], st["fx"]["private_indices"]
+
+
+def test_wat_emitter_reproduces_the_reference_rows_for_a_guest_with_arguments(pr):
+    """tests/golden/wasi_args.wat with {"args": [{"i64": 400}, {"i64": 600}, {"str": "hello"}], "private-indices": [1, 3]}: the
+    guest fetches its arguments through wasi args_sizes_get / args_get, the bytes of the private ones are marked in memory and
+    loads that touch them commit witnesses (even one that straddles a public and a private argument); it prints through
+    fd_write, reads the reference's constant-seeded random bytes and leaves through proc_exit from inside a call with
+    witnesses alive on the stack and in locals.  Rows, coefficient rows and const_sum are those of the reference run
+    (its interpreter + wasi_preview1 / env modules: tests/golden/refctx_wasi_k256.json), in all three spellings"""
+    st = U.load("wasi_k256")
+    args, private = _fixture_args(st)
+    assert args == pr.config_args([{"i64": 400}, {"i64": 600}, {"str": "hello"}])
+    text = open(os.path.join(U.HERE, "golden", "wasi_args.wat")).read()
+    for spelling in (text, U.wat_to_wasm(text), U.wat_to_plain(text)):
+        kinds, vals, coefs, const_sum, stats, code = pr.wat_emit(spelling, st["l"], bytes.fromhex(st["fx"]["stage1_seed"]), args=args, private_indices=private,
+                                                               want_exit_code=True)
+        assert list(kinds) == list(st["kinds"]) and np.array_equal(vals, st["values"]) and np.array_equal(coefs, st["coefs"])
+        assert const_sum == st["const_sum"] and stats["violated_constraints"] == 0 and code == 3
+    # with other private indices other rows exist: nothing private -> the loads are numbers and far fewer witnesses are committed
+    kinds_pub, _, _, _, stats_pub = pr.wat_emit(text, st["l"], args=args, private_indices=())
+    assert stats_pub["violated_constraints"] == 0 and len(kinds_pub) < len(st["kinds"])
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("private", [(), (1,), (2, 3), (0, 1, 2, 3)])
+def test_wat_emitter_wasi_arguments_against_the_reference(oracle, pr, private):
+    """live differential of the same guest with other arguments and other choices of the private ones (argv[0] included)"""
+    import random
+    rng = random.Random(77 + len(private))
+    a = rng.randrange(1000)
+    args = [b"Ligero\0", a.to_bytes(8, "little"), (1000 - a).to_bytes(8, "little"), b"hello\0"]
+    text = open(os.path.join(U.HERE, "golden", "wasi_args.wat")).read()
+    raw = U.run_reference_on_wat(text, 256, seed_byte=5, args=args, private_indices=private)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    kinds, vals, coefs, const_sum, stats = pr.wat_emit(text, st["l"], bytes.fromhex(st["fx"]["stage1_seed"]), args=args, private_indices=private)
+    assert list(kinds) == list(st["kinds"]) and np.array_equal(vals, st["values"]) and np.array_equal(coefs, st["coefs"]) and const_sum == st["const_sum"]
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
