@@ -2003,10 +2003,19 @@ private:
             const sexpr &f = *bodies[k];
             func_t &fn = funcs_[k];
             size_t i = (f.list.size() >= 2 && !f.list[1].is_list) ? 2 : 1;
+            int64_t typed = -1;
             for (; i < f.list.size() && f.list[i].is_list; i++) {
                 const sexpr &e = f.list[i];
                 const std::string &h = e.head();
-                if (h == "type") continue;
+                if (h == "type") {                             // (func $f (type $t) ...): the signature is the type's; a (param ..) / (result ..) list after it repeats it
+                    if (e.list.size() != 2 || e.list[1].is_list || typed >= 0 || !fn.locals.empty() || !fn.results.empty()) throw std::invalid_argument("wat: malformed function header");
+                    const std::string &id = e.list[1].atom;
+                    const auto it = type_ids.find(id);
+                    const uint64_t t = it != type_ids.end() ? it->second : ((!id.empty() && id[0] >= '0' && id[0] <= '9') ? parse_i64(id) : ~0ULL);
+                    if (t >= sigs_.size()) throw std::invalid_argument("wat: unknown type " + id);
+                    typed = (int64_t)t;
+                    continue;
+                }
                 if (h != "param" && h != "result" && h != "local") break;
                 if (h != "param" && fn.locals.size() < fn.params.size()) throw std::invalid_argument("wat: malformed function header");
                 size_t j = 1;
@@ -2019,6 +2028,14 @@ private:
                 }
             }
             first_instr[k] = i;
+            if (typed >= 0) {
+                const sig_t &sg = sigs_[(size_t)typed];
+                if (fn.params.empty() && fn.results.empty()) {   // the parameters come before the declared locals: named locals move up
+                    fn.params = sg.params; fn.results = sg.results;
+                    fn.locals.insert(fn.locals.begin(), sg.params.begin(), sg.params.end());
+                    for (auto &named : local_ids[k]) named.second += sg.params.size();
+                } else if (fn.params != sg.params || fn.results != sg.results) throw std::invalid_argument("wat: a function header disagrees with its type");
+            }
         }
         // element segments: (elem [$id] [(table ..)] (offset? (i32.const n)) [func] $f ...) writes functions into the table at instantiation
         const text_scope names{imports, func_ids, data_ids, global_ids, type_ids, {}};

@@ -101,16 +101,18 @@ def wat_module(text):
             continue
         fn = {"id": f[1] if isinstance(f[1], str) else None, "params": [], "results": [], "locals": [], "names": {}, "body": []}
         for e in f[2 if fn["id"] else 1:]:
-            if isinstance(e, list) and e[0] in ("param", "local"):
+            if isinstance(e, list) and e[0] in ("param", "local") and not fn["body"]:
                 rest = e[1:]
                 if len(rest) == 2 and rest[0].startswith("$"):
                     fn["names"][rest[0]] = len(fn["params"]) + len(fn["locals"])
                     rest = rest[1:]
                 fn["params" if e[0] == "param" else "locals"].extend(rest)
-            elif isinstance(e, list) and e[0] == "result":
+            elif isinstance(e, list) and e[0] == "result" and not fn["body"]:
                 fn["results"].extend(e[1:])
-            elif isinstance(e, list) and e[0] == "type":
-                pass
+            elif isinstance(e, list) and e[0] == "type" and not fn["body"]:          # (func $f (type $t) ...): the signature comes from the type
+                sig = next(([t for part in ty[2][1:] if part[0] == "param" for t in part[1:]], [t for part in ty[2][1:] if part[0] == "result" for t in part[1:]])
+                           for ty in mod[1:] if ty[0] == "type" and ty[1] == e[1])
+                fn["params"], fn["results"] = list(sig[0]), list(sig[1])
             else:
                 fn["body"].append(e)
         funcs.append(fn)
@@ -159,6 +161,21 @@ def _lit(s):
     return int(s.replace("_", ""), 0) % (1 << 64)
 
 
+def wat_tables(text):
+    """(named types {id: (params, results)}, table size or None, [(offset, [function ids])]) of a module"""
+    types, table, elems = {}, None, []
+    for f in _sexpr(text)[1:]:
+        if f[0] == "type":
+            sig = ([t for part in f[2][1:] if part[0] == "param" for t in part[1:]], [t for part in f[2][1:] if part[0] == "result" for t in part[1:]])
+            types[f[1]] = sig
+        elif f[0] == "table":
+            table = int(next(x for x in f[1:] if isinstance(x, str) and x[0].isdigit()))
+        elif f[0] == "elem":
+            off = f[1][1] if f[1][0] == "offset" else f[1]
+            elems.append((_lit(off[1]) % (1 << 32), [x for x in f[2:] if x != "func"]))
+    return types, table, elems
+
+
 def float_bits(lit, single):
     """bit pattern of an fNN.const literal: decimal / hexadecimal floating point, inf, nan, nan:0x<payload>"""
     import struct
@@ -198,7 +215,7 @@ def wat_globals(text):
     return out
 
 
-def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None):
+def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None, types=None):
     """post-order walk of a function's body (folded forms, plain instructions, or both mixed): visit(kind, name, immediate)"""
     data_ids = data_ids or {}
     global_ids = global_ids or {}
@@ -219,6 +236,16 @@ def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None):
             part = rest.pop(0)
             (params if part[0] == "param" else results).extend(part[1:])
         return name, params, results
+
+    def type_use(parts):
+        """(type $t) and / or (param ..) (result ..) -> (params, results)"""
+        params, results = [], []
+        for part in parts:
+            if part[0] == "type":
+                params, results = types[part[1]]
+            else:
+                (params if part[0] == "param" else results).extend(part[1:])
+        return list(params), list(results)
 
     def is_label(x):
         return isinstance(x, str) and (x.startswith("$") or x[0].isdigit())
@@ -247,6 +274,9 @@ def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None):
                 n = i
                 if e == "br_table":
                     while n < len(items) and is_label(items[n]):
+                        n += 1
+                elif e == "call_indirect":
+                    while n < len(items) and isinstance(items[n], list) and items[n][0] in ("type", "param", "result"):
                         n += 1
                 elif e[3:] in (".const",) or e in ("local.get", "local.set", "local.tee", "global.get", "global.set", "call", "br", "br_if", "memory.init", "data.drop"):
                     n += 1
@@ -310,6 +340,12 @@ def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None):
                 visit("host", imports[e[1]][0], imports[e[1]][1])
             else:
                 visit("callf", e[1], ids[e[1]])
+        elif h == "call_indirect":
+            use = [a for a in e[1:] if isinstance(a, list) and a[0] in ("type", "param", "result")]
+            for a in e[1:]:
+                if a not in use:
+                    emit(a)
+            visit("indirect", h, type_use(use))
         elif h in ("local.get", "local.set", "local.tee"):
             for a in e[2:]:
                 emit(a)
@@ -350,6 +386,11 @@ def wat_to_tokens(text):
     globals_ = wat_globals(text)
     global_ids = {g[0]: k for k, g in enumerate(globals_) if g[0]}
     out = ["global %s %d" % (ty, init) for _, ty, _, init in globals_]
+    types, table, elems = wat_tables(text)
+    if table is not None:
+        out.append("table %d" % table)
+    for off, fs in elems:
+        out.append("elem %d %d %s" % (off, len(fs), " ".join(str(ids[f]) for f in fs)))
     if memory:
         out.append("memory %d %d" % memory)
     for _, active, offset, data in datas:
@@ -362,6 +403,8 @@ def wat_to_tokens(text):
             out.append("%s %d" % (name, imm[0]))
         elif kind == "global":
             out.append("%s %d" % (name, imm))
+        elif kind == "indirect":
+            out.append(name)
         elif kind == "host":
             out.append("call:" + name)
         elif kind == "callf":
@@ -378,7 +421,7 @@ def wat_to_tokens(text):
     for fn in funcs:
         if structured:
             out.append("func %s %s %s" % tuple(",".join(fn[key]) or "-" for key in ("params", "results", "locals")))
-        _walk(fn, imports, ids, visit, data_ids, global_ids)
+        _walk(fn, imports, ids, visit, data_ids, global_ids, types)
     if structured:
         out.append("start %d" % start)
     return out
@@ -607,6 +650,7 @@ def wat_to_wasm(text, custom_section=True):
     data_ids = {d[0]: k for k, d in enumerate(datas) if d[0]}
     globals_ = wat_globals(text)
     global_ids = {g[0]: k for k, g in enumerate(globals_) if g[0]}
+    named_types, table, elems = wat_tables(text)
     access = ["i32.load", "i64.load", "f32.load", "f64.load", "i32.load8_s", "i32.load8_u", "i32.load16_s", "i32.load16_u", "i64.load8_s", "i64.load8_u", "i64.load16_s",
               "i64.load16_u", "i64.load32_s", "i64.load32_u", "i32.store", "i64.store", "f32.store", "f64.store", "i32.store8", "i32.store16", "i64.store8", "i64.store16", "i64.store32"]
     vt = {"i32": 0x7f, "i64": 0x7e, "f32": 0x7d, "f64": 0x7c}
@@ -638,6 +682,8 @@ def wat_to_wasm(text, custom_section=True):
                 code.extend(b"\x43" + imm[0].to_bytes(4, "little") if nm == "f32.const" else b"\x44" + imm[0].to_bytes(8, "little"))
             elif kind == "global":
                 code.extend(bytes([0x23 if nm == "global.get" else 0x24]) + _uleb(imm))
+            elif kind == "indirect":
+                code.extend(b"\x11" + _uleb(typeidx(*imm)) + b"\x00")
             elif nm in _FLOAT_OPS:
                 code.extend(_FLOAT_OPS[nm])
             elif kind == "host":
@@ -671,7 +717,7 @@ def wat_to_wasm(text, custom_section=True):
             else:
                 w, op = nm[:3], nm[4:]
                 code.append((0x45 if w == "i32" else 0x50) + _CMP_OPS.index(op) if op in _CMP_OPS else (0x67 if w == "i32" else 0x79) + _INT_OPS.index(op))
-        _walk(fn, imports, ids, visit, data_ids, global_ids)
+        _walk(fn, imports, ids, visit, data_ids, global_ids, named_types)
         code.append(0x0B)
         body = vec([_uleb(1) + bytes([vt[t]]) for t in fn["locals"]]) + bytes(code)
         bodies.append(_uleb(len(body)) + body)
@@ -679,12 +725,16 @@ def wat_to_wasm(text, custom_section=True):
     out += section(1, vec([b"\x60" + vec([bytes([t]) for t in p]) + vec([bytes([t]) for t in r]) for p, r in types]))
     out += section(2, vec([name(m) + name(f) + b"\x00" + _uleb(t) for m, f, t in import_list]))
     out += section(3, vec([_uleb(t) for t in func_types]))
+    if table is not None:
+        out += section(4, vec([b"\x70\x00" + _uleb(table)]))
     if memory:
         out += section(5, vec([(b"\x01" + _uleb(memory[0]) + _uleb(memory[1])) if memory[1] else (b"\x00" + _uleb(memory[0]))]))
     if globals_:
         out += section(6, vec([bytes([vt[ty], int(mut), 0x41 if ty == "i32" else 0x42]) + _sleb(init - (1 << int(ty[1:])) if init >> (int(ty[1:]) - 1) else init) + b"\x0b"
                                for _, ty, mut, init in globals_]))
     out += section(7, vec([name("_start") + b"\x00" + _uleb(len(import_list) + start)]))
+    if elems:
+        out += section(9, vec([b"\x00\x41" + _sleb(off) + b"\x0b" + vec([_uleb(len(import_list) + ids[f]) for f in fs]) for off, fs in elems]))
     if datas:
         out += section(12, _uleb(len(datas)))
     out += section(10, vec(bodies))
@@ -706,6 +756,11 @@ def wat_to_plain(text):
     global_ids = {g[0]: k for k, g in enumerate(globals_) if g[0]}
     for _, ty, mut, init in globals_:
         out.append("(global %s (%s.const %d))" % ("(mut %s)" % ty if mut else ty, ty, init))
+    named_types, table, elems = wat_tables(text)
+    if table is not None:
+        out.append("(table %d funcref)" % table)
+    for off, fs in elems:
+        out.append("(elem (i32.const %d) func %s)" % (off, " ".join(fs)))
     if memory:
         out.append("(memory %d%s)" % (memory[0], " %d" % memory[1] if memory[1] else ""))
     for _, active, off, data in datas:
@@ -722,6 +777,8 @@ def wat_to_plain(text):
                 body.append("%s %s" % (nm, imm[1]))
             elif kind == "global":
                 body.append("%s %d" % (nm, imm))
+            elif kind == "indirect":
+                body.append("call_indirect%s%s" % ("".join(" (param %s)" % t for t in imm[0]), "".join(" (result %s)" % t for t in imm[1])))
             elif kind == "host":
                 body.append("call %s" % by_index.get(imm))
             elif kind == "callf":
@@ -736,7 +793,7 @@ def wat_to_plain(text):
                 body.append("%s %s" % (nm, " ".join(map(str, imm))))
             else:
                 body.append(nm)
-        _walk(fn, imports, ids, visit, data_ids, global_ids)
+        _walk(fn, imports, ids, visit, data_ids, global_ids, named_types)
         out.append(head + "\n" + "\n".join(body) + "\n)")
     out.append('(export "_start" (func %s)))' % (funcs[start]["id"] or "$f%d" % start))
     return "\n".join(out) + "\n"

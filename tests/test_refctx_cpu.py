@@ -518,6 +518,22 @@ def test_wat_emitter_wasi_arguments_against_the_reference(oracle, pr, private):
     assert list(kinds) == list(st["kinds"]) and np.array_equal(vals, st["values"]) and np.array_equal(coefs, st["coefs"]) and const_sum == st["const_sum"]
 
 
+INDIRECT_PROGRAM = open(os.path.join(U.HERE, "golden", "indirect.wat")).read()
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+def test_wat_emitter_indirect_calls_against_the_reference(oracle, pr):
+    """call_indirect through a function table filled by element segments (run_call_indirect, interpreter.hpp:372-398): a
+    dispatch loop over add / mul / sub with a witness accumulator, an indirect call inside an indirectly called function, type
+    uses by name and inline, functions declared by (type $t); same rows through the reference's interpreter and the emitter
+    in all three spellings (the binary carries table and element sections)"""
+    raw = U.run_reference_on_wat(INDIRECT_PROGRAM, 256, seed_byte=6)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    for spelling in (INDIRECT_PROGRAM, U.wat_to_wasm(INDIRECT_PROGRAM), U.wat_to_plain(INDIRECT_PROGRAM)):
+        _emitter_equals_reference_rows(pr, spelling, st)
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
