@@ -117,21 +117,24 @@ typedef struct {
 int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
 
 /* ---- interpreter boundary (BASELINE config 4) ------------------------------------------
- * A front end for integer programs (control flow, locals, functions, linear memory) over the env host module and the witness emitter behind it
+ * A front end for WebAssembly programs over the env and wasi_snapshot_preview1 host modules and the witness emitter behind it
  * (host/wat_emitter.hpp).  `wat` is WebAssembly text (folded like the .wat files under the reference's tests/, or plain) or a WebAssembly
  * binary (it starts with "\0asm"): the reference's prover takes both (src/webgpu_prover.cpp:189-207).  Supported: every
  * integer instruction the reference implements (interpreter_impl.hpp:155-1309: const, add sub mul, div / rem, and or xor,
  * shifts and rotates, comparisons, clz ctz popcnt, extend / wrap; 32 and 64 bits), select, drop, nop, local.get / set / tee,
  * calls of the module's own functions, linear memory (loads / stores of every width, memory.size / grow / fill / copy / init,
- * data.drop, data segments), and env.i32_private_const,
- * i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast_u32 / _u64, assert_is_concrete.
- * Not supported (LGRP error naming the construct): globals, tables, floating point, other host modules.
+ * data.drop, data segments), structured control flow (block / loop / if / br / br_if / br_table / return / unreachable), i32 / i64
+ * globals, f32 / f64 arithmetic and conversions (numbers only, as in the reference), call_indirect through a function table, and
+ * env.i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast_u32 / _u64,
+ * assert_is_concrete; wasi args_sizes_get, args_get, fd_write, proc_exit, random_get (lgrp_wat_args below).
+ * Not supported (LGRP error naming the construct): the bn254fr / vbn254fr / uint256 / ecc host modules, table instructions other
+ * than call_indirect, passive element segments.
  * It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under include/zkp/backend/ stand in
  * the reference.  It is not a general WASM machine, but for what it takes it gives every instruction the reference's
  * meaning -- the same witnesses, released in the same order, with the same linear-test randomness -- so the rows, the
  * stage-2 coefficient rows and const_sum are the reference's, element for element: checked against runs of the
- * reference's own interpreter / env module / backend / witness manager (tests/refctx/ref_contexts.cpp,
- * tests/golden/refctx_*.json, tests/test_refctx_cpu.py) on all 65 integer programs of its tests/ and on random programs. */
+ * reference's own interpreter / env and WASI modules / backend / witness manager (tests/refctx/ref_contexts.cpp,
+ * tests/golden/refctx_*.json, tests/test_refctx_cpu.py) on all 69 programs of its tests/ and on random programs. */
 typedef struct {
     uint64_t private_consts, asserts, arithmetic_ops;
     uint64_t linear_witnesses, quadratic_slots, linear_constraints;

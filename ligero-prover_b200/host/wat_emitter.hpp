@@ -1,12 +1,16 @@
-// Interpreter boundary (BASELINE config 4): a front end for integer programs over the env host
-// module -- WebAssembly text (folded, as the reference's tests/*.wat are written, or plain) and WebAssembly binaries, both of
-// which the reference's prover takes (src/webgpu_prover.cpp:189-207) -- and the witness machine behind it.
-// It is NOT the reference's interpreter (include/interpreter_impl.hpp + include/zkp/backend/*.hpp: a general WASM machine with
-// globals, tables and floating point over an expression-template backend; those stay out of scope).  For the instructions it
-// takes -- every integer instruction the reference implements (interpreter_impl.hpp:155-1309), select, drop, nop, locals, structured control flow,
-// calls of the module's own functions, linear memory (loads, stores, memory.size / grow / fill / copy / init, data segments), and the env
-// functions iNN_private_const / assert_equal / assert_zero / assert_one / assert_constant / witness_cast / assert_is_concrete
-// (host_modules/env.hpp) -- it gives each one the meaning the reference gives it: which witnesses exist, which draws of the
+// Interpreter boundary (BASELINE config 4): a front end for WebAssembly programs over the env and
+// wasi_snapshot_preview1 host modules -- WebAssembly text (folded, as the reference's tests/*.wat are written, or plain) and
+// WebAssembly binaries, both of which the reference's prover takes (src/webgpu_prover.cpp:189-207) -- and the witness machine
+// behind it.  It stands where the reference's interpreter stands (include/interpreter.hpp, interpreter_impl.hpp over the
+// expression-template backend of include/zkp/backend/*.hpp) without being a translation of it.  What it takes: every integer
+// instruction the reference implements (interpreter_impl.hpp:155-1309), floating point on numbers (:1314-1853), select, drop,
+// nop, locals, i32 / i64 globals, structured control flow, calls of the module's own functions and call_indirect through a
+// function table, linear memory (loads, stores, memory.size / grow / fill / copy / init, data segments), the env functions
+// iNN_private_const / assert_equal / assert_zero / assert_one / assert_constant / witness_cast / assert_is_concrete
+// (host_modules/env.hpp) and wasi args_sizes_get / args_get / fd_write / proc_exit / random_get (host_modules/wasi_preview1.hpp;
+// args_get marks the bytes of the private arguments, which is how secret inputs reach a guest).  The other host modules
+// (bn254fr, vbn254fr, uint256, ecc), table instructions other than call_indirect and passive element segments are refused.
+// It gives each instruction the meaning the reference gives it: which witnesses exist, which draws of the
 // linear stream land on them, and WHEN each one is released into a row.  That order is decided in the reference by C++
 // object lifetimes (a witness is committed when the last shared_ptr to it dies), so the machine below is built from counted
 // handles with the same copy / move / destruction behaviour and its gadgets mirror where the reference creates, copies and
@@ -15,10 +19,11 @@
 // drawn in execution order, so the program is run again once the seed exists (as the reference re-runs it in stage 2).
 //
 // Parity statement: pinned to runs of the reference itself.  tests/refctx/ref_contexts.cpp compiles the reference's own
-// interpreter, env module, backend and witness manager and runs programs through them as token streams; on all 65 integer
-// programs and both memory programs of the reference's tests/ (tests/i64_mul.wat = BASELINE config 4 among them), on the repo's mul64.wat / arith32.wat /
-// intops.wat (tests/golden/refctx_*.json) and on random expression trees over the whole instruction set this emitter produces
-// the same rows, the same coefficient rows and the same const_sum, element for element (tests/test_refctx_cpu.py).
+// interpreter, env and WASI modules, backend and witness manager and runs programs through them as token streams; on all 69
+// programs of the reference's tests/ (tests/i64_mul.wat = BASELINE config 4 among them), on the repo's mul64.wat / arith32.wat /
+// intops.wat / wasi_args.wat (tests/golden/refctx_*.json), indirect.wat and on random programs over the whole instruction set
+// (expression trees, locals and functions, memory, control flow, floating point and globals) this emitter produces the same
+// rows, the same coefficient rows and the same const_sum, element for element (tests/test_refctx_cpu.py).
 // The release order follows the lifetimes of C++ objects as GCC orders them (parameters, temporaries, structured
 // bindings); this file leans on the same rules and is built with the same compiler.
 #pragma once
@@ -504,10 +509,10 @@ inline std::pair<witness_machine::wref, witness_machine::wref> witness_machine::
 }
 
 // ---- front end ------------------------------------------------------------------------------------------------
-// A program is the flat instruction list of its exported `_start` function, read either from WebAssembly text (the folded
-// style of the reference's tests/*.wat, plain instruction sequences too) or from a WebAssembly binary (the other input the
-// reference's prover takes, src/webgpu_prover.cpp:189-207): type, import, function, export and code sections of a module
-// whose `_start` is integer code calling env functions.  No wabt on either path.
+// A program is a module whose functions are flat instruction lists, read either from WebAssembly text (the folded style of
+// the reference's tests/*.wat, plain instruction sequences too) or from a WebAssembly binary (the other input the reference's
+// prover takes, src/webgpu_prover.cpp:189-207): type, import, function, table, memory, global, export, element, code and
+// data sections.  Execution starts at the exported `_start`.  No wabt on either path.
 class wat_program {
 public:
     explicit wat_program(const std::string &data) {
