@@ -306,7 +306,7 @@ int lgrp_prove_wat_args(lgr_ctx *ctx, const char *wat, size_t len, const lgrp_wa
     wat_program prog(std::string(wat, len));
     take_args(prog, args);
     wat_stats ws;
-    row_packer values(l);
+    row_packer values(l, true, false);
     {
         witness_machine m(values, nullptr);                  // stage 1 needs the values only
         prog.set_echo(true);                                 // what the guest prints appears once, not once per stage
@@ -331,12 +331,13 @@ int lgrp_prove_wat_args(lgr_ctx *ctx, const char *wat, size_t len, const lgrp_wa
         st.events.push_back(ev);
     }
     st.coef_provider = [&](const uint8_t seed[32], std::vector<uint32_t> &coef_rows, uint32_t const_sum[8]) {
-        row_packer with_coefs(l);                            // the program again, now drawing the linear-test randomness
+        row_packer with_coefs(l, false, true);               // the program again, now drawing the linear-test randomness
+        with_coefs.reserve_rows(values.rows());
         witness_machine m(with_coefs, seed);
         wat_stats again;
         prog.run(m, again);
         m.finish(const_sum);
-        coef_rows = with_coefs.coefs();
+        coef_rows = with_coefs.take_coefs();
     };
     lgrp_proof *p = new lgrp_proof();
     try {

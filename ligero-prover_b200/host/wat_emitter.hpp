@@ -247,13 +247,13 @@ public:
         if (!(w_[w].val == v)) violated_++;
         const Fr r = draw();
         coef_add(w, r);
-        const_sub(lgr::host::mul(v, r));
+        const_sub(fmul(v, r));
     }
     wid clone_raw(wid w) { const wid c = acquire_raw(w_[w].val); constrain_equal(w, c); return c; }       // clone_witness (:393-397)
 
     // constrain_quadratic (:474-492): slot positions (a, b, c); a witness that already sits in a slot is replaced by a clone
     void constrain_quadratic(wid c, wid a, wid b) {
-        if (!(lgr::host::mul(w_[a].val, w_[b].val) == w_[c].val)) violated_++;
+        if (!(fmul(w_[a].val, w_[b].val) == w_[c].val)) violated_++;
         uint32_t s;
         if (!free_s_.empty()) { s = free_s_.back(); free_s_.pop_back(); slots_[s] = slot{}; }
         else { slots_.push_back(slot{}); s = (uint32_t)slots_.size() - 1; }
@@ -312,7 +312,7 @@ public:
         case expr::AND: {                                     // :537-550, :637-652: operands materialised, slot (x, y, z)
             wref x = eval(*e.a);
             wref y = eval(*e.b);
-            const Fr zv = e.kind == expr::AND ? lgr::host::from_u64(x.val().v[0] & y.val().v[0]) : lgr::host::mul(x.val(), y.val());
+            const Fr zv = e.kind == expr::AND ? lgr::host::from_u64(x.val().v[0] & y.val().v[0]) : fmul(x.val(), y.val());
             const wid z = acquire_raw(zv);
             constrain_quadratic(z, x.id(), y.id());
             return wref(this, z);
@@ -334,18 +334,18 @@ public:
         case expr::WIT: coef_add(e.w.id(), r); return e.w.val();
         case expr::ADD: {
             const Fr x = spread(*e.a, r);
-            if (e.b->kind == expr::CONST) { const_add(mul(e.b->k, r)); return add(x, e.b->k); }
+            if (e.b->kind == expr::CONST) { const_add(fmul(e.b->k, r)); return add(x, e.b->k); }
             const Fr y = spread(*e.b, r);
             return add(x, y);
         }
         case expr::SUB: {
             if (e.a->kind == expr::CONST) {                   // K - x
                 const Fr x = spread(*e.b, neg(r));
-                const_add(mul(e.a->k, r));
+                const_add(fmul(e.a->k, r));
                 return sub(e.a->k, x);
             }
             const Fr x = spread(*e.a, r);
-            if (e.b->kind == expr::CONST) { const_sub(mul(e.b->k, r)); return sub(x, e.b->k); }
+            if (e.b->kind == expr::CONST) { const_sub(fmul(e.b->k, r)); return sub(x, e.b->k); }
             const Fr y = spread(*e.b, neg(r));
             return sub(x, y);
         }
@@ -356,8 +356,8 @@ public:
         }
         case expr::MUL:
             if (e.b->kind == expr::CONST) {                   // x * K: the leaf takes K*r
-                const Fr x = spread(*e.a, mul(e.b->k, r));
-                return mul(x, e.b->k);
+                const Fr x = spread(*e.a, fmul(e.b->k, r));
+                return fmul(x, e.b->k);
             }
             [[fallthrough]];
         case expr::AND: {                                     // a product inside a linear form: its own witness takes r
@@ -435,6 +435,38 @@ public:
     uint64_t linear_released() const { return nlinear_; }
 
     static Fr zero() { return Fr{{0, 0, 0, 0}}; }
+    // a * b mod p.  Most values of an integer program are below 2^64 (bits, bytes, machine words, small constants): their
+    // product is below 2^128 < p and needs no reduction; in the stage-1 run every rho is zero as well
+    static Fr fmul(const Fr &a, const Fr &b) {
+        if (!(a.v[1] | a.v[2] | a.v[3] | b.v[1] | b.v[2] | b.v[3])) {
+            const unsigned __int128 c = (unsigned __int128)a.v[0] * b.v[0];
+            return Fr{{(uint64_t)c, (uint64_t)(c >> 64), 0, 0}};
+        }
+        if (!(a.v[0] | a.v[1] | a.v[2] | a.v[3]) || !(b.v[0] | b.v[1] | b.v[2] | b.v[3])) return zero();
+        // 2^i * rho (bit composition spreads one rho over 32 / 64 bits): the Montgomery form of 2^i comes from a table, one multiplication left
+        const int ia = pow2_index(a), ib = ia < 0 ? pow2_index(b) : -1;
+        if (ia >= 0) return lgr::host::montmul(pow2_mont()[(size_t)ia], b);
+        if (ib >= 0) return lgr::host::montmul(pow2_mont()[(size_t)ib], a);
+        return lgr::host::mul(a, b);
+    }
+    static int pow2_index(const Fr &a) {                      // i if a = 2^i (i < 254), else -1
+        int at = -1;
+        for (int j = 0; j < 4; j++) {
+            if (!a.v[j]) continue;
+            if (at >= 0 || (a.v[j] & (a.v[j] - 1))) return -1;
+            at = 64 * j + __builtin_ctzll(a.v[j]);
+        }
+        return at < 254 ? at : -1;
+    }
+    static const std::vector<Fr> &pow2_mont() {
+        static const std::vector<Fr> table = [] {
+            std::vector<Fr> t;
+            Fr x = lgr::host::from_u64(1);
+            for (int i = 0; i < 254; i++) { t.push_back(lgr::host::to_mont(x)); x = lgr::host::add(x, x); }
+            return t;
+        }();
+        return table;
+    }
     static Fr sub(const Fr &a, const Fr &b) {
         Fr r;
         if (lgr::host::sub4(r.v, a.v, b.v)) lgr::host::add4(r.v, r.v, lgr::host::kP);
@@ -444,7 +476,7 @@ public:
     static Fr shl(const Fr &a, int i) {                       // a * 2^i mod p, i < 254
         Fr p2 = zero();
         p2.v[i >> 6] = 1ULL << (i & 63);
-        return lgr::host::mul(a, p2);
+        return fmul(a, p2);
     }
 
 private:

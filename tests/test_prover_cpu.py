@@ -333,7 +333,7 @@ def test_wat_emitter_on_the_repo_fixture(pr, oracle):
 
 
 def test_wat_emitter_rejects_what_it_does_not_support(pr):
-    for text, why in (("(module (func $f) (export \"_start\" (func $f)) (table 1 funcref))", "module field"),
+    for text, why in (("(module (func $f) (export \"_start\" (func $f)) (start $f))", "module field"),
                       ("(module (import \"wasi\" \"x\" (func $x)) (func $f) (export \"_start\" (func $f)))", "host modules are supported"),
                       ("(module (func $f (drop (f64.fma (f64.const 1) (f64.const 2)))) (export \"_start\" (func $f)))", "unsupported instruction"),
                       ("(module (func $f (drop (ref.null func))) (export \"_start\" (func $f)))", "unsupported instruction"),
@@ -447,7 +447,7 @@ def test_wasm_binary_front_end_rejects_what_it_does_not_support(pr):
     pr.wat_emit(good, 64)
     sec = lambda sid, body: bytes([sid, len(body)]) + body
     for data, why in ((good[:-3], "section runs past the end|unexpected end"),
-                      (good[:8] + sec(4, b"\x01\x70\x00\x01") + good[8:], "unsupported module section"),       # a table
+                      (good[:8] + sec(8, b"\x00") + good[8:], "unsupported module section"),                   # a start section
                       (b"\0asm\x02\0\0\0" + good[8:], "binary version"),
                       (good[:-1] + b"\x28\x0b", "section runs past|unexpected end|unsupported"),
                       (b"\0asm\x01\0\0\0", "_start")):
