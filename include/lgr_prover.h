@@ -118,7 +118,7 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
 
 /* ---- interpreter boundary (BASELINE config 4) ------------------------------------------
  * A front end for WebAssembly programs over the env and wasi_snapshot_preview1 host modules and the witness emitter behind it
- * (host/wat_emitter.hpp).  `wat` is WebAssembly text (folded like the .wat files under the reference's tests/, or plain) or a WebAssembly
+ * (host/wat_emitter.hpp, host/witness_machine.hpp).  `wat` is WebAssembly text (folded like the .wat files under the reference's tests/, or plain) or a WebAssembly
  * binary (it starts with "\0asm"): the reference's prover takes both (src/webgpu_prover.cpp:189-207).  Supported: every
  * integer instruction the reference implements (interpreter_impl.hpp:155-1309: const, add sub mul, div / rem, and or xor,
  * shifts and rotates, comparisons, clz ctz popcnt, extend / wrap; 32 and 64 bits), select, drop, nop, local.get / set / tee,
