@@ -1548,8 +1548,11 @@ private:
                 bodies.push_back(&f);
             } else if (f.head() == "export") {
                 if (f.list.size() >= 3 && unquote(f.list[1].atom) == "_start" && f.list[2].head() == "func" && f.list[2].list.size() == 2) start = f.list[2].list[1].atom;
+            } else if (f.head() == "start") {
+                // a start function is NOT run by the reference's instantiate() (include/runtime.hpp:345-604 never reads module.starts): ignored here too
             } else if (f.head() == "memory") {                 // (memory [$id] min [max])
                 size_t j = (f.list.size() >= 2 && !f.list[1].is_list && f.list[1].atom[0] == '$') ? 2 : 1;
+                while (j < f.list.size() && f.list[j].head() == "export") j++;                    // (memory (export "memory") 1): exports other than _start say nothing here
                 if (has_memory_ || j >= f.list.size() || f.list[j].is_list) throw std::invalid_argument("wat: unsupported memory declaration");
                 set_memory(parse_i64(f.list[j].atom), j + 1 < f.list.size() && !f.list[j + 1].is_list ? parse_i64(f.list[j + 1].atom) : 0);
             } else if (f.head() == "data") {                   // (data [$id] "bytes"...) passive; (data [$id] (i32.const off) "bytes"...) active
@@ -1619,6 +1622,11 @@ private:
             for (; i < f.list.size() && f.list[i].is_list; i++) {
                 const sexpr &e = f.list[i];
                 const std::string &h = e.head();
+                if (h == "export") {                           // (func $f (export "name") ...): the inline form of an export
+                    if (e.list.size() != 2 || e.list[1].is_list) throw std::invalid_argument("wat: malformed function header");
+                    if (unquote(e.list[1].atom) == "_start") start = std::to_string(imports.size() + k);
+                    continue;
+                }
                 if (h == "type") {                             // (func $f (type $t) ...): the signature is the type's; a (param ..) / (result ..) list after it repeats it
                     if (e.list.size() != 2 || e.list[1].is_list || typed >= 0 || !fn.locals.empty() || !fn.results.empty()) throw std::invalid_argument("wat: malformed function header");
                     const std::string &id = e.list[1].atom;
@@ -2010,6 +2018,7 @@ private:
             reader s = r.sub((size_t)r.uleb());
             switch (id) {
             case 0: case 12: break;                           // custom / data count: nothing the subset needs
+            case 8: break;                                    // start function: the reference's instantiate() does not run it (include/runtime.hpp never reads module.starts)
             case 5: {                                         // memory: at most one
                 const size_t n = (size_t)s.uleb();
                 if (n > 1 || (n && has_memory_)) throw std::invalid_argument("wasm: more than one memory");

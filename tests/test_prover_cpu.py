@@ -333,7 +333,7 @@ def test_wat_emitter_on_the_repo_fixture(pr, oracle):
 
 
 def test_wat_emitter_rejects_what_it_does_not_support(pr):
-    for text, why in (("(module (func $f) (export \"_start\" (func $f)) (start $f))", "module field"),
+    for text, why in (("(module (func $f) (export \"_start\" (func $f)) (tag $e))", "module field"),
                       ("(module (import \"wasi\" \"x\" (func $x)) (func $f) (export \"_start\" (func $f)))", "host modules are supported"),
                       ("(module (func $f (drop (f64.fma (f64.const 1) (f64.const 2)))) (export \"_start\" (func $f)))", "unsupported instruction"),
                       ("(module (func $f (drop (ref.null func))) (export \"_start\" (func $f)))", "unsupported instruction"),
@@ -447,7 +447,7 @@ def test_wasm_binary_front_end_rejects_what_it_does_not_support(pr):
     pr.wat_emit(good, 64)
     sec = lambda sid, body: bytes([sid, len(body)]) + body
     for data, why in ((good[:-3], "section runs past the end|unexpected end"),
-                      (good[:8] + sec(8, b"\x00") + good[8:], "unsupported module section"),                   # a start section
+                      (good[:8] + sec(13, b"\x00") + good[8:], "unsupported module section"),                  # a tag section
                       (b"\0asm\x02\0\0\0" + good[8:], "binary version"),
                       (good[:-1] + b"\x28\x0b", "section runs past|unexpected end|unsupported"),
                       (b"\0asm\x01\0\0\0", "_start")):
@@ -703,3 +703,13 @@ def test_indirect_call_front_end(pr):
         pr.wat_emit(head.replace("$inc $seven)", "$pc $seven)") + tail, 64)
     with pytest.raises(pr.ProverError, match="needs a table|unknown table"):
         pr.wat_emit('(module (type $v (func)) (func $t (call_indirect (type $v) (i32.const 0))) (export "_start" (func $t)))', 64)
+
+
+def test_start_sections_are_ignored_and_inline_exports_are_read(pr):
+    """the reference's instantiate() never runs a module's start function (include/runtime.hpp reads no module.starts): a
+    program with one commits what _start commits and nothing else; (func (export "_start") ...) is the inline spelling"""
+    body = '(import "env" "i64_private_const" (func $pc (param i64) (result i64)))\n(func $init (drop (call $pc (i64.const 1))))\n'
+    plain = '(module ' + body + '(func $t (drop (call $pc (i64.const 2))))\n(export "_start" (func $t)))'
+    started = '(module ' + body + '(func $t (export "_start") (drop (call $pc (i64.const 2))))\n(start $init))'
+    a, b = pr.wat_emit(plain, 64), pr.wat_emit(started, 64)
+    assert np.array_equal(a[1], b[1]) and a[4] == b[4] and a[4]["private_consts"] == 1
