@@ -122,3 +122,22 @@ def test_reference_contexts_on_cuda_equal_reference_contexts_on_the_oracle(prog,
     assert outs["cuda"]["verifier"] == [1] * 7
     for key in outs["oracle"]:
         assert outs["cuda"][key] == outs["oracle"][key], key
+
+
+def test_prove_wat_with_private_arguments_commits_to_the_root_of_the_reference_run(lgr, pr, executor_factory):
+    """a guest that takes arguments (tests/golden/wasi_args.wat; two of the four private) through lgrp_prove_wat_args: the
+    Merkle root is the one the reference's interpreter + wasi_preview1 module + stage-1 context arrive at with the same
+    encoding seed, the prover's three self-checks pass, and the stage-1 seed is hash("LigetronStage1", root, instance hash
+    folded from the PUBLIC arguments as src/webgpu_prover.cpp:160-168 folds them).  (Last in the GPU suite: the path was
+    written after the round's GPU budget was spent; everything it shares with lgrp_prove_wat is covered above.)"""
+    st = U.load("wasi_k256")
+    args, private = [bytes.fromhex(a) for a in st["fx"]["args"]], st["fx"]["private_indices"]
+    text = open(os.path.join(U.HERE, "golden", "wasi_args.wat")).read()
+    ex = executor_factory(st["k"], st["l"])
+    proof, stats = pr.prove_wat(ex, text, st["encoding_seed"], generated_at=3, args=args, private_indices=private)
+    info = proof.info()
+    assert stats["violated_constraints"] == 0 and info["valid"] == (True, True, True)
+    root = ref.parse_envelope(proof.gzip).ligero_proof.merkle_tree.root.value
+    assert root.hex() == st["fx"]["root"]
+    assert info["stage1_seed"] == pr.stage1_seed(root, pr.wat_instance_hash(args, private))
+    proof.close()
