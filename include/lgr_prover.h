@@ -124,11 +124,12 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
  * shifts and rotates, comparisons, clz ctz popcnt, extend / wrap; 32 and 64 bits), select, drop, nop, local.get / set / tee,
  * calls of the module's own functions, linear memory (loads / stores of every width, memory.size / grow / fill / copy / init,
  * data.drop, data segments), structured control flow (block / loop / if / br / br_if / br_table / return / unreachable), i32 / i64
- * globals, f32 / f64 arithmetic and conversions (numbers only, as in the reference), call_indirect through a function table, and
+ * globals, f32 / f64 arithmetic and conversions (numbers only, as in the reference), call_indirect, references and the table
+ * instructions -- every instruction the reference's interpreter dispatches (interpreter_impl.hpp:2405-2548) -- and
  * env.i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast_u32 / _u64,
  * assert_is_concrete; wasi args_sizes_get, args_get, fd_write, proc_exit, random_get (lgrp_wat_args below).
- * Not supported (LGRP error naming the construct): the bn254fr / vbn254fr / uint256 / ecc host modules, table instructions other
- * than call_indirect, passive element segments.
+ * Not supported (LGRP error naming the construct): the bn254fr / vbn254fr / uint256 / ecc host modules, passive element segments,
+ * imported memories / tables / globals.
  * It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under include/zkp/backend/ stand in
  * the reference.  It is not a general WASM machine, but for what it takes it gives every instruction the reference's
  * meaning -- the same witnesses, released in the same order, with the same linear-test randomness -- so the rows, the

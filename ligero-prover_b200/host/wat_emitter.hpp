@@ -5,11 +5,11 @@
 // expression-template backend of include/zkp/backend/*.hpp) without being a translation of it.  What it takes: every integer
 // instruction the reference implements (interpreter_impl.hpp:155-1309), floating point on numbers (:1314-1853), select, drop,
 // nop, locals, i32 / i64 globals, structured control flow, calls of the module's own functions and call_indirect through a
-// function table, linear memory (loads, stores, memory.size / grow / fill / copy / init, data segments), the env functions
+// function table, references and the table instructions (:1926-2106), linear memory (loads, stores, memory.size / grow / fill / copy / init, data segments), the env functions
 // iNN_private_const / assert_equal / assert_zero / assert_one / assert_constant / witness_cast / assert_is_concrete
 // (host_modules/env.hpp) and wasi args_sizes_get / args_get / fd_write / proc_exit / random_get (host_modules/wasi_preview1.hpp;
 // args_get marks the bytes of the private arguments, which is how secret inputs reach a guest).  The other host modules
-// (bn254fr, vbn254fr, uint256, ecc), table instructions other than call_indirect and passive element segments are refused.
+// (bn254fr, vbn254fr, uint256, ecc) and passive element segments are refused.
 // It gives each instruction the meaning the reference gives it: which witnesses exist, which draws of the
 // linear stream land on them, and WHEN each one is released into a row.  That order is decided in the reference by C++
 // object lifetimes (a witness is committed when the last shared_ptr to it dies), so the machine below is built from counted
@@ -132,6 +132,8 @@ public:
         run_state rs{m, st};
         rs.step_limit = step_limit_;
         for (const global_t &g : globals_) rs.globals.push_back(g.init);
+        rs.table = table_;
+        rs.elems = elem_segs_;
         rs.memory.assign((size_t)mem_pages_ * 65536, 0);
         rs.max_pages = mem_max_;
         for (const data_t &d : datas_) {                      // instantiate (runtime.hpp:537-556): active segments are copied in and dropped
@@ -173,10 +175,10 @@ private:
         ~frame_t() { while (!locals.empty()) locals.pop_back(); }
     };
     struct value {
-        enum kind_t : uint8_t { NUM, WIT, BITS, LABEL, FRAME } kind = NUM;
+        enum kind_t : uint8_t { NUM, WIT, BITS, LABEL, FRAME, REF } kind = NUM;
         bool is64 = false;
         bool isf = false;                                     // NUM: a floating-point number (native_numeric's f32 / f64 tags); `num` holds its bits
-        uint64_t num = 0;                                     // NUM: the number; LABEL: the arity of the block it closes
+        uint64_t num = 0;                                     // NUM: the number; LABEL: the arity of the block it closes; REF: a function index (imports first), ~0 = null
         wref wit;
         bitvec bits;
         std::unique_ptr<frame_t> frame;
@@ -199,6 +201,8 @@ private:
             else if (kind == FRAME) frame = std::move(o.frame);
             return *this;
         }
+        static value ref(int64_t f) { value r; r.kind = REF; r.num = f < 0 ? ~0ULL : (uint64_t)f; return r; }     // reference_t (types.hpp:46)
+        int64_t as_ref() const { return num == ~0ULL ? -1 : (int64_t)num; }
         static value label(uint32_t arity) { value r; r.kind = LABEL; r.num = arity; return r; }
         static value of(std::unique_ptr<frame_t> f) { value r; r.kind = FRAME; r.frame = std::move(f); return r; }
         // local.get / local.tee (interpreter_impl.hpp:1855-1900): another handle on the same witnesses
@@ -254,6 +258,8 @@ private:
         uint32_t max_pages = 0;
         std::vector<frame_t *> frames;                        // current_frame() = frames.back()
         std::vector<uint64_t> globals;
+        std::vector<int64_t> table;                           // table 0 (table.set / grow / fill / copy / init change it)
+        std::vector<std::vector<int64_t>> elems;              // the element segments (elem.drop empties one)
         std::mt19937 rand{1145141919};                        // wasi random_get (wasi_preview1.hpp:47,203-215)
         uint64_t steps = 0, step_limit = 0;
         void push(value v) { stack.push_back(std::move(v)); }
@@ -283,17 +289,20 @@ private:
         }
         // nonbatch_context.hpp:249-316
         uint64_t make_numeric(value s) {
+            if (s.kind == value::REF) throw std::invalid_argument("wat: a reference where a number is needed (the reference traps: Unexpected stack value)");
             if (s.kind == value::NUM) return s.num;
             if (s.kind == value::WIT) return s.wit.val().v[0];
             return witness_machine::bit_compose_constant(s.bits);
         }
         wref make_witness(value s) {
+            if (s.kind == value::REF) throw std::invalid_argument("wat: a reference where a witness is needed (the reference traps: Unexpected stack value)");
             if (s.kind == value::NUM && s.isf) throw std::invalid_argument("wat: a floating-point value where a witness is needed (the reference traps: Unexpected numeric)");
             if (s.kind == value::NUM) return m.acquire(lgr::host::from_u64(s.is64 ? s.as_u64() : s.as_u32()));
             if (s.kind == value::WIT) return std::move(s.wit);
             return m.bit_compose(s.bits);
         }
         bitvec make_decomposed(value s, size_t nbits) {
+            if (s.kind == value::REF) throw std::invalid_argument("wat: a reference where a number is needed (the reference traps: Unexpected stack value)");
             if (s.kind == value::NUM) return m.bit_decompose_constant(s.as_u64(), nbits);
             if (s.kind == value::WIT) return m.bit_decompose(s.wit, nbits);
             return s.bits;
@@ -329,9 +338,10 @@ private:
     }
     static value numeric(bool is64, uint64_t v) { return is64 ? value::u64(v) : value::u32((uint32_t)v); }
     // value types: the integer widths 32 / 64 and, next to them, the two floating-point types
-    static constexpr uint8_t F32 = 33, F64 = 65;
+    static constexpr uint8_t F32 = 33, F64 = 65, FUNCREF = 0x70, EXTERNREF = 0x6F;
     static bool is_float(uint8_t t) { return t == F32 || t == F64; }
-    static std::string type_name(uint8_t t) { return t == 32 ? "i32" : (t == 64 ? "i64" : (t == F32 ? "f32" : (t == F64 ? "f64" : "?"))); }
+    static bool is_ref(uint8_t t) { return t == FUNCREF || t == EXTERNREF; }
+    static std::string type_name(uint8_t t) { return t == 32 ? "i32" : (t == 64 ? "i64" : (t == F32 ? "f32" : (t == F64 ? "f64" : (t == FUNCREF ? "funcref" : (t == EXTERNREF ? "externref" : "?"))))); }
     static size_t bytes_of(uint8_t t) { return (t == 32 || t == F32) ? 4 : 8; }
     static value of_bits(uint8_t t, uint64_t bits) {         // a number of type `t` from its bit pattern
         value r = numeric(t == 64 || t == F64, bits);
@@ -763,7 +773,8 @@ private:
     struct ins {
         enum kind_t : uint8_t { konst, unary_op, shift_op, binary_op, host_call, func_call, local_get, local_set, local_tee, select, drop, nop,
                                 load, store, memory_size, memory_grow, memory_fill, memory_copy, memory_init, data_drop,
-                                block, loop, if_, else_, end, br, br_if, br_table, return_, unreachable, float_op, global_get, global_set, call_indirect } kind;
+                                block, loop, if_, else_, end, br, br_if, br_table, return_, unreachable, float_op, global_get, global_set, call_indirect,
+                                ref_null, ref_is_null, ref_func, table_get, table_set, table_size, table_grow, table_fill, table_copy, table_init, elem_drop } kind;
         uint8_t o = 0;                                        // op, fop or host_fn; bytes moved by a load / store
         uint8_t width = 0;                                    // the value type the instruction computes in (32, 64, F32, F64); conversions: of the result
         bool sgn = false;
@@ -940,13 +951,19 @@ private:
             value v = rs.pop();
             if (v.kind != value::NUM) throw std::invalid_argument("wat: call_indirect takes a concrete index (a witness here ends the reference's run)");
             const uint32_t at = v.as_u32();
-            if (at >= table_.size()) throw std::invalid_argument("wat: call_indirect: index out of bound");
-            if (table_[at] < 0) throw std::invalid_argument("wat: call_indirect: null pointer");
-            const func_t &callee = funcs_[(size_t)table_[at]];
+            if (at >= rs.table.size()) throw std::invalid_argument("wat: call_indirect: index out of bound");
+            if (rs.table[at] < 0) throw std::invalid_argument("wat: call_indirect: null pointer");
+            if ((uint64_t)rs.table[at] < nimports_) throw std::invalid_argument("wat: an indirect call of an imported function is not supported");
+            const size_t target = (size_t)rs.table[at] - nimports_;
+            const func_t &callee = funcs_[target];
             const sig_t &want_sig = sigs_[(size_t)i.imm];       // (the reference leaves this check as a TODO; a mismatch would misread its stack.  WebAssembly traps)
             if (callee.params != want_sig.params || callee.results != want_sig.results) throw std::invalid_argument("wat: call_indirect: indirect call type mismatch");
-            return call((size_t)table_[at], rs, depth + 1);
+            return call(target, rs, depth + 1);
         }
+        case ins::ref_null: case ins::ref_is_null: case ins::ref_func: case ins::table_get: case ins::table_set: case ins::table_size: case ins::table_grow:
+        case ins::table_fill: case ins::table_copy: case ins::table_init: case ins::elem_drop:
+            reference_op(i, rs);
+            break;
         case ins::local_get: rs.push(rs.frames.back()->locals[(size_t)i.imm].share()); break;
         case ins::local_set: rs.frames.back()->locals[(size_t)i.imm] = rs.pop(); break;
         case ins::local_tee: rs.frames.back()->locals[(size_t)i.imm] = rs.stack.back().share(); break;
@@ -1029,6 +1046,68 @@ private:
         rs.drop_n_below(distance - n + 1, n);
         flow r; r.kind = flow::jump; r.label = l;
         return r;
+    }
+    // references and the table (interpreter_impl.hpp:1926-2106): a reference is a function index or null; indices and counts are
+    // read with as_u32(), references with as_ref() -- anything else on the stack ends the reference's run
+    static int64_t pop_ref(run_state &rs, const char *what) {
+        value v = rs.pop();
+        if (v.kind != value::REF) throw std::invalid_argument(std::string("wat: ") + what + " takes a reference");
+        return v.as_ref();
+    }
+    static void reference_op(const ins &i, run_state &rs) {
+        const auto index = [&](const char *what) { return pop_number(rs, what).as_u32(); };
+        std::vector<int64_t> &tab = rs.table;
+        switch (i.kind) {
+        case ins::ref_null: rs.push(value::ref(-1)); break;
+        case ins::ref_is_null: rs.push(value::u32(pop_ref(rs, "ref.is_null") < 0)); break;
+        case ins::ref_func: rs.push(value::ref((int64_t)i.imm)); break;
+        case ins::table_get: {
+            const uint32_t at = index("table.get");
+            if (at >= tab.size()) throw std::invalid_argument("wat: table_get: index out of range");
+            rs.push(value::ref(tab[at]));
+            break;
+        }
+        case ins::table_set: {
+            const int64_t r = pop_ref(rs, "table.set");
+            const uint32_t at = index("table.set");
+            if (at >= tab.size()) throw std::invalid_argument("wat: table_set: index out of range");
+            tab[at] = r;
+            break;
+        }
+        case ins::table_size: rs.push(value::u32((uint32_t)tab.size())); break;
+        case ins::table_grow: {                               // (:1997-2019) no maximum is consulted: it grows until memory runs out (capped here)
+            const uint32_t n = index("table.grow");
+            const int64_t r = pop_ref(rs, "table.grow");
+            if ((uint64_t)tab.size() + n > 1000000) { rs.push(value::u32(0xFFFFFFFFu)); break; }
+            rs.push(value::u32((uint32_t)tab.size()));
+            tab.insert(tab.end(), n, r);
+            break;
+        }
+        case ins::table_fill: {
+            const uint32_t n = index("table.fill");
+            const int64_t r = pop_ref(rs, "table.fill");
+            const uint32_t at = index("table.fill");
+            if ((uint64_t)at + n > tab.size()) throw std::invalid_argument("wat: table_fill: index out of bound");
+            std::fill_n(tab.begin() + at, n, r);
+            break;
+        }
+        case ins::table_copy: {
+            const uint32_t n = index("table.copy"), src = index("table.copy"), dst = index("table.copy");
+            if ((uint64_t)src + n > tab.size() || (uint64_t)dst + n > tab.size()) throw std::invalid_argument("wat: table_copy: index out of bound");
+            if (dst <= src) std::copy(tab.begin() + src, tab.begin() + src + n, tab.begin() + dst);
+            else std::copy_backward(tab.begin() + src, tab.begin() + src + n, tab.begin() + dst + n);
+            break;
+        }
+        case ins::table_init: {
+            const uint32_t n = index("table.init"), src = index("table.init"), dst = index("table.init");
+            const std::vector<int64_t> &seg = rs.elems[(size_t)i.imm];
+            if ((uint64_t)src + n > seg.size() || (uint64_t)dst + n > tab.size()) throw std::invalid_argument("wat: table_init: index out of bound");
+            std::copy(seg.begin() + src, seg.begin() + src + n, tab.begin() + dst);
+            break;
+        }
+        case ins::elem_drop: rs.elems[(size_t)i.imm].clear(); break;
+        default: throw std::logic_error("wat: unknown instruction kind");
+        }
     }
     // do_load (interpreter_impl.hpp:2206-2228): the address is read as a number; a range that holds a stored witness gives a new witness
     static void load(const ins &i, run_state &rs) {
@@ -1396,12 +1475,39 @@ private:
     void set_elements(uint64_t offset, const std::vector<int64_t> &funcs, size_t nimports) {
         if (!has_table_) throw std::invalid_argument("wat: an element segment needs a table");
         if (offset + funcs.size() > table_.size()) throw std::invalid_argument("wat: table_init: index out of bound");
+        nimports_ = nimports;
         for (size_t i = 0; i < funcs.size(); i++) {
-            if (funcs[i] < 0) { table_[(size_t)offset + i] = -1; continue; }
-            if ((uint64_t)funcs[i] < nimports) throw std::invalid_argument("wat: an imported function in a table is not supported");
-            if ((uint64_t)funcs[i] - nimports >= funcs_.size()) throw std::invalid_argument("wat: an element segment names an unknown function");
-            table_[(size_t)offset + i] = funcs[i] - (int64_t)nimports;
+            if (funcs[i] >= 0 && (uint64_t)funcs[i] >= nimports + funcs_.size()) throw std::invalid_argument("wat: an element segment names an unknown function");
+            table_[(size_t)offset + i] = funcs[i];
         }
+        elem_segs_.push_back(funcs);                          // active segments are NOT dropped by the reference's instantiate() (runtime.hpp:518-536): table.init may read them again
+    }
+    // ref.null / ref.is_null / ref.func and the table instructions; `a`, `b`: table / segment / function indices as the instruction has them
+    void emit_reference(ins::kind_t k, uint64_t a = 0, uint64_t b = 0, uint8_t type = FUNCREF) {
+        const auto table_known = [&](uint64_t t, const char *shown) { if (!has_table_ || t != 0) throw std::invalid_argument(std::string("wat: ") + shown + " on an unknown table"); };
+        switch (k) {
+        case ins::ref_null: if (!is_ref(type)) throw std::invalid_argument("wat: ref.null of an unknown type"); types_.push_back(type); break;
+        case ins::ref_is_null: { const uint8_t t = pop_type("ref.is_null"); if (t && !is_ref(t)) throw std::invalid_argument("wat: type mismatch: ref.is_null applied to an " + type_name(t) + " value"); types_.push_back(32); break; }
+        case ins::ref_func: if (a >= nimports_ + funcs_.size()) throw std::invalid_argument("wat: ref.func of an unknown function"); types_.push_back(FUNCREF); break;
+        case ins::table_get: table_known(a, "table.get"); want(32, "table.get"); types_.push_back(FUNCREF); break;
+        case ins::table_set: table_known(a, "table.set"); want(FUNCREF, "table.set"); want(32, "table.set"); break;
+        case ins::table_size: table_known(a, "table.size"); types_.push_back(32); break;
+        case ins::table_grow: table_known(a, "table.grow"); want(32, "table.grow"); want(FUNCREF, "table.grow"); types_.push_back(32); break;
+        case ins::table_fill: table_known(a, "table.fill"); want(32, "table.fill"); want(FUNCREF, "table.fill"); want(32, "table.fill"); break;
+        case ins::table_copy: table_known(a, "table.copy"); table_known(b, "table.copy"); for (int j = 0; j < 3; j++) want(32, "table.copy"); break;
+        case ins::table_init:                                 // a = segment, b = table
+            table_known(b, "table.init");
+            if (a >= elem_segs_.size()) throw std::invalid_argument("wat: table.init of an unknown element segment");
+            for (int j = 0; j < 3; j++) want(32, "table.init");
+            break;
+        case ins::elem_drop:
+            // exec_elem_drop (interpreter_impl.hpp:2095-2104) looks its operand up in the module's TABLE list and clears the ELEMENT
+            // segment at that address: right for segment 0 of a module with one table, out of bounds otherwise
+            if (a != 0 || !has_table_ || elem_segs_.empty()) throw std::invalid_argument("wat: elem.drop of a segment other than 0 is not supported (the reference's elem.drop reads outside its table list there)");
+            break;
+        default: throw std::logic_error("wat: not a reference instruction");
+        }
+        put(k, a);
     }
     void emit_local(ins::kind_t k, uint64_t index) {
         if (index >= cur_->locals.size()) throw std::invalid_argument("wat: unknown local " + std::to_string(index));
@@ -1477,7 +1583,9 @@ private:
         if (t == "i64") return 64;
         if (t == "f32") return F32;
         if (t == "f64") return F64;
-        throw std::invalid_argument("wat: only i32, i64, f32 and f64 values are supported (" + printable(t) + ")");
+        if (t == "funcref") return FUNCREF;
+        if (t == "externref") return EXTERNREF;
+        throw std::invalid_argument("wat: unknown value type (" + printable(t) + ")");
     }
 
     // ---- text ------------------------------------------------------------------------------------------------
@@ -1487,6 +1595,7 @@ private:
         const std::map<std::string, size_t> &data_ids;
         const std::map<std::string, size_t> &global_ids;
         const std::map<std::string, size_t> &type_ids;
+        const std::map<std::string, size_t> &elem_ids;
         std::map<std::string, size_t> local_ids;
     };
     void set_memory(uint64_t pages, uint64_t max_pages) {
@@ -1531,7 +1640,7 @@ private:
         const sexpr top = p.parse_top();
         if (top.head() != "module") throw std::invalid_argument("wat: expected (module ...)");
         std::vector<import_t> imports;
-        std::map<std::string, size_t> func_ids, data_ids, global_ids, type_ids;
+        std::map<std::string, size_t> func_ids, data_ids, global_ids, type_ids, elem_ids;
         std::vector<const sexpr *> bodies, elems, inline_elems;
         std::string start;
         for (size_t i = 1; i < top.list.size(); i++) {
@@ -1643,6 +1752,7 @@ private:
                 for (; j < e.list.size(); j++) {
                     const uint8_t w = width_of(e.list[j].atom);
                     if (h == "result") { fn.results.push_back(w); continue; }
+                    if (h == "local" && is_ref(w)) throw std::invalid_argument("wat: locals of a reference type are not supported (the reference stops: Unsupported local type)");
                     if (h == "param") { if (fn.locals.size() != fn.params.size()) throw std::invalid_argument("wat: parameters must come before locals"); fn.params.push_back(w); }
                     fn.locals.push_back(w);
                 }
@@ -1658,7 +1768,8 @@ private:
             }
         }
         // element segments: (elem [$id] [(table ..)] (offset? (i32.const n)) [func] $f ...) writes functions into the table at instantiation
-        const text_scope names{imports, func_ids, data_ids, global_ids, type_ids, {}};
+        nimports_ = imports.size();
+        const text_scope names{imports, func_ids, data_ids, global_ids, type_ids, elem_ids, {}};
         const auto functions_from = [&](const sexpr &e, size_t j) {
             std::vector<int64_t> fs;
             for (; j < e.list.size(); j++) {
@@ -1670,7 +1781,7 @@ private:
         for (const sexpr *e : inline_elems) set_elements(0, functions_from(*e, 1), imports.size());
         for (const sexpr *e : elems) {
             size_t j = 1;
-            if (j + 1 < e->list.size() && !e->list[j].is_list && e->list[j].atom[0] == '$' && e->list[j + 1].is_list) j++;      // the segment's own name
+            if (j + 1 < e->list.size() && !e->list[j].is_list && e->list[j].atom[0] == '$' && e->list[j + 1].is_list) elem_ids[e->list[j++].atom] = elem_segs_.size();   // the segment's own name
             if (j < e->list.size() && e->list[j].head() == "table") j++;
             if (j < e->list.size() && !e->list[j].is_list && e->list[j].atom == "declare") continue;   // declarative: only announces ref.func targets
             if (j >= e->list.size() || !e->list[j].is_list) throw std::invalid_argument("wat: passive element segments are not supported (no table.init)");
@@ -1692,7 +1803,7 @@ private:
         for (size_t k = 0; k < bodies.size(); k++) {
             const sexpr &f = *bodies[k];
             func_t &fn = funcs_[k];
-            text_scope sc{imports, func_ids, data_ids, global_ids, type_ids, local_ids[k]};
+            text_scope sc{imports, func_ids, data_ids, global_ids, type_ids, elem_ids, local_ids[k]};
             begin_body(fn);
             parse_seq(f.list, first_instr[k], f.list.size(), sc);
             end_body(f.list.size() >= 2 && !f.list[1].is_list ? f.list[1].atom : "function " + std::to_string(k));
@@ -1752,7 +1863,18 @@ private:
                 emit_call_indirect(t, 0);
             }
             else if (a == "local.get" || a == "local.set" || a == "local.tee") emit_local(a == "local.get" ? ins::local_get : (a == "local.set" ? ins::local_set : ins::local_tee), local_index(next(), sc));
-            else if (a == "select") emit_plain(ins::select);
+            else if (a == "select") {
+                while (i + 1 < to && list[i + 1].is_list && list[i + 1].head() == "result") i++;      // select (result t): the typed spelling of the same instruction
+                emit_plain(ins::select);
+            }
+            else if (a == "ref.null") { const std::string &t = next(); emit_reference(ins::ref_null, 0, 0, (t == "func" || t == "funcref") ? FUNCREF : ((t == "extern" || t == "externref") ? EXTERNREF : 0)); }
+            else if (a == "ref.is_null") emit_reference(ins::ref_is_null);
+            else if (a == "ref.func") emit_reference(ins::ref_func, func_index(next(), sc));
+            else if (a == "table.get" || a == "table.set" || a == "table.size" || a == "table.grow" || a == "table.fill" || a == "table.copy" || a == "table.init" || a == "elem.drop") {
+                std::vector<std::string> imm;                 // table names / indices (and the segment for table.init / elem.drop)
+                while (i + 1 < to && !list[i + 1].is_list && (list[i + 1].atom[0] == '$' || (list[i + 1].atom[0] >= '0' && list[i + 1].atom[0] <= '9')) && imm.size() < 2) imm.push_back(list[++i].atom);
+                emit_table_text(a, imm, sc);
+            }
             else if (a == "drop") emit_plain(ins::drop);
             else if (a == "nop") emit_plain(ins::nop);
             else if (a == "block" || a == "loop" || a == "if") {
@@ -1801,6 +1923,26 @@ private:
         if (it != sc.func_ids.end()) return it->second;
         if (!id.empty() && id[0] >= '0' && id[0] <= '9') return parse_i64(id);
         throw std::invalid_argument("wat: call of an unknown function (" + id + ")");
+    }
+    // table.* / elem.drop with their textual immediates: tables are named $t or 0 (there is one), segments by $name or index
+    void emit_table_text(const std::string &name, const std::vector<std::string> &imm, const text_scope &sc) {
+        const auto segment = [&](const std::string &id) -> uint64_t {
+            const auto it = sc.elem_ids.find(id);
+            if (it != sc.elem_ids.end()) return it->second;
+            if (!id.empty() && id[0] >= '0' && id[0] <= '9') return parse_i64(id);
+            throw std::invalid_argument("wat: unknown element segment " + id);
+        };
+        const auto table = [&](const std::string &id) -> uint64_t { return (!id.empty() && id[0] >= '0' && id[0] <= '9') ? parse_i64(id) : 0; };
+        if (name == "elem.drop") { if (imm.size() != 1) throw std::invalid_argument("wat: malformed elem.drop"); emit_reference(ins::elem_drop, segment(imm[0])); return; }
+        if (name == "table.init") {                           // table.init [$t] $e
+            if (imm.empty()) throw std::invalid_argument("wat: malformed table.init");
+            emit_reference(ins::table_init, segment(imm.back()), imm.size() == 2 ? table(imm[0]) : 0);
+            return;
+        }
+        if (name == "table.copy") { emit_reference(ins::table_copy, imm.size() == 2 ? table(imm[0]) : 0, imm.size() == 2 ? table(imm[1]) : 0); return; }
+        if (imm.size() > 1) throw std::invalid_argument("wat: malformed " + name);
+        const ins::kind_t k = name == "table.get" ? ins::table_get : (name == "table.set" ? ins::table_set : (name == "table.size" ? ins::table_size : (name == "table.grow" ? ins::table_grow : ins::table_fill)));
+        emit_reference(k, imm.empty() ? 0 : table(imm[0]));
     }
     static uint64_t global_index(const std::string &id, const text_scope &sc) {
         const auto it = sc.global_ids.find(id);
@@ -1897,9 +2039,31 @@ private:
             return;
         }
         if (h == "select") {
-            if (e.list.size() != 4) throw std::invalid_argument("wat: select takes three folded operands");
-            operands(1);
+            size_t j = 1;
+            while (j < e.list.size() && e.list[j].head() == "result") j++;                        // (select (result t) a b c)
+            if (e.list.size() - j > 3) throw std::invalid_argument("wat: select takes three folded operands");
+            operands(j);
             emit_plain(ins::select);
+            return;
+        }
+        if (h == "ref.null") {
+            if (e.list.size() != 2 || e.list[1].is_list) throw std::invalid_argument("wat: malformed ref.null");
+            const std::string &t = e.list[1].atom;
+            emit_reference(ins::ref_null, 0, 0, (t == "func" || t == "funcref") ? FUNCREF : ((t == "extern" || t == "externref") ? EXTERNREF : 0));
+            return;
+        }
+        if (h == "ref.is_null") { if (e.list.size() > 2) throw std::invalid_argument("wat: malformed ref.is_null"); operands(1); emit_reference(ins::ref_is_null); return; }
+        if (h == "ref.func") {
+            if (e.list.size() != 2 || e.list[1].is_list) throw std::invalid_argument("wat: malformed ref.func");
+            emit_reference(ins::ref_func, func_index(e.list[1].atom, sc));
+            return;
+        }
+        if (h == "table.get" || h == "table.set" || h == "table.size" || h == "table.grow" || h == "table.fill" || h == "table.copy" || h == "table.init" || h == "elem.drop") {
+            std::vector<std::string> imm;
+            size_t j = 1;
+            for (; j < e.list.size() && !e.list[j].is_list && imm.size() < 2; j++) imm.push_back(e.list[j].atom);
+            operands(j);
+            emit_table_text(h, imm, sc);
             return;
         }
         if (h == "block" || h == "loop") {                       // (block $l? (param ..)* (result ..)* instr*)
@@ -1999,7 +2163,8 @@ private:
             if (t == 0x7e) return 64;
             if (t == 0x7d) return F32;
             if (t == 0x7c) return F64;
-            throw std::invalid_argument("wasm: only i32, i64, f32 and f64 values are supported");
+            if (t == 0x70 || t == 0x6F) return t;
+            throw std::invalid_argument("wasm: unknown value type");
         }
     };
     void parse_binary(const std::string &data) {
@@ -2059,8 +2224,8 @@ private:
                         const size_t cnt = (size_t)s.uleb();
                         for (size_t j = 0; j < cnt; j++) {
                             const uint8_t v = s.byte();
-                            if (v != 0x7f && v != 0x7e && v != 0x7d && v != 0x7c) t.usable = false;
-                            (part ? t.results : t.params).push_back(v == 0x7f ? 32 : (v == 0x7e ? 64 : (v == 0x7d ? F32 : F64)));
+                            if (v != 0x7f && v != 0x7e && v != 0x7d && v != 0x7c && v != 0x70 && v != 0x6F) t.usable = false;
+                            (part ? t.results : t.params).push_back(v == 0x7f ? 32 : (v == 0x7e ? 64 : (v == 0x7d ? F32 : (v == 0x7c ? F64 : v))));
                         }
                     }
                     types.push_back(t);
@@ -2158,6 +2323,7 @@ private:
                 throw std::invalid_argument("wasm: unsupported module section (id " + std::to_string(id) + ")");
             }
         }
+        nimports_ = imports.size();
         if (bodies.size() != func_types.size()) throw std::invalid_argument("wasm: function and code sections disagree");
         for (const data_t &d : datas_) if (d.active && !has_memory_) throw std::invalid_argument("wasm: an active data segment needs a memory");
         if (start < 0 || (size_t)start < imports.size() || (size_t)start - imports.size() >= bodies.size()) throw std::invalid_argument("wasm: no exported _start function");
@@ -2172,6 +2338,7 @@ private:
             for (size_t g = 0; g < groups; g++) {
                 const uint64_t cnt = b.uleb();
                 const uint8_t w = b.valtype();
+                if (is_ref(w)) throw std::invalid_argument("wasm: locals of a reference type are not supported (the reference stops: Unsupported local type)");
                 if (cnt > 10000 || funcs_[k].locals.size() + cnt > 10000) throw std::invalid_argument("wasm: too many locals");
                 funcs_[k].locals.insert(funcs_[k].locals.end(), (size_t)cnt, w);
             }
@@ -2196,7 +2363,7 @@ private:
                 else if (c == 0x02 || c == 0x03 || c == 0x04) {
                     std::vector<uint8_t> params, results;
                     if (b.p < b.end && *b.p == 0x40) b.byte();
-                    else if (b.p < b.end && (*b.p == 0x7f || *b.p == 0x7e || *b.p == 0x7d || *b.p == 0x7c)) results.push_back(b.valtype());
+                    else if (b.p < b.end && (*b.p == 0x7f || *b.p == 0x7e || *b.p == 0x7d || *b.p == 0x7c || *b.p == 0x70 || *b.p == 0x6F)) results.push_back(b.valtype());
                     else {
                         const int64_t t = b.sleb(33);
                         if (t < 0 || (uint64_t)t >= types.size() || !types[(size_t)t].usable) throw std::invalid_argument("wasm: unsupported block type");
@@ -2216,6 +2383,11 @@ private:
                 else if (c == 0x0F) emit_return();
                 else if (c == 0x1A) emit_plain(ins::drop);
                 else if (c == 0x1B) emit_plain(ins::select);
+                else if (c == 0x1C) { const uint64_t n = b.uleb(); if (n != 1) throw std::invalid_argument("wasm: malformed typed select"); b.valtype(); emit_plain(ins::select); }
+                else if (c == 0x25 || c == 0x26) emit_reference(c == 0x25 ? ins::table_get : ins::table_set, b.uleb());
+                else if (c == 0xD0) emit_reference(ins::ref_null, 0, 0, b.valtype());
+                else if (c == 0xD1) emit_reference(ins::ref_is_null);
+                else if (c == 0xD2) emit_reference(ins::ref_func, b.uleb());
                 else if (c == 0x10) emit_call(b.uleb(), imports);
                 else if (c == 0x11) {
                     const uint64_t t = b.uleb(), tab = b.uleb();
@@ -2241,6 +2413,12 @@ private:
                     else if (sub == 9) emit_bulk(ins::data_drop, b.uleb());
                     else if (sub == 10) { if (b.byte() != 0 || b.byte() != 0) throw std::invalid_argument("wasm: unknown memory"); emit_bulk(ins::memory_copy); }
                     else if (sub == 11) { if (b.byte() != 0) throw std::invalid_argument("wasm: unknown memory"); emit_bulk(ins::memory_fill); }
+                    else if (sub == 12) { const uint64_t seg = b.uleb(), tab = b.uleb(); emit_reference(ins::table_init, seg, tab); }
+                    else if (sub == 13) emit_reference(ins::elem_drop, b.uleb());
+                    else if (sub == 14) { const uint64_t dst = b.uleb(), src = b.uleb(); emit_reference(ins::table_copy, dst, src); }
+                    else if (sub == 15) emit_reference(ins::table_grow, b.uleb());
+                    else if (sub == 16) emit_reference(ins::table_size, b.uleb());
+                    else if (sub == 17) emit_reference(ins::table_fill, b.uleb());
                     else if (sub <= 7) {                        // iNN.trunc_sat_fMM_s/u
                         static const char *const sat[] = {"i32.trunc_sat_f32_s", "i32.trunc_sat_f32_u", "i32.trunc_sat_f64_s", "i32.trunc_sat_f64_u",
                                                           "i64.trunc_sat_f32_s", "i64.trunc_sat_f32_u", "i64.trunc_sat_f64_s", "i64.trunc_sat_f64_u"};
@@ -2298,7 +2476,9 @@ private:
     struct sig_t { std::vector<uint8_t> params, results; };   // the module's function types (call_indirect names one)
     std::vector<sig_t> sigs_;
     bool has_table_ = false;
-    std::vector<int64_t> table_;                              // table 0: index among the module's own functions, -1 = null (table_instance, runtime.hpp:96-102)
+    std::vector<int64_t> table_;                              // table 0 after instantiation: function index (imports first), -1 = null (table_instance, runtime.hpp:96-102)
+    std::vector<std::vector<int64_t>> elem_segs_;             // the active element segments, in order
+    size_t nimports_ = 0;
     struct global_t { uint8_t type = 32; bool mut = false; uint64_t init = 0; };   // global_instance (runtime.hpp:181-187): i32 / i64 only (:441-455)
     std::vector<global_t> globals_;
     std::vector<func_t> funcs_;

@@ -127,7 +127,8 @@ struct tiny_module {
     };
     struct data_seg { std::vector<u8> bytes; bool active = false; u32 offset = 0; };
     explicit tiny_module(std::vector<module_func> functions, size_t start_function, u32 mem_pages = 1, u32 mem_max = 0, const std::vector<data_seg> &datas = {},
-                         const std::vector<std::pair<value_kind, uint64_t>> &globals = {}, const std::vector<reference_t> *table = nullptr) {
+                         const std::vector<std::pair<value_kind, uint64_t>> &globals = {}, const std::vector<reference_t> *table = nullptr,
+                         const std::vector<std::vector<reference_t>> &segments = {}) {
         function_kind k_pc({value_kind::i64}, {value_kind::i64}), k_eq({value_kind::i64, value_kind::i64}, {}), k_pc32({value_kind::i32}, {value_kind::i32}),
             k_one({value_kind::i64}, {}), k_w2({value_kind::i32, value_kind::i32}, {value_kind::i32}),
             k_w4({value_kind::i32, value_kind::i32, value_kind::i32, value_kind::i32}, {value_kind::i32}), k_w1({value_kind::i32}, {});
@@ -160,6 +161,7 @@ struct tiny_module {
             }
         }
         if (table) inst.tableaddrs.push_back(store.emplace_back<table_instance>(table_kind{value_kind::funcref, limits((u32)table->size())}, *table));
+        for (const auto &seg : segments) inst.elemaddrs.push_back(store.emplace_back<element_instance>(value_kind::funcref, seg));
         // globals as instantiate() creates them (include/runtime.hpp:428-456): i32 / i64, holding a native number
         for (const auto &g : globals) {
             if (g.first == value_kind::i32) inst.globaladdrs.push_back(store.emplace_back<global_instance>(g.first, (u32)g.second));
@@ -188,6 +190,8 @@ static value_kind token_kind(const std::string &t) {
     if (t == "i64") return value_kind::i64;
     if (t == "f32") return value_kind::f32;
     if (t == "f64") return value_kind::f64;
+    if (t == "funcref") return value_kind::funcref;
+    if (t == "externref") return value_kind::externref;
     throw std::runtime_error("unknown value type " + t);
 }
 static std::vector<value_kind> token_kinds(const std::string &list) {      // "i32,i64" or "-"
@@ -308,6 +312,18 @@ static std::vector<instr_ptr> assemble_until(const std::vector<wasm_token> &toks
             continue;
         }
         if (t.op == "call_indirect") { flush(); body.push_back(make_instr<call_indirect>((index_t)0, (index_t)0)); continue; }   // (the type index is not read at run time)
+        // references and the table (include/transpiler.hpp:546-553,612-641)
+        if (t.op == "ref.null") { plain(opcode(opcode::ref_null, value_kind::funcref)); continue; }
+        if (t.op == "ref.is_null") { plain(opcode(opcode::ref_is_null)); continue; }
+        if (t.op == "ref.func") { plain(opcode(opcode::ref_func, (index_t)(tiny_module::env_imports().size() + t.imm))); continue; }
+        if (t.op == "table.get") { plain(opcode(opcode::table_get, (index_t)0)); continue; }
+        if (t.op == "table.set") { plain(opcode(opcode::table_set, (index_t)0)); continue; }
+        if (t.op == "table.size") { plain(opcode(opcode::table_size, (index_t)0)); continue; }
+        if (t.op == "table.grow") { plain(opcode(opcode::table_grow, (index_t)0)); continue; }
+        if (t.op == "table.fill") { plain(opcode(opcode::table_fill, (index_t)0)); continue; }
+        if (t.op == "table.copy") { plain(opcode(opcode::table_copy, (index_t)0, (index_t)0)); continue; }
+        if (t.op == "table.init") { plain(opcode(opcode::table_init, (index_t)t.imm, (index_t)0)); continue; }
+        if (t.op == "elem.drop") { plain(opcode(opcode::elem_drop, (index_t)t.imm)); continue; }
         if (t.op == "global.get") { plain(opcode(opcode::global_get, (index_t)t.imm)); continue; }
         if (t.op == "global.set") { plain(opcode(opcode::global_set, (index_t)t.imm)); continue; }
         const bool typed = t.op.size() > 4 && (t.op.rfind("i32.", 0) == 0 || t.op.rfind("i64.", 0) == 0);
@@ -397,7 +413,7 @@ static std::vector<wasm_token> read_tokens(const std::string &path) {
     std::string op;
     while (in >> op) {
         wasm_token tok{op};
-        if (op == "c" || op == "i32.const" || op == "i64.const" || op == "f32.const" || op == "f64.const" || op == "global.get" || op == "global.set" || op == "local.get" || op == "local.set" || op == "local.tee" || op == "callf" || op == "start" || op == "memory.init" || op == "data.drop" || op == "br" || op == "br_if" ||
+        if (op == "c" || op == "i32.const" || op == "i64.const" || op == "f32.const" || op == "f64.const" || op == "global.get" || op == "global.set" || op == "ref.func" || op == "table.init" || op == "elem.drop" || op == "local.get" || op == "local.set" || op == "local.tee" || op == "callf" || op == "start" || op == "memory.init" || op == "data.drop" || op == "br" || op == "br_if" ||
             ((op.rfind("i32.", 0) == 0 || op.rfind("i64.", 0) == 0 || op.rfind("f32.", 0) == 0 || op.rfind("f64.", 0) == 0) && (op.find(".load") != std::string::npos || op.find(".store") != std::string::npos))) {
             std::string lit; in >> lit; tok.imm = std::stoull(lit, nullptr, 0);
         }
@@ -444,6 +460,7 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
     std::vector<tiny_module::data_seg> datas;
     std::vector<std::pair<value_kind, uint64_t>> globals;
     std::vector<reference_t> table;
+    std::vector<std::vector<reference_t>> segments;
     bool has_table = false;
     std::vector<wasm_token> body;
     size_t start = 0;
@@ -461,8 +478,12 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
         else if (t.op == "arg") continue;
         else if (t.op == "table") { has_table = true; table.assign((size_t)t.imm, std::nullopt); }
         else if (t.op == "elem") {                            // what table_init leaves after instantiation (include/runtime.hpp:518-536): function addresses = indices here
-            for (size_t j = 0; j < t.types.size(); j++)
-                table.at((size_t)t.imm + j) = t.types[j] == "-" ? reference_t{} : reference_t{(index_t)(tiny_module::env_imports().size() + std::stoul(t.types[j]))};
+            segments.emplace_back();
+            for (size_t j = 0; j < t.types.size(); j++) {
+                const reference_t r = t.types[j] == "-" ? reference_t{} : reference_t{(index_t)(tiny_module::env_imports().size() + std::stoul(t.types[j]))};
+                table.at((size_t)t.imm + j) = r;
+                segments.back().push_back(r);                 // active segments stay in the store (instantiate() only drops the others)
+            }
         }
         else if (t.op == "global") globals.emplace_back(token_kind(t.types[0]), t.imm);
         else if (t.op == "memory") { pages = (u32)std::stoul(t.types[0]); max_pages = (u32)std::stoul(t.types[1]); }
@@ -477,7 +498,7 @@ static tiny_module build_module(const std::vector<wasm_token> &toks) {
         else body.push_back(t);
     }
     close();
-    return tiny_module(std::move(functions), start, pages, max_pages, datas, globals, has_table ? &table : nullptr);
+    return tiny_module(std::move(functions), start, pages, max_pages, datas, globals, has_table ? &table : nullptr, segments);
 }
 
 template <typename Ctx>

@@ -162,7 +162,7 @@ def _lit(s):
 
 
 def wat_tables(text):
-    """(named types {id: (params, results)}, table size or None, [(offset, [function ids])]) of a module"""
+    """(named types {id: (params, results)}, table size or None, [(offset, [function ids], segment id or None)]) of a module"""
     types, table, elems = {}, None, []
     for f in _sexpr(text)[1:]:
         if f[0] == "type":
@@ -171,8 +171,10 @@ def wat_tables(text):
         elif f[0] == "table":
             table = int(next(x for x in f[1:] if isinstance(x, str) and x[0].isdigit()))
         elif f[0] == "elem":
-            off = f[1][1] if f[1][0] == "offset" else f[1]
-            elems.append((_lit(off[1]) % (1 << 32), [x for x in f[2:] if x != "func"]))
+            rest = f[1:]
+            eid = rest.pop(0) if isinstance(rest[0], str) else None
+            off = rest[0][1] if rest[0][0] == "offset" else rest[0]
+            elems.append((_lit(off[1]) % (1 << 32), [x for x in rest[1:] if x != "func"], eid))
     return types, table, elems
 
 
@@ -215,10 +217,11 @@ def wat_globals(text):
     return out
 
 
-def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None, types=None):
+def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None, types=None, elem_ids=None):
     """post-order walk of a function's body (folded forms, plain instructions, or both mixed): visit(kind, name, immediate)"""
     data_ids = data_ids or {}
     global_ids = global_ids or {}
+    elem_ids = elem_ids or {}
     def local(x):
         return fn["names"][x] if x in fn["names"] else int(x)
 
@@ -278,7 +281,13 @@ def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None, types=None):
                 elif e == "call_indirect":
                     while n < len(items) and isinstance(items[n], list) and items[n][0] in ("type", "param", "result"):
                         n += 1
-                elif e[3:] in (".const",) or e in ("local.get", "local.set", "local.tee", "global.get", "global.set", "call", "br", "br_if", "memory.init", "data.drop"):
+                elif e in ("table.get", "table.set", "table.size", "table.grow", "table.fill", "table.copy", "table.init", "elem.drop"):
+                    while n < len(items) and is_label(items[n]) and n - i < 2:
+                        n += 1
+                elif e == "select":
+                    while n < len(items) and isinstance(items[n], list) and items[n][0] == "result":
+                        n += 1
+                elif e[3:] in (".const",) or e in ("ref.null", "ref.func", "local.get", "local.set", "local.tee", "global.get", "global.set", "call", "br", "br_if", "memory.init", "data.drop"):
                     n += 1
                 else:
                     while n < len(items) and isinstance(items[n], str) and items[n].partition("=")[0] in ("offset", "align"):
@@ -350,6 +359,24 @@ def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None, types=None):
             for a in e[2:]:
                 emit(a)
             visit("local", h, local(e[1]))
+        elif h == "ref.null":
+            visit("op", h, None)
+        elif h == "ref.func":
+            visit("reffunc", h, ids[e[1]])
+        elif h in ("table.get", "table.set", "table.size", "table.grow", "table.fill", "table.copy", "table.init", "elem.drop", "ref.is_null"):
+            names = [a for a in e[1:] if isinstance(a, str)]
+            for a in e[1:]:
+                if isinstance(a, list):
+                    emit(a)
+            if h in ("table.init", "elem.drop"):
+                visit("elemseg", h, elem_ids[names[-1]] if names[-1] in elem_ids else int(names[-1]))
+            else:
+                visit("op", h, None)
+        elif h == "select":
+            for a in e[1:]:
+                if not (isinstance(a, list) and a[0] == "result"):
+                    emit(a)
+            visit("op", h, None)
         elif h[:4] in ("i32.", "i64.", "f32.", "f64.") and (h[4:8] == "load" or h[4:9] == "store"):
             offset, rest = 0, e[1:]
             while rest and isinstance(rest[0], str):
@@ -367,7 +394,7 @@ def _walk(fn, imports, ids, visit, data_ids=None, global_ids=None, types=None):
             for a in e[1:]:
                 emit(a)
             visit("op", h, None)
-        elif h[:4] in ("i32.", "i64.", "f32.", "f64.") or h in ("drop", "nop", "select"):
+        elif h[:4] in ("i32.", "i64.", "f32.", "f64.") or h in ("drop", "nop"):
             for a in e[1:]:
                 emit(a)
             visit("op", h, None)
@@ -389,8 +416,9 @@ def wat_to_tokens(text):
     types, table, elems = wat_tables(text)
     if table is not None:
         out.append("table %d" % table)
-    for off, fs in elems:
+    for off, fs, _ in elems:
         out.append("elem %d %d %s" % (off, len(fs), " ".join(str(ids[f]) for f in fs)))
+    elem_ids = {eid: k for k, (_, _, eid) in enumerate(elems) if eid}
     if memory:
         out.append("memory %d %d" % memory)
     for _, active, offset, data in datas:
@@ -405,6 +433,8 @@ def wat_to_tokens(text):
             out.append("%s %d" % (name, imm))
         elif kind == "indirect":
             out.append(name)
+        elif kind in ("reffunc", "elemseg"):
+            out.append("%s %d" % (name, imm))
         elif kind == "host":
             out.append("call:" + name)
         elif kind == "callf":
@@ -421,7 +451,7 @@ def wat_to_tokens(text):
     for fn in funcs:
         if structured:
             out.append("func %s %s %s" % tuple(",".join(fn[key]) or "-" for key in ("params", "results", "locals")))
-        _walk(fn, imports, ids, visit, data_ids, global_ids, types)
+        _walk(fn, imports, ids, visit, data_ids, global_ids, types, elem_ids)
     if structured:
         out.append("start %d" % start)
     return out
@@ -653,7 +683,10 @@ def wat_to_wasm(text, custom_section=True):
     named_types, table, elems = wat_tables(text)
     access = ["i32.load", "i64.load", "f32.load", "f64.load", "i32.load8_s", "i32.load8_u", "i32.load16_s", "i32.load16_u", "i64.load8_s", "i64.load8_u", "i64.load16_s",
               "i64.load16_u", "i64.load32_s", "i64.load32_u", "i32.store", "i64.store", "f32.store", "f64.store", "i32.store8", "i32.store16", "i64.store8", "i64.store16", "i64.store32"]
-    vt = {"i32": 0x7f, "i64": 0x7e, "f32": 0x7d, "f64": 0x7c}
+    vt = {"i32": 0x7f, "i64": 0x7e, "f32": 0x7d, "f64": 0x7c, "funcref": 0x70, "externref": 0x6f}
+    elem_ids = {eid: k for k, (_, _, eid) in enumerate(elems) if eid}
+    table_ops = {"table.get": b"\x25\x00", "table.set": b"\x26\x00", "table.copy": b"\xfc\x0e\x00\x00", "table.grow": b"\xfc\x0f\x00", "table.size": b"\xfc\x10\x00",
+                 "table.fill": b"\xfc\x11\x00", "ref.null": b"\xd0\x70", "ref.is_null": b"\xd1"}
     types, import_list = [], []
 
     def typeidx(params, results):
@@ -684,6 +717,12 @@ def wat_to_wasm(text, custom_section=True):
                 code.extend(bytes([0x23 if nm == "global.get" else 0x24]) + _uleb(imm))
             elif kind == "indirect":
                 code.extend(b"\x11" + _uleb(typeidx(*imm)) + b"\x00")
+            elif kind == "reffunc":
+                code.extend(b"\xd2" + _uleb(len(import_list) + imm))
+            elif kind == "elemseg":
+                code.extend(b"\xfc" + (_uleb(12) + _uleb(imm) + b"\x00" if nm == "table.init" else _uleb(13) + _uleb(imm)))
+            elif nm in table_ops:
+                code.extend(table_ops[nm])
             elif nm in _FLOAT_OPS:
                 code.extend(_FLOAT_OPS[nm])
             elif kind == "host":
@@ -717,7 +756,7 @@ def wat_to_wasm(text, custom_section=True):
             else:
                 w, op = nm[:3], nm[4:]
                 code.append((0x45 if w == "i32" else 0x50) + _CMP_OPS.index(op) if op in _CMP_OPS else (0x67 if w == "i32" else 0x79) + _INT_OPS.index(op))
-        _walk(fn, imports, ids, visit, data_ids, global_ids, named_types)
+        _walk(fn, imports, ids, visit, data_ids, global_ids, named_types, elem_ids)
         code.append(0x0B)
         body = vec([_uleb(1) + bytes([vt[t]]) for t in fn["locals"]]) + bytes(code)
         bodies.append(_uleb(len(body)) + body)
@@ -734,7 +773,7 @@ def wat_to_wasm(text, custom_section=True):
                                for _, ty, mut, init in globals_]))
     out += section(7, vec([name("_start") + b"\x00" + _uleb(len(import_list) + start)]))
     if elems:
-        out += section(9, vec([b"\x00\x41" + _sleb(off) + b"\x0b" + vec([_uleb(len(import_list) + ids[f]) for f in fs]) for off, fs in elems]))
+        out += section(9, vec([b"\x00\x41" + _sleb(off) + b"\x0b" + vec([_uleb(len(import_list) + ids[f]) for f in fs]) for off, fs, _ in elems]))
     if datas:
         out += section(12, _uleb(len(datas)))
     out += section(10, vec(bodies))
@@ -759,8 +798,9 @@ def wat_to_plain(text):
     named_types, table, elems = wat_tables(text)
     if table is not None:
         out.append("(table %d funcref)" % table)
-    for off, fs in elems:
+    for off, fs, _ in elems:
         out.append("(elem (i32.const %d) func %s)" % (off, " ".join(fs)))
+    elem_ids = {eid: k for k, (_, _, eid) in enumerate(elems) if eid}
     if memory:
         out.append("(memory %d%s)" % (memory[0], " %d" % memory[1] if memory[1] else ""))
     for _, active, off, data in datas:
@@ -777,6 +817,12 @@ def wat_to_plain(text):
                 body.append("%s %s" % (nm, imm[1]))
             elif kind == "global":
                 body.append("%s %d" % (nm, imm))
+            elif kind == "reffunc":
+                body.append("ref.func %s" % (funcs[imm]["id"] or "$f%d" % imm))
+            elif kind == "elemseg":
+                body.append("%s %d" % (nm, imm))
+            elif nm == "ref.null":
+                body.append("ref.null func")
             elif kind == "indirect":
                 body.append("call_indirect%s%s" % ("".join(" (param %s)" % t for t in imm[0]), "".join(" (result %s)" % t for t in imm[1])))
             elif kind == "host":
@@ -793,7 +839,7 @@ def wat_to_plain(text):
                 body.append("%s %s" % (nm, " ".join(map(str, imm))))
             else:
                 body.append(nm)
-        _walk(fn, imports, ids, visit, data_ids, global_ids, named_types)
+        _walk(fn, imports, ids, visit, data_ids, global_ids, named_types, elem_ids)
         out.append(head + "\n" + "\n".join(body) + "\n)")
     out.append('(export "_start" (func %s)))' % (funcs[start]["id"] or "$f%d" % start))
     return "\n".join(out) + "\n"

@@ -534,6 +534,20 @@ def test_wat_emitter_indirect_calls_against_the_reference(oracle, pr):
         _emitter_equals_reference_rows(pr, spelling, st)
 
 
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+def test_wat_emitter_references_and_table_instructions_against_the_reference(oracle, pr):
+    """the last instructions of the reference's interpreter the front end did not take (interpreter_impl.hpp:1926-2106):
+    ref.null / ref.is_null / ref.func, table.get / set / size / grow / fill / copy / init, elem.drop, typed select, funcref
+    parameters and results (tests/golden/tables.wat).  Every result is committed and asserted, the reference's own run is valid,
+    and the rows agree in all three spellings (the binary uses the 0xD0-0xD2, 0x25 / 0x26 and 0xFC 12-17 encodings)"""
+    text = open(os.path.join(U.HERE, "golden", "tables.wat")).read()
+    raw = U.run_reference_on_wat(text, 256, seed_byte=8)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    for spelling in (text, U.wat_to_wasm(text), U.wat_to_plain(text)):
+        _emitter_equals_reference_rows(pr, spelling, st)
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
