@@ -707,12 +707,13 @@ private:
 
     // env host functions (include/host_modules/env.hpp:40-110,160-190)
     enum class host_fn : uint8_t { i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast, assert_is_concrete,
-                                   wasi_args_sizes_get, wasi_args_get, wasi_fd_write, wasi_proc_exit, wasi_random_get };
+                                   wasi_args_sizes_get, wasi_args_get, wasi_fd_write, wasi_proc_exit, wasi_random_get, print_str, dump_memory };
     static bool host_lookup(const std::string &name, host_fn &out) {
         static const std::map<std::string, host_fn> table = {
             {"i32_private_const", host_fn::i32_private_const}, {"i64_private_const", host_fn::i64_private_const}, {"assert_equal", host_fn::assert_equal},
             {"assert_zero", host_fn::assert_zero}, {"assert_one", host_fn::assert_one}, {"assert_constant", host_fn::assert_constant},
             {"witness_cast_u32", host_fn::witness_cast}, {"witness_cast_u64", host_fn::witness_cast}, {"assert_is_concrete", host_fn::assert_is_concrete},
+            {"print_str", host_fn::print_str}, {"dump_memory", host_fn::dump_memory},
         };
         const auto it = table.find(name);
         if (it == table.end()) return false;
@@ -918,6 +919,16 @@ private:
             std::uniform_int_distribution<> dist(0, 255);
             for (uint32_t i = 0; i < len; i++) buf[i] = (uint8_t)dist(rs.rand);
             rs.push(value::u32(0));
+            break;
+        }
+        case host_fn::print_str: case host_fn::dump_memory: {  // env.print_str / dump_memory (host_modules/env.hpp:92-126): (ptr, len) of linear memory to stdout, raw or as hex
+            const uint32_t len = wasi_u32(rs), ptr = wasi_u32(rs);
+            const uint8_t *bytes = wasi_mem(rs, ptr, len);
+            if (echo_) {
+                if (f == host_fn::print_str) fwrite(bytes, 1, len, stdout);
+                else { fputs("@dump: ", stdout); for (uint32_t i = 0; i < len; i++) printf("%02X", bytes[i]); fputc('\n', stdout); }
+                fflush(stdout);
+            }
             break;
         }
         default: host(f, rs); break;
@@ -1435,7 +1446,8 @@ private:
         if (!host_lookup(field, f)) throw std::invalid_argument("wat: env." + printable(field) + " is not supported by the front end");
         const std::string shown = "call env." + field;
         pop_type(shown);
-        if (f == host_fn::assert_equal) pop_type(shown);
+        if (f == host_fn::assert_equal || f == host_fn::print_str || f == host_fn::dump_memory) pop_type(shown);
+        if ((f == host_fn::print_str || f == host_fn::dump_memory) && !has_memory_) throw std::invalid_argument("wat: " + shown + " in a module without a memory");
         if (f == host_fn::i32_private_const || f == host_fn::i64_private_const) types_.push_back(f == host_fn::i32_private_const ? 32 : 64);
         if (f == host_fn::witness_cast) types_.push_back(field == "witness_cast_u32" ? 32 : 64);
         ins i; i.kind = ins::host_call; i.o = (uint8_t)f; cur_->code.push_back(i);

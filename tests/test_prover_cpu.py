@@ -739,3 +739,16 @@ def test_reference_and_table_instructions_front_end(pr):
                       ("(func $t (drop (ref.func $nope)))", "unknown function")):
         with pytest.raises(pr.ProverError, match=why):
             pr.wat_emit(head + body + tail, 64)
+
+
+def test_env_output_functions(pr):
+    """env.print_str / dump_memory (host_modules/env.hpp:92-126) only read linear memory: no row; file_size_get / file_get would read
+    host files on behalf of the guest and are refused"""
+    prog = ('(module (import "env" "print_str" (func $p (param i32 i32))) (import "env" "dump_memory" (func $d (param i32 i32))) (memory 1) (data (i32.const 8) "hi\\n")'
+            ' (func (export "_start") (call $p (i32.const 8) (i32.const 3)) (call $d (i32.const 8) (i32.const 3))))')
+    kinds, _, _, _, st = pr.wat_emit(prog, 64)
+    assert len(kinds) == 0 and st["violated_constraints"] == 0
+    with pytest.raises(pr.ProverError, match="reaches outside the memory"):
+        pr.wat_emit(prog.replace("(i32.const 8) (i32.const 3)) (call $d", "(i32.const 65534) (i32.const 3)) (call $d"), 64)
+    with pytest.raises(pr.ProverError, match="env.file_get is not supported"):
+        pr.wat_emit('(module (import "env" "file_get" (func $p (param i64 i64) (result i32))) (memory 1) (func (export "_start") (drop (call $p (i64.const 8) (i64.const 3)))))', 64)
