@@ -127,7 +127,7 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
  * globals, f32 / f64 arithmetic and conversions (numbers only, as in the reference), call_indirect, references and the table
  * instructions -- every instruction the reference's interpreter dispatches (interpreter_impl.hpp:2405-2548) -- and
  * env.i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast_u32 / _u64,
- * assert_is_concrete; wasi args_sizes_get, args_get, fd_write, proc_exit, random_get (lgrp_wat_args below).
+ * assert_is_concrete, print_str, dump_memory; wasi args_sizes_get, args_get, fd_write, proc_exit, random_get (lgrp_wat_args below).
  * Not supported (LGRP error naming the construct): the bn254fr / vbn254fr / uint256 / ecc host modules, passive element segments,
  * imported memories / tables / globals.
  * It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under include/zkp/backend/ stand in
