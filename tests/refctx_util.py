@@ -101,6 +101,8 @@ def wat_module(text):
             continue
         fn = {"id": f[1] if isinstance(f[1], str) else None, "params": [], "results": [], "locals": [], "names": {}, "body": []}
         for e in f[2 if fn["id"] else 1:]:
+            if isinstance(e, list) and e[0] == "param" and fn.get("typed") and not fn["body"]:
+                continue                                          # (func (type t) (param ..) ...): the parameters repeat the type
             if isinstance(e, list) and e[0] in ("param", "local") and not fn["body"]:
                 rest = e[1:]
                 if len(rest) == 2 and rest[0].startswith("$"):
@@ -108,11 +110,13 @@ def wat_module(text):
                     rest = rest[1:]
                 fn["params" if e[0] == "param" else "locals"].extend(rest)
             elif isinstance(e, list) and e[0] == "result" and not fn["body"]:
-                fn["results"].extend(e[1:])
+                if not fn.get("typed"):
+                    fn["results"].extend(e[1:])
             elif isinstance(e, list) and e[0] == "type" and not fn["body"]:          # (func $f (type $t) ...): the signature comes from the type
-                sig = next(([t for part in ty[2][1:] if part[0] == "param" for t in part[1:]], [t for part in ty[2][1:] if part[0] == "result" for t in part[1:]])
-                           for ty in mod[1:] if ty[0] == "type" and ty[1] == e[1])
-                fn["params"], fn["results"] = list(sig[0]), list(sig[1])
+                sig = wat_tables(text)[0][e[1]]
+                if not fn["params"] and not fn["results"]:
+                    fn["params"], fn["results"] = list(sig[0]), list(sig[1])
+                fn["typed"] = True
             else:
                 fn["body"].append(e)
         funcs.append(fn)
@@ -165,9 +169,12 @@ def wat_tables(text):
     """(named types {id: (params, results)}, table size or None, [(offset, [function ids], segment id or None)]) of a module"""
     types, table, elems = {}, None, []
     for f in _sexpr(text)[1:]:
-        if f[0] == "type":
-            sig = ([t for part in f[2][1:] if part[0] == "param" for t in part[1:]], [t for part in f[2][1:] if part[0] == "result" for t in part[1:]])
-            types[f[1]] = sig
+        if f[0] == "type":                                     # by $name and by position ("0", "1", ...)
+            fn = f[-1]
+            sig = ([t for part in fn[1:] if part[0] == "param" for t in part[1:]], [t for part in fn[1:] if part[0] == "result" for t in part[1:]])
+            types[str(sum(1 for k in types if k.isdigit()))] = sig
+            if isinstance(f[1], str):
+                types[f[1]] = sig
         elif f[0] == "table":
             table = int(next(x for x in f[1:] if isinstance(x, str) and x[0].isdigit()))
         elif f[0] == "elem":

@@ -752,3 +752,16 @@ def test_env_output_functions(pr):
         pr.wat_emit(prog.replace("(i32.const 8) (i32.const 3)) (call $d", "(i32.const 65534) (i32.const 3)) (call $d"), 64)
     with pytest.raises(pr.ProverError, match="env.file_get is not supported"):
         pr.wat_emit('(module (import "env" "file_get" (func $p (param i64 i64) (result i32))) (memory 1) (func (export "_start") (drop (call $p (i64.const 8) (i64.const 3)))))', 64)
+
+
+def test_module_spelled_the_way_wasm2wat_prints_compiled_code(pr):
+    """tests/golden/compiled_style.wat: numeric type uses, (;n;) comments, `align=`, labels as comments, a shadow-stack global, WASI
+    start-up, a private argument squared in a loop, an indirect call and proc_exit -- no compiler or wabt exists here, so this
+    stands in for the text a maintainer would get from a compiled guest"""
+    text = open(os.path.join(ROOT, "tests", "golden", "compiled_style.wat")).read()
+    out = pr.wat_emit(text, 64, args=[b"Ligero\0", (7).to_bytes(8, "little")], private_indices=[1], want_exit_code=True)
+    assert out[4]["violated_constraints"] == 0 and out[4]["asserts"] == 1 and out[5] == 0
+    wrong = pr.wat_emit(text, 64, args=[b"Ligero\0", (8).to_bytes(8, "little")], private_indices=[1])
+    assert wrong[4]["violated_constraints"] == 1                      # 8^4 mod 2^16 is not 2401
+    public = pr.wat_emit(text, 64, args=[b"Ligero\0", (7).to_bytes(8, "little")], private_indices=[])
+    assert public[4]["quadratic_slots"] < out[4]["quadratic_slots"]   # a public argument is a number: the squaring commits nothing

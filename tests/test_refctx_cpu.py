@@ -548,6 +548,21 @@ def test_wat_emitter_references_and_table_instructions_against_the_reference(ora
         _emitter_equals_reference_rows(pr, spelling, st)
 
 
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+def test_wat_emitter_on_a_module_spelled_like_compiled_code_against_the_reference(oracle, pr):
+    """tests/golden/compiled_style.wat (the way wasm2wat prints a C guest: shadow stack in a global, WASI start-up, a private
+    argument, a loop, an indirect call, proc_exit) with a private argument: the reference's interpreter and the emitter give
+    the same rows from the text, the binary and the plain spelling"""
+    text = open(os.path.join(U.HERE, "golden", "compiled_style.wat")).read()
+    args = [b"Ligero\0", (7).to_bytes(8, "little")]
+    raw = U.run_reference_on_wat(text, 256, seed_byte=9, args=args, private_indices=[1])
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    for spelling in (text, U.wat_to_wasm(text), U.wat_to_plain(text)):
+        kinds, vals, coefs, const_sum, stats = pr.wat_emit(spelling, st["l"], bytes.fromhex(st["fx"]["stage1_seed"]), args=args, private_indices=[1])
+        assert list(kinds) == list(st["kinds"]) and np.array_equal(vals, st["values"]) and np.array_equal(coefs, st["coefs"]) and const_sum == st["const_sum"]
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
