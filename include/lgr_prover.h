@@ -128,8 +128,9 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
  * instructions -- every instruction the reference's interpreter dispatches (interpreter_impl.hpp:2405-2548) -- and
  * env.i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast_u32 / _u64,
  * assert_is_concrete, print_str, dump_memory; wasi args_sizes_get, args_get, fd_write, proc_exit, random_get (lgrp_wat_args below).
- * Not supported (LGRP error naming the construct): the bn254fr / vbn254fr / uint256 / ecc host modules, passive element segments,
- * imported memories / tables / globals.
+ * Not provided: the bn254fr / vbn254fr / uint256 / ecc host modules and the other WASI functions -- a module may import them (imports
+ * resolve when they are called, as in the reference); CALLING one is an LGRP error naming it.  Refused when the module is read:
+ * passive element segments, imported memories / tables / globals.
  * It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under include/zkp/backend/ stand in
  * the reference.  It is not a general WASM machine, but for what it takes it gives every instruction the reference's
  * meaning -- the same witnesses, released in the same order, with the same linear-test randomness -- so the rows, the

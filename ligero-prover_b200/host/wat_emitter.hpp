@@ -707,7 +707,7 @@ private:
 
     // env host functions (include/host_modules/env.hpp:40-110,160-190)
     enum class host_fn : uint8_t { i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast, assert_is_concrete,
-                                   wasi_args_sizes_get, wasi_args_get, wasi_fd_write, wasi_proc_exit, wasi_random_get, print_str, dump_memory };
+                                   wasi_args_sizes_get, wasi_args_get, wasi_fd_write, wasi_proc_exit, wasi_random_get, print_str, dump_memory, unsupported };
     static bool host_lookup(const std::string &name, host_fn &out) {
         static const std::map<std::string, host_fn> table = {
             {"i32_private_const", host_fn::i32_private_const}, {"i64_private_const", host_fn::i64_private_const}, {"assert_equal", host_fn::assert_equal},
@@ -931,6 +931,7 @@ private:
             }
             break;
         }
+        case host_fn::unsupported: throw std::logic_error("wat: unresolved import");   // (step() reports these by name)
         default: host(f, rs); break;
         }
         return flow{};
@@ -956,7 +957,11 @@ private:
         case ins::unary_op: unary((op)i.o, i.width, i.sgn, rs); break;
         case ins::shift_op: shift((op)i.o, i.width, i.sgn, rs); break;
         case ins::binary_op: binary((op)i.o, i.width, i.sgn, rs); break;
-        case ins::host_call: return host_call((host_fn)i.o, rs);
+        case ins::host_call:
+            // imports resolve when they are CALLED in the reference (nonbatch_context.hpp:201-208): a module may import what the front end
+            // does not provide as long as it does not call it
+            if ((host_fn)i.o == host_fn::unsupported) throw std::invalid_argument("wat: call of " + unprovided_[(size_t)i.imm] + ", which the front end does not provide");
+            return host_call((host_fn)i.o, rs);
         case ins::func_call: return call((size_t)i.imm, rs, depth + 1);
         case ins::call_indirect: {                            // run_call_indirect (interpreter.hpp:372-398): the index is read with as_u32(), i.e. it must be a number
             value v = rs.pop();
@@ -1214,7 +1219,11 @@ private:
     // wabt would have parsed (not validated) the module for the reference; here an instruction applied to a value of the
     // other width is rejected (the handlers index operand bits by the instruction's width).  Host calls are checked for
     // operand COUNT only: the reference's own tests call assert_equal (param i64 i64) with i32 operands.
-    struct import_t { std::string module, field; };
+    struct import_t {
+        std::string module, field;
+        bool typed = false;                                   // its signature is known (a function the front end does not provide can then be
+        std::vector<uint8_t> params, results;                 // called in the text: the call fails when it is executed, as in the reference)
+    };
     func_t *cur_ = nullptr;                                   // the function being built
     std::vector<uint8_t> types_;                              // 32 / 64 / F32 / F64; 0 = any (a value popped in unreachable code)
     // the enclosing blocks of the instruction being added (the function body is the outermost), as WebAssembly validation keeps them
@@ -1428,12 +1437,23 @@ private:
         if (!end || *end) throw std::invalid_argument("wat: bad floating-point literal " + lit);
         return bits | sign;
     }
-    void emit_host(const std::string &module, const std::string &field) {
+    // a call of an import the front end does not provide: typed by the import's signature, failing when executed
+    bool emit_unprovided(const import_t &im) {
+        if (!im.typed) return false;
+        want_all(im.params, "call " + im.module + "." + im.field);
+        types_.insert(types_.end(), im.results.begin(), im.results.end());
+        unprovided_.push_back(printable(im.module + "." + im.field));
+        ins i; i.kind = ins::host_call; i.o = (uint8_t)host_fn::unsupported; i.imm = unprovided_.size() - 1; cur_->code.push_back(i);
+        return true;
+    }
+    void emit_host(const import_t &im) {
+        const std::string &module = im.module, &field = im.field;
         if (module == "wasi_snapshot_preview1") {
             static const std::map<std::string, std::pair<host_fn, int>> wasi = {       // function, operands (all i32); all but proc_exit return an i32 errno
                 {"args_sizes_get", {host_fn::wasi_args_sizes_get, 2}}, {"args_get", {host_fn::wasi_args_get, 2}}, {"fd_write", {host_fn::wasi_fd_write, 4}},
                 {"proc_exit", {host_fn::wasi_proc_exit, 1}}, {"random_get", {host_fn::wasi_random_get, 2}}};
             const auto it = wasi.find(field);
+            if (it == wasi.end() && emit_unprovided(im)) return;
             if (it == wasi.end()) throw std::invalid_argument("wat: wasi_snapshot_preview1." + printable(field) + " is not supported by the front end (args_sizes_get, args_get, fd_write, proc_exit, random_get are)");
             if (!has_memory_ && it->second.first != host_fn::wasi_proc_exit) throw std::invalid_argument("wat: a WASI call in a module without a memory");
             for (int j = 0; j < it->second.second; j++) want(32, "call wasi_snapshot_preview1." + field);
@@ -1441,8 +1461,9 @@ private:
             ins i; i.kind = ins::host_call; i.o = (uint8_t)it->second.first; cur_->code.push_back(i);
             return;
         }
+        host_fn f = host_fn::unsupported;
+        if ((module != "env" || !host_lookup(field, f)) && emit_unprovided(im)) return;
         if (module != "env") throw std::invalid_argument("wat: only the env and wasi_snapshot_preview1 host modules are supported (no bn254fr / vbn254fr / uint256 / ecc imports)");
-        host_fn f;
         if (!host_lookup(field, f)) throw std::invalid_argument("wat: env." + printable(field) + " is not supported by the front end");
         const std::string shown = "call env." + field;
         pop_type(shown);
@@ -1454,7 +1475,7 @@ private:
     }
     // a call by function index: imports first, then the module's own functions
     void emit_call(uint64_t index, const std::vector<import_t> &imports) {
-        if (index < imports.size()) { emit_host(imports[(size_t)index].module, imports[(size_t)index].field); return; }
+        if (index < imports.size()) { emit_host(imports[(size_t)index]); return; }
         const uint64_t fi = index - imports.size();
         if (fi >= funcs_.size()) throw std::invalid_argument("wat: call of an unknown function (" + std::to_string(index) + ")");
         const func_t &f = funcs_[(size_t)fi];
@@ -1653,17 +1674,17 @@ private:
         if (top.head() != "module") throw std::invalid_argument("wat: expected (module ...)");
         std::vector<import_t> imports;
         std::map<std::string, size_t> func_ids, data_ids, global_ids, type_ids, elem_ids;
-        std::vector<const sexpr *> bodies, elems, inline_elems;
+        std::vector<const sexpr *> bodies, elems, inline_elems, import_descs;
         std::string start;
         for (size_t i = 1; i < top.list.size(); i++) {
             const sexpr &f = top.list[i];
             if (f.head() == "import") {
                 // (import "env" "name" (func $id ...))
                 if (f.list.size() < 4 || f.list[3].head() != "func") throw std::invalid_argument("wat: unsupported import");
-                if (f.list[1].atom != "\"env\"" && f.list[1].atom != "\"wasi_snapshot_preview1\"") throw std::invalid_argument("wat: only the env and wasi_snapshot_preview1 host modules are supported (no bn254fr / vbn254fr / uint256 / ecc imports)");
                 if (!bodies.empty()) throw std::invalid_argument("wat: imports must come before the module's functions");
                 if (f.list[3].list.size() >= 2 && !f.list[3].list[1].is_list) func_ids[f.list[3].list[1].atom] = imports.size();
-                imports.push_back(import_t{unquote(f.list[1].atom), unquote(f.list[2].atom)});
+                imports.push_back(import_t{unquote(f.list[1].atom), unquote(f.list[2].atom), false, {}, {}});
+                import_descs.push_back(&f.list[3]);
             } else if (f.head() == "func") {
                 if (f.list.size() >= 2 && !f.list[1].is_list) func_ids[f.list[1].atom] = imports.size() + bodies.size();
                 bodies.push_back(&f);
@@ -1782,6 +1803,14 @@ private:
         // element segments: (elem [$id] [(table ..)] (offset? (i32.const n)) [func] $f ...) writes functions into the table at instantiation
         nimports_ = imports.size();
         const text_scope names{imports, func_ids, data_ids, global_ids, type_ids, elem_ids, {}};
+        for (size_t k = 0; k < imports.size(); k++) {          // (func $id? (type t) | (param ..)* (result ..)*): the import's signature, if it is spelled out
+            const sexpr &d = *import_descs[k];
+            size_t j = (d.list.size() >= 2 && !d.list[1].is_list) ? 2 : 1;
+            try {
+                const uint64_t t = type_use(d.list, j, names);
+                if (j == d.list.size()) { imports[k].typed = true; imports[k].params = sigs_[(size_t)t].params; imports[k].results = sigs_[(size_t)t].results; }
+            } catch (const std::invalid_argument &) {}       // a signature over types the front end does not know: the import stays untyped
+        }
         const auto functions_from = [&](const sexpr &e, size_t j) {
             std::vector<int64_t> fs;
             for (; j < e.list.size(); j++) {
@@ -2290,10 +2319,10 @@ private:
             case 2: {                                         // imports: functions of env only
                 const size_t n = (size_t)s.uleb();
                 for (size_t i = 0; i < n; i++) {
-                    import_t im{s.name(), s.name()};
+                    import_t im{s.name(), s.name(), false, {}, {}};
                     if (s.byte() != 0x00) throw std::invalid_argument("wasm: only function imports are supported (" + printable(im.module + "." + im.field) + ")");
-                    s.uleb();
-                    if (im.module != "env" && im.module != "wasi_snapshot_preview1") throw std::invalid_argument("wasm: only the env and wasi_snapshot_preview1 host modules are supported (no bn254fr / vbn254fr / uint256 / ecc imports)");
+                    const uint64_t t = s.uleb();
+                    if (t < types.size() && types[(size_t)t].usable) { im.typed = true; im.params = types[(size_t)t].params; im.results = types[(size_t)t].results; }
                     imports.push_back(im);
                 }
                 break;
@@ -2480,6 +2509,7 @@ private:
         }
     }
 
+    std::vector<std::string> unprovided_;                     // names of the imports called in the text that the front end does not provide
     std::vector<std::vector<uint8_t>> args_;
     std::set<int> private_;
     bool echo_ = false;

@@ -334,9 +334,9 @@ def test_wat_emitter_on_the_repo_fixture(pr, oracle):
 
 def test_wat_emitter_rejects_what_it_does_not_support(pr):
     for text, why in (("(module (func $f) (export \"_start\" (func $f)) (tag $e))", "module field"),
-                      ("(module (import \"wasi\" \"x\" (func $x)) (func $f) (export \"_start\" (func $f)))", "host modules are supported"),
+                      ("(module (import \"wasi\" \"x\" (func $x)) (func $f (call $x)) (export \"_start\" (func $f)))", "call of wasi.x, which the front end does not provide"),
                       ("(module (func $f (drop (f64.fma (f64.const 1) (f64.const 2)))) (export \"_start\" (func $f)))", "unsupported instruction"),
-                      ("(module (func $f (drop (ref.null func))) (export \"_start\" (func $f)))", "unsupported instruction"),
+                      ("(module (func $f (drop (ref.null any))) (export \"_start\" (func $f)))", "ref.null of an unknown type"),
                       ("(module (func $f (drop (i64.load (i32.const 0)))) (export \"_start\" (func $f)))", "without a memory"),
                       ("(module (func $f)", "unbalanced"),
                       ("(module (func $f))", "_start")):
@@ -453,12 +453,12 @@ def test_wasm_binary_front_end_rejects_what_it_does_not_support(pr):
                       (b"\0asm\x01\0\0\0", "_start")):
         with pytest.raises(pr.ProverError, match=why):
             pr.wat_emit(data, 64)
-    # an opcode outside the subset inside _start (table.get = 0x25)
+    # an opcode the reference's interpreter does not have either, inside _start (try = 0x06)
     text = '(module (import "env" "assert_equal" (func $e (param i32 i32))) (func $f (call $e (i32.const 1) (i32.const 1))) (export "_start" (func $f)))'
     wasm = bytearray(U.wat_to_wasm(text, custom_section=False))
     at = wasm.rindex(b"\x41\x01\x41\x01")
-    wasm[at] = 0x25
-    with pytest.raises(pr.ProverError, match="unsupported instruction 0x25"):
+    wasm[at] = 0x06
+    with pytest.raises(pr.ProverError, match="unsupported instruction 0x06"):
         pr.wat_emit(bytes(wasm), 64)
 
 
@@ -678,10 +678,15 @@ def test_guest_arguments_and_wasi_front_end(pr):
                       ("(drop (call $args (i64.const 0) (i32.const 64)))", "type mismatch")):
         with pytest.raises(pr.ProverError, match=why):
             pr.wat_emit(head + body + tail, 64, args=[b"ab", b"cdef"])
-    with pytest.raises(pr.ProverError, match="environ_get is not supported"):
+    with pytest.raises(pr.ProverError, match="call of wasi_snapshot_preview1.environ_get, which the front end does not provide"):
         pr.wat_emit('(module (import "wasi_snapshot_preview1" "environ_get" (func $e (param i32 i32) (result i32))) (memory 1) (func $t (drop (call $e (i32.const 0) (i32.const 0)))) (export "_start" (func $t)))', 64)
-    with pytest.raises(pr.ProverError, match="env and wasi_snapshot_preview1"):
-        pr.wat_emit('(module (import "bn254fr" "bn254fr_alloc" (func $e (param i32))) (func $t) (export "_start" (func $t)))', 64)
+    # imports resolve when they are called (as in the reference): a module may import what the front end does not provide
+    bn = '(module (import "bn254fr" "bn254fr_alloc" (func $e (param i32))) (func $t (if (i32.const %d) (then (call $e (i32.const 8))))) (export "_start" (func $t)))'
+    assert pr.wat_emit(bn % 0, 64)[4]["violated_constraints"] == 0
+    with pytest.raises(pr.ProverError, match="call of bn254fr.bn254fr_alloc, which the front end does not provide"):
+        pr.wat_emit(bn % 1, 64)
+    with pytest.raises(pr.ProverError, match="env and wasi_snapshot_preview1"):      # without a signature the call cannot even be typed
+        pr.wat_emit('(module (import "bn254fr" "bn254fr_alloc" (func $e)) (func $t (call $e (i32.const 8))) (export "_start" (func $t)))'.replace("(func $e)", "(func $e (param v128))"), 64)
 
 
 def test_indirect_call_front_end(pr):
@@ -750,7 +755,7 @@ def test_env_output_functions(pr):
     assert len(kinds) == 0 and st["violated_constraints"] == 0
     with pytest.raises(pr.ProverError, match="reaches outside the memory"):
         pr.wat_emit(prog.replace("(i32.const 8) (i32.const 3)) (call $d", "(i32.const 65534) (i32.const 3)) (call $d"), 64)
-    with pytest.raises(pr.ProverError, match="env.file_get is not supported"):
+    with pytest.raises(pr.ProverError, match="call of env.file_get, which the front end does not provide"):
         pr.wat_emit('(module (import "env" "file_get" (func $p (param i64 i64) (result i32))) (memory 1) (func (export "_start") (drop (call $p (i64.const 8) (i64.const 3)))))', 64)
 
 
