@@ -128,6 +128,8 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
  * instructions -- every instruction the reference's interpreter dispatches (interpreter_impl.hpp:2405-2548) -- and
  * env.i32_private_const, i64_private_const, assert_equal, assert_zero, assert_one, assert_constant, witness_cast_u32 / _u64,
  * assert_is_concrete, print_str, dump_memory; wasi args_sizes_get, args_get, fd_write, proc_exit, random_get (lgrp_wat_args below).
+ * A run is bounded to 2 x 10^8 executed instructions (loops make running time a property of the guest); the environment variable
+ * LGRP_WAT_STEP_LIMIT sets another bound, 0 none.
  * Not provided: the bn254fr / vbn254fr / uint256 / ecc host modules and the other WASI functions -- a module may import them (imports
  * resolve when they are called, as in the reference); CALLING one is an LGRP error naming it.  Refused when the module is read:
  * passive element segments, imported memories / tables / globals.

@@ -31,6 +31,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -125,6 +126,11 @@ public:
     explicit wat_program(const std::string &data) {
         if (data.size() >= 4 && data.compare(0, 4, std::string("\0asm", 4)) == 0) parse_binary(data);
         else parse_text(data);
+        if (const char *limit = getenv("LGRP_WAT_STEP_LIMIT")) {   // executed instructions per run (default 2 x 10^8); 0 = no bound
+            char *end = nullptr;
+            const unsigned long long n = strtoull(limit, &end, 10);
+            if (end && !*end && *limit) step_limit_ = n ? n : ~0ULL;
+        }
     }
 
     // one execution of _start on the machine (rows leave through the machine's packer as witnesses are released)
