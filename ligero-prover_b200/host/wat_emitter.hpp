@@ -361,26 +361,34 @@ private:
     enum class op { clz, ctz, popcnt, add, sub, mul, div, rem, and_, or_, xor_, shl, shr, rotl, rotr, eqz, eq, ne, lt, gt, le, ge,
                     extend8, extend16, extend32, extend_i32, wrap };
 
+    // a number in a stack slot, written in place: instructions whose operands are all numbers touch no witness, so they replace the top
+    // of the stack instead of popping and pushing values (which carry a witness handle, a bit vector and a frame pointer along)
+    static void set_number(value &slot, bool is64, uint64_t v) { slot.num = is64 ? v : (uint64_t)(uint32_t)v; slot.is64 = is64; slot.isf = false; }
+    static void unary_number(op o, int w, bool sgn, uint64_t num, uint64_t &r, bool &r64) {
+        const uint64_t mask = w == 64 ? ~0ULL : 0xFFFFFFFFULL, x = num & mask;
+        r64 = false;
+        switch (o) {
+        case op::clz: r = x ? (uint32_t)(__builtin_clzll(x) - (64 - w)) : (uint32_t)w; break;
+        case op::ctz: r = x ? (uint32_t)__builtin_ctzll(x) : (uint32_t)w; break;
+        case op::popcnt: r = (uint32_t)__builtin_popcountll(x); break;
+        case op::eqz: r = x == 0; r64 = w == 64; break;
+        case op::extend8: r = (uint64_t)(int64_t)(int8_t)x; r64 = w == 64; break;
+        case op::extend16: r = w == 64 ? (uint64_t)(uint16_t)x : (uint64_t)(int64_t)(int16_t)x; r64 = w == 64; break;   // (sic: the i64 form zero-extends, :1208)
+        case op::extend32: r = (uint64_t)(int64_t)(int32_t)x; r64 = true; break;
+        case op::extend_i32: r = sgn ? (uint64_t)(int64_t)(int32_t)(uint32_t)num : (uint64_t)(uint32_t)num; r64 = true; break;
+        case op::wrap: r = (uint32_t)num; break;
+        default: throw std::logic_error("wat: not a unary instruction");
+        }
+    }
     static void unary(op o, int w, bool sgn, run_state &rs) {
         witness_machine &m = rs.m;
-        value sx = rs.pop();
-        const uint64_t mask = w == 64 ? ~0ULL : 0xFFFFFFFFULL;
-        if (sx.kind == value::NUM) {
-            const uint64_t x = sx.num & mask;
-            switch (o) {
-            case op::clz: rs.push(value::u32(x ? (uint32_t)(__builtin_clzll(x) - (64 - w)) : (uint32_t)w)); break;
-            case op::ctz: rs.push(value::u32(x ? (uint32_t)__builtin_ctzll(x) : (uint32_t)w)); break;
-            case op::popcnt: rs.push(value::u32((uint32_t)__builtin_popcountll(x))); break;
-            case op::eqz: rs.push(numeric(w == 64, x == 0)); break;
-            case op::extend8: rs.push(numeric(w == 64, (uint64_t)(int64_t)(int8_t)x)); break;
-            case op::extend16: rs.push(numeric(w == 64, w == 64 ? (uint64_t)(uint16_t)x : (uint64_t)(int64_t)(int16_t)x)); break;   // (sic: the i64 form zero-extends, :1208)
-            case op::extend32: rs.push(value::u64((uint64_t)(int64_t)(int32_t)x)); break;
-            case op::extend_i32: rs.push(value::u64(sgn ? (uint64_t)(int64_t)(int32_t)(uint32_t)sx.num : (uint64_t)(uint32_t)sx.num)); break;
-            case op::wrap: rs.push(value::u32((uint32_t)sx.num)); break;
-            default: throw std::logic_error("wat: not a unary instruction");
-            }
+        if (!rs.stack.empty() && rs.stack.back().kind == value::NUM) {
+            uint64_t r; bool r64;
+            unary_number(o, w, sgn, rs.stack.back().num, r, r64);
+            set_number(rs.stack.back(), r64, r);
             return;
         }
+        value sx = rs.pop();
         rs.st.arithmetic_ops++;
         const size_t nb = (size_t)w, msb = nb - 1;
         switch (o) {
@@ -443,6 +451,21 @@ private:
     // shl / shr_s / shr_u / rotl / rotr (:706-886): the count is read off its witnesses (no constraint), the bits are re-wired
     static void shift(op o, int w, bool sgn, run_state &rs) {
         witness_machine &m = rs.m;
+        if (rs.stack.size() >= 2 && rs.stack.back().kind == value::NUM && rs.stack[rs.stack.size() - 2].kind == value::NUM) {
+            const uint32_t n = (uint32_t)rs.stack.back().num % (uint32_t)w;
+            rs.stack.pop_back();
+            const uint64_t mask = w == 64 ? ~0ULL : 0xFFFFFFFFULL, x = rs.stack.back().num & mask;
+            uint64_t r = 0;
+            switch (o) {
+            case op::shl: r = x << n; break;
+            case op::shr: r = sgn ? (uint64_t)(sext(x, w) >> n) : x >> n; break;
+            case op::rotl: r = n ? (x << n) | (x >> ((uint32_t)w - n)) : x; break;
+            case op::rotr: r = n ? (x >> n) | (x << ((uint32_t)w - n)) : x; break;
+            default: throw std::logic_error("wat: not a shift");
+            }
+            set_number(rs.stack.back(), w == 64, r & mask);
+            return;
+        }
         value cnt = rs.pop();
         value sx = rs.pop();
         const size_t nb = (size_t)w, msb = nb - 1;
@@ -492,43 +515,46 @@ private:
         }
     }
 
+    static void binary_numbers(op o, int w, bool sgn, uint64_t xin, uint64_t yin, uint64_t &r, bool &r64) {
+        const uint64_t mask = w == 64 ? ~0ULL : 0xFFFFFFFFULL, x = xin & mask, y = yin & mask;
+        const int64_t xs = sext(x, w), ys = sext(y, w);
+        r64 = w == 64;
+        switch (o) {
+        case op::add: r = (x + y) & mask; break;
+        case op::sub: r = (x - y) & mask; break;
+        case op::mul: r = (x * y) & mask; break;
+        case op::div: case op::rem:
+            if (!y) throw std::invalid_argument("wat: integer divide by zero");
+            if (sgn) {
+                if (ys == -1) r = o == op::div ? (uint64_t)(0 - (uint64_t)xs) : 0;    // (INT_MIN / -1 traps in WASM; wraps here)
+                else r = (uint64_t)(o == op::div ? xs / ys : xs % ys);
+            } else r = o == op::div ? x / y : x % y;
+            r &= mask;
+            break;
+        case op::and_: r = x & y; break;
+        case op::or_: r = x | y; break;
+        case op::xor_: r = x ^ y; break;
+        case op::eq: r = x == y; r64 = false; break;
+        case op::ne: r = x != y; r64 = false; break;
+        case op::lt: r = sgn ? xs < ys : x < y; break;
+        case op::gt: r = sgn ? xs > ys : x > y; break;
+        case op::le: r = sgn ? xs <= ys : x <= y; break;
+        case op::ge: r = sgn ? xs >= ys : x >= y; break;
+        default: throw std::logic_error("wat: not a binary instruction");
+        }
+    }
     static void binary(op o, int w, bool sgn, run_state &rs) {
         witness_machine &m = rs.m;
+        if (rs.stack.size() >= 2 && rs.stack.back().kind == value::NUM && rs.stack[rs.stack.size() - 2].kind == value::NUM) {
+            uint64_t r; bool r64;
+            binary_numbers(o, w, sgn, rs.stack[rs.stack.size() - 2].num, rs.stack.back().num, r, r64);
+            rs.stack.pop_back();
+            set_number(rs.stack.back(), r64, r);
+            return;
+        }
         value sy = rs.pop();
         value sx = rs.pop();
         const size_t nb = (size_t)w, msb = nb - 1;
-        const uint64_t mask = w == 64 ? ~0ULL : 0xFFFFFFFFULL;
-        if (sx.kind == value::NUM && sy.kind == value::NUM) {
-            const uint64_t x = sx.num & mask, y = sy.num & mask;
-            const int64_t xs = sext(x, w), ys = sext(y, w);
-            const bool is64 = w == 64;
-            switch (o) {
-            case op::add: rs.push(numeric(is64, (x + y) & mask)); break;
-            case op::sub: rs.push(numeric(is64, (x - y) & mask)); break;
-            case op::mul: rs.push(numeric(is64, (x * y) & mask)); break;
-            case op::div: case op::rem: {
-                if (!y) throw std::invalid_argument("wat: integer divide by zero");
-                uint64_t r;
-                if (sgn) {
-                    if (ys == -1) r = o == op::div ? (uint64_t)(0 - (uint64_t)xs) : 0;    // (INT_MIN / -1 traps in WASM; wraps here)
-                    else r = (uint64_t)(o == op::div ? xs / ys : xs % ys);
-                } else r = o == op::div ? x / y : x % y;
-                rs.push(numeric(is64, r & mask));
-                break;
-            }
-            case op::and_: rs.push(numeric(is64, x & y)); break;
-            case op::or_: rs.push(numeric(is64, x | y)); break;
-            case op::xor_: rs.push(numeric(is64, x ^ y)); break;
-            case op::eq: rs.push(value::u32(x == y)); break;
-            case op::ne: rs.push(value::u32(x != y)); break;
-            case op::lt: rs.push(numeric(is64, sgn ? xs < ys : x < y)); break;
-            case op::gt: rs.push(numeric(is64, sgn ? xs > ys : x > y)); break;
-            case op::le: rs.push(numeric(is64, sgn ? xs <= ys : x <= y)); break;
-            case op::ge: rs.push(numeric(is64, sgn ? xs >= ys : x >= y)); break;
-            default: throw std::logic_error("wat: not a binary instruction");
-            }
-            return;
-        }
         rs.st.arithmetic_ops++;
         switch (o) {
         case op::add: case op::sub: case op::mul: {            // :265-392: the overflowing result, decomposed, top bits dropped
@@ -956,7 +982,12 @@ private:
         const ins &i = f.code[pc];
         if (++rs.steps > rs.step_limit) throw std::invalid_argument("wat: step budget exceeded (" + std::to_string(rs.step_limit) + " instructions)");
         switch (i.kind) {
-        case ins::konst: rs.push(of_bits(i.width, i.imm)); break;
+        case ins::konst: {
+            rs.stack.emplace_back();
+            value &v = rs.stack.back();
+            v.num = i.imm; v.is64 = i.width == 64 || i.width == F64; v.isf = is_float(i.width);
+            break;
+        }
         case ins::float_op: floating(i, rs); break;
         case ins::global_get: rs.push(of_bits(globals_[(size_t)i.imm].type, rs.globals[(size_t)i.imm])); break;   // exec_global_get / set (interpreter_impl.hpp:1902-1924):
         case ins::global_set: rs.globals[(size_t)i.imm] = pop_number(rs, "global.set").num; break;                // a global holds a native number
@@ -986,9 +1017,25 @@ private:
         case ins::table_fill: case ins::table_copy: case ins::table_init: case ins::elem_drop:
             reference_op(i, rs);
             break;
-        case ins::local_get: rs.push(rs.frames.back()->locals[(size_t)i.imm].share()); break;
-        case ins::local_set: rs.frames.back()->locals[(size_t)i.imm] = rs.pop(); break;
-        case ins::local_tee: rs.frames.back()->locals[(size_t)i.imm] = rs.stack.back().share(); break;
+        case ins::local_get: {
+            const value &l = rs.frames.back()->locals[(size_t)i.imm];
+            if (l.kind != value::NUM) { rs.push(l.share()); break; }
+            rs.stack.emplace_back();
+            value &v = rs.stack.back();
+            v.num = l.num; v.is64 = l.is64; v.isf = l.isf;
+            break;
+        }
+        case ins::local_set: case ins::local_tee: {
+            value &l = rs.frames.back()->locals[(size_t)i.imm];
+            if (rs.stack.empty()) throw std::invalid_argument("wat: operand stack underflow");
+            value &top = rs.stack.back();
+            if (l.kind == value::NUM && top.kind == value::NUM) {              // number over number: member-wise, nothing is released
+                l.num = top.num; l.is64 = top.is64; l.isf = top.isf;
+                if (i.kind == ins::local_set) rs.stack.pop_back();
+            } else if (i.kind == ins::local_set) l = rs.pop();
+            else l = top.share();
+            break;
+        }
         case ins::select: select(rs); break;
         case ins::drop: rs.pop(); break;                      // exec_drop (interpreter_impl.hpp:112-116)
         case ins::nop: break;
@@ -1133,18 +1180,37 @@ private:
     }
     // do_load (interpreter_impl.hpp:2206-2228): the address is read as a number; a range that holds a stored witness gives a new witness
     static void load(const ins &i, run_state &rs) {
-        value tmp = rs.pop();
-        const uint64_t ea = (uint64_t)(uint32_t)rs.make_numeric(std::move(tmp)) + i.imm, n = i.o;
+        const bool plain = !rs.stack.empty() && rs.stack.back().kind == value::NUM;      // a number as the address: the slot is reused for the result
+        uint64_t ea;
+        if (plain) ea = (uint64_t)(uint32_t)rs.stack.back().num + i.imm;
+        else { value tmp = rs.pop(); ea = (uint64_t)(uint32_t)rs.make_numeric(std::move(tmp)) + i.imm; }
+        const uint64_t n = i.o;
         if (ea + n > rs.memory.size()) throw std::invalid_argument("wat: invalid memory address");
         uint64_t c = 0;
         memcpy(&c, rs.memory.data() + ea, (size_t)n);
         if (i.sgn && n < 8 && (c >> (8 * n - 1)) & 1) c |= ~0ULL << (8 * n);
         if (bytes_of(i.width) == 4) c &= 0xFFFFFFFFULL;
+        if (plain) {
+            if (!rs.secrets.iv.empty() && rs.secrets.intersects((uint32_t)ea, (uint32_t)(ea + n))) rs.stack.pop_back();
+            else { value &v = rs.stack.back(); v.num = c; v.is64 = i.width == 64 || i.width == F64; v.isf = is_float(i.width); return; }
+        }
         if (rs.secrets.intersects((uint32_t)ea, (uint32_t)(ea + n))) rs.push(value::of(rs.make_witness(of_bits(i.width, c))));   // (a float here traps, as in the reference)
         else rs.push(of_bits(i.width, c));
     }
     // do_store (:2310-2344): the value is read as a number and its witnesses are let go; the range is marked iff it was not a number
     static void store(const ins &i, run_state &rs) {
+        const size_t depth = rs.stack.size();
+        if (depth >= 2 && rs.stack[depth - 1].kind == value::NUM && rs.stack[depth - 2].kind == value::NUM) {      // a number to an address that is a number
+            const uint64_t ea = (uint64_t)(uint32_t)rs.stack[depth - 2].num + i.imm, n = i.o;
+            if (ea + n > rs.memory.size()) throw std::invalid_argument("wat: invalid memory address");
+            if (!rs.secrets.iv.empty()) rs.secrets.subtract((uint32_t)ea, (uint32_t)(ea + n));
+            uint64_t c = rs.stack[depth - 1].num;
+            if (bytes_of(i.width) == 4) c &= 0xFFFFFFFFULL;
+            memcpy(rs.memory.data() + ea, &c, (size_t)n);
+            rs.stack.pop_back();
+            rs.stack.pop_back();
+            return;
+        }
         value tmp = rs.pop();
         value addr = rs.pop();
         const uint64_t ea = (uint64_t)(uint32_t)rs.make_numeric(std::move(addr)) + i.imm, n = i.o;
