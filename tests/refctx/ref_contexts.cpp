@@ -4,7 +4,7 @@
 //   include/zkp/nonbatch_context.hpp   stage 1/2/3 contexts (the row schedule)
 //   include/zkp/backend/*.hpp          ligetron_backend + witness_manager (witness -> row packing, masks, randomness)
 //   include/interpreter*.hpp           the WASM interpreter's opcode semantics over witnesses
-//   include/host_modules/{env,vbn254fr}.hpp   the two host modules the test programs call
+//   include/host_modules/{env,vbn254fr,wasi_preview1}.hpp   the host modules the test programs call
 //   include/zkp/{hash,merkle_tree,random}.hpp, src/bn254.cpp   transcript, tree, field
 // and what this file adds is ONLY what `main` of src/webgpu_prover.cpp:228-471 does around them (the three passes, the
 // seeds, the self-check) plus a hand-assembled instruction list where the reference would call wabt (absent here).
