@@ -770,3 +770,12 @@ def test_module_spelled_the_way_wasm2wat_prints_compiled_code(pr):
     assert wrong[4]["violated_constraints"] == 1                      # 8^4 mod 2^16 is not 2401
     public = pr.wat_emit(text, 64, args=[b"Ligero\0", (7).to_bytes(8, "little")], private_indices=[])
     assert public[4]["quadratic_slots"] < out[4]["quadratic_slots"]   # a public argument is a number: the squaring commits nothing
+
+
+def test_every_family_interleaved_holds_its_assertions(pr):
+    """needs no reference run: tests/golden/kitchen_sink.wat asserts what it computes (nine assertions over every instruction family)"""
+    import refctx_util as U
+    text = open(os.path.join(ROOT, "tests", "golden", "kitchen_sink.wat")).read()
+    for spelling in (text, U.wat_to_wasm(text), U.wat_to_plain(text)):
+        st = pr.wat_emit(spelling, 64)[4]
+        assert st["violated_constraints"] == 0 and st["asserts"] == 9 and st["private_consts"] == 11

@@ -563,6 +563,20 @@ def test_wat_emitter_on_a_module_spelled_like_compiled_code_against_the_referenc
         assert list(kinds) == list(st["kinds"]) and np.array_equal(vals, st["values"]) and np.array_equal(coefs, st["coefs"]) and const_sum == st["const_sum"]
 
 
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+def test_wat_emitter_on_every_family_interleaved_against_the_reference(oracle, pr):
+    """tests/golden/kitchen_sink.wat: witnesses held in locals across loops and branches, stores and loads of witnesses inside
+    indirectly called functions, floats and globals between them, a value-carrying block left by br_table with witnesses above
+    the label, an early return that drops live bit vectors, a typed select on references -- 40 row events, the same through
+    the reference's interpreter and the emitter in all three spellings"""
+    text = open(os.path.join(U.HERE, "golden", "kitchen_sink.wat")).read()
+    raw = U.run_reference_on_wat(text, 256, seed_byte=10)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7 and len(raw["kinds"]) == 40
+    st = _reference_rows(raw)
+    for spelling in (text, U.wat_to_wasm(text), U.wat_to_plain(text)):
+        _emitter_equals_reference_rows(pr, spelling, st)
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
