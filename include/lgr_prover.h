@@ -134,7 +134,7 @@ int lgrp_prove(lgr_ctx *ctx, const lgrp_statement *st, lgrp_proof **out);
  * resolve when they are called, as in the reference); CALLING one is an LGRP error naming it.  Refused when the module is read:
  * passive element segments, imported memories / tables / globals.
  * It stands where include/invoke.hpp:79-98 + include/interpreter_impl.hpp + the headers under include/zkp/backend/ stand in
- * the reference.  It is not a general WASM machine, but for what it takes it gives every instruction the reference's
+ * the reference.  It gives every instruction the reference's
  * meaning -- the same witnesses, released in the same order, with the same linear-test randomness -- so the rows, the
  * stage-2 coefficient rows and const_sum are the reference's, element for element: checked against runs of the
  * reference's own interpreter / env and WASI modules / backend / witness manager (tests/refctx/ref_contexts.cpp,
