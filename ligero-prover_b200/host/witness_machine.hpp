@@ -135,10 +135,11 @@ public:
         rng_.next(limbs);
         return lgr::host::from_u32(limbs);
     }
-    void coef_add(wid w, const Fr &r) { w_[w].coef = lgr::host::add(w_[w].coef, r); }
-    void coef_sub(wid w, const Fr &r) { w_[w].coef = sub(w_[w].coef, r); }
-    void const_add(const Fr &r) { const_sum_ = lgr::host::add(const_sum_, r); }
-    void const_sub(const Fr &r) { const_sum_ = sub(const_sum_, r); }
+    // (without a seed every rho is zero: the coefficient rows and const_sum stay zero and nothing needs adding)
+    void coef_add(wid w, const Fr &r) { if (seeded_) w_[w].coef = lgr::host::add(w_[w].coef, r); }
+    void coef_sub(wid w, const Fr &r) { if (seeded_) w_[w].coef = sub(w_[w].coef, r); }
+    void const_add(const Fr &r) { if (seeded_) const_sum_ = lgr::host::add(const_sum_, r); }
+    void const_sub(const Fr &r) { if (seeded_) const_sum_ = sub(const_sum_, r); }
 
     // constrain_equal (witness_manager.hpp:421-429): one draw, +r on a, -r on b
     void constrain_equal(wid a, wid b) {
@@ -183,10 +184,10 @@ public:
 
     // commit_release_witness (:117-186)
     void release(wid w) {
-        uint32_t v[3][8], c[3][8];
+        // (an Fr is four little-endian 64-bit limbs: the same 32 bytes as the eight 32-bit limbs of a row element)
+        const auto limbs = [](const Fr &x) { return reinterpret_cast<const uint32_t *>(x.v); };
         if (w_[w].slot == none) {
-            lgr::host::to_u32(v[0], w_[w].val); lgr::host::to_u32(c[0], w_[w].coef);
-            pk_.push_linear(v[0], c[0]);
+            pk_.push_linear(limbs(w_[w].val), limbs(w_[w].coef));
             nlinear_++;
             free_w_.push_back(w);
             return;
@@ -195,8 +196,8 @@ public:
         slot &s = slots_[si];
         s.ready[w_[w].pos] = true;
         if (!(s.ready[0] && s.ready[1] && s.ready[2])) return;
-        for (int j = 0; j < 3; j++) { lgr::host::to_u32(v[j], w_[s.w[j]].val); lgr::host::to_u32(c[j], w_[s.w[j]].coef); }
-        pk_.push_quadratic(v[0], v[1], v[2], c[0], c[1], c[2]);
+        const wit &x = w_[s.w[0]], &y = w_[s.w[1]], &z = w_[s.w[2]];
+        pk_.push_quadratic(limbs(x.val), limbs(y.val), limbs(z.val), limbs(x.coef), limbs(y.coef), limbs(z.coef));
         for (int j = 0; j < 3; j++) free_w_.push_back(s.w[j]);
         free_s_.push_back(si);
     }
