@@ -1926,7 +1926,8 @@ private:
     static void blocktype(const std::vector<sexpr> &list, size_t &j, std::vector<uint8_t> &params, std::vector<uint8_t> &results) {
         for (; j < list.size() && list[j].is_list && (list[j].head() == "param" || list[j].head() == "result" || list[j].head() == "type"); j++) {
             if (list[j].head() == "type") throw std::invalid_argument("wat: block types by index are not supported in text");
-            for (size_t t = 1; t < list[j].list.size(); t++) (list[j].head() == "param" ? params : results).push_back(width_of(list[j].list[t].atom));
+            const size_t first = (list[j].list.size() == 3 && !list[j].list[1].is_list && !list[j].list[1].atom.empty() && list[j].list[1].atom[0] == '$') ? 2 : 1;   // (param $name t)
+            for (size_t t = first; t < list[j].list.size(); t++) (list[j].head() == "param" ? params : results).push_back(width_of(list[j].list[t].atom));
         }
     }
     // the type use after call_indirect: (type $t) and / or (param ..)* (result ..)*, from list[j] on -> type index
