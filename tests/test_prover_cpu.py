@@ -779,3 +779,22 @@ def test_every_family_interleaved_holds_its_assertions(pr):
     for spelling in (text, U.wat_to_wasm(text), U.wat_to_plain(text)):
         st = pr.wat_emit(spelling, 64)[4]
         assert st["violated_constraints"] == 0 and st["asserts"] == 9 and st["private_consts"] == 11
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference tree not present")
+def test_all_programs_of_the_reference_in_three_spellings(pr):
+    """all 69 programs of the reference's tests/, read where they lie: the WebAssembly binary assembled from each (what
+    `webgpu_prover` is given after wat2wasm) and its plain-instruction spelling give the rows of the folded text, coefficient
+    rows and const_sum included"""
+    import glob
+    import refctx_util as U
+    files = sorted(glob.glob("/root/reference/tests/*.wat"))
+    assert len(files) == 69
+    seed = bytes(range(32))
+    for path in files:
+        text = open(path).read()
+        a = pr.wat_emit(text, 64, seed)
+        assert a[4]["violated_constraints"] == 0, path
+        for spelling in (U.wat_to_wasm(text), U.wat_to_plain(text)):
+            b = pr.wat_emit(spelling, 64, seed)
+            assert list(a[0]) == list(b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3], path
