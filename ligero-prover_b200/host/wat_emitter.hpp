@@ -682,6 +682,17 @@ private:
         }
         const F y = get_float<F>(pop_number(rs, "a floating-point instruction"));
         const F x = get_float<F>(pop_number(rs, "a floating-point instruction"));
+        // two NaN operands: SSE returns the FIRST SOURCE of the instruction, quieted -- and which C++ operand that is, is the
+        // compiler's choice for the commutative operations.  The reference's handlers (interpreter_impl.hpp:1478-1522), compiled
+        // with GCC 13 at -O1 and at its release -O3 alike, return the FIRST operand's NaN for add, sub, mul and div; this compiler,
+        // inlining the same expressions here, commuted add and mul (found by the differential test).  Spelled out, so that it
+        // does not depend on how this file is compiled
+        if (o <= fop::div && std::isnan(x) && std::isnan(y)) {
+            value r = put_float<F>(x);
+            r.num |= sizeof(F) == 4 ? 0x00400000ULL : 0x0008000000000000ULL;
+            rs.push(std::move(r));
+            return;
+        }
         switch (o) {
         case fop::add: rs.push(put_float<F>(x + y)); break;
         case fop::sub: rs.push(put_float<F>(x - y)); break;

@@ -1148,3 +1148,23 @@ def rand_float_program(rng, nstmt=10, depth=3):
     head = WAT_HEAD_BOTH[:WAT_HEAD_BOTH.index("(func $t")]
     return (head + "(global $g (mut i64) (i64.const 5))\n(global $h (mut i32) (i32.const -7))\n(global $k i64 (i64.const 0x123456789))\n(memory 1)\n"
             "(func $t (local $a f32) (local $b f32) (local $c f64) (local $d f64)\n" + "\n".join(body) + "\n" + WAT_TAIL)
+
+
+def rand_mixed_program(rng, nmem=10, nfloat=8):
+    """statements of rand_memory_program and rand_float_program shuffled into ONE function (each list keeps its own order): witness
+    stores / loads / bulk memory operations between floating-point arithmetic, conversions, globals and float memory traffic.
+    The float statements use their own memory window (1064 ...), so no float load meets a stored witness"""
+    import re
+    mem, flt = rand_memory_program(rng, nstmt=nmem), rand_float_program(rng, nstmt=nfloat)
+    body = lambda text: text[text.index("\n", text.index("(func $t")) + 1:text.rindex(WAT_TAIL)].split("\n")
+    fbody = [re.sub(r"\(i32\.const (64|72|80)\)\)", lambda m: "(i32.const %d))" % (int(m.group(1)) + 1000), line) if ("load" in line or "store" in line) else line for line in body(flt)]
+    fbody = [re.sub(r"\(i32\.const (64|72|80)\) ", lambda m: "(i32.const %d) " % (int(m.group(1)) + 1000), line) if ".store" in line else line for line in fbody]
+    mbody = body(mem)
+    merged = []
+    while mbody or fbody:
+        src = mbody if (mbody and (not fbody or rng.random() < len(mbody) / (len(mbody) + len(fbody)))) else fbody
+        merged.append(src.pop(0))
+    head = WAT_HEAD_BOTH[:WAT_HEAD_BOTH.index("(func $t")]
+    seg = mem[mem.index("(data $seg"):mem.index("\n", mem.index("(data $seg")) + 1]
+    return (head + "(global $g (mut i64) (i64.const 5))\n(global $h (mut i32) (i32.const -7))\n(global $k i64 (i64.const 0x123456789))\n(memory 1)\n" + seg +
+            "(func $t (local $a f32) (local $b f32) (local $c f64) (local $d f64)\n" + "\n".join(merged) + "\n" + WAT_TAIL)

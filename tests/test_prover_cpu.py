@@ -627,6 +627,8 @@ def test_floating_point_and_globals_front_end(pr):
             '(call $eq (call $p32 (i32.reinterpret_f32 (f32.max (f32.const -0.0) (f32.const 0.0)))) (i32.const 0))\n'                 # the second operand wins a tie
             '(call $eq (call $p32 (i32.reinterpret_f32 (f32.max (f32.const 0.0) (f32.const -0.0)))) (i32.const 0x80000000))\n'
             '(call $eq (call $p32 (i32.reinterpret_f32 (f32.min (f32.const nan:0x1) (f32.const 1)))) (i32.const 0x7fc00000))\n'
+            '(call $eq (call $p32 (i32.reinterpret_f32 (f32.mul (f32.const -nan) (f32.const nan:0x200001)))) (i32.const 0xffc00000))\n'         # two NaNs: the first operand's,
+            '(call $eq (call $p64 (i64.reinterpret_f64 (f64.add (f64.const nan:0x4000000000001) (f64.const -nan)))) (i64.const 0x7ffc000000000001))\n'   # for the commutative operations too
             '(call $eq (call $p32 (i32.trunc_sat_f64_s (f64.const -1e300))) (i32.const 0x80000000))\n'
             '(call $eq (call $p64 (i64.trunc_f32_u (f32.const 0x1p63))) (i64.const 0x8000000000000000))\n'
             '(call $eq (call $p32 (i32.reinterpret_f32 (f32.demote_f64 (f64.const 16777217)))) (i32.const 0x4b800000))\n'
@@ -636,7 +638,7 @@ def test_floating_point_and_globals_front_end(pr):
             '(global.set $g (i64.add (global.get $g) (i64.extend_i32_u (global.get $c))))\n(call $eq (call $p64 (global.get $g)) (i64.const 6))\n')
     for spelling in (head + body + tail, U.wat_to_wasm(head + body + tail), U.wat_to_plain(head + body + tail)):
         _, _, _, _, st = pr.wat_emit(spelling, 64)
-        assert st["violated_constraints"] == 0 and st["asserts"] == 10 and st["private_consts"] == 10
+        assert st["violated_constraints"] == 0 and st["asserts"] == 12 and st["private_consts"] == 12
     for bad, why in (("(drop (i32.trunc_f32_s (f32.const 3e9)))", "integer overflow"),
                      ("(drop (i64.trunc_f64_u (f64.const -1)))", "integer overflow"),
                      ("(drop (i32.trunc_f64_u (f64.const nan)))", "integer overflow"),

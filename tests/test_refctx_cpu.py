@@ -577,6 +577,41 @@ def test_wat_emitter_on_every_family_interleaved_against_the_reference(oracle, p
         _emitter_equals_reference_rows(pr, spelling, st)
 
 
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("seed", range(6))
+def test_wat_emitter_against_the_reference_interpreter_on_mixed_programs(oracle, pr, seed):
+    """differential: witness stores / loads / bulk memory operations shuffled between floating-point statements, globals and float
+    memory traffic in one function (tests/refctx_util.py: rand_mixed_program), text and binary"""
+    import random
+    rng = random.Random(5500 + seed)
+    text = U.rand_mixed_program(rng, nmem=rng.randrange(6, 14), nfloat=rng.randrange(4, 10))
+    raw = U.run_reference_on_wat(text, 256, seed_byte=seed + 1)
+    assert raw["valid"] == [1, 1, 1] and raw["verifier"] == [1] * 7
+    st = _reference_rows(raw)
+    _emitter_equals_reference_rows(pr, text, st)
+    _emitter_equals_reference_rows(pr, U.wat_to_wasm(text), st)
+
+
+@pytest.mark.skipif(not os.path.exists(U.REF_BIN_CPU), reason="oracle/_ref/refctx_cpu not built (needs /root/reference at build time)")
+def test_wat_emitter_nan_propagation_against_the_reference(oracle, pr):
+    """two NaN operands of different sign and payload through add / sub / mul / div in both widths and both orders: SSE returns
+    the first source of the instruction, and which C++ operand that is, is the compiler's choice for the commutative ones --
+    the reference's handlers (GCC 13, -O1 and -O3 alike) return the first operand's; the emitter says so explicitly (a mixed
+    random program found that, left to the compiler, it returned the second's for add and mul)"""
+    stmts = []
+    for w, t, pay in ((32, "f32", "0x200001"), (64, "f64", "0x4000000000001")):
+        for op in ("add", "sub", "mul", "div"):
+            for x, y in (("-nan", "nan:" + pay), ("nan:" + pay, "-nan")):
+                stmts.append("(drop (call $i%d_private_const (i%d.reinterpret_%s (%s.%s (%s.const %s) (%s.const %s)))))" % (w, w, t, t, op, t, x, t, y))
+    head = U.WAT_HEAD_BOTH[:U.WAT_HEAD_BOTH.index("(func $t")]
+    text = head + "(func $t\n" + "\n".join(stmts) + "\n" + U.WAT_TAIL
+    raw = U.run_reference_on_wat(text, 256, seed_byte=11)
+    assert raw["valid"] == [1, 1, 1]
+    st = _reference_rows(raw)
+    _emitter_equals_reference_rows(pr, text, st)
+    _emitter_equals_reference_rows(pr, U.wat_to_wasm(text), st)
+
+
 REFERENCE_INTEGER_PROGRAMS = [w + "_" + op for w in ("i32", "i64") for op in (
     "add and clz ctz div_s div_u eq eqz ge_s ge_u gt_s gt_u le_s le_u lt_s lt_u mul ne or popcnt rem_s rem_u rotl rotr shl shr_s shr_u sub xor").split()] + [
     "i32_extend", "i32_wrap_i64", "i64_extend8_s", "i64_extend16_s", "i64_extend32_s", "i64_extend_i32_s", "i64_extend_i32_u"]
